@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py — the driver contract.
+
+A "step" is one pass of hot path (i) over one batch: the fused on-device negative sampler + triple scoring
+forward/backward kernel + the row optimiser on both tables (what one session.run([loss, optimizer]) of
+models/basic_model.py:224-230 does in the reference).  Default workload = BASELINE.json configs[1]
+(BootEA on the D_W_15K_V1 shape, dim 100, batch 5000, 10 ε-truncated negatives), synthetic KG of that shape.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload bootea_15k|bootea_100k]
+
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[1]; args from the reference's run/args/bootea_args_15K.json
+    "bootea_15k": dict(shape="15K", dim=100, batch=5000, k=10, eps=0.9, lr=0.01, margin=0.01, neg_margin=2.0,
+                       balance=0.2, name="BootEA D_W_15K_V1 shape (synthetic), dim=100, batch=5000, 10 eps-truncated negatives"),
+    # the shape the north-star target is quoted on; args from bootea_args_100K.json
+    "bootea_100k": dict(shape="100K", dim=100, batch=20000, k=10, eps=0.98, lr=0.01, margin=0.01, neg_margin=2.0,
+                        balance=0.2, name="BootEA D_W_100K_V1 shape (synthetic), dim=100, batch=20000, 10 eps-truncated negatives"),
+}
+L2_FLUSH_BYTES = 512 << 20
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def __enter__(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(names, r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_workload(wl, rank, device):
+    """Synthetic KG of the workload's shape, resident on the device, plus tables and the trainer."""
+    import torch
+    from openea_b200 import engine as eng
+    from openea_b200.synth import synth_id_arrays
+    cfg = WORKLOADS[wl]
+    arr = synth_id_arrays(cfg["shape"], seed=20200901)
+    g = torch.Generator(device="cpu").manual_seed(1234 + rank)
+    d = cfg["dim"]
+    # init='normal': truncated normal σ = 1/√d (initializers.py:29-34); plain clamp-resampled normal here
+    ent0 = torch.nn.init.trunc_normal_(torch.empty(arr["n_ent"], d), std=d ** -0.5, a=-2 * d ** -0.5, b=2 * d ** -0.5, generator=g)
+    rel0 = torch.nn.init.trunc_normal_(torch.empty(arr["n_rel"], d), std=d ** -0.5, a=-2 * d ** -0.5, b=2 * d ** -0.5, generator=g)
+    ent = eng.EmbeddingTable(ent0, True, "Adagrad", device)
+    rel = eng.EmbeddingTable(rel0, True, "Adagrad", device)
+    kg1 = eng.DeviceKG(arr["triples1"], arr["entities1"], arr["n_ent"], device)
+    kg2 = eng.DeviceKG(arr["triples2"], arr["entities2"], arr["n_ent"], device)
+    # ε-truncated candidate lists: k_c = int((1-ε)·N_kg) ids per entity (basic_model.py:270-271).  For the
+    # benchmark the lists are random same-KG ids (the access pattern of the sampler does not depend on which).
+    for kg, ents in ((kg1, arr["entities1"]), (kg2, arr["entities2"])):
+        n_kg = len(ents)
+        n_cand = int((1 - cfg["eps"]) * n_kg)
+        idx = torch.randint(0, n_kg, (n_kg, n_cand), generator=g, dtype=torch.int32)
+        cand = torch.from_numpy(ents)[idx.long()].to(torch.int32).to(device)
+        kg.set_candidates(cand, ents)
+    tset = eng.DeviceTripleSet([kg1.triples, kg2.triples], arr["n_ent"], arr["n_rel"], device)
+    loss = eng.loss_cfg("limited", "L2", cfg["margin"], cfg["neg_margin"], cfg["balance"])
+    trainer = eng.TripleTrainer(ent, rel, loss, cfg["lr"])
+    T = kg1.triples.shape[0] + kg2.triples.shape[0]
+    steps_per_epoch = int(np.ceil(T / cfg["batch"]))
+    return dict(cfg=cfg, arr=arr, ent=ent, rel=rel, kg1=kg1, kg2=kg2, tset=tset, trainer=trainer,
+                steps_per_epoch=steps_per_epoch, n_triples=T)
+
+
+def decode_dbg(dbg, n, t1, t2, k):
+    """Host (pos, neg) [3, n] index arrays of the batch the fused kernel sampled (vectorised)."""
+    rows = dbg[:n]
+    tri = rows[:, 0].astype(np.int64)
+    q = (tri >> 30) & 1
+    idx = tri & ((1 << 30) - 1)
+    hrt = np.where(q[:, None] == 0, t1[np.minimum(idx, len(t1) - 1)], t2[np.minimum(idx, len(t2) - 1)])
+    pos = np.ascontiguousarray(hrt.T.astype(np.int32))
+    mask = rows[:, 1].astype(np.int64)
+    e = rows[:, 2:2 + k].astype(np.int32)
+    head = ((mask[:, None] >> np.arange(k)[None, :]) & 1).astype(bool)
+    nh = np.where(head, e, hrt[:, 0:1]).reshape(-1)
+    nr = np.repeat(hrt[:, 1], k)
+    nt = np.where(head, hrt[:, 2:3], e).reshape(-1)
+    neg = np.ascontiguousarray(np.stack([nh, nr, nt]).astype(np.int32))
+    return pos, neg
+
+
+def cpu_reference_run(wl, steps, warmup, batches=None, budget_s=25.0):
+    """Times the CPU oracle port of the TF step (dense normalise + dense grads + dense Adagrad) with all host
+    threads on a bounded sample of the workload's batches.  Returns (pos_triples_per_s, info)."""
+    from oracle import triple as orc
+    from openea_b200.synth import synth_id_arrays
+    cfg = WORKLOADS[wl]
+    arr = synth_id_arrays(cfg["shape"], seed=20200901)
+    rng = np.random.default_rng(4321)
+    d = cfg["dim"]
+    ent = (rng.standard_normal((arr["n_ent"], d)) / np.sqrt(d)).astype(np.float32)
+    rel = (rng.standard_normal((arr["n_rel"], d)) / np.sqrt(d)).astype(np.float32)
+    st = orc.DenseState(ent, rel, "Adagrad")
+    if batches is None:  # host-side uniform corruption, same batch geometry (used by --impl reference)
+        batches = []
+        tri = np.concatenate([arr["triples1"], arr["triples2"]])
+        for _ in range(4):
+            sel = rng.integers(0, len(tri), size=cfg["batch"])
+            pos = np.ascontiguousarray(tri[sel].T)
+            neg = np.repeat(pos, cfg["k"], axis=1)
+            side = rng.random(neg.shape[1]) < 0.5
+            par = neg[0] & 1
+            repl = (rng.integers(0, arr["n_ent"] // 2, size=neg.shape[1]) * 2 + par).astype(np.int32)
+            neg[0, side] = repl[side]; neg[2, ~side] = repl[~side]
+            batches.append((pos, np.ascontiguousarray(neg)))
+    kw = dict(margin=cfg["margin"], neg_margin=cfg["neg_margin"], balance=cfg["balance"])
+    for i in range(max(1, warmup)):
+        orc.step(st, *batches[i % len(batches)], "limited", "L2", True, True, cfg["lr"], **kw)
+    t0 = time.perf_counter()
+    done, n_pos = 0, 0
+    while done < steps:
+        pos, neg = batches[done % len(batches)]
+        orc.step(st, pos, neg, "limited", "L2", True, True, cfg["lr"], **kw)
+        n_pos += pos.shape[1]
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    info = dict(cores=orc.num_threads(), steps=done, seconds=dt,
+                sample="%d steps of %d positives + %d negatives (dense TF-style step, C/OpenMP port)" % (done, batches[0][0].shape[1], batches[0][1].shape[1]))
+    return n_pos / dt, info
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="bootea_15k", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cfg = WORKLOADS[args.workload]
+    unit = "positive triples/s"
+    config = {"workload": cfg["name"], "batch_size": cfg["batch"], "neg_per_pos": cfg["k"], "dim": cfg["dim"],
+              "sharding": "replicas" if world > 1 else "single", "l2": "flushed between timed steps (512 MiB write)"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        val, info = cpu_reference_run(args.workload, args.steps, args.warmup)
+        line = {"impl": "reference", "metric": "training triples/sec", "value": val, "unit": unit, "n_gpus": args.gpus,
+                "steps": info["steps"], "warmup": args.warmup, "ms_per_step": 1e3 * info["seconds"] / max(1, info["steps"]),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config,
+                "cpu_baseline": {"value": val, "unit": unit, "cores": info["cores"], "kind": "port", "sample": info["sample"]},
+                "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    W = build_workload(args.workload, rank, device)
+    tr, kg1, kg2, tset = W["trainer"], W["kg1"], W["kg2"], W["tset"]
+    B, k, d = cfg["batch"], cfg["k"], cfg["dim"]
+    spe = W["steps_per_epoch"]
+    flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device=device)
+    npos_dev = torch.zeros(1, dtype=torch.int32, device=device)
+
+    def one_step(i, ev=None):
+        # every rank walks the epoch from its own offset: per-GPU work is fixed (weak scaling)
+        step = (i + rank * 7) % max(1, spe - 1)
+        seed = 0xB007EA + 1000003 * ((i + rank * 7) // max(1, spe - 1)) + rank
+        if ev: ev[0].record()
+        tr.score_sampled(kg1, kg2, tset, B, k, step, seed, n_pos_out=npos_dev)
+        if ev: ev[1].record()
+        tr.apply()
+        if ev: ev[2].record()
+
+    for i in range(max(3, args.warmup)):
+        one_step(i)
+    torch.cuda.synchronize()
+    n_pos_step = int(npos_dev.item())
+    tr.read_loss()
+
+    # ---- device-timed region: EXACTLY K steps, CUDA events on the launching stream --------------------------
+    K = args.steps
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    with ClockSampler(local_rank) as clocks:
+        t_wall0 = time.perf_counter()
+        for i in range(K):
+            flush.fill_(float(i))   # L2 flush (not timed: outside the event pairs)
+            one_step(args.warmup + i, evs[i])
+        torch.cuda.synchronize()
+        t_wall = time.perf_counter() - t_wall0
+    if world > 1:
+        dist.barrier()
+    score_ms = np.array([e[0].elapsed_time(e[1]) for e in evs])
+    step_ms = np.array([e[0].elapsed_time(e[2]) for e in evs])
+    total_ms = float(step_ms.sum())
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    loss_val = tr.read_loss()
+    value = world * n_pos_step * K / (total_ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (k_score_sampled) ---------------------------------------------------
+    pk, pk_kind = peaks()
+    alg_bytes = 24.0 * d * (1 + k) * n_pos_step   # 24·d bytes per scored triple
+    score_med_ms = float(np.median(score_ms))
+    achieved = alg_bytes / (score_med_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic_%s.json" % args.workload)
+    if os.path.exists(tp):
+        with open(tp) as f:
+            traffic = json.load(f).get("k_score_sampled_dram_bytes_per_launch")
+    roofline = {"bound": "hbm", "kernel": "k_score_sampled", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "peak_kind": pk_kind + " (burst copy)",
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms_median": score_med_ms,
+                "kernel_share_of_step": float(score_ms.sum() / step_ms.sum())}
+
+    # ---- e2e: the session.run(feed_dict) boundary with HOST index buffers -------------------------------------
+    e2e = None
+    cpu_base = None
+    if True:
+        n_b = min(K, 8)
+        t1, t2 = W["arr"]["triples1"], W["arr"]["triples2"]
+        host_batches = []
+        dbg = torch.empty(B, 2 + k, dtype=torch.int32, device=device)
+        for i in range(n_b):
+            tr.score_sampled(kg1, kg2, tset, B, k, i % max(1, spe - 1), 0xE2E + i + rank, dbg=dbg, n_pos_out=npos_dev)
+            torch.cuda.synchronize()
+            pos, neg = decode_dbg(dbg.cpu().numpy(), int(npos_dev.item()), t1, t2, k)
+            host_batches.append((torch.from_numpy(pos).pin_memory(), torch.from_numpy(neg).pin_memory()))
+            tr.ent.grad.zero_(); tr.rel.grad.zero_(); tr.ent.touched.zero_(); tr.rel.touched.zero_()
+        tr.read_loss()
+        for i in range(3):
+            tr.step_fed_host(*host_batches[i % n_b])
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e2e_s = 0.0
+        for i in range(K):
+            flush.fill_(float(i)); torch.cuda.synchronize()
+            pos, neg = host_batches[i % n_b]
+            t0 = time.perf_counter()
+            tr.step_fed_host(pos, neg)          # H2D of 6 index vectors, score, optimiser, D2H loss, sync
+            e2e_s += time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([e2e_s], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        n_pos_h, n_neg_h = host_batches[0][0].shape[1], host_batches[0][1].shape[1]
+        e2e = {"value": world * n_pos_h * K / e2e_s, "unit": unit, "h2d_bytes_per_step": 12 * (n_pos_h + n_neg_h),
+               "d2h_bytes_per_step": 8, "ms_per_step": 1e3 * e2e_s / K,
+               "api": "oea_triple_step_fed_host (host index buffers, tables resident, synchronous)"}
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            np_batches = [(p.numpy(), n.numpy()) for p, n in host_batches]
+            val, info = cpu_reference_run(args.workload, 1000, 2, batches=np_batches, budget_s=12.0)
+            cpu_base = {"value": val, "unit": unit, "cores": info["cores"], "kind": "port", "sample": info["sample"]}
+
+    if rank == 0:
+        line = {"metric": "training triples/sec", "value": value, "unit": unit, "n_gpus": world, "steps": K,
+                "warmup": max(3, args.warmup), "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "scored_triples_per_s": value * (1 + k), "positives_per_step": n_pos_step,
+                "gpu_launches": 3 * K, "kernels": ["k_score_sampled", "k_rowopt(ent)", "k_rowopt(rel)"],
+                "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_base, "clocks": clocks.summary(),
+                "wall_s_timed_region": t_wall, "last_loss_sum": loss_val}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

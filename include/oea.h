@@ -1,0 +1,174 @@
+/*
+ * oea.h — C-ABI of liboea.so, the B200 (sm_100a) engine behind the OpenEA hot path.
+ *
+ * The reference (nju-websoft/OpenEA) has NO native / FFI layer: its "operator API" is a set of
+ * Python callables that bottom out in TensorFlow-1 session.run() and NumPy.  Each entry point
+ * below names the reference callable(s) it replaces (file:line under /root/reference/src/openea).
+ *
+ * Conventions (all entry points):
+ *   - extern "C", plain pointers and sizes, no C++/torch types.
+ *   - return int: 0 = OEA_OK, >0 = argument error (OEA_ERR_*), <0 = -(cudaError_t).
+ *   - device pointers unless the name ends in _host; `stream` is a cudaStream_t passed as void*.
+ *   - never allocate or free device memory; the caller owns every buffer (incl. workspaces).
+ *   - asynchronous on `stream` unless documented otherwise (the *_host entry points synchronise,
+ *     mirroring the synchronous session.run() they replace).
+ *   - no CUDA context is created at load time (safe to dlopen in forked workers).
+ */
+#ifndef OEA_H_
+#define OEA_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OEA_ABI_VERSION 1
+
+enum {
+    OEA_OK = 0,
+    OEA_ERR_NULL = 1,        /* required pointer is NULL */
+    OEA_ERR_DIM = 2,         /* dim/pitch/rows out of the supported range */
+    OEA_ERR_ALIGN = 3,       /* pointer or pitch not 16-byte aligned */
+    OEA_ERR_KIND = 4,        /* unknown score / loss / optimiser / metric kind */
+    OEA_ERR_SHAPE = 5,       /* inconsistent batch sizes (e.g. margin loss needs n_neg == n_pos) */
+    OEA_ERR_RANGE = 6,       /* k, n_cand, … out of range */
+    OEA_ERR_WORKSPACE = 7    /* workspace too small */
+};
+
+/* ---- score / loss / optimiser kinds -------------------------------------------------------- */
+/* modules/base/losses.py:15-73: `loss_norm == 'L1'` → Σ|h+r−t| ; anything else → Σ(h+r−t)² (squared) */
+enum { OEA_SCORE_L1 = 0, OEA_SCORE_L2SQ = 1 };
+/* losses.py margin_loss:15, limited_loss:42, logistic_loss:59, positive_loss:30;
+ * approaches/bootea.py:197 alignment loss  −Σ log σ(−s)  (OEA_LOSS_LOGSIGMOID, positives only) */
+enum { OEA_LOSS_MARGIN = 0, OEA_LOSS_LIMITED = 1, OEA_LOSS_LOGISTIC = 2, OEA_LOSS_POSITIVE = 3,
+       OEA_LOSS_LOGSIGMOID = 4 };
+/* modules/base/optimizers.py:10-20 (TF1 semantics: Adagrad acc0 = 0.1 and no epsilon; TF-Adam) */
+enum { OEA_OPT_SGD = 0, OEA_OPT_ADAGRAD = 1, OEA_OPT_ADAM = 2 };
+
+/* An embedding table as TF holds it: the raw variable + optimiser slots (+ our gradient scratch).
+ * Replaces the tf.Variable made by modules/base/initializers.py:9-50; `l2_norm` mirrors the
+ * `is_l2_norm` flag: every lookup goes through x·rsqrt(max(Σx², 1e-12)) and the gradient flows
+ * back through that normalisation (initializers.py:26,34,41,50).
+ * Layout: row-major [rows, pitch] fp32, pitch % 4 == 0, pitch >= dim, padding columns are zero.
+ * `grad` must be all-zero and `touched` all-zero between steps (oea_rowopt_apply restores that). */
+typedef struct oea_table {
+    float*   weight;   /* [rows, pitch] raw variable (NOT normalised) */
+    float*   grad;     /* [rows, pitch] gradient accumulator */
+    float*   state1;   /* [rows, pitch] Adagrad accumulator / Adam m (NULL for SGD) */
+    float*   state2;   /* [rows, pitch] Adam v (NULL otherwise) */
+    int32_t* touched;  /* [rows] 0/1 flags: row received gradient this step */
+    int32_t  rows;
+    int32_t  dim;
+    int32_t  pitch;
+    int32_t  l2_norm;
+} oea_table;
+
+typedef struct oea_loss_cfg {
+    int32_t score_kind;   /* OEA_SCORE_* */
+    int32_t loss_kind;    /* OEA_LOSS_* */
+    float   margin;       /* margin (margin-based) or pos_margin (limited) */
+    float   neg_margin;   /* limited */
+    float   balance;      /* limited: weight of the negative part (aligne.py:63-65) */
+} oea_loss_cfg;
+
+typedef struct oea_opt_cfg {
+    int32_t kind;         /* OEA_OPT_* */
+    float   lr;
+    float   beta1, beta2, eps;  /* Adam only (TF defaults .9 / .999 / 1e-8) */
+    int32_t t;            /* Adam only: 1-based step count */
+} oea_opt_cfg;
+
+/* One KG's share of the training data for the fused on-device sampler.
+ * Replaces the Python lists handed to modules/train/batch.py:36-45. */
+typedef struct oea_kg_view {
+    const int32_t* triples;   /* [n_triples, 3] (h, r, t) */
+    int32_t        n_triples;
+    const int32_t* entities;  /* [n_entities] entity ids of this KG (uniform candidate list) */
+    int32_t        n_entities;
+    const int32_t* cand;      /* [cand_rows, n_cand] ε-truncated neighbour lists, or NULL */
+    const int32_t* ent2row;   /* [ent table rows] entity id → row of `cand`, −1 = no list; NULL iff cand NULL */
+    int32_t        n_cand;
+} oea_kg_view;
+
+/* Open-addressing set of packed (h, r, t) keys (triple membership test of batch.py:104-109). */
+typedef struct oea_tripleset {
+    const uint64_t* slots;    /* [capacity], empty = 0xFFFFFFFFFFFFFFFF */
+    uint32_t        capacity; /* power of two */
+    uint32_t        ent_bits; /* key = (h << (ent_bits + rel_bits)) | (r << ent_bits) | t */
+    uint32_t        rel_bits;
+} oea_tripleset;
+
+typedef struct oea_sample_cfg {
+    int32_t  batch_size;      /* args.batch_size: positives per step over both KGs */
+    int32_t  neg_per_pos;     /* args.neg_triple_num (1..32) */
+    int32_t  step;            /* step index inside the epoch */
+    int32_t  max_try;         /* batch.py:89 max_try (10) */
+    uint64_t epoch_seed;      /* permutation + sampling seed of this epoch */
+} oea_sample_cfg;
+
+/* ---- misc ---------------------------------------------------------------------------------- */
+int         oea_abi_version(void);
+const char* oea_error_string(int code);
+
+/* ---- path (i): negative-sampled triple scoring, forward + backward ------------------------- */
+
+/* Fed step, forward+backward only.  Replaces the graph of models/basic_model.py:80-98 /
+ * approaches/aligne.py:47-66 / approaches/mtranse.py:46-57 / approaches/bootea.py:190-199 up to
+ * compute_gradients: gathers rows, scores, evaluates the loss of modules/base/losses.py and
+ * scatter-adds d(loss)/d(raw variable) into ent->grad / rel->grad (setting `touched`).
+ * n_neg may be 0 (positive / logsigmoid losses).  *loss_out (device, fp64) is incremented by the
+ * batch loss (sum over the batch, as TF's reduce_sum). */
+int oea_triple_score_fed(const oea_table* ent, const oea_table* rel,
+                         const int32_t* pos_h, const int32_t* pos_r, const int32_t* pos_t, int32_t n_pos,
+                         const int32_t* neg_h, const int32_t* neg_r, const int32_t* neg_t, int32_t n_neg,
+                         const oea_loss_cfg* loss, double* loss_out, void* stream);
+
+/* Optimiser step on a table whose `grad` was filled by a score call.  Replaces
+ * optimizer.apply_gradients of modules/base/optimizers.py:4-7.  Adagrad / SGD touch only flagged
+ * rows (identical to TF's dense update because untouched rows have g = 0); Adam is dense.
+ * Leaves grad = 0 and touched = 0. */
+int oea_rowopt_apply(const oea_table* table, const oea_opt_cfg* opt, void* stream);
+
+/* Fused on-device step: batch slicing + negative sampling of modules/train/batch.py:36-119 and the
+ * forward/backward above in ONE kernel (no index buffers).  Positive p of step s is
+ * triples[perm_epoch(s·B_kg + p)] with B_1 = ⌊B·T1/(T1+T2)⌋, B_2 = B − B_1 (batch.py:39-42);
+ * negatives corrupt head or tail (one Bernoulli(.5) per try for all missing negatives),
+ * candidates = ε-truncated list of the corrupted entity or the KG's entity list, sampled without
+ * replacement inside a try, rejected when in `tset`, last try accepts unfiltered (batch.py:89-119).
+ * Only OEA_LOSS_LIMITED / OEA_LOSS_LOGISTIC are valid here.
+ * dbg_neg: optional [batch_size, 2 + neg_per_pos] int32 dump (triple index, side bitmask, sampled
+ * entities) so a test can replay the identical batch through the fed path / the oracle.
+ * n_pos_out (device int32, optional) receives the number of positives actually in this step. */
+int oea_triple_score_sampled(const oea_table* ent, const oea_table* rel,
+                             const oea_kg_view* kg1, const oea_kg_view* kg2, const oea_tripleset* tset,
+                             const oea_sample_cfg* smp, const oea_loss_cfg* loss,
+                             double* loss_out, int32_t* n_pos_out, int32_t* dbg_neg, void* stream);
+
+/* Reference-facing synchronous step with HOST index buffers (the session.run(feed_dict) boundary of
+ * models/basic_model.py:222-232): H2D copy of the six index vectors into `dev_idx_ws`
+ * (>= 3·(n_pos+n_neg) int32), score, optimiser step on both tables, D2H of the batch loss,
+ * stream synchronise.  Returns the batch loss in *loss_host. */
+int oea_triple_step_fed_host(const oea_table* ent, const oea_table* rel,
+                             const int32_t* pos_hrt_host, int32_t n_pos,   /* [3, n_pos] h|r|t */
+                             const int32_t* neg_hrt_host, int32_t n_neg,   /* [3, n_neg] */
+                             const oea_loss_cfg* loss, const oea_opt_cfg* opt,
+                             int32_t* dev_idx_ws, double* dev_loss_ws, double* loss_pinned_host,
+                             float* loss_host, void* stream);
+
+/* Normalised view of a table (what TF returns for `ent_embeds` when is_l2_norm):
+ * out[i, :dim] = normalise(weight[ids[i]]) (ids == NULL → all rows).  Replaces
+ * tf.nn.embedding_lookup(self.ent_embeds, ids).eval() of basic_model.py:106-121,185,198-204. */
+int oea_table_lookup(const oea_table* table, const int32_t* ids, int32_t n, float* out, int32_t out_pitch,
+                     void* stream);
+
+/* Build the triple membership set on device: slots[capacity] (capacity = power of two, >= 2·n) is
+ * reset to empty and filled with the packed keys of triples [n,3].  Replaces the Python
+ * `relation_triples_set` handed to batch.py:36 (modules/load/kg.py:63). */
+int oea_tripleset_build(const int32_t* triples, int32_t n, uint64_t* slots, uint32_t capacity,
+                        uint32_t ent_bits, uint32_t rel_bits, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OEA_H_ */

@@ -1,0 +1,134 @@
+// oea_common.cuh — device helpers shared by the liboea kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/oea.h"
+
+#define OEA_WARP 32
+#define OEA_FULL 0xffffffffu
+
+#define OEA_CUDA_TRY(expr)                                   \
+    do {                                                     \
+        cudaError_t _e = (expr);                             \
+        if (_e != cudaSuccess) return -(int)_e;              \
+    } while (0)
+
+#define OEA_LAUNCH_CHECK()                                   \
+    do {                                                     \
+        cudaError_t _e = cudaPeekAtLastError();              \
+        if (_e != cudaSuccess) { cudaGetLastError(); return -(int)_e; } \
+    } while (0)
+
+namespace oea {
+
+__host__ __device__ __forceinline__ bool aligned16(const void* p) {
+    return (reinterpret_cast<uintptr_t>(p) & 15u) == 0;
+}
+
+// ---- float4 arithmetic -------------------------------------------------------------------------
+__device__ __forceinline__ float4 f4(float a) { return make_float4(a, a, a, a); }
+__device__ __forceinline__ float4 operator+(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 operator-(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+__device__ __forceinline__ float4 operator*(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+__device__ __forceinline__ float4 neg(float4 a) { return make_float4(-a.x, -a.y, -a.z, -a.w); }
+__device__ __forceinline__ float dot4(float4 a, float4 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w))); }
+__device__ __forceinline__ float4 fma4(float4 a, float s, float4 c) { return make_float4(fmaf(a.x, s, c.x), fmaf(a.y, s, c.y), fmaf(a.z, s, c.z), fmaf(a.w, s, c.w)); }
+__device__ __forceinline__ float sgn(float x) { return (float)(x > 0.f) - (float)(x < 0.f); }  // TF sign(0) = 0
+__device__ __forceinline__ float4 sgn4(float4 a) { return make_float4(sgn(a.x), sgn(a.y), sgn(a.z), sgn(a.w)); }
+__device__ __forceinline__ float abs_sum4(float4 a) { return fabsf(a.x) + fabsf(a.y) + fabsf(a.z) + fabsf(a.w); }
+
+// ---- memory ------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// 128-bit vector reduction to global memory (sm_90+: red.global.add.v4.f32), no return value.
+__device__ __forceinline__ void red_add4(float* p, float4 v) {
+    asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// ---- warp reductions ---------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(OEA_FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ void warp_sum2(float& a, float& b) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(OEA_FULL, a, o);
+        b += __shfl_xor_sync(OEA_FULL, b, o);
+    }
+}
+__device__ __forceinline__ void warp_sum3(float& a, float& b, float& c) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(OEA_FULL, a, o);
+        b += __shfl_xor_sync(OEA_FULL, b, o);
+        c += __shfl_xor_sync(OEA_FULL, c, o);
+    }
+}
+
+// ---- hashing / counter RNG ---------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {  // splitmix64 finaliser
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {  // lowbias32
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+// Unbiased-enough bounded draw: high 32 bits of a 64-bit hash, multiply-shift into [0, n).
+__host__ __device__ __forceinline__ uint32_t bounded(uint64_t r, uint32_t n) {
+    return (uint32_t)(((r >> 32) * (uint64_t)n) >> 32);
+}
+
+// Pseudo-random permutation of [0, n) by a 4-round balanced Feistel network + cycle walking.
+// Replaces random.shuffle(triples_list) of models/basic_model.py:234-235: a bijection per epoch key.
+__host__ __device__ __forceinline__ uint32_t feistel_perm(uint32_t i, uint32_t n, uint64_t key) {
+    if (n <= 1) return 0;
+    uint32_t bits = 32 - (uint32_t)
+#ifdef __CUDA_ARCH__
+        __clz(n - 1);
+#else
+        __builtin_clz(n - 1);
+#endif
+    uint32_t hb = (bits + 1) >> 1;
+    if (hb == 0) hb = 1;
+    const uint32_t hmask = (1u << hb) - 1u;
+    uint32_t x = i;
+    do {
+        uint32_t l = x >> hb, r = x & hmask;
+#pragma unroll
+        for (int round = 0; round < 4; ++round) {
+            uint32_t f = mix32(r ^ (uint32_t)(key >> (16 * round)) ^ (0x9E3779B9u * (round + 1))) & hmask;
+            uint32_t nl = r;
+            r = l ^ f;
+            l = nl;
+        }
+        x = (l << hb) | r;
+    } while (x >= n);
+    return x;
+}
+
+// ---- triple membership set ---------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint64_t triple_key(uint32_t h, uint32_t r, uint32_t t, uint32_t ent_bits, uint32_t rel_bits) {
+    return ((uint64_t)h << (ent_bits + rel_bits)) | ((uint64_t)r << ent_bits) | (uint64_t)t;
+}
+__device__ __forceinline__ bool tset_contains(const oea_tripleset& s, uint64_t key) {
+    const uint32_t mask = s.capacity - 1u;
+    uint32_t slot = (uint32_t)mix64(key) & mask;
+    while (true) {
+        uint64_t v = __ldg(s.slots + slot);
+        if (v == key) return true;
+        if (v == 0xFFFFFFFFFFFFFFFFull) return false;
+        slot = (slot + 1u) & mask;
+    }
+}
+
+// softplus(x) = log(1 + e^x), overflow-safe (losses.py:70-71 use the naive form; identical in range)
+__device__ __forceinline__ float softplus(float x) { return fmaxf(x, 0.f) + log1pf(__expf(-fabsf(x))); }
+__device__ __forceinline__ float sigmoidf(float x) { return 1.f / (1.f + __expf(-x)); }
+
+}  // namespace oea

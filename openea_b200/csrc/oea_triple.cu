@@ -1,0 +1,744 @@
+// oea_triple.cu — path (i): negative-sampled triple scoring forward+backward (K1), the row
+// optimiser, the fused on-device sampler, and the table lookup.  sm_100a.
+//
+// Maths restated from the reference (no code shared):
+//   modules/base/losses.py:15-73      score + losses (sums, squared L2)
+//   modules/base/initializers.py:26   l2_normalize wrapper around every lookup
+//   modules/base/optimizers.py:10-20  TF1 Adagrad / Adam / SGD
+//   modules/train/batch.py:36-119     batch slicing + corrupt-head/tail negative sampling
+//   approaches/bootea.py:197          alignment loss
+//
+// Work decomposition: one warp per triple (fed path) or per positive + its k negatives (sampled
+// path).  A row of `dim` floats is held as VEC float4 per lane (dim <= 128·VEC), loaded with
+// 128-bit coalesced reads; row reductions are warp shuffles; gradients leave through 128-bit
+// vector reductions (red.global.add.v4.f32) into the L2-resident gradient table.
+#include "oea_common.cuh"
+
+namespace oea {
+
+constexpr int kWarpsPerBlock = 8;
+constexpr int kThreads = kWarpsPerBlock * OEA_WARP;
+constexpr float kNormEps = 1e-12f;  // tf.nn.l2_normalize epsilon
+
+template <int VEC>
+struct Row {
+    float4 v[VEC];
+};
+
+template <int VEC>
+__device__ __forceinline__ Row<VEC> load_row(const float* __restrict__ base, int row, int pitch, int lane) {
+    Row<VEC> r;
+    const float* p = base + (size_t)row * pitch;
+    const int p4 = pitch >> 2;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        const int c = lane + i * OEA_WARP;
+        r.v[i] = (c < p4) ? ldg4(p + 4 * c) : f4(0.f);
+    }
+    return r;
+}
+
+template <int VEC>
+__device__ __forceinline__ void red_row(float* __restrict__ base, int row, int pitch, int lane, const Row<VEC>& g) {
+    float* p = base + (size_t)row * pitch;
+    const int p4 = pitch >> 2;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        const int c = lane + i * OEA_WARP;
+        if (c < p4) red_add4(p + 4 * c, g.v[i]);
+    }
+}
+
+template <int VEC>
+__device__ __forceinline__ float sumsq(const Row<VEC>& a) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) s += dot4(a.v[i], a.v[i]);
+    return s;
+}
+template <int VEC>
+__device__ __forceinline__ float dotr(const Row<VEC>& a, const Row<VEC>& b) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) s += dot4(a.v[i], b.v[i]);
+    return s;
+}
+
+// inverse norm as tf.nn.l2_normalize: rsqrt(max(Σx², 1e-12)); 1 when the table is not normalised.
+__device__ __forceinline__ float inv_norm(float ss, bool on) { return on ? rsqrtf(fmaxf(ss, kNormEps)) : 1.f; }
+
+// Gradient w.r.t. the raw row given the gradient w.r.t. the normalised row (ghat), the normalised
+// row xhat, <xhat, ghat> (dot) and 1/||x||.  When Σx² < eps TF's max() picks eps and the Jacobian
+// is just the scale.
+template <int VEC>
+__device__ __forceinline__ Row<VEC> through_norm(const Row<VEC>& ghat, const Row<VEC>& xhat, float dot, float inv,
+                                                 float ss, bool on) {
+    Row<VEC> g;
+    const float proj = (on && ss >= kNormEps) ? dot : 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) g.v[i] = fma4(xhat.v[i], -proj, ghat.v[i]) * inv;
+    return g;
+}
+
+template <int SCORE, int VEC>
+__device__ __forceinline__ float score_partial(const Row<VEC>& u) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) s += (SCORE == OEA_SCORE_L1) ? abs_sum4(u.v[i]) : dot4(u.v[i], u.v[i]);
+    return s;
+}
+// d score / d u
+template <int SCORE, int VEC>
+__device__ __forceinline__ Row<VEC> score_dir(const Row<VEC>& u) {
+    Row<VEC> d;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) d.v[i] = (SCORE == OEA_SCORE_L1) ? sgn4(u.v[i]) : u.v[i] * 2.f;
+    return d;
+}
+
+// Per-triple loss value and d(loss)/d(score).  TF conventions: relu'(0) = 0.
+__device__ __forceinline__ void loss_of(int loss_kind, bool is_neg, float s, const oea_loss_cfg& c, float& L, float& g) {
+    switch (loss_kind) {
+        case OEA_LOSS_LIMITED:
+            if (!is_neg) { L = fmaxf(s - c.margin, 0.f); g = (s > c.margin) ? 1.f : 0.f; }
+            else { L = c.balance * fmaxf(c.neg_margin - s, 0.f); g = (s < c.neg_margin) ? -c.balance : 0.f; }
+            break;
+        case OEA_LOSS_LOGISTIC:
+            if (!is_neg) { L = softplus(s); g = 1.f / (1.f + expf(-s)); }
+            else { L = softplus(-s); g = -1.f / (1.f + expf(s)); }
+            break;
+        case OEA_LOSS_LOGSIGMOID:  // −log σ(−s) = softplus(s)
+            L = softplus(s); g = 1.f / (1.f + expf(-s));
+            break;
+        default:  // OEA_LOSS_POSITIVE
+            L = s; g = 1.f;
+            break;
+    }
+}
+
+// Block-level loss accumulation: per-warp partials → one fp64 atomic per block.
+struct LossAcc {
+    double* smem;  // [kWarpsPerBlock]
+    __device__ __forceinline__ void flush(float warp_loss, double* out) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        if (lane == 0) smem[warp] = (double)warp_loss;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+#pragma unroll
+            for (int i = 0; i < kWarpsPerBlock; ++i) t += smem[i];
+            if (t != 0.0) atomicAdd(out, t);
+        }
+    }
+};
+
+struct TableDev {
+    const float* w;
+    float* g;
+    int32_t* touched;
+    int pitch;
+    bool norm;
+};
+
+__host__ inline TableDev table_dev(const oea_table* t) {
+    TableDev d;
+    d.w = t->weight; d.g = t->grad; d.touched = t->touched; d.pitch = t->pitch; d.norm = t->l2_norm != 0;
+    return d;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fed path, independent losses (limited / logistic / positive / logsigmoid): one warp per triple.
+// ------------------------------------------------------------------------------------------------
+template <int SCORE, int VEC>
+__global__ void __launch_bounds__(kThreads)
+k_score_fed(TableDev ent, TableDev rel,
+            const int32_t* __restrict__ ph, const int32_t* __restrict__ pr, const int32_t* __restrict__ pt, int n_pos,
+            const int32_t* __restrict__ nh, const int32_t* __restrict__ nr, const int32_t* __restrict__ nt, int n_neg,
+            oea_loss_cfg cfg, double* __restrict__ loss_out) {
+    __shared__ double s_loss[kWarpsPerBlock];
+    const int lane = threadIdx.x & 31;
+    const int warp_global = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int n_warps = gridDim.x * kWarpsPerBlock;
+    const int total = n_pos + n_neg;
+    float warp_loss = 0.f;
+
+    for (int i = warp_global; i < total; i += n_warps) {
+        const bool is_neg = i >= n_pos;
+        const int j = is_neg ? i - n_pos : i;
+        const int h = is_neg ? __ldg(nh + j) : __ldg(ph + j);
+        const int r = is_neg ? __ldg(nr + j) : __ldg(pr + j);
+        const int t = is_neg ? __ldg(nt + j) : __ldg(pt + j);
+        Row<VEC> xh = load_row<VEC>(ent.w, h, ent.pitch, lane);
+        Row<VEC> xr = load_row<VEC>(rel.w, r, rel.pitch, lane);
+        Row<VEC> xt = load_row<VEC>(ent.w, t, ent.pitch, lane);
+        float ssh = sumsq(xh), ssr = sumsq(xr), sst = sumsq(xt);
+        warp_sum3(ssh, ssr, sst);
+        const float ih = inv_norm(ssh, ent.norm), ir = inv_norm(ssr, rel.norm), it = inv_norm(sst, ent.norm);
+        Row<VEC> u;
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) {
+            xh.v[c] = xh.v[c] * ih; xr.v[c] = xr.v[c] * ir; xt.v[c] = xt.v[c] * it;
+            u.v[c] = xh.v[c] + xr.v[c] - xt.v[c];
+        }
+        const float s = warp_sum(score_partial<SCORE, VEC>(u));
+        float L, g;
+        loss_of(cfg.loss_kind, is_neg, s, cfg, L, g);
+        warp_loss += L;
+        if (g != 0.f) {
+            Row<VEC> du = score_dir<SCORE, VEC>(u);
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) du.v[c] = du.v[c] * g;
+            float dh = dotr(xh, du), dr = dotr(xr, du), dt = dotr(xt, du);
+            warp_sum3(dh, dr, dt);
+            Row<VEC> gh = through_norm(du, xh, dh, ih, ssh, ent.norm);
+            Row<VEC> gr = through_norm(du, xr, dr, ir, ssr, rel.norm);
+            Row<VEC> gt = through_norm(du, xt, dt, it, sst, ent.norm);
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) gt.v[c] = neg(gt.v[c]);
+            red_row<VEC>(ent.g, h, ent.pitch, lane, gh);
+            red_row<VEC>(rel.g, r, rel.pitch, lane, gr);
+            red_row<VEC>(ent.g, t, ent.pitch, lane, gt);
+            if (lane == 0) { ent.touched[h] = 1; rel.touched[r] = 1; ent.touched[t] = 1; }
+        }
+    }
+    LossAcc acc{s_loss};
+    acc.flush(warp_loss, loss_out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fed path, margin-based loss Σ relu(m + s⁺_i − s⁻_i) (losses.py:15-27; k = 1): warp per pair.
+// ------------------------------------------------------------------------------------------------
+template <int SCORE, int VEC>
+__global__ void __launch_bounds__(kThreads)
+k_score_margin(TableDev ent, TableDev rel,
+               const int32_t* __restrict__ ph, const int32_t* __restrict__ pr, const int32_t* __restrict__ pt,
+               const int32_t* __restrict__ nh, const int32_t* __restrict__ nr, const int32_t* __restrict__ nt, int n,
+               oea_loss_cfg cfg, double* __restrict__ loss_out) {
+    __shared__ double s_loss[kWarpsPerBlock];
+    const int lane = threadIdx.x & 31;
+    const int warp_global = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int n_warps = gridDim.x * kWarpsPerBlock;
+    float warp_loss = 0.f;
+
+    for (int i = warp_global; i < n; i += n_warps) {
+        int idx[2][3] = {{__ldg(ph + i), __ldg(pr + i), __ldg(pt + i)}, {__ldg(nh + i), __ldg(nr + i), __ldg(nt + i)}};
+        Row<VEC> xh[2], xr[2], xt[2], u[2];
+        float ih[2], ir[2], it[2], ssh[2], ssr[2], sst[2], s[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            xh[q] = load_row<VEC>(ent.w, idx[q][0], ent.pitch, lane);
+            xr[q] = load_row<VEC>(rel.w, idx[q][1], rel.pitch, lane);
+            xt[q] = load_row<VEC>(ent.w, idx[q][2], ent.pitch, lane);
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            ssh[q] = sumsq(xh[q]); ssr[q] = sumsq(xr[q]); sst[q] = sumsq(xt[q]);
+            warp_sum3(ssh[q], ssr[q], sst[q]);
+            ih[q] = inv_norm(ssh[q], ent.norm); ir[q] = inv_norm(ssr[q], rel.norm); it[q] = inv_norm(sst[q], ent.norm);
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) {
+                xh[q].v[c] = xh[q].v[c] * ih[q]; xr[q].v[c] = xr[q].v[c] * ir[q]; xt[q].v[c] = xt[q].v[c] * it[q];
+                u[q].v[c] = xh[q].v[c] + xr[q].v[c] - xt[q].v[c];
+            }
+            s[q] = score_partial<SCORE, VEC>(u[q]);
+        }
+        warp_sum2(s[0], s[1]);
+        const float v = cfg.margin + s[0] - s[1];
+        warp_loss += fmaxf(v, 0.f);
+        if (v > 0.f) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const float g = q == 0 ? 1.f : -1.f;
+                Row<VEC> du = score_dir<SCORE, VEC>(u[q]);
+#pragma unroll
+                for (int c = 0; c < VEC; ++c) du.v[c] = du.v[c] * g;
+                float dh = dotr(xh[q], du), dr = dotr(xr[q], du), dt = dotr(xt[q], du);
+                warp_sum3(dh, dr, dt);
+                Row<VEC> gh = through_norm(du, xh[q], dh, ih[q], ssh[q], ent.norm);
+                Row<VEC> gr = through_norm(du, xr[q], dr, ir[q], ssr[q], rel.norm);
+                Row<VEC> gt = through_norm(du, xt[q], dt, it[q], sst[q], ent.norm);
+#pragma unroll
+                for (int c = 0; c < VEC; ++c) gt.v[c] = neg(gt.v[c]);
+                red_row<VEC>(ent.g, idx[q][0], ent.pitch, lane, gh);
+                red_row<VEC>(rel.g, idx[q][1], rel.pitch, lane, gr);
+                red_row<VEC>(ent.g, idx[q][2], ent.pitch, lane, gt);
+                if (lane == 0) { ent.touched[idx[q][0]] = 1; rel.touched[idx[q][1]] = 1; ent.touched[idx[q][2]] = 1; }
+            }
+        }
+    }
+    LossAcc acc{s_loss};
+    acc.flush(warp_loss, loss_out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused sampled step: warp per positive; samples its k negatives on device, loads 3 + k rows,
+// keeps the gradients of the three shared rows in registers, and issues 3 + k row reductions.
+// ------------------------------------------------------------------------------------------------
+struct SampledParams {
+    oea_kg_view kg[2];
+    oea_tripleset tset;
+    int n_slice[2];      // positives of this step taken from each KG
+    int start[2];        // offset of the slice inside the (permuted) triple list
+    int k;               // negatives per positive
+    int step;
+    int max_try;
+    uint64_t seed;
+};
+
+__device__ __forceinline__ uint64_t rng_draw(uint64_t seed, uint32_t step, uint32_t p, uint32_t a, uint32_t b) {
+    uint64_t x = mix64(seed ^ ((uint64_t)step << 40) ^ ((uint64_t)p << 8));
+    return mix64(x ^ ((uint64_t)a << 32) ^ (uint64_t)b);
+}
+
+template <int SCORE, int VEC>
+__global__ void __launch_bounds__(kThreads)
+k_score_sampled(TableDev ent, TableDev rel, SampledParams P, oea_loss_cfg cfg,
+                double* __restrict__ loss_out, int32_t* __restrict__ dbg) {
+    __shared__ double s_loss[kWarpsPerBlock];
+    const int lane = threadIdx.x & 31;
+    const int warp_global = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int n_warps = gridDim.x * kWarpsPerBlock;
+    const int n_pos = P.n_slice[0] + P.n_slice[1];
+    const int k = P.k;
+    float warp_loss = 0.f;
+
+    for (int p = warp_global; p < n_pos; p += n_warps) {
+        const int q = p < P.n_slice[0] ? 0 : 1;
+        const oea_kg_view& kg = P.kg[q];
+        const int local = q == 0 ? p : p - P.n_slice[0];
+        const uint32_t tri = feistel_perm((uint32_t)(P.start[q] + local), (uint32_t)kg.n_triples,
+                                          P.seed ^ (q ? 0xA5A5A5A5DEADBEEFull : 0x0123456789ABCDEFull));
+        int hrt = 0;
+        if (lane < 3) hrt = __ldg(kg.triples + 3 * (size_t)tri + lane);
+        const int h = __shfl_sync(OEA_FULL, hrt, 0);
+        const int r = __shfl_sync(OEA_FULL, hrt, 1);
+        const int t = __shfl_sync(OEA_FULL, hrt, 2);
+
+        // ---- negative sampling (batch.py:89-119), lane j < k owns negative j ----
+        bool need = lane < k;
+        int neg_e = 0;
+        bool neg_head = false;
+        for (int tr = 0; tr < P.max_try; ++tr) {
+            const unsigned missing = __ballot_sync(OEA_FULL, need);
+            if (missing == 0u) break;
+            const bool head = (rng_draw(P.seed, P.step, p, 0x51DEu, tr) >> 63) != 0;  // np.random.binomial(1, .5)
+            const int corrupted = head ? h : t;
+            const int32_t* list = kg.entities;
+            uint32_t C = (uint32_t)kg.n_entities;
+            if (kg.cand != nullptr) {
+                const int row = __ldg(kg.ent2row + corrupted);
+                if (row >= 0) { list = kg.cand + (size_t)row * kg.n_cand; C = (uint32_t)kg.n_cand; }
+            }
+            // random.sample(candidates, #missing): distinct positions among the needing lanes
+            uint32_t pos = 0;
+            bool unsettled = need;
+            for (uint32_t redraw = 0; ; ++redraw) {
+                if (unsettled) pos = bounded(rng_draw(P.seed, P.step, p, (tr << 8) | lane, 0xC0FFEEu + redraw), C);
+                const unsigned active = __ballot_sync(OEA_FULL, need);
+                unsigned same = 0u;
+                if (need) same = __match_any_sync(active, pos);
+                // the lowest lane of a duplicate group keeps its draw, the others redraw
+                unsettled = need && ((same & ((1u << lane) - 1u)) != 0u);
+                if (__ballot_sync(OEA_FULL, unsettled) == 0u) break;
+            }
+            if (need) {
+                const int e = __ldg(list + pos);
+                bool accept = tr == P.max_try - 1;
+                if (!accept) {
+                    const uint64_t key = head ? triple_key(e, r, t, P.tset.ent_bits, P.tset.rel_bits)
+                                              : triple_key(h, r, e, P.tset.ent_bits, P.tset.rel_bits);
+                    accept = !tset_contains(P.tset, key);
+                }
+                if (accept) { neg_e = e; neg_head = head; need = false; }
+            }
+        }
+        const unsigned head_mask = __ballot_sync(OEA_FULL, neg_head);
+        if (dbg != nullptr) {
+            int32_t* row = dbg + (size_t)p * (2 + k);
+            if (lane == 0) { row[0] = (int32_t)tri + (q ? (1 << 30) : 0); row[1] = (int32_t)head_mask; }
+            if (lane < k) row[2 + lane] = neg_e;
+        }
+
+        // ---- positive triple ----
+        Row<VEC> xh = load_row<VEC>(ent.w, h, ent.pitch, lane);
+        Row<VEC> xr = load_row<VEC>(rel.w, r, rel.pitch, lane);
+        Row<VEC> xt = load_row<VEC>(ent.w, t, ent.pitch, lane);
+        float ssh = sumsq(xh), ssr = sumsq(xr), sst = sumsq(xt);
+        warp_sum3(ssh, ssr, sst);
+        const float ih = inv_norm(ssh, ent.norm), ir = inv_norm(ssr, rel.norm), it = inv_norm(sst, ent.norm);
+        Row<VEC> hr, rt, u, Gh, Gr, Gt;  // hr = ĥ + r̂, rt = r̂ − t̂
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) {
+            xh.v[c] = xh.v[c] * ih; xr.v[c] = xr.v[c] * ir; xt.v[c] = xt.v[c] * it;
+            hr.v[c] = xh.v[c] + xr.v[c];
+            rt.v[c] = xr.v[c] - xt.v[c];
+            u.v[c] = hr.v[c] - xt.v[c];
+        }
+        const float sp = warp_sum(score_partial<SCORE, VEC>(u));
+        float L, g;
+        loss_of(cfg.loss_kind, false, sp, cfg, L, g);
+        warp_loss += L;
+        bool any_grad = g != 0.f;
+        {
+            Row<VEC> du = score_dir<SCORE, VEC>(u);
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) { Gh.v[c] = du.v[c] * g; Gr.v[c] = Gh.v[c]; Gt.v[c] = neg(Gh.v[c]); }
+        }
+
+        // ---- negatives: only the corrupted row is new ----
+        for (int j = 0; j < k; ++j) {
+            const int e = __shfl_sync(OEA_FULL, neg_e, j);
+            const bool head = (head_mask >> j) & 1u;
+            Row<VEC> xe = load_row<VEC>(ent.w, e, ent.pitch, lane);
+            const float sse = warp_sum(sumsq(xe));
+            const float ie = inv_norm(sse, ent.norm);
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) {
+                xe.v[c] = xe.v[c] * ie;
+                u.v[c] = head ? (xe.v[c] + rt.v[c]) : (hr.v[c] - xe.v[c]);
+            }
+            Row<VEC> dir = score_dir<SCORE, VEC>(u);
+            float sn = score_partial<SCORE, VEC>(u), de = dotr(xe, dir);
+            warp_sum2(sn, de);
+            loss_of(cfg.loss_kind, true, sn, cfg, L, g);
+            warp_loss += L;
+            if (g != 0.f) {
+                any_grad = true;
+                const float ge = head ? g : -g;  // d/dê = ±g·dir
+                Row<VEC> Ge;
+#pragma unroll
+                for (int c = 0; c < VEC; ++c) {
+                    const float4 du = dir.v[c] * g;
+                    Gr.v[c] = Gr.v[c] + du;
+                    if (head) Gt.v[c] = Gt.v[c] - du; else Gh.v[c] = Gh.v[c] + du;
+                    Ge.v[c] = dir.v[c] * ge;
+                }
+                Row<VEC> out = through_norm(Ge, xe, ge * de, ie, sse, ent.norm);
+                red_row<VEC>(ent.g, e, ent.pitch, lane, out);
+                if (lane == 0) ent.touched[e] = 1;
+            }
+        }
+
+        if (any_grad) {
+            float dh = dotr(xh, Gh), dr = dotr(xr, Gr), dt = dotr(xt, Gt);
+            warp_sum3(dh, dr, dt);
+            Row<VEC> oh = through_norm(Gh, xh, dh, ih, ssh, ent.norm);
+            Row<VEC> orr = through_norm(Gr, xr, dr, ir, ssr, rel.norm);
+            Row<VEC> ot = through_norm(Gt, xt, dt, it, sst, ent.norm);
+            red_row<VEC>(ent.g, h, ent.pitch, lane, oh);
+            red_row<VEC>(rel.g, r, rel.pitch, lane, orr);
+            red_row<VEC>(ent.g, t, ent.pitch, lane, ot);
+            if (lane == 0) { ent.touched[h] = 1; rel.touched[r] = 1; ent.touched[t] = 1; }
+        }
+    }
+    LossAcc acc{s_loss};
+    acc.flush(warp_loss, loss_out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row optimiser: one warp per row, flagged rows only (Adagrad / SGD) or all rows (Adam).
+// TF1 semantics (optimizers.py:10-20): Adagrad acc += g², x −= lr·g/√acc (no ε, acc0 = 0.1 set by
+// the caller); Adam lr_t = lr·√(1−β2^t)/(1−β1^t), x −= lr_t·m/(√v + ε).
+// ------------------------------------------------------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(kThreads)
+k_rowopt(float* __restrict__ w, float* __restrict__ grad, float* __restrict__ s1, float* __restrict__ s2,
+         int32_t* __restrict__ touched, int rows, int pitch, float lr, float beta1, float beta2, float eps,
+         float lr_t) {
+    const int lane = threadIdx.x & 31;
+    const int warp_global = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int n_warps = gridDim.x * kWarpsPerBlock;
+    const int p4 = pitch >> 2;
+    for (int row = warp_global; row < rows; row += n_warps) {
+        if (KIND != OEA_OPT_ADAM) {
+            if (touched[row] == 0) continue;
+        }
+        const size_t base = (size_t)row * pitch;
+        for (int c = lane; c < p4; c += OEA_WARP) {
+            const size_t o = base + 4 * (size_t)c;
+            float4 g = *reinterpret_cast<float4*>(grad + o);
+            float4 x = *reinterpret_cast<float4*>(w + o);
+            if (KIND == OEA_OPT_ADAGRAD) {
+                float4 a = *reinterpret_cast<float4*>(s1 + o);
+                a.x = fmaf(g.x, g.x, a.x); a.y = fmaf(g.y, g.y, a.y); a.z = fmaf(g.z, g.z, a.z); a.w = fmaf(g.w, g.w, a.w);
+                x.x -= lr * g.x * rsqrtf(a.x); x.y -= lr * g.y * rsqrtf(a.y);
+                x.z -= lr * g.z * rsqrtf(a.z); x.w -= lr * g.w * rsqrtf(a.w);
+                *reinterpret_cast<float4*>(s1 + o) = a;
+            } else if (KIND == OEA_OPT_SGD) {
+                x.x -= lr * g.x; x.y -= lr * g.y; x.z -= lr * g.z; x.w -= lr * g.w;
+            } else {
+                float4 m = *reinterpret_cast<float4*>(s1 + o);
+                float4 v = *reinterpret_cast<float4*>(s2 + o);
+                m.x = beta1 * m.x + (1.f - beta1) * g.x; m.y = beta1 * m.y + (1.f - beta1) * g.y;
+                m.z = beta1 * m.z + (1.f - beta1) * g.z; m.w = beta1 * m.w + (1.f - beta1) * g.w;
+                v.x = beta2 * v.x + (1.f - beta2) * g.x * g.x; v.y = beta2 * v.y + (1.f - beta2) * g.y * g.y;
+                v.z = beta2 * v.z + (1.f - beta2) * g.z * g.z; v.w = beta2 * v.w + (1.f - beta2) * g.w * g.w;
+                x.x -= lr_t * m.x / (sqrtf(v.x) + eps); x.y -= lr_t * m.y / (sqrtf(v.y) + eps);
+                x.z -= lr_t * m.z / (sqrtf(v.z) + eps); x.w -= lr_t * m.w / (sqrtf(v.w) + eps);
+                *reinterpret_cast<float4*>(s1 + o) = m;
+                *reinterpret_cast<float4*>(s2 + o) = v;
+            }
+            *reinterpret_cast<float4*>(w + o) = x;
+            *reinterpret_cast<float4*>(grad + o) = f4(0.f);
+        }
+        if (lane == 0) touched[row] = 0;
+    }
+}
+
+// Normalised lookup: out[i] = normalise(weight[ids[i]]) (basic_model.py:106-121 `.eval()` reads).
+__global__ void __launch_bounds__(kThreads)
+k_lookup(const float* __restrict__ w, int pitch, int dim, bool norm, const int32_t* __restrict__ ids, int n,
+         float* __restrict__ out, int out_pitch) {
+    const int lane = threadIdx.x & 31;
+    const int warp_global = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int n_warps = gridDim.x * kWarpsPerBlock;
+    for (int i = warp_global; i < n; i += n_warps) {
+        const int row = ids ? __ldg(ids + i) : i;
+        const float* src = w + (size_t)row * pitch;
+        float ss = 0.f;
+        for (int c = lane; c < dim; c += OEA_WARP) { const float x = __ldg(src + c); ss = fmaf(x, x, ss); }
+        ss = warp_sum(ss);
+        const float inv = inv_norm(ss, norm);
+        float* dst = out + (size_t)i * out_pitch;
+        for (int c = lane; c < out_pitch; c += OEA_WARP) dst[c] = c < dim ? __ldg(src + c) * inv : 0.f;
+    }
+}
+
+// ---- host-side validation + dispatch -----------------------------------------------------------
+static int check_table(const oea_table* t, bool need_grad) {
+    if (t == nullptr || t->weight == nullptr) return OEA_ERR_NULL;
+    if (need_grad && (t->grad == nullptr || t->touched == nullptr)) return OEA_ERR_NULL;
+    if (t->rows <= 0 || t->dim <= 0 || t->pitch < t->dim || (t->pitch & 3) != 0) return OEA_ERR_DIM;
+    if (t->pitch > 512) return OEA_ERR_DIM;
+    if (!aligned16(t->weight) || (need_grad && !aligned16(t->grad))) return OEA_ERR_ALIGN;
+    return OEA_OK;
+}
+
+static int grid_for(int n_warp_items) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int blocks_needed = (n_warp_items + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const int cap = sms * 8;  // 8 CTAs × 8 warps = 64 resident warps per SM
+    return blocks_needed < 1 ? 1 : (blocks_needed < cap ? blocks_needed : cap);
+}
+
+#define OEA_DISPATCH_VEC(pitch, CALL)                 \
+    do {                                              \
+        if ((pitch) <= 128) { CALL(1); }              \
+        else if ((pitch) <= 256) { CALL(2); }         \
+        else if ((pitch) <= 384) { CALL(3); }         \
+        else { CALL(4); }                             \
+    } while (0)
+
+}  // namespace oea
+
+using namespace oea;
+
+extern "C" int oea_abi_version(void) { return OEA_ABI_VERSION; }
+
+extern "C" const char* oea_error_string(int code) {
+    if (code < 0) return cudaGetErrorString((cudaError_t)(-code));
+    switch (code) {
+        case OEA_OK: return "ok";
+        case OEA_ERR_NULL: return "required pointer is NULL";
+        case OEA_ERR_DIM: return "rows/dim/pitch out of range (pitch % 4 == 0, dim <= pitch <= 512)";
+        case OEA_ERR_ALIGN: return "pointer not 16-byte aligned";
+        case OEA_ERR_KIND: return "unknown score/loss/optimiser/metric kind";
+        case OEA_ERR_SHAPE: return "inconsistent batch shapes";
+        case OEA_ERR_RANGE: return "parameter out of range";
+        case OEA_ERR_WORKSPACE: return "workspace too small";
+        default: return "unknown error";
+    }
+}
+
+extern "C" int oea_triple_score_fed(const oea_table* ent, const oea_table* rel,
+                                    const int32_t* pos_h, const int32_t* pos_r, const int32_t* pos_t, int32_t n_pos,
+                                    const int32_t* neg_h, const int32_t* neg_r, const int32_t* neg_t, int32_t n_neg,
+                                    const oea_loss_cfg* loss, double* loss_out, void* stream) {
+    int rc = check_table(ent, true); if (rc) return rc;
+    rc = check_table(rel, true); if (rc) return rc;
+    if (loss == nullptr || loss_out == nullptr) return OEA_ERR_NULL;
+    if (n_pos < 0 || n_neg < 0) return OEA_ERR_SHAPE;
+    if (n_pos > 0 && (!pos_h || !pos_r || !pos_t)) return OEA_ERR_NULL;
+    if (n_neg > 0 && (!neg_h || !neg_r || !neg_t)) return OEA_ERR_NULL;
+    if (ent->pitch != rel->pitch || ent->dim != rel->dim) return OEA_ERR_DIM;
+    if (loss->score_kind != OEA_SCORE_L1 && loss->score_kind != OEA_SCORE_L2SQ) return OEA_ERR_KIND;
+    if (loss->loss_kind < OEA_LOSS_MARGIN || loss->loss_kind > OEA_LOSS_LOGSIGMOID) return OEA_ERR_KIND;
+    if (loss->loss_kind == OEA_LOSS_MARGIN && n_neg != n_pos) return OEA_ERR_SHAPE;  // args_hander.py:19-21
+    if ((loss->loss_kind == OEA_LOSS_POSITIVE || loss->loss_kind == OEA_LOSS_LOGSIGMOID) && n_neg != 0) return OEA_ERR_SHAPE;
+    if (n_pos + n_neg == 0) return OEA_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    TableDev e = table_dev(ent), r = table_dev(rel);
+    const bool l1 = loss->score_kind == OEA_SCORE_L1;
+    if (loss->loss_kind == OEA_LOSS_MARGIN) {
+        const int grid = grid_for(n_pos);
+#define CALL(V)                                                                                                         \
+        if (l1) k_score_margin<OEA_SCORE_L1, V><<<grid, kThreads, 0, st>>>(e, r, pos_h, pos_r, pos_t, neg_h, neg_r, neg_t, n_pos, *loss, loss_out); \
+        else k_score_margin<OEA_SCORE_L2SQ, V><<<grid, kThreads, 0, st>>>(e, r, pos_h, pos_r, pos_t, neg_h, neg_r, neg_t, n_pos, *loss, loss_out)
+        OEA_DISPATCH_VEC(ent->pitch, CALL);
+#undef CALL
+    } else {
+        const int grid = grid_for(n_pos + n_neg);
+#define CALL(V)                                                                                                         \
+        if (l1) k_score_fed<OEA_SCORE_L1, V><<<grid, kThreads, 0, st>>>(e, r, pos_h, pos_r, pos_t, n_pos, neg_h, neg_r, neg_t, n_neg, *loss, loss_out); \
+        else k_score_fed<OEA_SCORE_L2SQ, V><<<grid, kThreads, 0, st>>>(e, r, pos_h, pos_r, pos_t, n_pos, neg_h, neg_r, neg_t, n_neg, *loss, loss_out)
+        OEA_DISPATCH_VEC(ent->pitch, CALL);
+#undef CALL
+    }
+    OEA_LAUNCH_CHECK();
+    return OEA_OK;
+}
+
+extern "C" int oea_rowopt_apply(const oea_table* t, const oea_opt_cfg* opt, void* stream) {
+    int rc = check_table(t, true); if (rc) return rc;
+    if (opt == nullptr) return OEA_ERR_NULL;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = grid_for(t->rows);
+    switch (opt->kind) {
+        case OEA_OPT_ADAGRAD:
+            if (!t->state1) return OEA_ERR_NULL;
+            k_rowopt<OEA_OPT_ADAGRAD><<<grid, kThreads, 0, st>>>(t->weight, t->grad, t->state1, nullptr, t->touched, t->rows, t->pitch, opt->lr, 0.f, 0.f, 0.f, 0.f);
+            break;
+        case OEA_OPT_SGD:
+            k_rowopt<OEA_OPT_SGD><<<grid, kThreads, 0, st>>>(t->weight, t->grad, nullptr, nullptr, t->touched, t->rows, t->pitch, opt->lr, 0.f, 0.f, 0.f, 0.f);
+            break;
+        case OEA_OPT_ADAM: {
+            if (!t->state1 || !t->state2) return OEA_ERR_NULL;
+            if (opt->t < 1) return OEA_ERR_RANGE;
+            const double b1t = 1.0 - pow((double)opt->beta1, (double)opt->t);
+            const double b2t = 1.0 - pow((double)opt->beta2, (double)opt->t);
+            const float lr_t = (float)((double)opt->lr * sqrt(b2t) / b1t);
+            k_rowopt<OEA_OPT_ADAM><<<grid, kThreads, 0, st>>>(t->weight, t->grad, t->state1, t->state2, t->touched, t->rows, t->pitch, opt->lr, opt->beta1, opt->beta2, opt->eps, lr_t);
+            break;
+        }
+        default:
+            return OEA_ERR_KIND;
+    }
+    OEA_LAUNCH_CHECK();
+    return OEA_OK;
+}
+
+static int check_kg(const oea_kg_view* kg, int k) {
+    if (kg == nullptr) return OEA_ERR_NULL;
+    if (kg->n_triples < 0 || kg->n_entities < 0) return OEA_ERR_RANGE;
+    if (kg->n_triples > 0 && (kg->triples == nullptr || kg->entities == nullptr)) return OEA_ERR_NULL;
+    if (kg->n_triples > 0 && kg->n_entities < k) return OEA_ERR_RANGE;  // random.sample would raise
+    if (kg->cand != nullptr && (kg->ent2row == nullptr || kg->n_cand < k)) return OEA_ERR_RANGE;
+    return OEA_OK;
+}
+
+// batch.py:39-42 / :48-53 — slice bounds of one KG for one step, computed as the reference does.
+static void slice_of(int n_triples, int batch_kg, int step, int* start, int* count) {
+    long long s = (long long)step * batch_kg, e = s + batch_kg;
+    if (e > n_triples) e = n_triples;
+    if (s > n_triples) s = n_triples;
+    *start = (int)s;
+    *count = (int)(e - s > 0 ? e - s : 0);
+}
+
+extern "C" int oea_triple_score_sampled(const oea_table* ent, const oea_table* rel,
+                                        const oea_kg_view* kg1, const oea_kg_view* kg2, const oea_tripleset* tset,
+                                        const oea_sample_cfg* smp, const oea_loss_cfg* loss,
+                                        double* loss_out, int32_t* n_pos_out, int32_t* dbg_neg, void* stream) {
+    int rc = check_table(ent, true); if (rc) return rc;
+    rc = check_table(rel, true); if (rc) return rc;
+    if (!smp || !loss || !loss_out || !tset || !tset->slots) return OEA_ERR_NULL;
+    if (ent->pitch != rel->pitch || ent->dim != rel->dim) return OEA_ERR_DIM;
+    if (smp->neg_per_pos < 1 || smp->neg_per_pos > 32 || smp->batch_size < 1 || smp->max_try < 1 || smp->step < 0) return OEA_ERR_RANGE;
+    if (tset->capacity == 0 || (tset->capacity & (tset->capacity - 1)) != 0) return OEA_ERR_RANGE;
+    if (loss->loss_kind != OEA_LOSS_LIMITED && loss->loss_kind != OEA_LOSS_LOGISTIC) return OEA_ERR_KIND;
+    if (loss->score_kind != OEA_SCORE_L1 && loss->score_kind != OEA_SCORE_L2SQ) return OEA_ERR_KIND;
+    rc = check_kg(kg1, smp->neg_per_pos); if (rc) return rc;
+    rc = check_kg(kg2, smp->neg_per_pos); if (rc) return rc;
+    const long long T = (long long)kg1->n_triples + kg2->n_triples;
+    if (T == 0) return OEA_ERR_RANGE;
+    // int(len(l1) / (len(l1) + len(l2)) * batch_size): float division, multiply, truncate (batch.py:39)
+    const int b1 = (int)((double)kg1->n_triples / (double)T * (double)smp->batch_size);
+    const int b2 = smp->batch_size - b1;
+
+    SampledParams P;
+    P.kg[0] = *kg1; P.kg[1] = *kg2; P.tset = *tset;
+    slice_of(kg1->n_triples, b1, smp->step, &P.start[0], &P.n_slice[0]);
+    slice_of(kg2->n_triples, b2, smp->step, &P.start[1], &P.n_slice[1]);
+    P.k = smp->neg_per_pos; P.step = smp->step; P.max_try = smp->max_try; P.seed = smp->epoch_seed;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n_pos = P.n_slice[0] + P.n_slice[1];
+    if (n_pos_out) OEA_CUDA_TRY(cudaMemcpyAsync(n_pos_out, &n_pos, sizeof(int), cudaMemcpyHostToDevice, st));
+    if (n_pos == 0) return OEA_OK;
+    TableDev e = table_dev(ent), r = table_dev(rel);
+    const int grid = grid_for(n_pos);
+    const bool l1 = loss->score_kind == OEA_SCORE_L1;
+#define CALL(V)                                                                                              \
+    if (l1) k_score_sampled<OEA_SCORE_L1, V><<<grid, kThreads, 0, st>>>(e, r, P, *loss, loss_out, dbg_neg);  \
+    else k_score_sampled<OEA_SCORE_L2SQ, V><<<grid, kThreads, 0, st>>>(e, r, P, *loss, loss_out, dbg_neg)
+    OEA_DISPATCH_VEC(ent->pitch, CALL);
+#undef CALL
+    OEA_LAUNCH_CHECK();
+    return OEA_OK;
+}
+
+extern "C" int oea_triple_step_fed_host(const oea_table* ent, const oea_table* rel,
+                                        const int32_t* pos_hrt_host, int32_t n_pos,
+                                        const int32_t* neg_hrt_host, int32_t n_neg,
+                                        const oea_loss_cfg* loss, const oea_opt_cfg* opt,
+                                        int32_t* dev_idx_ws, double* dev_loss_ws, double* loss_pinned_host,
+                                        float* loss_host, void* stream) {
+    if (!dev_idx_ws || !dev_loss_ws || !loss_pinned_host || !loss_host || !opt) return OEA_ERR_NULL;
+    if (n_pos < 0 || n_neg < 0) return OEA_ERR_SHAPE;
+    if ((n_pos > 0 && !pos_hrt_host) || (n_neg > 0 && !neg_hrt_host)) return OEA_ERR_NULL;
+    cudaStream_t st = (cudaStream_t)stream;
+    int32_t* dpos = dev_idx_ws;
+    int32_t* dneg = dev_idx_ws + 3 * (size_t)n_pos;
+    if (n_pos) OEA_CUDA_TRY(cudaMemcpyAsync(dpos, pos_hrt_host, 3 * (size_t)n_pos * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    if (n_neg) OEA_CUDA_TRY(cudaMemcpyAsync(dneg, neg_hrt_host, 3 * (size_t)n_neg * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    OEA_CUDA_TRY(cudaMemsetAsync(dev_loss_ws, 0, sizeof(double), st));
+    int rc = oea_triple_score_fed(ent, rel, dpos, dpos + n_pos, dpos + 2 * (size_t)n_pos, n_pos,
+                                  dneg, dneg + n_neg, dneg + 2 * (size_t)n_neg, n_neg, loss, dev_loss_ws, stream);
+    if (rc) return rc;
+    rc = oea_rowopt_apply(ent, opt, stream); if (rc) return rc;
+    rc = oea_rowopt_apply(rel, opt, stream); if (rc) return rc;
+    OEA_CUDA_TRY(cudaMemcpyAsync(loss_pinned_host, dev_loss_ws, sizeof(double), cudaMemcpyDeviceToHost, st));
+    OEA_CUDA_TRY(cudaStreamSynchronize(st));
+    *loss_host = (float)(*loss_pinned_host);
+    return OEA_OK;
+}
+
+extern "C" int oea_table_lookup(const oea_table* t, const int32_t* ids, int32_t n, float* out, int32_t out_pitch,
+                                void* stream) {
+    int rc = check_table(t, false); if (rc) return rc;
+    if (out == nullptr) return OEA_ERR_NULL;
+    if (n < 0 || out_pitch < t->dim) return OEA_ERR_SHAPE;
+    if (n == 0) return OEA_OK;
+    k_lookup<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(t->weight, t->pitch, t->dim, t->l2_norm != 0, ids, n, out, out_pitch);
+    OEA_LAUNCH_CHECK();
+    return OEA_OK;
+}
+
+namespace oea {
+__global__ void k_tripleset_build(const int32_t* __restrict__ triples, int n, unsigned long long* slots, uint32_t capacity,
+                                  uint32_t ent_bits, uint32_t rel_bits) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t key = triple_key(triples[3 * (size_t)i], triples[3 * (size_t)i + 1], triples[3 * (size_t)i + 2], ent_bits, rel_bits);
+    const uint32_t mask = capacity - 1u;
+    uint32_t slot = (uint32_t)mix64(key) & mask;
+    while (true) {
+        const unsigned long long prev = atomicCAS(slots + slot, 0xFFFFFFFFFFFFFFFFull, (unsigned long long)key);
+        if (prev == 0xFFFFFFFFFFFFFFFFull || prev == key) return;
+        slot = (slot + 1u) & mask;
+    }
+}
+}  // namespace oea
+
+extern "C" int oea_tripleset_build(const int32_t* triples, int32_t n, uint64_t* slots, uint32_t capacity,
+                                   uint32_t ent_bits, uint32_t rel_bits, void* stream) {
+    if (!slots || (n > 0 && !triples)) return OEA_ERR_NULL;
+    if (n < 0 || capacity == 0 || (capacity & (capacity - 1)) != 0 || (uint64_t)capacity < 2ull * (uint64_t)n) return OEA_ERR_RANGE;
+    if (2 * ent_bits + rel_bits > 63) return OEA_ERR_RANGE;
+    cudaStream_t st = (cudaStream_t)stream;
+    OEA_CUDA_TRY(cudaMemsetAsync(slots, 0xFF, (size_t)capacity * sizeof(uint64_t), st));
+    if (n == 0) return OEA_OK;
+    k_tripleset_build<<<(n + 255) / 256, 256, 0, st>>>(triples, n, (unsigned long long*)slots, capacity, ent_bits, rel_bits);
+    OEA_LAUNCH_CHECK();
+    return OEA_OK;
+}

@@ -1,0 +1,248 @@
+"""Host side of path (i): device-resident embedding tables, the triple trainer and device KG views.
+
+PyTorch is used for device memory and streams only; every numeric operation goes through the C-ABI
+of liboea.so (openea_b200.lib).  Nothing here falls back to PyTorch maths.
+
+Reference boundary this mirrors: the TF variables + placeholders + session.run of
+models/basic_model.py:73-98,211-236 (variables live on the device, index batches are fed).
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import lib as L
+
+ADAGRAD_INIT_ACC = 0.1  # tf.train.AdagradOptimizer initial_accumulator_value (TF1 default)
+
+
+def _stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def pitch_for(dim):
+    """Internal row pitch: next multiple of 4 floats (16 B) so rows are float4-addressable (d=75 → 76)."""
+    return (int(dim) + 3) // 4 * 4
+
+
+class EmbeddingTable:
+    """A TF-style embedding variable + optimiser slots on the device.
+
+    `weight` is the RAW variable; when `l2_norm` every lookup goes through l2_normalize and gradients
+    flow through it (modules/base/initializers.py:26,34,41,50).
+    """
+
+    def __init__(self, init, l2_norm, optimizer="Adagrad", device="cuda"):
+        init = torch.as_tensor(init, dtype=torch.float32)
+        rows, dim = init.shape
+        self.rows, self.dim, self.pitch = int(rows), int(dim), pitch_for(dim)
+        self.l2_norm = bool(l2_norm)
+        self.device = torch.device(device)
+        self.weight = torch.zeros(rows, self.pitch, dtype=torch.float32, device=self.device)
+        self.weight[:, :dim] = init.to(self.device)
+        self.grad = torch.zeros_like(self.weight)
+        self.touched = torch.zeros(rows, dtype=torch.int32, device=self.device)
+        self.optimizer = optimizer
+        self.state1 = None
+        self.state2 = None
+        self.adam_t = 0
+        self._make_state()
+        self._struct = None
+
+    def _make_state(self):
+        if self.optimizer == "Adagrad":
+            self.state1 = torch.full_like(self.weight, ADAGRAD_INIT_ACC)
+            self.state1[:, self.dim:] = 1.0  # padding columns: g = 0 there, keep rsqrt finite
+        elif self.optimizer == "Adam":
+            self.state1 = torch.zeros_like(self.weight)
+            self.state2 = torch.zeros_like(self.weight)
+        elif self.optimizer in ("SGD", "GradientDescent"):
+            self.optimizer = "SGD"
+        else:
+            raise ValueError("unsupported optimizer for the fused row optimiser: %s" % self.optimizer)
+
+    def new_slots(self):
+        """A second optimiser instance over the same variable (each generate_optimizer call in the
+        reference owns its slot variables): returns a view sharing weight/grad/touched."""
+        other = object.__new__(EmbeddingTable)
+        other.__dict__.update(self.__dict__)
+        other._struct = None
+        other._make_state()
+        other.adam_t = 0
+        return other
+
+    def c_struct(self):
+        if self._struct is None:
+            self._struct = L.Table(self.weight.data_ptr(), self.grad.data_ptr(),
+                                   0 if self.state1 is None else self.state1.data_ptr(),
+                                   0 if self.state2 is None else self.state2.data_ptr(),
+                                   self.touched.data_ptr(), self.rows, self.dim, self.pitch, int(self.l2_norm))
+        return self._struct
+
+    def raw(self):
+        return self.weight[:, :self.dim]
+
+    def lookup(self, ids=None):
+        """Normalised rows as TF's `embedding_lookup(self.ent_embeds, ids).eval()` → device tensor [n, dim]."""
+        lib = L.load()
+        if ids is None:
+            n, ids_t = self.rows, None
+        else:
+            ids_t = torch.as_tensor(ids, dtype=torch.int32, device=self.device).contiguous()
+            n = ids_t.numel()
+        out = torch.empty(n, self.dim, dtype=torch.float32, device=self.device)
+        L.check(lib.oea_table_lookup(C.byref(self.c_struct()), _ptr(ids_t), n, _ptr(out), self.dim, _stream_ptr()),
+                "oea_table_lookup")
+        return out
+
+
+def loss_cfg(loss, loss_norm, margin=0.0, neg_margin=0.0, balance=1.0):
+    kinds = {"margin-based": L.LOSS_MARGIN, "limited": L.LOSS_LIMITED, "logistic": L.LOSS_LOGISTIC,
+             "positive": L.LOSS_POSITIVE, "logsigmoid": L.LOSS_LOGSIGMOID}
+    if loss not in kinds:
+        raise ValueError("unknown loss %r" % (loss,))
+    score = L.SCORE_L1 if loss_norm == "L1" else L.SCORE_L2SQ  # losses.py: anything but 'L1' is squared L2
+    return L.LossCfg(score, kinds[loss], float(margin), float(neg_margin), float(balance))
+
+
+def opt_cfg(table, lr):
+    kind = {"SGD": L.OPT_SGD, "Adagrad": L.OPT_ADAGRAD, "Adam": L.OPT_ADAM}[table.optimizer]
+    return L.OptCfg(kind, float(lr), 0.9, 0.999, 1e-8, max(1, table.adam_t))
+
+
+class DeviceKG:
+    """Device copy of one KG's training triples + candidate lists (oea_kg_view)."""
+
+    def __init__(self, triples, entities, ent_rows, device="cuda"):
+        self.device = torch.device(device)
+        tri = np.asarray(triples, dtype=np.int32).reshape(-1, 3)
+        self.triples = torch.from_numpy(np.ascontiguousarray(tri)).to(self.device)
+        self.entities = torch.as_tensor(np.asarray(entities, dtype=np.int32), device=self.device)
+        self.ent_rows = int(ent_rows)
+        self.cand = None
+        self.ent2row = None
+
+    def set_candidates(self, cand, row_entities):
+        """cand: [rows, n_cand] int32 device tensor of ε-truncated neighbour ids; row_entities: the entity id
+        owning each row (batch.py:145-165 builds dict entity → list)."""
+        self.cand = cand.contiguous()
+        e2r = torch.full((self.ent_rows,), -1, dtype=torch.int32, device=self.device)
+        rows = torch.as_tensor(row_entities, dtype=torch.int64, device=self.device)
+        e2r[rows] = torch.arange(rows.numel(), dtype=torch.int32, device=self.device)
+        self.ent2row = e2r
+
+    def clear_candidates(self):
+        self.cand = None
+        self.ent2row = None
+
+    def view(self):
+        return L.KgView(self.triples.data_ptr(), self.triples.shape[0], self.entities.data_ptr(),
+                        self.entities.numel(), 0 if self.cand is None else self.cand.data_ptr(),
+                        0 if self.ent2row is None else self.ent2row.data_ptr(),
+                        0 if self.cand is None else self.cand.shape[1])
+
+
+class DeviceTripleSet:
+    """Open-addressing membership set of (h, r, t) built on device (oea_tripleset_build)."""
+
+    def __init__(self, triple_tensors, n_ent, n_rel, device="cuda"):
+        lib = L.load()
+        self.device = torch.device(device)
+        allt = torch.cat([t.reshape(-1, 3) for t in triple_tensors], dim=0).contiguous()
+        n = allt.shape[0]
+        self.ent_bits = max(1, int(math.ceil(math.log2(max(2, n_ent)))))
+        self.rel_bits = max(1, int(math.ceil(math.log2(max(2, n_rel)))))
+        cap = 1 << max(4, int(math.ceil(math.log2(max(2, 2 * n)))))
+        self.slots = torch.empty(cap, dtype=torch.int64, device=self.device)
+        self.capacity = cap
+        L.check(lib.oea_tripleset_build(_ptr(allt), n, _ptr(self.slots), cap, self.ent_bits, self.rel_bits,
+                                        _stream_ptr()), "oea_tripleset_build")
+
+    def view(self):
+        return L.TripleSet(self.slots.data_ptr(), self.capacity, self.ent_bits, self.rel_bits)
+
+
+class TripleTrainer:
+    """Forward/backward + optimiser for one (loss, optimiser instance) over the entity/relation tables."""
+
+    def __init__(self, ent, rel, loss, lr):
+        self.lib = L.load()
+        self.ent, self.rel = ent, rel
+        self.loss = loss
+        self.lr = float(lr)
+        dev = ent.device
+        self.loss_dev = torch.zeros(1, dtype=torch.float64, device=dev)
+        self._idx_ws = None
+        self._loss_pinned = torch.zeros(1, dtype=torch.float64).pin_memory() if dev.type == "cuda" else None
+
+    # -- device-index API -------------------------------------------------------------------------
+    def score_fed(self, pos, neg=None, loss_out=None):
+        """pos/neg: int32 device tensors [3, n] (h | r | t rows).  Accumulates gradients; adds the batch
+        loss into loss_out (device fp64 scalar tensor, default self.loss_dev)."""
+        out = self.loss_dev if loss_out is None else loss_out
+        n_pos = pos.shape[1]
+        n_neg = 0 if neg is None else neg.shape[1]
+        np_ = lambda t, i: C.c_void_p(0 if t is None or t.shape[1] == 0 else t[i].data_ptr())
+        L.check(self.lib.oea_triple_score_fed(
+            C.byref(self.ent.c_struct()), C.byref(self.rel.c_struct()),
+            np_(pos, 0), np_(pos, 1), np_(pos, 2), n_pos, np_(neg, 0), np_(neg, 1), np_(neg, 2), n_neg,
+            C.byref(self.loss), _ptr(out), _stream_ptr()), "oea_triple_score_fed")
+
+    def apply(self):
+        for tab in (self.ent, self.rel):
+            if tab.optimizer == "Adam":
+                tab.adam_t += 1
+            cfg = opt_cfg(tab, self.lr)
+            L.check(self.lib.oea_rowopt_apply(C.byref(tab.c_struct()), C.byref(cfg), _stream_ptr()),
+                    "oea_rowopt_apply")
+
+    def score_sampled(self, kg1, kg2, tset, batch_size, neg_per_pos, step, epoch_seed, max_try=10,
+                      loss_out=None, dbg=None, n_pos_out=None):
+        out = self.loss_dev if loss_out is None else loss_out
+        smp = L.SampleCfg(int(batch_size), int(neg_per_pos), int(step), int(max_try), int(epoch_seed) & (2**64 - 1))
+        k1, k2, ts = kg1.view(), kg2.view(), tset.view()
+        L.check(self.lib.oea_triple_score_sampled(
+            C.byref(self.ent.c_struct()), C.byref(self.rel.c_struct()), C.byref(k1), C.byref(k2), C.byref(ts),
+            C.byref(smp), C.byref(self.loss), _ptr(out), _ptr(n_pos_out), _ptr(dbg), _stream_ptr()),
+            "oea_triple_score_sampled")
+
+    # -- host-index API (the session.run(feed_dict) boundary) --------------------------------------
+    def step_fed_host(self, pos_hrt, neg_hrt=None):
+        """pos_hrt / neg_hrt: host int32 arrays [3, n] (pinned torch tensors or numpy).  Synchronous; returns
+        the batch loss as a Python float (what session.run returns for `triple_loss`)."""
+        pos_t = _as_host_i32(pos_hrt)
+        neg_t = _as_host_i32(neg_hrt) if neg_hrt is not None else None
+        n_pos = pos_t.shape[1]
+        n_neg = 0 if neg_t is None else neg_t.shape[1]
+        need = 3 * (n_pos + n_neg)
+        if self._idx_ws is None or self._idx_ws.numel() < need:
+            self._idx_ws = torch.empty(max(need, 1), dtype=torch.int32, device=self.ent.device)
+        for tab in (self.ent, self.rel):
+            if tab.optimizer == "Adam":
+                tab.adam_t += 1
+        cfg = opt_cfg(self.ent, self.lr)
+        loss = C.c_float(0.0)
+        L.check(self.lib.oea_triple_step_fed_host(
+            C.byref(self.ent.c_struct()), C.byref(self.rel.c_struct()),
+            C.c_void_p(pos_t.data_ptr()), n_pos, C.c_void_p(0 if neg_t is None else neg_t.data_ptr()), n_neg,
+            C.byref(self.loss), C.byref(cfg), _ptr(self._idx_ws), _ptr(self.loss_dev),
+            C.c_void_p(self._loss_pinned.data_ptr()), C.byref(loss), _stream_ptr()), "oea_triple_step_fed_host")
+        return float(loss.value)
+
+    def read_loss(self, reset=True):
+        v = float(self.loss_dev.item())
+        if reset:
+            self.loss_dev.zero_()
+        return v
+
+
+def _as_host_i32(a):
+    if isinstance(a, torch.Tensor):
+        assert a.dtype == torch.int32 and not a.is_cuda and a.is_contiguous()
+        return a
+    return torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.int32)))
