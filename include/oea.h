@@ -17,6 +17,7 @@
 #ifndef OEA_H_
 #define OEA_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -167,6 +168,56 @@ int oea_table_lookup(const oea_table* table, const int32_t* ids, int32_t n, floa
  * `relation_triples_set` handed to batch.py:36 (modules/load/kg.py:63). */
 int oea_tripleset_build(const int32_t* triples, int32_t n, uint64_t* slots, uint32_t capacity,
                         uint32_t ent_bits, uint32_t rel_bits, void* stream);
+
+/* ---- path (iii): all-pairs similarity, CSLS, top-k, rank ----------------------------------- */
+
+/* modules/finding/similarity.py:33-51.  INNER also serves 'cosine' (rows normalised first with
+ * oea_rows_normalize).  L1 = 'manhattan' (1 − cityblock), L2 = 'euclidean' (1 − ‖a−b‖₂). */
+enum { OEA_METRIC_INNER = 0, OEA_METRIC_L1 = 1, OEA_METRIC_L2 = 2 };
+
+/* E1 [n1, pitch1], E2 [n2, pitch2]: row-major fp32, pitch % 4 == 0, columns >= dim are ZERO. */
+typedef struct oea_sim_cfg {
+    int32_t metric;
+    int32_t n1, n2, dim;
+    int32_t pitch1, pitch2;
+} oea_sim_cfg;
+
+/* Per-row k best columns of S (or of the CSLS matrix 2·S − row_off[i] − col_off[j] when the two
+ * offset vectors are given; similarity.py:57-77), k <= 32, without materialising S.
+ * out_val/out_idx [n1, k] sorted descending (ties: lower column first), out_mean [n1] = mean of the
+ * k values (= calculate_nearest_k, similarity.py:80-83); each output may be NULL.
+ * Replaces calculate_nearest_k (call with (E1,E2) for rows, (E2,E1) for columns),
+ * search_nearest_k (bootstrapping/alignment_finder.py:66-76) and the top-k part of predict(). */
+size_t oea_sim_topk_workspace_bytes(const oea_sim_cfg* cfg, int32_t k);
+int oea_sim_topk(const oea_sim_cfg* cfg, const float* e1, const float* e2,
+                 const float* row_off, const float* col_off, int32_t k,
+                 float* out_val, int32_t* out_idx, float* out_mean,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* calculate_rank (modules/finding/alignment.py:146-168) without the sort: for every row i,
+ * out_top1[i] = argmax_j S'_ij and out_rank[i] = 0-based rank of column gold[i] in descending order
+ * (ties: lower column index first).  S' as above. */
+size_t oea_sim_rank_workspace_bytes(const oea_sim_cfg* cfg);
+int oea_sim_rank(const oea_sim_cfg* cfg, const float* e1, const float* e2,
+                 const float* row_off, const float* col_off, const int32_t* gold,
+                 int32_t* out_top1, int32_t* out_rank,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* Materialise S' into out [n1, ld_out] (sim(), similarity.py:11-54; BootEA.eval_ref_sim_mat,
+ * approaches/bootea.py:214-219).  Also the first stage of the large-k neighbour search. */
+int oea_sim_matrix(const oea_sim_cfg* cfg, const float* e1, const float* e2,
+                   const float* row_off, const float* col_off, float* out, int64_t ld_out, void* stream);
+
+/* sklearn.preprocessing.normalize (similarity.py:30-32): rows scaled to unit L2 norm, zero rows kept;
+ * writes zero padding up to out_pitch. */
+int oea_rows_normalize(const float* in, int32_t in_pitch, int32_t n, int32_t dim, float* out, int32_t out_pitch,
+                       void* stream);
+
+/* Per-row k LARGEST entries of a materialised matrix, large k (the ε-truncated neighbour search,
+ * modules/train/batch.py:157-165: np.argpartition(-sim, k)[:k]); only SET membership is defined.
+ * out_idx [n_rows, k] = col_ids[column] (col_ids == NULL → the column index itself). */
+int oea_rows_select_topk(const float* mat, int64_t ld, int32_t n_rows, int32_t n_cols, int32_t k,
+                         const int32_t* col_ids, int32_t* out_idx, void* stream);
 
 #ifdef __cplusplus
 }

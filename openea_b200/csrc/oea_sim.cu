@@ -1,0 +1,609 @@
+// oea_sim.cu — path (iii): all-pairs similarity, CSLS, per-row top-k, rank-of-gold (K3).  sm_100a.
+//
+// Restates (no code shared):
+//   modules/finding/similarity.py:11-83   sim(): inner / cosine / euclidean / manhattan, csls_sim()
+//   modules/finding/alignment.py:146-168  calculate_rank(): argmax + rank of the gold column
+//   modules/bootstrapping/alignment_finder.py:54-76  threshold filter ∧ per-row top-k
+//   modules/train/batch.py:157-165        find_neighbours(): per-row k largest (large k)
+//
+// The n1×n2 matrix is never materialised for top-k / rank: a 128×128 FP32 register-tiled kernel
+// (FP32 FFMA so that alignment indices match float32 BLAS; manhattan is not a contraction) walks the
+// column tiles of one row block and folds each finished tile into a per-row top-k list (smem) or a
+// per-thread argmax + rank counter (registers).
+#include <float.h>
+#include "oea_common.cuh"
+
+namespace oea {
+
+enum { EPI_TOPK = 0, EPI_RANK = 1, EPI_STORE = 2 };
+
+constexpr int TM = 128, TN = 128, BK = 16;
+constexpr int SIM_THREADS = 256;
+constexpr int KMAX = 32;  // per-row top-k list lives in one warp's lanes
+
+// similarity value from the accumulated contraction (similarity.py:36-51)
+template <int METRIC>
+__device__ __forceinline__ float sim_value(float acc) {
+    if (METRIC == OEA_METRIC_INNER) return acc;
+    if (METRIC == OEA_METRIC_L1) return 1.f - acc;       // 1 − cityblock
+    return 1.f - sqrtf(fmaxf(acc, 0.f));                 // 1 − euclidean
+}
+template <int METRIC>
+__device__ __forceinline__ float sim_accum(float a, float b, float acc) {
+    if (METRIC == OEA_METRIC_INNER) return fmaf(a, b, acc);
+    if (METRIC == OEA_METRIC_L1) return acc + fabsf(a - b);
+    const float dlt = a - b;
+    return fmaf(dlt, dlt, acc);
+}
+// CSLS: 2·S − r_i − c_j (similarity.py:73-77)
+__device__ __forceinline__ float csls_value(float s, float r, float c) { return (2.f * s - r) - c; }
+
+struct SimParams {
+    const float* e1; const float* e2;
+    int n1, n2, pitch1, pitch2, kdim;      // kdim = min(pitch1, pitch2) rounded: contraction length
+    const float* row_off; const float* col_off;  // CSLS r_i / c_j or nullptr
+    int col_tiles_per_split;
+    // top-k
+    int k; float* part_val; int* part_idx; int splits;
+    // rank
+    const int* gold; const float* gold_val; unsigned long long* best; int* rank;
+    // store
+    float* out; long long ld_out;
+};
+
+template <int METRIC, int EPI>
+__global__ void __launch_bounds__(SIM_THREADS)
+k_sim_tile(SimParams P) {
+    extern __shared__ __align__(16) float smem[];
+    float (*As)[BK][TM] = reinterpret_cast<float (*)[BK][TM]>(smem);                 // [2][BK][TM]
+    float (*Bs)[BK][TN] = reinterpret_cast<float (*)[BK][TN]>(smem + 2 * BK * TM);   // [2][BK][TN]
+    float* Ts = smem + 2 * BK * TM + 2 * BK * TN;                                    // [TM][TN+1] (TOPK only)
+    float* Lv = Ts + TM * (TN + 1);                                                  // [TM][KMAX]
+    int* Li = reinterpret_cast<int*>(Lv + TM * KMAX);                                // [TM][KMAX]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int row0 = blockIdx.x * TM;
+    const int n_col_tiles = (P.n2 + TN - 1) / TN;
+    const int ct0 = blockIdx.y * P.col_tiles_per_split;
+    const int ct1 = min(n_col_tiles, ct0 + P.col_tiles_per_split);
+
+    // loader mapping: thread → (row = tid % 128, k-half = tid / 128)
+    const int lrow = tid & 127, lhalf = tid >> 7;
+    const int arow = row0 + lrow;
+    const bool arow_ok = arow < P.n1;
+    const float* aptr = P.e1 + (size_t)(arow_ok ? arow : 0) * P.pitch1 + lhalf * 8;
+
+    if (EPI == EPI_TOPK) {
+        for (int i = tid; i < TM * KMAX; i += SIM_THREADS) { Lv[i] = -FLT_MAX; Li[i] = -1; }
+    }
+    // per-thread rank state (EPI_RANK)
+    float gval[8], bestv[8]; int besti[8], cnt[8], goldc[8];
+    float roff[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = row0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4);
+        const bool ok = r < P.n1;
+        roff[i] = (P.row_off && ok) ? __ldg(P.row_off + r) : 0.f;
+        if (EPI == EPI_RANK) {
+            gval[i] = ok ? __ldg(P.gold_val + r) : FLT_MAX;
+            goldc[i] = ok ? __ldg(P.gold + r) : -1;
+            bestv[i] = -FLT_MAX; besti[i] = 0x7fffffff; cnt[i] = 0;
+        }
+    }
+    const int nk = (P.kdim + BK - 1) / BK;
+
+    for (int ct = ct0; ct < ct1; ++ct) {
+        const int col0 = ct * TN;
+        const int brow = col0 + lrow;
+        const bool brow_ok = brow < P.n2;
+        const float* bptr = P.e2 + (size_t)(brow_ok ? brow : 0) * P.pitch2 + lhalf * 8;
+
+        float acc[8][8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+        float4 ra[2], rb[2];
+        auto gload = [&](int kc) {
+            const int kbase = kc * BK + lhalf * 8;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int kk = kbase + 4 * q;
+                ra[q] = (arow_ok && kk < P.kdim) ? ldg4(aptr + kc * BK + 4 * q) : f4(0.f);
+                rb[q] = (brow_ok && kk < P.kdim) ? ldg4(bptr + kc * BK + 4 * q) : f4(0.f);
+            }
+        };
+        auto sstore = [&](int buf) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int kk = lhalf * 8 + 4 * q;
+                As[buf][kk + 0][lrow] = ra[q].x; As[buf][kk + 1][lrow] = ra[q].y;
+                As[buf][kk + 2][lrow] = ra[q].z; As[buf][kk + 3][lrow] = ra[q].w;
+                Bs[buf][kk + 0][lrow] = rb[q].x; Bs[buf][kk + 1][lrow] = rb[q].y;
+                Bs[buf][kk + 2][lrow] = rb[q].z; Bs[buf][kk + 3][lrow] = rb[q].w;
+            }
+        };
+        gload(0);
+        __syncthreads();   // previous tile's epilogue / smem readers are done
+        sstore(0);
+        __syncthreads();
+        for (int kc = 0; kc < nk; ++kc) {
+            const int buf = kc & 1;
+            if (kc + 1 < nk) gload(kc + 1);
+#pragma unroll
+            for (int kk = 0; kk < BK; ++kk) {
+                const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+                const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][64 + ty * 4]);
+                const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+                const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][64 + tx * 4]);
+                const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[i][j] = sim_accum<METRIC>(a[i], b[j], acc[i][j]);
+            }
+            if (kc + 1 < nk) {
+                sstore(buf ^ 1);
+                __syncthreads();
+            }
+        }
+
+        // ---- epilogue ----
+        float coff[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = col0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + j - 4);
+            coff[j] = (P.col_off && c < P.n2) ? __ldg(P.col_off + c) : 0.f;
+        }
+        const bool use_csls = P.row_off != nullptr;
+        if (EPI == EPI_TOPK) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int rl = i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int cl = j < 4 ? tx * 4 + j : 64 + tx * 4 + j - 4;
+                    float v = sim_value<METRIC>(acc[i][j]);
+                    if (use_csls) v = csls_value(v, roff[i], coff[j]);
+                    if (col0 + cl >= P.n2) v = -FLT_MAX;
+                    Ts[rl * (TN + 1) + cl] = v;
+                }
+            }
+            __syncthreads();
+            const int k = P.k;
+            for (int rl = warp; rl < TM; rl += SIM_THREADS / 32) {
+                float lv = Lv[rl * KMAX + lane];
+                int li = Li[rl * KMAX + lane];
+                float tau = __shfl_sync(OEA_FULL, lv, k - 1);
+                bool changed = false;
+#pragma unroll
+                for (int m = 0; m < TN / 32; ++m) {
+                    const float c = Ts[rl * (TN + 1) + lane + 32 * m];
+                    unsigned pass = __ballot_sync(OEA_FULL, c > tau);
+                    while (pass) {
+                        const int src = __ffs(pass) - 1;
+                        pass &= pass - 1;
+                        const float cv = __shfl_sync(OEA_FULL, c, src);
+                        if (!(cv > tau)) continue;   // tau rose since the ballot
+                        const int ci = col0 + src + 32 * m;
+                        // entries with value >= cv keep their place (they have lower column indices)
+                        const int pos = __popc(__ballot_sync(OEA_FULL, lane < k && lv >= cv));
+                        const float up_v = __shfl_up_sync(OEA_FULL, lv, 1);
+                        const int up_i = __shfl_up_sync(OEA_FULL, li, 1);
+                        if (lane > pos) { lv = up_v; li = up_i; }
+                        else if (lane == pos) { lv = cv; li = ci; }
+                        tau = __shfl_sync(OEA_FULL, lv, k - 1);
+                        changed = true;
+                    }
+                }
+                if (changed) { Lv[rl * KMAX + lane] = lv; Li[rl * KMAX + lane] = li; }
+            }
+            // the next tile's first __syncthreads orders these smem reads before Ts is rewritten
+        } else if (EPI == EPI_RANK) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int c = col0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + j - 4);
+                    float v = sim_value<METRIC>(acc[i][j]);
+                    if (use_csls) v = csls_value(v, roff[i], coff[j]);
+                    if (c < P.n2) {
+                        // rank of gold = #{better} + #{equal with a lower index} ("lower index wins")
+                        cnt[i] += (v > gval[i]) || (v == gval[i] && c < goldc[i]);
+                        if (v > bestv[i]) { bestv[i] = v; besti[i] = c; }   // columns ascend per thread
+                    }
+                }
+            }
+        } else {  // EPI_STORE
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = row0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4);
+                if (r >= P.n1) continue;
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj) {
+                    const int c = col0 + (jj == 0 ? tx * 4 : 64 + tx * 4);
+                    float v[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        v[j] = sim_value<METRIC>(acc[i][jj * 4 + j]);
+                        if (use_csls) v[j] = csls_value(v[j], roff[i], coff[jj * 4 + j]);
+                    }
+                    float* o = P.out + (size_t)r * P.ld_out + c;
+                    if (c + 3 < P.n2 && (P.ld_out & 3) == 0) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+                    else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) if (c + j < P.n2) o[j] = v[j];
+                    }
+                }
+            }
+        }
+    }
+
+    if (EPI == EPI_TOPK) {
+        __syncthreads();
+        for (int rl = warp; rl < TM; rl += SIM_THREADS / 32) {
+            const int r = row0 + rl;
+            if (r < P.n1 && lane < P.k) {
+                const size_t o = ((size_t)r * P.splits + blockIdx.y) * P.k + lane;
+                P.part_val[o] = Lv[rl * KMAX + lane];
+                P.part_idx[o] = Li[rl * KMAX + lane];
+            }
+        }
+    } else if (EPI == EPI_RANK) {
+        // reduce across the 16 threads (tx) that share a row: they sit in one half-warp
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            int c = cnt[i]; float bv = bestv[i]; int bi = besti[i];
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) {
+                c += __shfl_xor_sync(OEA_FULL, c, o);
+                const float ov = __shfl_xor_sync(OEA_FULL, bv, o);
+                const int oi = __shfl_xor_sync(OEA_FULL, bi, o);
+                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            }
+            const int r = row0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4);
+            if (tx == 0 && r < P.n1) {
+                if (c) atomicAdd(P.rank + r, c);
+                // order-preserving float → uint, high word; low word = ~index so the lowest index wins ties
+                unsigned u = __float_as_uint(bv);
+                u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+                const unsigned long long packed = ((unsigned long long)u << 32) | (unsigned)(0x7fffffff - bi);
+                atomicMax(P.best + r, packed);
+            }
+        }
+    }
+}
+
+// Merge the per-split sorted lists of a row (splits ascend in column index, so ties keep the lower index).
+__global__ void __launch_bounds__(256)
+k_topk_merge(const float* __restrict__ part_val, const int* __restrict__ part_idx, int n1, int splits, int k,
+             float* __restrict__ out_val, int* __restrict__ out_idx, float* __restrict__ out_mean) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= n1) return;
+    float lv = -FLT_MAX; int li = -1;
+    const size_t base = (size_t)row * splits * k;
+    if (lane < k) { lv = part_val[base + lane]; li = part_idx[base + lane]; }
+    for (int s = 1; s < splits; ++s) {
+        float tau = __shfl_sync(OEA_FULL, lv, k - 1);
+        for (int m = 0; m < k; ++m) {
+            const float cv = part_val[base + (size_t)s * k + m];
+            const int ci = part_idx[base + (size_t)s * k + m];
+            if (!(cv > tau)) break;  // lists are sorted descending
+            const int pos = __popc(__ballot_sync(OEA_FULL, lane < k && lv >= cv));
+            const float up_v = __shfl_up_sync(OEA_FULL, lv, 1);
+            const int up_i = __shfl_up_sync(OEA_FULL, li, 1);
+            if (lane > pos) { lv = up_v; li = up_i; }
+            else if (lane == pos) { lv = cv; li = ci; }
+            tau = __shfl_sync(OEA_FULL, lv, k - 1);
+        }
+    }
+    if (lane < k) {
+        if (out_val) out_val[(size_t)row * k + lane] = lv;
+        if (out_idx) out_idx[(size_t)row * k + lane] = li;
+    }
+    if (out_mean) {  // np.mean over the k nearest values (similarity.py:80-83)
+        float s = lane < k ? lv : 0.f;
+        s = warp_sum(s);
+        if (lane == 0) out_mean[row] = s / (float)k;
+    }
+}
+
+// Similarity of row i with its gold column, bit-identical to the tile kernel's accumulation order.
+template <int METRIC>
+__global__ void k_sim_gold(const float* __restrict__ e1, const float* __restrict__ e2, int n1, int pitch1, int pitch2,
+                           int kdim, const int* __restrict__ gold, const float* __restrict__ row_off,
+                           const float* __restrict__ col_off, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n1) return;
+    const int g = gold[i];
+    const float* a = e1 + (size_t)i * pitch1;
+    const float* b = e2 + (size_t)g * pitch2;
+    float acc = 0.f;
+    for (int k = 0; k < kdim; ++k) acc = sim_accum<METRIC>(__ldg(a + k), __ldg(b + k), acc);
+    float v = sim_value<METRIC>(acc);
+    if (row_off) v = csls_value(v, row_off[i], col_off[g]);
+    out[i] = v;
+}
+
+__global__ void k_rank_finish(const unsigned long long* __restrict__ best, int n1, int* __restrict__ top1) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n1) top1[i] = 0x7fffffff - (int)(best[i] & 0xffffffffu);
+}
+
+// sklearn.preprocessing.normalize(x) (similarity.py:30-32): x / ||x||₂, zero rows stay zero.
+__global__ void __launch_bounds__(256)
+k_rows_normalize(const float* __restrict__ in, int in_pitch, int n, int dim, float* __restrict__ out, int out_pitch) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= n) return;
+    const float* src = in + (size_t)row * in_pitch;
+    float ss = 0.f;
+    for (int c = lane; c < dim; c += 32) { const float x = src[c]; ss = fmaf(x, x, ss); }
+    ss = warp_sum(ss);
+    const float inv = ss > 0.f ? 1.f / sqrtf(ss) : 0.f;
+    float* dst = out + (size_t)row * out_pitch;
+    for (int c = lane; c < out_pitch; c += 32) dst[c] = c < dim ? src[c] * inv : 0.f;
+}
+
+static size_t sim_smem_bytes(int epi) {
+    size_t f = 2 * BK * TM + 2 * BK * TN;
+    if (epi == EPI_TOPK) f += TM * (TN + 1) + 2 * TM * KMAX;
+    return f * sizeof(float);
+}
+
+static int check_sim(const oea_sim_cfg* c, const float* e1, const float* e2) {
+    if (!c || !e1 || !e2) return OEA_ERR_NULL;
+    if (c->n1 <= 0 || c->n2 <= 0 || c->dim <= 0) return OEA_ERR_DIM;
+    if (c->pitch1 < c->dim || c->pitch2 < c->dim || (c->pitch1 & 3) || (c->pitch2 & 3)) return OEA_ERR_DIM;
+    if (!aligned16(e1) || !aligned16(e2)) return OEA_ERR_ALIGN;
+    if (c->metric < OEA_METRIC_INNER || c->metric > OEA_METRIC_L2) return OEA_ERR_KIND;
+    return OEA_OK;
+}
+
+static int sm_count() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+    }
+    return sms;
+}
+
+template <int EPI>
+static int launch_sim(const oea_sim_cfg* c, SimParams& P, int splits, cudaStream_t st) {
+    const dim3 grid((c->n1 + TM - 1) / TM, splits);
+    const size_t smem = sim_smem_bytes(EPI);
+#define OEA_SIM_LAUNCH(M)                                                                                     \
+    do {                                                                                                      \
+        OEA_CUDA_TRY(cudaFuncSetAttribute(k_sim_tile<M, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_sim_tile<M, EPI><<<grid, SIM_THREADS, smem, st>>>(P);                                               \
+    } while (0)
+    switch (c->metric) {
+        case OEA_METRIC_INNER: OEA_SIM_LAUNCH(OEA_METRIC_INNER); break;
+        case OEA_METRIC_L1: OEA_SIM_LAUNCH(OEA_METRIC_L1); break;
+        default: OEA_SIM_LAUNCH(OEA_METRIC_L2); break;
+    }
+#undef OEA_SIM_LAUNCH
+    OEA_LAUNCH_CHECK();
+    return OEA_OK;
+}
+
+static int pick_splits(int n1, int n2) {
+    const int row_blocks = (n1 + TM - 1) / TM, col_tiles = (n2 + TN - 1) / TN;
+    int splits = (2 * sm_count() + row_blocks - 1) / row_blocks;   // aim at >= 2 CTAs per SM
+    if (splits > col_tiles) splits = col_tiles;
+    if (splits < 1) splits = 1;
+    if (splits > 64) splits = 64;
+    return splits;
+}
+
+static void fill_common(SimParams& P, const oea_sim_cfg* c, const float* e1, const float* e2,
+                        const float* row_off, const float* col_off, int splits) {
+    P.e1 = e1; P.e2 = e2; P.n1 = c->n1; P.n2 = c->n2; P.pitch1 = c->pitch1; P.pitch2 = c->pitch2;
+    P.kdim = c->pitch1 < c->pitch2 ? c->pitch1 : c->pitch2;   // padding columns are zero on both sides
+    P.row_off = row_off; P.col_off = col_off;
+    const int col_tiles = (c->n2 + TN - 1) / TN;
+    P.col_tiles_per_split = (col_tiles + splits - 1) / splits;
+    P.splits = splits;
+}
+
+}  // namespace oea
+
+using namespace oea;
+
+extern "C" size_t oea_sim_topk_workspace_bytes(const oea_sim_cfg* c, int32_t k) {
+    if (!c || k < 1 || k > KMAX) return 0;
+    const int splits = pick_splits(c->n1, c->n2);
+    return (size_t)c->n1 * splits * k * (sizeof(float) + sizeof(int));
+}
+
+extern "C" int oea_sim_topk(const oea_sim_cfg* c, const float* e1, const float* e2,
+                            const float* row_off, const float* col_off, int32_t k,
+                            float* out_val, int32_t* out_idx, float* out_mean,
+                            void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = check_sim(c, e1, e2); if (rc) return rc;
+    if (k < 1 || k > KMAX || k > c->n2) return OEA_ERR_RANGE;
+    if ((row_off == nullptr) != (col_off == nullptr)) return OEA_ERR_NULL;
+    if (!out_val && !out_idx && !out_mean) return OEA_ERR_NULL;
+    const int splits = pick_splits(c->n1, c->n2);
+    const size_t need = (size_t)c->n1 * splits * k * (sizeof(float) + sizeof(int));
+    if (!workspace || workspace_bytes < need) return OEA_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    SimParams P{};
+    fill_common(P, c, e1, e2, row_off, col_off, splits);
+    // splits that start past the last column tile would leave garbage: recompute the effective count
+    const int col_tiles = (c->n2 + TN - 1) / TN;
+    const int eff_splits = (col_tiles + P.col_tiles_per_split - 1) / P.col_tiles_per_split;
+    P.splits = eff_splits;
+    P.k = k;
+    P.part_val = (float*)workspace;
+    P.part_idx = (int*)((char*)workspace + (size_t)c->n1 * splits * k * sizeof(float));
+    rc = launch_sim<EPI_TOPK>(c, P, eff_splits, st); if (rc) return rc;
+    k_topk_merge<<<(c->n1 + 7) / 8, 256, 0, st>>>(P.part_val, P.part_idx, c->n1, eff_splits, k, out_val, out_idx, out_mean);
+    OEA_LAUNCH_CHECK();
+    return OEA_OK;
+}
+
+extern "C" size_t oea_sim_rank_workspace_bytes(const oea_sim_cfg* c) {
+    if (!c) return 0;
+    return (size_t)c->n1 * (sizeof(unsigned long long) + sizeof(float));
+}
+
+extern "C" int oea_sim_rank(const oea_sim_cfg* c, const float* e1, const float* e2,
+                            const float* row_off, const float* col_off, const int32_t* gold,
+                            int32_t* out_top1, int32_t* out_rank,
+                            void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = check_sim(c, e1, e2); if (rc) return rc;
+    if (!gold || !out_top1 || !out_rank) return OEA_ERR_NULL;
+    if ((row_off == nullptr) != (col_off == nullptr)) return OEA_ERR_NULL;
+    const size_t need = oea_sim_rank_workspace_bytes(c);
+    if (!workspace || workspace_bytes < need) return OEA_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long* best = (unsigned long long*)workspace;
+    float* gold_val = (float*)((char*)workspace + (size_t)c->n1 * sizeof(unsigned long long));
+    OEA_CUDA_TRY(cudaMemsetAsync(best, 0, (size_t)c->n1 * sizeof(unsigned long long), st));
+    OEA_CUDA_TRY(cudaMemsetAsync(out_rank, 0, (size_t)c->n1 * sizeof(int), st));
+    const int splits = pick_splits(c->n1, c->n2);
+    SimParams P{};
+    fill_common(P, c, e1, e2, row_off, col_off, splits);
+    const int col_tiles = (c->n2 + TN - 1) / TN;
+    const int eff_splits = (col_tiles + P.col_tiles_per_split - 1) / P.col_tiles_per_split;
+    P.splits = eff_splits;
+    const int gb = (c->n1 + 127) / 128;
+    switch (c->metric) {
+        case OEA_METRIC_INNER: k_sim_gold<OEA_METRIC_INNER><<<gb, 128, 0, st>>>(e1, e2, c->n1, c->pitch1, c->pitch2, P.kdim, gold, row_off, col_off, gold_val); break;
+        case OEA_METRIC_L1: k_sim_gold<OEA_METRIC_L1><<<gb, 128, 0, st>>>(e1, e2, c->n1, c->pitch1, c->pitch2, P.kdim, gold, row_off, col_off, gold_val); break;
+        default: k_sim_gold<OEA_METRIC_L2><<<gb, 128, 0, st>>>(e1, e2, c->n1, c->pitch1, c->pitch2, P.kdim, gold, row_off, col_off, gold_val); break;
+    }
+    OEA_LAUNCH_CHECK();
+    P.gold = gold; P.gold_val = gold_val; P.best = best; P.rank = out_rank;
+    rc = launch_sim<EPI_RANK>(c, P, eff_splits, st); if (rc) return rc;
+    k_rank_finish<<<gb, 128, 0, st>>>(best, c->n1, out_top1);
+    OEA_LAUNCH_CHECK();
+    return OEA_OK;
+}
+
+extern "C" int oea_sim_matrix(const oea_sim_cfg* c, const float* e1, const float* e2,
+                              const float* row_off, const float* col_off, float* out, int64_t ld_out, void* stream) {
+    int rc = check_sim(c, e1, e2); if (rc) return rc;
+    if (!out) return OEA_ERR_NULL;
+    if (ld_out < c->n2) return OEA_ERR_SHAPE;
+    if ((row_off == nullptr) != (col_off == nullptr)) return OEA_ERR_NULL;
+    SimParams P{};
+    const int col_tiles = (c->n2 + TN - 1) / TN;
+    int splits = pick_splits(c->n1, c->n2);
+    fill_common(P, c, e1, e2, row_off, col_off, splits);
+    const int eff_splits = (col_tiles + P.col_tiles_per_split - 1) / P.col_tiles_per_split;
+    P.out = out; P.ld_out = ld_out;
+    return launch_sim<EPI_STORE>(c, P, eff_splits, (cudaStream_t)stream);
+}
+
+extern "C" int oea_rows_normalize(const float* in, int32_t in_pitch, int32_t n, int32_t dim, float* out, int32_t out_pitch,
+                                  void* stream) {
+    if (!in || !out) return OEA_ERR_NULL;
+    if (n < 0 || dim <= 0 || in_pitch < dim || out_pitch < dim) return OEA_ERR_DIM;
+    if (n == 0) return OEA_OK;
+    k_rows_normalize<<<(n + 7) / 8, 256, 0, (cudaStream_t)stream>>>(in, in_pitch, n, dim, out, out_pitch);
+    OEA_LAUNCH_CHECK();
+    return OEA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Large-k per-row selection (ε-truncated neighbour search): 3-pass MSB radix select (11+11+10 bits)
+// on the order-preserving integer image of the floats, then one compaction pass.  One CTA per row;
+// passes 2-4 re-read the row from L2.
+// ------------------------------------------------------------------------------------------------
+namespace oea {
+
+__device__ __forceinline__ unsigned fkey(float f) {
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+constexpr int SEL_THREADS = 512;
+constexpr int SEL_BINS = 2048;
+
+__global__ void __launch_bounds__(SEL_THREADS)
+k_rows_select(const float* __restrict__ mat, long long ld, int n_rows, int n_cols, int k,
+              const int32_t* __restrict__ col_ids, int32_t* __restrict__ out) {
+    __shared__ unsigned hist[SEL_BINS];
+    __shared__ unsigned s_chunk[32];
+    __shared__ unsigned s_prefix, s_mask, s_remaining, s_gt, s_eq;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int row = blockIdx.x; row < n_rows; row += gridDim.x) {
+        const float* src = mat + (size_t)row * ld;
+        if (tid == 0) { s_prefix = 0u; s_mask = 0u; s_remaining = (unsigned)k; s_gt = 0u; s_eq = 0u; }
+        __syncthreads();
+#pragma unroll 1
+        for (int pass = 0; pass < 3; ++pass) {
+            const int shift = pass == 0 ? 21 : (pass == 1 ? 10 : 0);
+            const int nb = pass == 2 ? 1024 : 2048;
+            for (int i = tid; i < SEL_BINS; i += SEL_THREADS) hist[i] = 0u;
+            __syncthreads();
+            const unsigned prefix = s_prefix, mask = s_mask;
+            for (int j = tid; j < n_cols; j += SEL_THREADS) {
+                const unsigned u = fkey(__ldg(src + j));
+                if ((u & mask) == prefix) atomicAdd(&hist[(u >> shift) & (unsigned)(nb - 1)], 1u);
+            }
+            __syncthreads();
+            // suffix search from the top bin: find digit D with count(> D) < remaining <= count(>= D)
+            if (warp == 0) {
+                const int per = nb / 32;
+                unsigned csum = 0;
+                for (int b = 0; b < per; ++b) csum += hist[lane * per + b];
+                s_chunk[lane] = csum;
+                __syncwarp();
+                unsigned above = 0;  // elements in chunks above this lane's chunk
+                for (int l = lane + 1; l < 32; ++l) above += s_chunk[l];
+                const unsigned remaining = s_remaining;
+                const bool mine = above < remaining && above + csum >= remaining;
+                if (mine) {
+                    unsigned acc = above;
+                    for (int b = per - 1; b >= 0; --b) {
+                        const unsigned h = hist[lane * per + b];
+                        if (acc + h >= remaining) {
+                            s_prefix = prefix | ((unsigned)(lane * per + b) << shift);
+                            s_mask = mask | ((unsigned)(nb - 1) << shift);
+                            s_remaining = remaining - acc;
+                            break;
+                        }
+                        acc += h;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        const unsigned T = s_prefix, take_eq = s_remaining;
+        const unsigned n_gt = (unsigned)k - take_eq;
+        int32_t* dst = out + (size_t)row * k;
+        for (int j = tid; j < n_cols; j += SEL_THREADS) {
+            const unsigned u = fkey(__ldg(src + j));
+            if (u > T) {
+                const unsigned p = atomicAdd(&s_gt, 1u);
+                dst[p] = col_ids ? __ldg(col_ids + j) : j;
+            } else if (u == T) {
+                const unsigned e = atomicAdd(&s_eq, 1u);
+                if (e < take_eq) dst[n_gt + e] = col_ids ? __ldg(col_ids + j) : j;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace oea
+
+extern "C" int oea_rows_select_topk(const float* mat, int64_t ld, int32_t n_rows, int32_t n_cols, int32_t k,
+                                    const int32_t* col_ids, int32_t* out_idx, void* stream) {
+    if (!mat || !out_idx) return OEA_ERR_NULL;
+    if (n_rows < 0 || n_cols <= 0 || ld < n_cols) return OEA_ERR_SHAPE;
+    if (k < 1 || k > n_cols) return OEA_ERR_RANGE;
+    if (n_rows == 0) return OEA_OK;
+    const int grid = n_rows < 4 * sm_count() ? n_rows : 4 * sm_count();
+    k_rows_select<<<grid, SEL_THREADS, 0, (cudaStream_t)stream>>>(mat, ld, n_rows, n_cols, k, col_ids, out_idx);
+    OEA_LAUNCH_CHECK();
+    return OEA_OK;
+}

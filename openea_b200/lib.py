@@ -73,6 +73,13 @@ SIGNATURES = {
     "oea_triple_step_fed_host": (C.c_int, [_TP, _TP, _P, _I, _P, _I, C.POINTER(LossCfg), C.POINTER(OptCfg),
                                            _P, _P, _P, C.POINTER(C.c_float), _P]),
     "oea_table_lookup": (C.c_int, [_TP, _P, _I, _P, _I, _P]),
+    "oea_sim_topk_workspace_bytes": (C.c_size_t, [C.POINTER(SimCfg), _I]),
+    "oea_sim_topk": (C.c_int, [C.POINTER(SimCfg), _P, _P, _P, _P, _I, _P, _P, _P, _P, C.c_size_t, _P]),
+    "oea_sim_rank_workspace_bytes": (C.c_size_t, [C.POINTER(SimCfg)]),
+    "oea_sim_rank": (C.c_int, [C.POINTER(SimCfg), _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "oea_sim_matrix": (C.c_int, [C.POINTER(SimCfg), _P, _P, _P, _P, _P, _L, _P]),
+    "oea_rows_normalize": (C.c_int, [_P, _I, _I, _I, _P, _I, _P]),
+    "oea_rows_select_topk": (C.c_int, [_P, _L, _I, _I, _I, _P, _P, _P]),
     "oea_tripleset_build": (C.c_int, [_P, _I, _P, C.c_uint32, C.c_uint32, C.c_uint32, _P]),
 }
 
