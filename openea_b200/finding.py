@@ -1,0 +1,191 @@
+"""Host side of path (iii): similarity / CSLS / top-k / rank / neighbour search through liboea.so.
+
+Mirrors the call signatures of the reference's modules/finding/{similarity,alignment}.py and
+modules/train/batch.py:145-165 but keeps everything on the device; inputs may be NumPy arrays (reference
+API) or CUDA tensors (internal fast path: no host round trip).  No fallback to NumPy/torch maths.
+"""
+import ctypes as C
+import time
+
+import numpy as np
+import torch
+
+from . import lib as L
+from .engine import _ptr, _stream_ptr, pitch_for
+
+_METRICS = {"inner": L.METRIC_INNER, "cosine": L.METRIC_INNER, "euclidean": L.METRIC_L2, "manhattan": L.METRIC_L1}
+
+
+def _device():
+    if not torch.cuda.is_available():
+        raise L.OeaError("openea_b200.finding needs a CUDA device (no CPU fallback)")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def to_device_rows(x, normalize=False):
+    """→ float32 CUDA tensor [n, pitch] with zero padding (pitch % 4 == 0); optional sklearn-style row normalise."""
+    lib = L.load()
+    dev = _device()
+    t = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.float32)))
+    t = t.to(device=dev, dtype=torch.float32)
+    n, d = t.shape
+    p = pitch_for(d)
+    if not normalize and p == d and t.is_contiguous():
+        return t, d
+    out = torch.zeros(n, p, dtype=torch.float32, device=dev)
+    if normalize:
+        t = t.contiguous()
+        L.check(lib.oea_rows_normalize(_ptr(t), d, n, d, _ptr(out), p, _stream_ptr()), "oea_rows_normalize")
+    else:
+        out[:, :d] = t
+    return out, d
+
+
+def _cfg(metric, e1, e2, d):
+    if metric not in _METRICS:
+        raise ValueError("metric %r is not supported by the B200 engine (inner/cosine/euclidean/manhattan)" % (metric,))
+    return L.SimCfg(_METRICS[metric], e1.shape[0], e2.shape[0], d, e1.shape[1], e2.shape[1])
+
+
+def _prep_pair(embed1, embed2, metric, normalize):
+    # 'cosine' without normalize is 1 − cosine distance = cosine similarity: normalise, then inner product
+    norm = bool(normalize) or metric == "cosine"
+    e1, d = to_device_rows(embed1, norm)
+    e2, d2 = to_device_rows(embed2, norm)
+    assert d == d2, "embedding dimensions differ"
+    return e1, e2, d
+
+
+def topk(e1, e2, d, metric, k, row_off=None, col_off=None, want=("val", "idx", "mean")):
+    """Per-row top-k of S (or CSLS S' when offsets are given) of prepared device rows → dict of tensors."""
+    lib = L.load()
+    cfg = _cfg(metric, e1, e2, d)
+    n1 = e1.shape[0]
+    dev = e1.device
+    ws_bytes = lib.oea_sim_topk_workspace_bytes(C.byref(cfg), k)
+    ws = torch.empty(max(1, ws_bytes), dtype=torch.uint8, device=dev)
+    out = {}
+    val = torch.empty(n1, k, dtype=torch.float32, device=dev) if "val" in want else None
+    idx = torch.empty(n1, k, dtype=torch.int32, device=dev) if "idx" in want else None
+    mean = torch.empty(n1, dtype=torch.float32, device=dev) if "mean" in want else None
+    L.check(lib.oea_sim_topk(C.byref(cfg), _ptr(e1), _ptr(e2), _ptr(row_off), _ptr(col_off), k,
+                             _ptr(val), _ptr(idx), _ptr(mean), _ptr(ws), ws_bytes, _stream_ptr()), "oea_sim_topk")
+    out["val"], out["idx"], out["mean"] = val, idx, mean
+    return out
+
+
+def csls_offsets(e1, e2, d, metric, k):
+    """r_i = mean of the k nearest of row i, c_j = mean of the k nearest of column j (similarity.py:73-83)."""
+    r = topk(e1, e2, d, metric, k, want=("mean",))["mean"]
+    c = topk(e2, e1, d, metric, k, want=("mean",))["mean"]
+    return r, c
+
+
+def rank(e1, e2, d, metric, gold, row_off=None, col_off=None):
+    """(argmax column, 0-based rank of gold[i]) per row → two int32 CUDA tensors."""
+    lib = L.load()
+    cfg = _cfg(metric, e1, e2, d)
+    n1, dev = e1.shape[0], e1.device
+    gold_t = torch.as_tensor(gold, dtype=torch.int32, device=dev).contiguous()
+    ws_bytes = lib.oea_sim_rank_workspace_bytes(C.byref(cfg))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    top1 = torch.empty(n1, dtype=torch.int32, device=dev)
+    rk = torch.empty(n1, dtype=torch.int32, device=dev)
+    L.check(lib.oea_sim_rank(C.byref(cfg), _ptr(e1), _ptr(e2), _ptr(row_off), _ptr(col_off), _ptr(gold_t),
+                             _ptr(top1), _ptr(rk), _ptr(ws), ws_bytes, _stream_ptr()), "oea_sim_rank")
+    return top1, rk
+
+
+def sim_matrix(e1, e2, d, metric, row_off=None, col_off=None, out=None):
+    lib = L.load()
+    cfg = _cfg(metric, e1, e2, d)
+    if out is None:
+        out = torch.empty(e1.shape[0], e2.shape[0], dtype=torch.float32, device=e1.device)
+    L.check(lib.oea_sim_matrix(C.byref(cfg), _ptr(e1), _ptr(e2), _ptr(row_off), _ptr(col_off), _ptr(out),
+                               out.stride(0), _stream_ptr()), "oea_sim_matrix")
+    return out
+
+
+def sim(embed1, embed2, metric="inner", normalize=False, csls_k=0):
+    """Drop-in for modules/finding/similarity.py:11 `sim` → float32 CUDA tensor [n1, n2]."""
+    e1, e2, d = _prep_pair(embed1, embed2, metric, normalize)
+    r = c = None
+    if csls_k > 0:
+        r, c = csls_offsets(e1, e2, d, metric, csls_k)
+    return sim_matrix(e1, e2, d, metric, r, c)
+
+
+def eval_alignment(embed1, embed2, top_k, metric, normalize, csls_k, gold=None):
+    """The numeric core of greedy_alignment: returns (top1 idx tensor, rank tensor, hits list, mr, mrr)."""
+    e1, e2, d = _prep_pair(embed1, embed2, metric, normalize)
+    n1 = e1.shape[0]
+    r = c = None
+    if csls_k > 0:
+        r, c = csls_offsets(e1, e2, d, metric, csls_k)
+    if gold is None:
+        gold = torch.arange(n1, dtype=torch.int32, device=e1.device)   # alignment.py:153: gold of row i is i
+    top1, rk = rank(e1, e2, d, metric, gold, r, c)
+    rk64 = rk.to(torch.float64)
+    hits = [round(float((rk < k).sum().item()) / n1 * 100, 3) for k in top_k]
+    mr = float((rk64 + 1).sum().item() / n1)
+    mrr = float((1.0 / (rk64 + 1)).sum().item() / n1)
+    return top1, rk, hits, mr, mrr
+
+
+def greedy_alignment(embed1, embed2, top_k, nums_threads, metric, normalize, csls_k, accurate):
+    """Drop-in for modules/finding/alignment.py:13.  `nums_threads` is accepted and ignored (one GPU pass).
+    Quick mode (accurate=False) computes the same exact ranks; only the printed line differs."""
+    t = time.time()
+    top1, _, hits, mr, mrr = eval_alignment(embed1, embed2, top_k, metric, normalize, csls_k)
+    top1_h = top1.cpu().numpy()
+    alignment_rest = set(zip(range(len(top1_h)), top1_h.tolist()))
+    hits_arr = np.array(hits)
+    cost = time.time() - t
+    if accurate:
+        if csls_k > 0:
+            print("accurate results with csls: csls={}, hits@{} = {}%, mr = {:.3f}, mrr = {:.6f}, time = {:.3f} s ".
+                  format(csls_k, top_k, hits_arr, mr, mrr, cost))
+        else:
+            print("accurate results: hits@{} = {}%, mr = {:.3f}, mrr = {:.6f}, time = {:.3f} s ".
+                  format(top_k, hits_arr, mr, mrr, cost))
+    else:
+        if csls_k > 0:
+            print("quick results with csls: csls={}, hits@{} = {}%, time = {:.3f} s ".format(csls_k, top_k, hits_arr, cost))
+        else:
+            print("quick results: hits@{} = {}%, time = {:.3f} s ".format(top_k, hits_arr, cost))
+    return alignment_rest, hits_arr[0], mr, mrr
+
+
+def find_neighbours_device(embeds, entity_list, k, row_block=8192):
+    """ε-truncated neighbour search (batch.py:145-165) on device: for every row of `embeds` the k entities of
+    `entity_list` with the largest inner product → int32 CUDA tensor [n, k] of ENTITY IDS (set semantics)."""
+    lib = L.load()
+    e, d = to_device_rows(embeds, False)
+    n = e.shape[0]
+    dev = e.device
+    ids = torch.as_tensor(np.asarray(entity_list, dtype=np.int32) if not isinstance(entity_list, torch.Tensor) else entity_list,
+                          dtype=torch.int32, device=dev).contiguous()
+    assert ids.numel() == n
+    out = torch.empty(n, k, dtype=torch.int32, device=dev)
+    rb = min(n, row_block)
+    ld = (n + 3) // 4 * 4
+    buf = torch.empty(rb, ld, dtype=torch.float32, device=dev)
+    for r0 in range(0, n, rb):
+        r1 = min(n, r0 + rb)
+        sub = e[r0:r1]
+        cfg = L.SimCfg(L.METRIC_INNER, r1 - r0, n, d, e.shape[1], e.shape[1])
+        L.check(lib.oea_sim_matrix(C.byref(cfg), _ptr(sub), _ptr(e), None, None, _ptr(buf), ld, _stream_ptr()),
+                "oea_sim_matrix")
+        L.check(lib.oea_rows_select_topk(_ptr(buf), ld, r1 - r0, n, k, _ptr(ids), _ptr(out[r0:r1]), _stream_ptr()),
+                "oea_rows_select_topk")
+    return out
+
+
+def find_alignment_device(embed1, embed2, sim_th, k, metric="inner", normalize=True):
+    """Bootstrapping candidate pairs (alignment_finder.py:28-51): {(i,j): S_ij > th} ∩ {j in top-k of row i}.
+    Returns (rows, cols, vals) CUDA tensors of the surviving pairs."""
+    e1, e2, d = _prep_pair(embed1, embed2, metric, normalize)
+    res = topk(e1, e2, d, metric, k, want=("val", "idx"))
+    keep = res["val"] > sim_th
+    rows = torch.arange(e1.shape[0], device=e1.device, dtype=torch.int32)[:, None].expand_as(keep)[keep]
+    return rows, res["idx"][keep], res["val"][keep]
