@@ -102,7 +102,7 @@ typedef struct oea_tripleset {
 
 typedef struct oea_sample_cfg {
     int32_t  batch_size;      /* args.batch_size: positives per step over both KGs */
-    int32_t  neg_per_pos;     /* args.neg_triple_num (1..32) */
+    int32_t  neg_per_pos;     /* args.neg_triple_num (0..32) */
     int32_t  step;            /* step index inside the epoch */
     int32_t  max_try;         /* batch.py:89 max_try (10) */
     uint64_t epoch_seed;      /* permutation + sampling seed of this epoch */
@@ -137,7 +137,7 @@ int oea_rowopt_apply(const oea_table* table, const oea_opt_cfg* opt, void* strea
  * negatives corrupt head or tail (one Bernoulli(.5) per try for all missing negatives),
  * candidates = ε-truncated list of the corrupted entity or the KG's entity list, sampled without
  * replacement inside a try, rejected when in `tset`, last try accepts unfiltered (batch.py:89-119).
- * Only OEA_LOSS_LIMITED / OEA_LOSS_LOGISTIC are valid here.
+ * neg_per_pos: >= 1 for LIMITED / LOGISTIC, exactly 1 for MARGIN (pairs), 0 for POSITIVE / LOGSIGMOID.
  * dbg_neg: optional [batch_size, 2 + neg_per_pos] int32 dump (triple index, side bitmask, sampled
  * entities) so a test can replay the identical batch through the fed path / the oracle.
  * n_pos_out (device int32, optional) receives the number of positives actually in this step. */
@@ -168,6 +168,30 @@ int oea_table_lookup(const oea_table* table, const int32_t* ids, int32_t n, floa
  * `relation_triples_set` handed to batch.py:36 (modules/load/kg.py:63). */
 int oea_tripleset_build(const int32_t* triples, int32_t n, uint64_t* slots, uint32_t capacity,
                         uint32_t ent_bits, uint32_t rel_bits, void* stream);
+
+/* Backward of oea_table_lookup: grad_rows [n, grad_pitch] = d loss / d (normalised row i); pushes it through
+ * the l2_normalize Jacobian of row ids[i] and scatter-adds into table->grad (sets touched).  Together with
+ * oea_table_lookup this is tf.nn.embedding_lookup(l2_normalize(var), ids) + its gradient for arbitrary
+ * graphs (e.g. modules/base/mapping.py:14-15). */
+int oea_table_scatter_grad(const oea_table* table, const int32_t* ids, int32_t n, const float* grad_rows,
+                           int32_t grad_pitch, void* stream);
+
+/* modules/base/losses.py on already-gathered rows [n, pitch]: margin_loss:15, positive_loss:30,
+ * limited_loss:42, logistic_loss:59 (+ bootea.py:197).  Adds the loss to *loss_out and writes d loss /
+ * d row for all six inputs (the tensor-in → scalar-out API of get_loss_func, losses.py:4). */
+int oea_loss_rows(const float* ph, const float* pr, const float* pt, int32_t n_pos,
+                  const float* nh, const float* nr, const float* nt, int32_t n_neg,
+                  int32_t dim, int32_t pitch, const oea_loss_cfg* loss, double* loss_out,
+                  float* g_ph, float* g_pr, float* g_pt, float* g_nh, float* g_nr, float* g_nt, void* stream);
+
+/* mapping_loss (modules/base/losses.py:76-80) forward+backward: alpha·(Σ‖e2 − e1·M‖² + Σ(M·Mᵀ − I)²)
+ * (alpha = args.alpha of mapping.py:17).  e1/e2 [n, pitch]; M [dim, mpitch].  Adds the loss to
+ * *loss_out, writes g_e1 / g_e2 [n, pitch] and ADDS into g_M [dim, mpitch]. */
+size_t oea_mapping_workspace_bytes(int32_t dim);
+int oea_mapping_fwd_bwd(const float* e1, const float* e2, int32_t n, int32_t dim, int32_t pitch,
+                        const float* M, int32_t mpitch, float alpha, double* loss_out,
+                        float* g_e1, float* g_e2, float* g_M, void* workspace, size_t workspace_bytes,
+                        void* stream);
 
 /* ---- path (iii): all-pairs similarity, CSLS, top-k, rank ----------------------------------- */
 
@@ -218,6 +242,36 @@ int oea_rows_normalize(const float* in, int32_t in_pitch, int32_t n, int32_t dim
  * out_idx [n_rows, k] = col_ids[column] (col_ids == NULL → the column index itself). */
 int oea_rows_select_topk(const float* mat, int64_t ld, int32_t n_rows, int32_t n_cols, int32_t k,
                          const int32_t* col_ids, int32_t* out_idx, void* stream);
+
+/* ---- path (ii): sparse adjacency × dense embeddings (GCN-Align / AliNet / RDGCN aggregation) -------- */
+
+/* CSR matrix: int32 column indices, fp32 values (the tf.SparseTensor supports of gcn_align.py:575-578). */
+typedef struct oea_csr {
+    const int32_t* rowptr;   /* [n_rows + 1] */
+    const int32_t* col;      /* [nnz] */
+    const float*   val;      /* [nnz] */
+    int32_t        n_rows, n_cols;
+    int64_t        nnz;
+} oea_csr;
+
+/* Y[n_rows, d] = A · X[n_cols, d] (+ beta·Y), optional fused epilogues: relu (the `act` of GraphConvolution,
+ * gcn_align.py:259-267) or masking by mask_src > 0 (relu backward).  Replaces tf.sparse_tensor_dense_matmul
+ * (gcn_align.py:83, alinet.py:581, rdgcn.py:187).  d % 4 == 0, d <= 512.  long_rows lists the rows with more
+ * than oea_spmm_long_row_threshold() non-zeros (hub entities); they are processed by a whole CTA each.
+ * The backward pass is the same call on the CSR of Aᵀ. */
+int oea_spmm_long_row_threshold(void);
+int oea_spmm_csr(const oea_csr* A, const int32_t* long_rows, int32_t n_long,
+                 const float* X, int32_t ldx, float* Y, int32_t ldy, int32_t d,
+                 int32_t relu, const float* mask_src, float beta, void* stream);
+
+/* align_loss (approaches/gcn_align.py:298-320; rdgcn.py:293-315 has the same form): L1 margin loss over t
+ * seed pairs with k negatives per side, mean over 2·k·t, forward + backward.  x [N, ld] are the output
+ * embeddings; neg_left/neg_right/neg2_left/neg2_right are [t·k] row ids; *loss_out += loss;
+ * grad [N, ld] += d loss / d x (caller zeroes it). */
+int oea_align_loss_l1(const float* x, int32_t ld, int32_t dim, const int32_t* left, const int32_t* right, int32_t t,
+                      int32_t k, const int32_t* neg_left, const int32_t* neg_right,
+                      const int32_t* neg2_left, const int32_t* neg2_right, float gamma,
+                      double* loss_out, float* grad, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,30 @@
+from openea_b200.approaches.aligne import AlignE
+from openea_b200.approaches.bootea import BootEA
+from openea_b200.approaches.mtranse import MTransE
+from openea_b200.models._stubs import out_of_scope
+
+try:
+    from openea_b200.approaches.gcn_align import GCN_Align
+except ImportError:  # pragma: no cover - file lands later in the build plan
+    GCN_Align = out_of_scope("GCN_Align", "not built yet")
+try:
+    from openea_b200.approaches.alinet import AliNet
+except ImportError:  # pragma: no cover
+    AliNet = out_of_scope("AliNet", "not built yet")
+try:
+    from openea_b200.approaches.rdgcn import RDGCN
+except ImportError:  # pragma: no cover
+    RDGCN = out_of_scope("RDGCN", "not built yet")
+
+JAPE = out_of_scope("JAPE", "attribute skip-gram encoder")
+Attr2Vec = out_of_scope("Attr2Vec", "attribute skip-gram encoder")
+IPTransE = out_of_scope("IPTransE", "path-based TransE with soft alignment")
+AttrE = out_of_scope("AttrE", "character-level literal encoder")
+IMUSE = out_of_scope("IMUSE", "string-similarity preprocessing")
+SEA = out_of_scope("SEA", "adversarial degree-aware training")
+RSN4EA = out_of_scope("RSN4EA", "recurrent skipping network over paths")
+MultiKE = out_of_scope("MultiKE", "multi-view literal/attribute encoders")
+GMNN = out_of_scope("GMNN", "graph matching network")
+KDCoE = out_of_scope("KDCoE", "description encoder co-training")
+BootEA_RotatE = out_of_scope("BootEA_RotatE", "float64 complex rotation score")
+BootEA_TransH = out_of_scope("BootEA_TransH", "hyperplane projection score ('next' K1 variant)")

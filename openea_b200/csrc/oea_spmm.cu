@@ -1,0 +1,235 @@
+// oea_spmm.cu — path (ii): sparse-adjacency × dense-embedding neighbour aggregation (K2) and the
+// L1 margin alignment loss of the GNN approaches.  sm_100a.
+//
+// Restates (no code shared):
+//   approaches/gcn_align.py:79-86,239-267   dot(sparse) = tf.sparse_tensor_dense_matmul ; GraphConvolution
+//   approaches/gcn_align.py:298-320         align_loss (L1 margin over seed pairs, k negatives per side)
+//   approaches/rdgcn.py:293-315             get_loss (same shape, k negatives per side)
+//
+// SpMM Y = A·X with A in CSR (int32 col, fp32 val): HBM/L2-bound gather of X rows.  Rows with at most
+// LONG_ROW non-zeros are handled one warp per row (col/val fetched 32 at a time, coalesced, and
+// broadcast by shuffle; the X row is read with 128-bit loads); hub rows (Zipf degree) get a whole CTA
+// whose 8 warps split the non-zeros and reduce through shared memory — no atomics, deterministic.
+#include "oea_common.cuh"
+
+namespace oea {
+
+constexpr int SPMM_WARPS = 8;
+constexpr int SPMM_THREADS = SPMM_WARPS * 32;
+constexpr int LONG_ROW = 256;
+
+template <int VEC>
+struct Acc {
+    float4 v[VEC];
+};
+
+template <int VEC>
+__device__ __forceinline__ void acc_zero(Acc<VEC>& a) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) a.v[i] = f4(0.f);
+}
+
+// accumulate val·X[col, :] over the non-zeros [p0, p1) of one row into acc (lane owns float4 columns lane+32i)
+template <int VEC>
+__device__ __forceinline__ void spmm_span(const int32_t* __restrict__ col, const float* __restrict__ val,
+                                          int p0, int p1, const float* __restrict__ X, int ldx, int d4, int lane,
+                                          Acc<VEC>& acc) {
+    for (int base = p0; base < p1; base += 32) {
+        const int p = base + lane;
+        int c = 0; float w = 0.f;
+        if (p < p1) { c = __ldg(col + p); w = __ldg(val + p); }
+        const int cnt = min(32, p1 - base);
+        for (int j = 0; j < cnt; ++j) {
+            const int cj = __shfl_sync(OEA_FULL, c, j);
+            const float wj = __shfl_sync(OEA_FULL, w, j);
+            const float* xr = X + (size_t)cj * ldx;
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                const int q = lane + 32 * i;
+                if (q < d4) acc.v[i] = fma4(ldg4(xr + 4 * q), wj, acc.v[i]);
+            }
+        }
+    }
+}
+
+struct SpmmEpi {
+    int relu;                 // y = max(y, 0)
+    const float* mask_src;    // y = mask_src[row, c] > 0 ? y : 0   (relu backward), same ld as Y
+    float beta;               // y += beta · Y_old
+};
+
+template <int VEC>
+__device__ __forceinline__ void spmm_store(const Acc<VEC>& acc, float* __restrict__ Y, int ldy, int row, int d4, int lane,
+                                           const SpmmEpi& e) {
+    float* yr = Y + (size_t)row * ldy;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        const int q = lane + 32 * i;
+        if (q >= d4) continue;
+        float4 v = acc.v[i];
+        if (e.beta != 0.f) { const float4 o = *reinterpret_cast<const float4*>(yr + 4 * q); v = fma4(o, e.beta, v); }
+        if (e.relu) v = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+        if (e.mask_src) {
+            const float4 m = ldg4(e.mask_src + (size_t)row * ldy + 4 * q);
+            v = make_float4(m.x > 0.f ? v.x : 0.f, m.y > 0.f ? v.y : 0.f, m.z > 0.f ? v.z : 0.f, m.w > 0.f ? v.w : 0.f);
+        }
+        *reinterpret_cast<float4*>(yr + 4 * q) = v;
+    }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(SPMM_THREADS)
+k_spmm_warp_rows(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ val,
+                 int n_rows, const float* __restrict__ X, int ldx, float* __restrict__ Y, int ldy, int d4, SpmmEpi epi) {
+    const int lane = threadIdx.x & 31;
+    const int warp_global = blockIdx.x * SPMM_WARPS + (threadIdx.x >> 5);
+    const int n_warps = gridDim.x * SPMM_WARPS;
+    for (int row = warp_global; row < n_rows; row += n_warps) {
+        const int p0 = __ldg(rowptr + row), p1 = __ldg(rowptr + row + 1);
+        if (p1 - p0 > LONG_ROW) continue;   // a CTA handles it (k_spmm_cta_rows)
+        Acc<VEC> acc;
+        acc_zero(acc);
+        spmm_span<VEC>(col, val, p0, p1, X, ldx, d4, lane, acc);
+        spmm_store<VEC>(acc, Y, ldy, row, d4, lane, epi);
+    }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(SPMM_THREADS)
+k_spmm_cta_rows(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ val,
+                const int32_t* __restrict__ long_rows, int n_long,
+                const float* __restrict__ X, int ldx, float* __restrict__ Y, int ldy, int d4, SpmmEpi epi) {
+    extern __shared__ __align__(16) float red[];   // [SPMM_WARPS][VEC*32] float4
+    float4* red4 = reinterpret_cast<float4*>(red);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int li = blockIdx.x; li < n_long; li += gridDim.x) {
+        const int row = __ldg(long_rows + li);
+        const int p0 = __ldg(rowptr + row), p1 = __ldg(rowptr + row + 1);
+        const int per = ((p1 - p0 + SPMM_WARPS - 1) / SPMM_WARPS + 31) / 32 * 32;
+        const int a = min(p1, p0 + warp * per), b = min(p1, a + per);
+        Acc<VEC> acc;
+        acc_zero(acc);
+        spmm_span<VEC>(col, val, a, b, X, ldx, d4, lane, acc);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) red4[(warp * VEC + i) * 32 + lane] = acc.v[i];
+        __syncthreads();
+        if (warp == 0) {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                float4 s = red4[i * 32 + lane];
+                for (int w = 1; w < SPMM_WARPS; ++w) s = s + red4[(w * VEC + i) * 32 + lane];
+                acc.v[i] = s;
+            }
+            spmm_store<VEC>(acc, Y, ldy, row, d4, lane, epi);
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// L1 margin alignment loss (gcn_align.py:298-320 / rdgcn.py:293-315):
+//   A_i = ‖x[l_i] − x[r_i]‖₁ ; for each of the 2k negatives (nl, nr) of i: relu(A_i + γ − ‖x[nl] − x[nr]‖₁)
+//   loss = Σ / (2·k·t).  One warp per seed pair; gradients scatter-add into grad [N, ld] (pre-zeroed).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_align_loss_l1(const float* __restrict__ x, int ld, int dim, const int32_t* __restrict__ left, const int32_t* __restrict__ right,
+                int t, int k, const int32_t* __restrict__ neg_left, const int32_t* __restrict__ neg_right,
+                const int32_t* __restrict__ neg2_left, const int32_t* __restrict__ neg2_right, float gamma, float scale,
+                double* __restrict__ loss_out, float* __restrict__ grad) {
+    __shared__ double s_part[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int warp_global = blockIdx.x * 8 + warp, n_warps = gridDim.x * 8;
+    float wloss = 0.f;
+    for (int i = warp_global; i < t; i += n_warps) {
+        const int l = __ldg(left + i), r = __ldg(right + i);
+        const float* xl = x + (size_t)l * ld; const float* xr = x + (size_t)r * ld;
+        float a = 0.f;
+        for (int c = lane; c < dim; c += 32) a += fabsf(__ldg(xl + c) - __ldg(xr + c));
+        a = warp_sum(a);
+        const float dplus = a + gamma;
+        int active = 0;
+        for (int j = 0; j < 2 * k; ++j) {
+            const int idx = i * k + (j < k ? j : j - k);
+            const int nl = j < k ? __ldg(neg_left + idx) : __ldg(neg2_left + idx);
+            const int nr = j < k ? __ldg(neg_right + idx) : __ldg(neg2_right + idx);
+            const float* yl = x + (size_t)nl * ld; const float* yr = x + (size_t)nr * ld;
+            float b = 0.f;
+            for (int c = lane; c < dim; c += 32) b += fabsf(__ldg(yl + c) - __ldg(yr + c));
+            b = warp_sum(b);
+            const float v = dplus - b;
+            if (v > 0.f) {
+                wloss += v;
+                ++active;
+                for (int c = lane; c < dim; c += 32) {
+                    const float s = sgn(__ldg(yl + c) - __ldg(yr + c)) * scale;
+                    if (s != 0.f) { atomicAdd(grad + (size_t)nl * ld + c, -s); atomicAdd(grad + (size_t)nr * ld + c, s); }
+                }
+            }
+        }
+        if (active) {
+            for (int c = lane; c < dim; c += 32) {
+                const float s = sgn(__ldg(xl + c) - __ldg(xr + c)) * scale * (float)active;
+                if (s != 0.f) { atomicAdd(grad + (size_t)l * ld + c, s); atomicAdd(grad + (size_t)r * ld + c, -s); }
+            }
+        }
+    }
+    if (lane == 0) s_part[warp] = (double)wloss;
+    __syncthreads();
+    if (threadIdx.x == 0) { double s = 0.0; for (int w = 0; w < 8; ++w) s += s_part[w]; if (s != 0.0) atomicAdd(loss_out, s * (double)scale); }
+}
+
+static int spmm_sm_count() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+    }
+    return sms;
+}
+
+}  // namespace oea
+
+using namespace oea;
+
+extern "C" int oea_spmm_csr(const oea_csr* A, const int32_t* long_rows, int32_t n_long,
+                            const float* X, int32_t ldx, float* Y, int32_t ldy, int32_t d,
+                            int32_t relu, const float* mask_src, float beta, void* stream) {
+    if (!A || !A->rowptr || !X || !Y) return OEA_ERR_NULL;
+    if (A->nnz > 0 && (!A->col || !A->val)) return OEA_ERR_NULL;
+    if (A->n_rows <= 0 || d <= 0 || (d & 3) || d > 512 || ldx < d || ldy < d || (ldx & 3) || (ldy & 3)) return OEA_ERR_DIM;
+    if (!aligned16(X) || !aligned16(Y) || (mask_src && !aligned16(mask_src))) return OEA_ERR_ALIGN;
+    if (n_long < 0 || (n_long > 0 && !long_rows)) return OEA_ERR_NULL;
+    cudaStream_t st = (cudaStream_t)stream;
+    SpmmEpi epi{relu, mask_src, beta};
+    const int d4 = d >> 2;
+    const int blocks = (A->n_rows + SPMM_WARPS - 1) / SPMM_WARPS;
+    const int grid = blocks < spmm_sm_count() * 8 ? blocks : spmm_sm_count() * 8;
+    const int lgrid = n_long < spmm_sm_count() * 4 ? n_long : spmm_sm_count() * 4;
+#define OEA_SPMM(V)                                                                                                          \
+    do {                                                                                                                     \
+        k_spmm_warp_rows<V><<<grid, SPMM_THREADS, 0, st>>>(A->rowptr, A->col, A->val, A->n_rows, X, ldx, Y, ldy, d4, epi);   \
+        if (n_long > 0)                                                                                                      \
+            k_spmm_cta_rows<V><<<lgrid, SPMM_THREADS, SPMM_WARPS * V * 32 * sizeof(float4), st>>>(                           \
+                A->rowptr, A->col, A->val, long_rows, n_long, X, ldx, Y, ldy, d4, epi);                                      \
+    } while (0)
+    if (d <= 128) OEA_SPMM(1); else if (d <= 256) OEA_SPMM(2); else if (d <= 384) OEA_SPMM(3); else OEA_SPMM(4);
+#undef OEA_SPMM
+    OEA_LAUNCH_CHECK();
+    return OEA_OK;
+}
+
+extern "C" int oea_spmm_long_row_threshold(void) { return LONG_ROW; }
+
+extern "C" int oea_align_loss_l1(const float* x, int32_t ld, int32_t dim, const int32_t* left, const int32_t* right, int32_t t,
+                                 int32_t k, const int32_t* neg_left, const int32_t* neg_right,
+                                 const int32_t* neg2_left, const int32_t* neg2_right, float gamma,
+                                 double* loss_out, float* grad, void* stream) {
+    if (!x || !left || !right || !neg_left || !neg_right || !neg2_left || !neg2_right || !loss_out || !grad) return OEA_ERR_NULL;
+    if (t <= 0 || k <= 0 || dim <= 0 || ld < dim) return OEA_ERR_SHAPE;
+    const float scale = 1.0f / (2.0f * (float)k * (float)t);
+    const int blocks = (t + 7) / 8;
+    k_align_loss_l1<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, ld, dim, left, right, t, k, neg_left, neg_right, neg2_left,
+                                                              neg2_right, gamma, scale, loss_out, grad);
+    OEA_LAUNCH_CHECK();
+    return OEA_OK;
+}

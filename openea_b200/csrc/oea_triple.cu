@@ -375,15 +375,14 @@ k_score_sampled(TableDev ent, TableDev rel, SampledParams P, oea_loss_cfg cfg,
             u.v[c] = hr.v[c] - xt.v[c];
         }
         const float sp = warp_sum(score_partial<SCORE, VEC>(u));
-        float L, g;
-        loss_of(cfg.loss_kind, false, sp, cfg, L, g);
+        const bool margin_mode = cfg.loss_kind == OEA_LOSS_MARGIN;   // Σ relu(m + s⁺ − s⁻), k == 1
+        float L = 0.f, g = 0.f;
+        if (!margin_mode) loss_of(cfg.loss_kind, false, sp, cfg, L, g);
         warp_loss += L;
         bool any_grad = g != 0.f;
-        {
-            Row<VEC> du = score_dir<SCORE, VEC>(u);
+        const Row<VEC> dir_pos = score_dir<SCORE, VEC>(u);
 #pragma unroll
-            for (int c = 0; c < VEC; ++c) { Gh.v[c] = du.v[c] * g; Gr.v[c] = Gh.v[c]; Gt.v[c] = neg(Gh.v[c]); }
-        }
+        for (int c = 0; c < VEC; ++c) { Gh.v[c] = dir_pos.v[c] * g; Gr.v[c] = Gh.v[c]; Gt.v[c] = neg(Gh.v[c]); }
 
         // ---- negatives: only the corrupted row is new ----
         for (int j = 0; j < k; ++j) {
@@ -400,7 +399,17 @@ k_score_sampled(TableDev ent, TableDev rel, SampledParams P, oea_loss_cfg cfg,
             Row<VEC> dir = score_dir<SCORE, VEC>(u);
             float sn = score_partial<SCORE, VEC>(u), de = dotr(xe, dir);
             warp_sum2(sn, de);
-            loss_of(cfg.loss_kind, true, sn, cfg, L, g);
+            if (margin_mode) {
+                const float v = cfg.margin + sp - sn;
+                L = fmaxf(v, 0.f);
+                g = v > 0.f ? -1.f : 0.f;
+                if (v > 0.f) {   // the positive's share of the active hinge
+#pragma unroll
+                    for (int c = 0; c < VEC; ++c) { Gh.v[c] = Gh.v[c] + dir_pos.v[c]; Gr.v[c] = Gr.v[c] + dir_pos.v[c]; Gt.v[c] = Gt.v[c] - dir_pos.v[c]; }
+                }
+            } else {
+                loss_of(cfg.loss_kind, true, sn, cfg, L, g);
+            }
             warp_loss += L;
             if (g != 0.f) {
                 any_grad = true;
@@ -644,9 +653,12 @@ extern "C" int oea_triple_score_sampled(const oea_table* ent, const oea_table* r
     rc = check_table(rel, true); if (rc) return rc;
     if (!smp || !loss || !loss_out || !tset || !tset->slots) return OEA_ERR_NULL;
     if (ent->pitch != rel->pitch || ent->dim != rel->dim) return OEA_ERR_DIM;
-    if (smp->neg_per_pos < 1 || smp->neg_per_pos > 32 || smp->batch_size < 1 || smp->max_try < 1 || smp->step < 0) return OEA_ERR_RANGE;
+    if (smp->neg_per_pos < 0 || smp->neg_per_pos > 32 || smp->batch_size < 1 || smp->max_try < 1 || smp->step < 0) return OEA_ERR_RANGE;
     if (tset->capacity == 0 || (tset->capacity & (tset->capacity - 1)) != 0) return OEA_ERR_RANGE;
-    if (loss->loss_kind != OEA_LOSS_LIMITED && loss->loss_kind != OEA_LOSS_LOGISTIC) return OEA_ERR_KIND;
+    if (loss->loss_kind < OEA_LOSS_MARGIN || loss->loss_kind > OEA_LOSS_LOGSIGMOID) return OEA_ERR_KIND;
+    if (loss->loss_kind == OEA_LOSS_MARGIN && smp->neg_per_pos != 1) return OEA_ERR_SHAPE;   // args_hander.py:19-21
+    if ((loss->loss_kind == OEA_LOSS_POSITIVE || loss->loss_kind == OEA_LOSS_LOGSIGMOID) && smp->neg_per_pos != 0) return OEA_ERR_SHAPE;
+    if ((loss->loss_kind == OEA_LOSS_LIMITED || loss->loss_kind == OEA_LOSS_LOGISTIC) && smp->neg_per_pos < 1) return OEA_ERR_SHAPE;
     if (loss->score_kind != OEA_SCORE_L1 && loss->score_kind != OEA_SCORE_L2SQ) return OEA_ERR_KIND;
     rc = check_kg(kg1, smp->neg_per_pos); if (rc) return rc;
     rc = check_kg(kg2, smp->neg_per_pos); if (rc) return rc;
@@ -739,6 +751,221 @@ extern "C" int oea_tripleset_build(const int32_t* triples, int32_t n, uint64_t* 
     OEA_CUDA_TRY(cudaMemsetAsync(slots, 0xFF, (size_t)capacity * sizeof(uint64_t), st));
     if (n == 0) return OEA_OK;
     k_tripleset_build<<<(n + 255) / 256, 256, 0, st>>>(triples, n, (unsigned long long*)slots, capacity, ent_bits, rel_bits);
+    OEA_LAUNCH_CHECK();
+    return OEA_OK;
+}
+
+// ================================================================================================
+// Generic pieces for graphs that are not the fused triple step: gradient scatter through the
+// normalised lookup, the losses of modules/base/losses.py on already-gathered rows, and the
+// MTransE mapping loss (losses.py:76-80).
+// ================================================================================================
+namespace oea {
+
+// backward of `normalise(weight[ids[i]])`: grad_rows [n, gpitch] are d/d(normalised row)
+__global__ void __launch_bounds__(kThreads)
+k_table_scatter(const float* __restrict__ w, float* __restrict__ grad, int32_t* __restrict__ touched, int pitch,
+                int dim, bool norm, const int32_t* __restrict__ ids, int n, const float* __restrict__ g_rows, int gpitch) {
+    const int lane = threadIdx.x & 31;
+    const int warp_global = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int n_warps = gridDim.x * kWarpsPerBlock;
+    for (int i = warp_global; i < n; i += n_warps) {
+        const int row = __ldg(ids + i);
+        const float* x = w + (size_t)row * pitch;
+        const float* g = g_rows + (size_t)i * gpitch;
+        float ss = 0.f, dot = 0.f;
+        for (int c = lane; c < dim; c += 32) { const float xv = __ldg(x + c); ss = fmaf(xv, xv, ss); dot = fmaf(xv, __ldg(g + c), dot); }
+        warp_sum2(ss, dot);
+        const float inv = inv_norm(ss, norm);
+        // x̂ = x·inv ; <x̂, g> = dot·inv ; dx = (g − x̂·<x̂,g>)·inv
+        const float proj = (norm && ss >= kNormEps) ? dot * inv * inv : 0.f;
+        float* o = grad + (size_t)row * pitch;
+        for (int c = lane; c < dim; c += 32) atomicAdd(o + c, (__ldg(g + c) - __ldg(x + c) * proj) * inv);
+        if (lane == 0) touched[row] = 1;
+    }
+}
+
+// losses.py on gathered rows: warp per triple (or per pos/neg pair for the margin loss)
+template <int SCORE>
+__global__ void __launch_bounds__(kThreads)
+k_loss_rows(const float* __restrict__ ph, const float* __restrict__ pr, const float* __restrict__ pt, int n_pos,
+            const float* __restrict__ nh, const float* __restrict__ nr, const float* __restrict__ nt, int n_neg,
+            int dim, int pitch, oea_loss_cfg cfg, double* __restrict__ loss_out,
+            float* __restrict__ gph, float* __restrict__ gpr, float* __restrict__ gpt,
+            float* __restrict__ gnh, float* __restrict__ gnr, float* __restrict__ gnt) {
+    __shared__ double s_loss[kWarpsPerBlock];
+    const int lane = threadIdx.x & 31;
+    const int warp_global = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int n_warps = gridDim.x * kWarpsPerBlock;
+    const bool margin = cfg.loss_kind == OEA_LOSS_MARGIN;
+    const int total = margin ? n_pos : n_pos + n_neg;
+    float warp_loss = 0.f;
+    for (int i = warp_global; i < total; i += n_warps) {
+        const bool is_neg = !margin && i >= n_pos;
+        const size_t o = (size_t)(is_neg ? i - n_pos : i) * pitch;
+        const float* h = (is_neg ? nh : ph) + o; const float* r = (is_neg ? nr : pr) + o; const float* t = (is_neg ? nt : pt) + o;
+        float s = 0.f, s2 = 0.f;
+        for (int c = lane; c < dim; c += 32) {
+            const float u = h[c] + r[c] - t[c];
+            s += SCORE == OEA_SCORE_L1 ? fabsf(u) : u * u;
+            if (margin) { const float v = nh[o + c] + nr[o + c] - nt[o + c]; s2 += SCORE == OEA_SCORE_L1 ? fabsf(v) : v * v; }
+        }
+        warp_sum2(s, s2);
+        float L, g, g2 = 0.f;
+        if (margin) { const float v = cfg.margin + s - s2; L = fmaxf(v, 0.f); g = v > 0.f ? 1.f : 0.f; g2 = -g; }
+        else loss_of(cfg.loss_kind, is_neg, s, cfg, L, g);
+        warp_loss += L;
+        float* gh = (is_neg ? gnh : gph) + o; float* gr = (is_neg ? gnr : gpr) + o; float* gt = (is_neg ? gnt : gpt) + o;
+        for (int c = lane; c < dim; c += 32) {
+            const float u = h[c] + r[c] - t[c];
+            const float du = g * (SCORE == OEA_SCORE_L1 ? sgn(u) : 2.f * u);
+            gh[c] = du; gr[c] = du; gt[c] = -du;
+            if (margin) {
+                const float v = nh[o + c] + nr[o + c] - nt[o + c];
+                const float dv = g2 * (SCORE == OEA_SCORE_L1 ? sgn(v) : 2.f * v);
+                gnh[o + c] = dv; gnr[o + c] = dv; gnt[o + c] = -dv;
+            }
+        }
+    }
+    LossAcc acc{s_loss};
+    acc.flush(warp_loss, loss_out);
+}
+
+// Mapping loss part 1 (losses.py:77-78): per pair r = e2 − e1·M ; loss += ‖r‖² ; g2 = 2r ; g1 = −2·r·Mᵀ ;
+// gM += −2·e1ᵀ r.  One CTA per 8 pairs; the CTA's partial gM goes out with one atomic per element.
+constexpr int MAP_PAIRS = 8;
+__global__ void __launch_bounds__(256)
+k_mapping_pairs(const float* __restrict__ e1, const float* __restrict__ e2, int n, int dim, int pitch,
+                const float* __restrict__ M, int mpitch, float alpha, double* __restrict__ loss_out,
+                float* __restrict__ g1, float* __restrict__ g2, float* __restrict__ gM) {
+    extern __shared__ float sm[];
+    float* a = sm;                       // [MAP_PAIRS][dim]  e1 rows
+    float* r = sm + MAP_PAIRS * dim;     // [MAP_PAIRS][dim]  residuals
+    __shared__ double s_part[8];
+    const int tid = threadIdx.x, p0 = blockIdx.x * MAP_PAIRS;
+    const int np = min(MAP_PAIRS, n - p0);
+    for (int i = tid; i < MAP_PAIRS * dim; i += 256) {
+        const int p = i / dim, c = i % dim;
+        a[i] = p < np ? e1[(size_t)(p0 + p) * pitch + c] : 0.f;
+    }
+    __syncthreads();
+    float local = 0.f;
+    for (int i = tid; i < MAP_PAIRS * dim; i += 256) {          // y = e1·M, column c of pair p
+        const int p = i / dim, c = i % dim;
+        float y = 0.f;
+        for (int k = 0; k < dim; ++k) y = fmaf(a[p * dim + k], __ldg(M + (size_t)k * mpitch + c), y);
+        const float res = p < np ? e2[(size_t)(p0 + p) * pitch + c] - y : 0.f;
+        r[i] = res;
+        local += res * res;
+        if (p < np) g2[(size_t)(p0 + p) * pitch + c] = 2.f * alpha * res;
+    }
+    __syncthreads();
+    for (int i = tid; i < MAP_PAIRS * dim; i += 256) {          // g1 = −2·r·Mᵀ
+        const int p = i / dim, k = i % dim;
+        if (p >= np) continue;
+        float acc = 0.f;
+        for (int c = 0; c < dim; ++c) acc = fmaf(r[p * dim + c], __ldg(M + (size_t)k * mpitch + c), acc);
+        g1[(size_t)(p0 + p) * pitch + k] = -2.f * alpha * acc;
+    }
+    for (int i = tid; i < dim * dim; i += 256) {                // gM[k][c] += −2·Σ_p e1[p][k]·r[p][c]
+        const int k = i / dim, c = i % dim;
+        float acc = 0.f;
+#pragma unroll
+        for (int p = 0; p < MAP_PAIRS; ++p) acc = fmaf(a[p * dim + k], r[p * dim + c], acc);
+        if (acc != 0.f) atomicAdd(gM + (size_t)k * mpitch + c, -2.f * alpha * acc);
+    }
+    local = warp_sum(local);
+    if ((tid & 31) == 0) s_part[tid >> 5] = (double)local;
+    __syncthreads();
+    if (tid == 0) { double t = 0.0; for (int i = 0; i < 8; ++i) t += s_part[i]; atomicAdd(loss_out, (double)alpha * t); }
+}
+
+// Mapping loss part 2 (losses.py:79): G = M·Mᵀ − I ; loss += ΣG² ; gM += 4·G·M.  Grid of row blocks of G.
+__global__ void __launch_bounds__(256)
+k_mapping_orth(const float* __restrict__ M, int dim, int mpitch, float alpha, double* __restrict__ loss_out,
+               float* __restrict__ gM, float* __restrict__ Gws) {
+    // pass A (blockIdx.y == 0): G rows ; pass B is a second launch reading Gws
+    const int row = blockIdx.x;
+    __shared__ double s_part[8];
+    float local = 0.f;
+    for (int j = threadIdx.x; j < dim; j += 256) {
+        float acc = 0.f;
+        for (int k = 0; k < dim; ++k) acc = fmaf(__ldg(M + (size_t)row * mpitch + k), __ldg(M + (size_t)j * mpitch + k), acc);
+        const float g = acc - (row == j ? 1.f : 0.f);
+        Gws[(size_t)row * dim + j] = g;
+        local += g * g;
+    }
+    local = warp_sum(local);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = (double)local;
+    __syncthreads();
+    if (threadIdx.x == 0) { double t = 0.0; for (int i = 0; i < 8; ++i) t += s_part[i]; atomicAdd(loss_out, (double)alpha * t); }
+}
+__global__ void __launch_bounds__(256)
+k_mapping_orth_grad(const float* __restrict__ M, int dim, int mpitch, float alpha, const float* __restrict__ Gws, float* __restrict__ gM) {
+    const int row = blockIdx.x;
+    for (int c = threadIdx.x; c < dim; c += 256) {
+        float acc = 0.f;
+        for (int j = 0; j < dim; ++j) acc = fmaf(Gws[(size_t)row * dim + j], __ldg(M + (size_t)j * mpitch + c), acc);
+        atomicAdd(gM + (size_t)row * mpitch + c, 4.f * alpha * acc);
+    }
+}
+
+}  // namespace oea
+
+extern "C" int oea_table_scatter_grad(const oea_table* t, const int32_t* ids, int32_t n, const float* grad_rows,
+                                      int32_t grad_pitch, void* stream) {
+    int rc = check_table(t, true); if (rc) return rc;
+    if (n < 0 || grad_pitch < t->dim) return OEA_ERR_SHAPE;
+    if (n == 0) return OEA_OK;
+    if (!ids || !grad_rows) return OEA_ERR_NULL;
+    k_table_scatter<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(t->weight, t->grad, t->touched, t->pitch, t->dim,
+                                                                        t->l2_norm != 0, ids, n, grad_rows, grad_pitch);
+    OEA_LAUNCH_CHECK();
+    return OEA_OK;
+}
+
+extern "C" int oea_loss_rows(const float* ph, const float* pr, const float* pt, int32_t n_pos,
+                             const float* nh, const float* nr, const float* nt, int32_t n_neg,
+                             int32_t dim, int32_t pitch, const oea_loss_cfg* loss, double* loss_out,
+                             float* g_ph, float* g_pr, float* g_pt, float* g_nh, float* g_nr, float* g_nt, void* stream) {
+    if (!loss || !loss_out) return OEA_ERR_NULL;
+    if (n_pos < 0 || n_neg < 0 || dim <= 0 || pitch < dim) return OEA_ERR_SHAPE;
+    if (n_pos > 0 && (!ph || !pr || !pt || !g_ph || !g_pr || !g_pt)) return OEA_ERR_NULL;
+    if (n_neg > 0 && (!nh || !nr || !nt || !g_nh || !g_nr || !g_nt)) return OEA_ERR_NULL;
+    if (loss->loss_kind < OEA_LOSS_MARGIN || loss->loss_kind > OEA_LOSS_LOGSIGMOID) return OEA_ERR_KIND;
+    if (loss->loss_kind == OEA_LOSS_MARGIN && n_neg != n_pos) return OEA_ERR_SHAPE;
+    if ((loss->loss_kind == OEA_LOSS_POSITIVE || loss->loss_kind == OEA_LOSS_LOGSIGMOID) && n_neg != 0) return OEA_ERR_SHAPE;
+    if (n_pos + n_neg == 0) return OEA_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = grid_for(n_pos + n_neg);
+    if (loss->score_kind == OEA_SCORE_L1)
+        k_loss_rows<OEA_SCORE_L1><<<grid, kThreads, 0, st>>>(ph, pr, pt, n_pos, nh, nr, nt, n_neg, dim, pitch, *loss, loss_out, g_ph, g_pr, g_pt, g_nh, g_nr, g_nt);
+    else if (loss->score_kind == OEA_SCORE_L2SQ)
+        k_loss_rows<OEA_SCORE_L2SQ><<<grid, kThreads, 0, st>>>(ph, pr, pt, n_pos, nh, nr, nt, n_neg, dim, pitch, *loss, loss_out, g_ph, g_pr, g_pt, g_nh, g_nr, g_nt);
+    else return OEA_ERR_KIND;
+    OEA_LAUNCH_CHECK();
+    return OEA_OK;
+}
+
+extern "C" size_t oea_mapping_workspace_bytes(int32_t dim) { return dim > 0 ? (size_t)dim * dim * sizeof(float) : 0; }
+
+extern "C" int oea_mapping_fwd_bwd(const float* e1, const float* e2, int32_t n, int32_t dim, int32_t pitch,
+                                   const float* M, int32_t mpitch, float alpha, double* loss_out,
+                                   float* g_e1, float* g_e2, float* g_M, void* workspace, size_t workspace_bytes,
+                                   void* stream) {
+    if (!M || !loss_out || !g_M || !workspace) return OEA_ERR_NULL;
+    if (n < 0 || dim <= 0 || dim > 512 || pitch < dim || mpitch < dim) return OEA_ERR_DIM;
+    if (n > 0 && (!e1 || !e2 || !g_e1 || !g_e2)) return OEA_ERR_NULL;
+    if (workspace_bytes < oea_mapping_workspace_bytes(dim)) return OEA_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n > 0) {
+        const size_t smem = 2 * (size_t)MAP_PAIRS * dim * sizeof(float);
+        k_mapping_pairs<<<(n + MAP_PAIRS - 1) / MAP_PAIRS, 256, smem, st>>>(e1, e2, n, dim, pitch, M, mpitch, alpha, loss_out, g_e1, g_e2, g_M);
+        OEA_LAUNCH_CHECK();
+    }
+    k_mapping_orth<<<dim, 256, 0, st>>>(M, dim, mpitch, alpha, loss_out, g_M, (float*)workspace);
+    OEA_LAUNCH_CHECK();
+    k_mapping_orth_grad<<<dim, 256, 0, st>>>(M, dim, mpitch, alpha, (const float*)workspace, g_M);
     OEA_LAUNCH_CHECK();
     return OEA_OK;
 }

@@ -87,18 +87,40 @@ class EmbeddingTable:
     def raw(self):
         return self.weight[:, :self.dim]
 
-    def lookup(self, ids=None):
-        """Normalised rows as TF's `embedding_lookup(self.ent_embeds, ids).eval()` → device tensor [n, dim]."""
+    def lookup(self, ids=None, padded=False):
+        """Normalised rows as TF's `embedding_lookup(self.ent_embeds, ids).eval()` → device tensor [n, dim]
+        (or [n, pitch] zero-padded when `padded`, the layout the SpMM / similarity kernels take)."""
         lib = L.load()
         if ids is None:
             n, ids_t = self.rows, None
         else:
             ids_t = torch.as_tensor(ids, dtype=torch.int32, device=self.device).contiguous()
             n = ids_t.numel()
-        out = torch.empty(n, self.dim, dtype=torch.float32, device=self.device)
-        L.check(lib.oea_table_lookup(C.byref(self.c_struct()), _ptr(ids_t), n, _ptr(out), self.dim, _stream_ptr()),
+        width = self.pitch if padded else self.dim
+        out = torch.empty(n, width, dtype=torch.float32, device=self.device)
+        L.check(lib.oea_table_lookup(C.byref(self.c_struct()), _ptr(ids_t), n, _ptr(out), width, _stream_ptr()),
                 "oea_table_lookup")
         return out
+
+    def scatter_grad(self, grad_rows, ids=None):
+        """Backward of lookup(): push d loss / d (normalised rows) through the normalisation into self.grad."""
+        lib = L.load()
+        if ids is None:
+            if getattr(self, "_all_ids", None) is None:
+                self._all_ids = torch.arange(self.rows, dtype=torch.int32, device=self.device)
+            ids_t = self._all_ids
+        else:
+            ids_t = torch.as_tensor(ids, dtype=torch.int32, device=self.device).contiguous()
+        L.check(lib.oea_table_scatter_grad(C.byref(self.c_struct()), _ptr(ids_t), ids_t.numel(), _ptr(grad_rows),
+                                           grad_rows.stride(0), _stream_ptr()), "oea_table_scatter_grad")
+
+    def apply(self, lr):
+        """One optimiser step on this table with its own slots (oea_rowopt_apply)."""
+        lib = L.load()
+        if self.optimizer == "Adam":
+            self.adam_t += 1
+        cfg = opt_cfg(self, lr)
+        L.check(lib.oea_rowopt_apply(C.byref(self.c_struct()), C.byref(cfg), _stream_ptr()), "oea_rowopt_apply")
 
 
 def loss_cfg(loss, loss_norm, margin=0.0, neg_margin=0.0, balance=1.0):
@@ -246,3 +268,44 @@ def _as_host_i32(a):
         assert a.dtype == torch.int32 and not a.is_cuda and a.is_contiguous()
         return a
     return torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.int32)))
+
+
+class MappingTrainer:
+    """MTransE-style mapping module: loss alpha·(Σ‖e2 − e1·M‖² + Σ(MMᵀ − I)²) over seed pairs
+    (modules/base/mapping.py:9-19, losses.py:76-80) with its OWN optimiser slots on the entity table and on M."""
+
+    def __init__(self, ent, mapping, alpha, lr):
+        self.lib = L.load()
+        self.ent = ent.new_slots()          # a separate optimiser instance ⇒ separate accumulators (SURVEY A.3)
+        self.M = mapping
+        self.alpha, self.lr = float(alpha), float(lr)
+        self.loss_dev = torch.zeros(1, dtype=torch.float64, device=ent.device)
+        ws = self.lib.oea_mapping_workspace_bytes(ent.dim)
+        self.ws = torch.empty(max(1, ws), dtype=torch.uint8, device=ent.device)
+
+    def step(self, ents1, ents2):
+        """One session.run([mapping_loss, mapping_optimizer]) (basic_model.py:244-246); returns the batch loss."""
+        dev = self.ent.device
+        i1 = torch.as_tensor(ents1, dtype=torch.int32, device=dev).contiguous()
+        i2 = torch.as_tensor(ents2, dtype=torch.int32, device=dev).contiguous()
+        n, d, p = i1.numel(), self.ent.dim, self.ent.pitch
+        e1 = torch.empty(n, p, dtype=torch.float32, device=dev)
+        e2 = torch.empty(n, p, dtype=torch.float32, device=dev)
+        st = _stream_ptr()
+        es, ms = self.ent.c_struct(), self.M.c_struct()
+        L.check(self.lib.oea_table_lookup(C.byref(es), _ptr(i1), n, _ptr(e1), p, st), "oea_table_lookup")
+        L.check(self.lib.oea_table_lookup(C.byref(es), _ptr(i2), n, _ptr(e2), p, st), "oea_table_lookup")
+        g1, g2 = torch.empty_like(e1), torch.empty_like(e2)
+        self.loss_dev.zero_()
+        L.check(self.lib.oea_mapping_fwd_bwd(_ptr(e1), _ptr(e2), n, d, p, _ptr(self.M.weight), self.M.pitch, self.alpha,
+                                             _ptr(self.loss_dev), _ptr(g1), _ptr(g2), _ptr(self.M.grad), _ptr(self.ws),
+                                             self.ws.numel(), st), "oea_mapping_fwd_bwd")
+        L.check(self.lib.oea_table_scatter_grad(C.byref(es), _ptr(i1), n, _ptr(g1), p, st), "oea_table_scatter_grad")
+        L.check(self.lib.oea_table_scatter_grad(C.byref(es), _ptr(i2), n, _ptr(g2), p, st), "oea_table_scatter_grad")
+        self.M.touched.fill_(1)
+        for tab in (self.ent, self.M):
+            if tab.optimizer == "Adam":
+                tab.adam_t += 1
+            cfg = opt_cfg(tab, self.lr)
+            L.check(self.lib.oea_rowopt_apply(C.byref(tab.c_struct()), C.byref(cfg), st), "oea_rowopt_apply")
+        return float(self.loss_dev.item())

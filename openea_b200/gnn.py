@@ -1,0 +1,129 @@
+"""Host side of path (ii): device CSR matrices, the SpMM wrapper, adjacency builders of GCN-Align.
+
+Adjacency construction is host-side SciPy (one-off, like the reference); the per-epoch work (A·X forward,
+Aᵀ·dY backward, L1 alignment loss) runs in liboea.so kernels.
+"""
+import ctypes as C
+
+import numpy as np
+import scipy.sparse as sp
+import torch
+
+from . import lib as L
+from .engine import _ptr, _stream_ptr
+
+
+class DeviceCsr:
+    """A sparse matrix on the device in CSR (int32 / fp32) plus, lazily, its transpose (for the backward)."""
+
+    def __init__(self, mat, device="cuda"):
+        m = sp.csr_matrix(mat, dtype=np.float32)
+        m.sum_duplicates()
+        m.sort_indices()
+        self.shape = m.shape
+        self.nnz = int(m.nnz)
+        self.device = torch.device(device)
+        self._host = m
+        self.rowptr = torch.from_numpy(m.indptr.astype(np.int32)).to(self.device)
+        self.col = torch.from_numpy(m.indices.astype(np.int32)).to(self.device)
+        self.val = torch.from_numpy(m.data.astype(np.float32)).to(self.device)
+        thr = L.load().oea_spmm_long_row_threshold()
+        long_rows = np.flatnonzero(np.diff(m.indptr) > thr).astype(np.int32)
+        self.long_rows = torch.from_numpy(long_rows).to(self.device)
+        self._t = None
+
+    def transpose(self):
+        if self._t is None:
+            self._t = DeviceCsr(self._host.T.tocsr(), self.device)
+            self._t._t = self
+        return self._t
+
+    def c_struct(self):
+        return L.Csr(self.rowptr.data_ptr(), self.col.data_ptr(), self.val.data_ptr(), self.shape[0], self.shape[1],
+                     self.nnz)
+
+
+def spmm(A, X, out=None, relu=False, mask_src=None, beta=0.0):
+    """Y = A·X (fp32, X row-major with X.shape[1] % 4 == 0), optional fused relu / relu-backward mask."""
+    lib = L.load()
+    assert X.is_cuda and X.dtype == torch.float32 and X.stride(1) == 1
+    d = X.shape[1]
+    if out is None:
+        out = torch.empty(A.shape[0], d, dtype=torch.float32, device=X.device)
+    cs = A.c_struct()
+    L.check(lib.oea_spmm_csr(C.byref(cs), _ptr(A.long_rows), A.long_rows.numel(), _ptr(X), X.stride(0), _ptr(out),
+                             out.stride(0), d, int(relu), _ptr(mask_src), float(beta), _stream_ptr()), "oea_spmm_csr")
+    return out
+
+
+def align_loss_l1(x, dim, left, right, k, neg_left, neg_right, neg2_left, neg2_right, gamma, grad, loss_out):
+    lib = L.load()
+    L.check(lib.oea_align_loss_l1(_ptr(x), x.stride(0), dim, _ptr(left), _ptr(right), left.numel(), k,
+                                  _ptr(neg_left), _ptr(neg_right), _ptr(neg2_left), _ptr(neg2_right), float(gamma),
+                                  _ptr(loss_out), _ptr(grad), _stream_ptr()), "oea_align_loss_l1")
+
+
+# ---- adjacency builders of GCN-Align (approaches/gcn_align.py:566-578,610-664) ---------------------------
+def relation_functionality(triples):
+    """r2f[r] = #distinct heads / #triples of r ; r2if[r] = #distinct tails / #triples of r (gcn_align.py:610-640)."""
+    tri = np.asarray(triples, dtype=np.int64).reshape(-1, 3)
+    rels, inv, cnt = np.unique(tri[:, 1], return_inverse=True, return_counts=True)
+    n_heads = np.bincount(np.unique(np.stack([inv, tri[:, 0]], 1), axis=0)[:, 0], minlength=len(rels))
+    n_tails = np.bincount(np.unique(np.stack([inv, tri[:, 2]], 1), axis=0)[:, 0], minlength=len(rels))
+    r2f = dict(zip(rels.tolist(), (n_heads / cnt).tolist()))
+    r2if = dict(zip(rels.tolist(), (n_tails / cnt).tolist()))
+    return r2f, r2if
+
+
+def weighted_adjacency(n_ent, triples):
+    """get_weighted_adj (gcn_align.py:642-664): for every triple with h ≠ t,
+    M[(h,t)] += max(r2if[r], .3) and M[(t,h)] += max(r2f[r], .3); the COO entry of key (a, b) sits at
+    (row = b, col = a)."""
+    tri = np.asarray(triples, dtype=np.int64).reshape(-1, 3)
+    r2f, r2if = relation_functionality(tri)
+    keep = tri[:, 0] != tri[:, 2]
+    h, r, t = tri[keep, 0], tri[keep, 1], tri[keep, 2]
+    w_if = np.maximum(np.array([r2if[x] for x in r.tolist()]), 0.3)
+    w_f = np.maximum(np.array([r2f[x] for x in r.tolist()]), 0.3)
+    rows = np.concatenate([t, h])     # key (h,t) → row t, col h ; key (t,h) → row h, col t
+    cols = np.concatenate([h, t])
+    data = np.concatenate([w_if, w_f])
+    return sp.coo_matrix((data, (rows, cols)), shape=(n_ent, n_ent)).tocsr()   # duplicates sum, as M[...] += does
+
+
+def normalize_adj(adj):
+    """D^-½ · adjᵀ · D^-½ with D = diag(row sums of adj) (gcn_align.py:566-573; the transpose is real for the
+    asymmetric weighted adjacency)."""
+    adj = sp.coo_matrix(adj)
+    rowsum = np.asarray(adj.sum(1)).flatten()
+    with np.errstate(divide="ignore"):
+        d_inv_sqrt = np.power(rowsum, -0.5)
+    d_inv_sqrt[np.isinf(d_inv_sqrt)] = 0.0
+    dm = sp.diags(d_inv_sqrt)
+    return adj.dot(dm).transpose().dot(dm).tocoo()
+
+
+def preprocess_adj(adj):
+    return normalize_adj(adj + sp.eye(adj.shape[0]))
+
+
+def attribute_features(n_ent, entity_attributes_dict):
+    """load_attr (gcn_align.py:89-111): 0/1 entity × attribute matrix over the 70 % most frequent attributes
+    (ties in frequency keep first-seen order, as sorted(cnt, key=cnt.get, reverse=True) does)."""
+    cnt = {}
+    for _, attrs in entity_attributes_dict.items():
+        for a in attrs:
+            cnt[a] = cnt.get(a, 0) + 1
+    ranked = sorted(cnt, key=cnt.get, reverse=True)
+    num = int(0.7 * len(cnt))
+    attr2id = {a: i for i, a in enumerate(ranked[:num])}
+    rows, cols = [], []
+    for ent, attrs in entity_attributes_dict.items():
+        for a in attrs:
+            if a in attr2id:
+                rows.append(ent)
+                cols.append(attr2id[a])
+    data = np.ones(len(rows), dtype=np.float32)
+    m = sp.coo_matrix((data, (rows, cols)), shape=(n_ent, max(num, 1))).tocsr()
+    m.data[:] = 1.0   # attr[ent][id] = 1.0 is an assignment, not an accumulation
+    return m

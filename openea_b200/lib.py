@@ -80,6 +80,13 @@ SIGNATURES = {
     "oea_sim_matrix": (C.c_int, [C.POINTER(SimCfg), _P, _P, _P, _P, _P, _L, _P]),
     "oea_rows_normalize": (C.c_int, [_P, _I, _I, _I, _P, _I, _P]),
     "oea_rows_select_topk": (C.c_int, [_P, _L, _I, _I, _I, _P, _P, _P]),
+    "oea_table_scatter_grad": (C.c_int, [_TP, _P, _I, _P, _I, _P]),
+    "oea_loss_rows": (C.c_int, [_P, _P, _P, _I, _P, _P, _P, _I, _I, _I, C.POINTER(LossCfg), _P, _P, _P, _P, _P, _P, _P, _P]),
+    "oea_mapping_workspace_bytes": (C.c_size_t, [_I]),
+    "oea_mapping_fwd_bwd": (C.c_int, [_P, _P, _I, _I, _I, _P, _I, C.c_float, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "oea_spmm_long_row_threshold": (C.c_int, []),
+    "oea_spmm_csr": (C.c_int, [C.POINTER(Csr), _P, _I, _P, _I, _P, _I, _I, _I, _P, C.c_float, _P]),
+    "oea_align_loss_l1": (C.c_int, [_P, _I, _I, _P, _P, _I, _I, _P, _P, _P, _P, C.c_float, _P, _P, _P]),
     "oea_tripleset_build": (C.c_int, [_P, _I, _P, C.c_uint32, C.c_uint32, C.c_uint32, _P]),
 }
 

@@ -1,0 +1,49 @@
+"""Hyper-parameter presets of the BASELINE.json configs as ARGs objects (values as shipped in the reference's
+run/args/*.json; a user can equally pass those JSON files to run/main_from_args.py unchanged)."""
+from openea_b200.modules.args.args_hander import ARGs
+
+_COMMON = dict(training_data="../../datasets/", output="../../output/results/", dataset_division="721_5fold/1/",
+               search_module="greedy", ordered=True, start_valid=100, eval_freq=10, stop_metric="hits1", csls=10,
+               top_k=[1, 5, 10, 50], is_save=True, max_epoch=2000, batch_threads_num=2, test_threads_num=4)
+
+
+def _args(**kw):
+    d = dict(_COMMON)
+    d.update(kw)
+    return ARGs(d)
+
+
+def mtranse(scale="15K", dim=100):
+    return _args(embedding_module="MTransE", alignment_module="mapping", dim=dim, init="unit", ent_l2_norm=True,
+                 rel_l2_norm=True, loss_norm="L2", learning_rate=0.01, optimizer="Adagrad",
+                 batch_size=5000 if scale == "15K" else 20000, alpha=5, eval_metric="inner", eval_norm=True)
+
+
+def bootea(scale="15K"):
+    big = scale != "15K"
+    return _args(embedding_module="BootEA", alignment_module="swapping", dim=100, init="normal", ent_l2_norm=True,
+                 rel_l2_norm=True, loss="limited", loss_norm="L2", learning_rate=0.01, optimizer="Adagrad",
+                 batch_size=20000 if big else 5000, pos_margin=0.01, neg_margin=2.0, neg_margin_balance=0.2,
+                 neg_sampling="truncated", neg_triple_num=10, truncated_epsilon=0.98 if big else 0.9, truncated_freq=10,
+                 eval_metric="inner", eval_norm=False, sim_th=0.7, k=10, likelihood_slice=10,
+                 sub_epoch=20 if big else 10, batch_threads_num=4 if big else 2, test_threads_num=12 if big else 4)
+
+
+def aligne(scale="15K"):
+    a = bootea(scale)
+    a.embedding_module = "AlignE"
+    return a
+
+
+def transe(scale="15K"):
+    return _args(embedding_module="TransE", alignment_module="sharing", dim=100, init="normal", ent_l2_norm=True,
+                 rel_l2_norm=True, loss="margin-based", loss_norm="L2", margin=1.5, learning_rate=0.01,
+                 optimizer="Adagrad", batch_size=5000 if scale == "15K" else 20000, neg_sampling="uniform",
+                 neg_triple_num=1, truncated_epsilon=0.9, truncated_freq=10, eval_metric="inner", eval_norm=True)
+
+
+def gcn_align(scale="15K"):
+    return _args(embedding_module="GCN_Align", alignment_module="mapping", dim=100, neg_sampling="uniform",
+                 neg_triple_num=5, learning_rate=8, batch_size=5000, test_threads_num=3, eval_metric="manhattan",
+                 eval_norm=False, support_number=1, se_dim=100, ae_dim=100, hidden1=100, gamma=3, early_stop=False,
+                 dropout=0, test_method="sa", beta=0.9)

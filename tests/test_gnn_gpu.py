@@ -1,0 +1,143 @@
+"""GPU parity of path (ii): SpMM (K2), the L1 alignment loss and one full GCN-Align unit step against the
+CPU oracle (torch-CPU autograd restatement, oracle/gnn.py).  fp32 tolerance 1e-4 relative."""
+import contextlib
+import io
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+from oracle import gnn as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand_csr(rng, n_rows, n_cols, avg, hubs=3):
+    rows = rng.integers(0, n_rows, size=avg * n_rows)
+    cols = rng.integers(0, n_cols, size=avg * n_rows)
+    # a few hub rows with > 256 non-zeros exercise the CTA-per-row path; also leave some rows empty
+    for h in range(hubs):
+        extra = rng.integers(0, n_cols, size=700 + 300 * h)
+        rows = np.concatenate([rows, np.full(extra.size, h * 7 % n_rows)])
+        cols = np.concatenate([cols, extra])
+    keep = rows % 11 != 5
+    vals = rng.standard_normal(rows.size).astype(np.float32)
+    return sp.csr_matrix((vals[keep], (rows[keep], cols[keep])), shape=(n_rows, n_cols))
+
+
+@pytest.mark.parametrize("d", [100, 200, 300, 500])
+def test_spmm_matches_scipy(cuda_device, d):
+    from openea_b200 import gnn
+    rng = np.random.default_rng(d)
+    A = _rand_csr(rng, 3000, 2500, 6)
+    X = rng.standard_normal((2500, d)).astype(np.float32)
+    dA = gnn.DeviceCsr(A)
+    assert dA.long_rows.numel() >= 1
+    Xd = torch.from_numpy(X).cuda()
+    want = A @ X
+    got = gnn.spmm(dA, Xd).cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-4)
+    got = gnn.spmm(dA, Xd, relu=True).cpu().numpy()
+    np.testing.assert_allclose(got, np.maximum(want, 0), rtol=1e-4, atol=1e-4)
+    mask = rng.standard_normal(want.shape).astype(np.float32)
+    got = gnn.spmm(dA, Xd, mask_src=torch.from_numpy(mask).cuda()).cpu().numpy()
+    np.testing.assert_allclose(got, np.where(mask > 0, want, 0), rtol=1e-4, atol=1e-4)
+    y0 = rng.standard_normal(want.shape).astype(np.float32)
+    out = torch.from_numpy(y0.copy()).cuda()
+    gnn.spmm(dA, Xd, out=out, beta=0.5)
+    np.testing.assert_allclose(out.cpu().numpy(), want + 0.5 * y0, rtol=1e-4, atol=1e-4)
+    # transpose (the backward operand)
+    G = rng.standard_normal((3000, d)).astype(np.float32)
+    got = gnn.spmm(dA.transpose(), torch.from_numpy(G).cuda()).cpu().numpy()
+    np.testing.assert_allclose(got, A.T @ G, rtol=1e-4, atol=2e-4)
+
+
+def test_spmm_empty_rows_and_single_row(cuda_device):
+    from openea_b200 import gnn
+    A = sp.csr_matrix((np.array([2.0], dtype=np.float32), (np.array([3]), np.array([1]))), shape=(5, 4))
+    X = torch.arange(16, dtype=torch.float32).reshape(4, 4).cuda()
+    got = gnn.spmm(gnn.DeviceCsr(A), X).cpu().numpy()
+    want = np.zeros((5, 4), dtype=np.float32); want[3] = 2 * np.arange(4, 8)
+    np.testing.assert_array_equal(got, want)
+
+
+def _negs(rng, ill, n, k):
+    t = len(ill)
+    return (np.repeat(ill[:, 0], k).astype(np.int32), rng.integers(0, n, t * k).astype(np.int32),
+            rng.integers(0, n, t * k).astype(np.int32), np.repeat(ill[:, 1], k).astype(np.int32))
+
+
+def test_align_loss_l1_matches_autograd(cuda_device):
+    from openea_b200 import gnn
+    rng = np.random.default_rng(1)
+    n, d, t, k, gamma = 800, 100, 120, 5, 3.0
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    ill = np.stack([rng.choice(n, t, replace=False), rng.choice(n, t, replace=False)], 1)
+    negs = _negs(rng, ill, n, k)
+    xt = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+    want = orc.align_loss(xt, ill, gamma, k, *negs)
+    want.backward()
+    xd = torch.from_numpy(x).cuda()
+    grad = torch.zeros_like(xd)
+    loss = torch.zeros(1, dtype=torch.float64, device="cuda")
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    gnn.align_loss_l1(xd, d, dev(ill[:, 0].astype(np.int32)), dev(ill[:, 1].astype(np.int32)), k, *[dev(a) for a in negs],
+                      gamma, grad, loss)
+    assert float(loss.item()) == pytest.approx(float(want.detach()), rel=1e-5)
+    np.testing.assert_allclose(grad.cpu().numpy(), xt.grad.numpy(), rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("with_features", [False, True])
+def test_gcn_unit_step_matches_oracle(cuda_device, with_features):
+    """One session.run([loss, opt_op]) of a GCN_Align_Unit (SE: featureless, AE: sparse features)."""
+    from openea_b200 import gnn
+    from openea_b200.approaches.gcn_align import GCNAlignUnit
+    from openea_b200.engine import EmbeddingTable
+    from openea_b200.synth import synth_id_arrays
+    arr = synth_id_arrays("tiny", swapping=False)
+    n, d, k, gamma, lr = arr["n_ent"], 100, 5, 3.0, 8.0
+    triples = np.concatenate([arr["triples1"], arr["triples2"]])
+    support = gnn.preprocess_adj(gnn.weighted_adjacency(n, triples))
+    rng = np.random.default_rng(3)
+    feats = None
+    rows = n
+    if with_features:
+        feats = sp.csr_matrix((rng.random((n, 40)) < 0.1).astype(np.float32))
+        rows = 40
+    W0 = (rng.standard_normal((rows, d)) / np.sqrt(rows)).astype(np.float32)
+    ill = arr["train_links"].astype(np.int64)
+    negs = _negs(rng, ill, n, k)
+    want_loss, want_W, want_out = orc.unit_train_step(support, W0, feats, ill, gamma, k, negs, lr)
+
+    table = EmbeddingTable(W0, True, "SGD")
+    unit = GCNAlignUnit(gnn.DeviceCsr(support), table, None if feats is None else gnn.DeviceCsr(feats), ill, gamma, k, lr)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    loss = unit.train_step(*[dev(a) for a in negs])
+    assert float(loss.item()) == pytest.approx(want_loss, rel=1e-4)
+    np.testing.assert_allclose(unit.outputs[:, :d].cpu().numpy(), want_out, rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(table.raw().cpu().numpy(), want_W, rtol=1e-4, atol=2e-6 * np.abs(want_W).max() + 1e-7)
+
+
+def test_gcn_align_lifecycle(cuda_device, tmp_path):
+    import os
+    import re
+    from openea_b200 import presets
+    from openea_b200.approaches import GCN_Align
+    from openea_b200.modules.load.kgs import read_kgs_from_folder
+    from openea_b200.synth import write_dataset
+    folder = str(tmp_path) + "/data/"
+    write_dataset(folder, "tiny")
+    args = presets.gcn_align()
+    args.training_data, args.output = folder, str(tmp_path) + "/out/"
+    args.max_epoch, args.start_valid, args.se_dim, args.ae_dim = 60, 30, 64, 32
+    np.random.seed(0)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        kgs = read_kgs_from_folder(folder, args.dataset_division, "mapping", True)
+        m = GCN_Align(); m.set_args(args); m.set_kgs(kgs); m.init(); m.run(); m.test(); m.save()
+    out = buf.getvalue()
+    assert "avg. relation triple loss" in out
+    h1 = float(re.findall(r"accurate results: hits@\[1, 5, 10, 50\] = \[\s*([0-9.]+)", out)[-1])
+    assert h1 > 5.0, h1          # chance = 0.24 %
+    assert os.path.exists(m.out_folder + "ent_embeds.npy") and os.path.exists(m.out_folder + "attr_embeds.npy")

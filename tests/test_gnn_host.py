@@ -1,0 +1,60 @@
+"""CPU: GCN-Align adjacency / attribute-feature builders value-for-value against the reference's own GCN_Utils
+and load_attr source (extracted; skipped when /root/reference is absent) and against hand-computed cases."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oracle import gnn as orc_gnn
+
+
+def _toy():
+    # r=0: 3 triples, heads {0,1} tails {2,3} ; r=1: 1 triple ; one self loop that must be skipped
+    return [(0, 0, 2), (0, 0, 3), (1, 0, 2), (2, 1, 3), (3, 1, 3)]
+
+
+def test_weighted_adjacency_hand_computed():
+    from openea_b200 import gnn
+    tri = _toy()
+    r2f, r2if = gnn.relation_functionality(tri)
+    assert r2f[0] == pytest.approx(2 / 3) and r2if[0] == pytest.approx(2 / 3)
+    assert r2f[1] == pytest.approx(2 / 2) and r2if[1] == pytest.approx(1 / 2)
+    adj = gnn.weighted_adjacency(4, tri).toarray()
+    # key (h,t) → entry [t, h] = max(r2if, .3) ; key (t,h) → entry [h, t] = max(r2f, .3)
+    want = np.zeros((4, 4))
+    for h, r, t in tri:
+        if h == t:
+            continue
+        want[t, h] += max(r2if[r], 0.3)
+        want[h, t] += max(r2f[r], 0.3)
+    np.testing.assert_allclose(adj, want)
+    norm = gnn.preprocess_adj(sp.csr_matrix(adj)).toarray()
+    x = adj + np.eye(4)
+    dis = 1 / np.sqrt(x.sum(1))
+    np.testing.assert_allclose(norm, dis[:, None] * x.T * dis[None, :], rtol=1e-12)
+
+
+@pytest.mark.skipif(orc_gnn.reference_gcn_utils() is None, reason="/root/reference not present on this box")
+def test_builders_equal_reference_source():
+    from openea_b200 import gnn
+    from openea_b200.synth import synth_id_arrays
+    Utils, load_attr = orc_gnn.reference_gcn_utils()
+    arr = synth_id_arrays("tiny", swapping=False)
+    triples = [tuple(x) for x in np.concatenate([arr["triples1"], arr["triples2"]]).tolist()]
+    n = arr["n_ent"]
+    utils = Utils(None, None)
+    ref_adj = utils.get_weighted_adj(n, triples)
+    mine = gnn.weighted_adjacency(n, triples)
+    assert abs(sp.csr_matrix(ref_adj) - mine).max() < 1e-12
+    ref_norm = Utils.normalize_adj(ref_adj + sp.eye(n))
+    assert abs(sp.csr_matrix(ref_norm) - sp.csr_matrix(gnn.preprocess_adj(mine))).max() < 1e-12
+    rng = np.random.default_rng(0)
+    ent_attrs = {int(e): set(rng.integers(0, 30, size=rng.integers(1, 5)).tolist()) for e in range(n)}
+
+    class K:  # the two attributes of `kgs` load_attr reads
+        pass
+    kgs = K(); kgs.kg1 = K(); kgs.kg2 = K()
+    kgs.kg1.entity_attributes_dict = {e: v for e, v in ent_attrs.items() if e % 2 == 0}
+    kgs.kg2.entity_attributes_dict = {e: v for e, v in ent_attrs.items() if e % 2 == 1}
+    ref_attr = load_attr(n, kgs)
+    mine_attr = gnn.attribute_features(n, {**kgs.kg1.entity_attributes_dict, **kgs.kg2.entity_attributes_dict})
+    np.testing.assert_array_equal(ref_attr, mine_attr.toarray())

@@ -1,0 +1,183 @@
+"""CPU tests of the host-side mirror of the reference interface: args, task_divide, batch slicing, id
+assignment, dataset loading (against goldens generated from the reference and, where present, the live
+reference), the host sampler's rules, Gale-Shapley, early_stop, and the `openea` drop-in import surface."""
+import ast
+import contextlib
+import io
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+from oracle import ref_adapter
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "finding_golden.npz"))
+
+
+def test_args_loader(tmp_path):
+    from openea_b200.modules.args.args_hander import load_args, check_args
+    p = tmp_path / "a.json"
+    p.write_text(json.dumps({"dim": 100, "embedding_module": "TransE", "neg_triple_num": 1, "top_k": [1, 5]}))
+    with contextlib.redirect_stdout(io.StringIO()):
+        a = load_args(str(p))
+    assert a.dim == 100 and a.top_k == [1, 5]
+    check_args(a)
+    a.neg_triple_num = 2
+    with pytest.raises(AssertionError):
+        check_args(a)
+
+
+def test_task_divide_golden():
+    from openea_b200.modules.utils.util import task_divide, merge_dic
+    want = ast.literal_eval(str(GOLD["task_divide"][0]))
+    got = [task_divide(list(range(n)), t) for n, t in ((10, 3), (7, 7), (5, 8), (0, 2), (12, 4))]
+    assert got == want
+    assert merge_dic({1: 2}, {1: 3, 4: 5}) == {1: 3, 4: 5}
+
+
+def test_pos_batch_slices_golden():
+    from openea_b200.modules.train.batch import generate_pos_batch
+    tl1 = [(i, 0, i + 1) for i in range(23)]
+    tl2 = [(100 + i, 1, 101 + i) for i in range(11)]
+    want = ast.literal_eval(str(GOLD["pos_batch_slices"][0]))
+    assert [generate_pos_batch(tl1, tl2, 8, step) for step in range(5)] == want
+
+
+def test_id_assignment_golden():
+    from openea_b200.modules.load import read as rd
+    t1 = {("a", "r1", "b"), ("a", "r1", "c"), ("b", "r2", "c")}
+    t2 = {("x", "s1", "y"), ("y", "s1", "z"), ("z", "s2", "x"), ("y", "s2", "w"), ("w", "s1", "v")}
+    i1, i2 = rd.generate_mapping_id(t1, {"a", "b", "c"}, t2, {"x", "y", "z", "w", "v"}, ordered=True)
+    assert [str(sorted(i1.items())), str(sorted(i2.items()))] == GOLD["mapping_id"].tolist()
+    # hand check of the interleaving: KG1 rank i → 2i, KG2 rank i → 2i+1, KG2 overflow continues after 2·n1
+    assert i1 == {"c": 0, "b": 2, "a": 4} or set(i1.values()) == {0, 2, 4}
+    assert sorted(i2.values()) == [1, 3, 5, 6, 7]
+    i1, i2 = rd.generate_sharing_id([("a", "y")], t1, {"a", "b", "c"}, t2, {"x", "y", "z", "w", "v"}, ordered=True)
+    assert [str(sorted(i1.items())), str(sorted(i2.items()))] == GOLD["sharing_id"].tolist()
+    assert i2["y"] == i1["a"]
+
+
+def test_host_sampler_rules():
+    """generate_neg_triples_fast: k negatives per positive, same relation, exactly one side corrupted per
+    negative, candidates from the neighbour list when present, known triples filtered (except last try)."""
+    from openea_b200.modules.train.batch import generate_neg_triples_fast, generate_relation_triple_batch
+    random.seed(1); np.random.seed(1)
+    ents = list(range(0, 200, 2))
+    triples = [(random.choice(ents), random.randrange(5), random.choice(ents)) for _ in range(300)]
+    tset = set(triples)
+    neigh = {e: random.sample(ents, 12) for e in ents[:50]}
+    pos = triples[:64]
+    neg = generate_neg_triples_fast(pos, tset, ents, 10, neighbor=neigh)
+    assert len(neg) == 640
+    for i, (h, r, t) in enumerate(pos):
+        block = neg[10 * i:10 * i + 10]
+        for nh, nr, nt in block:
+            assert nr == r and ((nh == h) != (nt == t) or (nh, nr, nt) == (h, r, t))
+            if nh != h and h in neigh:
+                assert nh in neigh[h]
+            if nt != t and t in neigh:
+                assert nt in neigh[t]
+    assert sum(1 for x in neg if x in tset) <= 2
+    p, n = generate_relation_triple_batch(triples[:100], triples[100:], tset, tset, ents, ents, 40, 1, None, None, 3)
+    assert len(n) == 3 * len(p) and len(p) == 40
+
+
+def test_galeshapley_and_early_stop():
+    from openea_b200.modules.finding.alignment import galeshapley
+    from openea_b200.modules.finding.evaluation import early_stop
+    suitors = {"x_0": ["y_0", "y_1"], "x_1": ["y_0", "y_1"]}
+    reviewers = {"y_0": ["x_1", "x_0"], "y_1": ["x_0", "x_1"]}
+    assert galeshapley(suitors, reviewers, 100) == {"x_1": "y_0", "x_0": "y_1"}
+    with contextlib.redirect_stdout(io.StringIO()):
+        assert early_stop(0.5, 0.4, 0.3) == (0.4, 0.3, True)
+        assert early_stop(0.3, 0.4, 0.5) == (0.4, 0.5, False)
+        assert early_stop(-1, -1, 0.2) == (-1, 0.2, False)
+
+
+def test_calculate_rank_host_helper_matches_oracle():
+    from openea_b200.modules.finding.alignment import calculate_rank
+    from oracle import finding as orf
+    rng = np.random.default_rng(0)
+    s = rng.standard_normal((40, 60)).astype(np.float32)
+    mr, mrr, hits, pairs = calculate_rank(list(range(40)), s, [1, 5], True, 40)
+    top1, rank = orf.rank_rows(s)
+    assert pairs == {(i, int(j)) for i, j in enumerate(top1)}
+    assert hits == [int((rank < 1).sum()), int((rank < 5).sum())]
+    assert mr == pytest.approx((rank + 1).mean()) and mrr == pytest.approx((1 / (rank + 1)).mean())
+
+
+def test_openea_dropin_import_surface():
+    """Every import of the reference's run/main_from_args.py:5-35 resolves, and `openea.*` aliases `openea_b200.*`."""
+    import importlib
+    import sys
+    import openea  # noqa: F401
+    for mod, names in (("openea.modules.args.args_hander", ["check_args", "load_args", "ARGs"]),
+                       ("openea.modules.load.kgs", ["read_kgs_from_folder", "KGs"]),
+                       ("openea.modules.load.kg", ["KG"]),
+                       ("openea.modules.base.losses", ["get_loss_func", "margin_loss", "positive_loss", "limited_loss", "logistic_loss", "mapping_loss"]),
+                       ("openea.modules.base.initializers", ["init_embeddings"]),
+                       ("openea.modules.base.optimizers", ["generate_optimizer", "get_optimizer"]),
+                       ("openea.modules.base.mapping", ["add_mapping_variables", "add_mapping_module"]),
+                       ("openea.modules.train.batch", ["generate_relation_triple_batch", "generate_neg_triples_fast", "generate_neighbours_single_thread", "find_neighbours"]),
+                       ("openea.modules.finding.similarity", ["sim", "csls_sim"]),
+                       ("openea.modules.finding.alignment", ["greedy_alignment", "stable_alignment", "calculate_rank"]),
+                       ("openea.modules.finding.evaluation", ["valid", "test", "early_stop"]),
+                       ("openea.modules.bootstrapping.alignment_finder", ["find_alignment", "find_potential_alignment_mwgm", "find_potential_alignment_greedily", "search_nearest_k", "check_new_alignment"]),
+                       ("openea.models.basic_model", ["BasicModel"]),
+                       ("openea.models.trans", ["TransD", "TransE", "TransH", "TransR"]),
+                       ("openea.models.semantic", ["DistMult", "HolE", "SimplE", "RotatE"]),
+                       ("openea.models.neural", ["ConvE", "ProjE"]),
+                       ("openea.approaches", ["AlignE", "BootEA", "JAPE", "Attr2Vec", "MTransE", "IPTransE", "GCN_Align", "AttrE", "IMUSE", "SEA", "MultiKE", "RSN4EA", "GMNN", "KDCoE", "RDGCN", "BootEA_RotatE", "BootEA_TransH", "AliNet"])):
+        m = importlib.import_module(mod)
+        for n in names:
+            assert hasattr(m, n), "%s.%s" % (mod, n)
+    assert sys.modules["openea.models.basic_model"] is sys.modules["openea_b200.models.basic_model"]
+    from openea.models.basic_model import BasicModel
+    for meth in ("set_args", "set_kgs", "init", "run", "valid", "test", "save", "retest", "predict"):
+        assert callable(getattr(BasicModel, meth))
+    from openea.approaches import JAPE
+    with pytest.raises(NotImplementedError):
+        JAPE().init()
+
+
+@pytest.mark.skipif(not ref_adapter.available(), reason="/root/reference not present on this box")
+def test_dataset_loading_equals_live_reference(tmp_path):
+    """Full read_kgs_from_folder equivalence (id dicts, triples incl. swap triples, links) on a synthetic folder."""
+    import importlib
+    import sys
+    import types
+    from openea_b200.synth import write_dataset
+    folder = str(tmp_path) + "/"
+    write_dataset(folder, "tiny")
+    with contextlib.redirect_stdout(io.StringIO()):
+        from openea_b200.modules.load.kgs import read_kgs_from_folder
+        mine = {m: read_kgs_from_folder(folder, "721_5fold/1/", m, True) for m in ("swapping", "mapping", "sharing")}
+    saved = {k: v for k, v in sys.modules.items() if k == "openea" or k.startswith("openea.")}
+    for k in saved:
+        del sys.modules[k]
+    sys.modules["tensorflow"] = types.ModuleType("tensorflow")
+    pkg = types.ModuleType("openea")
+    pkg.__path__ = [os.path.join(ref_adapter.REF_SRC, "openea")]
+    sys.modules["openea"] = pkg
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            rk = importlib.import_module("openea.modules.load.kgs")
+            theirs = {m: rk.read_kgs_from_folder(folder, "721_5fold/1/", m, True) for m in mine}
+    finally:
+        for k in [k for k in sys.modules if k == "openea" or k.startswith("openea.")]:
+            del sys.modules[k]
+        sys.modules.pop("tensorflow", None)
+        sys.modules.update(saved)
+    for m in mine:
+        a, b = mine[m], theirs[m]
+        assert a.entities_num == b.entities_num and a.relations_num == b.relations_num and a.attributes_num == b.attributes_num
+        for side in ("kg1", "kg2"):
+            ka, kb = getattr(a, side), getattr(b, side)
+            assert ka.entities_id_dict == kb.entities_id_dict and ka.relations_id_dict == kb.relations_id_dict
+            assert ka.attributes_id_dict == kb.attributes_id_dict
+            assert ka.relation_triples_set == kb.relation_triples_set and ka.attribute_triples_set == kb.attribute_triples_set
+            assert ka.rt_dict == kb.rt_dict and ka.hr_dict == kb.hr_dict
+            assert ka.sup_relation_triples_set == kb.sup_relation_triples_set
+        assert a.train_links == b.train_links and a.valid_links == b.valid_links and a.test_links == b.test_links
