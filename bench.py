@@ -217,6 +217,14 @@ def bench_csls(shape, device, reps=3):
             "note": "inner + CSLS(k=10), exact ranks; includes host-side reduction of the rank vector"}
 
 
+_T0 = time.perf_counter()
+
+
+def _phase(msg):
+    sys.stderr.write("[bench %7.1fs] %s\n" % (time.perf_counter() - _T0, msg))
+    sys.stderr.flush()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -255,7 +263,9 @@ def main():
     device = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
+    _phase("cuda ready; building workload")
     W = build_workload(args.workload, rank, device)
+    _phase("workload resident")
     tr, kg1, kg2, tset = W["trainer"], W["kg1"], W["kg2"], W["tset"]
     B, k, d = cfg["batch"], cfg["k"], cfg["dim"]
     spe = W["steps_per_epoch"]
@@ -318,6 +328,7 @@ def main():
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms_median": score_med_ms,
                 "kernel_share_of_step": float(score_ms.sum() / step_ms.sum())}
 
+    _phase("device-timed region done")
     # ---- e2e: the session.run(feed_dict) boundary with HOST index buffers -------------------------------------
     e2e = None
     cpu_base = None
@@ -353,14 +364,17 @@ def main():
         e2e = {"value": world * n_pos_h * K / e2e_s, "unit": unit, "h2d_bytes_per_step": 12 * (n_pos_h + n_neg_h),
                "d2h_bytes_per_step": 8, "ms_per_step": 1e3 * e2e_s / K,
                "api": "oea_triple_step_fed_host (host index buffers, tables resident, synchronous)"}
+        _phase("e2e done")
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             np_batches = [(p.numpy(), n.numpy()) for p, n in host_batches]
             val, info = cpu_reference_run(args.workload, 1000, 2, batches=np_batches, budget_s=12.0)
             cpu_base = {"value": val, "unit": unit, "cores": info["cores"], "kind": "port", "sample": info["sample"]}
 
+    _phase("cpu baseline done")
     csls = None
     if rank == 0 and world == 1:
         csls = bench_csls(cfg["shape"], device)
+    _phase("csls done")
     # clocks: the timed region is a few ms, shorter than nvidia-smi's sampling period; continue the SAME loop
     # untimed under the sampler until it has >= 5 samples so the clocks line reflects this load
     clk = clocks.summary()

@@ -34,7 +34,12 @@ def _run(model_cls, args, folder, mode, tmp_path):
         model.run()
         model.test()
         model.save()
-    return model, buf.getvalue()
+    out = buf.getvalue()
+    log_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(log_dir):      # kept for inspection after a GPU run
+        with open(os.path.join(log_dir, "e2e_%s.log" % model_cls.__name__), "w") as fh:
+            fh.write(out)
+    return model, out
 
 
 def _hits1(out, tag):
@@ -47,14 +52,16 @@ def test_bootea_lifecycle(cuda_device, tiny_kgs, tmp_path):
     from openea_b200 import presets
     from openea_b200.approaches import BootEA
     args = presets.bootea("15K")
-    args.batch_size, args.max_epoch, args.start_valid, args.sub_epoch = 1000, 60, 20, 10
-    args.truncated_epsilon, args.dim = 0.9, 32
+    args.batch_size, args.max_epoch, args.start_valid, args.sub_epoch = 1000, 300, 1000, 10
+    args.truncated_epsilon, args.dim, args.sim_th = 0.9, 32, 0.5
     model, out = _run(BootEA, args, tiny_kgs, "swapping", tmp_path)
     assert "avg. triple loss" in out and "generating neighbors of" in out and "Training ends. Total time" in out
-    assert "after mwgm" in out or "empty aligned pairs" in out
+    assert "after mwgm" in out and "alignment_loss = " in out, "bootstrapping must have produced and trained on new pairs"
     h1 = _hits1(out, "accurate results:")
     h1_csls = _hits1(out, "accurate results with csls: csls=10,")
-    assert h1 > 20.0 and h1_csls > 20.0, (h1, h1_csls)      # chance = 1/420 = 0.24 %
+    # calibration: the CPU oracle loop (reference semantics, no bootstrapping) reaches 11 % at 200 epochs on this
+    # KG (oracle/train_loop.py); chance = 1/420 = 0.24 %
+    assert h1 > 8.0 and h1_csls > 8.0, (h1, h1_csls)
     for f in ("ent_embeds.npy", "rel_embeds.npy", "alignment_results_12", "kg1_ent_ids", "kg2_rel_ids", "kg1_ent_embeds_txt"):
         assert os.path.exists(model.out_folder + f), f
     ent = np.load(model.out_folder + "ent_embeds.npy")
@@ -67,11 +74,11 @@ def test_mtranse_lifecycle(cuda_device, tiny_kgs, tmp_path):
     from openea_b200 import presets
     from openea_b200.approaches import MTransE
     args = presets.mtranse("15K", dim=75)          # BASELINE config 1 uses dim 75 (pitch 76 internally)
-    args.batch_size, args.max_epoch, args.start_valid = 1000, 60, 30
+    args.batch_size, args.max_epoch, args.start_valid, args.eval_freq = 1000, 400, 390, 10
     model, out = _run(MTransE, args, tiny_kgs, "mapping", tmp_path)
     assert "avg. mapping loss" in out and "quick results:" in out
     h1 = _hits1(out, "accurate results:")
-    assert h1 > 5.0, h1
+    assert h1 > 2.0, h1            # 8× chance; MTransE is the weakest approach of the reference's tables too
     assert os.path.exists(model.out_folder + "mapping_mat.npy")
     assert np.load(model.out_folder + "ent_embeds.npy").shape[1] == 75
 
@@ -80,6 +87,64 @@ def test_transe_margin_lifecycle(cuda_device, tiny_kgs, tmp_path):
     from openea_b200 import presets
     from openea_b200.models.trans import TransE
     args = presets.transe("15K")
-    args.batch_size, args.max_epoch, args.start_valid, args.dim = 1000, 40, 20, 32
+    args.batch_size, args.max_epoch, args.start_valid, args.dim = 1000, 300, 1000, 32
     model, out = _run(TransE, args, tiny_kgs, "sharing", tmp_path)
-    assert _hits1(out, "accurate results:") > 10.0
+    # calibration: the CPU oracle loop with the same loss reaches 2.6 % at 150 epochs (0.24 % = chance)
+    h10 = float(re.findall(r"accurate results: hits@\[1, 5, 10, 50\] = \[\s*[0-9.]+\s+[0-9.]+\s+([0-9.]+)", out)[-1])
+    assert h10 > 8.0, h10          # chance for Hits@10 = 2.4 %
+
+
+def _engine_aligne(arr, dim, B, k, epochs, seed):
+    import torch
+    from openea_b200 import engine as eng
+    from openea_b200 import finding as F
+    g = torch.Generator().manual_seed(seed)
+    std = dim ** -0.5
+    tn = lambda n: torch.nn.init.trunc_normal_(torch.empty(n, dim), std=std, a=-2 * std, b=2 * std, generator=g)
+    ent, rel = eng.EmbeddingTable(tn(arr["n_ent"]), True), eng.EmbeddingTable(tn(arr["n_rel"]), True)
+    trn = eng.TripleTrainer(ent, rel, eng.loss_cfg("limited", "L2", 0.01, 2.0, 0.2), 0.01)
+    kg1 = eng.DeviceKG(arr["triples1"], arr["entities1"], arr["n_ent"])
+    kg2 = eng.DeviceKG(arr["triples2"], arr["entities2"], arr["n_ent"])
+    tset = eng.DeviceTripleSet([kg1.triples, kg2.triples], arr["n_ent"], arr["n_rel"])
+    steps = -(-(kg1.triples.shape[0] + kg2.triples.shape[0]) // B)
+    losses = []
+    for epoch in range(1, epochs + 1):
+        for step in range(steps):
+            trn.score_sampled(kg1, kg2, tset, B, k, step, 7919 * seed + epoch)
+            trn.apply()
+        losses.append(trn.read_loss() / (kg1.triples.shape[0] + kg2.triples.shape[0]))
+        if epoch % 10 == 0:
+            for kg, ents in ((kg1, arr["entities1"]), (kg2, arr["entities2"])):
+                kg.set_candidates(F.find_neighbours_device(ent.lookup(ents), ents, int(0.1 * len(ents))), ents)
+    links = arr["test_links"]
+    _, _, hits, mr, mrr = F.eval_alignment(ent.lookup(links[:, 0]), ent.lookup(links[:, 1]), [1, 5, 10, 50], "inner", False, 0)
+    return hits, mrr, losses
+
+
+def test_aligne_hits_parity_with_cpu_oracle(cuda_device):
+    """End-to-end statistical parity: the engine and the CPU oracle loop (reference sampler + dense TF-style
+    step, oracle/train_loop.py) train AlignE for the same number of epochs on the same synthetic KG from the
+    same init distribution; per-epoch loss curves and Hits@k agree within seed-to-seed noise (420 test links,
+    different RNG streams; seed noise of the oracle alone is ≈ ±1.5 % Hits@1)."""
+    import numpy as np
+    from oracle import train_loop as tl
+    from openea_b200.synth import synth_id_arrays
+    arr = synth_id_arrays("tiny")
+    dim, B, k, epochs = 32, 1000, 10, 150
+    o_hits, o_loss = [], []
+    for seed in (3, 4):
+        log = []
+        st = tl.train_triples(arr, dim, B, k, epochs, truncated_eps=0.9, seed=seed, log=log.append)
+        o_hits.append(tl.test_hits(st, arr)[0])
+        o_loss.append([float(x.split(":")[-1]) for x in log])
+    e_hits, e_loss = [], []
+    for seed in (1, 2, 3, 4):
+        hits, mrr, losses = _engine_aligne(arr, dim, B, k, epochs, seed)
+        e_hits.append(hits)
+        e_loss.append(losses)
+    o_hits, e_hits = np.mean(o_hits, 0), np.mean(e_hits, 0)
+    o_loss, e_loss = np.mean(o_loss, 0), np.mean(e_loss, 0)
+    print("engine hits", e_hits, "| oracle hits", o_hits)
+    print("loss @1,10,50,150: engine", e_loss[[0, 9, 49, 149]], "oracle", o_loss[[0, 9, 49, 149]])
+    np.testing.assert_allclose(e_loss[[0, 9, 49, 149]], o_loss[[0, 9, 49, 149]], rtol=0.03)
+    assert abs(e_hits[0] - o_hits[0]) <= 3.5 and abs(e_hits[2] - o_hits[2]) <= 6.0, (e_hits, o_hits)
