@@ -131,6 +131,10 @@ int oea_triple_score_fed(const oea_table* ent, const oea_table* rel,
  * Leaves grad = 0 and touched = 0. */
 int oea_rowopt_apply(const oea_table* table, const oea_opt_cfg* opt, void* stream);
 
+/* The optimiser step of BOTH tables in one launch (Adagrad / SGD; Adam falls back to two dense launches).
+ * Same semantics as two oea_rowopt_apply calls. */
+int oea_rowopt_apply_pair(const oea_table* a, const oea_table* b, const oea_opt_cfg* opt, void* stream);
+
 /* Fused on-device step: batch slicing + negative sampling of modules/train/batch.py:36-119 and the
  * forward/backward above in ONE kernel (no index buffers).  Positive p of step s is
  * triples[perm_epoch(s·B_kg + p)] with B_1 = ⌊B·T1/(T1+T2)⌋, B_2 = B − B_1 (batch.py:39-42);
@@ -145,6 +149,13 @@ int oea_triple_score_sampled(const oea_table* ent, const oea_table* rel,
                              const oea_kg_view* kg1, const oea_kg_view* kg2, const oea_tripleset* tset,
                              const oea_sample_cfg* smp, const oea_loss_cfg* loss,
                              double* loss_out, int32_t* n_pos_out, int32_t* dbg_neg, void* stream);
+
+/* One whole training step in one call: oea_triple_score_sampled + oea_rowopt_apply_pair (what one
+ * session.run([triple_loss, triple_optimizer]) of basic_model.py:224 does, without the feed). */
+int oea_triple_step_sampled(const oea_table* ent, const oea_table* rel,
+                            const oea_kg_view* kg1, const oea_kg_view* kg2, const oea_tripleset* tset,
+                            const oea_sample_cfg* smp, const oea_loss_cfg* loss, const oea_opt_cfg* opt,
+                            double* loss_out, int32_t* n_pos_out, void* stream);
 
 /* Reference-facing synchronous step with HOST index buffers (the session.run(feed_dict) boundary of
  * models/basic_model.py:222-232): H2D copy of the six index vectors into `dev_idx_ws`

@@ -20,6 +20,7 @@ enum { EPI_TOPK = 0, EPI_RANK = 1, EPI_STORE = 2 };
 constexpr int TM = 128, TN = 128, BK = 16;
 constexpr int SIM_THREADS = 256;
 constexpr int KMAX = 32;  // per-row top-k list lives in one warp's lanes
+constexpr int TS_LD = TN + 4;  // tile staging row stride: 16-B aligned rows, conflict-free 128-bit stores
 
 // similarity value from the accumulated contraction (similarity.py:36-51)
 template <int METRIC>
@@ -44,7 +45,7 @@ struct SimParams {
     const float* row_off; const float* col_off;  // CSLS r_i / c_j or nullptr
     int col_tiles_per_split;
     // top-k
-    int k; float* part_val; int* part_idx; int splits;
+    int k, kcap; float* part_val; int* part_idx; int splits;
     // rank
     const int* gold; const float* gold_val; unsigned long long* best; int* rank;
     // store
@@ -52,14 +53,14 @@ struct SimParams {
 };
 
 template <int METRIC, int EPI>
-__global__ void __launch_bounds__(SIM_THREADS)
+__global__ void __launch_bounds__(SIM_THREADS, 2)
 k_sim_tile(SimParams P) {
     extern __shared__ __align__(16) float smem[];
     float (*As)[BK][TM] = reinterpret_cast<float (*)[BK][TM]>(smem);                 // [2][BK][TM]
     float (*Bs)[BK][TN] = reinterpret_cast<float (*)[BK][TN]>(smem + 2 * BK * TM);   // [2][BK][TN]
-    float* Ts = smem + 2 * BK * TM + 2 * BK * TN;                                    // [TM][TN+1] (TOPK only)
-    float* Lv = Ts + TM * (TN + 1);                                                  // [TM][KMAX]
-    int* Li = reinterpret_cast<int*>(Lv + TM * KMAX);                                // [TM][KMAX]
+    float* Ts = smem + 2 * BK * TM + 2 * BK * TN;                                    // [TM][TS_LD] (TOPK only)
+    float* Lv = Ts + (TM / 2) * TS_LD;                                            // [TM][kcap]
+    int* Li = reinterpret_cast<int*>(Lv + TM * P.kcap);                              // [TM][kcap]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tx = tid & 15, ty = tid >> 4;
@@ -75,22 +76,12 @@ k_sim_tile(SimParams P) {
     const float* aptr = P.e1 + (size_t)(arow_ok ? arow : 0) * P.pitch1 + lhalf * 8;
 
     if (EPI == EPI_TOPK) {
-        for (int i = tid; i < TM * KMAX; i += SIM_THREADS) { Lv[i] = -FLT_MAX; Li[i] = -1; }
+        for (int i = tid; i < TM * P.kcap; i += SIM_THREADS) { Lv[i] = -FLT_MAX; Li[i] = -1; }
     }
-    // per-thread rank state (EPI_RANK)
-    float gval[8], bestv[8]; int besti[8], cnt[8], goldc[8];
-    float roff[8];
+    // per-thread rank state (EPI_RANK): counters + running arg-max; gold value/column are re-read per tile
+    float bestv[8]; int besti[8], cnt[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int r = row0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4);
-        const bool ok = r < P.n1;
-        roff[i] = (P.row_off && ok) ? __ldg(P.row_off + r) : 0.f;
-        if (EPI == EPI_RANK) {
-            gval[i] = ok ? __ldg(P.gold_val + r) : FLT_MAX;
-            goldc[i] = ok ? __ldg(P.gold + r) : -1;
-            bestv[i] = -FLT_MAX; besti[i] = 0x7fffffff; cnt[i] = 0;
-        }
-    }
+    for (int i = 0; i < 8; ++i) { bestv[i] = -FLT_MAX; besti[i] = 0x7fffffff; cnt[i] = 0; }
     const int nk = (P.kdim + BK - 1) / BK;
 
     for (int ct = ct0; ct < ct1; ++ct) {
@@ -132,8 +123,9 @@ k_sim_tile(SimParams P) {
         for (int kc = 0; kc < nk; ++kc) {
             const int buf = kc & 1;
             if (kc + 1 < nk) gload(kc + 1);
-#pragma unroll
-            for (int kk = 0; kk < BK; ++kk) {
+            const int kk_end = min(BK, P.kdim - kc * BK);   // kdim % 4 == 0: the tail chunk runs 4, 8 or 12 steps
+#pragma unroll 4
+            for (int kk = 0; kk < kk_end; ++kk) {
                 const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
                 const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][64 + ty * 4]);
                 const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
@@ -152,59 +144,76 @@ k_sim_tile(SimParams P) {
         }
 
         // ---- epilogue ----
-        float coff[8];
+        float coff[8], roff[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int c = col0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + j - 4);
             coff[j] = (P.col_off && c < P.n2) ? __ldg(P.col_off + c) : 0.f;
+            const int r = row0 + (j < 4 ? ty * 4 + j : 64 + ty * 4 + j - 4);
+            roff[j] = (P.row_off && r < P.n1) ? __ldg(P.row_off + r) : 0.f;
         }
         const bool use_csls = P.row_off != nullptr;
         if (EPI == EPI_TOPK) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int rl = i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int cl = j < 4 ? tx * 4 + j : 64 + tx * 4 + j - 4;
-                    float v = sim_value<METRIC>(acc[i][j]);
-                    if (use_csls) v = csls_value(v, roff[i], coff[j]);
-                    if (col0 + cl >= P.n2) v = -FLT_MAX;
-                    Ts[rl * (TN + 1) + cl] = v;
-                }
-            }
-            __syncthreads();
+            // two halves of 64 rows (thread rows i = 0..3, then 4..7) through a 64-row staging buffer
             const int k = P.k;
-            for (int rl = warp; rl < TM; rl += SIM_THREADS / 32) {
-                float lv = Lv[rl * KMAX + lane];
-                int li = Li[rl * KMAX + lane];
-                float tau = __shfl_sync(OEA_FULL, lv, k - 1);
-                bool changed = false;
 #pragma unroll
-                for (int m = 0; m < TN / 32; ++m) {
-                    const float c = Ts[rl * (TN + 1) + lane + 32 * m];
-                    unsigned pass = __ballot_sync(OEA_FULL, c > tau);
-                    while (pass) {
-                        const int src = __ffs(pass) - 1;
-                        pass &= pass - 1;
-                        const float cv = __shfl_sync(OEA_FULL, c, src);
-                        if (!(cv > tau)) continue;   // tau rose since the ballot
-                        const int ci = col0 + src + 32 * m;
-                        // entries with value >= cv keep their place (they have lower column indices)
-                        const int pos = __popc(__ballot_sync(OEA_FULL, lane < k && lv >= cv));
-                        const float up_v = __shfl_up_sync(OEA_FULL, lv, 1);
-                        const int up_i = __shfl_up_sync(OEA_FULL, li, 1);
-                        if (lane > pos) { lv = up_v; li = up_i; }
-                        else if (lane == pos) { lv = cv; li = ci; }
-                        tau = __shfl_sync(OEA_FULL, lv, k - 1);
-                        changed = true;
+            for (int half = 0; half < 2; ++half) {
+                if (half == 1) __syncthreads();   // scan of half 0 finished before Ts is overwritten
+#pragma unroll
+                for (int ii = 0; ii < 4; ++ii) {
+                    const int i = half * 4 + ii;
+                    const int rl = ty * 4 + ii;   // row inside the half
+#pragma unroll
+                    for (int jj = 0; jj < 2; ++jj) {
+                        const int cl = jj == 0 ? tx * 4 : 64 + tx * 4;
+                        float v[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            v[j] = sim_value<METRIC>(acc[i][jj * 4 + j]);
+                            if (use_csls) v[j] = csls_value(v[j], roff[i], coff[jj * 4 + j]);
+                            if (col0 + cl + j >= P.n2) v[j] = -FLT_MAX;
+                        }
+                        *reinterpret_cast<float4*>(&Ts[rl * TS_LD + cl]) = make_float4(v[0], v[1], v[2], v[3]);
                     }
                 }
-                if (changed) { Lv[rl * KMAX + lane] = lv; Li[rl * KMAX + lane] = li; }
+                __syncthreads();
+                for (int rh = warp; rh < TM / 2; rh += SIM_THREADS / 32) {
+                    const int rl = half * 64 + rh;   // row inside the tile
+                    float lv = lane < P.kcap ? Lv[rl * P.kcap + lane] : -FLT_MAX;
+                    int li = lane < P.kcap ? Li[rl * P.kcap + lane] : -1;
+                    float tau = __shfl_sync(OEA_FULL, lv, k - 1);
+                    bool changed = false;
+#pragma unroll
+                    for (int m = 0; m < TN / 32; ++m) {
+                        const float c = Ts[rh * TS_LD + lane + 32 * m];
+                        unsigned pass = __ballot_sync(OEA_FULL, c > tau);
+                        while (pass) {
+                            const int src = __ffs(pass) - 1;
+                            pass &= pass - 1;
+                            const float cv = __shfl_sync(OEA_FULL, c, src);
+                            if (!(cv > tau)) continue;   // tau rose since the ballot
+                            const int ci = col0 + src + 32 * m;
+                            // entries with value >= cv keep their place (they have lower column indices)
+                            const int pos = __popc(__ballot_sync(OEA_FULL, lane < k && lv >= cv));
+                            const float up_v = __shfl_up_sync(OEA_FULL, lv, 1);
+                            const int up_i = __shfl_up_sync(OEA_FULL, li, 1);
+                            if (lane > pos) { lv = up_v; li = up_i; }
+                            else if (lane == pos) { lv = cv; li = ci; }
+                            tau = __shfl_sync(OEA_FULL, lv, k - 1);
+                            changed = true;
+                        }
+                    }
+                    if (changed && lane < P.kcap) { Lv[rl * P.kcap + lane] = lv; Li[rl * P.kcap + lane] = li; }
+                }
             }
             // the next tile's first __syncthreads orders these smem reads before Ts is rewritten
         } else if (EPI == EPI_RANK) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
+                const int r = row0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4);
+                const bool ok = r < P.n1;
+                const float gval = ok ? __ldg(P.gold_val + r) : FLT_MAX;
+                const int goldc = ok ? __ldg(P.gold + r) : -1;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const int c = col0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + j - 4);
@@ -212,7 +221,7 @@ k_sim_tile(SimParams P) {
                     if (use_csls) v = csls_value(v, roff[i], coff[j]);
                     if (c < P.n2) {
                         // rank of gold = #{better} + #{equal with a lower index} ("lower index wins")
-                        cnt[i] += (v > gval[i]) || (v == gval[i] && c < goldc[i]);
+                        cnt[i] += (v > gval) || (v == gval && c < goldc);
                         if (v > bestv[i]) { bestv[i] = v; besti[i] = c; }   // columns ascend per thread
                     }
                 }
@@ -248,8 +257,8 @@ k_sim_tile(SimParams P) {
             const int r = row0 + rl;
             if (r < P.n1 && lane < P.k) {
                 const size_t o = ((size_t)r * P.splits + blockIdx.y) * P.k + lane;
-                P.part_val[o] = Lv[rl * KMAX + lane];
-                P.part_idx[o] = Li[rl * KMAX + lane];
+                P.part_val[o] = Lv[rl * P.kcap + lane];
+                P.part_idx[o] = Li[rl * P.kcap + lane];
             }
         }
     } else if (EPI == EPI_RANK) {
@@ -349,9 +358,9 @@ k_rows_normalize(const float* __restrict__ in, int in_pitch, int n, int dim, flo
     for (int c = lane; c < out_pitch; c += 32) dst[c] = c < dim ? src[c] * inv : 0.f;
 }
 
-static size_t sim_smem_bytes(int epi) {
+static size_t sim_smem_bytes(int epi, int kcap) {
     size_t f = 2 * BK * TM + 2 * BK * TN;
-    if (epi == EPI_TOPK) f += TM * (TN + 1) + 2 * TM * KMAX;
+    if (epi == EPI_TOPK) f += (TM / 2) * TS_LD + 2 * TM * kcap;
     return f * sizeof(float);
 }
 
@@ -376,7 +385,7 @@ static int sm_count() {
 template <int EPI>
 static int launch_sim(const oea_sim_cfg* c, SimParams& P, int splits, cudaStream_t st) {
     const dim3 grid((c->n1 + TM - 1) / TM, splits);
-    const size_t smem = sim_smem_bytes(EPI);
+    const size_t smem = sim_smem_bytes(EPI, P.kcap);
 #define OEA_SIM_LAUNCH(M)                                                                                     \
     do {                                                                                                      \
         OEA_CUDA_TRY(cudaFuncSetAttribute(k_sim_tile<M, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
@@ -440,6 +449,7 @@ extern "C" int oea_sim_topk(const oea_sim_cfg* c, const float* e1, const float* 
     const int eff_splits = (col_tiles + P.col_tiles_per_split - 1) / P.col_tiles_per_split;
     P.splits = eff_splits;
     P.k = k;
+    P.kcap = k <= 8 ? 8 : (k <= 16 ? 16 : 32);
     P.part_val = (float*)workspace;
     P.part_idx = (int*)((char*)workspace + (size_t)c->n1 * splits * k * sizeof(float));
     rc = launch_sim<EPI_TOPK>(c, P, eff_splits, st); if (rc) return rc;

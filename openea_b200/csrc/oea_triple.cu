@@ -689,6 +689,8 @@ extern "C" int oea_triple_score_sampled(const oea_table* ent, const oea_table* r
     return OEA_OK;
 }
 
+extern "C" int oea_rowopt_apply_pair(const oea_table* a, const oea_table* b, const oea_opt_cfg* opt, void* stream);
+
 extern "C" int oea_triple_step_fed_host(const oea_table* ent, const oea_table* rel,
                                         const int32_t* pos_hrt_host, int32_t n_pos,
                                         const int32_t* neg_hrt_host, int32_t n_neg,
@@ -707,8 +709,7 @@ extern "C" int oea_triple_step_fed_host(const oea_table* ent, const oea_table* r
     int rc = oea_triple_score_fed(ent, rel, dpos, dpos + n_pos, dpos + 2 * (size_t)n_pos, n_pos,
                                   dneg, dneg + n_neg, dneg + 2 * (size_t)n_neg, n_neg, loss, dev_loss_ws, stream);
     if (rc) return rc;
-    rc = oea_rowopt_apply(ent, opt, stream); if (rc) return rc;
-    rc = oea_rowopt_apply(rel, opt, stream); if (rc) return rc;
+    rc = oea_rowopt_apply_pair(ent, rel, opt, stream); if (rc) return rc;
     OEA_CUDA_TRY(cudaMemcpyAsync(loss_pinned_host, dev_loss_ws, sizeof(double), cudaMemcpyDeviceToHost, st));
     OEA_CUDA_TRY(cudaStreamSynchronize(st));
     *loss_host = (float)(*loss_pinned_host);
@@ -968,4 +969,76 @@ extern "C" int oea_mapping_fwd_bwd(const float* e1, const float* e2, int32_t n, 
     k_mapping_orth_grad<<<dim, 256, 0, st>>>(M, dim, mpitch, alpha, (const float*)workspace, g_M);
     OEA_LAUNCH_CHECK();
     return OEA_OK;
+}
+
+// ================================================================================================
+// One call per training step: fused sampler+scorer, then ONE row-optimiser launch over both tables.
+// ================================================================================================
+namespace oea {
+
+struct OptTab { float* w; float* g; float* s1; int32_t* touched; int rows; };
+
+// Adagrad / SGD over the concatenated row space [ent rows | rel rows] (same pitch), flagged rows only.
+template <int KIND>
+__global__ void __launch_bounds__(kThreads)
+k_rowopt_pair(OptTab A, OptTab B, int pitch, float lr) {
+    const int lane = threadIdx.x & 31;
+    const int warp_global = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int n_warps = gridDim.x * kWarpsPerBlock;
+    const int p4 = pitch >> 2;
+    const int total = A.rows + B.rows;
+    for (int r = warp_global; r < total; r += n_warps) {
+        const bool first = r < A.rows;
+        const OptTab& T = first ? A : B;
+        const int row = first ? r : r - A.rows;
+        if (T.touched[row] == 0) continue;
+        const size_t base = (size_t)row * pitch;
+        for (int c = lane; c < p4; c += OEA_WARP) {
+            const size_t o = base + 4 * (size_t)c;
+            const float4 g = *reinterpret_cast<const float4*>(T.g + o);
+            float4 x = *reinterpret_cast<float4*>(T.w + o);
+            if (KIND == OEA_OPT_ADAGRAD) {
+                float4 a = *reinterpret_cast<float4*>(T.s1 + o);
+                a.x = fmaf(g.x, g.x, a.x); a.y = fmaf(g.y, g.y, a.y); a.z = fmaf(g.z, g.z, a.z); a.w = fmaf(g.w, g.w, a.w);
+                x.x -= lr * g.x * rsqrtf(a.x); x.y -= lr * g.y * rsqrtf(a.y);
+                x.z -= lr * g.z * rsqrtf(a.z); x.w -= lr * g.w * rsqrtf(a.w);
+                *reinterpret_cast<float4*>(T.s1 + o) = a;
+            } else {
+                x.x -= lr * g.x; x.y -= lr * g.y; x.z -= lr * g.z; x.w -= lr * g.w;
+            }
+            *reinterpret_cast<float4*>(T.w + o) = x;
+            *reinterpret_cast<float4*>(T.g + o) = f4(0.f);
+        }
+        if (lane == 0) T.touched[row] = 0;
+    }
+}
+
+}  // namespace oea
+
+extern "C" int oea_rowopt_apply_pair(const oea_table* a, const oea_table* b, const oea_opt_cfg* opt, void* stream) {
+    int rc = check_table(a, true); if (rc) return rc;
+    rc = check_table(b, true); if (rc) return rc;
+    if (!opt) return OEA_ERR_NULL;
+    if (opt->kind == OEA_OPT_ADAM || a->pitch != b->pitch) {   // dense Adam / mismatched pitch: two launches
+        rc = oea_rowopt_apply(a, opt, stream); if (rc) return rc;
+        return oea_rowopt_apply(b, opt, stream);
+    }
+    if (opt->kind == OEA_OPT_ADAGRAD && (!a->state1 || !b->state1)) return OEA_ERR_NULL;
+    OptTab A{a->weight, a->grad, a->state1, a->touched, a->rows}, B{b->weight, b->grad, b->state1, b->touched, b->rows};
+    const int grid = grid_for(a->rows + b->rows);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (opt->kind == OEA_OPT_ADAGRAD) k_rowopt_pair<OEA_OPT_ADAGRAD><<<grid, kThreads, 0, st>>>(A, B, a->pitch, opt->lr);
+    else if (opt->kind == OEA_OPT_SGD) k_rowopt_pair<OEA_OPT_SGD><<<grid, kThreads, 0, st>>>(A, B, a->pitch, opt->lr);
+    else return OEA_ERR_KIND;
+    OEA_LAUNCH_CHECK();
+    return OEA_OK;
+}
+
+extern "C" int oea_triple_step_sampled(const oea_table* ent, const oea_table* rel,
+                                       const oea_kg_view* kg1, const oea_kg_view* kg2, const oea_tripleset* tset,
+                                       const oea_sample_cfg* smp, const oea_loss_cfg* loss, const oea_opt_cfg* opt,
+                                       double* loss_out, int32_t* n_pos_out, void* stream) {
+    int rc = oea_triple_score_sampled(ent, rel, kg1, kg2, tset, smp, loss, loss_out, n_pos_out, nullptr, stream);
+    if (rc) return rc;
+    return oea_rowopt_apply_pair(ent, rel, opt, stream);
 }

@@ -219,9 +219,31 @@ class TripleTrainer:
         for tab in (self.ent, self.rel):
             if tab.optimizer == "Adam":
                 tab.adam_t += 1
-            cfg = opt_cfg(tab, self.lr)
-            L.check(self.lib.oea_rowopt_apply(C.byref(tab.c_struct()), C.byref(cfg), _stream_ptr()),
-                    "oea_rowopt_apply")
+        cfg = opt_cfg(self.ent, self.lr)
+        L.check(self.lib.oea_rowopt_apply_pair(C.byref(self.ent.c_struct()), C.byref(self.rel.c_struct()), C.byref(cfg),
+                                               _stream_ptr()), "oea_rowopt_apply_pair")
+
+    def step_sampled(self, kg1, kg2, tset, batch_size, neg_per_pos, step, epoch_seed, max_try=10, n_pos_out=None):
+        """One whole training step in one C call (fused sampler+scorer, then one optimiser launch)."""
+        smp = L.SampleCfg(int(batch_size), int(neg_per_pos), int(step), int(max_try), int(epoch_seed) & (2**64 - 1))
+        views = self._views(kg1, kg2, tset)
+        for tab in (self.ent, self.rel):
+            if tab.optimizer == "Adam":
+                tab.adam_t += 1
+        cfg = opt_cfg(self.ent, self.lr)
+        L.check(self.lib.oea_triple_step_sampled(
+            C.byref(self.ent.c_struct()), C.byref(self.rel.c_struct()), C.byref(views[0]), C.byref(views[1]),
+            C.byref(views[2]), C.byref(smp), C.byref(self.loss), C.byref(cfg), _ptr(self.loss_dev), _ptr(n_pos_out),
+            _stream_ptr()), "oea_triple_step_sampled")
+
+    def _views(self, kg1, kg2, tset):
+        """ctypes views of the KGs / triple set, cached until their device buffers change."""
+        key = (kg1.triples.data_ptr(), kg2.triples.data_ptr(), 0 if kg1.cand is None else kg1.cand.data_ptr(),
+               0 if kg2.cand is None else kg2.cand.data_ptr(), tset.slots.data_ptr())
+        if getattr(self, "_view_key", None) != key:
+            self._view_key = key
+            self._view_val = (kg1.view(), kg2.view(), tset.view())
+        return self._view_val
 
     def score_sampled(self, kg1, kg2, tset, batch_size, neg_per_pos, step, epoch_seed, max_try=10,
                       loss_out=None, dbg=None, n_pos_out=None):

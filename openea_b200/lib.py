@@ -68,6 +68,9 @@ SIGNATURES = {
     "oea_error_string": (C.c_char_p, [C.c_int]),
     "oea_triple_score_fed": (C.c_int, [_TP, _TP, _P, _P, _P, _I, _P, _P, _P, _I, C.POINTER(LossCfg), _P, _P]),
     "oea_rowopt_apply": (C.c_int, [_TP, C.POINTER(OptCfg), _P]),
+    "oea_rowopt_apply_pair": (C.c_int, [_TP, _TP, C.POINTER(OptCfg), _P]),
+    "oea_triple_step_sampled": (C.c_int, [_TP, _TP, C.POINTER(KgView), C.POINTER(KgView), C.POINTER(TripleSet),
+                                          C.POINTER(SampleCfg), C.POINTER(LossCfg), C.POINTER(OptCfg), _P, _P, _P]),
     "oea_triple_score_sampled": (C.c_int, [_TP, _TP, C.POINTER(KgView), C.POINTER(KgView), C.POINTER(TripleSet),
                                            C.POINTER(SampleCfg), C.POINTER(LossCfg), _P, _P, _P, _P]),
     "oea_triple_step_fed_host": (C.c_int, [_TP, _TP, _P, _I, _P, _I, C.POINTER(LossCfg), C.POINTER(OptCfg),

@@ -224,8 +224,7 @@ class BasicModel:
         trained_samples_num = 0
         trainer = self.triple_trainer
         for step in range(triple_steps):
-            trainer.score_sampled(kg1, kg2, tset, self.args.batch_size, self.neg_per_pos, step, self._epoch_seed)
-            trainer.apply()
+            trainer.step_sampled(kg1, kg2, tset, self.args.batch_size, self.neg_per_pos, step, self._epoch_seed)
             trained_samples_num += self._slice_count(t1, b1, step) + self._slice_count(t2, b2, step)
         epoch_loss = trainer.read_loss() / max(1, trained_samples_num)     # one device→host read per epoch
         print('epoch {}, avg. triple loss: {:.4f}, cost time: {:.4f}s'.format(epoch, epoch_loss, time.time() - start))
