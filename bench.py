@@ -94,14 +94,19 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def build_workload(wl, rank, device):
+def build_workload(wl, rank, device, world=1):
     """Synthetic KG of the workload's shape, resident on the device, plus tables and the trainer."""
     import torch
     from openea_b200 import engine as eng
     from openea_b200.synth import synth_id_arrays
     cfg = WORKLOADS[wl]
     arr = synth_id_arrays(cfg["shape"], seed=20200901)
-    g = torch.Generator(device="cpu").manual_seed(1234 + rank)
+    if world > 1:   # every rank trains on the triples whose head row it owns (openea_b200/parallel.py)
+        from openea_b200 import parallel as par
+        arr = dict(arr)
+        arr["triples1"] = np.ascontiguousarray(par.shard_triples(arr["triples1"], rank, world))
+        arr["triples2"] = np.ascontiguousarray(par.shard_triples(arr["triples2"], rank, world))
+    g = torch.Generator(device="cpu").manual_seed(1234)      # replicas start identical
     d = cfg["dim"]
     # init='normal': truncated normal σ = 1/√d (initializers.py:29-34); plain clamp-resampled normal here
     ent0 = torch.nn.init.trunc_normal_(torch.empty(arr["n_ent"], d), std=d ** -0.5, a=-2 * d ** -0.5, b=2 * d ** -0.5, generator=g)
@@ -217,6 +222,36 @@ def bench_csls(shape, device, reps=3):
             "note": "inner + CSLS(k=10), exact ranks; includes host-side reduction of the rank vector"}
 
 
+def bench_csls_sharded(shape, device, reps=3):
+    """CSLS evaluation with E1's rows block-sharded over the ranks (E2 replicated, one all-gather of partial
+    column top-k lists).  Time = max over ranks (device events)."""
+    import torch
+    import torch.distributed as dist
+    from openea_b200 import finding as F
+    from openea_b200.synth import SHAPES
+    n, d = SHAPES[shape]["links"][2], 100
+    g = torch.Generator(device="cpu").manual_seed(99)
+    e2 = torch.randn(n, d, generator=g)
+    e1 = (e2 + 0.5 * torch.randn(n, d, generator=g)).to(device)
+    e2 = e2.to(device)
+    times = []
+    for i in range(reps + 1):
+        dist.barrier()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        hits, mr, mrr, _ = F.eval_alignment_sharded(e1, e2, [1, 5, 10, 50], "inner", False, 10)
+        ev1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if i:
+            times.append(float(t.item()))
+    ms = float(np.median(times))
+    return {"metric": "CSLS pairs/sec", "value": float(n) * n / (ms * 1e-3), "unit": "pairs/s", "n1": n, "n2": n, "dim": d,
+            "ms": ms, "hits1": hits[0], "sharding": "E1 row blocks per rank, E2 replicated, all-gather of partial column top-k"}
+
+
 _T0 = time.perf_counter()
 
 
@@ -240,7 +275,8 @@ def main():
     cfg = WORKLOADS[args.workload]
     unit = "positive triples/s"
     config = {"workload": cfg["name"], "batch_size": cfg["batch"], "neg_per_pos": cfg["k"], "dim": cfg["dim"],
-              "sharding": "replicas" if world > 1 else "single", "l2": "flushed between timed steps (512 MiB write)"}
+              "sharding": ("triples sharded by head-row owner (id mod G), replicated tables, per-epoch NCCL all-gather of "
+                           "seed-pair rows") if world > 1 else "single", "l2": "flushed between timed steps (512 MiB write)"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -264,7 +300,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     _phase("cuda ready; building workload")
-    W = build_workload(args.workload, rank, device)
+    W = build_workload(args.workload, rank, device, world)
     _phase("workload resident")
     tr, kg1, kg2, tset = W["trainer"], W["kg1"], W["kg2"], W["tset"]
     B, k, d = cfg["batch"], cfg["k"], cfg["dim"]
@@ -272,12 +308,25 @@ def main():
     flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device=device)
     npos_dev = torch.zeros(1, dtype=torch.int32, device=device)
 
+    sync = None
+    if world > 1:
+        from openea_b200 import parallel as par
+        seeds = np.concatenate([W["arr"]["train_links"][:, 0], W["arr"]["train_links"][:, 1]])
+        sync = par.SeedRowSync(W["ent"].weight, seeds, rank, world)
+    full_steps = max(1, spe - 1) if spe > 1 else 1   # full batches per local epoch (the ragged last step is skipped)
+    n_syncs = [0]
+
     def one_step(i, ev=None):
-        # every rank walks the epoch from its own offset: per-GPU work is fixed (weak scaling)
-        step = (i + rank * 7) % max(1, spe - 1)
-        seed = 0xB007EA + 1000003 * ((i + rank * 7) // max(1, spe - 1)) + rank
+        # weak scaling: every rank steps through ITS shard with the full per-GPU batch; at each local epoch
+        # boundary the owners' seed-pair rows are all-gathered into every replica (the only collective)
+        step = i % full_steps
+        seed = 0xB007EA + 1000003 * (i // full_steps) + rank
         if ev:
             ev[0].record()
+        if sync is not None and step == 0 and i > 0:
+            sync.sync()
+            n_syncs[0] += 1
+        if ev:
             tr.score_sampled(kg1, kg2, tset, B, k, step, seed, n_pos_out=npos_dev)
             ev[1].record()
             tr.apply()
@@ -341,7 +390,7 @@ def main():
         host_batches = []
         dbg = torch.empty(B, 2 + k, dtype=torch.int32, device=device)
         for i in range(n_b):
-            tr.score_sampled(kg1, kg2, tset, B, k, i % max(1, spe - 1), 0xE2E + i + rank, dbg=dbg, n_pos_out=npos_dev)
+            tr.score_sampled(kg1, kg2, tset, B, k, i % full_steps, 0xE2E + i + rank, dbg=dbg, n_pos_out=npos_dev)
             torch.cuda.synchronize()
             pos, neg = decode_dbg(dbg.cpu().numpy(), int(npos_dev.item()), t1, t2, k)
             host_batches.append((torch.from_numpy(pos).pin_memory(), torch.from_numpy(neg).pin_memory()))
@@ -375,8 +424,10 @@ def main():
 
     _phase("cpu baseline done")
     csls = None
-    if rank == 0 and world == 1:
+    if world == 1:
         csls = bench_csls(cfg["shape"], device)
+    else:
+        csls = bench_csls_sharded(cfg["shape"], device)
     _phase("csls done")
     # clocks: the timed region is a few ms, shorter than nvidia-smi's sampling period; continue the SAME loop
     # untimed under the sampler until it has >= 5 samples so the clocks line reflects this load
@@ -400,7 +451,9 @@ def main():
                 "scored_triples_per_s": value * (1 + k), "positives_per_step": n_pos_step,
                 "gpu_launches": 2 * K, "kernels": ["k_score_sampled", "k_rowopt_pair(ent+rel)"],
                 "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_base, "clocks": clk, "csls": csls,
-                "wall_s_timed_region": t_wall, "last_loss_sum": loss_val}
+                "wall_s_timed_region": t_wall, "last_loss_sum": loss_val,
+                "collective": None if sync is None else {"kind": "ncclAllGather of seed-pair rows per local epoch",
+                                                         "bytes_per_sync": sync.bytes_per_sync, "syncs_in_run": n_syncs[0]}}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -189,3 +189,32 @@ def find_alignment_device(embed1, embed2, sim_th, k, metric="inner", normalize=T
     keep = res["val"] > sim_th
     rows = torch.arange(e1.shape[0], device=e1.device, dtype=torch.int32)[:, None].expand_as(keep)[keep]
     return rows, res["idx"][keep], res["val"][keep]
+
+
+def eval_alignment_sharded(embed1, embed2, top_k, metric, normalize, csls_k):
+    """Multi-GPU greedy_alignment core: this rank evaluates a contiguous block of embed1's rows against ALL of
+    embed2 (replicated).  Row top-k / rank are local; the CSLS column means need one all-gather of each rank's
+    partial [n2, k] column lists.  Returns (hits list, mr, mrr) of the WHOLE problem on every rank, plus this
+    rank's (row range, top1, rank) tensors."""
+    from . import parallel as par
+    rank_id, ws = par.world()
+    e1_all, e2, d = _prep_pair(embed1, embed2, metric, normalize)
+    n1 = e1_all.shape[0]
+    lo, hi = par.block_range(n1, rank_id, ws)
+    e1 = e1_all[lo:hi].contiguous()
+    r = c = None
+    if csls_k > 0:
+        r = topk(e1, e2, d, metric, csls_k, want=("mean",))["mean"]             # local rows: exact
+        part = topk(e2, e1, d, metric, min(csls_k, hi - lo), want=("val",))["val"]   # columns over MY rows
+        if part.shape[1] < csls_k:   # fewer local rows than k: pad so the merge still sees k slots per rank
+            pad = torch.full((part.shape[0], csls_k - part.shape[1]), -3.0e38, device=part.device)
+            part = torch.cat([part, pad], 1)
+        c = par.merge_partial_topk(par.allgather_partial(part), csls_k)
+    gold = torch.arange(lo, hi, dtype=torch.int32, device=e1.device)
+    top1, rk = rank(e1, e2, d, metric, gold, r, c)
+    rk64 = rk.to(torch.float64)
+    stats = torch.stack([(rk < k).sum().to(torch.float64) for k in top_k] + [(rk64 + 1).sum(), (1.0 / (rk64 + 1)).sum()])
+    par.allreduce_sum(stats)
+    stats = stats.cpu().numpy()
+    hits = [round(float(x) / n1 * 100, 3) for x in stats[:len(top_k)]]
+    return hits, float(stats[-2] / n1), float(stats[-1] / n1), (lo, hi, top1, rk)

@@ -1,0 +1,55 @@
+"""GPU, >= 2 devices: the sharded CSLS evaluation over NCCL equals the single-GPU evaluation; the seed-row sync
+moves the owners' rows between replicas.  Skipped on single-GPU boxes (run with `gpurun --gpus 2`)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from openea_b200 import finding as F, parallel as par
+        rng = np.random.default_rng(0)
+        e2 = rng.standard_normal((3000, 100)).astype(np.float32)
+        e1 = (e2[:2500] + 0.5 * rng.standard_normal((2500, 100))).astype(np.float32)
+        for metric, csls in (("inner", 10), ("manhattan", 5), ("inner", 0)):
+            hits, mr, mrr, (lo, hi, top1, rk) = F.eval_alignment_sharded(e1, e2, [1, 5, 10], metric, metric == "inner", csls)
+            wtop1, wrk, whits, wmr, wmrr = F.eval_alignment(e1, e2, [1, 5, 10], metric, metric == "inner", csls)
+            assert hits == whits and abs(mr - wmr) < 1e-9 and abs(mrr - wmrr) < 1e-12, (metric, csls, hits, whits)
+            assert torch.equal(top1, wtop1[lo:hi]) and torch.equal(rk, wrk[lo:hi])
+        w = torch.full((101, 8), float(rank + 1), device="cuda")
+        par.SeedRowSync(w, np.array([3, 4, 10, 11, 50]), rank, world).sync()
+        assert float(w[3, 0]) == 3 % world + 1 and float(w[4, 0]) == 4 % world + 1 and float(w[5, 0]) == rank + 1
+        out.put((rank, "ok"))
+    except Exception as e:
+        out.put((rank, "FAIL: %r" % (e,)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_eval_equals_single_gpu():
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
