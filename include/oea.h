@@ -87,8 +87,10 @@ typedef struct oea_kg_view {
     int32_t        n_triples;
     const int32_t* entities;  /* [n_entities] entity ids of this KG (uniform candidate list) */
     int32_t        n_entities;
-    const int32_t* cand;      /* [cand_rows, n_cand] ε-truncated neighbour lists, or NULL */
-    const int32_t* ent2row;   /* [ent table rows] entity id → row of `cand`, −1 = no list; NULL iff cand NULL */
+    const int32_t* cand;      /* ε-truncated neighbour lists [cand_rows, n_cand], or NULL */
+    const int32_t* ent2row;   /* [ent table rows] entity id → row of `cand`, −1 = no list.  NULL with cand != NULL:
+                               * `cand` is indexed by ENTITY ID ([ent table rows, n_cand]) and a row whose first
+                               * element is −1 means "no list" (one dependent load less per positive) */
     int32_t        n_cand;
 } oea_kg_view;
 

@@ -46,6 +46,14 @@ __device__ __forceinline__ void red_add4(float* p, float4 v) {
                  :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// L2 prefetch of the 128-B lines a row of `bytes` bytes starting at p touches (p is 16-B aligned)
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+__device__ __forceinline__ void prefetch_row_l2(const float* row, int pitch_floats) {
+    const char* b = reinterpret_cast<const char*>(row);
+    const int bytes = pitch_floats * 4;
+    for (int o = 0; o < bytes; o += 128) prefetch_l2(b + o);
+}
+
 // ---- warp reductions ---------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -112,13 +120,26 @@ __host__ __device__ __forceinline__ uint32_t feistel_perm(uint32_t i, uint32_t n
     return x;
 }
 
+// 32-bit counter RNG for the sampler: one PCG-style output permutation per draw (≈6 integer instructions).
+__host__ __device__ __forceinline__ uint32_t pcg32(uint32_t x) {
+    x = x * 747796405u + 2891336453u;
+    const uint32_t w = ((x >> ((x >> 28) + 4u)) ^ x) * 277803737u;
+    return (w >> 22) ^ w;
+}
+// uniform integer in [0, n) from 32 random bits (multiply-high)
+__device__ __forceinline__ uint32_t bounded32(uint32_t r, uint32_t n) { return __umulhi(r, n); }
+// slot hash of a packed 64-bit triple key
+__host__ __device__ __forceinline__ uint32_t key_hash(uint64_t key) {
+    return pcg32((uint32_t)key ^ pcg32((uint32_t)(key >> 32) + 0x9E3779B9u));
+}
+
 // ---- triple membership set ---------------------------------------------------------------------
 __host__ __device__ __forceinline__ uint64_t triple_key(uint32_t h, uint32_t r, uint32_t t, uint32_t ent_bits, uint32_t rel_bits) {
     return ((uint64_t)h << (ent_bits + rel_bits)) | ((uint64_t)r << ent_bits) | (uint64_t)t;
 }
 __device__ __forceinline__ bool tset_contains(const oea_tripleset& s, uint64_t key) {
     const uint32_t mask = s.capacity - 1u;
-    uint32_t slot = (uint32_t)mix64(key) & mask;
+    uint32_t slot = key_hash(key) & mask;
     while (true) {
         uint64_t v = __ldg(s.slots + slot);
         if (v == key) return true;

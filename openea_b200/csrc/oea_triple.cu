@@ -12,6 +12,7 @@
 // path).  A row of `dim` floats is held as VEC float4 per lane (dim <= 128·VEC), loaded with
 // 128-bit coalesced reads; row reductions are warp shuffles; gradients leave through 128-bit
 // vector reductions (red.global.add.v4.f32) into the L2-resident gradient table.
+#include <stdlib.h>
 #include "oea_common.cuh"
 
 namespace oea {
@@ -283,11 +284,69 @@ struct SampledParams {
     int step;
     int max_try;
     uint64_t seed;
+    int diag;            // OEA_DIAG bit mask (measurement only): 1 synthetic negatives (no cand/hash chain),
+                         // 2 no gradient output, 4 no negatives, 8 identity permutation
 };
 
-__device__ __forceinline__ uint64_t rng_draw(uint64_t seed, uint32_t step, uint32_t p, uint32_t a, uint32_t b) {
-    uint64_t x = mix64(seed ^ ((uint64_t)step << 40) ^ ((uint64_t)p << 8));
-    return mix64(x ^ ((uint64_t)a << 32) ^ (uint64_t)b);
+// Counter RNG of the sampler: `rng_base` folds (epoch seed, step, positive) once per positive; every draw is one
+// pcg32 of the base xor a small counter.
+__device__ __forceinline__ uint32_t rng_base(uint64_t seed, uint32_t step, uint32_t p) {
+    return pcg32((uint32_t)seed ^ pcg32((uint32_t)(seed >> 32) ^ (step * 0x9E3779B9u)) ^ (p * 0x85EBCA6Bu));
+}
+__device__ __forceinline__ uint32_t rng_draw(uint32_t base, uint32_t a, uint32_t b) {
+    return pcg32(base ^ (a * 0xC2B2AE35u) ^ (b * 0x27D4EB2Fu));
+}
+
+// Negative sampling of one positive by its warp (batch.py:89-119): lane j < k ends up owning negative j
+// (corrupted entity neg_e, neg_head = head corrupted).  Up to max_try rounds; a round flips ONE coin for all
+// still-missing negatives, draws distinct candidate positions for them, keeps the draws that are not known
+// triples; the last round keeps everything.
+__device__ __forceinline__ void warp_sample_negatives(const SampledParams& P, const oea_kg_view& kg, int p, int h, int r,
+                                                      int t, int k, int lane, const float* __restrict__ ent_w, int ent_pitch,
+                                                      int& neg_e, bool& neg_head) {
+    bool need = lane < k;
+    const uint32_t base = rng_base(P.seed, (uint32_t)P.step, (uint32_t)p);
+    for (int tr = 0; tr < P.max_try; ++tr) {
+        const unsigned missing = __ballot_sync(OEA_FULL, need);
+        if (missing == 0u) break;
+        const bool head = (rng_draw(base, 0x51DEu, tr) >> 31) != 0;  // np.random.binomial(1, .5)
+        const int corrupted = head ? h : t;
+        const int32_t* list = kg.entities;
+        uint32_t C = (uint32_t)kg.n_entities;
+        if (kg.cand != nullptr) {
+            if (kg.ent2row == nullptr) {   // candidate matrix indexed by entity id; a row starting with −1 = no list
+                const int32_t* row = kg.cand + (size_t)corrupted * kg.n_cand;
+                if (__ldg(row) >= 0) { list = row; C = (uint32_t)kg.n_cand; }
+            } else {
+                const int row = __ldg(kg.ent2row + corrupted);
+                if (row >= 0) { list = kg.cand + (size_t)row * kg.n_cand; C = (uint32_t)kg.n_cand; }
+            }
+        }
+        // random.sample(candidates, #missing): distinct positions among the needing lanes
+        uint32_t pos = 0;
+        bool unsettled = need;
+        for (uint32_t redraw = 0; ; ++redraw) {
+            if (unsettled) pos = bounded32(rng_draw(base, (tr << 8) | lane, 0xC0FFEEu + redraw), C);
+            const unsigned active = __ballot_sync(OEA_FULL, need);
+            unsigned same = 0u;
+            if (need) same = __match_any_sync(active, pos);
+            // the lowest lane of a duplicate group keeps its draw, the others redraw
+            unsettled = need && ((same & ((1u << lane) - 1u)) != 0u);
+            if (__ballot_sync(OEA_FULL, unsettled) == 0u) break;
+        }
+        if (need) {
+            const int e = __ldg(list + pos);
+            // start fetching the candidate's row while the membership probe is in flight (rejections are < 1 %)
+            prefetch_row_l2(ent_w + (size_t)e * ent_pitch, ent_pitch);
+            bool accept = tr == P.max_try - 1;
+            if (!accept) {
+                const uint64_t key = head ? triple_key(e, r, t, P.tset.ent_bits, P.tset.rel_bits)
+                                          : triple_key(h, r, e, P.tset.ent_bits, P.tset.rel_bits);
+                accept = !tset_contains(P.tset, key);
+            }
+            if (accept) { neg_e = e; neg_head = head; need = false; }
+        }
+    }
 }
 
 template <int SCORE, int VEC>
@@ -313,45 +372,15 @@ k_score_sampled(TableDev ent, TableDev rel, SampledParams P, oea_loss_cfg cfg,
         const int h = __shfl_sync(OEA_FULL, hrt, 0);
         const int r = __shfl_sync(OEA_FULL, hrt, 1);
         const int t = __shfl_sync(OEA_FULL, hrt, 2);
+        if (lane < 3) {   // overlap the three shared rows' fetch with the sampling chain
+            const float* rowp = lane == 1 ? rel.w + (size_t)r * rel.pitch : ent.w + (size_t)(lane == 0 ? h : t) * ent.pitch;
+            prefetch_row_l2(rowp, ent.pitch);
+        }
 
         // ---- negative sampling (batch.py:89-119), lane j < k owns negative j ----
-        bool need = lane < k;
         int neg_e = 0;
         bool neg_head = false;
-        for (int tr = 0; tr < P.max_try; ++tr) {
-            const unsigned missing = __ballot_sync(OEA_FULL, need);
-            if (missing == 0u) break;
-            const bool head = (rng_draw(P.seed, P.step, p, 0x51DEu, tr) >> 63) != 0;  // np.random.binomial(1, .5)
-            const int corrupted = head ? h : t;
-            const int32_t* list = kg.entities;
-            uint32_t C = (uint32_t)kg.n_entities;
-            if (kg.cand != nullptr) {
-                const int row = __ldg(kg.ent2row + corrupted);
-                if (row >= 0) { list = kg.cand + (size_t)row * kg.n_cand; C = (uint32_t)kg.n_cand; }
-            }
-            // random.sample(candidates, #missing): distinct positions among the needing lanes
-            uint32_t pos = 0;
-            bool unsettled = need;
-            for (uint32_t redraw = 0; ; ++redraw) {
-                if (unsettled) pos = bounded(rng_draw(P.seed, P.step, p, (tr << 8) | lane, 0xC0FFEEu + redraw), C);
-                const unsigned active = __ballot_sync(OEA_FULL, need);
-                unsigned same = 0u;
-                if (need) same = __match_any_sync(active, pos);
-                // the lowest lane of a duplicate group keeps its draw, the others redraw
-                unsettled = need && ((same & ((1u << lane) - 1u)) != 0u);
-                if (__ballot_sync(OEA_FULL, unsettled) == 0u) break;
-            }
-            if (need) {
-                const int e = __ldg(list + pos);
-                bool accept = tr == P.max_try - 1;
-                if (!accept) {
-                    const uint64_t key = head ? triple_key(e, r, t, P.tset.ent_bits, P.tset.rel_bits)
-                                              : triple_key(h, r, e, P.tset.ent_bits, P.tset.rel_bits);
-                    accept = !tset_contains(P.tset, key);
-                }
-                if (accept) { neg_e = e; neg_head = head; need = false; }
-            }
-        }
+        warp_sample_negatives(P, kg, p, h, r, t, k, lane, ent.w, ent.pitch, neg_e, neg_head);
         const unsigned head_mask = __ballot_sync(OEA_FULL, neg_head);
         if (dbg != nullptr) {
             int32_t* row = dbg + (size_t)p * (2 + k);
@@ -444,6 +473,229 @@ k_score_sampled(TableDev ent, TableDev rel, SampledParams P, oea_loss_cfg cfg,
     acc.flush(warp_loss, loss_out);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Fused sampled step, v2 ("octet" layout) for the squared-L2 score and pitch <= 128 floats:
+// 8 lanes hold one row (4 float4 per lane), so a warp works on 4 rows at once — the three reductions of
+// a row are 3 shuffle steps shared by 4 rows instead of 5 steps per row, and 4 row gathers are in flight
+// per warp.  Because the score is quadratic, the gradients of the three shared rows are affine in the
+// negatives: only Σ g_j·ê_j (per corrupted side) and Σ g_j are accumulated per octet, merged across the
+// 4 octets once, and octets 0/1/2 finish rows h / r / t.
+// ------------------------------------------------------------------------------------------------
+struct R4 {
+    float4 v[4];
+};
+__device__ __forceinline__ R4 load_oct(const float* __restrict__ base, int row, int pitch, int l, int p4) {
+    R4 r;
+    const float* p = base + (size_t)row * pitch;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int q = l + 8 * i;
+        r.v[i] = q < p4 ? ldg4(p + 4 * q) : f4(0.f);
+    }
+    return r;
+}
+__device__ __forceinline__ void red_oct(float* __restrict__ base, int row, int pitch, int l, int p4, const R4& g) {
+    float* p = base + (size_t)row * pitch;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int q = l + 8 * i;
+        if (q < p4) red_add4(p + 4 * q, g.v[i]);
+    }
+}
+__device__ __forceinline__ float oct_sum(float v) {
+    v += __shfl_xor_sync(OEA_FULL, v, 1);
+    v += __shfl_xor_sync(OEA_FULL, v, 2);
+    v += __shfl_xor_sync(OEA_FULL, v, 4);
+    return v;
+}
+__device__ __forceinline__ float cross_oct_sum(float v) {
+    v += __shfl_xor_sync(OEA_FULL, v, 8);
+    v += __shfl_xor_sync(OEA_FULL, v, 16);
+    return v;
+}
+
+__global__ void __launch_bounds__(kThreads, 2)
+k_score_sampled_oct(TableDev ent, TableDev rel, SampledParams P, oea_loss_cfg cfg,
+                    double* __restrict__ loss_out, int32_t* __restrict__ dbg) {
+    __shared__ double s_loss[kWarpsPerBlock];
+    const int lane = threadIdx.x & 31, oct = lane >> 3, l = lane & 7;
+    const int warp_global = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int n_warps = gridDim.x * kWarpsPerBlock;
+    const int n_pos = P.n_slice[0] + P.n_slice[1];
+    const int k = P.k;
+    const int p4 = ent.pitch >> 2;
+    const bool margin_mode = cfg.loss_kind == OEA_LOSS_MARGIN;
+    float lane_loss = 0.f;
+
+    for (int p = warp_global; p < n_pos; p += n_warps) {
+        const int q = p < P.n_slice[0] ? 0 : 1;
+        const oea_kg_view& kg = P.kg[q];
+        const int local = q == 0 ? p : p - P.n_slice[0];
+        const uint32_t tri = (P.diag & 8) ? (uint32_t)(P.start[q] + local)
+                                          : feistel_perm((uint32_t)(P.start[q] + local), (uint32_t)kg.n_triples,
+                                                         P.seed ^ (q ? 0xA5A5A5A5DEADBEEFull : 0x0123456789ABCDEFull));
+        int hrt = 0;
+        if (lane < 3) hrt = __ldg(kg.triples + 3 * (size_t)tri + lane);
+        const int h = __shfl_sync(OEA_FULL, hrt, 0);
+        const int r = __shfl_sync(OEA_FULL, hrt, 1);
+        const int t = __shfl_sync(OEA_FULL, hrt, 2);
+        if (lane < 3) {   // overlap the three shared rows' fetch with the sampling chain
+            const float* rowp = lane == 1 ? rel.w + (size_t)r * rel.pitch : ent.w + (size_t)(lane == 0 ? h : t) * ent.pitch;
+            prefetch_row_l2(rowp, ent.pitch);
+        }
+
+        int neg_e = 0;
+        bool neg_head = false;
+        if (P.diag & 1) { neg_e = __ldg(kg.entities + (uint32_t)(p * 31 + lane * 977) % (uint32_t)kg.n_entities); neg_head = (p + lane) & 1; }
+        else warp_sample_negatives(P, kg, p, h, r, t, k, lane, ent.w, ent.pitch, neg_e, neg_head);
+        const unsigned head_mask = __ballot_sync(OEA_FULL, neg_head);
+        if (dbg != nullptr) {
+            int32_t* row = dbg + (size_t)p * (2 + k);
+            if (lane == 0) { row[0] = (int32_t)tri + (q ? (1 << 30) : 0); row[1] = (int32_t)head_mask; }
+            if (lane < k) row[2 + lane] = neg_e;
+        }
+
+        // ---- phase 1: the three shared rows (every octet holds a copy) ----
+        float ih, ir, it, ssh, ssr, sst, sp;
+        R4 hr, rt;   // ĥ + r̂ and r̂ − t̂
+        {
+            const R4 xh = load_oct(ent.w, h, ent.pitch, l, p4);
+            const R4 xr = load_oct(rel.w, r, rel.pitch, l, p4);
+            const R4 xt = load_oct(ent.w, t, ent.pitch, l, p4);
+            ssh = ssr = sst = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { ssh += dot4(xh.v[i], xh.v[i]); ssr += dot4(xr.v[i], xr.v[i]); sst += dot4(xt.v[i], xt.v[i]); }
+            ssh = oct_sum(ssh); ssr = oct_sum(ssr); sst = oct_sum(sst);
+            ih = inv_norm(ssh, ent.norm); ir = inv_norm(ssr, rel.norm); it = inv_norm(sst, ent.norm);
+            float sp_part = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 a = xh.v[i] * ih, b = xr.v[i] * ir, c = xt.v[i] * it;
+                hr.v[i] = a + b;
+                rt.v[i] = b - c;
+                const float4 up = hr.v[i] - c;
+                sp_part += dot4(up, up);
+            }
+            sp = oct_sum(sp_part);
+        }
+        float Lp = 0.f, gp = 0.f;
+        if (!margin_mode) loss_of(cfg.loss_kind, false, sp, cfg, Lp, gp);
+        if (lane == 0) lane_loss += Lp;
+
+        // ---- phase 2: negatives, four at a time (octet o takes negative 4·round + o) ----
+        R4 Eh, Et;   // Σ g_j·ê_j over head- / tail-corrupted negatives of this octet
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { Eh.v[i] = f4(0.f); Et.v[i] = f4(0.f); }
+        float Gh_s = 0.f, Gt_s = 0.f;
+        const int rounds = (P.diag & 4) ? 0 : (k + 3) >> 2;
+        for (int round = 0; round < rounds; ++round) {
+            const int j = 4 * round + oct;
+            const bool valid = j < k;
+            const int e_id = __shfl_sync(OEA_FULL, neg_e, valid ? j : 0);
+            const bool head = (head_mask >> (valid ? j : 0)) & 1u;
+            R4 e = load_oct(ent.w, valid ? e_id : h, ent.pitch, l, p4);
+            float sse = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) sse += dot4(e.v[i], e.v[i]);
+            sse = oct_sum(sse);
+            const float ie = inv_norm(sse, ent.norm);
+            R4 u;
+            float s_part = 0.f, d_part = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                e.v[i] = e.v[i] * ie;
+                u.v[i] = head ? (e.v[i] + rt.v[i]) : (hr.v[i] - e.v[i]);
+                s_part += dot4(u.v[i], u.v[i]);
+                d_part += dot4(e.v[i], u.v[i]);
+            }
+            const float sn = oct_sum(s_part);
+            const float de = oct_sum(d_part);
+            float L = 0.f, g = 0.f;
+            if (margin_mode) {
+                const float v = cfg.margin + sp - sn;
+                L = fmaxf(v, 0.f);
+                g = v > 0.f ? -1.f : 0.f;
+                if (valid && v > 0.f) gp = 1.f;   // k == 1: only octet 0 is valid; broadcast below
+            } else {
+                loss_of(cfg.loss_kind, true, sn, cfg, L, g);
+            }
+            if (!valid) { L = 0.f; g = 0.f; }
+            if (l == 0) lane_loss += L;
+            if (g != 0.f) {
+                // d s/d ê = ±2u ; through the normaliser: (ĝ − ê<ê,ĝ>)/‖x‖
+                const float c = (head ? 2.f : -2.f) * g * ie;
+                const float proj = (ent.norm && sse >= kNormEps) ? de : 0.f;
+                R4 out;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    out.v[i] = fma4(e.v[i], -proj, u.v[i]) * c;
+                    if (head) Eh.v[i] = fma4(e.v[i], g, Eh.v[i]); else Et.v[i] = fma4(e.v[i], g, Et.v[i]);
+                }
+                if (head) Gh_s += g; else Gt_s += g;
+                if (!(P.diag & 2)) {
+                    red_oct(ent.g, e_id, ent.pitch, l, p4, out);
+                    if (l == 0) ent.touched[e_id] = 1;
+                }
+            }
+        }
+        if (margin_mode) gp = __shfl_sync(OEA_FULL, gp, 0);
+
+        // ---- phase 3: merge the octets, finish rows h (octet 0), r (octet 1), t (octet 2) ----
+        Gh_s = cross_oct_sum(Gh_s);
+        Gt_s = cross_oct_sum(Gt_s);
+        if (gp != 0.f || Gh_s != 0.f || Gt_s != 0.f) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                Eh.v[i].x = cross_oct_sum(Eh.v[i].x); Eh.v[i].y = cross_oct_sum(Eh.v[i].y);
+                Eh.v[i].z = cross_oct_sum(Eh.v[i].z); Eh.v[i].w = cross_oct_sum(Eh.v[i].w);
+                Et.v[i].x = cross_oct_sum(Et.v[i].x); Et.v[i].y = cross_oct_sum(Et.v[i].y);
+                Et.v[i].z = cross_oct_sum(Et.v[i].z); Et.v[i].w = cross_oct_sum(Et.v[i].w);
+            }
+            {   // all four octets run the same arithmetic on their own row (full-mask shuffles inside); octet 3
+                // mirrors octet 2 and writes nothing.  Ĝ = α·P + β·A + γ·B with per-role scalars:
+                //   h: P + A      r: P + A + B      t: −P − B      (P = 2g⁺u⁺, A = 2(G_t·hr − E_t), B = 2(G_h·rt + E_h))
+                const int role = oct < 3 ? oct : 2;
+                const R4 xt = load_oct(ent.w, t, ent.pitch, l, p4);                      // t̂ for u⁺ (L1 hit)
+                const int row = role == 0 ? h : (role == 1 ? r : t);
+                const TableDev& tab = role == 1 ? rel : ent;
+                const R4 xo = load_oct(tab.w, row, tab.pitch, l, p4);
+                const float io = role == 0 ? ih : (role == 1 ? ir : it);
+                const float so = role == 0 ? ssh : (role == 1 ? ssr : sst);
+                const float alpha = role == 2 ? -2.f * gp : 2.f * gp;
+                const float beta = role == 2 ? 0.f : 2.f, gamma = role == 0 ? 0.f : (role == 1 ? 2.f : -2.f);
+                const float c_hr = alpha + beta * Gt_s, c_rt = gamma * Gh_s, c_t = -alpha * it;
+                R4 G;
+                float dpart = 0.f;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    // α(hr − t̂) + β(G_t·hr − E_t) + γ(G_h·rt + E_h)
+                    float4 g4 = hr.v[i] * c_hr;
+                    g4 = fma4(rt.v[i], c_rt, g4);
+                    g4 = fma4(xt.v[i], c_t, g4);
+                    g4 = fma4(Et.v[i], -beta, g4);
+                    g4 = fma4(Eh.v[i], gamma, g4);
+                    G.v[i] = g4;
+                    dpart += dot4(xo.v[i], g4);
+                }
+                dpart *= io;
+                const float dot = oct_sum(dpart);
+                const float proj = (tab.norm && so >= kNormEps) ? dot : 0.f;
+                if (oct < 3 && !(P.diag & 2)) {
+                    R4 out;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) out.v[i] = fma4(xo.v[i] * io, -proj, G.v[i]) * io;
+                    red_oct(tab.g, row, tab.pitch, l, p4, out);
+                    if (l == 0) tab.touched[row] = 1;
+                }
+            }
+        }
+    }
+    const float warp_loss = warp_sum(lane_loss);
+    LossAcc acc{s_loss};
+    acc.flush(warp_loss, loss_out);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Row optimiser: one warp per row, flagged rows only (Adagrad / SGD) or all rows (Adam).
 // TF1 semantics (optimizers.py:10-20): Adagrad acc += g², x −= lr·g/√acc (no ε, acc0 = 0.1 set by
@@ -523,11 +775,29 @@ static int check_table(const oea_table* t, bool need_grad) {
     return OEA_OK;
 }
 
+static int sm_count_cached() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+    }
+    return sms;
+}
+
 static int grid_for(int n_warp_items) {
-    int dev = 0, sms = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int blocks_needed = (n_warp_items + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    const int cap = sms * 8;  // 8 CTAs × 8 warps = 64 resident warps per SM
+    const int cap = sm_count_cached() * 8;  // 8 CTAs × 8 warps = 64 resident warps per SM
+    return blocks_needed < 1 ? 1 : (blocks_needed < cap ? blocks_needed : cap);
+}
+
+// Exactly one resident wave for kernel `fn` (grid-stride loops do the rest): a partial last wave would run at a
+// fraction of the machine for a whole block duration (measured: 2.11 waves cost 3 block durations).
+template <typename Fn>
+static int grid_one_wave(Fn fn, int n_warp_items) {
+    static int occ = 0;   // one static per kernel instantiation
+    if (occ == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kThreads, 0) != cudaSuccess || occ < 1)) occ = 1;
+    const int blocks_needed = (n_warp_items + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const int cap = sm_count_cached() * occ;
     return blocks_needed < 1 ? 1 : (blocks_needed < cap ? blocks_needed : cap);
 }
 
@@ -587,10 +857,11 @@ extern "C" int oea_triple_score_fed(const oea_table* ent, const oea_table* rel,
         OEA_DISPATCH_VEC(ent->pitch, CALL);
 #undef CALL
     } else {
-        const int grid = grid_for(n_pos + n_neg);
 #define CALL(V)                                                                                                         \
-        if (l1) k_score_fed<OEA_SCORE_L1, V><<<grid, kThreads, 0, st>>>(e, r, pos_h, pos_r, pos_t, n_pos, neg_h, neg_r, neg_t, n_neg, *loss, loss_out); \
-        else k_score_fed<OEA_SCORE_L2SQ, V><<<grid, kThreads, 0, st>>>(e, r, pos_h, pos_r, pos_t, n_pos, neg_h, neg_r, neg_t, n_neg, *loss, loss_out)
+        if (l1) { const int grid = grid_one_wave(k_score_fed<OEA_SCORE_L1, V>, n_pos + n_neg);                              \
+                  k_score_fed<OEA_SCORE_L1, V><<<grid, kThreads, 0, st>>>(e, r, pos_h, pos_r, pos_t, n_pos, neg_h, neg_r, neg_t, n_neg, *loss, loss_out); } \
+        else { const int grid = grid_one_wave(k_score_fed<OEA_SCORE_L2SQ, V>, n_pos + n_neg);                               \
+               k_score_fed<OEA_SCORE_L2SQ, V><<<grid, kThreads, 0, st>>>(e, r, pos_h, pos_r, pos_t, n_pos, neg_h, neg_r, neg_t, n_neg, *loss, loss_out); }
         OEA_DISPATCH_VEC(ent->pitch, CALL);
 #undef CALL
     }
@@ -627,12 +898,18 @@ extern "C" int oea_rowopt_apply(const oea_table* t, const oea_opt_cfg* opt, void
     return OEA_OK;
 }
 
+// OEA_SCORE_V1=1 selects the warp-per-row kernel for every shape (A/B measurements, tests of both paths).
+static bool oea_force_v1() {
+    const char* v = getenv("OEA_SCORE_V1");   // read per call: tests flip it inside one process
+    return v != nullptr && v[0] == '1';
+}
+
 static int check_kg(const oea_kg_view* kg, int k) {
     if (kg == nullptr) return OEA_ERR_NULL;
     if (kg->n_triples < 0 || kg->n_entities < 0) return OEA_ERR_RANGE;
     if (kg->n_triples > 0 && (kg->triples == nullptr || kg->entities == nullptr)) return OEA_ERR_NULL;
     if (kg->n_triples > 0 && kg->n_entities < k) return OEA_ERR_RANGE;  // random.sample would raise
-    if (kg->cand != nullptr && (kg->ent2row == nullptr || kg->n_cand < k)) return OEA_ERR_RANGE;
+    if (kg->cand != nullptr && kg->n_cand < (k > 1 ? k : 1)) return OEA_ERR_RANGE;
     return OEA_OK;
 }
 
@@ -673,18 +950,29 @@ extern "C" int oea_triple_score_sampled(const oea_table* ent, const oea_table* r
     slice_of(kg1->n_triples, b1, smp->step, &P.start[0], &P.n_slice[0]);
     slice_of(kg2->n_triples, b2, smp->step, &P.start[1], &P.n_slice[1]);
     P.k = smp->neg_per_pos; P.step = smp->step; P.max_try = smp->max_try; P.seed = smp->epoch_seed;
+    {   // measurement-only ablation switches ("where the time goes"); read once per process
+        static int diag_cached = -1;
+        if (diag_cached < 0) { const char* dg = getenv("OEA_DIAG"); diag_cached = dg ? atoi(dg) : 0; }
+        P.diag = diag_cached;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     const int n_pos = P.n_slice[0] + P.n_slice[1];
     if (n_pos_out) OEA_CUDA_TRY(cudaMemcpyAsync(n_pos_out, &n_pos, sizeof(int), cudaMemcpyHostToDevice, st));
     if (n_pos == 0) return OEA_OK;
     TableDev e = table_dev(ent), r = table_dev(rel);
-    const int grid = grid_for(n_pos);
     const bool l1 = loss->score_kind == OEA_SCORE_L1;
+    if (!l1 && ent->pitch <= 128 && !oea_force_v1()) {
+        const int grid = grid_one_wave(k_score_sampled_oct, n_pos);
+        k_score_sampled_oct<<<grid, kThreads, 0, st>>>(e, r, P, *loss, loss_out, dbg_neg);
+    } else {
 #define CALL(V)                                                                                              \
-    if (l1) k_score_sampled<OEA_SCORE_L1, V><<<grid, kThreads, 0, st>>>(e, r, P, *loss, loss_out, dbg_neg);  \
-    else k_score_sampled<OEA_SCORE_L2SQ, V><<<grid, kThreads, 0, st>>>(e, r, P, *loss, loss_out, dbg_neg)
-    OEA_DISPATCH_VEC(ent->pitch, CALL);
+    if (l1) { const int grid = grid_one_wave(k_score_sampled<OEA_SCORE_L1, V>, n_pos);                       \
+              k_score_sampled<OEA_SCORE_L1, V><<<grid, kThreads, 0, st>>>(e, r, P, *loss, loss_out, dbg_neg); } \
+    else { const int grid = grid_one_wave(k_score_sampled<OEA_SCORE_L2SQ, V>, n_pos);                        \
+           k_score_sampled<OEA_SCORE_L2SQ, V><<<grid, kThreads, 0, st>>>(e, r, P, *loss, loss_out, dbg_neg); }
+        OEA_DISPATCH_VEC(ent->pitch, CALL);
 #undef CALL
+    }
     OEA_LAUNCH_CHECK();
     return OEA_OK;
 }
@@ -734,7 +1022,7 @@ __global__ void k_tripleset_build(const int32_t* __restrict__ triples, int n, un
     if (i >= n) return;
     const uint64_t key = triple_key(triples[3 * (size_t)i], triples[3 * (size_t)i + 1], triples[3 * (size_t)i + 2], ent_bits, rel_bits);
     const uint32_t mask = capacity - 1u;
-    uint32_t slot = (uint32_t)mix64(key) & mask;
+    uint32_t slot = key_hash(key) & mask;
     while (true) {
         const unsigned long long prev = atomicCAS(slots + slot, 0xFFFFFFFFFFFFFFFFull, (unsigned long long)key);
         if (prev == 0xFFFFFFFFFFFFFFFFull || prev == key) return;

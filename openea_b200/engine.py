@@ -148,19 +148,27 @@ class DeviceKG:
         self.ent_rows = int(ent_rows)
         self.cand = None
         self.ent2row = None
+        self.cand_src = None
 
-    def set_candidates(self, cand, row_entities):
+    def set_candidates(self, cand, row_entities, direct=True):
         """cand: [rows, n_cand] int32 device tensor of ε-truncated neighbour ids; row_entities: the entity id
         owning each row (batch.py:145-165 builds dict entity → list)."""
+        rows = torch.as_tensor(row_entities, dtype=torch.int64, device=self.device)
+        self.cand_src = cand          # identity of the caller's tensor (lets callers skip redundant re-installs)
+        if direct:   # candidate matrix indexed by entity id: the sampler skips the ent2row indirection
+            full = torch.full((self.ent_rows, cand.shape[1]), -1, dtype=torch.int32, device=self.device)
+            full[rows] = cand
+            self.cand, self.ent2row = full, None
+            return
         self.cand = cand.contiguous()
         e2r = torch.full((self.ent_rows,), -1, dtype=torch.int32, device=self.device)
-        rows = torch.as_tensor(row_entities, dtype=torch.int64, device=self.device)
         e2r[rows] = torch.arange(rows.numel(), dtype=torch.int32, device=self.device)
         self.ent2row = e2r
 
     def clear_candidates(self):
         self.cand = None
         self.ent2row = None
+        self.cand_src = None
 
     def view(self):
         return L.KgView(self.triples.data_ptr(), self.triples.shape[0], self.entities.data_ptr(),

@@ -215,7 +215,7 @@ class BasicModel:
                              (kg2, neighbors2, self.kgs.useful_entities_list2)):
             if nb is None:
                 kg.clear_candidates()
-            elif kg.cand is not nb:
+            elif kg.cand_src is not nb:
                 kg.set_candidates(nb, ents)
         t1, t2 = kg1.triples.shape[0], kg2.triples.shape[0]
         b1 = int(t1 / (t1 + t2) * self.args.batch_size)

@@ -149,16 +149,25 @@ def _decode_dbg(dbg, kgs_triples, k):
         for j in range(k):
             e = int(row[2 + j])
             neg_cols.append((e, r, t) if (mask >> j) & 1 else (h, r, e))
-    return np.array(pos_cols, dtype=np.int32).T.copy(), np.array(neg_cols, dtype=np.int32).T.copy()
+    neg = np.array(neg_cols, dtype=np.int32).T.copy() if neg_cols else np.zeros((3, 0), dtype=np.int32)
+    return np.array(pos_cols, dtype=np.int32).T.copy(), neg
 
 
-@pytest.mark.parametrize("truncated", [False, True])
-def test_sampled_step_replays_through_oracle(cuda_device, truncated):
-    """The fused sampler+scorer: (a) its sampled batch obeys batch.py's rules, (b) replaying that exact batch
-    through the oracle reproduces loss and gradients."""
+@pytest.mark.parametrize("truncated,loss,k,d,norm,force_v1", [
+    (False, "limited", 10, 100, True, False), (True, "limited", 10, 100, True, False),
+    (True, "limited", 10, 100, True, True),          # the warp-per-row kernel (v1) on the same case
+    (False, "logistic", 7, 75, True, False), (True, "limited", 5, 128, False, False),
+    (False, "margin-based", 1, 100, True, False), (False, "margin-based", 1, 100, True, True),
+    (False, "positive", 0, 75, True, False), (False, "limited", 32, 64, True, False),
+    (False, "limited", 10, 300, True, False),        # pitch > 128 always takes v1
+])
+def test_sampled_step_replays_through_oracle(cuda_device, monkeypatch, truncated, loss, k, d, norm, force_v1):
+    """The fused sampler+scorer (octet-layout v2 and warp-per-row v1): (a) its sampled batch obeys batch.py's
+    rules, (b) replaying that exact batch through the oracle reproduces loss and gradients."""
+    monkeypatch.setenv("OEA_SCORE_V1", "1" if force_v1 else "0")
     eng = _engine()
-    rng = np.random.default_rng(21)
-    d, n_ent, n_rel, k, B = 100, 4000, 30, 10, 512
+    rng = np.random.default_rng(21 + k + d)
+    n_ent, n_rel, B = 4000, 30, 512
     ent, rel = make_tables(rng, n_ent, n_rel, d)
     ents1 = np.arange(0, n_ent, 2, dtype=np.int32)
     ents2 = np.arange(1, n_ent, 2, dtype=np.int32)
@@ -172,12 +181,13 @@ def test_sampled_step_replays_through_oracle(cuda_device, truncated):
     if truncated:
         for kg, ents in ((kg1, ents1), (kg2, ents2)):
             cand = torch.from_numpy(rng.choice(ents, size=(len(ents), n_cand)).astype(np.int32)).cuda()
-            # distinct ids per row are not required by the sampler (it samples distinct POSITIONS)
-            kg.set_candidates(cand, ents)
+            # distinct ids per row are not required by the sampler (it samples distinct POSITIONS);
+            # both layouts of the candidate matrix are exercised: by entity id (default) and via ent2row
+            kg.set_candidates(cand, ents, direct=not force_v1)
     tset = eng.DeviceTripleSet([kg1.triples, kg2.triples], n_ent, n_rel)
-    kw = dict(margin=0.01, neg_margin=2.0, balance=0.2)
-    te, tr = _tables(ent, rel, True)
-    trn = eng.TripleTrainer(te, tr, eng.loss_cfg("limited", "L2", **kw), lr=0.01)
+    kw = dict(margin=1.2 if loss == "margin-based" else 0.01, neg_margin=2.0, balance=0.2)
+    te, tr = _tables(ent, rel, norm)
+    trn = eng.TripleTrainer(te, tr, eng.loss_cfg(loss, "L2", **kw), lr=0.01)
     all_set = {tuple(x) for x in t1.tolist()} | {tuple(x) for x in t2.tolist()}
     seen_tri = [set(), set()]
     T1, T2 = len(t1), len(t2)
@@ -195,16 +205,24 @@ def test_sampled_step_replays_through_oracle(cuda_device, truncated):
         for row in rows:
             q = 1 if int(row[0]) & (1 << 30) else 0
             seen_tri[q].add(int(row[0]) & ~(1 << 30))
-        # (a) sampler rules: same-KG corruption, distinct within a positive (single-try case), filtered
-        ent_kg = np.where(np.isin(neg[0], ents1) & np.isin(neg[2], ents1), 0, np.where(np.isin(neg[0], ents2) & np.isin(neg[2], ents2), 1, -1))
-        assert (ent_kg >= 0).all(), "negatives must stay inside the positive's KG"
-        in_set = np.mean([tuple(x) in all_set for x in neg.T.tolist()])
-        assert in_set < 0.01, "true triples must be (almost always) rejected"
+        if k > 0:
+            # (a) sampler rules: same-KG corruption, filtered against the known triples
+            ent_kg = np.where(np.isin(neg[0], ents1) & np.isin(neg[2], ents1), 0, np.where(np.isin(neg[0], ents2) & np.isin(neg[2], ents2), 1, -1))
+            assert (ent_kg >= 0).all(), "negatives must stay inside the positive's KG"
+            in_set = np.mean([tuple(x) in all_set for x in neg.T.tolist()])
+            assert in_set < 0.01, "true triples must be (almost always) rejected"
+            blocks = neg.reshape(3, n, k)
+            if k <= 20 and not truncated:
+                dup = np.mean([len({tuple(c) for c in blocks[:, i, :].T.tolist()}) < k for i in range(n)])
+                assert dup < 0.05, "negatives of one positive are distinct except across rare re-tries"
+        else:
+            neg = None
         # (b) replay through the oracle
-        want, want_ge, want_gr, _ = orc.fwd_bwd(ent, rel, pos, neg, "limited", "L2", True, True, **kw)
+        want, want_ge, want_gr, _ = orc.fwd_bwd(ent, rel, pos, neg, loss, "L2", norm, norm, **kw)
         assert trn.read_loss() == pytest.approx(want, rel=LOSS_TOL)
         _assert_rows_close(te.grad[:, :d].cpu().numpy(), want_ge, "entity gradient (sampled)")
         _assert_rows_close(tr.grad[:, :d].cpu().numpy(), want_gr, "relation gradient (sampled)")
+        assert not te.grad[:, d:].any().item()
         te.grad.zero_(); tr.grad.zero_(); te.touched.zero_(); tr.touched.zero_()
     # the epoch permutation is a bijection: slices partition (a prefix of) each triple list exactly once
     assert len(seen_tri[0]) == min(T1, steps * b1) and len(seen_tri[1]) == min(T2, steps * b2)
