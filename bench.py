@@ -429,6 +429,24 @@ def main():
             cpu_base = {"value": val, "unit": unit, "cores": info["cores"], "kind": "port", "sample": info["sample"]}
 
     _phase("cpu baseline done")
+    # ---- informational: the same steps as ONE CUDA graph per epoch, L2 warm (how the training loop really runs) ----
+    graph_info = None
+    if world == 1:
+        eg = tr.capture_epoch(kg1, kg2, tset, B, k, full_steps)
+        for e in range(3):
+            eg.replay(1234 + e)
+        torch.cuda.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 20
+        g0.record()
+        for e in range(reps):
+            eg.replay(99 + e)
+        g1.record()
+        torch.cuda.synchronize()
+        g_ms = g0.elapsed_time(g1) / (reps * full_steps)
+        graph_info = {"ms_per_step": g_ms, "positives_per_s": n_pos_step / (g_ms * 1e-3), "steps_per_graph": full_steps,
+                      "note": "one CUDA graph per epoch, L2 NOT flushed between steps: informational, not the bench value"}
+        tr.read_loss()
     csls = None
     if world == 1:
         csls = bench_csls(cfg["shape"], device)
@@ -456,7 +474,7 @@ def main():
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                 "scored_triples_per_s": value * (1 + k), "positives_per_step": n_pos_step,
                 "gpu_launches": 2 * K, "kernels": ["k_score_sampled", "k_rowopt_pair(ent+rel)"],
-                "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_base, "clocks": clk, "csls": csls,
+                "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_base, "clocks": clk, "csls": csls, "epoch_graph": graph_info,
                 "wall_s_timed_region": t_wall, "last_loss_sum": loss_val,
                 "collective": None if sync is None else {"kind": "ncclAllGather of seed-pair rows per local epoch",
                                                          "bytes_per_sync": sync.bytes_per_sync, "syncs_in_run": n_syncs[0]}}

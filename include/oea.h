@@ -108,6 +108,8 @@ typedef struct oea_sample_cfg {
     int32_t  step;            /* step index inside the epoch */
     int32_t  max_try;         /* batch.py:89 max_try (10) */
     uint64_t epoch_seed;      /* permutation + sampling seed of this epoch */
+    const uint64_t* dev_seed; /* optional DEVICE scalar xor-ed into epoch_seed at kernel start: lets a CUDA graph of a
+                               * whole epoch (one node pair per step) be replayed with a new seed every epoch */
 } oea_sample_cfg;
 
 /* ---- misc ---------------------------------------------------------------------------------- */

@@ -284,6 +284,7 @@ struct SampledParams {
     int step;
     int max_try;
     uint64_t seed;
+    const uint64_t* dev_seed;   // optional device scalar xor-ed into seed (CUDA-graph replays)
     int diag;            // OEA_DIAG bit mask (measurement only): 1 synthetic negatives (no cand/hash chain),
                          // 2 no gradient output, 4 no negatives, 8 identity permutation
 };
@@ -354,6 +355,7 @@ __global__ void __launch_bounds__(kThreads)
 k_score_sampled(TableDev ent, TableDev rel, SampledParams P, oea_loss_cfg cfg,
                 double* __restrict__ loss_out, int32_t* __restrict__ dbg) {
     __shared__ double s_loss[kWarpsPerBlock];
+    if (P.dev_seed != nullptr) P.seed ^= __ldg(reinterpret_cast<const unsigned long long*>(P.dev_seed));
     const int lane = threadIdx.x & 31;
     const int warp_global = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     const int n_warps = gridDim.x * kWarpsPerBlock;
@@ -519,6 +521,7 @@ __global__ void __launch_bounds__(kThreads, 2)
 k_score_sampled_oct(TableDev ent, TableDev rel, SampledParams P, oea_loss_cfg cfg,
                     double* __restrict__ loss_out, int32_t* __restrict__ dbg) {
     __shared__ double s_loss[kWarpsPerBlock];
+    if (P.dev_seed != nullptr) P.seed ^= __ldg(reinterpret_cast<const unsigned long long*>(P.dev_seed));
     const int lane = threadIdx.x & 31, oct = lane >> 3, l = lane & 7;
     const int warp_global = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     const int n_warps = gridDim.x * kWarpsPerBlock;
@@ -950,6 +953,7 @@ extern "C" int oea_triple_score_sampled(const oea_table* ent, const oea_table* r
     slice_of(kg1->n_triples, b1, smp->step, &P.start[0], &P.n_slice[0]);
     slice_of(kg2->n_triples, b2, smp->step, &P.start[1], &P.n_slice[1]);
     P.k = smp->neg_per_pos; P.step = smp->step; P.max_try = smp->max_try; P.seed = smp->epoch_seed;
+    P.dev_seed = smp->dev_seed;
     {   // measurement-only ablation switches ("where the time goes"); read once per process
         static int diag_cached = -1;
         if (diag_cached < 0) { const char* dg = getenv("OEA_DIAG"); diag_cached = dg ? atoi(dg) : 0; }

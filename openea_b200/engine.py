@@ -231,9 +231,11 @@ class TripleTrainer:
         L.check(self.lib.oea_rowopt_apply_pair(C.byref(self.ent.c_struct()), C.byref(self.rel.c_struct()), C.byref(cfg),
                                                _stream_ptr()), "oea_rowopt_apply_pair")
 
-    def step_sampled(self, kg1, kg2, tset, batch_size, neg_per_pos, step, epoch_seed, max_try=10, n_pos_out=None):
+    def step_sampled(self, kg1, kg2, tset, batch_size, neg_per_pos, step, epoch_seed, max_try=10, n_pos_out=None,
+                     dev_seed=None):
         """One whole training step in one C call (fused sampler+scorer, then one optimiser launch)."""
-        smp = L.SampleCfg(int(batch_size), int(neg_per_pos), int(step), int(max_try), int(epoch_seed) & (2**64 - 1))
+        smp = L.SampleCfg(int(batch_size), int(neg_per_pos), int(step), int(max_try), int(epoch_seed) & (2**64 - 1),
+                          0 if dev_seed is None else dev_seed.data_ptr())
         views = self._views(kg1, kg2, tset)
         for tab in (self.ent, self.rel):
             if tab.optimizer == "Adam":
@@ -243,6 +245,12 @@ class TripleTrainer:
             C.byref(self.ent.c_struct()), C.byref(self.rel.c_struct()), C.byref(views[0]), C.byref(views[1]),
             C.byref(views[2]), C.byref(smp), C.byref(self.loss), C.byref(cfg), _ptr(self.loss_dev), _ptr(n_pos_out),
             _stream_ptr()), "oea_triple_step_sampled")
+
+    def capture_epoch(self, kg1, kg2, tset, batch_size, neg_per_pos, steps, max_try=10):
+        """CUDA graph of one whole epoch (`steps` × [fused sampler/scorer, optimiser]).  The per-epoch seed lives in
+        a device scalar, so the same graph is replayed every epoch: `EpochGraph.replay(seed)`.  Must be re-captured
+        when the candidate lists (device pointers) change."""
+        return EpochGraph(self, kg1, kg2, tset, batch_size, neg_per_pos, steps, max_try)
 
     def _views(self, kg1, kg2, tset):
         """ctypes views of the KGs / triple set, cached until their device buffers change."""
@@ -256,7 +264,7 @@ class TripleTrainer:
     def score_sampled(self, kg1, kg2, tset, batch_size, neg_per_pos, step, epoch_seed, max_try=10,
                       loss_out=None, dbg=None, n_pos_out=None):
         out = self.loss_dev if loss_out is None else loss_out
-        smp = L.SampleCfg(int(batch_size), int(neg_per_pos), int(step), int(max_try), int(epoch_seed) & (2**64 - 1))
+        smp = L.SampleCfg(int(batch_size), int(neg_per_pos), int(step), int(max_try), int(epoch_seed) & (2**64 - 1), 0)
         k1, k2, ts = kg1.view(), kg2.view(), tset.view()
         L.check(self.lib.oea_triple_score_sampled(
             C.byref(self.ent.c_struct()), C.byref(self.rel.c_struct()), C.byref(k1), C.byref(k2), C.byref(ts),
@@ -339,3 +347,22 @@ class MappingTrainer:
             cfg = opt_cfg(tab, self.lr)
             L.check(self.lib.oea_rowopt_apply(C.byref(tab.c_struct()), C.byref(cfg), st), "oea_rowopt_apply")
         return float(self.loss_dev.item())
+
+
+class EpochGraph:
+    """One training epoch captured as a CUDA graph (launch-bound inner loop → one graph launch per epoch)."""
+
+    def __init__(self, trainer, kg1, kg2, tset, batch_size, neg_per_pos, steps, max_try=10):
+        self.trainer = trainer
+        dev = trainer.ent.device
+        self.seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.key = trainer._views(kg1, kg2, tset) and trainer._view_key
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            for step in range(steps):
+                trainer.step_sampled(kg1, kg2, tset, batch_size, neg_per_pos, step, 0, max_try=max_try,
+                                     dev_seed=self.seed_dev)
+
+    def replay(self, epoch_seed):
+        self.seed_dev.fill_(int(epoch_seed) & ((1 << 63) - 1))
+        self.graph.replay()

@@ -46,7 +46,7 @@ class TripleSet(C.Structure):
 
 class SampleCfg(C.Structure):
     _fields_ = [("batch_size", C.c_int32), ("neg_per_pos", C.c_int32), ("step", C.c_int32), ("max_try", C.c_int32),
-                ("epoch_seed", C.c_uint64)]
+                ("epoch_seed", C.c_uint64), ("dev_seed", C.c_void_p)]
 
 
 class SimCfg(C.Structure):

@@ -223,8 +223,17 @@ class BasicModel:
         self._epoch_seed = (self._epoch_seed * 6364136223846793005 + 1442695040888963407) & ((1 << 63) - 1)
         trained_samples_num = 0
         trainer = self.triple_trainer
+        use_graph = getattr(self.args, "cuda_graph", True) and epoch > 1   # epoch 1 runs eagerly (warm-up)
+        if use_graph:
+            key = (triple_steps, trainer._views(kg1, kg2, tset) and trainer._view_key)
+            if getattr(self, "_epoch_graph_key", None) != key:      # (re)capture: first use, or new candidate lists
+                self._epoch_graph = trainer.capture_epoch(kg1, kg2, tset, self.args.batch_size, self.neg_per_pos,
+                                                          triple_steps)
+                self._epoch_graph_key = key
+            self._epoch_graph.replay(self._epoch_seed)
         for step in range(triple_steps):
-            trainer.step_sampled(kg1, kg2, tset, self.args.batch_size, self.neg_per_pos, step, self._epoch_seed)
+            if not use_graph:
+                trainer.step_sampled(kg1, kg2, tset, self.args.batch_size, self.neg_per_pos, step, self._epoch_seed)
             trained_samples_num += self._slice_count(t1, b1, step) + self._slice_count(t2, b2, step)
         epoch_loss = trainer.read_loss() / max(1, trained_samples_num)     # one device→host read per epoch
         print('epoch {}, avg. triple loss: {:.4f}, cost time: {:.4f}s'.format(epoch, epoch_loss, time.time() - start))
