@@ -269,15 +269,31 @@ typedef struct oea_csr {
     int64_t        nnz;
 } oea_csr;
 
+/* Hub rows of a CSR matrix (more than oea_spmm_long_row_threshold() non-zeros; Zipf-degree entities) cut into
+ * segments of oea_spmm_segment_nnz() non-zeros, prepared once on the host:
+ *   long_rows [n_long] row ids; seg_ptr [n_long + 1] first segment of every hub row; for every segment
+ *   seg_row [n_seg] = index into long_rows and seg_start [n_seg] = its first non-zero (absolute position). */
+typedef struct oea_spmm_hubs {
+    const int32_t* long_rows;
+    const int32_t* seg_ptr;
+    const int32_t* seg_row;
+    const int32_t* seg_start;
+    int32_t        n_long, n_seg;
+} oea_spmm_hubs;
+
 /* Y[n_rows, d] = A · X[n_cols, d] (+ beta·Y), optional fused epilogues: relu (the `act` of GraphConvolution,
  * gcn_align.py:259-267) or masking by mask_src > 0 (relu backward).  Replaces tf.sparse_tensor_dense_matmul
- * (gcn_align.py:83, alinet.py:581, rdgcn.py:187).  d % 4 == 0, d <= 512.  long_rows lists the rows with more
- * than oea_spmm_long_row_threshold() non-zeros (hub entities); they are processed by a whole CTA each.
+ * (gcn_align.py:83, alinet.py:581, rdgcn.py:187).  d % 4 == 0, d <= 512.  Rows with at most the threshold run
+ * one warp each; hub rows go segment by segment through `workspace` (>= oea_spmm_workspace_bytes(n_seg, d))
+ * and are summed in order (deterministic).  hubs may be NULL when no row exceeds the threshold.
  * The backward pass is the same call on the CSR of Aᵀ. */
 int oea_spmm_long_row_threshold(void);
-int oea_spmm_csr(const oea_csr* A, const int32_t* long_rows, int32_t n_long,
+int oea_spmm_segment_nnz(void);
+size_t oea_spmm_workspace_bytes(int32_t n_segments, int32_t d);
+int oea_spmm_csr(const oea_csr* A, const oea_spmm_hubs* hubs,
                  const float* X, int32_t ldx, float* Y, int32_t ldy, int32_t d,
-                 int32_t relu, const float* mask_src, float beta, void* stream);
+                 int32_t relu, const float* mask_src, float beta,
+                 void* workspace, size_t workspace_bytes, void* stream);
 
 /* align_loss (approaches/gcn_align.py:298-320; rdgcn.py:293-315 has the same form): L1 margin loss over t
  * seed pairs with k negatives per side, mean over 2·k·t, forward + backward.  x [N, ld] are the output

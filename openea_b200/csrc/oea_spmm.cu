@@ -9,7 +9,7 @@
 // SpMM Y = A·X with A in CSR (int32 col, fp32 val): HBM/L2-bound gather of X rows.  Rows with at most
 // LONG_ROW non-zeros are handled one warp per row (col/val fetched 32 at a time, coalesced, and
 // broadcast by shuffle; the X row is read with 128-bit loads); hub rows (Zipf degree) get a whole CTA
-// whose 8 warps split the non-zeros and reduce through shared memory — no atomics, deterministic.
+// cut into 512-non-zero segments (one CTA each) whose partial rows are added in order — no atomics, deterministic.
 #include "oea_common.cuh"
 
 namespace oea {
@@ -29,25 +29,39 @@ __device__ __forceinline__ void acc_zero(Acc<VEC>& a) {
     for (int i = 0; i < VEC; ++i) a.v[i] = f4(0.f);
 }
 
-// accumulate val·X[col, :] over the non-zeros [p0, p1) of one row into acc (lane owns float4 columns lane+32i)
+// accumulate val·X[col, :] over the non-zeros [p0, p1) of one row into acc (lane owns float4 columns lane+32i).
+// The non-zeros are taken U at a time: U independent row gathers are issued before the first FMA, so a row's
+// latency is one round trip per U non-zeros instead of one per non-zero.
 template <int VEC>
 __device__ __forceinline__ void spmm_span(const int32_t* __restrict__ col, const float* __restrict__ val,
                                           int p0, int p1, const float* __restrict__ X, int ldx, int d4, int lane,
                                           Acc<VEC>& acc) {
+    constexpr int U = VEC <= 1 ? 8 : (VEC == 2 ? 4 : 2);
     for (int base = p0; base < p1; base += 32) {
         const int p = base + lane;
         int c = 0; float w = 0.f;
-        if (p < p1) { c = __ldg(col + p); w = __ldg(val + p); }
+        if (p < p1) { c = __ldg(col + p); w = __ldg(val + p); }   // lanes past the end contribute 0·X[0]
         const int cnt = min(32, p1 - base);
-        for (int j = 0; j < cnt; ++j) {
-            const int cj = __shfl_sync(OEA_FULL, c, j);
-            const float wj = __shfl_sync(OEA_FULL, w, j);
-            const float* xr = X + (size_t)cj * ldx;
+        for (int j0 = 0; j0 < cnt; j0 += U) {
+            float4 x[U][VEC];
+            float wj[U];
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) {
-                const int q = lane + 32 * i;
-                if (q < d4) acc.v[i] = fma4(ldg4(xr + 4 * q), wj, acc.v[i]);
+            for (int u = 0; u < U; ++u) {
+                const bool on = j0 + u < cnt;                       // warp-uniform
+                const int cj = __shfl_sync(OEA_FULL, c, (j0 + u) & 31);
+                const float ws = __shfl_sync(OEA_FULL, w, (j0 + u) & 31);
+                wj[u] = on ? ws : 0.f;
+                const float* xr = X + (size_t)cj * ldx;
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) {
+                    const int q = lane + 32 * i;
+                    x[u][i] = (on && q < d4) ? ldg4(xr + 4 * q) : f4(0.f);
+                }
             }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) acc.v[i] = fma4(x[u][i], wj[u], acc.v[i]);
         }
     }
 }
@@ -86,7 +100,7 @@ k_spmm_warp_rows(const int32_t* __restrict__ rowptr, const int32_t* __restrict__
     const int n_warps = gridDim.x * SPMM_WARPS;
     for (int row = warp_global; row < n_rows; row += n_warps) {
         const int p0 = __ldg(rowptr + row), p1 = __ldg(rowptr + row + 1);
-        if (p1 - p0 > LONG_ROW) continue;   // a CTA handles it (k_spmm_cta_rows)
+        if (p1 - p0 > LONG_ROW) continue;   // hub row: k_spmm_segments + k_spmm_finalize
         Acc<VEC> acc;
         acc_zero(acc);
         spmm_span<VEC>(col, val, p0, p1, X, ldx, d4, lane, acc);
@@ -94,19 +108,26 @@ k_spmm_warp_rows(const int32_t* __restrict__ rowptr, const int32_t* __restrict__
     }
 }
 
+// Hub rows (> LONG_ROW non-zeros) are cut into segments of SEG_NNZ non-zeros; one CTA per segment (8 warps ×
+// SEG_NNZ/8 non-zeros, smem reduction) writes a partial row into the workspace, then one warp per hub row adds its
+// partials IN ORDER and applies the epilogue — no atomics, deterministic, and the longest row no longer sets the
+// kernel's critical path.
+constexpr int SEG_NNZ = 512;
+
 template <int VEC>
 __global__ void __launch_bounds__(SPMM_THREADS)
-k_spmm_cta_rows(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ val,
-                const int32_t* __restrict__ long_rows, int n_long,
-                const float* __restrict__ X, int ldx, float* __restrict__ Y, int ldy, int d4, SpmmEpi epi) {
+k_spmm_segments(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ val,
+                const int32_t* __restrict__ long_rows, const int32_t* __restrict__ seg_row, const int32_t* __restrict__ seg_start,
+                int n_seg, const float* __restrict__ X, int ldx, float* __restrict__ partial, int ldp, int d4) {
     extern __shared__ __align__(16) float red[];   // [SPMM_WARPS][VEC*32] float4
     float4* red4 = reinterpret_cast<float4*>(red);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int li = blockIdx.x; li < n_long; li += gridDim.x) {
-        const int row = __ldg(long_rows + li);
-        const int p0 = __ldg(rowptr + row), p1 = __ldg(rowptr + row + 1);
-        const int per = ((p1 - p0 + SPMM_WARPS - 1) / SPMM_WARPS + 31) / 32 * 32;
-        const int a = min(p1, p0 + warp * per), b = min(p1, a + per);
+    for (int sgi = blockIdx.x; sgi < n_seg; sgi += gridDim.x) {
+        const int row = __ldg(long_rows + __ldg(seg_row + sgi));
+        const int p_end = __ldg(rowptr + row + 1);
+        const int s0 = __ldg(seg_start + sgi), s1 = min(p_end, s0 + SEG_NNZ);
+        const int per = SEG_NNZ / SPMM_WARPS;
+        const int a = min(s1, s0 + warp * per), b = min(s1, a + per);
         Acc<VEC> acc;
         acc_zero(acc);
         spmm_span<VEC>(col, val, a, b, X, ldx, d4, lane, acc);
@@ -114,16 +135,37 @@ k_spmm_cta_rows(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ 
         for (int i = 0; i < VEC; ++i) red4[(warp * VEC + i) * 32 + lane] = acc.v[i];
         __syncthreads();
         if (warp == 0) {
+            float* pr = partial + (size_t)sgi * ldp;
 #pragma unroll
             for (int i = 0; i < VEC; ++i) {
-                float4 s = red4[i * 32 + lane];
-                for (int w = 1; w < SPMM_WARPS; ++w) s = s + red4[(w * VEC + i) * 32 + lane];
-                acc.v[i] = s;
+                float4 sum = red4[i * 32 + lane];
+                for (int w = 1; w < SPMM_WARPS; ++w) sum = sum + red4[(w * VEC + i) * 32 + lane];
+                const int q = lane + 32 * i;
+                if (q < d4) *reinterpret_cast<float4*>(pr + 4 * q) = sum;
             }
-            spmm_store<VEC>(acc, Y, ldy, row, d4, lane, epi);
         }
         __syncthreads();
     }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(SPMM_THREADS)
+k_spmm_finalize(const int32_t* __restrict__ long_rows, const int32_t* __restrict__ seg_ptr, int n_long,
+                const float* __restrict__ partial, int ldp, float* __restrict__ Y, int ldy, int d4, SpmmEpi epi) {
+    const int lane = threadIdx.x & 31;
+    const int li = blockIdx.x * SPMM_WARPS + (threadIdx.x >> 5);
+    if (li >= n_long) return;
+    Acc<VEC> acc;
+    acc_zero(acc);
+    for (int sgi = __ldg(seg_ptr + li); sgi < __ldg(seg_ptr + li + 1); ++sgi) {
+        const float* pr = partial + (size_t)sgi * ldp;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            const int q = lane + 32 * i;
+            if (q < d4) acc.v[i] = acc.v[i] + *reinterpret_cast<const float4*>(pr + 4 * q);
+        }
+    }
+    spmm_store<VEC>(acc, Y, ldy, __ldg(long_rows + li), d4, lane, epi);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -191,32 +233,47 @@ static int spmm_sm_count() {
 
 using namespace oea;
 
-extern "C" int oea_spmm_csr(const oea_csr* A, const int32_t* long_rows, int32_t n_long,
+extern "C" size_t oea_spmm_workspace_bytes(int32_t n_segments, int32_t d) {
+    return n_segments > 0 && d > 0 ? (size_t)n_segments * (size_t)d * sizeof(float) : 0;
+}
+
+extern "C" int oea_spmm_csr(const oea_csr* A, const oea_spmm_hubs* hubs,
                             const float* X, int32_t ldx, float* Y, int32_t ldy, int32_t d,
-                            int32_t relu, const float* mask_src, float beta, void* stream) {
+                            int32_t relu, const float* mask_src, float beta,
+                            void* workspace, size_t workspace_bytes, void* stream) {
     if (!A || !A->rowptr || !X || !Y) return OEA_ERR_NULL;
     if (A->nnz > 0 && (!A->col || !A->val)) return OEA_ERR_NULL;
     if (A->n_rows <= 0 || d <= 0 || (d & 3) || d > 512 || ldx < d || ldy < d || (ldx & 3) || (ldy & 3)) return OEA_ERR_DIM;
     if (!aligned16(X) || !aligned16(Y) || (mask_src && !aligned16(mask_src))) return OEA_ERR_ALIGN;
-    if (n_long < 0 || (n_long > 0 && !long_rows)) return OEA_ERR_NULL;
+    const int n_long = hubs ? hubs->n_long : 0, n_seg = hubs ? hubs->n_seg : 0;
+    if (n_long < 0 || n_seg < n_long) return OEA_ERR_RANGE;
+    if (n_long > 0) {
+        if (!hubs->long_rows || !hubs->seg_ptr || !hubs->seg_row || !hubs->seg_start) return OEA_ERR_NULL;
+        if (!workspace || workspace_bytes < oea_spmm_workspace_bytes(n_seg, d) || !aligned16(workspace)) return OEA_ERR_WORKSPACE;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     SpmmEpi epi{relu, mask_src, beta};
     const int d4 = d >> 2;
     const int blocks = (A->n_rows + SPMM_WARPS - 1) / SPMM_WARPS;
     const int grid = blocks < spmm_sm_count() * 8 ? blocks : spmm_sm_count() * 8;
-    const int lgrid = n_long < spmm_sm_count() * 4 ? n_long : spmm_sm_count() * 4;
+    float* partial = (float*)workspace;
 #define OEA_SPMM(V)                                                                                                          \
     do {                                                                                                                     \
         k_spmm_warp_rows<V><<<grid, SPMM_THREADS, 0, st>>>(A->rowptr, A->col, A->val, A->n_rows, X, ldx, Y, ldy, d4, epi);   \
-        if (n_long > 0)                                                                                                      \
-            k_spmm_cta_rows<V><<<lgrid, SPMM_THREADS, SPMM_WARPS * V * 32 * sizeof(float4), st>>>(                           \
-                A->rowptr, A->col, A->val, long_rows, n_long, X, ldx, Y, ldy, d4, epi);                                      \
+        if (n_long > 0) {                                                                                                    \
+            k_spmm_segments<V><<<n_seg, SPMM_THREADS, SPMM_WARPS * V * 32 * sizeof(float4), st>>>(                           \
+                A->rowptr, A->col, A->val, hubs->long_rows, hubs->seg_row, hubs->seg_start, n_seg, X, ldx, partial, d, d4);  \
+            k_spmm_finalize<V><<<(n_long + SPMM_WARPS - 1) / SPMM_WARPS, SPMM_THREADS, 0, st>>>(                             \
+                hubs->long_rows, hubs->seg_ptr, n_long, partial, d, Y, ldy, d4, epi);                                        \
+        }                                                                                                                    \
     } while (0)
     if (d <= 128) OEA_SPMM(1); else if (d <= 256) OEA_SPMM(2); else if (d <= 384) OEA_SPMM(3); else OEA_SPMM(4);
 #undef OEA_SPMM
     OEA_LAUNCH_CHECK();
     return OEA_OK;
 }
+
+extern "C" int oea_spmm_segment_nnz(void) { return SEG_NNZ; }
 
 extern "C" int oea_spmm_long_row_threshold(void) { return LONG_ROW; }
 

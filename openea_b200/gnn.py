@@ -27,9 +27,19 @@ class DeviceCsr:
         self.rowptr = torch.from_numpy(m.indptr.astype(np.int32)).to(self.device)
         self.col = torch.from_numpy(m.indices.astype(np.int32)).to(self.device)
         self.val = torch.from_numpy(m.data.astype(np.float32)).to(self.device)
-        thr = L.load().oea_spmm_long_row_threshold()
-        long_rows = np.flatnonzero(np.diff(m.indptr) > thr).astype(np.int32)
-        self.long_rows = torch.from_numpy(long_rows).to(self.device)
+        lib = L.load()
+        thr, seg = lib.oea_spmm_long_row_threshold(), lib.oea_spmm_segment_nnz()
+        nnz_row = np.diff(m.indptr)
+        long_rows = np.flatnonzero(nnz_row > thr).astype(np.int32)
+        n_seg_row = -(-nnz_row[long_rows] // seg)
+        seg_ptr = np.concatenate([[0], np.cumsum(n_seg_row)]).astype(np.int32)
+        seg_row = np.repeat(np.arange(len(long_rows)), n_seg_row).astype(np.int32)
+        within = np.arange(int(seg_ptr[-1])) - seg_ptr[seg_row] if len(long_rows) else np.zeros(0, dtype=np.int64)
+        seg_start = (m.indptr[long_rows][seg_row] + within * seg).astype(np.int32) if len(long_rows) else np.zeros(0, np.int32)
+        up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
+        self.long_rows, self.seg_ptr, self.seg_row, self.seg_start = up(long_rows), up(seg_ptr), up(seg_row), up(seg_start)
+        self.n_seg = int(seg_ptr[-1])
+        self._ws = None
         self._t = None
 
     def transpose(self):
@@ -37,6 +47,16 @@ class DeviceCsr:
             self._t = DeviceCsr(self._host.T.tocsr(), self.device)
             self._t._t = self
         return self._t
+
+    def hubs_struct(self):
+        return L.SpmmHubs(self.long_rows.data_ptr(), self.seg_ptr.data_ptr(), self.seg_row.data_ptr(),
+                          self.seg_start.data_ptr(), self.long_rows.numel(), self.n_seg)
+
+    def workspace(self, d):
+        need = L.load().oea_spmm_workspace_bytes(self.n_seg, d)
+        if self._ws is None or self._ws.numel() * 4 < need:
+            self._ws = torch.empty(max(1, need // 4), dtype=torch.float32, device=self.device)
+        return self._ws, need
 
     def c_struct(self):
         return L.Csr(self.rowptr.data_ptr(), self.col.data_ptr(), self.val.data_ptr(), self.shape[0], self.shape[1],
@@ -50,9 +70,10 @@ def spmm(A, X, out=None, relu=False, mask_src=None, beta=0.0):
     d = X.shape[1]
     if out is None:
         out = torch.empty(A.shape[0], d, dtype=torch.float32, device=X.device)
-    cs = A.c_struct()
-    L.check(lib.oea_spmm_csr(C.byref(cs), _ptr(A.long_rows), A.long_rows.numel(), _ptr(X), X.stride(0), _ptr(out),
-                             out.stride(0), d, int(relu), _ptr(mask_src), float(beta), _stream_ptr()), "oea_spmm_csr")
+    cs, hubs = A.c_struct(), A.hubs_struct()
+    ws, ws_bytes = A.workspace(d)
+    L.check(lib.oea_spmm_csr(C.byref(cs), C.byref(hubs), _ptr(X), X.stride(0), _ptr(out), out.stride(0), d, int(relu),
+                             _ptr(mask_src), float(beta), _ptr(ws), ws_bytes, _stream_ptr()), "oea_spmm_csr")
     return out
 
 

@@ -54,6 +54,11 @@ class SimCfg(C.Structure):
                 ("pitch1", C.c_int32), ("pitch2", C.c_int32)]
 
 
+class SpmmHubs(C.Structure):
+    _fields_ = [("long_rows", C.c_void_p), ("seg_ptr", C.c_void_p), ("seg_row", C.c_void_p), ("seg_start", C.c_void_p),
+                ("n_long", C.c_int32), ("n_seg", C.c_int32)]
+
+
 class Csr(C.Structure):
     _fields_ = [("rowptr", C.c_void_p), ("col", C.c_void_p), ("val", C.c_void_p), ("n_rows", C.c_int32),
                 ("n_cols", C.c_int32), ("nnz", C.c_int64)]
@@ -88,7 +93,9 @@ SIGNATURES = {
     "oea_mapping_workspace_bytes": (C.c_size_t, [_I]),
     "oea_mapping_fwd_bwd": (C.c_int, [_P, _P, _I, _I, _I, _P, _I, C.c_float, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "oea_spmm_long_row_threshold": (C.c_int, []),
-    "oea_spmm_csr": (C.c_int, [C.POINTER(Csr), _P, _I, _P, _I, _P, _I, _I, _I, _P, C.c_float, _P]),
+    "oea_spmm_segment_nnz": (C.c_int, []),
+    "oea_spmm_workspace_bytes": (C.c_size_t, [_I, _I]),
+    "oea_spmm_csr": (C.c_int, [C.POINTER(Csr), C.POINTER(SpmmHubs), _P, _I, _P, _I, _I, _I, _P, C.c_float, _P, C.c_size_t, _P]),
     "oea_align_loss_l1": (C.c_int, [_P, _I, _I, _P, _P, _I, _I, _P, _P, _P, _P, C.c_float, _P, _P, _P]),
     "oea_tripleset_build": (C.c_int, [_P, _I, _P, C.c_uint32, C.c_uint32, C.c_uint32, _P]),
 }
