@@ -295,6 +295,17 @@ int oea_spmm_csr(const oea_csr* A, const oea_spmm_hubs* hubs,
                  int32_t relu, const float* mask_src, float beta,
                  void* workspace, size_t workspace_bytes, void* stream);
 
+/* Edge-softmax attention over a sparse neighbourhood (AliNetGraphAttentionLayer.call, approaches/alinet.py:656-677;
+ * same shape in rdgcn.py:202-215):  alpha_e = softmax over the non-zeros of row i of leaky_relu(a_e·(s1[i] + s2[col e]))
+ * (replaces adj*s1, adj*s2ᵀ, tf.sparse_add, tf.nn.leaky_relu, tf.sparse_softmax).  alpha [nnz] is in A's CSR order;
+ * the aggregation Σ alpha·M is oea_spmm_csr with alpha as the values. */
+int oea_edge_softmax_fwd(const oea_csr* A, const float* s1, const float* s2, float slope, float* alpha, void* stream);
+/* out[e] = <G[row e, :d], M[col e, :d]> on A's pattern (d alpha of the aggregation). */
+int oea_sddmm(const oea_csr* A, const float* G, int32_t ldg, const float* M, int32_t ldm, int32_t d, float* out, void* stream);
+/* Backward of oea_edge_softmax_fwd: ds1 [n_rows] is written, ds2 [n_cols] is ACCUMULATED into (caller zeroes it). */
+int oea_edge_softmax_bwd(const oea_csr* A, const float* s1, const float* s2, float slope, const float* alpha,
+                         const float* dalpha, float* ds1, float* ds2, void* stream);
+
 /* align_loss (approaches/gcn_align.py:298-320; rdgcn.py:293-315 has the same form): L1 margin loss over t
  * seed pairs with k negatives per side, mean over 2·k·t, forward + backward.  x [N, ld] are the output
  * embeddings; neg_left/neg_right/neg2_left/neg2_right are [t·k] row ids; *loss_out += loss;

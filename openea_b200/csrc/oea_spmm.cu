@@ -290,3 +290,116 @@ extern "C" int oea_align_loss_l1(const float* x, int32_t ld, int32_t dim, const 
     OEA_LAUNCH_CHECK();
     return OEA_OK;
 }
+
+// ================================================================================================
+// Edge-softmax attention over a sparse neighbourhood (AliNet's AliNetGraphAttentionLayer, alinet.py:656-677;
+// RDGCN's add_sparse_att_layer has the same softmax-over-edges shape, rdgcn.py:202-215):
+//   logit_ij = leaky_relu(a_ij·(s1_i + s2_j)) over the non-zeros (i, j) of the adjacency, alpha = row softmax,
+//   out_i = Σ_j alpha_ij · M_j.
+// Forward  = k_edge_softmax_fwd (alpha per edge) + oea_spmm_csr with alpha as the values.
+// Backward = k_sddmm (d alpha_ij = <dOut_i, M_j>) + k_edge_softmax_bwd (softmax / leaky-relu Jacobians,
+//            d s1 by rows, d s2 scattered by column) + oea_spmm_csr on the transposed pattern for d M.
+// ================================================================================================
+namespace oea {
+
+__device__ __forceinline__ float leaky(float x, float slope) { return x > 0.f ? x : slope * x; }
+
+// one warp per row: alpha[e] = softmax_row(leaky(a_e·(s1_i + s2_col(e))))
+__global__ void __launch_bounds__(256)
+k_edge_softmax_fwd(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ aval,
+                   int n_rows, const float* __restrict__ s1, const float* __restrict__ s2, float slope,
+                   float* __restrict__ alpha) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const int p0 = __ldg(rowptr + row), p1 = __ldg(rowptr + row + 1);
+    const float si = __ldg(s1 + row);
+    float mx = -3.0e38f;
+    for (int p = p0 + lane; p < p1; p += 32) {
+        const float l = leaky(__ldg(aval + p) * (si + __ldg(s2 + __ldg(col + p))), slope);
+        alpha[p] = l;
+        mx = fmaxf(mx, l);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(OEA_FULL, mx, o));
+    float sum = 0.f;
+    for (int p = p0 + lane; p < p1; p += 32) { const float e = __expf(alpha[p] - mx); alpha[p] = e; sum += e; }
+    sum = warp_sum(sum);
+    const float inv = sum > 0.f ? 1.f / sum : 0.f;
+    for (int p = p0 + lane; p < p1; p += 32) alpha[p] *= inv;
+}
+
+// sampled dense-dense product on the sparsity pattern: out[e] = <G[row(e), :], M[col(e), :]>; warp per row
+__global__ void __launch_bounds__(256)
+k_sddmm(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int n_rows,
+        const float* __restrict__ G, int ldg_, const float* __restrict__ M, int ldm, int d4, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const int p0 = __ldg(rowptr + row), p1 = __ldg(rowptr + row + 1);
+    const float* g = G + (size_t)row * ldg_;
+    for (int p = p0; p < p1; ++p) {
+        const float* m = M + (size_t)__ldg(col + p) * ldm;
+        float acc = 0.f;
+        for (int q = lane; q < d4; q += 32) acc += dot4(ldg4(g + 4 * q), ldg4(m + 4 * q));
+        acc = warp_sum(acc);
+        if (lane == 0) out[p] = acc;
+    }
+}
+
+// softmax + leaky-relu backward per row; d s1[i] = Σ_e a_e·dlogit_e ; d s2[col(e)] += a_e·dlogit_e (atomics)
+__global__ void __launch_bounds__(256)
+k_edge_softmax_bwd(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ aval,
+                   int n_rows, const float* __restrict__ s1, const float* __restrict__ s2, float slope,
+                   const float* __restrict__ alpha, const float* __restrict__ dalpha,
+                   float* __restrict__ ds1, float* __restrict__ ds2) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const int p0 = __ldg(rowptr + row), p1 = __ldg(rowptr + row + 1);
+    float dotp = 0.f;
+    for (int p = p0 + lane; p < p1; p += 32) dotp += __ldg(alpha + p) * __ldg(dalpha + p);
+    dotp = warp_sum(dotp);
+    const float si = __ldg(s1 + row);
+    float acc1 = 0.f;
+    for (int p = p0 + lane; p < p1; p += 32) {
+        const int c = __ldg(col + p);
+        const float a = __ldg(aval + p);
+        const float pre = a * (si + __ldg(s2 + c));
+        const float dl = __ldg(alpha + p) * (__ldg(dalpha + p) - dotp) * (pre > 0.f ? 1.f : slope) * a;
+        acc1 += dl;
+        if (dl != 0.f) atomicAdd(ds2 + c, dl);
+    }
+    acc1 = warp_sum(acc1);
+    if (lane == 0) ds1[row] = acc1;
+}
+
+}  // namespace oea
+
+extern "C" int oea_edge_softmax_fwd(const oea_csr* A, const float* s1, const float* s2, float slope, float* alpha, void* stream) {
+    if (!A || !A->rowptr || !s1 || !s2 || !alpha) return OEA_ERR_NULL;
+    if (A->nnz > 0 && (!A->col || !A->val)) return OEA_ERR_NULL;
+    if (A->n_rows <= 0) return OEA_ERR_DIM;
+    k_edge_softmax_fwd<<<(A->n_rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(A->rowptr, A->col, A->val, A->n_rows, s1, s2, slope, alpha);
+    OEA_LAUNCH_CHECK();
+    return OEA_OK;
+}
+
+extern "C" int oea_sddmm(const oea_csr* A, const float* G, int32_t ldg_, const float* M, int32_t ldm, int32_t d, float* out, void* stream) {
+    if (!A || !A->rowptr || !G || !M || !out) return OEA_ERR_NULL;
+    if (A->n_rows <= 0 || d <= 0 || (d & 3) || ldg_ < d || ldm < d || (ldg_ & 3) || (ldm & 3)) return OEA_ERR_DIM;
+    if (!aligned16(G) || !aligned16(M)) return OEA_ERR_ALIGN;
+    k_sddmm<<<(A->n_rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(A->rowptr, A->col, A->n_rows, G, ldg_, M, ldm, d >> 2, out);
+    OEA_LAUNCH_CHECK();
+    return OEA_OK;
+}
+
+extern "C" int oea_edge_softmax_bwd(const oea_csr* A, const float* s1, const float* s2, float slope, const float* alpha,
+                                    const float* dalpha, float* ds1, float* ds2, void* stream) {
+    if (!A || !A->rowptr || !s1 || !s2 || !alpha || !dalpha || !ds1 || !ds2) return OEA_ERR_NULL;
+    if (A->n_rows <= 0) return OEA_ERR_DIM;
+    k_edge_softmax_bwd<<<(A->n_rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(A->rowptr, A->col, A->val, A->n_rows, s1, s2, slope,
+                                                                             alpha, dalpha, ds1, ds2);
+    OEA_LAUNCH_CHECK();
+    return OEA_OK;
+}

@@ -48,6 +48,17 @@ class DeviceCsr:
             self._t._t = self
         return self._t
 
+    def transpose_perm(self):
+        """perm [nnz] (int64 CUDA tensor): position e of the TRANSPOSE's CSR order holds edge perm[e] of this matrix,
+        so `vals[perm]` are per-edge values re-ordered for the transposed pattern (backward of a weighted SpMM)."""
+        if getattr(self, "_perm", None) is None:
+            m = self._host
+            ids = sp.csr_matrix((np.arange(1, m.nnz + 1, dtype=np.float64), m.indices, m.indptr), shape=m.shape)
+            t = ids.T.tocsr()
+            t.sort_indices()
+            self._perm = torch.from_numpy((t.data - 1).astype(np.int64)).to(self.device)
+        return self._perm
+
     def hubs_struct(self):
         return L.SpmmHubs(self.long_rows.data_ptr(), self.seg_ptr.data_ptr(), self.seg_row.data_ptr(),
                           self.seg_start.data_ptr(), self.long_rows.numel(), self.n_seg)
@@ -58,23 +69,70 @@ class DeviceCsr:
             self._ws = torch.empty(max(1, need // 4), dtype=torch.float32, device=self.device)
         return self._ws, need
 
-    def c_struct(self):
-        return L.Csr(self.rowptr.data_ptr(), self.col.data_ptr(), self.val.data_ptr(), self.shape[0], self.shape[1],
-                     self.nnz)
+    def c_struct(self, vals=None):
+        v = self.val if vals is None else vals
+        return L.Csr(self.rowptr.data_ptr(), self.col.data_ptr(), v.data_ptr(), self.shape[0], self.shape[1], self.nnz)
 
 
-def spmm(A, X, out=None, relu=False, mask_src=None, beta=0.0):
-    """Y = A·X (fp32, X row-major with X.shape[1] % 4 == 0), optional fused relu / relu-backward mask."""
+def spmm(A, X, out=None, relu=False, mask_src=None, beta=0.0, vals=None):
+    """Y = A·X (fp32, X row-major with X.shape[1] % 4 == 0), optional fused relu / relu-backward mask.
+    `vals` [nnz] replaces A's values (same pattern), e.g. attention coefficients."""
     lib = L.load()
     assert X.is_cuda and X.dtype == torch.float32 and X.stride(1) == 1
     d = X.shape[1]
     if out is None:
         out = torch.empty(A.shape[0], d, dtype=torch.float32, device=X.device)
-    cs, hubs = A.c_struct(), A.hubs_struct()
+    cs, hubs = A.c_struct(vals), A.hubs_struct()
     ws, ws_bytes = A.workspace(d)
     L.check(lib.oea_spmm_csr(C.byref(cs), C.byref(hubs), _ptr(X), X.stride(0), _ptr(out), out.stride(0), d, int(relu),
                              _ptr(mask_src), float(beta), _ptr(ws), ws_bytes, _stream_ptr()), "oea_spmm_csr")
     return out
+
+
+class SpmmFn(torch.autograd.Function):
+    """Y = A·X for autograd graphs (A constant): backward is the same kernel on Aᵀ."""
+
+    @staticmethod
+    def forward(ctx, X, A):
+        ctx.A = A
+        return spmm(A, X.contiguous())
+
+    @staticmethod
+    def backward(ctx, gY):
+        return spmm(ctx.A.transpose(), gY.contiguous()), None
+
+
+class GatAggregateFn(torch.autograd.Function):
+    """out_i = Σ_j softmax_j(leaky_relu(a_ij·(s1_i + s2_j)))·M_j over the non-zeros of A (alinet.py:656-677)."""
+
+    @staticmethod
+    def forward(ctx, s1, s2, M, A, slope):
+        lib = L.load()
+        s1, s2, M = s1.contiguous(), s2.contiguous(), M.contiguous()
+        alpha = torch.empty(A.nnz, dtype=torch.float32, device=M.device)
+        cs = A.c_struct()
+        L.check(lib.oea_edge_softmax_fwd(C.byref(cs), _ptr(s1), _ptr(s2), float(slope), _ptr(alpha), _stream_ptr()),
+                "oea_edge_softmax_fwd")
+        ctx.A, ctx.slope = A, float(slope)
+        ctx.save_for_backward(s1, s2, M, alpha)
+        return spmm(A, M, vals=alpha)
+
+    @staticmethod
+    def backward(ctx, gOut):
+        lib = L.load()
+        s1, s2, M, alpha = ctx.saved_tensors
+        A = ctx.A
+        gOut = gOut.contiguous()
+        cs = A.c_struct()
+        dalpha = torch.empty_like(alpha)
+        L.check(lib.oea_sddmm(C.byref(cs), _ptr(gOut), gOut.stride(0), _ptr(M), M.stride(0), M.shape[1], _ptr(dalpha),
+                              _stream_ptr()), "oea_sddmm")
+        ds1 = torch.empty_like(s1)
+        ds2 = torch.zeros_like(s2)
+        L.check(lib.oea_edge_softmax_bwd(C.byref(cs), _ptr(s1), _ptr(s2), ctx.slope, _ptr(alpha), _ptr(dalpha), _ptr(ds1),
+                                         _ptr(ds2), _stream_ptr()), "oea_edge_softmax_bwd")
+        dM = spmm(A.transpose(), gOut, vals=alpha.index_select(0, A.transpose_perm()))
+        return ds1, ds2, dM, None, None
 
 
 def align_loss_l1(x, dim, left, right, k, neg_left, neg_right, neg2_left, neg2_right, gamma, grad, loss_out):

@@ -96,6 +96,9 @@ SIGNATURES = {
     "oea_spmm_segment_nnz": (C.c_int, []),
     "oea_spmm_workspace_bytes": (C.c_size_t, [_I, _I]),
     "oea_spmm_csr": (C.c_int, [C.POINTER(Csr), C.POINTER(SpmmHubs), _P, _I, _P, _I, _I, _I, _P, C.c_float, _P, C.c_size_t, _P]),
+    "oea_edge_softmax_fwd": (C.c_int, [C.POINTER(Csr), _P, _P, C.c_float, _P, _P]),
+    "oea_sddmm": (C.c_int, [C.POINTER(Csr), _P, _I, _P, _I, _I, _P, _P]),
+    "oea_edge_softmax_bwd": (C.c_int, [C.POINTER(Csr), _P, _P, C.c_float, _P, _P, _P, _P, _P]),
     "oea_align_loss_l1": (C.c_int, [_P, _I, _I, _P, _P, _I, _I, _P, _P, _P, _P, C.c_float, _P, _P, _P]),
     "oea_tripleset_build": (C.c_int, [_P, _I, _P, C.c_uint32, C.c_uint32, C.c_uint32, _P]),
 }

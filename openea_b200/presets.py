@@ -47,3 +47,13 @@ def gcn_align(scale="15K"):
                  neg_triple_num=5, learning_rate=8, batch_size=5000, test_threads_num=3, eval_metric="manhattan",
                  eval_norm=False, support_number=1, se_dim=100, ae_dim=100, hidden1=100, gamma=3, early_stop=False,
                  dropout=0, test_method="sa", beta=0.9)
+
+
+def alinet(scale="15K"):
+    big = scale != "15K"
+    return _args(embedding_module="AliNet", alignment_module="mapping", layer_dims=[500, 400, 300], init="xavier",
+                 ent_l2_norm=True, rel_l2_norm=True, learning_rate=0.001, optimizer="Adam",
+                 batch_size=20000 if big else 3000, neg_margin=1.5, neg_margin_balance=0.1, dropout=0.0,
+                 neg_sampling="truncated", neg_triple_num=10, truncated_epsilon=0.995 if big else 0.98, truncated_freq=10,
+                 start_valid=10, eval_metric="inner", eval_norm=False, is_save=False, min_rel_win=50 if not big else 15,
+                 start_augment=2, rel_param=0.01, num_features_nonzero=0, sim_th=0.0, k=20)

@@ -72,3 +72,78 @@ def unit_train_step(support, W0, features, ill, gamma, k, negs, lr, dtype=torch.
     with torch.no_grad():
         W_new = W - lr * W.grad
     return float(loss.detach()), W_new.numpy(), out.detach().numpy()
+
+
+# ---- AliNet (approaches/alinet.py) — torch-CPU restatement with dense-free sparse ops; PARITY UNPINNED vs TF ----
+ALINET_REF_FILE = "/root/reference/src/openea/approaches/alinet.py"
+
+
+def reference_alinet_builders():
+    """Namespace with the reference's own pure-Python/NumPy/pandas builders (AKG, enhance_triples, no_weighted_adj,
+    generate_2hop_triples, remove_unlinked_triples, generate_rel_ht, …) compiled from its source; None if absent."""
+    if not os.path.exists(ALINET_REF_FILE):
+        return None
+    import math
+    import time
+    import pandas as pd
+    with open(ALINET_REF_FILE) as f:
+        tree = ast.parse(f.read())
+    want = {"sparse_to_tuple", "normalize_adj", "preprocess_adj", "no_weighted_adj", "remove_unlinked_triples",
+            "generate_2hop_triples", "enhance_triples", "generate_rel_ht", "AKG"}
+    keep = [n for n in tree.body if isinstance(n, (ast.FunctionDef, ast.ClassDef)) and n.name in want]
+    ns = {"np": np, "sp": sp, "pd": pd, "math": math, "time": time, "print": lambda *a, **k: None}
+    exec(compile(ast.Module(body=keep, type_ignores=[]), ALINET_REF_FILE, "exec"), ns)
+    return ns
+
+
+def edge_softmax_aggregate(adj, s1, s2, M, slope=0.2):
+    """Σ_j softmax_j(leaky_relu(a_ij (s1_i + s2_j))) M_j over the non-zeros of `adj` (scipy), with torch autograd."""
+    m = sp.coo_matrix(adj)
+    row = torch.as_tensor(m.row, dtype=torch.long)
+    col = torch.as_tensor(m.col, dtype=torch.long)
+    a = torch.as_tensor(m.data, dtype=M.dtype)
+    logit = torch.nn.functional.leaky_relu(a * (s1[row] + s2[col]), slope)
+    mx = torch.full((m.shape[0],), -1e30, dtype=M.dtype).scatter_reduce(0, row, logit, "amax")
+    ex = torch.exp(logit - mx[row])
+    den = torch.zeros(m.shape[0], dtype=M.dtype).index_add(0, row, ex)
+    alpha = ex / den[row]
+    return torch.zeros(m.shape[0], M.shape[1], dtype=M.dtype).index_add(0, row, alpha[:, None] * M[col])
+
+
+def alinet_forward(params, adj1, adj2, n_layers, dtype=torch.float64):
+    """Same graph as openea_b200.approaches.alinet.AliNetModel.forward with torch.sparse / scatter ops."""
+    import math
+    bn = lambda x, g, b: x * (g / math.sqrt(1.0 + 1e-3)) + b
+    A1 = _sparse(adj1, dtype)
+    x = params["init_embedding"]
+    outs = []
+    for i in range(n_layers):
+        xb = bn(x, params["gcn%d.bn_gamma" % i], params["gcn%d.bn_beta" % i])
+        one = torch.tanh(torch.sparse.mm(A1, xb @ params["gcn%d.kernel" % i]) + params["gcn%d.bias" % i])
+        if i < n_layers - 1:
+            xg = bn(x, params["gat%d.bn_gamma" % i], params["gat%d.bn_beta" % i])
+            mapped = xg @ params["gat%d.kernel" % i]
+            s1 = torch.tanh(((xg @ params["gat%d.kernel1" % i]) * xg).sum(1))
+            s2 = torch.tanh(((xg @ params["gat%d.kernel2" % i]) * xg).sum(1))
+            two = torch.tanh(edge_softmax_aggregate(adj2, s1, s2, mapped))
+            g1 = bn(two, params["hw%d.bn_gamma" % i], params["hw%d.bn_beta" % i])
+            g2 = bn(one, params["hw%d.bn_gamma" % i], params["hw%d.bn_beta" % i])
+            gate = torch.relu(torch.tanh(g1 @ params["hw%d.kernel" % i]))
+            x = torch.tanh(g2 * (1 - gate) + g1 * gate)
+        else:
+            x = one
+        outs.append(x)
+    return outs
+
+
+def alinet_loss(params, outs, pos, neg, neg_margin, balance, hs, ts, rel_win, rel_param):
+    emb = l2n(torch.cat([l2n(o) for o in outs + [params["init_embedding"]]], dim=1))
+    tl = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.long)
+    pos, neg = tl(pos), tl(neg)
+    total = ((emb[pos[:, 0]] - emb[pos[:, 1]]) ** 2).sum()
+    total = total + balance * torch.relu(neg_margin - ((emb[neg[:, 0]] - emb[neg[:, 1]]) ** 2).sum(1)).sum()
+    if rel_param > 0:
+        diff = emb[tl(hs)] - emb[tl(ts)]
+        r = l2n(diff.reshape(-1, rel_win, emb.shape[1]).mean(1, keepdim=True).expand(-1, rel_win, -1).reshape(-1, emb.shape[1]))
+        total = total + rel_param * ((diff - r) ** 2).sum()
+    return total

@@ -141,3 +141,99 @@ def test_gcn_align_lifecycle(cuda_device, tmp_path):
     h1 = float(re.findall(r"accurate results: hits@\[1, 5, 10, 50\] = \[\s*([0-9.]+)", out)[-1])
     assert h1 > 5.0, h1          # chance = 0.24 %
     assert os.path.exists(m.out_folder + "ent_embeds.npy") and os.path.exists(m.out_folder + "attr_embeds.npy")
+
+
+def _small_graph(rng, n, avg):
+    rows = rng.integers(0, n, n * avg); cols = rng.integers(0, n, n * avg)
+    hub = rng.integers(0, n, 600)
+    rows = np.concatenate([rows, np.zeros(600, dtype=np.int64), np.arange(n)]); cols = np.concatenate([cols, hub, np.arange(n)])
+    m = sp.coo_matrix((rng.random(rows.size) + 0.1, (rows, cols)), shape=(n, n)).tocsr()
+    return m
+
+
+def test_gat_aggregate_fwd_bwd_matches_autograd(cuda_device):
+    """Edge-softmax attention aggregation (alinet.py:656-677): kernels vs a float64 torch scatter restatement."""
+    from openea_b200 import gnn
+    rng = np.random.default_rng(9)
+    n, d = 700, 100
+    adj = _small_graph(rng, n, 5)
+    A = gnn.DeviceCsr(adj)
+    assert A.long_rows.numel() >= 1
+    s1h, s2h = rng.standard_normal(n).astype(np.float32), rng.standard_normal(n).astype(np.float32)
+    Mh, Gh = rng.standard_normal((n, d)).astype(np.float32), rng.standard_normal((n, d)).astype(np.float32)
+    s1 = torch.tensor(s1h, device="cuda", requires_grad=True); s2 = torch.tensor(s2h, device="cuda", requires_grad=True)
+    M = torch.tensor(Mh, device="cuda", requires_grad=True)
+    out = gnn.GatAggregateFn.apply(s1, s2, M, A, 0.2)
+    (out * torch.tensor(Gh, device="cuda")).sum().backward()
+    o1 = torch.tensor(s1h, dtype=torch.float64, requires_grad=True); o2 = torch.tensor(s2h, dtype=torch.float64, requires_grad=True)
+    oM = torch.tensor(Mh, dtype=torch.float64, requires_grad=True)
+    want = orc.edge_softmax_aggregate(sp.csr_matrix(adj, dtype=np.float32), o1, o2, oM)
+    (want * torch.tensor(Gh, dtype=torch.float64)).sum().backward()
+    np.testing.assert_allclose(out.detach().cpu().numpy(), want.detach().numpy(), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(M.grad.cpu().numpy(), oM.grad.numpy(), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(s1.grad.cpu().numpy(), o1.grad.numpy(), rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(s2.grad.cpu().numpy(), o2.grad.numpy(), rtol=2e-4, atol=2e-5)
+
+
+def test_alinet_step_matches_oracle(cuda_device):
+    """One session.run([loss, optimizer]) of the AliNet graph: loss, gradients and the TF-Adam update."""
+    from openea_b200 import gnn
+    from openea_b200.approaches.alinet import AliNetModel, DenseAdam
+    rng = np.random.default_rng(4)
+    n, dims = 600, [64, 48, 32]
+    adj1 = gnn.normalize_adj(_small_graph(rng, n, 4)).tocsr()
+    adj2 = gnn.normalize_adj(_small_graph(rng, n, 6)).tocsr()
+    model = AliNetModel(n, dims, gnn.DeviceCsr(adj1), gnn.DeviceCsr(adj2), torch.device("cuda"), seed=1)
+    pos = np.stack([rng.integers(0, n, 80), rng.integers(0, n, 80)], 1)
+    neg = np.stack([rng.integers(0, n, 600), rng.integers(0, n, 600)], 1)
+    rel_win = 5
+    hs, ts = rng.integers(0, n, 7 * rel_win), rng.integers(0, n, 7 * rel_win)
+    tl = lambda a: torch.as_tensor(a, dtype=torch.long, device="cuda")
+    before = {k: v.detach().cpu().numpy().copy() for k, v in model.params.items()}
+    oparams = {k: torch.tensor(v, dtype=torch.float64, requires_grad=True) for k, v in before.items()}
+    oouts = orc.alinet_forward(oparams, adj1, adj2, 2)
+    oloss = orc.alinet_loss(oparams, oouts, pos, neg, 1.5, 0.1, hs, ts, rel_win, 0.01)
+    oloss.backward()
+    opt = DenseAdam(list(model.params.values()), 0.001)
+    outs = model.forward()
+    loss = model.loss(outs, tl(pos), tl(neg), 1.5, 0.1, tl(hs), tl(ts), rel_win, 0.01)
+    assert float(loss.detach().item()) == pytest.approx(float(oloss.detach()), rel=1e-4)
+    loss.backward()
+    for k in ("init_embedding", "gcn0.kernel", "gat0.kernel1", "hw0.kernel", "gcn1.bias", "gat0.bn_gamma"):
+        g, w = model.params[k].grad.cpu().numpy(), oparams[k].grad.numpy()
+        np.testing.assert_allclose(g, w, rtol=2e-3, atol=2e-5 * max(1e-6, np.abs(w).max()), err_msg=k)
+    opt.step()
+    # TF Adam, t = 1: lr_t = lr·√(1−β2)/(1−β1); m = (1−β1) g; v = (1−β2) g² → x −= lr_t·m/(√v + ε)
+    lr_t = 0.001 * np.sqrt(1 - 0.999) / (1 - 0.9)
+    for k in ("init_embedding", "gcn0.kernel"):
+        g = oparams[k].grad.numpy()
+        want = before[k] - lr_t * (0.1 * g) / (np.sqrt(0.001 * g * g) + 1e-8)
+        np.testing.assert_allclose(model.params[k].detach().cpu().numpy(), want, rtol=1e-3, atol=2e-6)
+
+
+def test_alinet_lifecycle(cuda_device, tmp_path):
+    import os
+    import re
+    from openea_b200 import presets
+    from openea_b200.approaches import AliNet
+    from openea_b200.modules.load.kgs import read_kgs_from_folder
+    from openea_b200.synth import write_dataset
+    folder = str(tmp_path) + "/data/"
+    write_dataset(folder, "tiny")
+    args = presets.alinet()
+    args.training_data, args.output = folder, str(tmp_path) + "/out/"
+    args.layer_dims, args.batch_size, args.max_epoch, args.start_valid, args.eval_freq = [64, 48, 32], 200, 60, 20, 20
+    args.truncated_epsilon, args.min_rel_win = 0.9, 5
+    np.random.seed(0)
+    import random
+    random.seed(0)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        kgs = read_kgs_from_folder(folder, args.dataset_division, "mapping", True)
+        m = AliNet(); m.set_args(args); m.set_kgs(kgs); m.init(); m.run(); m.test(); m.save()
+    out = buf.getvalue()
+    assert "epoch 60, loss:" in out and "neighbors num" in out
+    h1 = float(re.findall(r"accurate results: hits@\[1, 5, 10, 50\] = \[\s*([0-9.]+)", out)[-1])
+    assert h1 > 3.0, h1          # chance = 0.24 %
+    assert os.path.exists(m.out_folder + "ent_embeds.npy")
+    assert np.load(m.out_folder + "ent_embeds.npy").shape[1] == 64 + 48 + 32
