@@ -298,7 +298,10 @@ int oea_spmm_csr(const oea_csr* A, const oea_spmm_hubs* hubs,
 /* Edge-softmax attention over a sparse neighbourhood (AliNetGraphAttentionLayer.call, approaches/alinet.py:656-677;
  * same shape in rdgcn.py:202-215):  alpha_e = softmax over the non-zeros of row i of leaky_relu(a_e·(s1[i] + s2[col e]))
  * (replaces adj*s1, adj*s2ᵀ, tf.sparse_add, tf.nn.leaky_relu, tf.sparse_softmax).  alpha [nnz] is in A's CSR order;
- * the aggregation Σ alpha·M is oea_spmm_csr with alpha as the values. */
+ * the aggregation Σ alpha·M is oea_spmm_csr with alpha as the values.
+ * Edge-logit mode (s1 == s2 == NULL): A->val[e] is itself the pre-activation logit of edge e (RDGCN's
+ * add_sparse_att_layer, rdgcn.py:202-215: logit_e = dual_transform[relation of e]); in the backward ds1 is then a
+ * per-EDGE array [nnz] = d loss / d A->val[e] and ds2 is unused. */
 int oea_edge_softmax_fwd(const oea_csr* A, const float* s1, const float* s2, float slope, float* alpha, void* stream);
 /* out[e] = <G[row e, :d], M[col e, :d]> on A's pattern (d alpha of the aggregation). */
 int oea_sddmm(const oea_csr* A, const float* G, int32_t ldg, const float* M, int32_t ldm, int32_t d, float* out, void* stream);

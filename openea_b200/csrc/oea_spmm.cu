@@ -313,10 +313,12 @@ k_edge_softmax_fwd(const int32_t* __restrict__ rowptr, const int32_t* __restrict
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= n_rows) return;
     const int p0 = __ldg(rowptr + row), p1 = __ldg(rowptr + row + 1);
-    const float si = __ldg(s1 + row);
+    const bool node_mode = s1 != nullptr;     // else: aval[e] IS the pre-activation logit of edge e
+    const float si = node_mode ? __ldg(s1 + row) : 0.f;
     float mx = -3.0e38f;
     for (int p = p0 + lane; p < p1; p += 32) {
-        const float l = leaky(__ldg(aval + p) * (si + __ldg(s2 + __ldg(col + p))), slope);
+        const float pre = node_mode ? __ldg(aval + p) * (si + __ldg(s2 + __ldg(col + p))) : __ldg(aval + p);
+        const float l = leaky(pre, slope);
         alpha[p] = l;
         mx = fmaxf(mx, l);
     }
@@ -360,6 +362,13 @@ k_edge_softmax_bwd(const int32_t* __restrict__ rowptr, const int32_t* __restrict
     float dotp = 0.f;
     for (int p = p0 + lane; p < p1; p += 32) dotp += __ldg(alpha + p) * __ldg(dalpha + p);
     dotp = warp_sum(dotp);
+    if (s1 == nullptr) {   // edge-logit mode: ds1 is a per-EDGE output [nnz] = d loss / d aval[e]
+        for (int p = p0 + lane; p < p1; p += 32) {
+            const float pre = __ldg(aval + p);
+            ds1[p] = __ldg(alpha + p) * (__ldg(dalpha + p) - dotp) * (pre > 0.f ? 1.f : slope);
+        }
+        return;
+    }
     const float si = __ldg(s1 + row);
     float acc1 = 0.f;
     for (int p = p0 + lane; p < p1; p += 32) {
@@ -377,7 +386,8 @@ k_edge_softmax_bwd(const int32_t* __restrict__ rowptr, const int32_t* __restrict
 }  // namespace oea
 
 extern "C" int oea_edge_softmax_fwd(const oea_csr* A, const float* s1, const float* s2, float slope, float* alpha, void* stream) {
-    if (!A || !A->rowptr || !s1 || !s2 || !alpha) return OEA_ERR_NULL;
+    if (!A || !A->rowptr || !alpha) return OEA_ERR_NULL;
+    if ((s1 == nullptr) != (s2 == nullptr)) return OEA_ERR_NULL;     // both (node mode) or neither (edge-logit mode)
     if (A->nnz > 0 && (!A->col || !A->val)) return OEA_ERR_NULL;
     if (A->n_rows <= 0) return OEA_ERR_DIM;
     k_edge_softmax_fwd<<<(A->n_rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(A->rowptr, A->col, A->val, A->n_rows, s1, s2, slope, alpha);
@@ -396,7 +406,8 @@ extern "C" int oea_sddmm(const oea_csr* A, const float* G, int32_t ldg_, const f
 
 extern "C" int oea_edge_softmax_bwd(const oea_csr* A, const float* s1, const float* s2, float slope, const float* alpha,
                                     const float* dalpha, float* ds1, float* ds2, void* stream) {
-    if (!A || !A->rowptr || !s1 || !s2 || !alpha || !dalpha || !ds1 || !ds2) return OEA_ERR_NULL;
+    if (!A || !A->rowptr || !alpha || !dalpha || !ds1) return OEA_ERR_NULL;
+    if ((s1 == nullptr) != (s2 == nullptr) || (s1 != nullptr && !ds2)) return OEA_ERR_NULL;
     if (A->n_rows <= 0) return OEA_ERR_DIM;
     k_edge_softmax_bwd<<<(A->n_rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(A->rowptr, A->col, A->val, A->n_rows, s1, s2, slope,
                                                                              alpha, dalpha, ds1, ds2);

@@ -16,10 +16,12 @@ from .engine import _ptr, _stream_ptr
 class DeviceCsr:
     """A sparse matrix on the device in CSR (int32 / fp32) plus, lazily, its transpose (for the backward)."""
 
-    def __init__(self, mat, device="cuda"):
+    def __init__(self, mat, device="cuda", keep_duplicates=False):
         m = sp.csr_matrix(mat, dtype=np.float32)
-        m.sum_duplicates()
+        if not keep_duplicates:          # RDGCN's r_mat keeps one entry per triple, duplicates of (h, t) included
+            m.sum_duplicates()
         m.sort_indices()
+        self._keep_dup = keep_duplicates
         self.shape = m.shape
         self.nnz = int(m.nnz)
         self.device = torch.device(device)
@@ -44,7 +46,7 @@ class DeviceCsr:
 
     def transpose(self):
         if self._t is None:
-            self._t = DeviceCsr(self._host.T.tocsr(), self.device)
+            self._t = DeviceCsr(self._host.T.tocsr(), self.device, keep_duplicates=self._keep_dup)
             self._t._t = self
         return self._t
 
@@ -133,6 +135,57 @@ class GatAggregateFn(torch.autograd.Function):
                                          _ptr(ds2), _stream_ptr()), "oea_edge_softmax_bwd")
         dM = spmm(A.transpose(), gOut, vals=alpha.index_select(0, A.transpose_perm()))
         return ds1, ds2, dM, None, None
+
+
+class EdgeLogitAggregateFn(torch.autograd.Function):
+    """out_i = Σ_e softmax over row i of leaky_relu(logit_e) · X[col e] with per-EDGE logits (rdgcn.py:202-215)."""
+
+    @staticmethod
+    def forward(ctx, edge_logits, X, A, slope):
+        lib = L.load()
+        edge_logits, X = edge_logits.contiguous(), X.contiguous()
+        alpha = torch.empty(A.nnz, dtype=torch.float32, device=X.device)
+        cs = A.c_struct(edge_logits)
+        L.check(lib.oea_edge_softmax_fwd(C.byref(cs), None, None, float(slope), _ptr(alpha), _stream_ptr()),
+                "oea_edge_softmax_fwd")
+        ctx.A, ctx.slope = A, float(slope)
+        ctx.save_for_backward(edge_logits, X, alpha)
+        return spmm(A, X, vals=alpha)
+
+    @staticmethod
+    def backward(ctx, gOut):
+        lib = L.load()
+        edge_logits, X, alpha = ctx.saved_tensors
+        A = ctx.A
+        gOut = gOut.contiguous()
+        cs = A.c_struct(edge_logits)
+        dalpha = torch.empty_like(alpha)
+        L.check(lib.oea_sddmm(C.byref(cs), _ptr(gOut), gOut.stride(0), _ptr(X), X.stride(0), X.shape[1], _ptr(dalpha),
+                              _stream_ptr()), "oea_sddmm")
+        dlogit = torch.empty_like(alpha)
+        L.check(lib.oea_edge_softmax_bwd(C.byref(cs), None, None, ctx.slope, _ptr(alpha), _ptr(dalpha), _ptr(dlogit),
+                                         None, _stream_ptr()), "oea_edge_softmax_bwd")
+        dX = spmm(A.transpose(), gOut, vals=alpha.index_select(0, A.transpose_perm()))
+        return dlogit, dX, None, None
+
+
+class AlignLossL1Fn(torch.autograd.Function):
+    """align_loss / get_loss (gcn_align.py:298-320, rdgcn.py:293-315) for autograd graphs: forward+backward in one
+    kernel launch; the gradient is kept for backward()."""
+
+    @staticmethod
+    def forward(ctx, x, left, right, k, negs, gamma):
+        x = x.contiguous()
+        grad = torch.zeros_like(x)
+        loss = torch.zeros(1, dtype=torch.float64, device=x.device)
+        align_loss_l1(x, x.shape[1], left, right, k, negs[0], negs[1], negs[2], negs[3], gamma, grad, loss)
+        ctx.save_for_backward(grad)
+        return loss.to(torch.float32).reshape(())
+
+    @staticmethod
+    def backward(ctx, gout):
+        (grad,) = ctx.saved_tensors
+        return grad * gout, None, None, None, None, None
 
 
 def align_loss_l1(x, dim, left, right, k, neg_left, neg_right, neg2_left, neg2_right, gamma, grad, loss_out):

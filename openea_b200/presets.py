@@ -57,3 +57,11 @@ def alinet(scale="15K"):
                  neg_sampling="truncated", neg_triple_num=10, truncated_epsilon=0.995 if big else 0.98, truncated_freq=10,
                  start_valid=10, eval_metric="inner", eval_norm=False, is_save=False, min_rel_win=50 if not big else 15,
                  start_augment=2, rel_param=0.01, num_features_nonzero=0, sim_th=0.0, k=20)
+
+
+def rdgcn(scale="15K"):
+    big = scale != "15K"
+    return _args(embedding_module="RDGCN", alignment_module="mapping", dim=300, neg_sampling="uniform",
+                 neg_triple_num=10 if big else 125, learning_rate=0.001 if big else 0.002, batch_size=5000,
+                 test_threads_num=3, start_valid=30, eval_metric="manhattan", eval_norm=False, gamma=1.0, dropout=0,
+                 beta=0.3, alpha=0.1, synthetic_names=True)

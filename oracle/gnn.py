@@ -147,3 +147,64 @@ def alinet_loss(params, outs, pos, neg, neg_margin, balance, hs, ts, rel_win, re
         r = l2n(diff.reshape(-1, rel_win, emb.shape[1]).mean(1, keepdim=True).expand(-1, rel_win, -1).reshape(-1, emb.shape[1]))
         total = total + rel_param * ((diff - r) ** 2).sum()
     return total
+
+
+# ---- RDGCN (approaches/rdgcn.py) — torch-CPU restatement; PARITY UNPINNED vs TF -------------------------------
+RDGCN_REF_FILE = "/root/reference/src/openea/approaches/rdgcn.py"
+
+
+def reference_rdgcn_builders():
+    """get_mat / rfunc of the reference compiled from its source (tf.SparseTensor stubbed to a tuple)."""
+    if not os.path.exists(RDGCN_REF_FILE):
+        return None
+    import math
+    import types
+    with open(RDGCN_REF_FILE) as f:
+        tree = ast.parse(f.read())
+    keep = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in ("rfunc", "get_mat")]
+    tf_stub = types.SimpleNamespace(SparseTensor=lambda indices, values, dense_shape: (indices, values, dense_shape))
+    ns = {"np": np, "math": math, "tf": tf_stub}
+    exec(compile(ast.Module(body=keep, type_ignores=[]), RDGCN_REF_FILE, "exec"), ns)
+    return ns
+
+
+def rdgcn_forward(P, M, head_avg, tail_avg, dual_A, tri, alpha, beta, dtype=torch.float64, slope=0.2):
+    """Layer.build (rdgcn.py:317-338) with torch.sparse / scatter ops.  P: dict of float64 tensors named as in
+    openea_b200.approaches.rdgcn.RDGCNLayer; tri: [T, 3] int array (one r_mat entry per triple)."""
+    Ms, Hs, Ts = _sparse(M, dtype), _sparse(head_avg, dtype), _sparse(tail_avg, dtype)
+    A = torch.as_tensor(dual_A, dtype=dtype)
+    bias = -1e9 * (1.0 - (A > 0).to(dtype))
+    vec = lambda n: (P[n + ".w"][:, :1], P[n + ".b"][:, :1])
+    row = torch.as_tensor(tri[:, 0], dtype=torch.long); col = torch.as_tensor(tri[:, 2], dtype=torch.long)
+    rel = torch.as_tensor(tri[:, 1], dtype=torch.long)
+    E = M.shape[0]
+
+    def dual_input(x):
+        return torch.cat([torch.sparse.mm(Hs, x), torch.sparse.mm(Ts, x)], 1)
+
+    def att(fts, values, f1, f2):
+        (w1, b1), (w2, b2) = vec(f1), vec(f2)
+        logits = (fts @ w1 + b1) + (fts @ w2 + b2).t()
+        return torch.relu(torch.softmax(torch.nn.functional.leaky_relu(A * logits, slope) + bias, 1) @ values)
+
+    def sparse_att(x, dual_h, name):
+        w, b = vec(name)
+        logit = torch.nn.functional.leaky_relu((dual_h @ w + b).reshape(-1)[rel], slope)
+        mx = torch.full((E,), -1e30, dtype=dtype).scatter_reduce(0, row, logit, "amax")
+        ex = torch.exp(logit - mx[row])
+        den = torch.zeros(E, dtype=dtype).index_add(0, row, ex)
+        return torch.relu(torch.zeros(E, x.shape[1], dtype=dtype).index_add(0, row, (ex / den[row])[:, None] * x[col]))
+
+    def highway(l1, l2, name):
+        g = torch.sigmoid(l1 @ P[name + ".W"] + P[name + ".b"])
+        return g * l2 + (1 - g) * l1
+
+    x0 = P["X0"]
+    dx1 = dual_input(x0)
+    dh1 = att(dx1 @ P["self.W"], dx1, "self.f1", "self.f2")
+    x1 = x0 + alpha * sparse_att(x0, dh1, "sp1")
+    dx2 = dual_input(x1)
+    dh2 = att(dx2 @ P["dual.W"] + P["dual.b"], dh1, "dual.f1", "dual.f2")
+    x2 = x0 + beta * sparse_att(x1, dh2, "sp2")
+    g1 = highway(x2, torch.relu(torch.sparse.mm(Ms, x2 * P["diag1.w"])), "hw1")
+    return highway(g1, torch.relu(torch.sparse.mm(Ms, g1 * P["diag2.w"])), "hw2")

@@ -96,3 +96,32 @@ def test_alinet_builders_equal_reference_source():
     r_two = ref["generate_2hop_triples"](rk1, linked_ents=linked)
     # the 5 skipped patterns depend on tie order among equally frequent patterns: compare the path sets modulo that
     assert len(m_two ^ r_two) <= 0.05 * max(1, len(r_two)) or {(h, t) for h, _, t in m_two} == {(h, t) for h, _, t in r_two}
+
+
+@pytest.mark.skipif(orc_gnn.reference_rdgcn_builders() is None, reason="/root/reference not present on this box")
+def test_rdgcn_builders_equal_reference_source():
+    """get_mat (degree quirk included) / rfunc / get_dual_input's Jaccard matrix against the reference's own source."""
+    import math
+    from openea_b200.approaches import rdgcn as mine
+    from openea_b200.synth import synth_id_arrays
+    ref = orc_gnn.reference_rdgcn_builders()
+    arr = synth_id_arrays("tiny", swapping=False)
+    triples = [tuple(x) for x in np.concatenate([arr["triples1"], arr["triples2"]]).tolist()]
+    E, R = arr["n_ent"], arr["n_rel"]
+    pos, degree = ref["get_mat"](triples, E)
+    M = mine.get_sparse_matrix(triples, E).todok()
+    assert len(M) == len(pos)
+    for (fir, sec), v in list(pos.items())[::37]:
+        assert M[sec, fir] == pytest.approx(v / math.sqrt(degree[fir]) / math.sqrt(degree[sec]), rel=1e-12)
+    _, mdeg = mine.get_mat(triples, E)
+    assert mdeg.tolist() == list(degree)
+    head, tail, head_r, tail_r, r_mat = ref["rfunc"](triples, E, R)
+    mh, mt, tri = mine.rfunc(triples, E, R)
+    np.testing.assert_array_equal(mh.toarray(), head_r.T)
+    np.testing.assert_array_equal(mt.toarray(), tail_r.T)
+    assert sorted(map(tuple, np.stack([tri[:, 0], tri[:, 2], tri[:, 1]], 1).tolist())) == \
+        sorted((i[0], i[1], v) for i, v in zip(r_mat[0], r_mat[1]))
+    dual = mine.dual_adjacency(mh, mt)
+    for i, j in ((0, 0), (0, 1), (3, 7), (R - 1, 2)):
+        want = len(head[i] & head[j]) / len(head[i] | head[j]) + len(tail[i] & tail[j]) / len(tail[i] | tail[j])
+        assert dual[i, j] == pytest.approx(want, rel=1e-6)
