@@ -214,12 +214,22 @@ int oea_mapping_fwd_bwd(const float* e1, const float* e2, int32_t n, int32_t dim
  * oea_rows_normalize).  L1 = 'manhattan' (1 − cityblock), L2 = 'euclidean' (1 − ‖a−b‖₂). */
 enum { OEA_METRIC_INNER = 0, OEA_METRIC_L1 = 1, OEA_METRIC_L2 = 2 };
 
-/* E1 [n1, pitch1], E2 [n2, pitch2]: row-major fp32, pitch % 4 == 0, columns >= dim are ZERO. */
+/* E1 [n1, pitch1], E2 [n2, pitch2]: row-major fp32, pitch % 4 == 0, columns >= dim are ZERO.
+ * e1_t / e2_t: k-major copies of the operands made by oea_sim_transpose (ld*_t = oea_sim_transpose_ld(n)); the
+ * 128×128 tile kernel streams them with 16-byte cp.async in a 3-stage pipeline. */
 typedef struct oea_sim_cfg {
     int32_t metric;
     int32_t n1, n2, dim;
     int32_t pitch1, pitch2;
+    const float* e1_t;
+    const float* e2_t;
+    int64_t ld1_t, ld2_t;
 } oea_sim_cfg;
+
+/* k-major, zero-padded copy of an operand: out [ceil16(pitch), oea_sim_transpose_ld(n)], out[k][r] = in[r][k]. */
+int64_t oea_sim_transpose_ld(int32_t n);
+size_t  oea_sim_transpose_bytes(int32_t n, int32_t pitch);
+int     oea_sim_transpose(const float* in, int32_t pitch, int32_t n, float* out, void* stream);
 
 /* Per-row k best columns of S (or of the CSLS matrix 2·S − row_off[i] − col_off[j] when the two
  * offset vectors are given; similarity.py:57-77), k <= 32, without materialising S.
@@ -246,6 +256,17 @@ int oea_sim_rank(const oea_sim_cfg* cfg, const float* e1, const float* e2,
  * approaches/bootea.py:214-219).  Also the first stage of the large-k neighbour search. */
 int oea_sim_matrix(const oea_sim_cfg* cfg, const float* e1, const float* e2,
                    const float* row_off, const float* col_off, float* out, int64_t ld_out, void* stream);
+
+/* CSLS on a MATERIALISED similarity matrix (from oea_sim_matrix): used when n1·n2·4 B fits in memory, so the
+ * contraction runs once instead of three times (similarity.py:57-83, alignment.py:146-168).
+ *   oea_matrix_topk_mean: mean of the k (<= 32) largest entries of every row (by_column = 0) or every column
+ *                         (by_column = 1) of mat [n_rows, ld] → out_mean [n_rows] / [n_cols]  (= calculate_nearest_k);
+ *   oea_matrix_rank     : per row arg-max and 0-based rank of column gold[i] of 2·S − row_off[i] − col_off[j]
+ *                         (offsets NULL → of S itself); ties: lower column first. */
+int oea_matrix_topk_mean(const float* mat, int64_t ld, int32_t n_rows, int32_t n_cols, int32_t k,
+                         int32_t by_column, float* out_mean, void* stream);
+int oea_matrix_rank(const float* mat, int64_t ld, int32_t n_rows, int32_t n_cols, const float* row_off,
+                    const float* col_off, const int32_t* gold, int32_t* out_top1, int32_t* out_rank, void* stream);
 
 /* sklearn.preprocessing.normalize (similarity.py:30-32): rows scaled to unit L2 norm, zero rows kept;
  * writes zero padding up to out_pitch. */

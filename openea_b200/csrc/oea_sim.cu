@@ -19,6 +19,15 @@ enum { EPI_TOPK = 0, EPI_RANK = 1, EPI_STORE = 2 };
 
 constexpr int TM = 128, TN = 128, BK = 16;
 constexpr int SIM_THREADS = 256;
+constexpr int STAGES = 3;          // cp.async pipeline depth of the operand tiles
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N)); }
 constexpr int KMAX = 32;  // per-row top-k list lives in one warp's lanes
 constexpr int TS_LD = TN + 4;  // tile staging row stride: 16-B aligned rows, conflict-free 128-bit stores
 
@@ -41,6 +50,8 @@ __device__ __forceinline__ float csls_value(float s, float r, float c) { return 
 
 struct SimParams {
     const float* e1; const float* e2;
+    const float* e1t; const float* e2t;    // k-major copies [kpad, ldt] (zero padded): tiles stream in with 16-B cp.async
+    long long ld1t, ld2t;
     int n1, n2, pitch1, pitch2, kdim;      // kdim = min(pitch1, pitch2) rounded: contraction length
     const float* row_off; const float* col_off;  // CSLS r_i / c_j or nullptr
     int col_tiles_per_split;
@@ -56,9 +67,9 @@ template <int METRIC, int EPI>
 __global__ void __launch_bounds__(SIM_THREADS, 2)
 k_sim_tile(SimParams P) {
     extern __shared__ __align__(16) float smem[];
-    float (*As)[BK][TM] = reinterpret_cast<float (*)[BK][TM]>(smem);                 // [2][BK][TM]
-    float (*Bs)[BK][TN] = reinterpret_cast<float (*)[BK][TN]>(smem + 2 * BK * TM);   // [2][BK][TN]
-    float* Ts = smem + 2 * BK * TM + 2 * BK * TN;                                    // [TM][TS_LD] (TOPK only)
+    float (*As)[BK][TM] = reinterpret_cast<float (*)[BK][TM]>(smem);                      // [STAGES][BK][TM]
+    float (*Bs)[BK][TN] = reinterpret_cast<float (*)[BK][TN]>(smem + STAGES * BK * TM);   // [STAGES][BK][TN]
+    float* Ts = smem + STAGES * BK * TM + STAGES * BK * TN;                                    // [TM][TS_LD] (TOPK only)
     float* Lv = Ts + (TM / 2) * TS_LD;                                            // [TM][kcap]
     int* Li = reinterpret_cast<int*>(Lv + TM * P.kcap);                              // [TM][kcap]
 
@@ -69,11 +80,8 @@ k_sim_tile(SimParams P) {
     const int ct0 = blockIdx.y * P.col_tiles_per_split;
     const int ct1 = min(n_col_tiles, ct0 + P.col_tiles_per_split);
 
-    // loader mapping: thread → (row = tid % 128, k-half = tid / 128)
-    const int lrow = tid & 127, lhalf = tid >> 7;
-    const int arow = row0 + lrow;
-    const bool arow_ok = arow < P.n1;
-    const float* aptr = P.e1 + (size_t)(arow_ok ? arow : 0) * P.pitch1 + lhalf * 8;
+    const float* At = P.e1t + row0;      // this row block's columns of the k-major copy
+    const int ld_kk = tid >> 5, ld_c4 = (tid & 31) * 4;   // loader mapping: 2 × (k = tid/32 + 8i, 4 consecutive rows)
 
     if (EPI == EPI_TOPK) {
         for (int i = tid; i < TM * P.kcap; i += SIM_THREADS) { Lv[i] = -FLT_MAX; Li[i] = -1; }
@@ -86,43 +94,33 @@ k_sim_tile(SimParams P) {
 
     for (int ct = ct0; ct < ct1; ++ct) {
         const int col0 = ct * TN;
-        const int brow = col0 + lrow;
-        const bool brow_ok = brow < P.n2;
-        const float* bptr = P.e2 + (size_t)(brow_ok ? brow : 0) * P.pitch2 + lhalf * 8;
-
+        const float* Bt = P.e2t + col0;
         float acc[8][8];
 #pragma unroll
         for (int i = 0; i < 8; ++i)
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 
-        float4 ra[2], rb[2];
-        auto gload = [&](int kc) {
-            const int kbase = kc * BK + lhalf * 8;
+        auto issue = [&](int kc, int stage) {
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int kk = kbase + 4 * q;
-                ra[q] = (arow_ok && kk < P.kdim) ? ldg4(aptr + kc * BK + 4 * q) : f4(0.f);
-                rb[q] = (brow_ok && kk < P.kdim) ? ldg4(bptr + kc * BK + 4 * q) : f4(0.f);
+            for (int i = 0; i < 2; ++i) {
+                const int kk = ld_kk + 8 * i;
+                cp_async16(&As[stage][kk][ld_c4], At + (size_t)(kc * BK + kk) * P.ld1t + ld_c4);
+                cp_async16(&Bs[stage][kk][ld_c4], Bt + (size_t)(kc * BK + kk) * P.ld2t + ld_c4);
             }
         };
-        auto sstore = [&](int buf) {
+        __syncthreads();   // previous tile's compute / epilogue readers are done with every stage
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int kk = lhalf * 8 + 4 * q;
-                As[buf][kk + 0][lrow] = ra[q].x; As[buf][kk + 1][lrow] = ra[q].y;
-                As[buf][kk + 2][lrow] = ra[q].z; As[buf][kk + 3][lrow] = ra[q].w;
-                Bs[buf][kk + 0][lrow] = rb[q].x; Bs[buf][kk + 1][lrow] = rb[q].y;
-                Bs[buf][kk + 2][lrow] = rb[q].z; Bs[buf][kk + 3][lrow] = rb[q].w;
-            }
-        };
-        gload(0);
-        __syncthreads();   // previous tile's epilogue / smem readers are done
-        sstore(0);
-        __syncthreads();
+        for (int st = 0; st < STAGES - 1; ++st) {
+            if (st < nk) issue(st, st);
+            cp_async_commit();
+        }
         for (int kc = 0; kc < nk; ++kc) {
-            const int buf = kc & 1;
-            if (kc + 1 < nk) gload(kc + 1);
+            cp_async_wait<STAGES - 2>();   // chunk kc has landed (for this thread) …
+            __syncthreads();               // … for every thread; and everyone finished chunk kc−1 (its stage is refilled next)
+            if (kc + STAGES - 1 < nk) issue(kc + STAGES - 1, (kc + STAGES - 1) % STAGES);
+            cp_async_commit();
+            const int buf = kc % STAGES;
             const int kk_end = min(BK, P.kdim - kc * BK);   // kdim % 4 == 0: the tail chunk runs 4, 8 or 12 steps
 #pragma unroll 4
             for (int kk = 0; kk < kk_end; ++kk) {
@@ -136,10 +134,6 @@ k_sim_tile(SimParams P) {
                 for (int i = 0; i < 8; ++i)
 #pragma unroll
                     for (int j = 0; j < 8; ++j) acc[i][j] = sim_accum<METRIC>(a[i], b[j], acc[i][j]);
-            }
-            if (kc + 1 < nk) {
-                sstore(buf ^ 1);
-                __syncthreads();
             }
         }
 
@@ -358,8 +352,28 @@ k_rows_normalize(const float* __restrict__ in, int in_pitch, int n, int dim, flo
     for (int c = lane; c < out_pitch; c += 32) dst[c] = c < dim ? src[c] * inv : 0.f;
 }
 
+// k-major copy of an operand: out[k][r] = in[r][k] for r < n, k < pitch; zero elsewhere ([kpad, ld] with
+// kpad = ceil16(pitch), ld = ceil128(n)), so the tile loader needs no bounds checks.  32×32 smem tiles.
+__global__ void __launch_bounds__(256)
+k_sim_transpose(const float* __restrict__ in, int pitch, int n, float* __restrict__ out, long long ld, int kpad) {
+    __shared__ float t[32][33];
+    const int r0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 8 rows of 32 threads
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = r0 + ty + 8 * i, k = k0 + tx;
+        t[ty + 8 * i][tx] = (r < n && k < pitch) ? __ldg(in + (size_t)r * pitch + k) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int k = k0 + ty + 8 * i, r = r0 + tx;
+        if (k < kpad && r < ld) out[(size_t)k * ld + r] = t[tx][ty + 8 * i];
+    }
+}
+
 static size_t sim_smem_bytes(int epi, int kcap) {
-    size_t f = 2 * BK * TM + 2 * BK * TN;
+    size_t f = STAGES * BK * TM + STAGES * BK * TN;
     if (epi == EPI_TOPK) f += (TM / 2) * TS_LD + 2 * TM * kcap;
     return f * sizeof(float);
 }
@@ -370,6 +384,10 @@ static int check_sim(const oea_sim_cfg* c, const float* e1, const float* e2) {
     if (c->pitch1 < c->dim || c->pitch2 < c->dim || (c->pitch1 & 3) || (c->pitch2 & 3)) return OEA_ERR_DIM;
     if (!aligned16(e1) || !aligned16(e2)) return OEA_ERR_ALIGN;
     if (c->metric < OEA_METRIC_INNER || c->metric > OEA_METRIC_L2) return OEA_ERR_KIND;
+    if (!c->e1_t || !c->e2_t) return OEA_ERR_NULL;                       // k-major copies from oea_sim_transpose
+    const int64_t np1 = ((int64_t)c->n1 + TM - 1) / TM * TM, np2 = ((int64_t)c->n2 + TN - 1) / TN * TN;
+    if (c->ld1_t < np1 || c->ld2_t < np2 || (c->ld1_t & 3) || (c->ld2_t & 3)) return OEA_ERR_SHAPE;
+    if (!aligned16(c->e1_t) || !aligned16(c->e2_t)) return OEA_ERR_ALIGN;
     return OEA_OK;
 }
 
@@ -401,18 +419,28 @@ static int launch_sim(const oea_sim_cfg* c, SimParams& P, int splits, cudaStream
     return OEA_OK;
 }
 
+// Column splits per row block: the split count that wastes the least of the last wave.  A CTA's time is
+// proportional to its number of column tiles, so with `slots` resident CTAs the kernel takes
+// ceil(row_blocks·splits / slots) · ceil(col_tiles / splits) tile-times; 1.12 waves were measured to cost 2.
 static int pick_splits(int n1, int n2) {
     const int row_blocks = (n1 + TM - 1) / TM, col_tiles = (n2 + TN - 1) / TN;
-    int splits = (2 * sm_count() + row_blocks - 1) / row_blocks;   // aim at >= 2 CTAs per SM
-    if (splits > col_tiles) splits = col_tiles;
-    if (splits < 1) splits = 1;
-    if (splits > 64) splits = 64;
-    return splits;
+    const long long slots = 2LL * sm_count();              // 2 CTAs per SM (registers and shared memory both allow 2)
+    int best = 1;
+    long long best_cost = -1;
+    const int max_splits = col_tiles < 64 ? col_tiles : 64;
+    for (int sp = 1; sp <= max_splits; ++sp) {
+        const long long per = (col_tiles + sp - 1) / sp;
+        const long long eff_splits = (col_tiles + per - 1) / per;
+        const long long waves = (row_blocks * eff_splits + slots - 1) / slots;
+        const long long cost = waves * per * 64 + eff_splits;   // tile-times first, then fewer partial lists to merge
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = sp; }
+    }
+    return best;
 }
 
 static void fill_common(SimParams& P, const oea_sim_cfg* c, const float* e1, const float* e2,
                         const float* row_off, const float* col_off, int splits) {
-    P.e1 = e1; P.e2 = e2; P.n1 = c->n1; P.n2 = c->n2; P.pitch1 = c->pitch1; P.pitch2 = c->pitch2;
+    P.e1 = e1; P.e2 = e2; P.e1t = c->e1_t; P.e2t = c->e2_t; P.ld1t = c->ld1_t; P.ld2t = c->ld2_t; P.n1 = c->n1; P.n2 = c->n2; P.pitch1 = c->pitch1; P.pitch2 = c->pitch2;
     P.kdim = c->pitch1 < c->pitch2 ? c->pitch1 : c->pitch2;   // padding columns are zero on both sides
     P.row_off = row_off; P.col_off = col_off;
     const int col_tiles = (c->n2 + TN - 1) / TN;
@@ -423,6 +451,22 @@ static void fill_common(SimParams& P, const oea_sim_cfg* c, const float* e1, con
 }  // namespace oea
 
 using namespace oea;
+
+extern "C" int64_t oea_sim_transpose_ld(int32_t n) { return n > 0 ? ((int64_t)n + TM - 1) / TM * TM : 0; }
+extern "C" size_t oea_sim_transpose_bytes(int32_t n, int32_t pitch) {
+    if (n <= 0 || pitch <= 0) return 0;
+    return (size_t)((pitch + BK - 1) / BK * BK) * (size_t)oea_sim_transpose_ld(n) * sizeof(float);
+}
+extern "C" int oea_sim_transpose(const float* in, int32_t pitch, int32_t n, float* out, void* stream) {
+    if (!in || !out) return OEA_ERR_NULL;
+    if (n <= 0 || pitch <= 0 || (pitch & 3)) return OEA_ERR_DIM;
+    const long long ld = oea_sim_transpose_ld(n);
+    const int kpad = (pitch + BK - 1) / BK * BK;
+    const dim3 grid((unsigned)((ld + 31) / 32), (unsigned)((kpad + 31) / 32));
+    k_sim_transpose<<<grid, 256, 0, (cudaStream_t)stream>>>(in, pitch, n, out, ld, kpad);
+    OEA_LAUNCH_CHECK();
+    return OEA_OK;
+}
 
 extern "C" size_t oea_sim_topk_workspace_bytes(const oea_sim_cfg* c, int32_t k) {
     if (!c || k < 1 || k > KMAX) return 0;
@@ -614,6 +658,147 @@ extern "C" int oea_rows_select_topk(const float* mat, int64_t ld, int32_t n_rows
     if (n_rows == 0) return OEA_OK;
     const int grid = n_rows < 4 * sm_count() ? n_rows : 4 * sm_count();
     k_rows_select<<<grid, SEL_THREADS, 0, (cudaStream_t)stream>>>(mat, ld, n_rows, n_cols, k, col_ids, out_idx);
+    OEA_LAUNCH_CHECK();
+    return OEA_OK;
+}
+
+// ================================================================================================
+// CSLS evaluation on a MATERIALISED similarity matrix (one FP32 tile pass with the store epilogue, then three
+// HBM-bound streaming passes) — used when n1·n2·4 B fits the budget: 1 contraction pass instead of 3.
+//   k_mat_row_topk_mean : r_i  = mean of the k largest of row i            (warp per row, 128-bit streaming loads)
+//   k_mat_col_topk_mean : c_j  = mean of the k largest of column j         (CTA per 128-column strip, smem transpose)
+//   k_mat_rank          : arg-max and rank-of-gold of 2·S − r_i − c_j      (warp per row)
+// The per-row list logic (ballot + shuffle insertion into a lane-resident sorted list) is the one of the tile kernel.
+// ================================================================================================
+namespace oea {
+
+// insert candidate values (one per lane, `c`) into the lane-resident descending list `lv` (entries 0..k-1)
+__device__ __forceinline__ void list_insert_vals(float c, float& lv, float& tau, int k, int lane) {
+    unsigned pass = __ballot_sync(OEA_FULL, c > tau);
+    while (pass) {
+        const int src = __ffs(pass) - 1;
+        pass &= pass - 1;
+        const float cv = __shfl_sync(OEA_FULL, c, src);
+        if (!(cv > tau)) continue;
+        const int pos = __popc(__ballot_sync(OEA_FULL, lane < k && lv >= cv));
+        const float up = __shfl_up_sync(OEA_FULL, lv, 1);
+        if (lane > pos) lv = up; else if (lane == pos) lv = cv;
+        tau = __shfl_sync(OEA_FULL, lv, k - 1);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_mat_row_topk_mean(const float* __restrict__ mat, long long ld, int n_rows, int n_cols, int k, float* __restrict__ out_mean) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= n_rows) return;                       // whole warps exit together (8 rows per CTA, one per warp)
+    const float* src = mat + (size_t)row * ld;
+    float lv = -FLT_MAX, tau = -FLT_MAX;
+    const int n4 = n_cols >> 2;
+    for (int base = 0; base < n4; base += 32) {      // warp-uniform trip count: the list helpers use full-mask shuffles
+        const int q = base + lane;
+        const float4 v = q < n4 ? ldg4(src + 4 * q) : make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+        // the insertion path is rare once tau has risen; the order inside a row is irrelevant for the mean
+        if (__ballot_sync(OEA_FULL, v.x > tau || v.y > tau || v.z > tau || v.w > tau)) {
+            list_insert_vals(v.x, lv, tau, k, lane); list_insert_vals(v.y, lv, tau, k, lane);
+            list_insert_vals(v.z, lv, tau, k, lane); list_insert_vals(v.w, lv, tau, k, lane);
+        }
+    }
+    {   // the last n_cols % 4 columns
+        const int j = n4 * 4 + lane;
+        list_insert_vals(j < n_cols ? __ldg(src + j) : -FLT_MAX, lv, tau, k, lane);
+    }
+    float s = lane < k ? lv : 0.f;
+    s = warp_sum(s);
+    if (lane == 0) out_mean[row] = s / (float)k;
+}
+
+constexpr int CT_COLS = 128, CT_ROWS = 64, CT_LD = CT_ROWS + 1;
+
+__global__ void __launch_bounds__(256)
+k_mat_col_topk_mean(const float* __restrict__ mat, long long ld, int n_rows, int n_cols, int k, float* __restrict__ out_mean) {
+    __shared__ float T[CT_COLS * CT_LD];     // transposed tile: T[col][row]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int col0 = blockIdx.x * CT_COLS;
+    float lv[16], tau[16];                   // warp w owns columns w*16 .. w*16+15; lane l holds entry l of each list
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { lv[i] = -FLT_MAX; tau[i] = -FLT_MAX; }
+    for (int r0 = 0; r0 < n_rows; r0 += CT_ROWS) {
+        __syncthreads();
+        // load CT_ROWS × CT_COLS, coalesced along the row; thread → (row = tid / 128 + 2·i, col = tid % 128)
+#pragma unroll 4
+        for (int i = 0; i < CT_ROWS / 2; ++i) {
+            const int rr = (tid >> 7) + 2 * i, cc = tid & 127;
+            const int r = r0 + rr, c = col0 + cc;
+            T[cc * CT_LD + rr] = (r < n_rows && c < n_cols) ? __ldg(mat + (size_t)r * ld + c) : -FLT_MAX;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float* colp = T + (warp * 16 + i) * CT_LD;
+            list_insert_vals(colp[lane], lv[i], tau[i], k, lane);
+            list_insert_vals(colp[lane + 32], lv[i], tau[i], k, lane);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        float s = lane < k ? lv[i] : 0.f;
+        s = warp_sum(s);
+        const int c = col0 + warp * 16 + i;
+        if (lane == 0 && c < n_cols) out_mean[c] = s / (float)k;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_mat_rank(const float* __restrict__ mat, long long ld, int n_rows, int n_cols, const float* __restrict__ row_off,
+           const float* __restrict__ col_off, const int* __restrict__ gold, int* __restrict__ out_top1, int* __restrict__ out_rank) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const float* src = mat + (size_t)row * ld;
+    const bool csls = row_off != nullptr;
+    const float ro = csls ? __ldg(row_off + row) : 0.f;
+    const int g = __ldg(gold + row);
+    float gval = __ldg(src + g);
+    if (csls) gval = csls_value(gval, ro, __ldg(col_off + g));
+    int cnt = 0, besti = 0x7fffffff;
+    float bestv = -FLT_MAX;
+    for (int j = lane; j < n_cols; j += 32) {
+        float v = __ldg(src + j);
+        if (csls) v = csls_value(v, ro, __ldg(col_off + j));
+        cnt += (v > gval) || (v == gval && j < g);
+        if (v > bestv) { bestv = v; besti = j; }          // j ascends per lane: first maximum kept
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        cnt += __shfl_xor_sync(OEA_FULL, cnt, o);
+        const float ov = __shfl_xor_sync(OEA_FULL, bestv, o);
+        const int oi = __shfl_xor_sync(OEA_FULL, besti, o);
+        if (ov > bestv || (ov == bestv && oi < besti)) { bestv = ov; besti = oi; }
+    }
+    if (lane == 0) { out_rank[row] = cnt; out_top1[row] = besti; }
+}
+
+}  // namespace oea
+
+extern "C" int oea_matrix_topk_mean(const float* mat, int64_t ld, int32_t n_rows, int32_t n_cols, int32_t k,
+                                    int32_t by_column, float* out_mean, void* stream) {
+    if (!mat || !out_mean) return OEA_ERR_NULL;
+    if (n_rows <= 0 || n_cols <= 0 || ld < n_cols || (ld & 3) || !aligned16(mat)) return OEA_ERR_SHAPE;
+    if (k < 1 || k > KMAX || k > (by_column ? n_rows : n_cols)) return OEA_ERR_RANGE;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (by_column) k_mat_col_topk_mean<<<(n_cols + CT_COLS - 1) / CT_COLS, 256, 0, st>>>(mat, ld, n_rows, n_cols, k, out_mean);
+    else k_mat_row_topk_mean<<<(n_rows + 7) / 8, 256, 0, st>>>(mat, ld, n_rows, n_cols, k, out_mean);
+    OEA_LAUNCH_CHECK();
+    return OEA_OK;
+}
+
+extern "C" int oea_matrix_rank(const float* mat, int64_t ld, int32_t n_rows, int32_t n_cols, const float* row_off,
+                               const float* col_off, const int32_t* gold, int32_t* out_top1, int32_t* out_rank, void* stream) {
+    if (!mat || !gold || !out_top1 || !out_rank) return OEA_ERR_NULL;
+    if ((row_off == nullptr) != (col_off == nullptr)) return OEA_ERR_NULL;
+    if (n_rows <= 0 || n_cols <= 0 || ld < n_cols) return OEA_ERR_SHAPE;
+    k_mat_rank<<<(n_rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(mat, ld, n_rows, n_cols, row_off, col_off, gold, out_top1, out_rank);
     OEA_LAUNCH_CHECK();
     return OEA_OK;
 }

@@ -41,10 +41,32 @@ def to_device_rows(x, normalize=False):
     return out, d
 
 
-def _cfg(metric, e1, e2, d):
+def kmajor(t, tc=None):
+    """k-major zero-padded copy of prepared rows [n, pitch] (oea_sim_transpose) → (tensor, ld).  `tc` is a per-call
+    cache {id(tensor): result} so that the passes of one evaluation share the copies (never cached across calls:
+    the caller may change the rows in place)."""
+    if tc is not None and id(t) in tc:
+        return tc[id(t)][1:]
+    lib = L.load()
+    n, pitch = t.shape
+    ld = lib.oea_sim_transpose_ld(n)
+    out = torch.empty(lib.oea_sim_transpose_bytes(n, pitch) // 4, dtype=torch.float32, device=t.device)
+    L.check(lib.oea_sim_transpose(_ptr(t), pitch, n, _ptr(out), _stream_ptr()), "oea_sim_transpose")
+    if tc is not None:
+        tc[id(t)] = (t, out, ld)      # keeps `t` alive so the id stays unique for the duration of the call
+    return out, ld
+
+
+def _cfg(metric, e1, e2, d, tc=None):
     if metric not in _METRICS:
         raise ValueError("metric %r is not supported by the B200 engine (inner/cosine/euclidean/manhattan)" % (metric,))
-    return L.SimCfg(_METRICS[metric], e1.shape[0], e2.shape[0], d, e1.shape[1], e2.shape[1])
+    assert e1.is_contiguous() and e2.is_contiguous()
+    t1, ld1 = kmajor(e1, tc)
+    t2, ld2 = kmajor(e2, tc) if e2 is not e1 else (t1, ld1)
+    cfg = L.SimCfg(_METRICS[metric], e1.shape[0], e2.shape[0], d, e1.shape[1], e2.shape[1], t1.data_ptr(), t2.data_ptr(),
+                   ld1, ld2)
+    cfg._keep = (t1, t2)              # the k-major copies must outlive the (asynchronous) kernels using them
+    return cfg
 
 
 def _prep_pair(embed1, embed2, metric, normalize):
@@ -56,10 +78,10 @@ def _prep_pair(embed1, embed2, metric, normalize):
     return e1, e2, d
 
 
-def topk(e1, e2, d, metric, k, row_off=None, col_off=None, want=("val", "idx", "mean")):
+def topk(e1, e2, d, metric, k, row_off=None, col_off=None, want=("val", "idx", "mean"), tc=None):
     """Per-row top-k of S (or CSLS S' when offsets are given) of prepared device rows → dict of tensors."""
     lib = L.load()
-    cfg = _cfg(metric, e1, e2, d)
+    cfg = _cfg(metric, e1, e2, d, tc)
     n1 = e1.shape[0]
     dev = e1.device
     ws_bytes = lib.oea_sim_topk_workspace_bytes(C.byref(cfg), k)
@@ -74,17 +96,18 @@ def topk(e1, e2, d, metric, k, row_off=None, col_off=None, want=("val", "idx", "
     return out
 
 
-def csls_offsets(e1, e2, d, metric, k):
+def csls_offsets(e1, e2, d, metric, k, tc=None):
     """r_i = mean of the k nearest of row i, c_j = mean of the k nearest of column j (similarity.py:73-83)."""
-    r = topk(e1, e2, d, metric, k, want=("mean",))["mean"]
-    c = topk(e2, e1, d, metric, k, want=("mean",))["mean"]
+    tc = {} if tc is None else tc
+    r = topk(e1, e2, d, metric, k, want=("mean",), tc=tc)["mean"]
+    c = topk(e2, e1, d, metric, k, want=("mean",), tc=tc)["mean"]
     return r, c
 
 
-def rank(e1, e2, d, metric, gold, row_off=None, col_off=None):
+def rank(e1, e2, d, metric, gold, row_off=None, col_off=None, tc=None):
     """(argmax column, 0-based rank of gold[i]) per row → two int32 CUDA tensors."""
     lib = L.load()
-    cfg = _cfg(metric, e1, e2, d)
+    cfg = _cfg(metric, e1, e2, d, tc)
     n1, dev = e1.shape[0], e1.device
     gold_t = torch.as_tensor(gold, dtype=torch.int32, device=dev).contiguous()
     ws_bytes = lib.oea_sim_rank_workspace_bytes(C.byref(cfg))
@@ -96,9 +119,9 @@ def rank(e1, e2, d, metric, gold, row_off=None, col_off=None):
     return top1, rk
 
 
-def sim_matrix(e1, e2, d, metric, row_off=None, col_off=None, out=None):
+def sim_matrix(e1, e2, d, metric, row_off=None, col_off=None, out=None, tc=None):
     lib = L.load()
-    cfg = _cfg(metric, e1, e2, d)
+    cfg = _cfg(metric, e1, e2, d, tc)
     if out is None:
         out = torch.empty(e1.shape[0], e2.shape[0], dtype=torch.float32, device=e1.device)
     L.check(lib.oea_sim_matrix(C.byref(cfg), _ptr(e1), _ptr(e2), _ptr(row_off), _ptr(col_off), _ptr(out),
@@ -110,21 +133,55 @@ def sim(embed1, embed2, metric="inner", normalize=False, csls_k=0):
     """Drop-in for modules/finding/similarity.py:11 `sim` → float32 CUDA tensor [n1, n2]."""
     e1, e2, d = _prep_pair(embed1, embed2, metric, normalize)
     r = c = None
+    tc = {}
     if csls_k > 0:
-        r, c = csls_offsets(e1, e2, d, metric, csls_k)
-    return sim_matrix(e1, e2, d, metric, r, c)
+        r, c = csls_offsets(e1, e2, d, metric, csls_k, tc)
+    return sim_matrix(e1, e2, d, metric, r, c, tc=tc)
 
 
-def eval_alignment(embed1, embed2, top_k, metric, normalize, csls_k, gold=None):
-    """The numeric core of greedy_alignment: returns (top1 idx tensor, rank tensor, hits list, mr, mrr)."""
+MATERIALIZE_MAX_BYTES = 48 << 30   # CSLS runs on a stored n1×n2 matrix (1 contraction pass) below this size
+
+
+def _eval_materialized(e1, e2, d, metric, csls_k, gold):
+    """CSLS evaluation with ONE contraction pass: S stored once (tile kernel, store epilogue), then three
+    HBM-bound streaming kernels (row k-means, column k-means, rank)."""
+    lib = L.load()
+    n1, n2 = e1.shape[0], e2.shape[0]
+    ld = (n2 + 3) // 4 * 4
+    s = torch.empty(n1, ld, dtype=torch.float32, device=e1.device)
+    cfg = _cfg(metric, e1, e2, d)
+    st = _stream_ptr()
+    L.check(lib.oea_sim_matrix(C.byref(cfg), _ptr(e1), _ptr(e2), None, None, _ptr(s), ld, st), "oea_sim_matrix")
+    r = torch.empty(n1, dtype=torch.float32, device=e1.device)
+    c = torch.empty(n2, dtype=torch.float32, device=e1.device)
+    L.check(lib.oea_matrix_topk_mean(_ptr(s), ld, n1, n2, csls_k, 0, _ptr(r), st), "oea_matrix_topk_mean")
+    L.check(lib.oea_matrix_topk_mean(_ptr(s), ld, n1, n2, csls_k, 1, _ptr(c), st), "oea_matrix_topk_mean")
+    top1 = torch.empty(n1, dtype=torch.int32, device=e1.device)
+    rk = torch.empty(n1, dtype=torch.int32, device=e1.device)
+    L.check(lib.oea_matrix_rank(_ptr(s), ld, n1, n2, _ptr(r), _ptr(c), _ptr(gold), _ptr(top1), _ptr(rk), st),
+            "oea_matrix_rank")
+    return top1, rk
+
+
+def eval_alignment(embed1, embed2, top_k, metric, normalize, csls_k, gold=None, materialize=None):
+    """The numeric core of greedy_alignment: returns (top1 idx tensor, rank tensor, hits list, mr, mrr).
+    With CSLS the similarity matrix is stored once when it fits MATERIALIZE_MAX_BYTES (1 contraction pass + 3
+    streaming passes); otherwise, and without CSLS, nothing is materialised (tile kernel with fused epilogues)."""
     e1, e2, d = _prep_pair(embed1, embed2, metric, normalize)
     n1 = e1.shape[0]
-    r = c = None
-    if csls_k > 0:
-        r, c = csls_offsets(e1, e2, d, metric, csls_k)
     if gold is None:
         gold = torch.arange(n1, dtype=torch.int32, device=e1.device)   # alignment.py:153: gold of row i is i
-    top1, rk = rank(e1, e2, d, metric, gold, r, c)
+    gold = torch.as_tensor(gold, dtype=torch.int32, device=e1.device).contiguous()
+    if materialize is None:
+        materialize = csls_k > 0 and 4 * n1 * e2.shape[0] <= MATERIALIZE_MAX_BYTES and csls_k <= min(n1, e2.shape[0])
+    if materialize and csls_k > 0:
+        top1, rk = _eval_materialized(e1, e2, d, metric, csls_k, gold)
+    else:
+        r = c = None
+        tc = {}
+        if csls_k > 0:
+            r, c = csls_offsets(e1, e2, d, metric, csls_k, tc)
+        top1, rk = rank(e1, e2, d, metric, gold, r, c, tc=tc)
     rk64 = rk.to(torch.float64)
     hits = [round(float((rk < k).sum().item()) / n1 * 100, 3) for k in top_k]
     mr = float((rk64 + 1).sum().item() / n1)
@@ -170,10 +227,11 @@ def find_neighbours_device(embeds, entity_list, k, row_block=8192):
     rb = min(n, row_block)
     ld = (n + 3) // 4 * 4
     buf = torch.empty(rb, ld, dtype=torch.float32, device=dev)
+    tc = {}
     for r0 in range(0, n, rb):
         r1 = min(n, r0 + rb)
         sub = e[r0:r1]
-        cfg = L.SimCfg(L.METRIC_INNER, r1 - r0, n, d, e.shape[1], e.shape[1])
+        cfg = _cfg("inner", sub, e, d, tc)
         L.check(lib.oea_sim_matrix(C.byref(cfg), _ptr(sub), _ptr(e), None, None, _ptr(buf), ld, _stream_ptr()),
                 "oea_sim_matrix")
         L.check(lib.oea_rows_select_topk(_ptr(buf), ld, r1 - r0, n, k, _ptr(ids), _ptr(out[r0:r1]), _stream_ptr()),
@@ -204,8 +262,9 @@ def eval_alignment_sharded(embed1, embed2, top_k, metric, normalize, csls_k):
     e1 = e1_all[lo:hi].contiguous()
     r = c = None
     if csls_k > 0:
-        r = topk(e1, e2, d, metric, csls_k, want=("mean",))["mean"]             # local rows: exact
-        part = topk(e2, e1, d, metric, min(csls_k, hi - lo), want=("val",))["val"]   # columns over MY rows
+        tc = {}
+        r = topk(e1, e2, d, metric, csls_k, want=("mean",), tc=tc)["mean"]             # local rows: exact
+        part = topk(e2, e1, d, metric, min(csls_k, hi - lo), want=("val",), tc=tc)["val"]   # columns over MY rows
         if part.shape[1] < csls_k:   # fewer local rows than k: pad so the merge still sees k slots per rank
             pad = torch.full((part.shape[0], csls_k - part.shape[1]), -3.0e38, device=part.device)
             part = torch.cat([part, pad], 1)

@@ -51,7 +51,8 @@ class SampleCfg(C.Structure):
 
 class SimCfg(C.Structure):
     _fields_ = [("metric", C.c_int32), ("n1", C.c_int32), ("n2", C.c_int32), ("dim", C.c_int32),
-                ("pitch1", C.c_int32), ("pitch2", C.c_int32)]
+                ("pitch1", C.c_int32), ("pitch2", C.c_int32), ("e1_t", C.c_void_p), ("e2_t", C.c_void_p),
+                ("ld1_t", C.c_int64), ("ld2_t", C.c_int64)]
 
 
 class SpmmHubs(C.Structure):
@@ -81,11 +82,16 @@ SIGNATURES = {
     "oea_triple_step_fed_host": (C.c_int, [_TP, _TP, _P, _I, _P, _I, C.POINTER(LossCfg), C.POINTER(OptCfg),
                                            _P, _P, _P, C.POINTER(C.c_float), _P]),
     "oea_table_lookup": (C.c_int, [_TP, _P, _I, _P, _I, _P]),
+    "oea_sim_transpose_ld": (C.c_int64, [_I]),
+    "oea_sim_transpose_bytes": (C.c_size_t, [_I, _I]),
+    "oea_sim_transpose": (C.c_int, [_P, _I, _I, _P, _P]),
     "oea_sim_topk_workspace_bytes": (C.c_size_t, [C.POINTER(SimCfg), _I]),
     "oea_sim_topk": (C.c_int, [C.POINTER(SimCfg), _P, _P, _P, _P, _I, _P, _P, _P, _P, C.c_size_t, _P]),
     "oea_sim_rank_workspace_bytes": (C.c_size_t, [C.POINTER(SimCfg)]),
     "oea_sim_rank": (C.c_int, [C.POINTER(SimCfg), _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "oea_sim_matrix": (C.c_int, [C.POINTER(SimCfg), _P, _P, _P, _P, _P, _L, _P]),
+    "oea_matrix_topk_mean": (C.c_int, [_P, _L, _I, _I, _I, _I, _P, _P]),
+    "oea_matrix_rank": (C.c_int, [_P, _L, _I, _I, _P, _P, _P, _P, _P, _P]),
     "oea_rows_normalize": (C.c_int, [_P, _I, _I, _I, _P, _I, _P]),
     "oea_rows_select_topk": (C.c_int, [_P, _L, _I, _I, _I, _P, _P, _P]),
     "oea_table_scatter_grad": (C.c_int, [_TP, _P, _I, _P, _I, _P]),

@@ -178,7 +178,7 @@ def find_neighbours(frags, entity_list, sub_embed, embed, k):
     buf = torch.empty(n_sub, ld, dtype=torch.float32, device=sub.device)
     out = torch.empty(n_sub, k, dtype=torch.int32, device=sub.device)
     lib = L.load()
-    cfg = L.SimCfg(L.METRIC_INNER, n_sub, n, d, sub.shape[1], full.shape[1])
+    cfg = finding._cfg("inner", sub, full, d)
     L.check(lib.oea_sim_matrix(C.byref(cfg), _ptr(sub), _ptr(full), None, None, _ptr(buf), ld, _stream_ptr()), "oea_sim_matrix")
     L.check(lib.oea_rows_select_topk(_ptr(buf), ld, n_sub, n, k, _ptr(ids), _ptr(out), _stream_ptr()), "oea_rows_select_topk")
     host = out.cpu().numpy()

@@ -33,7 +33,9 @@ def test_sim_matrix_and_csls_vs_reference_golden(cuda_device, tag, metric, norm)
 @pytest.mark.parametrize("tag", ["a", "b"])
 @pytest.mark.parametrize("metric,norm", METRICS)
 @pytest.mark.parametrize("csls_k", [0, 10])
-def test_greedy_alignment_vs_reference_golden(cuda_device, capsys, tag, metric, norm, csls_k):
+def test_greedy_alignment_vs_reference_golden(cuda_device, capsys, monkeypatch, tag, metric, norm, csls_k):
+    if tag == "b":   # tag "a" runs the default (materialised CSLS); tag "b" forces the streaming strategy
+        monkeypatch.setattr(F(), "MATERIALIZE_MAX_BYTES", 0)
     e1, e2 = GOLD[tag + "_e1"], GOLD[tag + "_e2"]
     key = "%s_%s_%d_k%d" % (tag, metric, norm, csls_k)
     pairs, hits1, mr, mrr = F().greedy_alignment(e1, e2, [1, 5, 10, 50], 4, metric, bool(norm), csls_k, True)
@@ -48,13 +50,15 @@ def test_greedy_alignment_vs_reference_golden(cuda_device, capsys, tag, metric, 
 @pytest.mark.parametrize("n1,n2,d,metric,csls_k", [(2000, 2000, 100, "inner", 0), (2000, 2000, 100, "inner", 10),
                                                    (1500, 2300, 200, "manhattan", 10), (700, 3001, 75, "euclidean", 10),
                                                    (129, 127 + 128, 300, "inner", 10)])
-def test_rank_and_top1_vs_oracle_seeded(cuda_device, n1, n2, d, metric, csls_k):
+@pytest.mark.parametrize("materialize", [False, True])
+def test_rank_and_top1_vs_oracle_seeded(cuda_device, n1, n2, d, metric, csls_k, materialize):
     """identical (i, argmax) sets and Hits@k on seeded inputs; tie/near-tie disagreements reported."""
     rng = np.random.default_rng(n1 + n2 + d)
     e2 = rng.standard_normal((n2, d)).astype(np.float32)
     e1 = (e2[:n1] + 0.5 * rng.standard_normal((n1, d))).astype(np.float32)
     norm = metric == "inner"
-    top1, rk, hits, mr, mrr = F().eval_alignment(e1, e2, [1, 5, 10, 50], metric, norm, csls_k)
+    # both CSLS strategies: streaming (3 fused tile passes, nothing stored) and materialised (1 pass + 3 streaming reads)
+    top1, rk, hits, mr, mrr = F().eval_alignment(e1, e2, [1, 5, 10, 50], metric, norm, csls_k, materialize=materialize)
     s = orf.sim(e1, e2, metric, norm, csls_k)
     wtop1, wrank = orf.rank_rows(s)
     whits, wmr, wmrr = orf.metrics_from_ranks(wrank, [1, 5, 10, 50])
