@@ -308,6 +308,7 @@ def main():
         print(json.dumps(line))
         return 0
 
+    os.environ.setdefault("NCCL_DEBUG", "WARN")     # no version banner on stdout: the JSON line must stand alone
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
@@ -355,6 +356,9 @@ def main():
 
     for i in range(max(3, args.warmup)):
         one_step(i)
+    if sync is not None:      # the first collective of a shape pays NCCL's lazy channel set-up: keep that out of the timing
+        for _ in range(3):
+            sync.sync()
     torch.cuda.synchronize()
     n_pos_step = int(npos_dev.item())
     tr.read_loss()
