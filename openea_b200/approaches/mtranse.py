@@ -20,11 +20,10 @@ class MTransE(BasicModel):
         self._define_embed_graph()
         self._define_mapping_graph()
         # hyper-parameter guards of the reference (mtranse.py:31-37)
-        assert self.args.init == 'unit'
-        assert self.args.alignment_module == 'mapping'
-        assert self.args.optimizer == 'Adagrad'
-        assert self.args.eval_metric == 'inner'
-        assert self.args.ent_l2_norm is True
+        required = dict(init='unit', alignment_module='mapping', optimizer='Adagrad', eval_metric='inner',
+                        ent_l2_norm=True)
+        for key, want in required.items():
+            assert getattr(self.args, key) == want, "MTransE needs %s=%r" % (key, want)
         assert self.args.alpha > 1
 
     def _define_embed_graph(self):
@@ -37,15 +36,17 @@ class MTransE(BasicModel):
         self.launch_mapping_training_1epo(epoch, triple_steps)
 
     def run(self):
-        t = time.time()
-        triples_num = self.kgs.kg1.relation_triples_num + self.kgs.kg2.relation_triples_num
-        triple_steps = int(math.ceil(triples_num / self.args.batch_size))
-        steps_tasks = task_divide(list(range(triple_steps)), self.args.batch_threads_num)
-        for i in range(1, self.args.max_epoch + 1):
-            self.launch_training_1epo(i, triple_steps, steps_tasks, None, None, None)
-            if i >= self.args.start_valid and i % self.args.eval_freq == 0:
-                flag = self.valid(self.args.stop_metric)
-                self.flag1, self.flag2, self.early_stop = early_stop(self.flag1, self.flag2, flag)
-                if self.early_stop or i == self.args.max_epoch:
-                    break
-        print("Training ends. Total time = {:.3f} s.".format(time.time() - t))
+        started = time.time()
+        a = self.args
+        n_triples = self.kgs.kg1.relation_triples_num + self.kgs.kg2.relation_triples_num
+        triple_steps = int(math.ceil(n_triples / a.batch_size))
+        steps_tasks = task_divide(list(range(triple_steps)), a.batch_threads_num)
+        for epoch in range(1, a.max_epoch + 1):
+            self.launch_training_1epo(epoch, triple_steps, steps_tasks, None, None, None)
+            if epoch < a.start_valid or epoch % a.eval_freq:
+                continue
+            flag = self.valid(a.stop_metric)
+            self.flag1, self.flag2, self.early_stop = early_stop(self.flag1, self.flag2, flag)
+            if self.early_stop or epoch == a.max_epoch:
+                break
+        print("Training ends. Total time = {:.3f} s.".format(time.time() - started))
