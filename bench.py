@@ -334,7 +334,7 @@ def main():
     full_steps = max(1, spe - 1) if spe > 1 else 1   # full batches per local epoch (the ragged last step is skipped)
     n_syncs = [0]
 
-    def one_step(i, ev=None):
+    def one_step(i, ev=None, split=False):
         # weak scaling: every rank steps through ITS shard with the full per-GPU batch; at each local epoch
         # boundary the owners' seed-pair rows are all-gathered into every replica (the only collective)
         step = i % full_steps
@@ -344,11 +344,15 @@ def main():
         if sync is not None and step == 0 and i > 0:
             sync.sync()
             n_syncs[0] += 1
-        if ev:
+        if ev and split:
             ev[3].record()          # kernel-only interval starts after the (rare) collective
             tr.score_sampled(kg1, kg2, tset, B, k, step, seed)
             ev[1].record()
             tr.apply()
+            ev[2].record()
+        elif ev:
+            ev[3].record()
+            tr.step_sampled(kg1, kg2, tset, B, k, step, seed)      # ONE cooperative launch: score + optimiser
             ev[2].record()
         else:
             # n_pos_out costs a small H2D copy in front of the kernel: asked for once, outside the timed region
@@ -379,7 +383,7 @@ def main():
         t_wall = time.perf_counter() - t_wall0
     if world > 1:
         dist.barrier()
-    score_ms = np.array([e[3].elapsed_time(e[1]) for e in evs])
+    kern_ms = np.array([e[3].elapsed_time(e[2]) for e in evs])
     step_ms = np.array([e[0].elapsed_time(e[2]) for e in evs])
     total_ms = float(step_ms.sum())
     if world > 1:
@@ -389,20 +393,43 @@ def main():
     loss_val = tr.read_loss()
     value = world * n_pos_step * K / (total_ms * 1e-3)
 
-    # ---- roofline of the dominant kernel (k_score_sampled) ---------------------------------------------------
+    # ---- roofline of the dominant kernel: k_step_sampled_oct = the whole step in one launch --------------------
+    # algorithmic bytes: scoring 24·d per scored triple + row optimiser 24·d per
+    # touched row (read g, x, acc; write x, acc, g := 0).  Touched rows are counted on the device, outside the timing.
     pk, pk_kind = peaks()
-    alg_bytes = 24.0 * d * (1 + k) * n_pos_step   # 24·d bytes per scored triple
-    score_med_ms = float(np.median(score_ms))
-    achieved = alg_bytes / (score_med_ms * 1e-3) / 1e9
+    touched = []
+    for i in range(4):
+        tr.score_sampled(kg1, kg2, tset, B, k, (args.warmup + i) % full_steps, 0xB007EA + rank)
+        touched.append(int((tr.ent.touched != 0).sum().item()) + int((tr.rel.touched != 0).sum().item()))
+        tr.apply()
+    n_touched = float(np.mean(touched))
+    score_bytes = 24.0 * d * (1 + k) * n_pos_step
+    alg_bytes = score_bytes + 24.0 * d * n_touched
+    kern_med_ms = float(np.median(kern_ms))
+    achieved = alg_bytes / (kern_med_ms * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic_%s.json" % args.workload)
     if os.path.exists(tp):
         with open(tp) as f:
-            traffic = json.load(f).get("k_score_sampled_dram_bytes_per_launch")
-    roofline = {"bound": "hbm", "kernel": "k_score_sampled", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+            traffic = json.load(f).get("k_step_sampled_oct_dram_bytes_per_launch")
+    # the same steps as two launches (score kernel, optimiser kernel) with an event between them: what the score
+    # kernel alone achieves against SURVEY §8d's scoring bytes (continuity with the r01 two-launch numbers)
+    evs2 = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
+    for i in range(K):
+        if not args.no_flush:
+            flush.fill_(float(i))
+        one_step(args.warmup + K + i, evs2[i], split=True)
+    torch.cuda.synchronize()
+    score_med_ms = float(np.median([e[3].elapsed_time(e[1]) for e in evs2]))
+    split_step_ms = float(np.mean([e[0].elapsed_time(e[2]) for e in evs2]))
+    roofline = {"bound": "hbm", "kernel": "k_step_sampled_oct", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "peak_kind": pk_kind + " (burst copy)",
-                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms_median": score_med_ms,
-                "kernel_share_of_step": float(score_ms.sum() / step_ms.sum())}
+                "algorithmic_bytes_per_launch": alg_bytes, "scoring_bytes": score_bytes, "touched_rows_per_step": n_touched,
+                "kernel_ms_median": kern_med_ms, "kernel_share_of_step": float(kern_ms.sum() / step_ms.sum()),
+                "score_kernel_alone": {"kernel": "k_score_sampled_oct", "ms_median": score_med_ms,
+                                       "achieved": score_bytes / (score_med_ms * 1e-3) / 1e9,
+                                       "frac": score_bytes / (score_med_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
+                                       "two_launch_ms_per_step": split_step_ms}}
 
     _phase("device-timed region done")
     # ---- e2e: the session.run(feed_dict) boundary with HOST index buffers -------------------------------------
@@ -497,7 +524,7 @@ def main():
                 "warmup": max(3, args.warmup), "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                 "scored_triples_per_s": value * (1 + k), "positives_per_step": n_pos_step,
-                "gpu_launches": 2 * K, "kernels": ["k_score_sampled", "k_rowopt_pair(ent+rel)"],
+                "gpu_launches": K, "kernels": ["k_step_sampled_oct (score + grid barrier + row optimiser, one cooperative launch)"],
                 "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_base, "clocks": clk, "csls": csls, "epoch_graph": graph_info,
                 "wall_s_timed_region": t_wall, "last_loss_sum": loss_val,
                 "collective": None if sync is None else {"kind": "ncclAllGather of seed-pair rows per local epoch",

@@ -25,14 +25,58 @@ __host__ __device__ __forceinline__ bool aligned16(const void* p) {
     return (reinterpret_cast<uintptr_t>(p) & 15u) == 0;
 }
 
+// ---- packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2 / FMUL2 — one issue slot for two IEEE fp32 results) ---------
+// Same rounding as the scalar forms (fma.rn / add.rn / mul.rn), so results are bit-identical; the kernels here are
+// issue-slot bound, not flop bound, which is why halving the instruction count of the vector maths pays.
+#ifndef OEA_F32X2
+#define OEA_F32X2 1
+#endif
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+#if OEA_F32X2
+    float2 d;
+    asm("{.reg .b64 ra, rb, rc, rd;\n mov.b64 ra, {%2,%3};\n mov.b64 rb, {%4,%5};\n mov.b64 rc, {%6,%7};\n"
+        " fma.rn.f32x2 rd, ra, rb, rc;\n mov.b64 {%0,%1}, rd;}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+#else
+    return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#endif
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+#if OEA_F32X2
+    float2 d;
+    asm("{.reg .b64 ra, rb, rd;\n mov.b64 ra, {%2,%3};\n mov.b64 rb, {%4,%5};\n add.rn.f32x2 rd, ra, rb;\n mov.b64 {%0,%1}, rd;}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+#else
+    return make_float2(a.x + b.x, a.y + b.y);
+#endif
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+#if OEA_F32X2
+    float2 d;
+    asm("{.reg .b64 ra, rb, rd;\n mov.b64 ra, {%2,%3};\n mov.b64 rb, {%4,%5};\n mul.rn.f32x2 rd, ra, rb;\n mov.b64 {%0,%1}, rd;}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+#else
+    return make_float2(a.x * b.x, a.y * b.y);
+#endif
+}
+__device__ __forceinline__ float2 lo2(float4 a) { return make_float2(a.x, a.y); }
+__device__ __forceinline__ float2 hi2(float4 a) { return make_float2(a.z, a.w); }
+__device__ __forceinline__ float4 cat4(float2 lo, float2 hi) { return make_float4(lo.x, lo.y, hi.x, hi.y); }
+
 // ---- float4 arithmetic -------------------------------------------------------------------------
 __device__ __forceinline__ float4 f4(float a) { return make_float4(a, a, a, a); }
-__device__ __forceinline__ float4 operator+(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
-__device__ __forceinline__ float4 operator-(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
-__device__ __forceinline__ float4 operator*(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+__device__ __forceinline__ float4 operator+(float4 a, float4 b) { return cat4(add2(lo2(a), lo2(b)), add2(hi2(a), hi2(b))); }
+// a − b as fma(b, −1, a): one rounding, identical to the subtraction
+__device__ __forceinline__ float4 operator-(float4 a, float4 b) { const float2 m = make_float2(-1.f, -1.f); return cat4(fma2(lo2(b), m, lo2(a)), fma2(hi2(b), m, hi2(a))); }
+__device__ __forceinline__ float4 operator*(float4 a, float s) { const float2 ss = make_float2(s, s); return cat4(mul2(lo2(a), ss), mul2(hi2(a), ss)); }
 __device__ __forceinline__ float4 neg(float4 a) { return make_float4(-a.x, -a.y, -a.z, -a.w); }
 __device__ __forceinline__ float dot4(float4 a, float4 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w))); }
-__device__ __forceinline__ float4 fma4(float4 a, float s, float4 c) { return make_float4(fmaf(a.x, s, c.x), fmaf(a.y, s, c.y), fmaf(a.z, s, c.z), fmaf(a.w, s, c.w)); }
+__device__ __forceinline__ float4 fma4(float4 a, float s, float4 c) { const float2 ss = make_float2(s, s); return cat4(fma2(lo2(a), ss, lo2(c)), fma2(hi2(a), ss, hi2(c))); }
+// acc.x + acc.y accumulates <a, b> over calls: two independent fma chains, summed by the caller at the end
+__device__ __forceinline__ void dot4_acc2(float2& acc, float4 a, float4 b) { acc = fma2(lo2(a), lo2(b), acc); acc = fma2(hi2(a), hi2(b), acc); }
 __device__ __forceinline__ float sgn(float x) { return (float)(x > 0.f) - (float)(x < 0.f); }  // TF sign(0) = 0
 __device__ __forceinline__ float4 sgn4(float4 a) { return make_float4(sgn(a.x), sgn(a.y), sgn(a.z), sgn(a.w)); }
 __device__ __forceinline__ float abs_sum4(float4 a) { return fabsf(a.x) + fabsf(a.y) + fabsf(a.z) + fabsf(a.w); }

@@ -130,10 +130,23 @@ k_sim_tile(SimParams P) {
                 const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][64 + tx * 4]);
                 const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
                 const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                if (METRIC == OEA_METRIC_INNER && OEA_F32X2) {
+                    // packed FFMA2: 32 issue slots per k-step instead of 64; per-(i,j) accumulation order unchanged
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
+                    for (int i = 0; i < 8; ++i) {
+                        const float2 aa = make_float2(a[i], a[i]);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[i][j] = sim_accum<METRIC>(a[i], b[j], acc[i][j]);
+                        for (int j = 0; j < 8; j += 2) {
+                            const float2 r = fma2(aa, make_float2(b[j], b[j + 1]), make_float2(acc[i][j], acc[i][j + 1]));
+                            acc[i][j] = r.x; acc[i][j + 1] = r.y;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) acc[i][j] = sim_accum<METRIC>(a[i], b[j], acc[i][j]);
+                }
             }
         }
 

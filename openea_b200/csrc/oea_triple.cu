@@ -14,6 +14,7 @@
 // vector reductions (red.global.add.v4.f32) into the L2-resident gradient table.
 #include <stdlib.h>
 #include "oea_common.cuh"
+#include <cooperative_groups.h>
 
 namespace oea {
 
@@ -120,14 +121,13 @@ __device__ __forceinline__ void loss_of(int loss_kind, bool is_neg, float s, con
 // Block-level loss accumulation: per-warp partials → one fp64 atomic per block.
 struct LossAcc {
     double* smem;  // [kWarpsPerBlock]
-    __device__ __forceinline__ void flush(float warp_loss, double* out) {
+    __device__ __forceinline__ void flush(float warp_loss, double* out, int n_warps_block = kWarpsPerBlock) {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         if (lane == 0) smem[warp] = (double)warp_loss;
         __syncthreads();
         if (threadIdx.x == 0) {
             double t = 0.0;
-#pragma unroll
-            for (int i = 0; i < kWarpsPerBlock; ++i) t += smem[i];
+            for (int i = 0; i < n_warps_block; ++i) t += smem[i];
             if (t != 0.0) atomicAdd(out, t);
         }
     }
@@ -302,11 +302,11 @@ __device__ __forceinline__ uint32_t rng_draw(uint32_t base, uint32_t a, uint32_t
 // (corrupted entity neg_e, neg_head = head corrupted).  Up to max_try rounds; a round flips ONE coin for all
 // still-missing negatives, draws distinct candidate positions for them, keeps the draws that are not known
 // triples; the last round keeps everything.
-__device__ __forceinline__ void warp_sample_negatives(const SampledParams& P, const oea_kg_view& kg, int p, int h, int r,
+__device__ __forceinline__ void warp_sample_negatives(const SampledParams& P, uint64_t seed, const oea_kg_view& kg, int p, int h, int r,
                                                       int t, int k, int lane, const float* __restrict__ ent_w, int ent_pitch,
                                                       int& neg_e, bool& neg_head) {
     bool need = lane < k;
-    const uint32_t base = rng_base(P.seed, (uint32_t)P.step, (uint32_t)p);
+    const uint32_t base = rng_base(seed, (uint32_t)P.step, (uint32_t)p);
     for (int tr = 0; tr < P.max_try; ++tr) {
         const unsigned missing = __ballot_sync(OEA_FULL, need);
         if (missing == 0u) break;
@@ -382,7 +382,7 @@ k_score_sampled(TableDev ent, TableDev rel, SampledParams P, oea_loss_cfg cfg,
         // ---- negative sampling (batch.py:89-119), lane j < k owns negative j ----
         int neg_e = 0;
         bool neg_head = false;
-        warp_sample_negatives(P, kg, p, h, r, t, k, lane, ent.w, ent.pitch, neg_e, neg_head);
+        warp_sample_negatives(P, P.seed, kg, p, h, r, t, k, lane, ent.w, ent.pitch, neg_e, neg_head);
         const unsigned head_mask = __ballot_sync(OEA_FULL, neg_head);
         if (dbg != nullptr) {
             int32_t* row = dbg + (size_t)p * (2 + k);
@@ -517,14 +517,41 @@ __device__ __forceinline__ float cross_oct_sum(float v) {
     return v;
 }
 
-__global__ void __launch_bounds__(kThreads, 2)
-k_score_sampled_oct(TableDev ent, TableDev rel, SampledParams P, oea_loss_cfg cfg,
-                    double* __restrict__ loss_out, int32_t* __restrict__ dbg) {
-    __shared__ double s_loss[kWarpsPerBlock];
-    if (P.dev_seed != nullptr) P.seed ^= __ldg(reinterpret_cast<const unsigned long long*>(P.dev_seed));
+#ifndef OEA_OCT_WARPS
+#define OEA_OCT_WARPS 4
+#endif
+#ifndef OEA_OCT_MINB
+#define OEA_OCT_MINB 6       // measured on B200 (scripts/ab_score.sh): 6 CTAs × 4 warps, ≤ 80 registers beats both 5 and 8
+#endif
+#ifndef OEA_OCT_E_SMEM
+#define OEA_OCT_E_SMEM 1
+#endif
+constexpr int kOctWarps = OEA_OCT_WARPS;      // warps per CTA of the octet kernel
+constexpr int kOctThreads = kOctWarps * OEA_WARP;
+
+// Per-warp staging in shared memory.  The kernel is issue-latency bound (≈2 000 warp instructions per positive on
+// a chain of 5 dependent memory hops), so what matters is resident warps per scheduler: keeping ĥ+r̂ / r̂−t̂ (read-only
+// in phase 2, one copy per warp, broadcast to the 4 octets) and the per-octet Σ g·ê accumulators out of the register
+// file takes the kernel from 128 to ≤ 64 registers, i.e. from 16 to 32 resident warps per SM.
+struct OctStage {
+    float4 hr[4][8];     // ĥ + r̂   (slot q = l + 8·i)
+    float4 rt[4][8];     // r̂ − t̂
+#if OEA_OCT_E_SMEM
+    float4 Eh[4][32];    // Σ g_j·ê_j over this lane's octet, head-corrupted negatives
+    float4 Et[4][32];    //                                  tail-corrupted
+#endif
+};
+
+__device__ __forceinline__ void oct_score_body(const TableDev& ent, const TableDev& rel, const SampledParams& P,
+                                               const oea_loss_cfg& cfg, double* __restrict__ loss_out,
+                                               int32_t* __restrict__ dbg, double* s_loss, OctStage* s_stage) {
+    // P stays in the constant bank (P.kg[q] is indexed there, no local copy); the per-replay seed is a register
+    const uint64_t seed = P.dev_seed != nullptr ? P.seed ^ __ldg(reinterpret_cast<const unsigned long long*>(P.dev_seed))
+                                                : P.seed;
     const int lane = threadIdx.x & 31, oct = lane >> 3, l = lane & 7;
-    const int warp_global = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-    const int n_warps = gridDim.x * kWarpsPerBlock;
+    OctStage& S = s_stage[threadIdx.x >> 5];
+    const int warp_global = blockIdx.x * kOctWarps + (threadIdx.x >> 5);
+    const int n_warps = gridDim.x * kOctWarps;
     const int n_pos = P.n_slice[0] + P.n_slice[1];
     const int k = P.k;
     const int p4 = ent.pitch >> 2;
@@ -537,7 +564,7 @@ k_score_sampled_oct(TableDev ent, TableDev rel, SampledParams P, oea_loss_cfg cf
         const int local = q == 0 ? p : p - P.n_slice[0];
         const uint32_t tri = (P.diag & 8) ? (uint32_t)(P.start[q] + local)
                                           : feistel_perm((uint32_t)(P.start[q] + local), (uint32_t)kg.n_triples,
-                                                         P.seed ^ (q ? 0xA5A5A5A5DEADBEEFull : 0x0123456789ABCDEFull));
+                                                         seed ^ (q ? 0xA5A5A5A5DEADBEEFull : 0x0123456789ABCDEFull));
         int hrt = 0;
         if (lane < 3) hrt = __ldg(kg.triples + 3 * (size_t)tri + lane);
         const int h = __shfl_sync(OEA_FULL, hrt, 0);
@@ -551,7 +578,7 @@ k_score_sampled_oct(TableDev ent, TableDev rel, SampledParams P, oea_loss_cfg cf
         int neg_e = 0;
         bool neg_head = false;
         if (P.diag & 1) { neg_e = __ldg(kg.entities + (uint32_t)(p * 31 + lane * 977) % (uint32_t)kg.n_entities); neg_head = (p + lane) & 1; }
-        else warp_sample_negatives(P, kg, p, h, r, t, k, lane, ent.w, ent.pitch, neg_e, neg_head);
+        else warp_sample_negatives(P, seed, kg, p, h, r, t, k, lane, ent.w, ent.pitch, neg_e, neg_head);
         const unsigned head_mask = __ballot_sync(OEA_FULL, neg_head);
         if (dbg != nullptr) {
             int32_t* row = dbg + (size_t)p * (2 + k);
@@ -559,37 +586,46 @@ k_score_sampled_oct(TableDev ent, TableDev rel, SampledParams P, oea_loss_cfg cf
             if (lane < k) row[2 + lane] = neg_e;
         }
 
-        // ---- phase 1: the three shared rows (every octet holds a copy) ----
+        // ---- phase 1: the three shared rows (every octet computes the same copy; octet 0 stages it) ----
         float ih, ir, it, ssh, ssr, sst, sp;
-        R4 hr, rt;   // ĥ + r̂ and r̂ − t̂
+        __syncwarp();   // the previous positive's phase 3 has finished reading the stage
         {
             const R4 xh = load_oct(ent.w, h, ent.pitch, l, p4);
             const R4 xr = load_oct(rel.w, r, rel.pitch, l, p4);
             const R4 xt = load_oct(ent.w, t, ent.pitch, l, p4);
-            ssh = ssr = sst = 0.f;
+            {
+                float2 ah = make_float2(0.f, 0.f), ar = ah, at = ah;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { ssh += dot4(xh.v[i], xh.v[i]); ssr += dot4(xr.v[i], xr.v[i]); sst += dot4(xt.v[i], xt.v[i]); }
-            ssh = oct_sum(ssh); ssr = oct_sum(ssr); sst = oct_sum(sst);
+                for (int i = 0; i < 4; ++i) { dot4_acc2(ah, xh.v[i], xh.v[i]); dot4_acc2(ar, xr.v[i], xr.v[i]); dot4_acc2(at, xt.v[i], xt.v[i]); }
+                ssh = oct_sum(ah.x + ah.y); ssr = oct_sum(ar.x + ar.y); sst = oct_sum(at.x + at.y);
+            }
             ih = inv_norm(ssh, ent.norm); ir = inv_norm(ssr, rel.norm); it = inv_norm(sst, ent.norm);
-            float sp_part = 0.f;
+            float2 sp_part = make_float2(0.f, 0.f);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const float4 a = xh.v[i] * ih, b = xr.v[i] * ir, c = xt.v[i] * it;
-                hr.v[i] = a + b;
-                rt.v[i] = b - c;
-                const float4 up = hr.v[i] - c;
-                sp_part += dot4(up, up);
+                const float4 hr = a + b, rt = b - c;
+                if (oct == 0) { S.hr[i][l] = hr; S.rt[i][l] = rt; }
+                const float4 up = hr - c;
+                dot4_acc2(sp_part, up, up);
+#if OEA_OCT_E_SMEM
+                S.Eh[i][lane] = f4(0.f);
+                S.Et[i][lane] = f4(0.f);
+#endif
             }
-            sp = oct_sum(sp_part);
+            sp = oct_sum(sp_part.x + sp_part.y);
         }
+        __syncwarp();
         float Lp = 0.f, gp = 0.f;
         if (!margin_mode) loss_of(cfg.loss_kind, false, sp, cfg, Lp, gp);
         if (lane == 0) lane_loss += Lp;
 
         // ---- phase 2: negatives, four at a time (octet o takes negative 4·round + o) ----
+#if !OEA_OCT_E_SMEM
         R4 Eh, Et;   // Σ g_j·ê_j over head- / tail-corrupted negatives of this octet
 #pragma unroll
         for (int i = 0; i < 4; ++i) { Eh.v[i] = f4(0.f); Et.v[i] = f4(0.f); }
+#endif
         float Gh_s = 0.f, Gt_s = 0.f;
         const int rounds = (P.diag & 4) ? 0 : (k + 3) >> 2;
         for (int round = 0; round < rounds; ++round) {
@@ -598,22 +634,25 @@ k_score_sampled_oct(TableDev ent, TableDev rel, SampledParams P, oea_loss_cfg cf
             const int e_id = __shfl_sync(OEA_FULL, neg_e, valid ? j : 0);
             const bool head = (head_mask >> (valid ? j : 0)) & 1u;
             R4 e = load_oct(ent.w, valid ? e_id : h, ent.pitch, l, p4);
-            float sse = 0.f;
+            float2 sse2 = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) sse += dot4(e.v[i], e.v[i]);
-            sse = oct_sum(sse);
+            for (int i = 0; i < 4; ++i) dot4_acc2(sse2, e.v[i], e.v[i]);
+            const float sse = oct_sum(sse2.x + sse2.y);
             const float ie = inv_norm(sse, ent.norm);
+            // u = ê + (r̂ − t̂) for a corrupted head, (ĥ + r̂) − ê for a corrupted tail
+            const float4* base = head ? &S.rt[0][0] : &S.hr[0][0];
+            const float sgn = head ? 1.f : -1.f;
             R4 u;
-            float s_part = 0.f, d_part = 0.f;
+            float2 s_part = make_float2(0.f, 0.f), d_part = s_part;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 e.v[i] = e.v[i] * ie;
-                u.v[i] = head ? (e.v[i] + rt.v[i]) : (hr.v[i] - e.v[i]);
-                s_part += dot4(u.v[i], u.v[i]);
-                d_part += dot4(e.v[i], u.v[i]);
+                u.v[i] = fma4(e.v[i], sgn, base[i * 8 + l]);
+                dot4_acc2(s_part, u.v[i], u.v[i]);
+                dot4_acc2(d_part, e.v[i], u.v[i]);
             }
-            const float sn = oct_sum(s_part);
-            const float de = oct_sum(d_part);
+            const float sn = oct_sum(s_part.x + s_part.y);
+            const float de = oct_sum(d_part.x + d_part.y);
             float L = 0.f, g = 0.f;
             if (margin_mode) {
                 const float v = cfg.margin + sp - sn;
@@ -627,19 +666,23 @@ k_score_sampled_oct(TableDev ent, TableDev rel, SampledParams P, oea_loss_cfg cf
             if (l == 0) lane_loss += L;
             if (g != 0.f) {
                 // d s/d ê = ±2u ; through the normaliser: (ĝ − ê<ê,ĝ>)/‖x‖
-                const float c = (head ? 2.f : -2.f) * g * ie;
+                const float c = 2.f * sgn * g * ie;
                 const float proj = (ent.norm && sse >= kNormEps) ? de : 0.f;
-                R4 out;
+#if OEA_OCT_E_SMEM
+                float4* acc = head ? &S.Eh[0][0] : &S.Et[0][0];
+#endif
+                float* grow = ent.g + (size_t)e_id * ent.pitch;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    out.v[i] = fma4(e.v[i], -proj, u.v[i]) * c;
+#if OEA_OCT_E_SMEM
+                    acc[i * 32 + lane] = fma4(e.v[i], g, acc[i * 32 + lane]);
+#else
                     if (head) Eh.v[i] = fma4(e.v[i], g, Eh.v[i]); else Et.v[i] = fma4(e.v[i], g, Et.v[i]);
+#endif
+                    if (!(P.diag & 2) && l + 8 * i < p4) red_add4(grow + 4 * (l + 8 * i), fma4(e.v[i], -proj, u.v[i]) * c);
                 }
                 if (head) Gh_s += g; else Gt_s += g;
-                if (!(P.diag & 2)) {
-                    red_oct(ent.g, e_id, ent.pitch, l, p4, out);
-                    if (l == 0) ent.touched[e_id] = 1;
-                }
+                if (!(P.diag & 2) && l == 0) ent.touched[e_id] = 1;
             }
         }
         if (margin_mode) gp = __shfl_sync(OEA_FULL, gp, 0);
@@ -647,56 +690,151 @@ k_score_sampled_oct(TableDev ent, TableDev rel, SampledParams P, oea_loss_cfg cf
         // ---- phase 3: merge the octets, finish rows h (octet 0), r (octet 1), t (octet 2) ----
         Gh_s = cross_oct_sum(Gh_s);
         Gt_s = cross_oct_sum(Gt_s);
+        __syncwarp();   // the accumulators of all four octets are visible
         if (gp != 0.f || Gh_s != 0.f || Gt_s != 0.f) {
+            // all four octets run the same arithmetic on their own row (full-mask shuffles inside); octet 3
+            // mirrors octet 2 and writes nothing.  Ĝ = α·P + β·A + γ·B with per-role scalars:
+            //   h: P + A      r: P + A + B      t: −P − B      (P = 2g⁺u⁺, A = 2(G_t·hr − E_t), B = 2(G_h·rt + E_h))
+            const int role = oct < 3 ? oct : 2;
+            const int row = role == 0 ? h : (role == 1 ? r : t);
+            const TableDev& tab = role == 1 ? rel : ent;
+            const R4 xo = load_oct(tab.w, row, tab.pitch, l, p4);                    // L1 hit
+            const float io = role == 0 ? ih : (role == 1 ? ir : it);
+            const float so = role == 0 ? ssh : (role == 1 ? ssr : sst);
+            const float alpha = role == 2 ? -2.f * gp : 2.f * gp;
+            const float beta = role == 2 ? 0.f : 2.f, gamma = role == 0 ? 0.f : (role == 1 ? 2.f : -2.f);
+            // u⁺ = hr − t̂ and t̂ = r̂ − rt... kept affine in the staged rows: α·u⁺ = α·hr − α·t̂, t̂ reloaded (L1 hit)
+            const R4 xt = load_oct(ent.w, t, ent.pitch, l, p4);
+            const float c_hr = alpha + beta * Gt_s, c_rt = gamma * Gh_s, c_t = -alpha * it;
+            R4 G;
+            float2 dpart2 = make_float2(0.f, 0.f);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                Eh.v[i].x = cross_oct_sum(Eh.v[i].x); Eh.v[i].y = cross_oct_sum(Eh.v[i].y);
-                Eh.v[i].z = cross_oct_sum(Eh.v[i].z); Eh.v[i].w = cross_oct_sum(Eh.v[i].w);
-                Et.v[i].x = cross_oct_sum(Et.v[i].x); Et.v[i].y = cross_oct_sum(Et.v[i].y);
-                Et.v[i].z = cross_oct_sum(Et.v[i].z); Et.v[i].w = cross_oct_sum(Et.v[i].w);
+#if OEA_OCT_E_SMEM
+                const float4 eh = (S.Eh[i][l] + S.Eh[i][8 + l]) + (S.Eh[i][16 + l] + S.Eh[i][24 + l]);
+                const float4 et = (S.Et[i][l] + S.Et[i][8 + l]) + (S.Et[i][16 + l] + S.Et[i][24 + l]);
+#else
+                float4 eh = Eh.v[i], et = Et.v[i];
+                eh.x = cross_oct_sum(eh.x); eh.y = cross_oct_sum(eh.y); eh.z = cross_oct_sum(eh.z); eh.w = cross_oct_sum(eh.w);
+                et.x = cross_oct_sum(et.x); et.y = cross_oct_sum(et.y); et.z = cross_oct_sum(et.z); et.w = cross_oct_sum(et.w);
+#endif
+                // α(hr − t̂) + β(G_t·hr − E_t) + γ(G_h·rt + E_h)
+                float4 g4 = S.hr[i][l] * c_hr;
+                g4 = fma4(S.rt[i][l], c_rt, g4);
+                g4 = fma4(xt.v[i], c_t, g4);
+                g4 = fma4(et, -beta, g4);
+                g4 = fma4(eh, gamma, g4);
+                G.v[i] = g4;
+                dot4_acc2(dpart2, xo.v[i], g4);
             }
-            {   // all four octets run the same arithmetic on their own row (full-mask shuffles inside); octet 3
-                // mirrors octet 2 and writes nothing.  Ĝ = α·P + β·A + γ·B with per-role scalars:
-                //   h: P + A      r: P + A + B      t: −P − B      (P = 2g⁺u⁺, A = 2(G_t·hr − E_t), B = 2(G_h·rt + E_h))
-                const int role = oct < 3 ? oct : 2;
-                const R4 xt = load_oct(ent.w, t, ent.pitch, l, p4);                      // t̂ for u⁺ (L1 hit)
-                const int row = role == 0 ? h : (role == 1 ? r : t);
-                const TableDev& tab = role == 1 ? rel : ent;
-                const R4 xo = load_oct(tab.w, row, tab.pitch, l, p4);
-                const float io = role == 0 ? ih : (role == 1 ? ir : it);
-                const float so = role == 0 ? ssh : (role == 1 ? ssr : sst);
-                const float alpha = role == 2 ? -2.f * gp : 2.f * gp;
-                const float beta = role == 2 ? 0.f : 2.f, gamma = role == 0 ? 0.f : (role == 1 ? 2.f : -2.f);
-                const float c_hr = alpha + beta * Gt_s, c_rt = gamma * Gh_s, c_t = -alpha * it;
-                R4 G;
-                float dpart = 0.f;
+            const float dot = oct_sum((dpart2.x + dpart2.y) * io);
+            const float proj = (tab.norm && so >= kNormEps) ? dot : 0.f;
+            if (oct < 3 && !(P.diag & 2)) {
+                R4 out;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    // α(hr − t̂) + β(G_t·hr − E_t) + γ(G_h·rt + E_h)
-                    float4 g4 = hr.v[i] * c_hr;
-                    g4 = fma4(rt.v[i], c_rt, g4);
-                    g4 = fma4(xt.v[i], c_t, g4);
-                    g4 = fma4(Et.v[i], -beta, g4);
-                    g4 = fma4(Eh.v[i], gamma, g4);
-                    G.v[i] = g4;
-                    dpart += dot4(xo.v[i], g4);
-                }
-                dpart *= io;
-                const float dot = oct_sum(dpart);
-                const float proj = (tab.norm && so >= kNormEps) ? dot : 0.f;
-                if (oct < 3 && !(P.diag & 2)) {
-                    R4 out;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) out.v[i] = fma4(xo.v[i] * io, -proj, G.v[i]) * io;
-                    red_oct(tab.g, row, tab.pitch, l, p4, out);
-                    if (l == 0) tab.touched[row] = 1;
-                }
+                for (int i = 0; i < 4; ++i) out.v[i] = fma4(xo.v[i] * io, -proj, G.v[i]) * io;
+                red_oct(tab.g, row, tab.pitch, l, p4, out);
+                if (l == 0) tab.touched[row] = 1;
             }
         }
     }
     const float warp_loss = warp_sum(lane_loss);
     LossAcc acc{s_loss};
-    acc.flush(warp_loss, loss_out);
+    acc.flush(warp_loss, loss_out, kOctWarps);
+}
+
+__global__ void __launch_bounds__(kOctThreads, OEA_OCT_MINB)
+k_score_sampled_oct(TableDev ent, TableDev rel, const __grid_constant__ SampledParams P, oea_loss_cfg cfg,
+                    double* __restrict__ loss_out, int32_t* __restrict__ dbg) {
+    __shared__ double s_loss[kOctWarps];
+    __shared__ OctStage s_stage[kOctWarps];
+    oct_score_body(ent, rel, P, cfg, loss_out, dbg, s_loss, s_stage);
+}
+
+// Row optimiser over the concatenated row space [ent rows | rel rows] in the octet layout: a warp reads 32 row
+// flags at once, then finishes the flagged rows four at a time (octet o takes the o-th flagged row; 12 independent
+// 16-byte loads per lane are in flight).  TF1 Adagrad / SGD as in k_rowopt.
+struct OptTab {
+    float* w;
+    float* g;
+    float* s1;
+    int32_t* touched;
+    int rows;
+};
+
+template <int KIND>
+__device__ __forceinline__ void oct_rowopt_body(const OptTab& A, const OptTab& B, int pitch, float lr, int warp_global,
+                                                int n_warps) {
+    const int lane = threadIdx.x & 31, oct = lane >> 3, l = lane & 7;
+    const int p4 = pitch >> 2;
+    const int total = A.rows + B.rows;
+    const int n_quads = (total + 3) >> 2;          // work unit: 4 consecutive rows, one per octet
+    auto flag_of = [&](int quad) -> int32_t* {
+        const int r = 4 * quad + oct;
+        if (quad >= n_quads || r >= total) return nullptr;
+        return r < A.rows ? A.touched + r : B.touched + (r - A.rows);
+    };
+    int quad = warp_global;
+    int32_t* flag = flag_of(quad);
+    int on = (flag != nullptr && l == 0) ? *flag : 0;
+    while (quad < n_quads) {
+        // the next quad's flag is in flight while this quad's rows are processed
+        const int next = quad + n_warps;
+        int32_t* nflag = flag_of(next);
+        const int non = (nflag != nullptr && l == 0) ? *nflag : 0;
+        const bool mine = __shfl_sync(OEA_FULL, on, oct << 3) != 0;
+        if (mine) {
+            const int rr = 4 * quad + oct;
+            const bool first = rr < A.rows;
+            const OptTab& T = first ? A : B;
+            const size_t off = (size_t)(first ? rr : rr - A.rows) * pitch;
+            if (l == 0) *flag = 0;
+            for (int q0 = 0; q0 < p4; q0 += 32) {
+                float4 g[4], x[4], a[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int q = q0 + l + 8 * i;
+                    if (q < p4) {
+                        g[i] = *reinterpret_cast<const float4*>(T.g + off + 4 * q);
+                        x[i] = *reinterpret_cast<const float4*>(T.w + off + 4 * q);
+                        if (KIND == OEA_OPT_ADAGRAD) a[i] = *reinterpret_cast<const float4*>(T.s1 + off + 4 * q);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int q = q0 + l + 8 * i;
+                    if (q < p4) {
+                        if (KIND == OEA_OPT_ADAGRAD) {
+                            a[i].x = fmaf(g[i].x, g[i].x, a[i].x); a[i].y = fmaf(g[i].y, g[i].y, a[i].y);
+                            a[i].z = fmaf(g[i].z, g[i].z, a[i].z); a[i].w = fmaf(g[i].w, g[i].w, a[i].w);
+                            x[i].x -= lr * g[i].x * rsqrtf(a[i].x); x[i].y -= lr * g[i].y * rsqrtf(a[i].y);
+                            x[i].z -= lr * g[i].z * rsqrtf(a[i].z); x[i].w -= lr * g[i].w * rsqrtf(a[i].w);
+                            *reinterpret_cast<float4*>(T.s1 + off + 4 * q) = a[i];
+                        } else {
+                            x[i].x -= lr * g[i].x; x[i].y -= lr * g[i].y; x[i].z -= lr * g[i].z; x[i].w -= lr * g[i].w;
+                        }
+                        *reinterpret_cast<float4*>(T.w + off + 4 * q) = x[i];
+                        *reinterpret_cast<float4*>(T.g + off + 4 * q) = f4(0.f);
+                    }
+                }
+            }
+        }
+        quad = next; flag = nflag; on = non;
+    }
+}
+
+// The whole sampled training step as ONE cooperative launch: score + gradients, grid barrier, row optimiser.
+// Saves the second launch and its ramp (≈ 6 µs of a 43 µs step at the 15K shape); the grid is one resident wave by
+// construction (grid_one_wave), which is what a cooperative launch requires.
+template <int KIND>
+__global__ void __launch_bounds__(kOctThreads, OEA_OCT_MINB)
+k_step_sampled_oct(TableDev ent, TableDev rel, const __grid_constant__ SampledParams P, oea_loss_cfg cfg,
+                   double* __restrict__ loss_out, OptTab A, OptTab B, float lr) {
+    __shared__ double s_loss[kOctWarps];
+    __shared__ OctStage s_stage[kOctWarps];
+    oct_score_body(ent, rel, P, cfg, loss_out, nullptr, s_loss, s_stage);
+    cooperative_groups::this_grid().sync();
+    oct_rowopt_body<KIND>(A, B, ent.pitch, lr, blockIdx.x * kOctWarps + (threadIdx.x >> 5), gridDim.x * kOctWarps);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -796,10 +934,10 @@ static int grid_for(int n_warp_items) {
 // Exactly one resident wave for kernel `fn` (grid-stride loops do the rest): a partial last wave would run at a
 // fraction of the machine for a whole block duration (measured: 2.11 waves cost 3 block durations).
 template <typename Fn>
-static int grid_one_wave(Fn fn, int n_warp_items) {
+static int grid_one_wave(Fn fn, int n_warp_items, int warps_per_block = kWarpsPerBlock) {
     static int occ = 0;   // one static per kernel instantiation
-    if (occ == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kThreads, 0) != cudaSuccess || occ < 1)) occ = 1;
-    const int blocks_needed = (n_warp_items + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    if (occ == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, warps_per_block * OEA_WARP, 0) != cudaSuccess || occ < 1)) occ = 1;
+    const int blocks_needed = (n_warp_items + warps_per_block - 1) / warps_per_block;
     const int cap = sm_count_cached() * occ;
     return blocks_needed < 1 ? 1 : (blocks_needed < cap ? blocks_needed : cap);
 }
@@ -907,6 +1045,12 @@ static bool oea_force_v1() {
     return v != nullptr && v[0] == '1';
 }
 
+// OEA_NO_FUSE=1 keeps the sampled step as two launches (score, optimiser): A/B of the cooperative fused launch.
+static bool oea_no_fuse() {
+    const char* v = getenv("OEA_NO_FUSE");
+    return v != nullptr && v[0] == '1';
+}
+
 static int check_kg(const oea_kg_view* kg, int k) {
     if (kg == nullptr) return OEA_ERR_NULL;
     if (kg->n_triples < 0 || kg->n_entities < 0) return OEA_ERR_RANGE;
@@ -925,10 +1069,11 @@ static void slice_of(int n_triples, int batch_kg, int step, int* start, int* cou
     *count = (int)(e - s > 0 ? e - s : 0);
 }
 
-extern "C" int oea_triple_score_sampled(const oea_table* ent, const oea_table* rel,
-                                        const oea_kg_view* kg1, const oea_kg_view* kg2, const oea_tripleset* tset,
-                                        const oea_sample_cfg* smp, const oea_loss_cfg* loss,
-                                        double* loss_out, int32_t* n_pos_out, int32_t* dbg_neg, void* stream) {
+// Argument checks + step parameters shared by the score-only and the fused-step entry points.
+static int sampled_prepare(const oea_table* ent, const oea_table* rel, const oea_kg_view* kg1, const oea_kg_view* kg2,
+                           const oea_tripleset* tset, const oea_sample_cfg* smp, const oea_loss_cfg* loss,
+                           const double* loss_out, oea::SampledParams* Pout, int* n_pos_out_host) {
+    using namespace oea;
     int rc = check_table(ent, true); if (rc) return rc;
     rc = check_table(rel, true); if (rc) return rc;
     if (!smp || !loss || !loss_out || !tset || !tset->slots) return OEA_ERR_NULL;
@@ -948,7 +1093,7 @@ extern "C" int oea_triple_score_sampled(const oea_table* ent, const oea_table* r
     const int b1 = (int)((double)kg1->n_triples / (double)T * (double)smp->batch_size);
     const int b2 = smp->batch_size - b1;
 
-    SampledParams P;
+    SampledParams& P = *Pout;
     P.kg[0] = *kg1; P.kg[1] = *kg2; P.tset = *tset;
     slice_of(kg1->n_triples, b1, smp->step, &P.start[0], &P.n_slice[0]);
     slice_of(kg2->n_triples, b2, smp->step, &P.start[1], &P.n_slice[1]);
@@ -959,6 +1104,17 @@ extern "C" int oea_triple_score_sampled(const oea_table* ent, const oea_table* r
         if (diag_cached < 0) { const char* dg = getenv("OEA_DIAG"); diag_cached = dg ? atoi(dg) : 0; }
         P.diag = diag_cached;
     }
+    *n_pos_out_host = P.n_slice[0] + P.n_slice[1];
+    return OEA_OK;
+}
+
+extern "C" int oea_triple_score_sampled(const oea_table* ent, const oea_table* rel,
+                                        const oea_kg_view* kg1, const oea_kg_view* kg2, const oea_tripleset* tset,
+                                        const oea_sample_cfg* smp, const oea_loss_cfg* loss,
+                                        double* loss_out, int32_t* n_pos_out, int32_t* dbg_neg, void* stream) {
+    SampledParams P;
+    int n_pos_prepared = 0;
+    int rc = sampled_prepare(ent, rel, kg1, kg2, tset, smp, loss, loss_out, &P, &n_pos_prepared); if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int n_pos = P.n_slice[0] + P.n_slice[1];
     if (n_pos_out) OEA_CUDA_TRY(cudaMemcpyAsync(n_pos_out, &n_pos, sizeof(int), cudaMemcpyHostToDevice, st));
@@ -966,8 +1122,8 @@ extern "C" int oea_triple_score_sampled(const oea_table* ent, const oea_table* r
     TableDev e = table_dev(ent), r = table_dev(rel);
     const bool l1 = loss->score_kind == OEA_SCORE_L1;
     if (!l1 && ent->pitch <= 128 && !oea_force_v1()) {
-        const int grid = grid_one_wave(k_score_sampled_oct, n_pos);
-        k_score_sampled_oct<<<grid, kThreads, 0, st>>>(e, r, P, *loss, loss_out, dbg_neg);
+        const int grid = grid_one_wave(k_score_sampled_oct, n_pos, kOctWarps);
+        k_score_sampled_oct<<<grid, kOctThreads, 0, st>>>(e, r, P, *loss, loss_out, dbg_neg);
     } else {
 #define CALL(V)                                                                                              \
     if (l1) { const int grid = grid_one_wave(k_score_sampled<OEA_SCORE_L1, V>, n_pos);                       \
@@ -1268,7 +1424,6 @@ extern "C" int oea_mapping_fwd_bwd(const float* e1, const float* e2, int32_t n, 
 // ================================================================================================
 namespace oea {
 
-struct OptTab { float* w; float* g; float* s1; int32_t* touched; int rows; };
 
 // Adagrad / SGD over the concatenated row space [ent rows | rel rows] (same pitch), flagged rows only.
 template <int KIND>
@@ -1330,7 +1485,33 @@ extern "C" int oea_triple_step_sampled(const oea_table* ent, const oea_table* re
                                        const oea_kg_view* kg1, const oea_kg_view* kg2, const oea_tripleset* tset,
                                        const oea_sample_cfg* smp, const oea_loss_cfg* loss, const oea_opt_cfg* opt,
                                        double* loss_out, int32_t* n_pos_out, void* stream) {
-    int rc = oea_triple_score_sampled(ent, rel, kg1, kg2, tset, smp, loss, loss_out, n_pos_out, nullptr, stream);
-    if (rc) return rc;
-    return oea_rowopt_apply_pair(ent, rel, opt, stream);
+    if (!opt) return OEA_ERR_NULL;
+    // One cooperative launch when the octet kernel applies and the optimiser is row-sparse (Adagrad / SGD)
+    const bool fuse = loss && ent && rel && loss->score_kind == OEA_SCORE_L2SQ && ent->pitch <= 128 && !oea_force_v1() &&
+                      (opt->kind == OEA_OPT_ADAGRAD || opt->kind == OEA_OPT_SGD) && !oea_no_fuse();
+    if (!fuse) {
+        int rc = oea_triple_score_sampled(ent, rel, kg1, kg2, tset, smp, loss, loss_out, n_pos_out, nullptr, stream);
+        if (rc) return rc;
+        return oea_rowopt_apply_pair(ent, rel, opt, stream);
+    }
+    SampledParams P;
+    int n_pos = 0;
+    int rc = sampled_prepare(ent, rel, kg1, kg2, tset, smp, loss, loss_out, &P, &n_pos); if (rc) return rc;
+    if (opt->kind == OEA_OPT_ADAGRAD && (!ent->state1 || !rel->state1)) return OEA_ERR_NULL;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_pos_out) OEA_CUDA_TRY(cudaMemcpyAsync(n_pos_out, &n_pos, sizeof(int), cudaMemcpyHostToDevice, st));
+    if (n_pos == 0) return OEA_OK;
+    TableDev e = table_dev(ent), r = table_dev(rel);
+    OptTab A{ent->weight, ent->grad, ent->state1, ent->touched, ent->rows}, B{rel->weight, rel->grad, rel->state1, rel->touched, rel->rows};
+    oea_loss_cfg cfg = *loss;
+    float lr = opt->lr;
+    void* args[] = {&e, &r, &P, &cfg, &loss_out, &A, &B, &lr};
+    if (opt->kind == OEA_OPT_ADAGRAD) {
+        const int grid = grid_one_wave(k_step_sampled_oct<OEA_OPT_ADAGRAD>, n_pos, kOctWarps);
+        OEA_CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_step_sampled_oct<OEA_OPT_ADAGRAD>, dim3(grid), dim3(kOctThreads), args, 0, st));
+    } else {
+        const int grid = grid_one_wave(k_step_sampled_oct<OEA_OPT_SGD>, n_pos, kOctWarps);
+        OEA_CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_step_sampled_oct<OEA_OPT_SGD>, dim3(grid), dim3(kOctThreads), args, 0, st));
+    }
+    return OEA_OK;
 }

@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "liboea.so")
+# OEA_LIB_PATH: kernel A/B experiments only (scripts/ab_score.sh builds variant libraries next to the default one)
+LIB_PATH = os.environ.get("OEA_LIB_PATH") or os.path.join(_HERE, "_lib", "liboea.so")
 
 SCORE_L1, SCORE_L2SQ = 0, 1
 LOSS_MARGIN, LOSS_LIMITED, LOSS_LOGISTIC, LOSS_POSITIVE, LOSS_LOGSIGMOID = 0, 1, 2, 3, 4

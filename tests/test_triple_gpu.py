@@ -226,3 +226,77 @@ def test_sampled_step_replays_through_oracle(cuda_device, monkeypatch, truncated
         te.grad.zero_(); tr.grad.zero_(); te.touched.zero_(); tr.touched.zero_()
     # the epoch permutation is a bijection: slices partition (a prefix of) each triple list exactly once
     assert len(seen_tri[0]) == min(T1, steps * b1) and len(seen_tri[1]) == min(T2, steps * b2)
+
+
+def _sampled_world(rng, eng, n_ent=4000, n_rel=30):
+    ents1 = np.arange(0, n_ent, 2, dtype=np.int32)
+    ents2 = np.arange(1, n_ent, 2, dtype=np.int32)
+
+    def mk(ents, n, rlo, rhi):
+        tri = np.stack([rng.choice(ents, n), rng.integers(rlo, rhi, n), rng.choice(ents, n)], 1).astype(np.int32)
+        return np.unique(tri, axis=0)
+    t1, t2 = mk(ents1, 3000, 0, 15), mk(ents2, 2500, 15, 30)
+    kg1, kg2 = eng.DeviceKG(t1, ents1, n_ent), eng.DeviceKG(t2, ents2, n_ent)
+    return kg1, kg2, eng.DeviceTripleSet([kg1.triples, kg2.triples], n_ent, n_rel)
+
+
+@pytest.mark.parametrize("opt,d,loss,k", [("Adagrad", 100, "limited", 10), ("SGD", 75, "logistic", 4),
+                                          ("Adagrad", 128, "margin-based", 1), ("Adagrad", 64, "positive", 0)])
+def test_single_launch_step_equals_two_launch_step(cuda_device, monkeypatch, opt, d, loss, k):
+    """oea_triple_step_sampled as ONE cooperative launch (score, grid barrier, row optimiser) leaves the tables,
+    the optimiser slots, the flags and the loss exactly where the two-launch path (OEA_NO_FUSE=1: the same score
+    kernel, then k_rowopt_pair) leaves them — up to the order of the float atomics in the gradient rows."""
+    eng = _engine()
+    rng = np.random.default_rng(5 + d)
+    ent, rel = make_tables(rng, 4000, 30, d)
+    kg1, kg2, tset = _sampled_world(rng, eng)
+    kw = dict(margin=1.2 if loss == "margin-based" else 0.01, neg_margin=2.0, balance=0.2)
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("OEA_NO_FUSE", mode)
+        te, tr = _tables(ent, rel, True, opt)
+        trn = eng.TripleTrainer(te, tr, eng.loss_cfg(loss, "L2", **kw), lr=0.05)
+        losses = []
+        for step in range(6):
+            trn.step_sampled(kg1, kg2, tset, 512, k, step, epoch_seed=99)
+            losses.append(trn.read_loss())
+        assert not te.grad.any().item() and not tr.grad.any().item(), "gradient rows are zeroed by the optimiser"
+        assert not te.touched.any().item() and not tr.touched.any().item(), "row flags are cleared"
+        out[mode] = (te.weight.cpu().numpy(), tr.weight.cpu().numpy(),
+                     None if opt == "SGD" else te.state1.cpu().numpy(), losses)
+    a, b = out["0"], out["1"]
+    assert np.abs(a[0] - ent_pad(ent, a[0].shape[1])).max() > 1e-4, "the step moved the table"
+    np.testing.assert_allclose(a[0], b[0], rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(a[1], b[1], rtol=2e-5, atol=2e-6)
+    if a[2] is not None:
+        np.testing.assert_allclose(a[2], b[2], rtol=2e-5, atol=1e-7)
+    np.testing.assert_allclose(a[3], b[3], rtol=1e-5)
+
+
+def ent_pad(x, pitch):
+    out = np.zeros((x.shape[0], pitch), dtype=np.float32)
+    out[:, :x.shape[1]] = x
+    return out
+
+
+def test_single_launch_step_inside_a_cuda_graph(cuda_device):
+    """The cooperative launch is capturable: an epoch graph replays to the same tables as the eager steps."""
+    eng = _engine()
+    rng = np.random.default_rng(77)
+    ent, rel = make_tables(rng, 4000, 30, 100)
+    kg1, kg2, tset = _sampled_world(rng, eng)
+    res = []
+    for graph in (False, True):
+        te, tr = _tables(ent, rel, True)
+        trn = eng.TripleTrainer(te, tr, eng.loss_cfg("limited", "L2", margin=0.01, neg_margin=2.0, balance=0.2), lr=0.05)
+        if graph:
+            g = trn.capture_epoch(kg1, kg2, tset, 512, 10, 5)
+            g.replay(4242)           # capture itself executes nothing
+        else:
+            seed_dev = torch.tensor([4242], dtype=torch.int64, device="cuda")
+            for step in range(5):
+                trn.step_sampled(kg1, kg2, tset, 512, 10, step, epoch_seed=0, dev_seed=seed_dev)
+        torch.cuda.synchronize()
+        res.append((te.weight.cpu().numpy(), trn.read_loss()))
+    np.testing.assert_allclose(res[0][0], res[1][0], rtol=2e-5, atol=2e-6)
+    assert res[0][1] == pytest.approx(res[1][1], rel=1e-5)
