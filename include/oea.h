@@ -261,12 +261,20 @@ int oea_sim_matrix(const oea_sim_cfg* cfg, const float* e1, const float* e2,
  * contraction runs once instead of three times (similarity.py:57-83, alignment.py:146-168).
  *   oea_matrix_topk_mean: mean of the k (<= 32) largest entries of every row (by_column = 0) or every column
  *                         (by_column = 1) of mat [n_rows, ld] → out_mean [n_rows] / [n_cols]  (= calculate_nearest_k);
+ *                         the column form keeps per-row-split partial lists in `workspace` (size from
+ *                         oea_matrix_topk_mean_workspace_bytes; the row form needs none);
  *   oea_matrix_rank     : per row arg-max and 0-based rank of column gold[i] of 2·S − row_off[i] − col_off[j]
  *                         (offsets NULL → of S itself); ties: lower column first. */
+size_t oea_matrix_topk_mean_workspace_bytes(int32_t n_rows, int32_t n_cols, int32_t k, int32_t by_column);
 int oea_matrix_topk_mean(const float* mat, int64_t ld, int32_t n_rows, int32_t n_cols, int32_t k,
-                         int32_t by_column, float* out_mean, void* stream);
+                         int32_t by_column, float* out_mean, void* workspace, size_t workspace_bytes, void* stream);
 int oea_matrix_rank(const float* mat, int64_t ld, int32_t n_rows, int32_t n_cols, const float* row_off,
                     const float* col_off, const int32_t* gold, int32_t* out_top1, int32_t* out_rank, void* stream);
+
+/* Hits@k counts and rank sums of a 0-based rank vector in one launch (the NumPy reductions of
+ * greedy_alignment, alignment.py:55-69): out[i] = #{rank < top_k_host[i]} for i < n_top (<= 8),
+ * out[n_top] = Σ(rank+1), out[n_top+1] = Σ 1/(rank+1); device fp64 [n_top + 2], zeroed here. top_k_host is a HOST array. */
+int oea_rank_stats(const int32_t* rank, int32_t n, const int32_t* top_k_host, int32_t n_top, double* out, void* stream);
 
 /* sklearn.preprocessing.normalize (similarity.py:30-32): rows scaled to unit L2 norm, zero rows kept;
  * writes zero padding up to out_pitch. */

@@ -11,6 +11,7 @@
 // column tiles of one row block and folds each finished tile into a per-row top-k list (smem) or a
 // per-thread argmax + rank counter (registers).
 #include <float.h>
+#include <stdlib.h>
 #include "oea_common.cuh"
 
 namespace oea {
@@ -293,6 +294,127 @@ k_sim_tile(SimParams P) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Short-contraction store kernel (kdim ≤ 104, i.e. the d = 75 / 100 embeddings of MTransE / BootEA): the A panel of the
+// row block ([kdim][128], ≤ 53 KB) is loaded ONCE and stays in shared memory for every column tile; a B tile arrives as
+// two half-K stages ([KH][128] each), so a tile costs 2 block barriers instead of 7 and every load has half a tile of
+// FFMA2 work (≈ 1.7 µs) to land behind.  Same 8×8 register tile, same ascending-k accumulation as k_sim_tile, hence
+// bit-identical values.  2 CTAs per SM (2 × (2·KH + 2·KH)·128·4 B ≤ 213 KB).
+// ------------------------------------------------------------------------------------------------
+constexpr int SHORTK_MAX = 104;
+
+template <int METRIC>
+__global__ void __launch_bounds__(SIM_THREADS, 2)
+k_sim_store_shortk(SimParams P, int KH) {
+    extern __shared__ __align__(16) float smem[];
+    float* Ares = smem;                       // [2·KH][TM]
+    float* Bbuf0 = Ares + 2 * KH * TM;        // [KH][TN]  k in [0, KH)
+    float* Bbuf1 = Bbuf0 + KH * TN;           // [KH][TN]  k in [KH, 2·KH)
+
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int row0 = blockIdx.x * TM;
+    const int n_col_tiles = (P.n2 + TN - 1) / TN;
+    const int ct0 = blockIdx.y * P.col_tiles_per_split;
+    const int ct1 = min(n_col_tiles, ct0 + P.col_tiles_per_split);
+    if (ct0 >= ct1) return;
+    const int ld_kk = tid >> 5, ld_c4 = (tid & 31) * 4;
+    const float* At = P.e1t + row0;
+
+    auto issue_b = [&](int ct, int half) {
+        const float* Bt = P.e2t + (size_t)ct * TN + (size_t)(half * KH) * P.ld2t;
+        float* dst = half ? Bbuf1 : Bbuf0;
+        for (int kk = ld_kk; kk < KH; kk += 8) cp_async16(dst + kk * TN + ld_c4, Bt + (size_t)kk * P.ld2t + ld_c4);
+    };
+    for (int kk = ld_kk; kk < 2 * KH; kk += 8) cp_async16(Ares + kk * TM + ld_c4, At + (size_t)kk * P.ld1t + ld_c4);
+    issue_b(ct0, 0);
+    cp_async_commit();
+
+    const bool use_csls = P.row_off != nullptr;
+    float roff[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = row0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4);
+        roff[i] = (use_csls && r < P.n1) ? __ldg(P.row_off + r) : 0.f;
+    }
+    const int k_half1 = P.kdim - KH;          // k-steps of the second half that carry data (multiple of 4, ≥ 0)
+
+    for (int ct = ct0; ct < ct1; ++ct) {
+        const int col0 = ct * TN;
+        float acc[8][8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            cp_async_wait<0>();
+            __syncthreads();      // this half has landed for everyone; everyone is done with the other buffer
+            if (half == 0) issue_b(ct, 1);                       // second half of this tile → Bbuf1
+            else if (ct + 1 < ct1) issue_b(ct + 1, 0);           // first half of the next tile → Bbuf0
+            cp_async_commit();
+            const float* Ab = Ares + half * KH * TM;
+            const float* Bb = half ? Bbuf1 : Bbuf0;
+            const int kk_end = half ? k_half1 : min(KH, P.kdim);
+#pragma unroll 4
+            for (int kk = 0; kk < kk_end; ++kk) {
+                const float4 a0 = *reinterpret_cast<const float4*>(Ab + kk * TM + ty * 4);
+                const float4 a1 = *reinterpret_cast<const float4*>(Ab + kk * TM + 64 + ty * 4);
+                const float4 b0 = *reinterpret_cast<const float4*>(Bb + kk * TN + tx * 4);
+                const float4 b1 = *reinterpret_cast<const float4*>(Bb + kk * TN + 64 + tx * 4);
+                const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                if (METRIC == OEA_METRIC_INNER && OEA_F32X2) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float2 aa = make_float2(a[i], a[i]);
+#pragma unroll
+                        for (int j = 0; j < 8; j += 2) {
+                            const float2 r = fma2(aa, make_float2(b[j], b[j + 1]), make_float2(acc[i][j], acc[i][j + 1]));
+                            acc[i][j] = r.x; acc[i][j + 1] = r.y;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) acc[i][j] = sim_accum<METRIC>(a[i], b[j], acc[i][j]);
+                }
+            }
+        }
+
+        float coff[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = col0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + j - 4);
+            coff[j] = (use_csls && c < P.n2) ? __ldg(P.col_off + c) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = row0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4);
+            if (r >= P.n1) continue;
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+                const int c = col0 + (jj == 0 ? tx * 4 : 64 + tx * 4);
+                float v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    v[j] = sim_value<METRIC>(acc[i][jj * 4 + j]);
+                    if (use_csls) v[j] = csls_value(v[j], roff[i], coff[jj * 4 + j]);
+                }
+                float* o = P.out + (size_t)r * P.ld_out + c;
+                if (c + 3 < P.n2 && (P.ld_out & 3) == 0) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+                else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) if (c + j < P.n2) o[j] = v[j];
+                }
+            }
+        }
+    }
+    cp_async_wait<0>();
+}
+
 // Merge the per-split sorted lists of a row (splits ascend in column index, so ties keep the lower index).
 __global__ void __launch_bounds__(256)
 k_topk_merge(const float* __restrict__ part_val, const int* __restrict__ part_idx, int n1, int splits, int k,
@@ -402,6 +524,12 @@ static int check_sim(const oea_sim_cfg* c, const float* e1, const float* e2) {
     if (c->ld1_t < np1 || c->ld2_t < np2 || (c->ld1_t & 3) || (c->ld2_t & 3)) return OEA_ERR_SHAPE;
     if (!aligned16(c->e1_t) || !aligned16(c->e2_t)) return OEA_ERR_ALIGN;
     return OEA_OK;
+}
+
+// OEA_SIM_NO_SHORTK=1 keeps the 3-stage streaming tile kernel for every shape (A/B measurements, tests of both paths)
+static bool sim_no_shortk() {
+    const char* v = getenv("OEA_SIM_NO_SHORTK");
+    return v != nullptr && v[0] == '1';
 }
 
 static int sm_count() {
@@ -566,6 +694,25 @@ extern "C" int oea_sim_matrix(const oea_sim_cfg* c, const float* e1, const float
     fill_common(P, c, e1, e2, row_off, col_off, splits);
     const int eff_splits = (col_tiles + P.col_tiles_per_split - 1) / P.col_tiles_per_split;
     P.out = out; P.ld_out = ld_out;
+    if (P.kdim <= SHORTK_MAX && !sim_no_shortk()) {
+        const int KH = ((P.kdim + 1) / 2 + 3) / 4 * 4;        // k-steps per half stage; 2·KH ≤ the k-major copies' padded rows
+        const size_t smem = (size_t)(2 * KH * TM + 2 * KH * TN) * sizeof(float);
+        const dim3 grid((c->n1 + TM - 1) / TM, eff_splits);
+        cudaStream_t st = (cudaStream_t)stream;
+#define OEA_SHORTK_LAUNCH(M)                                                                                              \
+    do {                                                                                                                  \
+        OEA_CUDA_TRY(cudaFuncSetAttribute(k_sim_store_shortk<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_sim_store_shortk<M><<<grid, SIM_THREADS, smem, st>>>(P, KH);                                                    \
+    } while (0)
+        switch (c->metric) {
+            case OEA_METRIC_INNER: OEA_SHORTK_LAUNCH(OEA_METRIC_INNER); break;
+            case OEA_METRIC_L1: OEA_SHORTK_LAUNCH(OEA_METRIC_L1); break;
+            default: OEA_SHORTK_LAUNCH(OEA_METRIC_L2); break;
+        }
+#undef OEA_SHORTK_LAUNCH
+        OEA_LAUNCH_CHECK();
+        return OEA_OK;
+    }
     return launch_sim<EPI_STORE>(c, P, eff_splits, (cudaStream_t)stream);
 }
 
@@ -726,42 +873,129 @@ k_mat_row_topk_mean(const float* __restrict__ mat, long long ld, int n_rows, int
     if (lane == 0) out_mean[row] = s / (float)k;
 }
 
-constexpr int CT_COLS = 128, CT_ROWS = 64, CT_LD = CT_ROWS + 1;
+// ---- column k-means: thread-owned columns, register-resident sorted lists, rows split over warps ----------------
+// Lane l of a warp owns CPT consecutive columns (128-bit or 64-bit loads, a warp row is 32·CPT·4 contiguous bytes);
+// each owned column keeps its KCAP largest values in a descending register list (insert = one FMNMX pair per
+// slot, taken only when the value beats the list's tail).  The rows are cut into S = 8·gridDim.y splits (one per
+// warp), every split writes its KCAP-list per column and k_col_partial_merge folds the S lists.  No shared memory,
+// no block barrier; 8 row loads are in flight per thread.
+constexpr int CP_WARPS = 8, CP_UNROLL = 8;
 
-__global__ void __launch_bounds__(256)
-k_mat_col_topk_mean(const float* __restrict__ mat, long long ld, int n_rows, int n_cols, int k, float* __restrict__ out_mean) {
-    __shared__ float T[CT_COLS * CT_LD];     // transposed tile: T[col][row]
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int col0 = blockIdx.x * CT_COLS;
-    float lv[16], tau[16];                   // warp w owns columns w*16 .. w*16+15; lane l holds entry l of each list
+template <int KCAP>
+__device__ __forceinline__ void reg_list_insert(float (&L)[KCAP], float x) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) { lv[i] = -FLT_MAX; tau[i] = -FLT_MAX; }
-    for (int r0 = 0; r0 < n_rows; r0 += CT_ROWS) {
-        __syncthreads();
-        // load CT_ROWS × CT_COLS, coalesced along the row; thread → (row = tid / 128 + 2·i, col = tid % 128)
-#pragma unroll 4
-        for (int i = 0; i < CT_ROWS / 2; ++i) {
-            const int rr = (tid >> 7) + 2 * i, cc = tid & 127;
-            const int r = r0 + rr, c = col0 + cc;
-            T[cc * CT_LD + rr] = (r < n_rows && c < n_cols) ? __ldg(mat + (size_t)r * ld + c) : -FLT_MAX;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const float* colp = T + (warp * 16 + i) * CT_LD;
-            list_insert_vals(colp[lane], lv[i], tau[i], k, lane);
-            list_insert_vals(colp[lane + 32], lv[i], tau[i], k, lane);
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        float s = lane < k ? lv[i] : 0.f;
-        s = warp_sum(s);
-        const int c = col0 + warp * 16 + i;
-        if (lane == 0 && c < n_cols) out_mean[c] = s / (float)k;
+    for (int i = 0; i < KCAP; ++i) {
+        const float hi = fmaxf(L[i], x);
+        x = fminf(L[i], x);
+        L[i] = hi;
     }
 }
 
+template <int KCAP, int CPT>
+__global__ void __launch_bounds__(CP_WARPS * 32)
+k_mat_col_topk_partial(const float* __restrict__ mat, long long ld, int n_rows, int n_cols, int rows_per_split,
+                       float* __restrict__ part, long long ldp) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c0 = (blockIdx.x * 32 + lane) * CPT;
+    const int split = blockIdx.y * CP_WARPS + warp;
+    const int r0 = split * rows_per_split;
+    const int r1 = min(n_rows, r0 + rows_per_split);
+    float L[CPT][KCAP];
+#pragma unroll
+    for (int q = 0; q < CPT; ++q)
+#pragma unroll
+        for (int i = 0; i < KCAP; ++i) L[q][i] = -FLT_MAX;
+    if (c0 < n_cols) {
+        const float* src = mat + (size_t)r0 * ld + c0;
+        for (int r = r0; r < r1; r += CP_UNROLL) {
+            float v[CP_UNROLL][CPT];
+#pragma unroll
+            for (int u = 0; u < CP_UNROLL; ++u) {
+                if (r + u < r1) {
+                    if (CPT == 4) {
+                        const float4 t = ldg4(src + (size_t)u * ld);
+                        v[u][0] = t.x; v[u][1] = t.y; v[u][CPT - 2] = t.z; v[u][CPT - 1] = t.w;
+                    } else {
+                        const float2 t = __ldg(reinterpret_cast<const float2*>(src + (size_t)u * ld));
+                        v[u][0] = t.x; v[u][CPT - 1] = t.y;
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < CPT; ++q) v[u][q] = -FLT_MAX;
+                }
+            }
+            src += (size_t)CP_UNROLL * ld;
+#pragma unroll
+            for (int u = 0; u < CP_UNROLL; ++u)
+#pragma unroll
+                for (int q = 0; q < CPT; ++q)
+                    if (v[u][q] > L[q][KCAP - 1]) reg_list_insert<KCAP>(L[q], v[u][q]);
+        }
+    }
+    // columns past n_cols inside the padded leading dimension hold whatever the store pass left: never written out
+#pragma unroll
+    for (int q = 0; q < CPT; ++q) {
+        const int c = c0 + q;
+        if (c < n_cols) {
+#pragma unroll
+            for (int i = 0; i < KCAP; ++i) part[((size_t)split * KCAP + i) * ldp + c] = L[q][i];
+        }
+    }
+}
+
+// Fold the S per-split lists of a column: 32 columns per CTA, 8 threads per column each folding every 8th split,
+// then one of them folds the 8 intermediate lists (shared memory).  Reads are 128 contiguous bytes per warp.
+template <int KCAP>
+__global__ void __launch_bounds__(256)
+k_col_partial_merge(const float* __restrict__ part, long long ldp, int n_cols, int n_splits, int k, float* __restrict__ out_mean) {
+    __shared__ float s_lists[8][KCAP][32];
+    const int cx = threadIdx.x & 31, sg = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cx;
+    float M[KCAP];
+#pragma unroll
+    for (int i = 0; i < KCAP; ++i) M[i] = -FLT_MAX;
+    if (c < n_cols) {
+        for (int sidx = sg; sidx < n_splits; sidx += 8) {
+#pragma unroll
+            for (int i = 0; i < KCAP; ++i) {
+                const float x = __ldg(part + ((size_t)sidx * KCAP + i) * ldp + c);
+                if (x > M[KCAP - 1]) reg_list_insert<KCAP>(M, x);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < KCAP; ++i) s_lists[sg][i][cx] = M[i];
+    __syncthreads();
+    if (sg != 0 || c >= n_cols) return;
+    for (int g = 1; g < 8; ++g) {
+#pragma unroll
+        for (int i = 0; i < KCAP; ++i) {
+            const float x = s_lists[g][i][cx];
+            if (x > M[KCAP - 1]) reg_list_insert<KCAP>(M, x);
+        }
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < KCAP; ++i) if (i < k) sum += M[i];
+    out_mean[c] = sum / (float)k;
+}
+
+static int col_kcap(int k) { return k <= 4 ? 4 : (k <= 8 ? 8 : (k <= 10 ? 10 : (k <= 16 ? 16 : 32))); }
+static int col_cpt(int kcap) { return kcap <= 16 ? 4 : 2; }
+// row splits: 8 per CTA row; enough CTAs for two per SM, but at least 64 rows per split
+static int col_grid_y(int n_rows, int n_cols, int cpt) {
+    const int groups = (n_cols + 32 * cpt - 1) / (32 * cpt);
+    int gy = (2 * sm_count() + groups - 1) / groups;
+    if (gy < 1) gy = 1;
+    if (gy > 16) gy = 16;
+    while (gy > 1 && (n_rows + gy * CP_WARPS - 1) / (gy * CP_WARPS) < 64) --gy;
+    return gy;
+}
+
+// arg-max and rank of the gold column over one stored row (warp per row, 128-bit loads).  Rank rule of
+// calculate_rank's argsort (alignment.py:146-168, "lower index wins"): #{v > gold} + #{v == gold, j < gold column};
+// left of the gold column that is one ≥ test, right of it one > test, so only the group holding it takes the general
+// rule.  The running maximum is updated through a per-group max first (updates are rare after the first groups).
 __global__ void __launch_bounds__(256)
 k_mat_rank(const float* __restrict__ mat, long long ld, int n_rows, int n_cols, const float* __restrict__ row_off,
            const float* __restrict__ col_off, const int* __restrict__ gold, int* __restrict__ out_top1, int* __restrict__ out_rank) {
@@ -776,11 +1010,35 @@ k_mat_rank(const float* __restrict__ mat, long long ld, int n_rows, int n_cols, 
     if (csls) gval = csls_value(gval, ro, __ldg(col_off + g));
     int cnt = 0, besti = 0x7fffffff;
     float bestv = -FLT_MAX;
-    for (int j = lane; j < n_cols; j += 32) {
+    const bool vec = (ld & 3) == 0 && aligned16(mat) && (!csls || aligned16(col_off));
+    const int n4 = vec ? (n_cols >> 2) : 0;
+    for (int j4 = lane; j4 < n4; j4 += 32) {
+        const int j = 4 * j4;
+        float4 v = ldg4(src + j);
+        if (csls) {
+            const float4 co = ldg4(col_off + j);
+            v = fma4(v, 2.f, f4(-ro)) - co;          // (2·s − r) − c, the rounding of csls_value
+        }
+        if (j + 3 < g) cnt += (v.x >= gval) + (v.y >= gval) + (v.z >= gval) + (v.w >= gval);
+        else if (j > g) cnt += (v.x > gval) + (v.y > gval) + (v.z > gval) + (v.w > gval);
+        else {
+            cnt += (v.x > gval) || (v.x == gval && j < g);
+            cnt += (v.y > gval) || (v.y == gval && j + 1 < g);
+            cnt += (v.z > gval) || (v.z == gval && j + 2 < g);
+            cnt += (v.w > gval) || (v.w == gval && j + 3 < g);
+        }
+        if (fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)) > bestv) {      // columns ascend per lane: first maximum kept
+            if (v.x > bestv) { bestv = v.x; besti = j; }
+            if (v.y > bestv) { bestv = v.y; besti = j + 1; }
+            if (v.z > bestv) { bestv = v.z; besti = j + 2; }
+            if (v.w > bestv) { bestv = v.w; besti = j + 3; }
+        }
+    }
+    for (int j = 4 * n4 + lane; j < n_cols; j += 32) {
         float v = __ldg(src + j);
         if (csls) v = csls_value(v, ro, __ldg(col_off + j));
         cnt += (v > gval) || (v == gval && j < g);
-        if (v > bestv) { bestv = v; besti = j; }          // j ascends per lane: first maximum kept
+        if (v > bestv) { bestv = v; besti = j; }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -792,16 +1050,105 @@ k_mat_rank(const float* __restrict__ mat, long long ld, int n_rows, int n_cols, 
     if (lane == 0) { out_rank[row] = cnt; out_top1[row] = besti; }
 }
 
+// Hits@k counts, Σ(rank+1) and Σ1/(rank+1) of a rank vector in one launch (alignment.py:55-69 does this on the host).
+// out[0..n_top) = #{rank < top_k[i]}, out[n_top] = Σ(rank+1), out[n_top+1] = Σ 1/(rank+1); fp64, zeroed by the caller.
+constexpr int STATS_MAX_TOP = 8;
+struct TopKs { int v[STATS_MAX_TOP]; };
+__global__ void __launch_bounds__(256)
+k_rank_stats(const int* __restrict__ rank, int n, TopKs tk, int n_top, double* __restrict__ out) {
+    __shared__ double s_acc[8][STATS_MAX_TOP + 2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int hits[STATS_MAX_TOP];
+#pragma unroll
+    for (int i = 0; i < STATS_MAX_TOP; ++i) hits[i] = 0;
+    double mr = 0.0, mrr = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int r = __ldg(rank + i);
+#pragma unroll
+        for (int t = 0; t < STATS_MAX_TOP; ++t) hits[t] += (t < n_top && r < tk.v[t]);
+        mr += (double)(r + 1);
+        mrr += 1.0 / (double)(r + 1);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int t = 0; t < STATS_MAX_TOP; ++t) hits[t] += __shfl_xor_sync(OEA_FULL, hits[t], o);
+        mr += __shfl_xor_sync(OEA_FULL, mr, o);
+        mrr += __shfl_xor_sync(OEA_FULL, mrr, o);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int t = 0; t < STATS_MAX_TOP; ++t) s_acc[warp][t] = (double)hits[t];
+        s_acc[warp][STATS_MAX_TOP] = mr; s_acc[warp][STATS_MAX_TOP + 1] = mrr;
+    }
+    __syncthreads();
+    if (threadIdx.x < STATS_MAX_TOP + 2) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += s_acc[w][threadIdx.x];
+        const int slot = threadIdx.x < STATS_MAX_TOP ? threadIdx.x : n_top + (threadIdx.x - STATS_MAX_TOP);
+        if (threadIdx.x >= STATS_MAX_TOP || threadIdx.x < n_top) atomicAdd(out + slot, t);
+    }
+}
+
 }  // namespace oea
 
+extern "C" size_t oea_matrix_topk_mean_workspace_bytes(int32_t n_rows, int32_t n_cols, int32_t k, int32_t by_column) {
+    if (!by_column || n_rows <= 0 || n_cols <= 0 || k < 1 || k > KMAX) return 0;
+    const int kcap = col_kcap(k), cpt = col_cpt(kcap);
+    const int gy = col_grid_y(n_rows, n_cols, cpt);
+    const size_t ldp = ((size_t)n_cols + 3) / 4 * 4;
+    return (size_t)gy * CP_WARPS * kcap * ldp * sizeof(float);
+}
+
 extern "C" int oea_matrix_topk_mean(const float* mat, int64_t ld, int32_t n_rows, int32_t n_cols, int32_t k,
-                                    int32_t by_column, float* out_mean, void* stream) {
+                                    int32_t by_column, float* out_mean, void* workspace, size_t workspace_bytes,
+                                    void* stream) {
     if (!mat || !out_mean) return OEA_ERR_NULL;
     if (n_rows <= 0 || n_cols <= 0 || ld < n_cols || (ld & 3) || !aligned16(mat)) return OEA_ERR_SHAPE;
     if (k < 1 || k > KMAX || k > (by_column ? n_rows : n_cols)) return OEA_ERR_RANGE;
     cudaStream_t st = (cudaStream_t)stream;
-    if (by_column) k_mat_col_topk_mean<<<(n_cols + CT_COLS - 1) / CT_COLS, 256, 0, st>>>(mat, ld, n_rows, n_cols, k, out_mean);
-    else k_mat_row_topk_mean<<<(n_rows + 7) / 8, 256, 0, st>>>(mat, ld, n_rows, n_cols, k, out_mean);
+    if (!by_column) {
+        k_mat_row_topk_mean<<<(n_rows + 7) / 8, 256, 0, st>>>(mat, ld, n_rows, n_cols, k, out_mean);
+        OEA_LAUNCH_CHECK();
+        return OEA_OK;
+    }
+    const size_t need = oea_matrix_topk_mean_workspace_bytes(n_rows, n_cols, k, 1);
+    if (!workspace || workspace_bytes < need || !aligned16(workspace)) return OEA_ERR_WORKSPACE;
+    const int kcap = col_kcap(k), cpt = col_cpt(kcap);
+    const int gy = col_grid_y(n_rows, n_cols, cpt);
+    const int n_splits = gy * CP_WARPS;
+    const int rows_per_split = (n_rows + n_splits - 1) / n_splits;
+    const long long ldp = ((long long)n_cols + 3) / 4 * 4;
+    float* part = (float*)workspace;
+    const dim3 grid((n_cols + 32 * cpt - 1) / (32 * cpt), gy);
+#define OEA_COL_LAUNCH(KC, CP)                                                                                         \
+    do {                                                                                                               \
+        k_mat_col_topk_partial<KC, CP><<<grid, CP_WARPS * 32, 0, st>>>(mat, ld, n_rows, n_cols, rows_per_split, part, ldp); \
+        k_col_partial_merge<KC><<<(n_cols + 31) / 32, 256, 0, st>>>(part, ldp, n_cols, n_splits, k, out_mean);        \
+    } while (0)
+    switch (kcap) {
+        case 4: OEA_COL_LAUNCH(4, 4); break;
+        case 8: OEA_COL_LAUNCH(8, 4); break;
+        case 10: OEA_COL_LAUNCH(10, 4); break;
+        case 16: OEA_COL_LAUNCH(16, 4); break;
+        default: OEA_COL_LAUNCH(32, 2); break;
+    }
+#undef OEA_COL_LAUNCH
+    OEA_LAUNCH_CHECK();
+    return OEA_OK;
+}
+
+extern "C" int oea_rank_stats(const int32_t* rank, int32_t n, const int32_t* top_k_host, int32_t n_top, double* out,
+                              void* stream) {
+    if (!rank || !out || (n_top > 0 && !top_k_host)) return OEA_ERR_NULL;
+    if (n <= 0 || n_top < 0 || n_top > STATS_MAX_TOP) return OEA_ERR_RANGE;
+    TopKs tk{};
+    for (int i = 0; i < n_top; ++i) tk.v[i] = top_k_host[i];
+    cudaStream_t st = (cudaStream_t)stream;
+    OEA_CUDA_TRY(cudaMemsetAsync(out, 0, (size_t)(n_top + 2) * sizeof(double), st));
+    int blocks = (n + 255) / 256;
+    if (blocks > 2 * sm_count()) blocks = 2 * sm_count();
+    k_rank_stats<<<blocks, 256, 0, st>>>(rank, n, tk, n_top, out);
     OEA_LAUNCH_CHECK();
     return OEA_OK;
 }

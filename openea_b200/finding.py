@@ -154,8 +154,11 @@ def _eval_materialized(e1, e2, d, metric, csls_k, gold):
     L.check(lib.oea_sim_matrix(C.byref(cfg), _ptr(e1), _ptr(e2), None, None, _ptr(s), ld, st), "oea_sim_matrix")
     r = torch.empty(n1, dtype=torch.float32, device=e1.device)
     c = torch.empty(n2, dtype=torch.float32, device=e1.device)
-    L.check(lib.oea_matrix_topk_mean(_ptr(s), ld, n1, n2, csls_k, 0, _ptr(r), st), "oea_matrix_topk_mean")
-    L.check(lib.oea_matrix_topk_mean(_ptr(s), ld, n1, n2, csls_k, 1, _ptr(c), st), "oea_matrix_topk_mean")
+    L.check(lib.oea_matrix_topk_mean(_ptr(s), ld, n1, n2, csls_k, 0, _ptr(r), None, 0, st), "oea_matrix_topk_mean")
+    ws_bytes = lib.oea_matrix_topk_mean_workspace_bytes(n1, n2, csls_k, 1)
+    ws = torch.empty(max(16, ws_bytes), dtype=torch.uint8, device=e1.device)
+    L.check(lib.oea_matrix_topk_mean(_ptr(s), ld, n1, n2, csls_k, 1, _ptr(c), _ptr(ws), ws_bytes, st),
+            "oea_matrix_topk_mean")
     top1 = torch.empty(n1, dtype=torch.int32, device=e1.device)
     rk = torch.empty(n1, dtype=torch.int32, device=e1.device)
     L.check(lib.oea_matrix_rank(_ptr(s), ld, n1, n2, _ptr(r), _ptr(c), _ptr(gold), _ptr(top1), _ptr(rk), st),
@@ -182,11 +185,25 @@ def eval_alignment(embed1, embed2, top_k, metric, normalize, csls_k, gold=None, 
         if csls_k > 0:
             r, c = csls_offsets(e1, e2, d, metric, csls_k, tc)
         top1, rk = rank(e1, e2, d, metric, gold, r, c, tc=tc)
-    rk64 = rk.to(torch.float64)
-    hits = [round(float((rk < k).sum().item()) / n1 * 100, 3) for k in top_k]
-    mr = float((rk64 + 1).sum().item() / n1)
-    mrr = float((1.0 / (rk64 + 1)).sum().item() / n1)
+    hits, mr, mrr = rank_stats(rk, top_k)
     return top1, rk, hits, mr, mrr
+
+
+def rank_stats(rk, top_k):
+    """Hits@k (percent, 3 dp as alignment.py:66-69), MR and MRR of a device rank vector: one kernel, one D2H copy."""
+    lib = L.load()
+    n = rk.shape[0]
+    ks = [int(k) for k in top_k]
+    hits, sums = [], None
+    for lo in range(0, max(1, len(ks)), 8):          # the kernel takes up to 8 thresholds per launch
+        chunk = ks[lo:lo + 8]
+        arr = (C.c_int32 * max(1, len(chunk)))(*chunk)
+        out = torch.empty(len(chunk) + 2, dtype=torch.float64, device=rk.device)
+        L.check(lib.oea_rank_stats(_ptr(rk), n, arr, len(chunk), _ptr(out), _stream_ptr()), "oea_rank_stats")
+        vals = out.tolist()
+        hits += [round(v / n * 100, 3) for v in vals[:len(chunk)]]
+        sums = vals[len(chunk):]
+    return hits, float(sums[0] / n), float(sums[1] / n)
 
 
 def greedy_alignment(embed1, embed2, top_k, nums_threads, metric, normalize, csls_k, accurate):

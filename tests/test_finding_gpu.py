@@ -146,3 +146,63 @@ def test_rdgcn_get_neg_matches_cdist_argsort(cuda_device):
     want = np.argsort(sim, axis=1, kind="stable")[:, :k]
     assert (got[:, 0] == ill).all()
     assert (got == want).mean() > 0.999          # fp32 vs fp64 distances: only near-ties may swap
+
+
+@pytest.mark.parametrize("d", [3, 12, 75, 100, 104])
+@pytest.mark.parametrize("metric", ["inner", "euclidean", "manhattan"])
+def test_resident_panel_store_kernel_is_bit_identical_to_streaming_kernel(cuda_device, monkeypatch, d, metric):
+    """k_sim_store_shortk (A panel resident, two half-K stages per column tile) accumulates in the same ascending-k
+    order as k_sim_tile, so the stored matrix — plain and with CSLS offsets — is bit-identical; shapes cover ragged
+    row/column tiles and several column splits."""
+    rng = np.random.default_rng(1000 + d)
+    n1, n2 = 389, 1301
+    e1 = rng.standard_normal((n1, d)).astype(np.float32)
+    e2 = rng.standard_normal((n2, d)).astype(np.float32)
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("OEA_SIM_NO_SHORTK", mode)
+        out[mode] = (F().sim(e1, e2, metric, False, 0).cpu().numpy(), F().sim(e1, e2, metric, False, 5).cpu().numpy())
+    assert np.array_equal(out["0"][0], out["1"][0])
+    assert np.array_equal(out["0"][1], out["1"][1])
+    want = orf.sim(e1, e2, metric, False)
+    np.testing.assert_allclose(out["0"][0], want, rtol=2e-5, atol=3e-5)
+
+
+@pytest.mark.parametrize("n_rows,n_cols", [(700, 1301), (70, 37), (2100, 129)])
+@pytest.mark.parametrize("k", [1, 3, 8, 10, 16, 25, 32])
+def test_matrix_column_and_row_topk_mean_every_list_size(cuda_device, n_rows, n_cols, k):
+    """oea_matrix_topk_mean on a stored matrix: register-list column kernel (every KCAP instantiation, ragged last
+    column group, padded leading dimension holding garbage) + partial merge, and the row kernel, against NumPy."""
+    import ctypes as C
+    from openea_b200 import lib as L
+    from openea_b200.engine import _ptr, _stream_ptr
+    lib = L.load()
+    rng = np.random.default_rng(k * 1000 + n_cols)
+    m = rng.standard_normal((n_rows, n_cols)).astype(np.float32)
+    m[rng.integers(0, n_rows, 50), rng.integers(0, n_cols, 50)] = 3.5      # ties among the largest
+    ld = (n_cols + 3) // 4 * 4
+    dev = torch.full((n_rows, ld), 1e30, dtype=torch.float32, device="cuda")   # padding must never be read as data
+    dev[:, :n_cols] = torch.from_numpy(m).cuda()
+    for by_col in (0, 1):
+        n_out = n_cols if by_col else n_rows
+        if k > (n_rows if by_col else n_cols):
+            continue
+        out = torch.empty(n_out, dtype=torch.float32, device="cuda")
+        nbytes = lib.oea_matrix_topk_mean_workspace_bytes(n_rows, n_cols, k, by_col)
+        ws = torch.empty(max(16, nbytes), dtype=torch.uint8, device="cuda")
+        L.check(lib.oea_matrix_topk_mean(_ptr(dev), ld, n_rows, n_cols, k, by_col, _ptr(out), _ptr(ws), nbytes, _stream_ptr()))
+        a = m.T if by_col else m
+        want = -np.sort(-a, axis=1)[:, :k].astype(np.float64).mean(1)
+        np.testing.assert_allclose(out.cpu().numpy(), want, rtol=1e-5, atol=1e-6)
+
+
+def test_rank_stats_kernel_matches_numpy(cuda_device):
+    rng = np.random.default_rng(3)
+    rk = np.minimum(rng.geometric(0.05, 10500) - 1, 10499).astype(np.int32)
+    hits, mr, mrr = F().rank_stats(torch.from_numpy(rk).cuda(), [1, 5, 10, 50])
+    want_hits = [round(float((rk < k).sum()) / len(rk) * 100, 3) for k in [1, 5, 10, 50]]
+    assert hits == want_hits
+    assert mr == pytest.approx(float((rk + 1).mean()), rel=1e-12)
+    assert mrr == pytest.approx(float((1.0 / (rk + 1)).mean()), rel=1e-12)
+    hits9, _, _ = F().rank_stats(torch.from_numpy(rk).cuda(), list(range(1, 12)))    # more than 8 thresholds: two launches
+    assert hits9 == [round(float((rk < k).sum()) / len(rk) * 100, 3) for k in range(1, 12)]
