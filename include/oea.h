@@ -172,6 +172,50 @@ int oea_triple_step_fed_host(const oea_table* ent, const oea_table* rel,
                              int32_t* dev_idx_ws, double* dev_loss_ws, double* loss_pinned_host,
                              float* loss_host, void* stream);
 
+/* ---- path (i), SURVEY §8f-2: the other score functions of the reference's models/ ------------------------ */
+
+/* Which score function a fed step evaluates and which tables it reads:
+ *   TRANSE    Σ|ĥ + r̂ − t̂| or Σ(·)²                              models/trans/transe.py:33-45
+ *   TRANSH    the same on e⊥ = e − <e, n̂>n̂, n̂ = l2_normalize(normal_vector[r])   models/trans/transh.py:25-51,
+ *                                                                  approaches/bootea_transh.py:57-95
+ *   TRANSD    the same on e⊥ = l2_normalize(e + <e, e_p>·r_p)      models/trans/transd.py:26-65
+ *   DISTMULT  similarity Σ ĥ∘r̂∘t̂                                  models/semantic/distmult.py:43-59
+ *   SIMPLE    (Σ l2n(h_H∘r₁)∘t_T + Σ l2n(t_H∘r₂)∘h_T)/2            models/semantic/simple.py:50-86
+ * The two similarity models are scored as energies E = −similarity, so OEA_LOSS_LOGISTIC gives their
+ * softplus(−score⁺) + softplus(score⁻). */
+enum { OEA_MODEL_TRANSE = 0, OEA_MODEL_TRANSH = 1, OEA_MODEL_TRANSD = 2, OEA_MODEL_DISTMULT = 3, OEA_MODEL_SIMPLE = 4 };
+
+typedef struct oea_model {
+    int32_t kind;              /* OEA_MODEL_* */
+    const oea_table* ent;      /* ent_embeds                                 | SIMPLE: head_ent_embeds */
+    const oea_table* rel;      /* rel_embeds                                 | SIMPLE: rel_embeds1 */
+    const oea_table* ent_aux;  /* TRANSD: ent_transfer                       | SIMPLE: tail_ent_embeds | else NULL */
+    const oea_table* rel_aux;  /* TRANSH: normal_vector, TRANSD: rel_transfer | SIMPLE: rel_embeds2   | else NULL */
+} oea_model;
+
+/* oea_triple_score_fed for any oea_model: gathers the 3–6 rows of every triple, scores it, evaluates the loss of
+ * modules/base/losses.py and scatter-adds d(loss)/d(raw variable) into the grad of every table involved (setting
+ * `touched`).  MARGIN pairs positive i with negative i (n_pos == n_neg).  loss_scale multiplies loss and gradient
+ * (1 for TF's reduce_sum losses; 1/(n_pos+n_neg) for DistMult's reduce_mean, distmult.py:58).
+ * All tables share dim and pitch, pitch <= 256.  Run oea_rowopt_apply on every table afterwards. */
+int oea_model_score_fed(const oea_model* model,
+                        const int32_t* pos_h, const int32_t* pos_r, const int32_t* pos_t, int32_t n_pos,
+                        const int32_t* neg_h, const int32_t* neg_r, const int32_t* neg_t, int32_t n_neg,
+                        const oea_loss_cfg* loss, float loss_scale, double* loss_out, void* stream);
+
+/* The batch producer of modules/train/batch.py:36-45 (generate_relation_triple_batch) / :168-184
+ * (generate_triple_label_batch) on the device: writes the index vectors a fed step takes.
+ *   pos_hrt [3, n_pos] (h | r | t rows), neg_hrt [3, n_pos·neg_per_pos] (negatives of positive p at p·k … p·k+k−1),
+ *   n_pos = positives of this step (slice arithmetic of batch.py:39-42,48-53), returned in *n_pos_host (HOST int).
+ * sampler 0 = generate_neg_triples_fast (batch.py:89-119, as in oea_triple_score_sampled);
+ * sampler 1 = generate_neg_triples (batch.py:60-86): every negative flips its own coin and draws one candidate
+ *             with replacement per try; after max_try rejections the tail is replaced by a uniform entity of the KG.
+ * `warm` (optional): an entity table whose sampled rows are prefetched into L2 for the scoring kernel that follows.
+ * Both buffers must hold batch_size (·neg_per_pos) columns; their row stride is n_pos (·neg_per_pos). */
+int oea_triple_sample_batch(const oea_kg_view* kg1, const oea_kg_view* kg2, const oea_tripleset* tset,
+                            const oea_sample_cfg* smp, int32_t sampler, const oea_table* warm,
+                            int32_t* pos_hrt, int32_t* neg_hrt, int32_t* n_pos_host, void* stream);
+
 /* Normalised view of a table (what TF returns for `ent_embeds` when is_l2_norm):
  * out[i, :dim] = normalise(weight[ids[i]]) (ids == NULL → all rows).  Replaces
  * tf.nn.embedding_lookup(self.ent_embeds, ids).eval() of basic_model.py:106-121,185,198-204. */

@@ -301,6 +301,85 @@ class TripleTrainer:
         return v
 
 
+MODEL_KINDS = {"TransE": L.MODEL_TRANSE, "TransH": L.MODEL_TRANSH, "TransD": L.MODEL_TRANSD,
+               "DistMult": L.MODEL_DISTMULT, "SimplE": L.MODEL_SIMPLE}
+
+
+class ModelTrainer:
+    """Forward/backward + optimiser for the score functions beyond plain translation (oea_model_score_fed):
+    TransH / TransD / DistMult / SimplE graphs of the reference's models/ (SURVEY §8f-2).
+
+    tables = (ent, rel, ent_aux, rel_aux) EmbeddingTables in the slot order of `oea_model` (None where a model has
+    no such table).  A step = device batch producer (oea_triple_sample_batch) → fed scorer → one row-optimiser
+    launch per table; `mean_loss` applies DistMult's reduce_mean (distmult.py:58)."""
+
+    def __init__(self, model, tables, loss, lr, mean_loss=False, sampler="fast"):
+        self.lib = L.load()
+        self.kind = MODEL_KINDS[model]
+        self.tables = tuple(tables) + (None,) * (4 - len(tables))
+        self.live = [t for t in self.tables if t is not None]
+        self.loss, self.lr = loss, float(lr)
+        self.mean_loss = bool(mean_loss)
+        self.sampler = {"fast": 0, "independent": 1}[sampler]
+        dev = self.tables[0].device
+        self.loss_dev = torch.zeros(1, dtype=torch.float64, device=dev)
+        self._idx = None
+        self._n_pos = C.c_int32(0)
+
+    def _c_model(self):
+        # the Table structs are owned by the EmbeddingTables (cached there), so the pointers stay valid
+        ptr = lambda t: C.pointer(t.c_struct()) if t is not None else None
+        return L.Model(self.kind, *[ptr(t) for t in self.tables])
+
+    def score_fed(self, pos, neg=None, loss_out=None):
+        """pos / neg: int32 device tensors [3, n] (h | r | t rows); accumulates gradients into every table and adds
+        the batch loss into loss_out (default self.loss_dev)."""
+        out = self.loss_dev if loss_out is None else loss_out
+        n_pos = pos.shape[1]
+        n_neg = 0 if neg is None else neg.shape[1]
+        scale = 1.0 / max(1, n_pos + n_neg) if self.mean_loss else 1.0
+        np_ = lambda t, i: C.c_void_p(0 if t is None or t.shape[1] == 0 else t[i].data_ptr())
+        model = self._c_model()
+        L.check(self.lib.oea_model_score_fed(
+            C.byref(model), np_(pos, 0), np_(pos, 1), np_(pos, 2), n_pos, np_(neg, 0), np_(neg, 1), np_(neg, 2), n_neg,
+            C.byref(self.loss), scale, _ptr(out), _stream_ptr()), "oea_model_score_fed")
+
+    def apply(self):
+        for tab in self.live:
+            tab.apply(self.lr)
+
+    def sample_batch(self, kg1, kg2, tset, batch_size, neg_per_pos, step, epoch_seed, max_try=10):
+        """The device batch producer: returns (pos [3, n_pos], neg [3, n_pos·k] or None) int32 device tensors."""
+        need = 3 * batch_size * (1 + neg_per_pos)
+        if self._idx is None or self._idx.numel() < need:
+            self._idx = torch.empty(need, dtype=torch.int32, device=self.tables[0].device)
+        smp = L.SampleCfg(int(batch_size), int(neg_per_pos), int(step), int(max_try), int(epoch_seed) & (2**64 - 1), 0)
+        k1, k2, ts = kg1.view(), kg2.view(), tset.view()
+        pos_buf, neg_buf = self._idx[:3 * batch_size], self._idx[3 * batch_size:]
+        L.check(self.lib.oea_triple_sample_batch(
+            C.byref(k1), C.byref(k2), C.byref(ts), C.byref(smp), self.sampler, C.byref(self.tables[0].c_struct()),
+            _ptr(pos_buf), _ptr(neg_buf), C.byref(self._n_pos), _stream_ptr()), "oea_triple_sample_batch")
+        n = int(self._n_pos.value)
+        pos = pos_buf[:3 * n].view(3, n)
+        neg = neg_buf[:3 * n * neg_per_pos].view(3, n * neg_per_pos) if neg_per_pos > 0 else None
+        return pos, neg
+
+    def step_sampled(self, kg1, kg2, tset, batch_size, neg_per_pos, step, epoch_seed, max_try=10, **_):
+        """One whole training step (what one session.run([triple_loss, triple_optimizer]) does)."""
+        pos, neg = self.sample_batch(kg1, kg2, tset, batch_size, neg_per_pos, step, epoch_seed, max_try)
+        if pos.shape[1] == 0:
+            return 0
+        self.score_fed(pos, neg)
+        self.apply()
+        return pos.shape[1]
+
+    def read_loss(self, reset=True):
+        v = float(self.loss_dev.item())
+        if reset:
+            self.loss_dev.zero_()
+        return v
+
+
 def _as_host_i32(a):
     if isinstance(a, torch.Tensor):
         assert a.dtype == torch.int32 and not a.is_cuda and a.is_contiguous()

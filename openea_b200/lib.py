@@ -14,6 +14,7 @@ SCORE_L1, SCORE_L2SQ = 0, 1
 LOSS_MARGIN, LOSS_LIMITED, LOSS_LOGISTIC, LOSS_POSITIVE, LOSS_LOGSIGMOID = 0, 1, 2, 3, 4
 OPT_SGD, OPT_ADAGRAD, OPT_ADAM = 0, 1, 2
 METRIC_INNER, METRIC_L1, METRIC_L2 = 0, 1, 2
+MODEL_TRANSE, MODEL_TRANSH, MODEL_TRANSD, MODEL_DISTMULT, MODEL_SIMPLE = 0, 1, 2, 3, 4
 
 
 class OeaError(RuntimeError):
@@ -69,6 +70,11 @@ class Csr(C.Structure):
 _P, _I, _L = C.c_void_p, C.c_int32, C.c_int64
 _TP = C.POINTER(Table)
 
+
+class Model(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("ent", _TP), ("rel", _TP), ("ent_aux", _TP), ("rel_aux", _TP)]
+
+
 # name → (restype, argtypes).  Must list every symbol include/oea.h declares (tests check this).
 SIGNATURES = {
     "oea_abi_version": (C.c_int, []),
@@ -110,6 +116,10 @@ SIGNATURES = {
     "oea_edge_softmax_bwd": (C.c_int, [C.POINTER(Csr), _P, _P, C.c_float, _P, _P, _P, _P, _P]),
     "oea_align_loss_l1": (C.c_int, [_P, _I, _I, _P, _P, _I, _I, _P, _P, _P, _P, C.c_float, _P, _P, _P]),
     "oea_tripleset_build": (C.c_int, [_P, _I, _P, C.c_uint32, C.c_uint32, C.c_uint32, _P]),
+    "oea_model_score_fed": (C.c_int, [C.POINTER(Model), _P, _P, _P, _I, _P, _P, _P, _I, C.POINTER(LossCfg), C.c_float,
+                                      _P, _P]),
+    "oea_triple_sample_batch": (C.c_int, [C.POINTER(KgView), C.POINTER(KgView), C.POINTER(TripleSet),
+                                          C.POINTER(SampleCfg), _I, _TP, _P, _P, C.POINTER(C.c_int32), _P]),
 }
 
 _lib = None

@@ -1,0 +1,237 @@
+"""GPU parity tests of the projected / bilinear score family (oea_model_score_fed) and of the device batch producer
+(oea_triple_sample_batch), through the C-ABI, against oracle/triple_ext.py on identical fed index batches.
+Tolerances as in tests/test_triple_gpu.py: 1e-4 relative on the fp32 loss, 1e-4 relative (+ a floor tied to the
+gradient scale) on per-row gradients and updated tables; L1 sign gradients by counting disagreeing coordinates."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import triple_ext as ox
+from tests.helpers import make_batch
+
+pytestmark = pytest.mark.gpu
+
+LOSS_TOL = 1e-4
+
+
+def _engine():
+    from openea_b200 import engine
+    return engine
+
+
+def _dev(hrt):
+    return None if hrt is None else torch.from_numpy(np.ascontiguousarray(hrt.astype(np.int32))).cuda()
+
+
+def _case(model, seed, n_ent, n_rel, d, norm):
+    rng = np.random.default_rng(seed)
+    slots = ox.SLOTS[model] + (None,) * (4 - len(ox.SLOTS[model]))
+    tabs, norms = {}, {}
+    for i, s in enumerate(slots):
+        if s is None:
+            continue
+        rows = n_rel if i in (1, 3) else n_ent
+        tabs[s] = (rng.standard_normal((rows, d)) * (0.6 + 0.3 * i) / np.sqrt(d)).astype(np.float32)
+        norms[s] = norm
+    if model == "TransH":
+        norms["normal"] = True
+    return rng, slots, tabs, norms
+
+
+def _tables(slots, tabs, norms, opt="Adagrad"):
+    eng = _engine()
+    return tuple(None if s is None else eng.EmbeddingTable(tabs[s], norms[s], opt) for s in slots)
+
+
+def _assert_rows_close(got, want, what):
+    scale = max(1e-6, float(np.abs(want).max()))
+    np.testing.assert_allclose(got, want, rtol=1e-4, atol=2e-5 * scale, err_msg=what)
+
+
+CASES = [("TransE", "limited", 4, "L2"), ("TransE", "margin-based", 1, "L1"),
+         ("TransH", "margin-based", 1, "L2"), ("TransH", "margin-based", 1, "L1"), ("TransH", "limited", 5, "L2"),
+         ("TransD", "margin-based", 1, "L2"), ("TransD", "limited", 3, "L2"), ("TransD", "logistic", 2, "L1"),
+         ("TransD", "positive", 0, "L2"),
+         ("DistMult", "logistic", 3, "L2"), ("SimplE", "logistic", 2, "L2")]
+
+
+@pytest.mark.parametrize("model,loss,k,loss_norm", CASES)
+@pytest.mark.parametrize("norm", [True, False])
+@pytest.mark.parametrize("d", [12, 75, 100, 200])
+def test_model_forward_backward_matches_oracle(cuda_device, model, loss, k, loss_norm, norm, d):
+    eng = _engine()
+    n_ent, n_rel, n_pos = 1500, 29, 400
+    rng, slots, tabs, norms = _case(model, 7 * d + k + len(model), n_ent, n_rel, d, norm)
+    pos, neg = make_batch(rng, n_ent, n_rel, n_pos, k)
+    kw = dict(margin=1.1 if loss == "margin-based" else 0.3, neg_margin=2.2, balance=0.2)
+    mean = model == "DistMult"
+    scale = 1.0 / (n_pos * (1 + k)) if mean else 1.0
+    want_loss, want_g, _ = ox.fwd_bwd(model, tabs, norms, pos, neg, loss, loss_norm=loss_norm, scale=scale, **kw)
+
+    tables = _tables(slots, tabs, norms)
+    tr = eng.ModelTrainer(model, tables, eng.loss_cfg(loss, loss_norm, **kw), lr=0.01, mean_loss=mean)
+    tr.score_fed(_dev(pos), _dev(neg))
+    assert tr.read_loss() == pytest.approx(want_loss, rel=LOSS_TOL)
+    for s, tab in zip(slots, tables):
+        if s is None:
+            continue
+        got = tab.grad[:, :d].cpu().numpy()
+        want = want_g[s]
+        if loss_norm == "L1" and model in ("TransE", "TransH", "TransD"):
+            bad = np.abs(got - want) > 1e-4 * max(1.0, np.abs(want).max())
+            assert bad.mean() < 2e-3, s
+        else:
+            _assert_rows_close(got, want, "%s gradient of %s" % (s, model))
+        assert not tab.grad[:, d:].any().item(), "padding columns must stay zero"
+        touched = tab.touched.cpu().numpy().astype(bool)
+        assert (np.abs(want).sum(1)[~touched] == 0).all(), "untouched rows must have zero oracle gradient"
+
+
+def test_transe_through_the_model_entry_equals_the_k1_kernel(cuda_device):
+    """OEA_MODEL_TRANSE runs the same maths as oea_triple_score_fed: losses and gradients agree to fp32 rounding."""
+    eng = _engine()
+    rng, slots, tabs, norms = _case("TransE", 3, 2000, 31, 100, True)
+    pos, neg = make_batch(rng, 2000, 31, 500, 6)
+    cfg = eng.loss_cfg("limited", "L2", margin=0.2, neg_margin=2.0, balance=0.3)
+    a = _tables(slots, tabs, norms)
+    b = _tables(slots, tabs, norms)
+    ta = eng.ModelTrainer("TransE", a, cfg, lr=0.01)
+    tb = eng.TripleTrainer(b[0], b[1], cfg, lr=0.01)
+    ta.score_fed(_dev(pos), _dev(neg))
+    tb.score_fed(_dev(pos), _dev(neg))
+    assert ta.read_loss() == pytest.approx(tb.read_loss(), rel=1e-6)
+    for x, y in zip(a[:2], b[:2]):
+        np.testing.assert_allclose(x.grad.cpu().numpy(), y.grad.cpu().numpy(), rtol=1e-5, atol=1e-7)
+        assert torch.equal(x.touched, y.touched)
+
+
+@pytest.mark.parametrize("model,loss,k", [("TransH", "margin-based", 1), ("TransD", "limited", 4),
+                                          ("DistMult", "logistic", 2), ("SimplE", "logistic", 2)])
+@pytest.mark.parametrize("opt", ["Adagrad", "SGD"])
+def test_model_training_steps_equal_dense_tf_steps(cuda_device, model, loss, k, opt):
+    """Three full steps (scorer + row optimiser on every table) equal the oracle's dense TF-style steps."""
+    eng = _engine()
+    d, n_ent, n_rel = 100, 1200, 23
+    rng, slots, tabs, norms = _case(model, 11, n_ent, n_rel, d, True)
+    kw = dict(margin=1.0 if loss == "margin-based" else 0.05, neg_margin=1.8, balance=0.25)
+    mean = model == "DistMult"
+    st = ox.DenseState(tabs, opt)
+    tables = _tables(slots, tabs, norms, opt)
+    tr = eng.ModelTrainer(model, tables, eng.loss_cfg(loss, "L2", **kw), lr=0.05, mean_loss=mean)
+    for it in range(3):
+        pos, neg = make_batch(rng, n_ent, n_rel, 300, k)
+        scale = 1.0 / (300 * (1 + k)) if mean else 1.0
+        want = ox.step(st, model, norms, pos, neg, loss, 0.05, scale=scale, **kw)
+        tr.score_fed(_dev(pos), _dev(neg))
+        tr.apply()
+        assert tr.read_loss() == pytest.approx(want, rel=LOSS_TOL), it
+    for s, tab in zip(slots, tables):
+        if s is not None:
+            _assert_rows_close(tab.raw().cpu().numpy(), st.w[s], "%s after 3 steps" % s)
+            assert not tab.grad.any().item() and not tab.touched.any().item()
+
+
+def _tiny_kgs(rng, n_ent_kg=300, n_rel=11, n_tri=2000):
+    """Two KGs over disjoint entity id ranges (0..n) and (n..2n), relation ids shared."""
+    def kg(lo):
+        t = np.stack([rng.integers(lo, lo + n_ent_kg, n_tri), rng.integers(0, n_rel, n_tri),
+                      rng.integers(lo, lo + n_ent_kg, n_tri)], axis=1).astype(np.int32)
+        return np.unique(t, axis=0)
+    return kg(0), kg(n_ent_kg), n_ent_kg
+
+
+@pytest.mark.parametrize("sampler", ["fast", "independent"])
+@pytest.mark.parametrize("k", [0, 1, 7])
+def test_batch_producer_properties(cuda_device, sampler, k):
+    """batch.py:36-119 invariants of the device batch producer: an epoch's positives are a permutation of the triple
+    lists (each KG's share per step as batch.py:39-42), every negative keeps the relation and exactly one end of its
+    positive, the corrupted end comes from the positive's own KG, negatives are (almost never) known triples, the
+    fast sampler's k negatives of one positive are distinct (random.sample), and the same seed reproduces the batch."""
+    eng = _engine()
+    rng = np.random.default_rng(17 + k)
+    t1, t2, n = _tiny_kgs(rng)
+    ent = eng.EmbeddingTable(rng.standard_normal((2 * n, 16)).astype(np.float32), True)
+    rel = eng.EmbeddingTable(rng.standard_normal((11, 16)).astype(np.float32), True)
+    kg1 = eng.DeviceKG(t1, np.arange(0, n), 2 * n)
+    kg2 = eng.DeviceKG(t2, np.arange(n, 2 * n), 2 * n)
+    tset = eng.DeviceTripleSet([kg1.triples, kg2.triples], 2 * n, 11)
+    tr = eng.ModelTrainer("TransE", (ent, rel), eng.loss_cfg("limited", "L2", 0.1, 2.0, 0.2), 0.01, sampler=sampler)
+    B = 512
+    steps = int(np.ceil((len(t1) + len(t2)) / B))
+    b1 = int(len(t1) / (len(t1) + len(t2)) * B)
+    known = {tuple(x) for x in np.concatenate([t1, t2]).tolist()}
+    seen, n_known, n_neg, dup_rows = [], 0, 0, 0
+    for step in range(steps):
+        pos, neg = tr.sample_batch(kg1, kg2, tset, B, k, step, epoch_seed=12345)
+        p = pos.cpu().numpy().T
+        want1 = max(0, min((step + 1) * b1, len(t1)) - min(step * b1, len(t1)))
+        assert (p[:want1, 0] < n).all() and (p[want1:, 0] >= n).all()      # KG1's slice first, then KG2's
+        seen.append(p)
+        first = (pos.clone(), None if neg is None else neg.clone())   # the producer reuses one index buffer
+        pos, neg = tr.sample_batch(kg1, kg2, tset, B, k, step, epoch_seed=12345)
+        assert torch.equal(first[0], pos) and (neg is None or torch.equal(first[1], neg))
+        other, _ = tr.sample_batch(kg1, kg2, tset, B, k, step, epoch_seed=54321)
+        assert other.shape == first[0].shape and not torch.equal(other, first[0])
+        pos, neg = first
+        if k == 0:
+            assert neg is None
+            continue
+        q = neg.cpu().numpy().T.reshape(len(p), k, 3)
+        assert (q[:, :, 1] == p[:, None, 1]).all()
+        same_h, same_t = q[:, :, 0] == p[:, None, 0], q[:, :, 2] == p[:, None, 2]
+        assert (same_h | same_t).all()
+        assert ((q[:, :, 0] < n) == (p[:, None, 0] < n)).all() and ((q[:, :, 2] < n) == (p[:, None, 0] < n)).all()
+        n_known += sum(tuple(x) in known for x in q.reshape(-1, 3).tolist())
+        n_neg += q.shape[0] * k
+        if sampler == "fast" and k > 1:     # random.sample: distinct inside one try (a re-draw after a rejection may repeat)
+            dup_rows += sum(len({tuple(x) for x in row.tolist()}) < k for row in q)
+    allp = np.concatenate(seen)
+    assert len(allp) == len(t1) + len(t2)
+    assert {tuple(x) for x in allp.tolist()} == known                      # a permutation: every triple exactly once
+    if k:
+        assert n_known <= 1e-3 * n_neg + 2                                 # only a last try may keep a known triple
+        assert dup_rows <= 0.01 * len(allp)
+
+
+def test_fast_batch_producer_draws_the_same_negatives_as_the_fused_kernel(cuda_device, monkeypatch):
+    """sampler 0 shares warp_sample_negatives and the positive permutation with k_score_sampled: for one seed the
+    index vectors equal the fused kernel's debug dump."""
+    eng = _engine()
+    monkeypatch.setenv("OEA_SCORE_V1", "1")          # the warp-per-positive fused kernel
+    rng = np.random.default_rng(23)
+    t1, t2, n = _tiny_kgs(rng)
+    ent = eng.EmbeddingTable(rng.standard_normal((2 * n, 16)).astype(np.float32), True)
+    rel = eng.EmbeddingTable(rng.standard_normal((11, 16)).astype(np.float32), True)
+    kg1 = eng.DeviceKG(t1, np.arange(0, n), 2 * n)
+    kg2 = eng.DeviceKG(t2, np.arange(n, 2 * n), 2 * n)
+    tset = eng.DeviceTripleSet([kg1.triples, kg2.triples], 2 * n, 11)
+    cfg = eng.loss_cfg("limited", "L2", 0.1, 2.0, 0.2)
+    B, k, step, seed = 256, 5, 2, 777
+    dbg = torch.zeros(B, 2 + k, dtype=torch.int32, device="cuda")
+    eng.TripleTrainer(ent, rel, cfg, 0.01).score_sampled(kg1, kg2, tset, B, k, step, seed, dbg=dbg)
+    pos, neg = eng.ModelTrainer("TransE", (ent, rel), cfg, 0.01).sample_batch(kg1, kg2, tset, B, k, step, seed)
+    dbg = dbg.cpu().numpy()
+    p, q = pos.cpu().numpy().T, neg.cpu().numpy().T.reshape(-1, k, 3)
+    for i in range(len(p)):
+        tri = dbg[i, 0]
+        src = t2[tri - (1 << 30)] if tri >= (1 << 30) else t1[tri]
+        assert (p[i] == src).all()
+        for j in range(k):
+            head = (dbg[i, 1] >> j) & 1
+            want = (dbg[i, 2 + j], p[i, 1], p[i, 2]) if head else (p[i, 0], p[i, 1], dbg[i, 2 + j])
+            assert tuple(q[i, j]) == tuple(want)
+
+
+def test_model_entry_rejects_bad_arguments(cuda_device):
+    import ctypes as C
+    from openea_b200 import lib as L
+    eng = _engine()
+    rng, slots, tabs, norms = _case("TransD", 1, 50, 5, 16, True)
+    tables = _tables(slots, tabs, norms)
+    tr = eng.ModelTrainer("TransD", tables, eng.loss_cfg("margin-based", "L2", margin=1.0), 0.01)
+    pos, neg = make_batch(rng, 50, 5, 8, 2)                                 # margin needs n_pos == n_neg
+    with pytest.raises(L.OeaError):
+        tr.score_fed(_dev(pos), _dev(neg))
+    bad = eng.ModelTrainer("TransH", (tables[0], tables[1], None, None), eng.loss_cfg("limited", "L2"), 0.01)
+    with pytest.raises(L.OeaError):                                         # TransH without its normal vectors
+        bad.score_fed(_dev(pos), _dev(neg))
