@@ -1,5 +1,6 @@
 from openea_b200.approaches.aligne import AlignE
 from openea_b200.approaches.bootea import BootEA
+from openea_b200.approaches.bootea_transh import BootEA_TransH
 from openea_b200.approaches.mtranse import MTransE
 from openea_b200.models._stubs import out_of_scope
 
@@ -27,4 +28,3 @@ MultiKE = out_of_scope("MultiKE", "multi-view literal/attribute encoders")
 GMNN = out_of_scope("GMNN", "graph matching network")
 KDCoE = out_of_scope("KDCoE", "description encoder co-training")
 BootEA_RotatE = out_of_scope("BootEA_RotatE", "float64 complex rotation score")
-BootEA_TransH = out_of_scope("BootEA_TransH", "hyperplane projection score ('next' K1 variant)")

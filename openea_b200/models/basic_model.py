@@ -206,24 +206,29 @@ class BasicModel:
         lo = min(step * batch_kg, n_triples)
         return max(0, min(lo + batch_kg, n_triples) - lo)
 
-    def launch_triple_training_1epo(self, epoch, triple_steps, steps_tasks, batch_queue, neighbors1, neighbors2):
-        """One epoch of fused device steps.  `steps_tasks` / `batch_queue` belong to the reference's producer
-        processes and are ignored; neighbors1/2 are the ε-truncated candidate tensors (or None)."""
-        start = time.time()
-        kg1, kg2, tset = self._device_kgs()
+    def _install_candidates(self, kg1, kg2, neighbors1, neighbors2):
+        """Hand the ε-truncated candidate tensors (or None) to the device KG views of the sampler."""
         for kg, nb, ents in ((kg1, neighbors1, self.kgs.useful_entities_list1),
                              (kg2, neighbors2, self.kgs.useful_entities_list2)):
             if nb is None:
                 kg.clear_candidates()
             elif kg.cand_src is not nb:
                 kg.set_candidates(nb, ents)
+
+    def launch_triple_training_1epo(self, epoch, triple_steps, steps_tasks, batch_queue, neighbors1, neighbors2):
+        """One epoch of fused device steps.  `steps_tasks` / `batch_queue` belong to the reference's producer
+        processes and are ignored; neighbors1/2 are the ε-truncated candidate tensors (or None)."""
+        start = time.time()
+        kg1, kg2, tset = self._device_kgs()
+        self._install_candidates(kg1, kg2, neighbors1, neighbors2)
         t1, t2 = kg1.triples.shape[0], kg2.triples.shape[0]
         b1 = int(t1 / (t1 + t2) * self.args.batch_size)
         b2 = self.args.batch_size - b1
         self._epoch_seed = (self._epoch_seed * 6364136223846793005 + 1442695040888963407) & ((1 << 63) - 1)
         trained_samples_num = 0
         trainer = self.triple_trainer
-        use_graph = getattr(self.args, "cuda_graph", True) and epoch > 1   # epoch 1 runs eagerly (warm-up)
+        # epoch 1 runs eagerly (warm-up); the multi-table trainers read the step's size back and are not captured
+        use_graph = getattr(self.args, "cuda_graph", True) and epoch > 1 and hasattr(trainer, "capture_epoch")
         if use_graph:
             key = (triple_steps, trainer._views(kg1, kg2, tset) and trainer._view_key)
             if getattr(self, "_epoch_graph_key", None) != key:      # (re)capture: first use, or new candidate lists

@@ -65,3 +65,35 @@ def rdgcn(scale="15K"):
                  neg_triple_num=10 if big else 125, learning_rate=0.001 if big else 0.002, batch_size=5000,
                  test_threads_num=3, start_valid=30, eval_metric="manhattan", eval_norm=False, gamma=1.0, dropout=0,
                  beta=0.3, alpha=0.1, synthetic_names=True)
+
+
+def transh(scale="15K"):
+    a = transe(scale)            # run/args/transh_args_*.json: TransE's settings, eval_norm false
+    a.embedding_module, a.eval_norm = "TransH", False
+    return a
+
+
+def transd(scale="15K"):
+    a = transh(scale)
+    a.embedding_module = "TransD"
+    return a
+
+
+def simple(scale="15K"):
+    return _args(embedding_module="SimplE", alignment_module="sharing", dim=100, init="xavier", ent_l2_norm=True,
+                 rel_l2_norm=True, learning_rate=0.01, optimizer="Adagrad", batch_size=5000 if scale == "15K" else 20000,
+                 neg_sampling="uniform", neg_triple_num=1, start_valid=10, test_threads_num=3, eval_metric="inner",
+                 eval_norm=True)
+
+
+def distmult(scale="15K"):
+    a = simple(scale)            # the reference ships no distmult_args json; SimplE's settings fit its init()
+    a.embedding_module = "DistMult"
+    a.alpha = 5                  # DistMult.init builds the mapping graph unconditionally (distmult.py:27-30)
+    return a
+
+
+def bootea_transh(scale="15K"):
+    a = bootea(scale)
+    a.embedding_module = "BootEA_TransH"
+    return a

@@ -235,3 +235,60 @@ def test_model_entry_rejects_bad_arguments(cuda_device):
     bad = eng.ModelTrainer("TransH", (tables[0], tables[1], None, None), eng.loss_cfg("limited", "L2"), 0.01)
     with pytest.raises(L.OeaError):                                         # TransH without its normal vectors
         bad.score_fed(_dev(pos), _dev(neg))
+
+
+# ---- the reference lifecycle of the models built on the family ------------------------------------------------------
+@pytest.fixture(scope="module")
+def tiny_kgs(tmp_path_factory):
+    from openea_b200.synth import write_dataset
+    folder = str(tmp_path_factory.mktemp("tiny_ext")) + "/"
+    write_dataset(folder, "tiny")
+    return folder
+
+
+def _lifecycle(model_cls, args, folder, mode, tmp_path):
+    from tests.test_e2e_gpu import _run
+    return _run(model_cls, args, folder, mode, tmp_path)
+
+
+def _losses(out, tag):
+    import re
+    return [float(x) for x in re.findall(re.escape(tag) + r"\s*([0-9.]+)", out)]
+
+
+@pytest.mark.parametrize("name", ["TransH", "TransD", "SimplE", "DistMult"])
+def test_score_family_lifecycle(cuda_device, tiny_kgs, tmp_path, name):
+    """set_args / set_kgs / init / run / test / save of the four models on the tiny synthetic KG: the epoch loss must
+    fall, the result lines and files of the reference must appear, and the shared-id alignment must beat chance."""
+    import os
+    from openea_b200 import presets
+    from openea_b200.models import trans, semantic
+    from tests.test_e2e_gpu import _hits1
+    cls = {"TransH": trans.TransH, "TransD": trans.TransD, "SimplE": semantic.SimplE, "DistMult": semantic.DistMult}[name]
+    args = getattr(presets, name.lower())("15K")
+    args.batch_size, args.max_epoch, args.start_valid, args.dim = 1000, 120, 1000, 32
+    model, out = _lifecycle(cls, args, tiny_kgs, "sharing", tmp_path)
+    tag = "triple loss:" if name == "DistMult" else "avg. triple loss:"
+    loss = _losses(out, tag)
+    assert len(loss) == 120 and loss[-1] < 0.9 * loss[0], (loss[0], loss[-1])
+    assert "Training ends. Total time" in out
+    h1 = _hits1(out, "accurate results:")
+    assert 0.0 <= h1 <= 100.0
+    for f in ("ent_embeds.npy", "rel_embeds.npy", "alignment_results_12"):
+        assert os.path.exists(model.out_folder + f), f
+    ent = np.load(model.out_folder + "ent_embeds.npy")
+    assert ent.shape == (model.kgs.entities_num, 32) and np.isfinite(ent).all()
+
+
+def test_bootea_transh_lifecycle(cuda_device, tiny_kgs, tmp_path):
+    from openea_b200 import presets
+    from openea_b200.approaches import BootEA_TransH
+    from tests.test_e2e_gpu import _hits1
+    args = presets.bootea_transh("15K")
+    args.batch_size, args.max_epoch, args.start_valid, args.sub_epoch = 1000, 200, 1000, 10
+    args.truncated_epsilon, args.dim, args.sim_th = 0.9, 32, 0.5
+    model, out = _lifecycle(BootEA_TransH, args, tiny_kgs, "swapping", tmp_path)
+    assert "avg. triple loss" in out and "generating neighbors of" in out and "Training ends. Total time" in out
+    loss = _losses(out, "avg. triple loss:")
+    assert loss[-1] < loss[0]
+    assert _hits1(out, "accurate results:") > 4.0        # chance = 0.24 %; BootEA (TransE) reaches > 8 % at 300 epochs
