@@ -13,11 +13,15 @@
         if (_e != cudaSuccess) return -(int)_e;              \
     } while (0)
 
+#ifdef OEA_HOST_EMU   // tests/emu: the kernels run on the CPU's warp emulator; there is no launch to check
+#define OEA_LAUNCH_CHECK() do { } while (0)
+#else
 #define OEA_LAUNCH_CHECK()                                   \
     do {                                                     \
         cudaError_t _e = cudaPeekAtLastError();              \
         if (_e != cudaSuccess) { cudaGetLastError(); return -(int)_e; } \
     } while (0)
+#endif
 
 namespace oea {
 
@@ -86,12 +90,20 @@ __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpre
 
 // 128-bit vector reduction to global memory (sm_90+: red.global.add.v4.f32), no return value.
 __device__ __forceinline__ void red_add4(float* p, float4 v) {
+#ifdef OEA_HOST_EMU
+    p[0] += v.x; p[1] += v.y; p[2] += v.z; p[3] += v.w;
+#else
     asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
                  :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+#endif
 }
 
 // L2 prefetch of the 128-B lines a row of `bytes` bytes starting at p touches (p is 16-B aligned)
+#ifdef OEA_HOST_EMU
+__device__ __forceinline__ void prefetch_l2(const void*) {}
+#else
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+#endif
 __device__ __forceinline__ void prefetch_row_l2(const float* row, int pitch_floats) {
     const char* b = reinterpret_cast<const char*>(row);
     const int bytes = pitch_floats * 4;

@@ -14,6 +14,7 @@
 // vector reductions (red.global.add.v4.f32) into the L2-resident gradient table.
 #include <stdlib.h>
 #include "oea_rowmath.cuh"
+#include "oea_sampler.cuh"
 #include <cooperative_groups.h>
 
 namespace oea {
@@ -146,81 +147,6 @@ k_score_margin(TableDev ent, TableDev rel,
 // Fused sampled step: warp per positive; samples its k negatives on device, loads 3 + k rows,
 // keeps the gradients of the three shared rows in registers, and issues 3 + k row reductions.
 // ------------------------------------------------------------------------------------------------
-struct SampledParams {
-    oea_kg_view kg[2];
-    oea_tripleset tset;
-    int n_slice[2];      // positives of this step taken from each KG
-    int start[2];        // offset of the slice inside the (permuted) triple list
-    int k;               // negatives per positive
-    int step;
-    int max_try;
-    uint64_t seed;
-    const uint64_t* dev_seed;   // optional device scalar xor-ed into seed (CUDA-graph replays)
-    int diag;            // OEA_DIAG bit mask (measurement only): 1 synthetic negatives (no cand/hash chain),
-                         // 2 no gradient output, 4 no negatives, 8 identity permutation
-};
-
-// Counter RNG of the sampler: `rng_base` folds (epoch seed, step, positive) once per positive; every draw is one
-// pcg32 of the base xor a small counter.
-__device__ __forceinline__ uint32_t rng_base(uint64_t seed, uint32_t step, uint32_t p) {
-    return pcg32((uint32_t)seed ^ pcg32((uint32_t)(seed >> 32) ^ (step * 0x9E3779B9u)) ^ (p * 0x85EBCA6Bu));
-}
-__device__ __forceinline__ uint32_t rng_draw(uint32_t base, uint32_t a, uint32_t b) {
-    return pcg32(base ^ (a * 0xC2B2AE35u) ^ (b * 0x27D4EB2Fu));
-}
-
-// Negative sampling of one positive by its warp (batch.py:89-119): lane j < k ends up owning negative j
-// (corrupted entity neg_e, neg_head = head corrupted).  Up to max_try rounds; a round flips ONE coin for all
-// still-missing negatives, draws distinct candidate positions for them, keeps the draws that are not known
-// triples; the last round keeps everything.
-__device__ __forceinline__ void warp_sample_negatives(const SampledParams& P, uint64_t seed, const oea_kg_view& kg, int p, int h, int r,
-                                                      int t, int k, int lane, const float* __restrict__ ent_w, int ent_pitch,
-                                                      int& neg_e, bool& neg_head) {
-    bool need = lane < k;
-    const uint32_t base = rng_base(seed, (uint32_t)P.step, (uint32_t)p);
-    for (int tr = 0; tr < P.max_try; ++tr) {
-        const unsigned missing = __ballot_sync(OEA_FULL, need);
-        if (missing == 0u) break;
-        const bool head = (rng_draw(base, 0x51DEu, tr) >> 31) != 0;  // np.random.binomial(1, .5)
-        const int corrupted = head ? h : t;
-        const int32_t* list = kg.entities;
-        uint32_t C = (uint32_t)kg.n_entities;
-        if (kg.cand != nullptr) {
-            if (kg.ent2row == nullptr) {   // candidate matrix indexed by entity id; a row starting with −1 = no list
-                const int32_t* row = kg.cand + (size_t)corrupted * kg.n_cand;
-                if (__ldg(row) >= 0) { list = row; C = (uint32_t)kg.n_cand; }
-            } else {
-                const int row = __ldg(kg.ent2row + corrupted);
-                if (row >= 0) { list = kg.cand + (size_t)row * kg.n_cand; C = (uint32_t)kg.n_cand; }
-            }
-        }
-        // random.sample(candidates, #missing): distinct positions among the needing lanes
-        uint32_t pos = 0;
-        bool unsettled = need;
-        for (uint32_t redraw = 0; ; ++redraw) {
-            if (unsettled) pos = bounded32(rng_draw(base, (tr << 8) | lane, 0xC0FFEEu + redraw), C);
-            const unsigned active = __ballot_sync(OEA_FULL, need);
-            unsigned same = 0u;
-            if (need) same = __match_any_sync(active, pos);
-            // the lowest lane of a duplicate group keeps its draw, the others redraw
-            unsettled = need && ((same & ((1u << lane) - 1u)) != 0u);
-            if (__ballot_sync(OEA_FULL, unsettled) == 0u) break;
-        }
-        if (need) {
-            const int e = __ldg(list + pos);
-            // start fetching the candidate's row while the membership probe is in flight (rejections are < 1 %)
-            prefetch_row_l2(ent_w + (size_t)e * ent_pitch, ent_pitch);
-            bool accept = tr == P.max_try - 1;
-            if (!accept) {
-                const uint64_t key = head ? triple_key(e, r, t, P.tset.ent_bits, P.tset.rel_bits)
-                                          : triple_key(h, r, e, P.tset.ent_bits, P.tset.rel_bits);
-                accept = !tset_contains(P.tset, key);
-            }
-            if (accept) { neg_e = e; neg_head = head; need = false; }
-        }
-    }
-}
-
 template <int SCORE, int VEC>
 __global__ void __launch_bounds__(kThreads)
 k_score_sampled(TableDev ent, TableDev rel, SampledParams P, oea_loss_cfg cfg,
@@ -779,79 +705,6 @@ k_lookup(const float* __restrict__ w, int pitch, int dim, bool norm, const int32
 
 
 
-// ------------------------------------------------------------------------------------------------
-// Batch producer (modules/train/batch.py:36-45 / :168-184) for the fed entry points: one warp per positive writes
-// the positive's (h, r, t) and its k negatives as index vectors.  Same positive selection as k_score_sampled.
-// sampler 0: warp_sample_negatives (generate_neg_triples_fast).  sampler 1: generate_neg_triples (batch.py:60-86):
-// lane j < k owns negative j, flips its own coin per try, draws one candidate WITH replacement, accepts the first
-// draw that is not a known triple; after max_try rejections the tail becomes a uniform entity of the KG.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads)
-k_sample_batch(SampledParams P, int sampler, const float* __restrict__ warm_w, int warm_pitch,
-               int32_t* __restrict__ pos_out, int32_t* __restrict__ neg_out) {
-    if (P.dev_seed != nullptr) P.seed ^= __ldg(reinterpret_cast<const unsigned long long*>(P.dev_seed));
-    const int lane = threadIdx.x & 31;
-    const int warp_global = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-    const int n_warps = gridDim.x * kWarpsPerBlock;
-    const int n_pos = P.n_slice[0] + P.n_slice[1];
-    const int k = P.k;
-    const size_t n_neg = (size_t)n_pos * k;
-    for (int p = warp_global; p < n_pos; p += n_warps) {
-        const int q = p < P.n_slice[0] ? 0 : 1;
-        const oea_kg_view& kg = P.kg[q];
-        const int local = q == 0 ? p : p - P.n_slice[0];
-        const uint32_t tri = feistel_perm((uint32_t)(P.start[q] + local), (uint32_t)kg.n_triples,
-                                          P.seed ^ (q ? 0xA5A5A5A5DEADBEEFull : 0x0123456789ABCDEFull));
-        int hrt = 0;
-        if (lane < 3) {
-            hrt = __ldg(kg.triples + 3 * (size_t)tri + lane);
-            pos_out[(size_t)lane * n_pos + p] = hrt;
-        }
-        const int h = __shfl_sync(OEA_FULL, hrt, 0);
-        const int r = __shfl_sync(OEA_FULL, hrt, 1);
-        const int t = __shfl_sync(OEA_FULL, hrt, 2);
-        if (k == 0) continue;
-        int neg_e = 0;
-        bool neg_head = false;
-        if (sampler == 0) {
-            warp_sample_negatives(P, P.seed, kg, p, h, r, t, k, lane, warm_w, warm_pitch, neg_e, neg_head);
-        } else if (lane < k) {
-            const uint32_t base = rng_base(P.seed, (uint32_t)P.step, (uint32_t)p);
-            bool done = false;
-            for (int tr = 0; tr < P.max_try && !done; ++tr) {
-                const bool head = (rng_draw(base, 0x51DEu + (uint32_t)lane * 64u, (uint32_t)tr) >> 31) != 0;
-                const int corrupted = head ? h : t;
-                const int32_t* list = kg.entities;
-                uint32_t C = (uint32_t)kg.n_entities;
-                if (kg.cand != nullptr) {
-                    if (kg.ent2row == nullptr) {
-                        const int32_t* row = kg.cand + (size_t)corrupted * kg.n_cand;
-                        if (__ldg(row) >= 0) { list = row; C = (uint32_t)kg.n_cand; }
-                    } else {
-                        const int row = __ldg(kg.ent2row + corrupted);
-                        if (row >= 0) { list = kg.cand + (size_t)row * kg.n_cand; C = (uint32_t)kg.n_cand; }
-                    }
-                }
-                const int e = __ldg(list + bounded32(rng_draw(base, ((uint32_t)tr << 8) | (uint32_t)lane, 0xC0FFEEu), C));
-                const uint64_t key = head ? triple_key(e, r, t, P.tset.ent_bits, P.tset.rel_bits)
-                                          : triple_key(h, r, e, P.tset.ent_bits, P.tset.rel_bits);
-                if (!tset_contains(P.tset, key)) { neg_e = e; neg_head = head; done = true; }
-            }
-            if (!done) {   // batch.py:82-85: (head, relation, random.choice(entities_list))
-                neg_e = __ldg(kg.entities + bounded32(rng_draw(base, 0xFA11u, (uint32_t)lane), (uint32_t)kg.n_entities));
-                neg_head = false;
-            }
-            if (warm_w != nullptr) prefetch_row_l2(warm_w + (size_t)neg_e * warm_pitch, warm_pitch);
-        }
-        if (lane < k) {
-            const size_t o = (size_t)p * k + lane;
-            neg_out[o] = neg_head ? neg_e : h;
-            neg_out[n_neg + o] = r;
-            neg_out[2 * n_neg + o] = neg_head ? t : neg_e;
-        }
-    }
-}
-
 }  // namespace oea
 
 using namespace oea;
@@ -953,54 +806,6 @@ static bool oea_no_fuse() {
     return v != nullptr && v[0] == '1';
 }
 
-static int check_kg(const oea_kg_view* kg, int k) {
-    if (kg == nullptr) return OEA_ERR_NULL;
-    if (kg->n_triples < 0 || kg->n_entities < 0) return OEA_ERR_RANGE;
-    if (kg->n_triples > 0 && (kg->triples == nullptr || kg->entities == nullptr)) return OEA_ERR_NULL;
-    if (kg->n_triples > 0 && kg->n_entities < k) return OEA_ERR_RANGE;  // random.sample would raise
-    if (kg->cand != nullptr && kg->n_cand < (k > 1 ? k : 1)) return OEA_ERR_RANGE;
-    return OEA_OK;
-}
-
-// batch.py:39-42 / :48-53 — slice bounds of one KG for one step, computed as the reference does.
-static void slice_of(int n_triples, int batch_kg, int step, int* start, int* count) {
-    long long s = (long long)step * batch_kg, e = s + batch_kg;
-    if (e > n_triples) e = n_triples;
-    if (s > n_triples) s = n_triples;
-    *start = (int)s;
-    *count = (int)(e - s > 0 ? e - s : 0);
-}
-
-// Slice arithmetic + sampler parameters of one step (batch.py:36-53), shared by every sampling entry point.
-static int sampler_prepare(const oea_kg_view* kg1, const oea_kg_view* kg2, const oea_tripleset* tset,
-                           const oea_sample_cfg* smp, oea::SampledParams* Pout, int* n_pos_out_host) {
-    using namespace oea;
-    if (!smp || !tset || !tset->slots) return OEA_ERR_NULL;
-    if (smp->neg_per_pos < 0 || smp->neg_per_pos > 32 || smp->batch_size < 1 || smp->max_try < 1 || smp->step < 0) return OEA_ERR_RANGE;
-    if (tset->capacity == 0 || (tset->capacity & (tset->capacity - 1)) != 0) return OEA_ERR_RANGE;
-    int rc = check_kg(kg1, smp->neg_per_pos); if (rc) return rc;
-    rc = check_kg(kg2, smp->neg_per_pos); if (rc) return rc;
-    const long long T = (long long)kg1->n_triples + kg2->n_triples;
-    if (T == 0) return OEA_ERR_RANGE;
-    // int(len(l1) / (len(l1) + len(l2)) * batch_size): float division, multiply, truncate (batch.py:39)
-    const int b1 = (int)((double)kg1->n_triples / (double)T * (double)smp->batch_size);
-    const int b2 = smp->batch_size - b1;
-
-    SampledParams& P = *Pout;
-    P.kg[0] = *kg1; P.kg[1] = *kg2; P.tset = *tset;
-    slice_of(kg1->n_triples, b1, smp->step, &P.start[0], &P.n_slice[0]);
-    slice_of(kg2->n_triples, b2, smp->step, &P.start[1], &P.n_slice[1]);
-    P.k = smp->neg_per_pos; P.step = smp->step; P.max_try = smp->max_try; P.seed = smp->epoch_seed;
-    P.dev_seed = smp->dev_seed;
-    {   // measurement-only ablation switches ("where the time goes"); read once per process
-        static int diag_cached = -1;
-        if (diag_cached < 0) { const char* dg = getenv("OEA_DIAG"); diag_cached = dg ? atoi(dg) : 0; }
-        P.diag = diag_cached;
-    }
-    *n_pos_out_host = P.n_slice[0] + P.n_slice[1];
-    return OEA_OK;
-}
-
 // Argument checks + step parameters shared by the score-only and the fused-step entry points.
 static int sampled_prepare(const oea_table* ent, const oea_table* rel, const oea_kg_view* kg1, const oea_kg_view* kg2,
                            const oea_tripleset* tset, const oea_sample_cfg* smp, const oea_loss_cfg* loss,
@@ -1016,25 +821,6 @@ static int sampled_prepare(const oea_table* ent, const oea_table* rel, const oea
     if ((loss->loss_kind == OEA_LOSS_LIMITED || loss->loss_kind == OEA_LOSS_LOGISTIC) && smp->neg_per_pos < 1) return OEA_ERR_SHAPE;
     if (loss->score_kind != OEA_SCORE_L1 && loss->score_kind != OEA_SCORE_L2SQ) return OEA_ERR_KIND;
     return sampler_prepare(kg1, kg2, tset, smp, Pout, n_pos_out_host);
-}
-
-extern "C" int oea_triple_sample_batch(const oea_kg_view* kg1, const oea_kg_view* kg2, const oea_tripleset* tset,
-                                       const oea_sample_cfg* smp, int32_t sampler, const oea_table* warm,
-                                       int32_t* pos_hrt, int32_t* neg_hrt, int32_t* n_pos_host, void* stream) {
-    SampledParams P;
-    int n_pos = 0;
-    int rc = sampler_prepare(kg1, kg2, tset, smp, &P, &n_pos); if (rc) return rc;
-    if (sampler != 0 && sampler != 1) return OEA_ERR_KIND;
-    if (!pos_hrt || !n_pos_host || (smp->neg_per_pos > 0 && !neg_hrt)) return OEA_ERR_NULL;
-    if (warm != nullptr) { rc = check_table(warm, false); if (rc) return rc; }
-    if (sampler == 0 && warm == nullptr) return OEA_ERR_NULL;   // the fast sampler prefetches unconditionally
-    *n_pos_host = n_pos;
-    if (n_pos == 0) return OEA_OK;
-    P.diag = 0;
-    k_sample_batch<<<grid_for(n_pos), kThreads, 0, (cudaStream_t)stream>>>(
-        P, sampler, warm ? warm->weight : nullptr, warm ? warm->pitch : 0, pos_hrt, neg_hrt);
-    OEA_LAUNCH_CHECK();
-    return OEA_OK;
 }
 
 extern "C" int oea_triple_score_sampled(const oea_table* ent, const oea_table* rel,

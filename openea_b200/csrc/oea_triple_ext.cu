@@ -370,12 +370,17 @@ extern "C" int oea_model_score_fed(const oea_model* model,
     const bool l1 = !bilinear && loss->score_kind == OEA_SCORE_L1;
     const int grid = grid_for(margin ? n_pos : n_pos + n_neg);
 
+#ifdef OEA_HOST_EMU   // tests/emu: the same kernels on the CPU warp emulator (two blocks keep the thread count small)
+#define OEA_RUN(KERNEL, ...) emu::launch(grid < 2 ? grid : 2, kThreads, [&] { KERNEL(__VA_ARGS__); })
+#else
+#define OEA_RUN(KERNEL, ...) KERNEL<<<grid, kThreads, 0, st>>>(__VA_ARGS__)
+#endif
 #define OEA_LAUNCH_MODEL(MODEL, SCORE, V)                                                                              \
     do {                                                                                                               \
-        if (margin) k_model_margin<MODEL, SCORE, V><<<grid, kThreads, 0, st>>>(M, pos_h, pos_r, pos_t, neg_h, neg_r,   \
-                                                                               neg_t, n_pos, *loss, loss_scale, loss_out); \
-        else k_model_fed<MODEL, SCORE, V><<<grid, kThreads, 0, st>>>(M, pos_h, pos_r, pos_t, n_pos, neg_h, neg_r, neg_t, \
-                                                                     n_neg, *loss, loss_scale, loss_out);              \
+        if (margin) { auto kernel = k_model_margin<MODEL, SCORE, V>;                                                   \
+                      OEA_RUN(kernel, M, pos_h, pos_r, pos_t, neg_h, neg_r, neg_t, n_pos, *loss, loss_scale, loss_out); } \
+        else { auto kernel = k_model_fed<MODEL, SCORE, V>;                                                             \
+               OEA_RUN(kernel, M, pos_h, pos_r, pos_t, n_pos, neg_h, neg_r, neg_t, n_neg, *loss, loss_scale, loss_out); } \
     } while (0)
 #define OEA_LAUNCH_VEC(MODEL, SCORE)                                                  \
     do {                                                                              \
@@ -398,6 +403,7 @@ extern "C" int oea_model_score_fed(const oea_model* model,
 #undef OEA_LAUNCH_SCORE
 #undef OEA_LAUNCH_VEC
 #undef OEA_LAUNCH_MODEL
+#undef OEA_RUN
     OEA_LAUNCH_CHECK();
     return OEA_OK;
 }

@@ -1,0 +1,36 @@
+"""Builds tests/emu/libemu_oea.so: the product's kernel sources on the CPU warp emulator (test infrastructure)."""
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.path.join(HERE, "libemu_oea.so")
+SRC = os.path.join(HERE, "emu_kernels.cpp")
+CSRC = os.path.join(os.path.dirname(os.path.dirname(HERE)), "openea_b200", "csrc")
+DEPS = [SRC, os.path.join(HERE, "cuda_host_emu.h")] + [os.path.join(CSRC, f) for f in
+                                                        ("oea_triple_ext.cu", "oea_sampler.cu", "oea_sampler.cuh", "oea_rowmath.cuh", "oea_common.cuh")]
+
+
+def cuda_include():
+    for root in (os.environ.get("CUDA_HOME"), "/usr/local/cuda"):
+        if root and os.path.exists(os.path.join(root, "include", "cuda_runtime.h")):
+            return os.path.join(root, "include")
+    return None
+
+
+def build(force=False):
+    inc = cuda_include()
+    if inc is None:
+        return None
+    if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in DEPS):
+        return OUT
+    cmd = ["g++", "-std=c++20", "-O1", "-pthread", "-fPIC", "-shared", "-DOEA_HOST_EMU", "-DOEA_F32X2=0",
+           "-Wno-attributes", "-Wno-unknown-pragmas", "-I", inc, "-o", OUT, SRC,
+           "-L", os.path.join(os.path.dirname(inc), "lib64"), "-lcudart"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("emulator build failed:\n" + res.stderr[-4000:])
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force=True))
