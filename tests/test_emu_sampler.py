@@ -19,9 +19,9 @@ def pcg32(x):
     return ((w >> 22) ^ w) & M32
 
 
-def build_tripleset(triples, ent_bits, rel_bits):
+def build_tripleset(triples, ent_bits, rel_bits, capacity=None):
     """Host statement of oea_tripleset_build: open addressing, linear probing, key_hash of oea_common.cuh."""
-    cap = 1 << int(np.ceil(np.log2(max(16, 2 * len(triples)))))
+    cap = capacity or 1 << int(np.ceil(np.log2(max(16, 2 * len(triples)))))
     slots = np.full(cap, EMPTY, dtype=np.uint64)
     for h, r, t in triples.tolist():
         key = (h << (ent_bits + rel_bits)) | (r << ent_bits) | t
