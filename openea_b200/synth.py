@@ -16,6 +16,7 @@ SHAPES = {
     "15K": dict(n_ent=15000, n_rel=(250, 200), n_tri=45000, links=(3000, 1500, 10500), n_attr=400),
     "100K": dict(n_ent=100000, n_rel=(300, 300), n_tri=300000, links=(20000, 10000, 70000), n_attr=400),
     "tiny": dict(n_ent=600, n_rel=(12, 10), n_tri=2400, links=(120, 60, 420), n_attr=20),
+    "micro": dict(n_ent=40, n_rel=(4, 4), n_tri=120, links=(8, 4, 28), n_attr=5),   # CPU emulator runs (tests/emu)
 }
 
 

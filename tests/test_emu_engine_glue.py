@@ -114,3 +114,42 @@ def test_model_trainer_steps_on_the_emulator_equal_oracle_steps(cpu_engine, mode
         if s is not None:
             np.testing.assert_allclose(tab.raw().numpy(), st.w[s], rtol=1e-4, atol=2e-5, err_msg=s)
             assert not tab.grad.any() and not tab.touched.any()
+
+
+@pytest.mark.parametrize("name", ["TransH", "TransD", "SimplE", "DistMult"])
+def test_model_lifecycle_init_and_run_on_the_emulator(cpu_engine, monkeypatch, tmp_path, capsys, name):
+    """set_args / set_kgs / init / run of the four model classes on a 40-entity synthetic dataset: the reference's epoch
+    lines appear, the loss is finite and every table of the model has moved.  (test() / save() need the similarity
+    kernels, which only run on a GPU: tests/test_zz_triple_ext_gpu.py.)"""
+    import re
+    from openea_b200 import presets
+    from openea_b200.models import trans, semantic
+    from openea_b200.modules.base import initializers
+    from openea_b200.modules.load.kgs import read_kgs_from_folder
+    from openea_b200.synth import write_dataset
+    monkeypatch.setattr(initializers, "_make", lambda values, norm, optimizer=None: cpu_engine.EmbeddingTable(
+        values, bool(norm), optimizer or "Adagrad", "cpu"))
+    monkeypatch.setattr(L.load(), "oea_mapping_workspace_bytes", lambda dim: 0, raising=False)   # DistMult builds a mapper
+    from openea_b200.models.trans import transe
+    from openea_b200.models.semantic import distmult, simple
+    for mod in (transe, distmult, simple):       # load_session() refuses to run without a CUDA device (by design)
+        monkeypatch.setattr(mod, "load_session", lambda: None)
+    folder = write_dataset(str(tmp_path) + "/micro/", "micro")
+    cls = {"TransH": trans.TransH, "TransD": trans.TransD, "SimplE": semantic.SimplE, "DistMult": semantic.DistMult}[name]
+    args = getattr(presets, name.lower())("15K")
+    args.training_data, args.output = folder, str(tmp_path) + "/out/"
+    args.batch_size, args.max_epoch, args.start_valid, args.dim = 64, 2, 1000, 16
+    kgs = read_kgs_from_folder(folder, args.dataset_division, "sharing", args.ordered)
+    model = cls()
+    model.set_args(args)
+    model.set_kgs(kgs)
+    model.init()
+    before = [t.weight.clone() for t in model.triple_trainer.live]
+    model.run()
+    out = capsys.readouterr().out
+    tag = r"triple loss: ([0-9.]+)" if name == "DistMult" else r"avg\. triple loss: ([0-9.]+)"
+    losses = [float(x) for x in re.findall(tag, out)]
+    assert len(losses) == 2 and all(np.isfinite(losses)) and losses[0] > 0
+    assert "Training ends. Total time" in out
+    for b, t in zip(before, model.triple_trainer.live):
+        assert not torch.equal(b, t.weight) and torch.isfinite(t.weight).all()
