@@ -96,12 +96,23 @@ class GCN_Align(BasicModel):
         def trunc_normal(shape):  # stddev = 1/√shape[0] (gcn_align.py:52-56)
             std = 1.0 / math.sqrt(shape[0])
             return torch.nn.init.trunc_normal_(torch.empty(*shape), std=std, a=-2 * std, b=2 * std, generator=g)
-        ae_table = EmbeddingTable(trunc_normal([self.attr.shape[1], self.args.ae_dim]), True, "SGD", dev)
-        se_table = EmbeddingTable(trunc_normal([n, self.args.se_dim]), True, "SGD", dev)
-        self.model_ae = GCNAlignUnit(self.support, ae_table, self.ae_input, self.train, self.args.gamma,
-                                     self.args.neg_triple_num, self.args.learning_rate)
-        self.model_se = GCNAlignUnit(self.support, se_table, None, self.train, self.args.gamma,
-                                     self.args.neg_triple_num, self.args.learning_rate)
+        ae_init, se_init = trunc_normal([self.attr.shape[1], self.args.ae_dim]), trunc_normal([n, self.args.se_dim])
+        unit_args = (self.train, self.args.gamma, self.args.neg_triple_num, self.args.learning_rate)
+        from openea_b200 import parallel as par
+        if par.world()[1] > 1:
+            # one process per GPU (torchrun): adjacency, layer outputs and the SE entity table are row-sharded, one
+            # exchange per layer (openea_b200/parallel_gnn.py); every rank seeds the same generator, so the shards are
+            # slices of the single-GPU initialisation
+            from openea_b200 import parallel_gnn as pg
+            shard = pg.RowShard(n)
+            norm_adj = gnn.preprocess_adj(self.adj)
+            self.model_ae = pg.ShardedGCNAlignUnit(norm_adj, EmbeddingTable(ae_init, True, "SGD", dev), self.attr,
+                                                   *unit_args, shard=shard)
+            self.model_se = pg.ShardedGCNAlignUnit(norm_adj, EmbeddingTable(shard.local_rows(se_init.numpy()), True,
+                                                                            "SGD", dev), None, *unit_args, shard=shard)
+            return
+        self.model_ae = GCNAlignUnit(self.support, EmbeddingTable(ae_init, True, "SGD", dev), self.ae_input, *unit_args)
+        self.model_se = GCNAlignUnit(self.support, EmbeddingTable(se_init, True, "SGD", dev), None, *unit_args)
 
     def _embeddings(self):
         se = self.model_se.outputs[:, :self.args.se_dim]

@@ -53,3 +53,58 @@ def test_sharded_eval_equals_single_gpu():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
+def _gcn_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import scipy.sparse as sp
+        from openea_b200 import gnn, parallel_gnn as pg
+        from openea_b200.approaches.gcn_align import GCNAlignUnit
+        from openea_b200.engine import EmbeddingTable
+        rng = np.random.default_rng(4)
+        n, d, t, k = 2003, 100, 150, 5
+        a = sp.random(n, n, density=0.004, random_state=7, format="csr", dtype=np.float32)
+        support = gnn.preprocess_adj(a + a.T)
+        W0 = (rng.standard_normal((n, d)) / np.sqrt(n)).astype(np.float32)
+        ill = np.stack([rng.permutation(n)[:t], rng.permutation(n)[:t]], 1)
+        negs = [np.repeat(ill[:, 0], k), rng.integers(0, n, t * k), rng.integers(0, n, t * k), np.repeat(ill[:, 1], k)]
+        tn = [torch.as_tensor(x, dtype=torch.int32, device="cuda") for x in negs]
+        single = GCNAlignUnit(gnn.DeviceCsr(support, "cuda"), EmbeddingTable(W0, True, "SGD", "cuda"), None, ill, 3.0, k, 8.0)
+        shard = pg.RowShard(n)
+        unit = pg.ShardedGCNAlignUnit(support, EmbeddingTable(shard.local_rows(W0), True, "SGD", "cuda"), None, ill,
+                                      3.0, k, 8.0, shard=shard)
+        for _ in range(3):
+            want = float(single.train_step(*tn))
+            got = float(unit.train_step(*tn))
+            assert abs(got - want) <= 1e-4 * max(1.0, abs(want)), (got, want)
+            torch.testing.assert_close(unit.outputs, single.outputs, rtol=1e-4, atol=1e-6)
+        W = pg.all_gather_rows(unit.table.weight, shard)[:n]
+        torch.testing.assert_close(W, single.table.weight, rtol=1e-4, atol=1e-6)
+        out.put((rank, "ok"))
+    except Exception as e:
+        import traceback
+        out.put((rank, "FAIL: %r\n%s" % (e, traceback.format_exc())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_row_sharded_gcn_unit_equals_single_gpu():
+    """SURVEY §8e-ii over NCCL: the row-sharded GCN-Align unit (liboea kernels + 3 all-gathers / 3 reduce-scatters per
+    step) reproduces the single-GPU unit's loss, outputs and updated entity table."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gcn_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res

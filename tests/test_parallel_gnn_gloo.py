@@ -1,0 +1,152 @@
+"""CPU: the row-sharded GCN-Align unit (openea_b200/parallel_gnn.py) under torch.distributed/gloo with
+world sizes 2 and 3: partition + padding, the three all-gathers and three reduce-scatters per step, pair sharding and
+loss weighting.  The rank-local numerics come from a torch stand-in (the kernels need a GPU); the result must equal the
+single-process oracle step (oracle/gnn.py) — i.e. the collective algebra is exact."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+class _Csr:
+    def __init__(self, mat):
+        self.m = sp.csr_matrix(mat, dtype=np.float32)
+        self.shape = self.m.shape
+        c = self.m.tocoo()
+        self.t = torch.sparse_coo_tensor(np.vstack([c.row, c.col]), c.data, c.shape).coalesce()
+
+    def transpose(self):
+        return _Csr(self.m.T)
+
+
+class _Table:
+    def __init__(self, values):
+        self.weight = torch.tensor(values, dtype=torch.float32)
+        self.dim = self.weight.shape[1]
+        self.device = torch.device("cpu")
+
+
+class TorchOps:
+    """Rank-local numerics of the unit in plain torch (test stand-in for KernelOps)."""
+
+    def csr(self, mat, device):
+        return _Csr(mat)
+
+    def spmm(self, A, X, relu=False, mask_src=None):
+        y = torch.sparse.mm(A.t, X)
+        if relu:
+            y = torch.relu(y)
+        if mask_src is not None:
+            y = y * (mask_src > 0)
+        return y
+
+    def lookup(self, table):
+        from oracle.gnn import l2n
+        return l2n(table.weight)
+
+    def update(self, table, grad_rows, lr):
+        from oracle.gnn import l2n
+        w = table.weight.clone().requires_grad_(True)
+        (l2n(w) * grad_rows).sum().backward()
+        table.weight -= lr * w.grad
+
+    def align_loss(self, x, dim, left, right, k, negs, gamma, grad, loss_out):
+        from oracle.gnn import align_loss
+        xg = x.clone().requires_grad_(True)
+        ill = np.stack([left.numpy(), right.numpy()], 1)
+        loss = align_loss(xg, ill, gamma, k, *[n.numpy() for n in negs])
+        loss.backward()
+        grad += xg.grad
+        loss_out += loss.detach().double()
+
+
+def _problem(with_features):
+    rng = np.random.default_rng(4)
+    n, d, t, k = 53, 8, 11, 3                      # 53 rows: ragged last block for world 2 and 3
+    a = sp.random(n, n, density=0.08, random_state=7, format="csr", dtype=np.float32)
+    a = a + a.T + sp.eye(n, dtype=np.float32)
+    deg = np.asarray(a.sum(1)).ravel()
+    support = sp.diags(deg ** -0.5) @ a @ sp.diags(deg ** -0.5)
+    feats = sp.random(n, 9, density=0.3, random_state=3, format="csr", dtype=np.float32) if with_features else None
+    if feats is not None:
+        feats.data[:] = 1.0
+    W0 = rng.standard_normal((9 if with_features else n, d)).astype(np.float32)
+    ill = np.stack([rng.permutation(n)[:t], rng.permutation(n)[:t]], 1)
+    negs = [np.repeat(ill[:, 0], k), rng.integers(0, n, t * k), rng.integers(0, n, t * k), np.repeat(ill[:, 1], k)]
+    return support, feats, W0, ill, negs, k
+
+
+def _worker(rank, world, port, with_features, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from openea_b200 import parallel_gnn as pg
+        from oracle import gnn as orc
+        support, feats, W0, ill, negs, k = _problem(with_features)
+        gamma, lr = 1.0, 0.5
+        shard = pg.RowShard(support.shape[0])
+        assert (shard.rank, shard.world) == (rank, world) and shard.n_pad == shard.block * world >= shard.n
+        table = _Table(W0 if with_features else shard.local_rows(W0))
+        unit = pg.ShardedGCNAlignUnit(support, table, feats, ill, gamma, k, lr, shard=shard, ops=TorchOps())
+        tn = [torch.as_tensor(x, dtype=torch.int32) for x in negs]
+        want_W = W0
+        for _ in range(2):
+            got = float(unit.train_step(*tn))
+            want_loss, want_W, want_out = orc.unit_train_step(support, want_W, feats, ill, gamma, k, negs, lr)
+            assert abs(got - want_loss) <= 1e-5 * max(1.0, abs(want_loss)), (got, want_loss)
+            np.testing.assert_allclose(unit.outputs.numpy(), want_out, rtol=1e-4, atol=1e-6)
+        if with_features:
+            W = table.weight.numpy()                                     # replicated: identical on every rank
+        else:
+            W = pg.all_gather_rows(table.weight, shard).numpy()[:shard.n]   # assemble the owners' rows
+            assert not table.weight[shard.hi - shard.lo:].any(), "padding rows of the shard must stay zero"
+        np.testing.assert_allclose(W, want_W, rtol=1e-4, atol=1e-6)
+        out.put((rank, "ok"))
+    except Exception as e:  # surface the failure in the parent
+        import traceback
+        out.put((rank, "FAIL: %r\n%s" % (e, traceback.format_exc())))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("with_features", [False, True])
+def test_sharded_gcn_unit_equals_single_process_oracle(world, with_features):
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, with_features, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(r, "ok") for r in range(world)], res
+
+
+def test_row_shard_partition_is_exact():
+    from openea_b200 import parallel_gnn as pg
+    m = sp.random(10, 10, density=0.5, random_state=1, format="csr")
+    rows = []
+    for r in range(4):
+        sh = pg.RowShard(10, rank=r, world_size=4)
+        assert (sh.block, sh.n_pad) == (3, 12)
+        blk = sh.square_rows_of(m)
+        assert blk.shape == (3, 12)
+        rows.append(blk[:sh.hi - sh.lo, :10])
+        assert blk[sh.hi - sh.lo:].nnz == 0
+    assert (sp.vstack(rows) != m).nnz == 0
