@@ -135,6 +135,9 @@ class GCN_Align(BasicModel):
             if i % 10 == 1:   # uniform negatives over all entities, refreshed every 10 epochs (gcn_align.py:753-755)
                 neg2_left = torch.as_tensor(np.random.choice(self.e, train_num * neg_num), dtype=torch.int32, device=dev)
                 neg_right = torch.as_tensor(np.random.choice(self.e, train_num * neg_num), dtype=torch.int32, device=dev)
+                if torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+                    for neg in (neg2_left, neg_right):     # the sharded units need the same negatives on every rank
+                        torch.distributed.broadcast(neg, src=0)
             l1 = self.model_ae.train_step(neg_left, neg_right, neg2_left, neg2_right)
             l2 = self.model_se.train_step(neg_left, neg_right, neg2_left, neg2_right)
             batch_loss = float((l1 + l2).item())
