@@ -100,10 +100,13 @@ class BasicModel:
         """Device copies of both KGs' triple/entity lists + the triple membership set (built once)."""
         if self._dkg1 is None:
             dev = self.ent_embeds.device
-            self._dkg1 = eng.DeviceKG(self.kgs.kg1.relation_triples_list, self.kgs.kg1.entities_list,
-                                      self.kgs.entities_num, dev)
-            self._dkg2 = eng.DeviceKG(self.kgs.kg2.relation_triples_list, self.kgs.kg2.entities_list,
-                                      self.kgs.entities_num, dev)
+
+            def device_kg(kg):     # the array-backed loader hands its int32 arrays over without building Python lists
+                triples = getattr(kg, "relation_triples_array", None)
+                entities = getattr(kg, "entities_array", None)
+                return eng.DeviceKG(kg.relation_triples_list if triples is None else triples,
+                                    kg.entities_list if entities is None else entities, self.kgs.entities_num, dev)
+            self._dkg1, self._dkg2 = device_kg(self.kgs.kg1), device_kg(self.kgs.kg2)
             self._tset = eng.DeviceTripleSet([self._dkg1.triples, self._dkg2.triples], self.kgs.entities_num,
                                              self.kgs.relations_num, dev)
         return self._dkg1, self._dkg2, self._tset

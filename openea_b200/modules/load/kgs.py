@@ -83,9 +83,18 @@ def _build(rel1, rel2, attr1, attr2, links, mode, ordered, remove_unlinked):
 
 
 def read_kgs_from_folder(training_data_folder, division, mode, ordered, remove_unlinked=False):
+    """kgs.py:102-118 of the reference.  Datasets in the standard layout load through the array-backed layer
+    (modules/load/fast.py: C parser, vectorised id assignment, lazy Python containers, binary cache); what that layer
+    does not cover, or OEA_LOADER=containers, uses the container-based loader below."""
     lowered = training_data_folder.lower()
     if 'dbp15k' in lowered or 'dwy100k' in lowered:
         return read_kgs_from_dbp_dwy(training_data_folder, division, mode, ordered, remove_unlinked=remove_unlinked)
+    if os.environ.get("OEA_LOADER") != "containers":
+        from openea_b200.modules.load import fast
+        try:
+            return fast.load(training_data_folder, division, mode, ordered, remove_unlinked=remove_unlinked)
+        except fast.Unsupported as why:
+            print("array-backed loader not applicable (%s); using the container-based loader" % why)
     return _build(*_load_folder(training_data_folder, division, False), mode, ordered, remove_unlinked)
 
 

@@ -142,18 +142,11 @@ def test_openea_dropin_import_surface():
         JAPE().init()
 
 
-@pytest.mark.skipif(not ref_adapter.available(), reason="/root/reference not present on this box")
-def test_dataset_loading_equals_live_reference(tmp_path):
-    """Full read_kgs_from_folder equivalence (id dicts, triples incl. swap triples, links) on a synthetic folder."""
+def _reference_kgs(folder, modes):
+    """read_kgs_from_folder of the live reference (TensorFlow stubbed) for the given id modes."""
     import importlib
     import sys
     import types
-    from openea_b200.synth import write_dataset
-    folder = str(tmp_path) + "/"
-    write_dataset(folder, "tiny")
-    with contextlib.redirect_stdout(io.StringIO()):
-        from openea_b200.modules.load.kgs import read_kgs_from_folder
-        mine = {m: read_kgs_from_folder(folder, "721_5fold/1/", m, True) for m in ("swapping", "mapping", "sharing")}
     saved = {k: v for k, v in sys.modules.items() if k == "openea" or k.startswith("openea.")}
     for k in saved:
         del sys.modules[k]
@@ -164,20 +157,114 @@ def test_dataset_loading_equals_live_reference(tmp_path):
     try:
         with contextlib.redirect_stdout(io.StringIO()):
             rk = importlib.import_module("openea.modules.load.kgs")
-            theirs = {m: rk.read_kgs_from_folder(folder, "721_5fold/1/", m, True) for m in mine}
+            return {m: rk.read_kgs_from_folder(folder, "721_5fold/1/", m, True) for m in modes}
     finally:
         for k in [k for k in sys.modules if k == "openea" or k.startswith("openea.")]:
             del sys.modules[k]
         sys.modules.pop("tensorflow", None)
         sys.modules.update(saved)
+
+
+@pytest.mark.skipif(not ref_adapter.available(), reason="/root/reference not present on this box")
+@pytest.mark.parametrize("loader", ["arrays", "containers", "arrays-cached"])
+def test_dataset_loading_equals_live_reference(tmp_path, monkeypatch, loader):
+    """Full read_kgs_from_folder equivalence with the live reference on a synthetic folder, in all three id modes, for
+    the array-backed loader (fresh parse and binary cache) and the container-based loader: id dicts, triple sets and
+    lists incl. swap triples, every derived dict, vocabularies, counts, links, URI-level KGs."""
+    from openea_b200.modules.load import fast
+    from openea_b200.modules.load.kgs import read_kgs_from_folder
+    from openea_b200.synth import write_dataset
+    folder = str(tmp_path) + "/"
+    write_dataset(folder, "tiny")
+    monkeypatch.setenv("OEA_CACHE_DIR", str(tmp_path) + "/cache")
+    if loader == "containers":
+        monkeypatch.setenv("OEA_LOADER", "containers")
+    modes = ("swapping", "mapping", "sharing")
+    with contextlib.redirect_stdout(io.StringIO()) as log:
+        mine = {m: read_kgs_from_folder(folder, "721_5fold/1/", m, True) for m in modes}
+        if loader == "arrays-cached":
+            mine = {m: read_kgs_from_folder(folder, "721_5fold/1/", m, True) for m in modes}
+    if loader == "arrays-cached":
+        assert log.getvalue().count("loaded from cache") == 3
+    assert isinstance(mine["mapping"], fast.ArrayKGs) == (loader != "containers")
+    theirs = _reference_kgs(folder, modes)
     for m in mine:
         a, b = mine[m], theirs[m]
         assert a.entities_num == b.entities_num and a.relations_num == b.relations_num and a.attributes_num == b.attributes_num
+        for side in ("kg1", "kg2", "uri_kg1", "uri_kg2"):
+            ka, kb = getattr(a, side), getattr(b, side)
+            if not side.startswith("uri"):
+                assert ka.entities_id_dict == kb.entities_id_dict and ka.relations_id_dict == kb.relations_id_dict
+                assert ka.attributes_id_dict == kb.attributes_id_dict
+                assert ka.sup_relation_triples_set == kb.sup_relation_triples_set
+                assert ka.sup_attribute_triples_set == kb.sup_attribute_triples_set
+            assert ka.relation_triples_set == kb.relation_triples_set and ka.attribute_triples_set == kb.attribute_triples_set
+            assert ka.local_relation_triples_set == kb.local_relation_triples_set
+            for lst in ("relation_triples_list", "local_relation_triples_list", "attribute_triples_list",
+                        "local_attribute_triples_list", "entities_list", "relations_list", "attributes_list"):
+                la, lb = getattr(ka, lst), getattr(kb, lst)
+                assert len(la) == len(lb) and set(la) == set(lb), (m, side, lst)
+            for dct in ("rt_dict", "hr_dict", "av_dict", "entity_relations_dict", "entity_attributes_dict"):
+                assert getattr(ka, dct) == getattr(kb, dct), (m, side, dct)
+            for st in ("entities_set", "relations_set", "attributes_set"):
+                assert getattr(ka, st) == getattr(kb, st), (m, side, st)
+            for num in ("entities_num", "relations_num", "attributes_num", "relation_triples_num",
+                        "local_relation_triples_num", "attribute_triples_num", "local_attribute_triples_num"):
+                assert getattr(ka, num) == getattr(kb, num), (m, side, num)
+        for part in ("train", "valid", "test"):
+            assert getattr(a, part + "_links") == getattr(b, part + "_links")
+            assert getattr(a, part + "_entities1") == getattr(b, part + "_entities1")
+            assert getattr(a, "uri_%s_links" % part) == getattr(b, "uri_%s_links" % part)
+        assert set(a.useful_entities_list1) == set(b.useful_entities_list1)
+
+
+@pytest.mark.skipif(not ref_adapter.available(), reason="/root/reference not present on this box")
+@pytest.mark.parametrize("case", ["clean", "dirty"])
+def test_array_loader_edge_cases_equal_live_reference(tmp_path, monkeypatch, case):
+    """Hand-written folder: duplicate lines, padded fields, values with a trailing '.', an entity that only carries
+    attributes, a link naming an unknown entity, KGs of different sizes (id overflow branch), equal-frequency ties.
+    'clean' stays on the array path; 'dirty' adds attribute lines with too few / too many fields, which the array
+    path must hand to the container-based loader (same result as the reference either way)."""
+    from openea_b200.modules.load import fast
+    from openea_b200.modules.load.kgs import read_kgs_from_folder
+    folder = str(tmp_path) + "/"
+    os.makedirs(folder + "721_5fold/1")
+    w = lambda name, text: open(folder + name, "w", encoding="utf8").write(text)
+    w("rel_triples_1", "a\tp\tb\na\tp\tb\n b \tq\tc\nc\tp\ta\nd\tq\td\ne\tp\ta\nf\tr\tg\n")
+    w("rel_triples_2", "x\tP\ty\ny\tQ\tz\nz\tP\tx\nx\tQ\tz\n")
+    w("attr_triples_1", "a\tname\t\"Alice\" .\nb\tname\tBob.\nh\tage\t 42 \na\tname\t\"Alice\" .\n"
+      + ("a\tonly-two-fields\n\nb\tnote\tx\ty z\n" if case == "dirty" else ""))
+    w("attr_triples_2", "x\tlabel\tex\ny\tlabel\twhy.\n")
+    w("ent_links", "a\tx\nb\ty\nc\tz\n")
+    w("721_5fold/1/train_links", "a\tx\n")
+    w("721_5fold/1/valid_links", "b\ty\n")
+    w("721_5fold/1/test_links", "c\tz\nnobody\tz\n")
+    monkeypatch.setenv("OEA_NO_DATASET_CACHE", "1")
+    modes = ("swapping", "mapping", "sharing")
+    with contextlib.redirect_stdout(io.StringIO()) as log:
+        mine = {m: read_kgs_from_folder(folder, "721_5fold/1/", m, True) for m in modes}
+    assert isinstance(mine["mapping"], fast.ArrayKGs) == (case == "clean")
+    assert ("array-backed loader not applicable" in log.getvalue()) == (case == "dirty")
+    theirs = _reference_kgs(folder, modes)
+    for m in modes:
+        a, b = mine[m], theirs[m]
+        assert (a.entities_num, a.relations_num, a.attributes_num) == (b.entities_num, b.relations_num, b.attributes_num)
         for side in ("kg1", "kg2"):
             ka, kb = getattr(a, side), getattr(b, side)
-            assert ka.entities_id_dict == kb.entities_id_dict and ka.relations_id_dict == kb.relations_id_dict
-            assert ka.attributes_id_dict == kb.attributes_id_dict
-            assert ka.relation_triples_set == kb.relation_triples_set and ka.attribute_triples_set == kb.attribute_triples_set
-            assert ka.rt_dict == kb.rt_dict and ka.hr_dict == kb.hr_dict
-            assert ka.sup_relation_triples_set == kb.sup_relation_triples_set
+            for name in ("entities_id_dict", "relations_id_dict", "attributes_id_dict", "relation_triples_set",
+                         "attribute_triples_set", "sup_relation_triples_set", "sup_attribute_triples_set", "rt_dict",
+                         "hr_dict", "av_dict", "entity_attributes_dict", "entities_set"):
+                assert getattr(ka, name) == getattr(kb, name), (m, side, name)
         assert a.train_links == b.train_links and a.valid_links == b.valid_links and a.test_links == b.test_links
+
+
+def test_array_loader_refuses_what_only_the_container_loader_covers(tmp_path):
+    from openea_b200.modules.load import fast
+    from openea_b200.synth import write_dataset
+    folder = write_dataset(str(tmp_path) + "/d/", "micro")
+    with pytest.raises(fast.Unsupported):
+        fast.load(folder, "721_5fold/1/", "mapping", False)                  # unordered ids: Python set iteration order
+    with pytest.raises(fast.Unsupported):
+        fast.load(folder, "721_5fold/1/", "mapping", True, remove_unlinked=True)
+    rows = np.array([[3, 1, 2], [3, 1, 2], [0, 0, 0], [3, 1, 1]], dtype=np.int32)
+    assert fast.unique_int_rows(rows).tolist() == [[3, 1, 2], [0, 0, 0], [3, 1, 1]]
