@@ -3,9 +3,13 @@ import sys
 
 import pytest
 
+import tempfile
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# the dataset layer's binary cache (modules/load/fast.py) must not land in the user's ~/.cache during test runs
+os.environ.setdefault("OEA_CACHE_DIR", os.path.join(tempfile.gettempdir(), "oea_dataset_cache_tests_%d" % os.getpid()))
 
 
 def pytest_configure(config):
