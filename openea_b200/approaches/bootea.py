@@ -3,6 +3,9 @@
 Per iteration: `sub_epoch` epochs of fused triple steps → validation → bootstrapping (reference-entity
 cosine similarity on the GPU, threshold ∧ top-k filter, matching, editing) → one pass of the alignment loss
 −Σ log σ(−‖h+r−t‖²) on swapped triples (own Adagrad slots) → ε-truncated neighbour refresh.
+run() keeps the bootstrapping working set on the device (modules/bootstrapping/device.py: matching, label editing and
+swap-triple generation as tensor index arithmetic); the set / dict functions below are the reference's module-level
+API (bootea_transh.py imports them) and the statement the device versions are tested against.
 The likelihood graph of the reference (bootea.py:201-212) is never executed there (its call is commented
 out, :293) and is not built here.
 """
@@ -16,6 +19,7 @@ import torch
 from openea_b200 import engine as eng
 from openea_b200 import finding as F
 from openea_b200.approaches.aligne import AlignE
+from openea_b200.modules.bootstrapping import device as boot
 from openea_b200.modules.bootstrapping.alignment_finder import find_alignment_from_embeds, mwgm, mwgm_graph_tool, \
     check_new_alignment
 from openea_b200.modules.finding.evaluation import early_stop
@@ -184,13 +188,61 @@ class BootEA(AlignE):
             alignment_loss = self.alignment_trainer.read_loss() / max(1, total)
             print("alignment_loss = {:.3f}, time = {:.3f} s".format(alignment_loss, time.time() - t1))
 
+    # ---- device-resident bootstrapping ---------------------------------------------------------------
+    def _local_triples_device(self, kg):
+        """The KG's LOCAL relation triples (what rt_dict / hr_dict are built from, kg.py:86-91) as a device tensor."""
+        arr = getattr(kg, "local_relation_triples_array", None)
+        if arr is None:
+            arr = np.asarray(kg.local_relation_triples_list, dtype=np.int32).reshape(-1, 3)
+        return torch.as_tensor(np.ascontiguousarray(arr, dtype=np.int32), device=self.ent_embeds.device)
+
+    def bootstrap_on_device(self):
+        """bootstrapping() of bootea.py:19-32 without leaving the device: returns the labelled pairs as entity-id
+        tensors (entities1, entities2), or (None, None) when nothing is labelled yet."""
+        dev = self.ent_embeds.device
+        if getattr(self, "_label", None) is None:
+            self._label = torch.full((len(self.ref_ent1),), -1, dtype=torch.int64, device=dev)
+            self._ref1 = torch.as_tensor(self.ref_ent1, dtype=torch.int64, device=dev)
+            self._ref2 = torch.as_tensor(self.ref_ent2, dtype=torch.int64, device=dev)
+        sim = self.eval_ref_sim_mat()
+        cand = F.find_alignment_device(sim.e1, sim.e2, self.args.sim_th, max(self.args.k, 1), "inner", False)
+        _, i, j = boot.bootstrap_labels(sim.e1, sim.e2, self._label, cand)
+        if i.numel() == 0:
+            return None, None
+        return self._ref1[i], self._ref2[j]
+
+    def train_alignment_device(self, entities1, entities2, training_epochs):
+        """train_alignment (bootea.py:228-251) with the swap triples generated and batched on the device."""
+        if entities1 is None or entities1.numel() == 0:
+            return
+        if getattr(self, "_local1", None) is None:
+            self._local1 = self._local_triples_device(self.kgs.kg1)
+            self._local2 = self._local_triples_device(self.kgs.kg2)
+        n_ent = self.kgs.entities_num
+        new1 = boot.swap_triples(self._local1, entities1, entities2, n_ent)
+        new2 = boot.swap_triples(self._local2, entities2, entities1, n_ent)
+        print("newly triples: {}, {}".format(new1.shape[0], new2.shape[0]))
+        total = new1.shape[0] + new2.shape[0]
+        if total == 0:
+            return
+        steps = max(1, math.ceil(total / self.args.batch_size))
+        for _ in range(training_epochs):
+            t1 = time.time()
+            for step in range(steps):
+                pos = boot.pos_batch(new1, new2, step, self.args.batch_size)
+                if pos.shape[1] == 0:
+                    continue
+                self.alignment_trainer.score_fed(pos)
+                self.alignment_trainer.apply()
+            alignment_loss = self.alignment_trainer.read_loss() / total
+            print("alignment_loss = {:.3f}, time = {:.3f} s".format(alignment_loss, time.time() - t1))
+
     def run(self):
         t = time.time()
         triples_num = self.kgs.kg1.relation_triples_num + self.kgs.kg2.relation_triples_num
         triple_steps = int(math.ceil(triples_num / self.args.batch_size))
         steps_tasks = task_divide(list(range(triple_steps)), self.args.batch_threads_num)
         neighbors1, neighbors2 = None, None
-        labeled_align = set()
         sub_num = self.args.sub_epoch
         iter_nums = self.args.max_epoch // sub_num
         for i in range(1, iter_nums + 1):
@@ -201,9 +253,8 @@ class BootEA(AlignE):
                 self.flag1, self.flag2, self.early_stop = early_stop(self.flag1, self.flag2, flag)
                 if self.early_stop or i == iter_nums:
                     break
-            labeled_align, entities1, entities2 = bootstrapping(self.eval_ref_sim_mat(), self.ref_ent1, self.ref_ent2,
-                                                                labeled_align, self.args.sim_th, self.args.k)
-            self.train_alignment(self.kgs.kg1, self.kgs.kg2, entities1, entities2, 1)
+            entities1, entities2 = self.bootstrap_on_device()
+            self.train_alignment_device(entities1, entities2, 1)
             if i * sub_num >= self.args.start_valid:
                 self.valid(self.args.stop_metric)
             t1 = time.time()
