@@ -14,6 +14,14 @@ os.environ.setdefault("OEA_CACHE_DIR", os.path.join(tempfile.gettempdir(), "oea_
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "first_hw_run: exercises code that has not yet executed on a GPU; collected last so "
+                                       "that under `-x` it cannot mask the tests of already verified code")
+
+
+def pytest_collection_modifyitems(config, items):
+    late = [it for it in items if it.get_closest_marker("first_hw_run")]
+    if late:
+        items[:] = [it for it in items if not it.get_closest_marker("first_hw_run")] + late
 
 
 @pytest.fixture(scope="session")

@@ -125,3 +125,54 @@ def test_rdgcn_builders_equal_reference_source():
     for i, j in ((0, 0), (0, 1), (3, 7), (R - 1, 2)):
         want = len(head[i] & head[j]) / len(head[i] | head[j]) + len(tail[i] & tail[j]) / len(tail[i] | tail[j])
         assert dual[i, j] == pytest.approx(want, rel=1e-6)
+
+
+def test_graph_builders_give_the_same_graphs_from_either_dataset_loader(tmp_path, monkeypatch):
+    """The adjacency / incidence builders of GCN-Align, AliNet and RDGCN consume the KG containers
+    (`relation_triples_list`, `relation_triples_set`, `entity_attributes_dict`, link lists); they must build identical
+    matrices from the array-backed loader (sorted, lazily built containers) and from the container-based loader."""
+    import contextlib
+    import io
+    import scipy.sparse as sp
+    from openea_b200 import gnn
+    from openea_b200.approaches import alinet, rdgcn
+    from openea_b200.modules.load.kgs import read_kgs_from_folder
+    from openea_b200.modules.utils.util import merge_dic
+    from openea_b200.synth import write_dataset
+    folder = write_dataset(str(tmp_path) + "/tiny/", "tiny")
+    monkeypatch.setenv("OEA_NO_DATASET_CACHE", "1")
+    built = {}
+    for loader in ("arrays", "containers"):
+        monkeypatch.setenv("OEA_LOADER", loader)
+        with contextlib.redirect_stdout(io.StringIO()):
+            kgs = read_kgs_from_folder(folder, "721_5fold/1/", "mapping", True)
+            n = kgs.entities_num
+            triples = kgs.kg1.relation_triples_list + kgs.kg2.relation_triples_list
+            out = {"gcn_adj": gnn.preprocess_adj(gnn.weighted_adjacency(n, triples)),
+                   "gcn_attr": gnn.attribute_features(n, merge_dic(kgs.kg1.entity_attributes_dict,
+                                                                   kgs.kg2.entity_attributes_dict))}
+            kg1, kg2 = alinet.AKG(kgs.kg1.relation_triples_set), alinet.AKG(kgs.kg2.relation_triples_set)
+            linked = set(kgs.train_entities1 + kgs.train_entities2 + kgs.valid_entities1 + kgs.test_entities1 +
+                         kgs.test_entities2 + kgs.valid_entities2)
+            enh1, enh2 = alinet.enhance_triples(kg1, kg2, kgs.train_entities1, kgs.train_entities2)
+            tri = alinet.remove_unlinked_triples(kg1.triple_list + kg2.triple_list + list(enh1) + list(enh2), linked)
+            out["alinet_one"] = alinet.no_weighted_adj(n, tri)[0]
+            two = alinet.generate_2hop_triples(kg1, linked) | alinet.generate_2hop_triples(kg2, linked)
+            out["alinet_two"] = alinet.no_weighted_adj(n, list(two))[0]
+            out["alinet_rel_ht"] = {r: (sorted(v[0]), sorted(v[1])) if isinstance(v, tuple) else sorted(v)
+                                    for r, v in alinet.generate_rel_ht(tri).items()}
+            out["rdgcn_M"] = rdgcn.get_sparse_matrix(triples, n)
+            head_r, tail_r, _ = rdgcn.rfunc(triples, n, kgs.relations_num)
+            out["rdgcn_head_r"], out["rdgcn_tail_r"] = head_r, tail_r
+        built[loader] = out
+    a, b = built["arrays"], built["containers"]
+    assert a.keys() == b.keys()
+    for name in a:
+        x, y = a[name], b[name]
+        if name == "alinet_rel_ht":
+            assert x == y
+            continue
+        if isinstance(x, tuple):         # sparse_to_tuple form: (coords, values, shape)
+            x, y = sp.coo_matrix((x[1], (x[0][:, 0], x[0][:, 1])), shape=x[2]), sp.coo_matrix((y[1], (y[0][:, 0], y[0][:, 1])), shape=y[2])
+        x, y = sp.csr_matrix(x), sp.csr_matrix(y)
+        assert x.shape == y.shape and abs(x - y).max() < 1e-6, name

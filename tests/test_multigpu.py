@@ -92,6 +92,7 @@ def _gcn_worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
+@pytest.mark.first_hw_run
 def test_row_sharded_gcn_unit_equals_single_gpu():
     """SURVEY §8e-ii over NCCL: the row-sharded GCN-Align unit (liboea kernels + 3 all-gathers / 3 reduce-scatters per
     step) reproduces the single-GPU unit's loss, outputs and updated entity table."""

@@ -288,6 +288,7 @@ def test_score_family_lifecycle(cuda_device, tiny_kgs, tmp_path, name):
     assert ent.shape == (model.kgs.entities_num, 32) and np.isfinite(ent).all()
 
 
+@pytest.mark.first_hw_run      # passed on a B200 with the host bootstrapping; BootEA.run now bootstraps on the device
 def test_bootea_transh_lifecycle(cuda_device, tiny_kgs, tmp_path):
     from openea_b200 import presets
     from openea_b200.approaches import BootEA_TransH
