@@ -213,6 +213,24 @@ class AliNetModel:
                 p["hw%d.bn_gamma" % i], p["hw%d.bn_beta" % i] = torch.ones(1, do), torch.zeros(1, do)
         self.params = {k: v.to(device).requires_grad_(True) for k, v in p.items()}
         self.n_layers = n_layers
+        # the two sparse aggregations (liboea kernels with autograd wrappers); the row-sharded model and the gloo test of
+        # its collective algebra replace them per instance
+        self.spmm_fn, self.gat_fn = gnn.SpmmFn.apply, gnn.GatAggregateFn.apply
+
+    # hooks of the row-sharded variant (openea_b200/parallel_gnn.ShardedAliNetModel): identity on one GPU
+    def _layer_input(self, x):
+        """What an aggregation reads: all rows of x."""
+        return x
+
+    def _layer_outputs(self, outs):
+        return outs
+
+    def input_embedding(self):
+        """All rows of the input embedding table."""
+        return self.params["init_embedding"]
+
+    def set_adj1(self, mat, device):
+        self.adj1 = gnn.DeviceCsr(mat, device)
 
     def forward(self):
         """Returns [layer outputs…] (alinet.py:784-826)."""
@@ -221,13 +239,14 @@ class AliNetModel:
         outs = []
         for i in range(self.n_layers):
             xb = _bn(x, P["gcn%d.bn_gamma" % i], P["gcn%d.bn_beta" % i])
-            one = torch.tanh(gnn.SpmmFn.apply(xb @ P["gcn%d.kernel" % i], self.adj1) + P["gcn%d.bias" % i])
+            one = torch.tanh(self.spmm_fn(self._layer_input(xb @ P["gcn%d.kernel" % i]), self.adj1) + P["gcn%d.bias" % i])
             if i < self.n_layers - 1:
                 xg = _bn(x, P["gat%d.bn_gamma" % i], P["gat%d.bn_beta" % i])
                 mapped = xg @ P["gat%d.kernel" % i]
                 s1 = torch.tanh(((xg @ P["gat%d.kernel1" % i]) * xg).sum(1))
                 s2 = torch.tanh(((xg @ P["gat%d.kernel2" % i]) * xg).sum(1))
-                two = torch.tanh(gnn.GatAggregateFn.apply(s1, s2, mapped, self.adj2, LEAKY_SLOPE))
+                two = torch.tanh(self.gat_fn(s1, self._layer_input(s2[:, None])[:, 0], self._layer_input(mapped),
+                                             self.adj2, LEAKY_SLOPE))
                 g_in1 = _bn(two, P["hw%d.bn_gamma" % i], P["hw%d.bn_beta" % i])   # one BN object serves both inputs
                 g_in2 = _bn(one, P["hw%d.bn_gamma" % i], P["hw%d.bn_beta" % i])
                 gate = torch.relu(torch.tanh(g_in1 @ P["hw%d.kernel" % i]))
@@ -235,11 +254,11 @@ class AliNetModel:
             else:
                 x = one
             outs.append(x)
-        return outs
+        return self._layer_outputs(outs)
 
     def concat_embeds(self, outs):
         """l2-normalised concatenation of every layer's l2-normalised output + the input embedding (:832-837)."""
-        return _l2n(torch.cat([_l2n(o) for o in outs + [self.params["init_embedding"]]], dim=1))
+        return _l2n(torch.cat([_l2n(o) for o in outs + [self.input_embedding()]], dim=1))
 
     def loss(self, outs, pos_links, neg_links, neg_margin, balance, hs=None, ts=None, rel_win=None, rel_param=0.0):
         emb = self.concat_embeds(outs)
@@ -344,8 +363,18 @@ class AliNet(BasicModel):
         self.sim_th = self.args.sim_th
         self.sup_links = np.stack([np.array(self.sup_ent1), np.array(self.sup_ent2)], 1)
         self.sup_links_set = set(zip(self.sup_ent1, self.sup_ent2))
-        self.model = AliNetModel(self.kgs.entities_num, self.args.layer_dims, gnn.DeviceCsr(adj[0], dev),
-                                 gnn.DeviceCsr(adj[1], dev), dev, seed=getattr(self.args, "seed", 0) or 0)
+        seed = getattr(self.args, "seed", 0) or 0
+        from openea_b200 import parallel as par
+        if par.world()[1] > 1:
+            # one process per GPU (torchrun): rows of both adjacencies, of every layer and of the input embedding table
+            # are sharded (openea_b200/parallel_gnn.py); batches must be identical on every rank
+            from openea_b200 import parallel_gnn as pg
+            random.seed(seed)
+            np.random.seed(seed)
+            self.model = pg.ShardedAliNetModel(self.kgs.entities_num, self.args.layer_dims, adj[0], adj[1], dev, seed=seed)
+        else:
+            self.model = AliNetModel(self.kgs.entities_num, self.args.layer_dims, gnn.DeviceCsr(adj[0], dev),
+                                     gnn.DeviceCsr(adj[1], dev), dev, seed=seed)
         self.optimizer = DenseAdam(list(self.model.params.values()), self.args.learning_rate)
 
     # ---- batches (alinet.py:983-1017) ----
@@ -405,7 +434,7 @@ class AliNet(BasicModel):
     def _concat_rows(self, ids):
         with torch.no_grad():
             outs = self.model.forward()
-            parts = [_l2n(_l2n(o)[torch.as_tensor(ids, device=o.device)]) for o in [self.model.params["init_embedding"]] + outs]
+            parts = [_l2n(_l2n(o)[torch.as_tensor(ids, device=o.device)]) for o in [self.model.input_embedding()] + outs]
         return torch.cat(parts, dim=1)
 
     def _eval_valid_embeddings(self):
@@ -420,7 +449,7 @@ class AliNet(BasicModel):
     def save(self):
         with torch.no_grad():
             outs = self.model.forward()
-            ent = torch.cat([_l2n(o) for o in [self.model.params["init_embedding"]] + outs], dim=1).cpu().numpy()
+            ent = torch.cat([_l2n(o) for o in [self.model.input_embedding()] + outs], dim=1).cpu().numpy()
         rd.save_embeddings(self.out_folder, self.kgs, ent, None, None, mapping_mat=None)
 
     # ---- neighbourhood augmentation (alinet.py:885-920; disabled by sim_th = 0 in the shipped configs) ----
@@ -446,7 +475,7 @@ class AliNet(BasicModel):
                                           list(self.new_edges2), self.linked_ents)
         one_adj, _ = no_weighted_adj(self.kgs.entities_num, triples)
         print("gcn update adj...")
-        self.model.adj1 = gnn.DeviceCsr(one_adj, self.session.device)
+        self.model.set_adj1(one_adj, self.session.device)
 
     def train_step(self, pos_links, neg_links, hs=None, ts=None):
         dev = self.session.device
@@ -456,6 +485,8 @@ class AliNet(BasicModel):
                                None if hs is None else tl(hs), None if ts is None else tl(ts), self.rel_win_size,
                                self.args.rel_param)
         loss.backward()
+        if hasattr(self.model, "sync_grads"):        # row-sharded model: partial gradients of the replicated weights
+            self.model.sync_grads()
         self.optimizer.step()
         return float(loss.detach().item())
 

@@ -190,3 +190,82 @@ class ShardedGCNAlignUnit:
                 dist.all_reduce(g_w)
         self.ops.update(self.table, g_w, self.lr)
         return self.loss_dev
+
+
+# ---- AliNet (approaches/alinet.py:539-677,784-866) across GPUs ---------------------------------------------------------------
+class AllGatherRows(torch.autograd.Function):
+    """[block, p] per rank → [n_pad, p] on every rank, inside an autograd graph.
+
+    The backward depends on who consumes the gathered rows:
+      partitioned consumer (each rank aggregates into ITS rows, e.g. A_r · X): the gradients of the ranks are partial
+          sums over disjoint outputs → reduce-scatter;
+      replicated consumer (every rank computes the same thing from the full tensor, e.g. the loss on a batch of
+          pairs): every rank already holds the complete gradient → keep the own rows, no communication."""
+
+    @staticmethod
+    def forward(ctx, x_local, shard, replicated_consumer):
+        ctx.shard, ctx.replicated = shard, replicated_consumer
+        return all_gather_rows(x_local.contiguous(), shard)
+
+    @staticmethod
+    def backward(ctx, g_full):
+        sh = ctx.shard
+        if ctx.replicated or sh.world == 1:
+            return g_full[sh.rank * sh.block:(sh.rank + 1) * sh.block].contiguous(), None, None
+        return reduce_scatter_rows(g_full, sh), None, None
+
+
+def make_sharded_alinet(base_cls):
+    """ShardedAliNetModel over the (late-imported) AliNetModel: same parameters, same forward code, with
+      * the input embedding table, both adjacencies and every layer's rows sharded by `RowShard`;
+      * an all-gather in front of every aggregation (partitioned consumer) and after the last layer op of each block
+        (replicated consumer: loss, evaluation and neighbour search run unchanged on all rows on every rank);
+      * the small dense weights replicated, their partial gradients all-reduced by `sync_grads()` before the optimiser.
+    Exchanges per forward with L = 2 aggregation layers: 1 (X·W) + 2 (attention scores, mapped rows) per layer + one
+    gather per layer output + the input table = 8 all-gathers of N_pad·d·4 B."""
+
+    class ShardedAliNetModel(base_cls):
+
+        def __init__(self, n_ent, layer_dims, adj1, adj2, device, seed=0, shard=None, ops=None):
+            self.shard = shard or RowShard(n_ent)
+            self.ops = ops or KernelOps()
+            self.n_ent = n_ent
+            sh = self.shard
+            super().__init__(n_ent, layer_dims, self.ops.csr(sh.square_rows_of(adj1), device),
+                             self.ops.csr(sh.square_rows_of(adj2), device), device, seed=seed)
+            # every rank drew the same full table from the same generator: keep the owned rows only
+            full = self.params["init_embedding"].detach()
+            local = torch.zeros(sh.block, full.shape[1], dtype=full.dtype, device=full.device)
+            local[:sh.hi - sh.lo] = full[sh.lo:sh.hi]
+            self.params["init_embedding"] = local.requires_grad_(True)
+
+        def _layer_input(self, x):
+            return AllGatherRows.apply(x, self.shard, False)
+
+        def _layer_outputs(self, outs):
+            return [AllGatherRows.apply(o, self.shard, True)[:self.n_ent] for o in outs]
+
+        def input_embedding(self):
+            return AllGatherRows.apply(self.params["init_embedding"], self.shard, True)[:self.n_ent]
+
+        def set_adj1(self, mat, device):
+            self.adj1 = self.ops.csr(self.shard.square_rows_of(mat), device)
+
+        def sync_grads(self):
+            """Sum the partial gradients of the replicated parameters (everything but the sharded input table)."""
+            if self.shard.world == 1:
+                return
+            for name, p in self.params.items():
+                if name != "init_embedding" and p.grad is not None:
+                    dist.all_reduce(p.grad)
+
+    return ShardedAliNetModel
+
+
+def __getattr__(name):            # ShardedAliNetModel is built on first use: alinet.py imports this module's siblings
+    if name == "ShardedAliNetModel":
+        from .approaches.alinet import AliNetModel
+        cls = make_sharded_alinet(AliNetModel)
+        globals()[name] = cls
+        return cls
+    raise AttributeError(name)

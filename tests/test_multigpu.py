@@ -109,3 +109,65 @@ def test_row_sharded_gcn_unit_equals_single_gpu():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
+def _alinet_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import scipy.sparse as sp
+        from openea_b200 import gnn, parallel_gnn as pg
+        from openea_b200.approaches.alinet import AliNetModel
+        rng = np.random.default_rng(11)
+        n, dims = 3001, [64, 48, 32]
+        a1 = sp.csr_matrix(sp.random(n, n, density=0.003, random_state=1, format="csr", dtype=np.float32) + sp.eye(n, dtype=np.float32))
+        a2 = sp.csr_matrix(sp.random(n, n, density=0.006, random_state=2, format="csr", dtype=np.float32) + sp.eye(n, dtype=np.float32))
+        a2.data[:] = 1.0
+        dev = torch.device("cuda", rank)
+        pos = torch.as_tensor(np.stack([rng.permutation(n)[:200], rng.permutation(n)[:200]], 1), device=dev)
+        neg = torch.as_tensor(np.stack([rng.integers(0, n, 2000), rng.integers(0, n, 2000)], 1), device=dev)
+        ref = AliNetModel(n, dims, gnn.DeviceCsr(a1, dev), gnn.DeviceCsr(a2, dev), dev, seed=3)
+        ref_outs = ref.forward()
+        ref_loss = ref.loss(ref_outs, pos, neg, 1.5, 0.1)
+        ref_loss.backward()
+        shard = pg.RowShard(n)
+        model = pg.ShardedAliNetModel(n, dims, a1, a2, dev, seed=3, shard=shard)
+        outs = model.forward()
+        for o, r in zip(outs, ref_outs):
+            torch.testing.assert_close(o, r, rtol=1e-4, atol=1e-5)
+        loss = model.loss(outs, pos, neg, 1.5, 0.1)
+        torch.testing.assert_close(loss, ref_loss, rtol=1e-4, atol=1e-4)
+        loss.backward()
+        model.sync_grads()
+        for name, p in model.params.items():
+            want = ref.params[name].grad
+            if name == "init_embedding":
+                want = torch.as_tensor(shard.local_rows(want.cpu().numpy()), device=dev)
+            torch.testing.assert_close(p.grad, want, rtol=1e-3, atol=1e-5, msg=lambda m, name=name: "%s: %s" % (name, m))
+        out.put((rank, "ok"))
+    except Exception as e:
+        import traceback
+        out.put((rank, "FAIL: %r\n%s" % (e, traceback.format_exc())))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.first_hw_run
+def test_row_sharded_alinet_model_equals_single_gpu():
+    """The row-sharded AliNet model (liboea aggregation kernels on rectangular row blocks + autograd all-gathers) gives
+    the single-GPU model's layer outputs, loss and gradients."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_alinet_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res

@@ -150,3 +150,77 @@ def test_row_shard_partition_is_exact():
         rows.append(blk[:sh.hi - sh.lo, :10])
         assert blk[sh.hi - sh.lo:].nnz == 0
     assert (sp.vstack(rows) != m).nnz == 0
+
+
+# ---- AliNet: row-sharded model vs the single-process model (same forward code, torch stand-ins for the kernels) ----------
+def _alinet_standins(model):
+    from oracle.gnn import edge_softmax_aggregate
+    model.spmm_fn = lambda X, A: torch.sparse.mm(A.t, X)
+    model.gat_fn = lambda s1, s2, M, A, slope: edge_softmax_aggregate(A.m, s1, s2, M, slope)
+
+
+def _alinet_problem():
+    rng = np.random.default_rng(11)
+    n = 47
+    a1 = sp.random(n, n, density=0.1, random_state=1, format="csr", dtype=np.float32) + sp.eye(n, dtype=np.float32)
+    a2 = sp.random(n, n, density=0.15, random_state=2, format="csr", dtype=np.float32) + sp.eye(n, dtype=np.float32)
+    a2.data[:] = 1.0
+    pos = np.stack([rng.permutation(n)[:9], rng.permutation(n)[:9]], 1)
+    neg = np.stack([rng.integers(0, n, 40), rng.integers(0, n, 40)], 1)
+    return n, [8, 8, 4], sp.csr_matrix(a1), sp.csr_matrix(a2), torch.as_tensor(pos), torch.as_tensor(neg)
+
+
+def _alinet_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from openea_b200 import parallel_gnn as pg
+        from openea_b200.approaches.alinet import AliNetModel
+        n, dims, a1, a2, pos, neg = _alinet_problem()
+        ops = TorchOps()
+        ref = AliNetModel(n, dims, ops.csr(a1, "cpu"), ops.csr(a2, "cpu"), torch.device("cpu"), seed=3)
+        _alinet_standins(ref)
+        ref_outs = ref.forward()
+        ref_loss = ref.loss(ref_outs, pos, neg, 1.5, 0.1)
+        ref_loss.backward()
+
+        shard = pg.RowShard(n)
+        model = pg.ShardedAliNetModel(n, dims, a1, a2, torch.device("cpu"), seed=3, shard=shard, ops=ops)
+        _alinet_standins(model)
+        assert model.params["init_embedding"].shape[0] == shard.block
+        outs = model.forward()
+        for o, r in zip(outs, ref_outs):
+            assert o.shape == r.shape
+            torch.testing.assert_close(o, r, rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(model.input_embedding(), ref.params["init_embedding"])
+        loss = model.loss(outs, pos, neg, 1.5, 0.1)          # replicated consumer: the same value on every rank
+        torch.testing.assert_close(loss, ref_loss, rtol=1e-5, atol=1e-6)
+        loss.backward()
+        model.sync_grads()
+        for name, p in model.params.items():
+            want = ref.params[name].grad
+            if name == "init_embedding":
+                want = torch.as_tensor(shard.local_rows(want.numpy()))
+            assert p.grad is not None, name
+            torch.testing.assert_close(p.grad, want, rtol=1e-4, atol=1e-6, msg=lambda m, name=name: "%s: %s" % (name, m))
+        out.put((rank, "ok"))
+    except Exception as e:  # surface the failure in the parent
+        import traceback
+        out.put((rank, "FAIL: %r\n%s" % (e, traceback.format_exc())))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_alinet_model_equals_single_process_model(world):
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_alinet_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(r, "ok") for r in range(world)], res
