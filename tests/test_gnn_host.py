@@ -172,6 +172,17 @@ def test_graph_builders_give_the_same_graphs_from_either_dataset_loader(tmp_path
         if name == "alinet_rel_ht":
             assert x == y
             continue
+        if name == "gcn_attr":
+            # load_attr ranks attributes by frequency with ties in dict / set iteration order (string hashes differ
+            # per process, in the reference too): compare the columns as a multiset, leaving out the least frequent
+            # ones, where a tie at the 70 % cut-off may select different attributes
+            def columns(m):
+                m = sp.csc_matrix(m)
+                cols = [tuple(m.indices[m.indptr[j]:m.indptr[j + 1]].tolist()) for j in range(m.shape[1])]
+                cut = min(len(c) for c in cols)
+                return sorted(c for c in cols if len(c) > cut)
+            assert x.shape == y.shape and columns(x) == columns(y)
+            continue
         if isinstance(x, tuple):         # sparse_to_tuple form: (coords, values, shape)
             x, y = sp.coo_matrix((x[1], (x[0][:, 0], x[0][:, 1])), shape=x[2]), sp.coo_matrix((y[1], (y[0][:, 0], y[0][:, 1])), shape=y[2])
         x, y = sp.csr_matrix(x), sp.csr_matrix(y)
