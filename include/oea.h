@@ -45,7 +45,7 @@ enum { OEA_SCORE_L1 = 0, OEA_SCORE_L2SQ = 1 };
 enum { OEA_LOSS_MARGIN = 0, OEA_LOSS_LIMITED = 1, OEA_LOSS_LOGISTIC = 2, OEA_LOSS_POSITIVE = 3,
        OEA_LOSS_LOGSIGMOID = 4 };
 /* modules/base/optimizers.py:10-20 (TF1 semantics: Adagrad acc0 = 0.1 and no epsilon; TF-Adam) */
-enum { OEA_OPT_SGD = 0, OEA_OPT_ADAGRAD = 1, OEA_OPT_ADAM = 2 };
+enum { OEA_OPT_SGD = 0, OEA_OPT_ADAGRAD = 1, OEA_OPT_ADAM = 2, OEA_OPT_ADADELTA = 3 };
 
 /* An embedding table as TF holds it: the raw variable + optimiser slots (+ our gradient scratch).
  * Replaces the tf.Variable made by modules/base/initializers.py:9-50; `l2_norm` mirrors the
@@ -76,7 +76,7 @@ typedef struct oea_loss_cfg {
 typedef struct oea_opt_cfg {
     int32_t kind;         /* OEA_OPT_* */
     float   lr;
-    float   beta1, beta2, eps;  /* Adam only (TF defaults .9 / .999 / 1e-8) */
+    float   beta1, beta2, eps;  /* Adam (TF defaults .9 / .999 / 1e-8); Adadelta: beta1 = rho (.95), eps = epsilon (1e-8) */
     int32_t t;            /* Adam only: 1-based step count */
 } oea_opt_cfg;
 
@@ -134,6 +134,11 @@ int oea_triple_score_fed(const oea_table* ent, const oea_table* rel,
  * rows (identical to TF's dense update because untouched rows have g = 0); Adam is dense.
  * Leaves grad = 0 and touched = 0. */
 int oea_rowopt_apply(const oea_table* table, const oea_opt_cfg* opt, void* stream);
+
+/* tf.train.AdadeltaOptimizer (optimizers.py:13-15): dense update of every row (both accumulators decay on rows without
+ * gradient); state1 = accum, state2 = accum_update, both start at 0; opt->beta1 = rho, opt->eps = epsilon.
+ * oea_rowopt_apply dispatches OEA_OPT_ADADELTA here.  Leaves grad = 0 and touched = 0. */
+int oea_rowopt_adadelta(const oea_table* table, const oea_opt_cfg* opt, void* stream);
 
 /* The optimiser step of BOTH tables in one launch (Adagrad / SGD; Adam falls back to two dense launches).
  * Same semantics as two oea_rowopt_apply calls. */

@@ -778,6 +778,8 @@ extern "C" int oea_rowopt_apply(const oea_table* t, const oea_opt_cfg* opt, void
         case OEA_OPT_SGD:
             k_rowopt<OEA_OPT_SGD><<<grid, kThreads, 0, st>>>(t->weight, t->grad, nullptr, nullptr, t->touched, t->rows, t->pitch, opt->lr, 0.f, 0.f, 0.f, 0.f);
             break;
+        case OEA_OPT_ADADELTA:
+            return oea_rowopt_adadelta(t, opt, stream);   // oea_optim_ext.cu
         case OEA_OPT_ADAM: {
             if (!t->state1 || !t->state2) return OEA_ERR_NULL;
             if (opt->t < 1) return OEA_ERR_RANGE;
@@ -1181,7 +1183,7 @@ extern "C" int oea_rowopt_apply_pair(const oea_table* a, const oea_table* b, con
     int rc = check_table(a, true); if (rc) return rc;
     rc = check_table(b, true); if (rc) return rc;
     if (!opt) return OEA_ERR_NULL;
-    if (opt->kind == OEA_OPT_ADAM || a->pitch != b->pitch) {   // dense Adam / mismatched pitch: two launches
+    if (opt->kind == OEA_OPT_ADAM || opt->kind == OEA_OPT_ADADELTA || a->pitch != b->pitch) {   // dense rules / mismatched pitch: two launches
         rc = oea_rowopt_apply(a, opt, stream); if (rc) return rc;
         return oea_rowopt_apply(b, opt, stream);
     }

@@ -61,6 +61,9 @@ class EmbeddingTable:
         elif self.optimizer == "Adam":
             self.state1 = torch.zeros_like(self.weight)
             self.state2 = torch.zeros_like(self.weight)
+        elif self.optimizer == "Adadelta":       # tf.train.AdadeltaOptimizer: accum and accum_update start at 0
+            self.state1 = torch.zeros_like(self.weight)
+            self.state2 = torch.zeros_like(self.weight)
         elif self.optimizer in ("SGD", "GradientDescent"):
             self.optimizer = "SGD"
         else:
@@ -133,7 +136,9 @@ def loss_cfg(loss, loss_norm, margin=0.0, neg_margin=0.0, balance=1.0):
 
 
 def opt_cfg(table, lr):
-    kind = {"SGD": L.OPT_SGD, "Adagrad": L.OPT_ADAGRAD, "Adam": L.OPT_ADAM}[table.optimizer]
+    kind = {"SGD": L.OPT_SGD, "Adagrad": L.OPT_ADAGRAD, "Adam": L.OPT_ADAM, "Adadelta": L.OPT_ADADELTA}[table.optimizer]
+    if kind == L.OPT_ADADELTA:      # TF1 defaults rho = 0.95, epsilon = 1e-8 (beta1 carries rho)
+        return L.OptCfg(kind, float(lr), 0.95, 0.0, 1e-8, 1)
     return L.OptCfg(kind, float(lr), 0.9, 0.999, 1e-8, max(1, table.adam_t))
 
 

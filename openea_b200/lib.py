@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("OEA_LIB_PATH") or os.path.join(_HERE, "_lib", "liboea
 
 SCORE_L1, SCORE_L2SQ = 0, 1
 LOSS_MARGIN, LOSS_LIMITED, LOSS_LOGISTIC, LOSS_POSITIVE, LOSS_LOGSIGMOID = 0, 1, 2, 3, 4
-OPT_SGD, OPT_ADAGRAD, OPT_ADAM = 0, 1, 2
+OPT_SGD, OPT_ADAGRAD, OPT_ADAM, OPT_ADADELTA = 0, 1, 2, 3
 METRIC_INNER, METRIC_L1, METRIC_L2 = 0, 1, 2
 MODEL_TRANSE, MODEL_TRANSH, MODEL_TRANSD, MODEL_DISTMULT, MODEL_SIMPLE = 0, 1, 2, 3, 4
 
@@ -82,6 +82,7 @@ SIGNATURES = {
     "oea_triple_score_fed": (C.c_int, [_TP, _TP, _P, _P, _P, _I, _P, _P, _P, _I, C.POINTER(LossCfg), _P, _P]),
     "oea_rowopt_apply": (C.c_int, [_TP, C.POINTER(OptCfg), _P]),
     "oea_rowopt_apply_pair": (C.c_int, [_TP, _TP, C.POINTER(OptCfg), _P]),
+    "oea_rowopt_adadelta": (C.c_int, [_TP, C.POINTER(OptCfg), _P]),
     "oea_triple_step_sampled": (C.c_int, [_TP, _TP, C.POINTER(KgView), C.POINTER(KgView), C.POINTER(TripleSet),
                                           C.POINTER(SampleCfg), C.POINTER(LossCfg), C.POINTER(OptCfg), _P, _P, _P]),
     "oea_triple_score_sampled": (C.c_int, [_TP, _TP, C.POINTER(KgView), C.POINTER(KgView), C.POINTER(TripleSet),

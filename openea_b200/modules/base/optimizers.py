@@ -15,9 +15,7 @@ from openea_b200.engine import EmbeddingTable, _ptr, _stream_ptr, opt_cfg
 
 class RowOptimizer:
     def __init__(self, opt, learning_rate):
-        if opt == 'Adadelta':
-            raise NotImplementedError("Adadelta is not on the accelerated path (no shipped config uses it)")
-        self.kind = opt if opt in ('Adagrad', 'Adam') else 'SGD'
+        self.kind = opt if opt in ('Adagrad', 'Adam', 'Adadelta') else 'SGD'
         self.lr = float(learning_rate)
         self._slots = {}
 

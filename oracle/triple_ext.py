@@ -113,7 +113,7 @@ class DenseState:
         self.optimizer, self.t = optimizer, 0
         if optimizer == "Adagrad":
             self.s1 = {k: np.full_like(v, 0.1) for k, v in self.w.items()}
-        elif optimizer == "Adam":
+        elif optimizer in ("Adam", "Adadelta"):
             self.s1 = {k: np.zeros_like(v) for k, v in self.w.items()}
             self.s2 = {k: np.zeros_like(v) for k, v in self.w.items()}
 
@@ -129,6 +129,12 @@ class DenseState:
                 self.s2[k] = b2 * self.s2[k] + (1 - b2) * g * g
                 lr_t = lr * np.sqrt(1 - b2 ** self.t) / (1 - b1 ** self.t)
                 self.w[k] -= lr_t * self.s1[k] / (np.sqrt(self.s2[k]) + eps)
+            elif self.optimizer == "Adadelta":     # TF1 ApplyAdadelta, rho = 0.95, epsilon = 1e-8 (optimizers.py:13-15)
+                rho, eps = 0.95, 1e-8
+                self.s1[k] = rho * self.s1[k] + (1 - rho) * g * g
+                upd = np.sqrt(self.s2[k] + eps) / np.sqrt(self.s1[k] + eps) * g
+                self.w[k] -= lr * upd
+                self.s2[k] = rho * self.s2[k] + (1 - rho) * upd * upd
             else:
                 self.w[k] -= lr * g
 

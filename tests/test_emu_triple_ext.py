@@ -115,3 +115,33 @@ def test_emulated_entry_point_argument_checks(emu):
     wide = {s: HostTable(np.zeros((t.weight.shape[0], 300), dtype=np.float32), True) for s, t in tables.items()}
     rc, _ = _run(emu, "TransD", slots, wide, pos, neg, "limited", "L2", 1.0)
     assert rc == 2                                        # OEA_ERR_DIM: pitch > 256
+
+
+def test_emulated_adadelta_update_matches_tf_rule(emu):
+    """oea_rowopt_adadelta (openea_b200/csrc/oea_optim_ext.cu) on the emulator: three dense steps equal TF1's ApplyAdadelta
+    (rho 0.95, epsilon 1e-8) on every row — rows without gradient decay their accumulators too — and leave grad /
+    touched zeroed."""
+    res, args = L.SIGNATURES["oea_rowopt_adadelta"]
+    emu.oea_rowopt_adadelta.restype, emu.oea_rowopt_adadelta.argtypes = res, args
+    rng = np.random.default_rng(2)
+    rows, d = 37, 10                                            # pitch 12
+    tab = HostTable(rng.standard_normal((rows, d)).astype(np.float32), False)
+    acc, acc_upd = np.zeros_like(tab.weight), np.zeros_like(tab.weight)
+    tab.struct = L.Table(tab.weight.ctypes.data, tab.grad.ctypes.data, acc.ctypes.data, acc_upd.ctypes.data,
+                         tab.touched.ctypes.data, rows, d, tab.pitch, 0)
+    st = ox.DenseState({"t": tab.weight[:, :d]}, "Adadelta")
+    cfg = L.OptCfg(L.OPT_ADADELTA, 0.7, 0.95, 0.0, 1e-8, 1)
+    for step in range(3):
+        g = np.zeros((rows, d), dtype=np.float32)
+        hot = rng.choice(rows, 9, replace=False)
+        g[hot] = rng.standard_normal((9, d)).astype(np.float32)
+        tab.grad[:, :d] = g
+        tab.touched[hot] = 1
+        assert emu.oea_rowopt_adadelta(C.byref(tab.struct), C.byref(cfg), None) == 0
+        st.apply({"t": g.astype(np.float64)}, 0.7)
+        np.testing.assert_allclose(tab.weight[:, :d], st.w["t"], rtol=2e-5, atol=1e-7)
+        np.testing.assert_allclose(acc[:, :d], st.s1["t"], rtol=2e-5, atol=1e-12)
+        np.testing.assert_allclose(acc_upd[:, :d], st.s2["t"], rtol=1e-4, atol=1e-12)
+        assert not tab.grad.any() and not tab.touched.any() and not tab.weight[:, d:].any()
+    bad = L.OptCfg(L.OPT_ADAM, 0.7, 0.95, 0.0, 1e-8, 1)
+    assert emu.oea_rowopt_adadelta(C.byref(tab.struct), C.byref(bad), None) == 4      # OEA_ERR_KIND

@@ -133,6 +133,30 @@ def test_model_training_steps_equal_dense_tf_steps(cuda_device, model, loss, k, 
             assert not tab.grad.any().item() and not tab.touched.any().item()
 
 
+@pytest.mark.first_hw_run
+def test_adadelta_steps_equal_dense_tf_steps(cuda_device):
+    """tf.train.AdadeltaOptimizer through oea_rowopt_apply (dense rule: rows without gradient decay their accumulators):
+    three TransE steps equal the oracle's dense steps on every row."""
+    eng = _engine()
+    d, n_ent, n_rel = 100, 900, 17
+    rng, slots, tabs, norms = _case("TransE", 21, n_ent, n_rel, d, True)
+    kw = dict(margin=0.05, neg_margin=1.8, balance=0.25)
+    st = ox.DenseState(tabs, "Adadelta")
+    tables = _tables(slots, tabs, norms, "Adadelta")
+    tr = eng.ModelTrainer("TransE", tables, eng.loss_cfg("limited", "L2", **kw), lr=1.0)
+    for it in range(3):
+        pos, neg = make_batch(rng, n_ent, n_rel, 200, 4)
+        want = ox.step(st, "TransE", norms, pos, neg, "limited", 1.0, **kw)
+        tr.score_fed(_dev(pos), _dev(neg))
+        tr.apply()
+        assert tr.read_loss() == pytest.approx(want, rel=LOSS_TOL), it
+    for s, tab in zip(slots, tables):
+        if s is not None:
+            _assert_rows_close(tab.raw().cpu().numpy(), st.w[s], "%s after 3 Adadelta steps" % s)
+            np.testing.assert_allclose(tab.state1[:, :d].cpu().numpy(), st.s1[s], rtol=1e-4, atol=1e-9)
+            assert not tab.grad.any().item() and not tab.touched.any().item()
+
+
 def _tiny_kgs(rng, n_ent_kg=300, n_rel=11, n_tri=2000):
     """Two KGs over disjoint entity id ranges (0..n) and (n..2n), relation ids shared."""
     def kg(lo):
