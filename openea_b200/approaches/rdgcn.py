@@ -99,18 +99,21 @@ class RDGCNLayer:
         self.alpha, self.beta, self.gamma, self.k = args.alpha, args.beta, args.gamma, args.neg_triple_num
         triples = kgs.kg1.relation_triples_list + kgs.kg2.relation_triples_list
         E, R = kgs.entities_num, kgs.relations_num
-        self.M = gnn.DeviceCsr(get_sparse_matrix(triples, E), device)
+        # the sparse aggregations (liboea kernels with autograd wrappers); the row-sharded layer and the gloo test of
+        # its collective algebra replace them per instance
+        self.spmm_fn, self.edge_fn = gnn.SpmmFn.apply, gnn.EdgeLogitAggregateFn.apply
+        self.M = self._entity_rows(get_sparse_matrix(triples, E), device)
         head_r, tail_r, tri = rfunc(triples, E, R)
         norm = lambda m: sp.diags(1.0 / np.maximum(np.asarray(m.sum(1)).reshape(-1), 1e-30)) @ m
-        self.head_avg, self.tail_avg = gnn.DeviceCsr(norm(head_r), device), gnn.DeviceCsr(norm(tail_r), device)
+        self.head_avg, self.tail_avg = self._entity_cols(norm(head_r), device), self._entity_cols(norm(tail_r), device)
         self.dual_A = torch.from_numpy(dual_adjacency(head_r, tail_r)).to(device)
         self.bias_mat = -1e9 * (1.0 - (self.dual_A > 0).to(torch.float32))
         # r_mat: one entry per triple at (h, t) whose value is the relation id; CSR order gives the edge → relation map
         order = np.lexsort((tri[:, 2], tri[:, 0]))          # CSR built by hand: the COO→CSR conversion would SUM duplicates
         indptr = np.concatenate([[0], np.cumsum(np.bincount(tri[:, 0], minlength=E))])
         rm = sp.csr_matrix((tri[order, 1].astype(np.float64) + 1.0, tri[order, 2], indptr), shape=(E, E))
-        self.r_mat = gnn.DeviceCsr(rm, device, keep_duplicates=True)
-        assert self.r_mat.nnz == len(tri)
+        self.r_mat = self._entity_rows(rm, device, keep_duplicates=True)
+        assert self.r_mat.nnz == len(tri) or self.r_mat.shape[0] != E       # a row block holds its rows' triples only
         self.edge_rel = (self.r_mat.val - 1.0).round().to(torch.long)
         gen = torch.Generator().manual_seed(seed)
         d = self.dim
@@ -124,17 +127,41 @@ class RDGCNLayer:
         p["diag1.w"], p["diag2.w"] = torch.ones(1, d), torch.ones(1, d)
         for name in ("hw1", "hw2"):
             p[name + ".W"], p[name + ".b"] = _glorot((d, d), gen), torch.zeros(1, d)
+        p["X0"] = self._own_rows(p["X0"])
         self.params = {k_: v.to(device).requires_grad_(True) for k_, v in p.items()}
         ill = np.array(kgs.train_links)
         self.left = torch.as_tensor(ill[:, 0], dtype=torch.int32, device=device).contiguous()
         self.right = torch.as_tensor(ill[:, 1], dtype=torch.int32, device=device).contiguous()
+
+    # ---- hooks of the row-sharded variant (openea_b200/parallel_gnn.ShardedRDGCNLayer): identities on one GPU -------
+    def _entity_rows(self, mat, device, keep_duplicates=False):
+        """An [E, E] matrix that aggregates INTO entity rows: the rows this process owns."""
+        return gnn.DeviceCsr(mat, device, keep_duplicates=keep_duplicates)
+
+    def _entity_cols(self, mat, device):
+        """An [R, E] matrix that reduces OVER entity rows: the columns this process owns."""
+        return gnn.DeviceCsr(mat, device)
+
+    def _own_rows(self, x):
+        return x
+
+    def _all_rows(self, x):
+        """What an aggregation into entity rows reads: every entity row of x."""
+        return x
+
+    def _sum_over_owners(self, x):
+        """Completes a reduction over entity rows of which every process holds a part."""
+        return x
+
+    def _full_output(self, x):
+        return x
 
     # column 0 of the [·, 4] vectors is the real 1-filter conv weight (kept 4 wide for the 16-B row optimiser)
     def _vec(self, name):
         return self.params[name + ".w"][:, :1], self.params[name + ".b"][:, :1]
 
     def _dual_input(self, x):
-        return torch.cat([gnn.SpmmFn.apply(x, self.head_avg), gnn.SpmmFn.apply(x, self.tail_avg)], dim=1)
+        return self._sum_over_owners(torch.cat([self.spmm_fn(x, self.head_avg), self.spmm_fn(x, self.tail_avg)], dim=1))
 
     def _att(self, fts, values, f1, f2):
         w1, b1 = self._vec(f1)
@@ -146,7 +173,7 @@ class RDGCNLayer:
     def _sparse_att(self, x, dual_h, name):
         w, b = self._vec(name)
         edge_logits = (dual_h @ w + b).reshape(-1)[self.edge_rel]
-        return torch.relu(gnn.EdgeLogitAggregateFn.apply(edge_logits, x, self.r_mat, LEAKY_SLOPE))
+        return torch.relu(self.edge_fn(edge_logits, self._all_rows(x), self.r_mat, LEAKY_SLOPE))
 
     def _highway(self, l1, l2, name):
         gate = torch.sigmoid(l1 @ self.params[name + ".W"] + self.params[name + ".b"])
@@ -161,9 +188,9 @@ class RDGCNLayer:
         dual_x2 = self._dual_input(x1)
         dual_h2 = self._att(dual_x2 @ P["dual.W"] + P["dual.b"], dual_h1, "dual.f1", "dual.f2")
         x2 = x0 + self.beta * self._sparse_att(x1, dual_h2, "sp2")
-        g1 = self._highway(x2, torch.relu(gnn.SpmmFn.apply(x2 * P["diag1.w"], self.M)), "hw1")
-        g2 = torch.relu(gnn.SpmmFn.apply(g1 * P["diag2.w"], self.M))
-        return self._highway(g1, g2, "hw2")
+        g1 = self._highway(x2, torch.relu(self.spmm_fn(self._all_rows(x2 * P["diag1.w"]), self.M)), "hw1")
+        g2 = torch.relu(self.spmm_fn(self._all_rows(g1 * P["diag2.w"]), self.M))
+        return self._full_output(self._highway(g1, g2, "hw2"))
 
     def loss(self, out, negs):
         return gnn.AlignLossL1Fn.apply(out, self.left, self.right, self.k, negs, self.gamma)
@@ -199,8 +226,13 @@ class RDGCN(BasicModel):
         assert getattr(self.args, "dropout", 0) == 0, "every shipped config trains without dropout"
         self.session = load_session()
         self.local_name_vectors = self._name_vectors()
-        self.gcn_model = RDGCNLayer(self.args, self.kgs, self.local_name_vectors, self.session.device,
-                                    seed=getattr(self.args, "seed", 0) or 0)
+        from openea_b200 import parallel as par
+        layer_cls = RDGCNLayer
+        if par.world()[1] > 1:      # one process per GPU (torchrun): entity rows sharded (openea_b200/parallel_gnn.py)
+            from openea_b200 import parallel_gnn as pg
+            layer_cls = pg.ShardedRDGCNLayer
+        self.gcn_model = layer_cls(self.args, self.kgs, self.local_name_vectors, self.session.device,
+                                   seed=getattr(self.args, "seed", 0) or 0)
         self.optimizer = DenseAdam(list(self.gcn_model.params.values()), self.args.learning_rate)
 
     def _output(self):
@@ -234,6 +266,8 @@ class RDGCN(BasicModel):
             out = self.gcn_model.forward()
             loss = self.gcn_model.loss(out, negs)
             loss.backward()
+            if hasattr(self.gcn_model, "sync_grads"):      # row-sharded layer: partial gradients of the replicated weights
+                self.gcn_model.sync_grads()
             self.optimizer.step()
             print('epoch {}, avg. relation triple loss: {:.4f}, cost time: {:.4f}s'.format(i, float(loss.detach().item()),
                                                                                            time.time() - start))

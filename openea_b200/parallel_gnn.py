@@ -97,9 +97,9 @@ def reduce_scatter_rows(x_partial, shard):
 class KernelOps:
     """Rank-local numerics through liboea.so (the product path; raises when the library or the GPU is missing)."""
 
-    def csr(self, mat, device):
+    def csr(self, mat, device, keep_duplicates=False):
         from . import gnn
-        return gnn.DeviceCsr(mat, device)
+        return gnn.DeviceCsr(mat, device, keep_duplicates=keep_duplicates)
 
     def spmm(self, A, X, relu=False, mask_src=None):
         from . import gnn
@@ -262,10 +262,97 @@ def make_sharded_alinet(base_cls):
     return ShardedAliNetModel
 
 
-def __getattr__(name):            # ShardedAliNetModel is built on first use: alinet.py imports this module's siblings
+# ---- RDGCN (approaches/rdgcn.py:184-338) across GPUs ------------------------------------------------------------------------
+class AllReduceSum(torch.autograd.Function):
+    """Σ over ranks of partial results of a reduction over sharded rows, inside an autograd graph.  Every rank's part
+    enters the sum with weight one, and what consumes the sum on each rank contributes a partial gradient (its own
+    rows' share), so the backward is the same all-reduce."""
+
+    @staticmethod
+    def forward(ctx, x):
+        out = x.clone()
+        dist.all_reduce(out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous().clone()
+        dist.all_reduce(g)
+        return g
+
+
+def row_block_keep_duplicates(mat, shard):
+    """Rows [lo, hi) of a CSR matrix as [block, n_pad] WITHOUT merging duplicate entries (RDGCN's r_mat holds one entry
+    per triple, several of them at the same (h, t))."""
+    m = sp.csr_matrix(mat) if not sp.isspmatrix_csr(mat) else mat
+    a, b = m.indptr[shard.lo], m.indptr[shard.hi]
+    indptr = np.full(shard.block + 1, b - a, dtype=m.indptr.dtype)
+    indptr[:shard.hi - shard.lo + 1] = m.indptr[shard.lo:shard.hi + 1] - a
+    return sp.csr_matrix((m.data[a:b], m.indices[a:b], indptr), shape=(shard.block, shard.n_pad))
+
+
+def make_sharded_rdgcn(base_cls):
+    """ShardedRDGCNLayer over the (late-imported) RDGCNLayer: the entity rows of X0, of every intermediate and of the
+    entity-side matrices (M, r_mat) are sharded; the relation-side tensors (dual input / attention, [R, ·] with R ≈ 500)
+    are replicated.  Exchanges per forward: 2 all-reduces of [R, 2d] (the relation-incidence averages reduce over all
+    entity rows, each rank holding its column block of head_r / tail_r), 4 all-gathers of [N_pad, d] in front of the
+    entity-row aggregations, 1 all-gather of the output (replicated consumers: loss, hard-negative search, evaluation)."""
+
+    class ShardedRDGCNLayer(base_cls):
+
+        def __init__(self, args, kgs, embedding, device, seed=0, shard=None, ops=None):
+            self.shard = shard or RowShard(kgs.entities_num)
+            self.ops = ops or KernelOps()
+            self.n_ent = kgs.entities_num
+            super().__init__(args, kgs, embedding, device, seed=seed)
+
+        def _entity_rows(self, mat, device, keep_duplicates=False):
+            sh = self.shard
+            if keep_duplicates:
+                return self.ops.csr(row_block_keep_duplicates(mat, sh), device, keep_duplicates=True)
+            return self.ops.csr(sh.square_rows_of(mat), device)
+
+        def _entity_cols(self, mat, device):
+            sh = self.shard
+            m = sp.csc_matrix(mat)[:, sh.lo:sh.hi]
+            if m.shape[1] < sh.block:
+                m = sp.hstack([m, sp.csc_matrix((m.shape[0], sh.block - m.shape[1]), dtype=m.dtype)])
+            return self.ops.csr(sp.csr_matrix(m), device)
+
+        def _own_rows(self, x):
+            sh = self.shard
+            local = torch.zeros(sh.block, x.shape[1], dtype=x.dtype)
+            local[:sh.hi - sh.lo] = x[sh.lo:sh.hi]
+            return local
+
+        def _all_rows(self, x):
+            return AllGatherRows.apply(x, self.shard, False)
+
+        def _sum_over_owners(self, x):
+            return AllReduceSum.apply(x) if self.shard.world > 1 else x
+
+        def _full_output(self, x):
+            return AllGatherRows.apply(x, self.shard, True)[:self.n_ent]
+
+        def sync_grads(self):
+            """Sum the partial gradients of the replicated parameters (everything but the sharded X0)."""
+            if self.shard.world == 1:
+                return
+            for name, p in self.params.items():
+                if name != "X0" and p.grad is not None:
+                    dist.all_reduce(p.grad)
+
+    return ShardedRDGCNLayer
+
+
+def __getattr__(name):            # built on first use: the approach modules import this module's siblings
     if name == "ShardedAliNetModel":
         from .approaches.alinet import AliNetModel
         cls = make_sharded_alinet(AliNetModel)
-        globals()[name] = cls
-        return cls
-    raise AttributeError(name)
+    elif name == "ShardedRDGCNLayer":
+        from .approaches.rdgcn import RDGCNLayer
+        cls = make_sharded_rdgcn(RDGCNLayer)
+    else:
+        raise AttributeError(name)
+    globals()[name] = cls
+    return cls

@@ -23,9 +23,10 @@ def _free_port():
 
 class _Csr:
     def __init__(self, mat):
-        self.m = sp.csr_matrix(mat, dtype=np.float32)
-        self.shape = self.m.shape
-        c = self.m.tocoo()
+        self.m = sp.csr_matrix(mat, dtype=np.float32)          # duplicate entries are kept as they are
+        self.shape, self.nnz = self.m.shape, self.m.nnz
+        self.val = torch.tensor(self.m.data, dtype=torch.float32)
+        c = self.m.tocoo(copy=True)
         self.t = torch.sparse_coo_tensor(np.vstack([c.row, c.col]), c.data, c.shape).coalesce()
 
     def transpose(self):
@@ -42,7 +43,7 @@ class _Table:
 class TorchOps:
     """Rank-local numerics of the unit in plain torch (test stand-in for KernelOps)."""
 
-    def csr(self, mat, device):
+    def csr(self, mat, device, keep_duplicates=False):
         return _Csr(mat)
 
     def spmm(self, A, X, relu=False, mask_src=None):
@@ -224,3 +225,127 @@ def test_sharded_alinet_model_equals_single_process_model(world):
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(r, "ok") for r in range(world)], res
+
+
+# ---- RDGCN: row-sharded layer vs the same layer on one process (torch stand-ins for the kernels) ---------------------------
+def _edge_logit_aggregate(edge_logits, X, A, slope):
+    """EdgeLogitAggregateFn in plain torch: softmax over every row's edges of leaky_relu(logit_e), times X[col e]."""
+    m = A.m
+    row = torch.as_tensor(np.repeat(np.arange(m.shape[0]), np.diff(m.indptr)), dtype=torch.long)
+    col = torch.as_tensor(m.indices, dtype=torch.long)
+    logit = torch.nn.functional.leaky_relu(edge_logits, slope)
+    mx = torch.full((m.shape[0],), -1e30).scatter_reduce(0, row, logit, "amax")
+    ex = torch.exp(logit - mx[row])
+    den = torch.zeros(m.shape[0]).index_add(0, row, ex)
+    return torch.zeros(m.shape[0], X.shape[1]).index_add(0, row, (ex / den[row])[:, None] * X[col])
+
+
+def _rdgcn_problem():
+    from types import SimpleNamespace
+    rng = np.random.default_rng(21)
+    n, r, d, t, k = 41, 5, 8, 7, 3
+    tri = np.unique(np.stack([rng.integers(0, n, 150), rng.integers(0, r, 150), rng.integers(0, n, 150)], 1), axis=0)
+    half = len(tri) // 2
+    kgs = SimpleNamespace(kg1=SimpleNamespace(relation_triples_list=[tuple(x) for x in tri[:half].tolist()]),
+                          kg2=SimpleNamespace(relation_triples_list=[tuple(x) for x in tri[half:].tolist()]),
+                          entities_num=n, relations_num=r,
+                          train_links=[(int(a), int(b)) for a, b in zip(rng.permutation(n)[:t], rng.permutation(n)[:t])])
+    args = SimpleNamespace(dim=d, alpha=0.1, beta=0.3, gamma=1.0, neg_triple_num=k)
+    emb = rng.standard_normal((n, d)).astype(np.float32)
+    ill = np.array(kgs.train_links)
+    negs = [np.repeat(ill[:, 0], k), rng.integers(0, n, t * k), rng.integers(0, n, t * k), np.repeat(ill[:, 1], k)]
+    return args, kgs, emb, ill, negs, k
+
+
+def _rdgcn_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from openea_b200 import parallel_gnn as pg
+        from oracle.gnn import align_loss
+        args, kgs, emb, ill, negs, k = _rdgcn_problem()
+        ops = TorchOps()
+
+        def build(shard):
+            layer = pg.ShardedRDGCNLayer(args, kgs, emb, torch.device("cpu"), seed=5, shard=shard, ops=ops)
+            layer.spmm_fn = lambda X, A: torch.sparse.mm(A.t, X)
+            layer.edge_fn = _edge_logit_aggregate
+            for name, p in layer.params.items():              # the reference initialises the gates / biases at zero:
+                if name.endswith(".b"):                       # perturb them so that their gradients are exercised too
+                    with torch.no_grad():
+                        p += 0.1 * torch.randn(p.shape, generator=torch.Generator().manual_seed(len(name)))
+            return layer
+        ref = build(pg.RowShard(kgs.entities_num, rank=0, world_size=1))
+        ref_out = ref.forward()
+        ref_loss = align_loss(ref_out, ill, args.gamma, k, *negs)
+        ref_loss.backward()
+
+        shard = pg.RowShard(kgs.entities_num)
+        layer = build(shard)
+        assert layer.params["X0"].shape[0] == shard.block and layer.r_mat.shape == (shard.block, shard.n_pad)
+        n_edges = torch.tensor([layer.r_mat.nnz])
+        dist.all_reduce(n_edges)
+        assert int(n_edges) == ref.r_mat.nnz                  # every triple's r_mat entry lives on exactly one rank
+        out_full = layer.forward()
+        torch.testing.assert_close(out_full, ref_out, rtol=1e-4, atol=1e-5)
+        loss = align_loss(out_full, ill, args.gamma, k, *negs)
+        torch.testing.assert_close(loss, ref_loss, rtol=1e-5, atol=1e-6)
+        loss.backward()
+        layer.sync_grads()
+        for name, p in layer.params.items():
+            want = ref.params[name].grad
+            assert p.grad is not None and want is not None, name
+            if name == "X0":
+                want = torch.as_tensor(shard.local_rows(want.numpy()))
+            # (the bias of a 1-filter conv in front of a row softmax has a mathematically zero gradient: only noise)
+            atol = max(1e-5 * float(want.abs().max()), 1e-7)
+            torch.testing.assert_close(p.grad, want, rtol=1e-3, atol=atol, msg=lambda m, name=name: "%s: %s" % (name, m))
+        out.put((rank, "ok"))
+    except Exception as e:  # surface the failure in the parent
+        import traceback
+        out.put((rank, "FAIL: %r\n%s" % (e, traceback.format_exc())))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_rdgcn_layer_equals_single_process_layer(world):
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_rdgcn_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(r, "ok") for r in range(world)], res
+
+
+def test_single_gpu_rdgcn_layer_hooks_are_identities():
+    """The unsharded RDGCNLayer (identity hooks, gnn.DeviceCsr containers) and the sharded layer on a one-rank partition
+    build the same graph data and give the same forward output with the torch stand-ins."""
+    from openea_b200 import lib as L
+    from openea_b200 import parallel_gnn as pg
+    from openea_b200.approaches.rdgcn import RDGCNLayer
+    if not os.path.exists(L.LIB_PATH):
+        pytest.skip("liboea.so not built (DeviceCsr asks it for the hub-row threshold)")
+    args, kgs, emb, ill, negs, k = _rdgcn_problem()
+
+    class _HostCsr(_Csr):                       # DeviceCsr → the stand-in container, from the same scipy matrix
+        def __init__(self, dc):
+            super().__init__(dc._host)
+    base = RDGCNLayer(args, kgs, emb, torch.device("cpu"), seed=5)
+    one = pg.ShardedRDGCNLayer(args, kgs, emb, torch.device("cpu"), seed=5, shard=pg.RowShard(kgs.entities_num, 0, 1),
+                               ops=TorchOps())
+    assert base.r_mat.nnz == one.r_mat.nnz and torch.equal(base.edge_rel, one.edge_rel)
+    for name in ("M", "head_avg", "tail_avg", "r_mat"):
+        a, b = getattr(base, name)._host, getattr(one, name).m
+        assert a.shape == b.shape and abs(a - b).max() < 1e-7, name
+        setattr(base, name, _HostCsr(getattr(base, name)))
+    for layer in (base, one):
+        layer.spmm_fn = lambda X, A: torch.sparse.mm(A.t, X)
+        layer.edge_fn = _edge_logit_aggregate
+    with torch.no_grad():
+        torch.testing.assert_close(base.forward(), one.forward(), rtol=1e-5, atol=1e-6)
