@@ -79,6 +79,25 @@ class EmbeddingTable:
         other.adam_t = 0
         return other
 
+    def state_dict(self):
+        """Variable + this optimiser instance's slots as host tensors (checkpointing; the reference has none)."""
+        cpu = lambda t: None if t is None else t.detach().cpu().clone()
+        return {"weight": cpu(self.weight), "state1": cpu(self.state1), "state2": cpu(self.state2),
+                "adam_t": int(self.adam_t), "optimizer": self.optimizer, "l2_norm": self.l2_norm, "dim": self.dim}
+
+    def load_state_dict(self, state):
+        """Restore in place (device buffers keep their addresses, so cached C structs and CUDA graphs stay valid)."""
+        if state["optimizer"] != self.optimizer or state["dim"] != self.dim or tuple(state["weight"].shape) != tuple(self.weight.shape):
+            raise ValueError("checkpoint does not match this table (optimizer %s/%s, shape %s/%s)" % (
+                state["optimizer"], self.optimizer, tuple(state["weight"].shape), tuple(self.weight.shape)))
+        self.weight.copy_(state["weight"])
+        for name in ("state1", "state2"):
+            if getattr(self, name) is not None:
+                getattr(self, name).copy_(state[name])
+        self.adam_t = int(state["adam_t"])
+        self.grad.zero_()
+        self.touched.zero_()
+
     def c_struct(self):
         if self._struct is None:
             self._struct = L.Table(self.weight.data_ptr(), self.grad.data_ptr(),

@@ -268,14 +268,62 @@ class BasicModel:
         n2 = bat.neighbours_device(self.eval_kg2_useful_ent_embeddings(), self.kgs.useful_entities_list2, num2)
         return n1, n2
 
+    # ---- checkpoint / resume (absent in the reference) -----------------------------------------
+    def _checkpoint_tables(self):
+        """Every optimiser instance that holds state: the model's tables by attribute name, plus the separate slot
+        views of the mapping / alignment trainers (they share the weights of the tables above)."""
+        tables = {name: v for name, v in vars(self).items() if isinstance(v, eng.EmbeddingTable)}
+        for tname in ("mapping_trainer", "alignment_trainer"):
+            trainer = getattr(self, tname, None)
+            for slot in ("ent", "rel"):
+                tab = getattr(trainer, slot, None)
+                if isinstance(tab, eng.EmbeddingTable):
+                    tables["%s.%s" % (tname, slot)] = tab
+        return tables
+
+    def save_checkpoint(self, path, epoch):
+        """Everything a run needs to continue after `epoch`: variables, optimiser slots, the sampler's epoch seed,
+        early-stopping state and the host RNG streams (mapping batches, GNN negatives)."""
+        state = {"epoch": int(epoch), "epoch_seed": int(self._epoch_seed), "flag1": self.flag1, "flag2": self.flag2,
+                 "class": self.__class__.__name__, "python_random": random.getstate(), "numpy_random": np.random.get_state(),
+                 "tables": {name: tab.state_dict() for name, tab in self._checkpoint_tables().items()}}
+        os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+        tmp = path + ".tmp"
+        torch.save(state, tmp)
+        os.replace(tmp, path)
+        return path
+
+    def load_checkpoint(self, path):
+        """Restore a save_checkpoint() file into an initialised model (call after init()); returns the epoch to
+        continue from and makes run() start there."""
+        state = torch.load(path, map_location="cpu", weights_only=False)
+        if state["class"] != self.__class__.__name__:
+            raise ValueError("checkpoint of %s loaded into %s" % (state["class"], self.__class__.__name__))
+        tables = self._checkpoint_tables()
+        if set(tables) != set(state["tables"]):
+            raise ValueError("checkpoint tables %s do not match the model's %s" % (sorted(state["tables"]), sorted(tables)))
+        for name, tab in tables.items():
+            tab.load_state_dict(state["tables"][name])
+        self._epoch_seed, self.flag1, self.flag2 = state["epoch_seed"], state["flag1"], state["flag2"]
+        random.setstate(state["python_random"])
+        np.random.set_state(state["numpy_random"])
+        self._start_epoch = state["epoch"] + 1
+        return self._start_epoch
+
     def run(self):
         t = time.time()
         triples_num = self.kgs.kg1.relation_triples_num + self.kgs.kg2.relation_triples_num
         triple_steps = int(math.ceil(triples_num / self.args.batch_size))
         steps_tasks = task_divide(list(range(triple_steps)), self.args.batch_threads_num)
         neighbors1, neighbors2 = None, None
-        for i in range(1, self.args.max_epoch + 1):
+        start_epoch = getattr(self, "_start_epoch", 1)
+        if start_epoch > 1 and self.args.neg_sampling == 'truncated' and (start_epoch - 1) >= self.args.truncated_freq:
+            neighbors1, neighbors2 = self._refresh_neighbours()     # the candidate lists are derived state: rebuild them
+        every = getattr(self.args, "checkpoint_every", 0)
+        for i in range(start_epoch, self.args.max_epoch + 1):
             self.launch_training_1epo(i, triple_steps, steps_tasks, None, neighbors1, neighbors2)
+            if every and i % every == 0:
+                self.save_checkpoint(self.out_folder + "checkpoint.pt", i)
             if i >= self.args.start_valid and i % self.args.eval_freq == 0:
                 flag = self.valid(self.args.stop_metric)
                 self.flag1, self.flag2, self.early_stop = early_stop(self.flag1, self.flag2, flag)

@@ -1,0 +1,83 @@
+"""CPU: checkpoint / resume of the engine state (the reference has none): table round trips with every
+optimiser's slots, the model-level file with the trainers' separate slot views, refusal of mismatching checkpoints."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from openea_b200 import engine as eng
+from openea_b200.models.basic_model import BasicModel
+
+
+def _table(rows, d, opt, seed):
+    g = torch.Generator().manual_seed(seed)
+    t = eng.EmbeddingTable(torch.randn(rows, d, generator=g), True, opt, device="cpu")
+    for name in ("state1", "state2"):
+        if getattr(t, name) is not None:
+            getattr(t, name).copy_(torch.rand(getattr(t, name).shape, generator=g))
+    t.adam_t = 7 if opt == "Adam" else 0
+    return t
+
+
+@pytest.mark.parametrize("opt", ["Adagrad", "Adam", "SGD", "Adadelta"])
+def test_table_state_round_trip(opt):
+    a, b = _table(30, 10, opt, 1), _table(30, 10, opt, 2)
+    ptr = b.weight.data_ptr()
+    b.grad.fill_(3.0)
+    b.touched.fill_(1)
+    b.load_state_dict(a.state_dict())
+    assert torch.equal(a.weight, b.weight) and b.weight.data_ptr() == ptr        # restored in place
+    for name in ("state1", "state2"):
+        x, y = getattr(a, name), getattr(b, name)
+        assert (x is None and y is None) or torch.equal(x, y)
+    assert b.adam_t == a.adam_t and not b.grad.any() and not b.touched.any()
+    with pytest.raises(ValueError):
+        _table(31, 10, opt, 3).load_state_dict(a.state_dict())
+    with pytest.raises(ValueError):
+        _table(30, 10, "SGD" if opt != "SGD" else "Adam", 3).load_state_dict(a.state_dict())
+
+
+def _model(seed):
+    m = BasicModel()
+    m.ent_embeds, m.rel_embeds = _table(40, 12, "Adagrad", seed), _table(6, 12, "Adagrad", seed + 1)
+    m.mapping_mat = _table(12, 12, "Adagrad", seed + 2)
+    # a second optimiser instance over the entity table, as MTransE's mapping trainer / BootEA's alignment trainer own
+    m.alignment_trainer = type("T", (), {})()
+    m.alignment_trainer.ent, m.alignment_trainer.rel = m.ent_embeds.new_slots(), m.rel_embeds.new_slots()
+    m.alignment_trainer.ent.state1.fill_(0.25 + seed)
+    m._epoch_seed, m.flag1, m.flag2 = 1000 + seed, 0.5, 0.25
+    return m
+
+
+def test_model_checkpoint_restores_tables_slot_views_seeds_and_rng(tmp_path):
+    a, b = _model(1), _model(5)
+    random.seed(3)
+    np.random.seed(4)
+    path = a.save_checkpoint(str(tmp_path) + "/ckpt/checkpoint.pt", epoch=17)
+    want_py, want_np = random.random(), np.random.rand()
+    assert b.load_checkpoint(path) == 18 and b._start_epoch == 18
+    for name, tab in a._checkpoint_tables().items():
+        other = b._checkpoint_tables()[name]
+        assert torch.equal(tab.weight, other.weight) and torch.equal(tab.state1, other.state1), name
+    assert sorted(a._checkpoint_tables()) == ["alignment_trainer.ent", "alignment_trainer.rel", "ent_embeds",
+                                              "mapping_mat", "rel_embeds"]
+    assert b.alignment_trainer.ent.weight.data_ptr() == b.ent_embeds.weight.data_ptr()    # still one variable, two slot sets
+    assert float(b.alignment_trainer.ent.state1[0, 0]) == 1.25 and (b._epoch_seed, b.flag1, b.flag2) == (1001, 0.5, 0.25)
+    assert (random.random(), np.random.rand()) == (want_py, want_np)                   # host RNG streams continue
+
+
+def test_checkpoint_of_another_model_is_refused(tmp_path):
+    a = _model(1)
+    path = a.save_checkpoint(str(tmp_path) + "/checkpoint.pt", epoch=2)
+    b = _model(2)
+    del b.mapping_mat
+    with pytest.raises(ValueError):
+        b.load_checkpoint(path)
+
+    class Other(BasicModel):
+        pass
+    c = Other()
+    c.__dict__.update(_model(3).__dict__)
+    with pytest.raises(ValueError):
+        c.load_checkpoint(path)

@@ -325,3 +325,42 @@ def test_bootea_transh_lifecycle(cuda_device, tiny_kgs, tmp_path):
     loss = _losses(out, "avg. triple loss:")
     assert loss[-1] < loss[0]
     assert _hits1(out, "accurate results:") > 4.0        # chance = 0.24 %; BootEA (TransE) reaches > 8 % at 300 epochs
+
+
+@pytest.mark.first_hw_run
+def test_resume_from_checkpoint_continues_the_same_run(cuda_device, tiny_kgs, tmp_path):
+    """6 epochs in one go == 3 epochs, checkpoint, a NEW model restored from the file, 3 more epochs (variables and
+    Adagrad accumulators; gradient sums are atomics, so agreement is to fp32 accumulation noise, not bit-wise)."""
+    import contextlib
+    import io
+    from openea_b200 import presets
+    from openea_b200.models.trans import TransE
+    from openea_b200.modules.base import initializers
+    from openea_b200.modules.load.kgs import read_kgs_from_folder
+
+    def make(max_epoch, out, **extra):
+        args = presets.transe("15K")
+        args.training_data, args.output = tiny_kgs, str(tmp_path) + "/" + out + "/"
+        args.batch_size, args.max_epoch, args.start_valid, args.dim = 1000, max_epoch, 1000, 32
+        for k, v in extra.items():
+            setattr(args, k, v)
+        initializers.set_seed(77)
+        m = TransE()
+        m.set_args(args)
+        m.set_kgs(read_kgs_from_folder(tiny_kgs, args.dataset_division, "sharing", True))
+        m.init()
+        m._epoch_seed = 424242
+        return m
+    with contextlib.redirect_stdout(io.StringIO()):
+        straight = make(6, "a")
+        straight.run()
+        first = make(3, "b", checkpoint_every=3)
+        first.run()
+        resumed = make(6, "c")
+        assert resumed.load_checkpoint(first.out_folder + "checkpoint.pt") == 4
+        resumed.run()
+    for name in ("ent_embeds", "rel_embeds"):
+        a, b = getattr(straight, name), getattr(resumed, name)
+        np.testing.assert_allclose(b.raw().cpu().numpy(), a.raw().cpu().numpy(), rtol=2e-3, atol=2e-5, err_msg=name)
+        np.testing.assert_allclose(b.state1.cpu().numpy(), a.state1.cpu().numpy(), rtol=2e-3, atol=2e-5, err_msg=name)
+    assert resumed._epoch_seed == straight._epoch_seed
