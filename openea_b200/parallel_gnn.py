@@ -1,9 +1,10 @@
 """Path (ii) across GPUs: the adjacency A, the layer outputs and — for the featureless first layer —
 the entity table itself are ROW-SHARDED; one exchange per layer.
 
-Partition: contiguous blocks of `block = ceil(N / G)` rows; rank r owns rows [r·block, min((r+1)·block, N)); every
-per-row tensor is padded to `block` rows so the collectives are fixed-size (`N_pad = G·block`; padding rows of A are
-empty and padding columns are never referenced).
+Partition: CYCLIC — rank r owns the ids r, r + G, … (ids are ordered by descending frequency, so this balances the
+non-zeros); every per-row tensor is padded to `block = ceil(N / G)` rows so the collectives are fixed-size
+(`N_pad = G·block`; padding rows of A are empty and padding columns are never referenced); gathered tensors are in
+rank-after-rank "position" order and adjacency columns are renumbered to positions once (`RowShard`).
 
 One GCN-Align unit step (approaches/gcn_align.py:239-267,298-320,498-539), rank-local work in liboea kernels:
 
@@ -38,7 +39,13 @@ from . import parallel as par
 
 
 class RowShard:
-    """Contiguous, padded row partition of n rows over the process group."""
+    """Cyclic, padded row partition of n rows over the process group: rank r owns the ids r, r + G, r + 2G, …
+
+    Entity ids interleave the two KGs by DESCENDING frequency (read.py:69-79), so contiguous blocks would give rank 0
+    every hub and most of the adjacency's non-zeros; cyclic ownership gives every rank the same degree profile.
+    Internally a gathered tensor is laid out rank after rank ("position" order): id i sits at position
+    pos_of_id[i] = (i mod G)·block + i div G, each rank's `block = ceil(n / G)` rows padded at the end.  Adjacency
+    columns are renumbered to positions once at build time; `to_global` returns a gathered tensor in id order."""
 
     def __init__(self, n, rank=None, world_size=None):
         r, w = par.world()
@@ -47,28 +54,59 @@ class RowShard:
         self.n = int(n)
         self.block = -(-self.n // self.world)
         self.n_pad = self.block * self.world
-        self.lo = min(self.rank * self.block, self.n)
-        self.hi = min(self.lo + self.block, self.n)
+        ids = np.arange(self.n, dtype=np.int64)
+        self.pos_of_id = (ids % self.world) * self.block + ids // self.world
+        self.my_ids = np.arange(self.rank, self.n, self.world, dtype=np.int64)
+        self.n_local = len(self.my_ids)
+        self._pos_t = {}
 
-    def rows_of(self, mat):
-        """Rows [lo, hi) of a scipy matrix as CSR [block, n_pad-or-original columns] (empty padding rows)."""
-        m = sp.csr_matrix(mat)[self.lo:self.hi]
+    def pos_tensor(self, device):
+        """pos_of_id as an int64 tensor on `device` (cached)."""
+        key = str(device)
+        if key not in self._pos_t:
+            self._pos_t[key] = torch.as_tensor(self.pos_of_id, device=device)
+        return self._pos_t[key]
+
+    def to_global(self, x_full):
+        """[n_pad, …] in position order → [n, …] in id order (drops the padding rows)."""
+        return x_full.index_select(0, self.pos_tensor(x_full.device))
+
+    def _pad_rows(self, m):
         if m.shape[0] < self.block:
             m = sp.vstack([m, sp.csr_matrix((self.block - m.shape[0], m.shape[1]), dtype=m.dtype)]).tocsr()
         return m
 
-    def square_rows_of(self, mat):
-        """Rows [lo, hi) of a square [n, n] matrix, columns padded to n_pad (the layer input is all-gathered)."""
-        m = self.rows_of(mat)
-        if m.shape[1] < self.n_pad:
-            m = sp.hstack([m, sp.csr_matrix((m.shape[0], self.n_pad - m.shape[1]), dtype=m.dtype)]).tocsr()
-        return m
+    def rows_of(self, mat):
+        """The owned rows of a scipy matrix [n, c] as CSR [block, c] (empty padding rows); columns untouched."""
+        return self._pad_rows(sp.csr_matrix(mat)[self.my_ids])
+
+    def square_rows_of(self, mat, keep_duplicates=False):
+        """The owned rows of an [n, n] matrix whose columns index a GATHERED tensor: columns renumbered to positions,
+        shape [block, n_pad].  keep_duplicates: repeated (row, col) entries stay separate entries (RDGCN's r_mat holds
+        one entry per triple) instead of being summed."""
+        m = sp.csr_matrix(mat) if not sp.isspmatrix_csr(mat) else mat
+        counts = np.diff(m.indptr)[self.my_ids]
+        indptr = np.full(self.block + 1, counts.sum(), dtype=np.int64)
+        indptr[:self.n_local + 1] = np.concatenate([[0], np.cumsum(counts)])
+        take = np.concatenate([np.arange(m.indptr[i], m.indptr[i + 1]) for i in self.my_ids]) if self.n_local and counts.sum() \
+            else np.zeros(0, dtype=np.int64)
+        out = sp.csr_matrix((m.data[take], self.pos_of_id[m.indices[take]], indptr), shape=(self.block, self.n_pad))
+        if not keep_duplicates:
+            out.sum_duplicates()
+        return out
+
+    def cols_of(self, mat):
+        """The owned columns of a scipy matrix [c, n] as CSR [c, block] (a reduction OVER rows of a sharded tensor)."""
+        m = sp.csc_matrix(mat)[:, self.my_ids]
+        if m.shape[1] < self.block:
+            m = sp.hstack([m, sp.csc_matrix((m.shape[0], self.block - m.shape[1]), dtype=m.dtype)])
+        return sp.csr_matrix(m)
 
     def local_rows(self, full):
-        """Rows [lo, hi) of a host array padded with zero rows to `block`."""
+        """The owned rows of a host array (or CPU tensor) padded with zero rows to `block`."""
         full = np.asarray(full)
         out = np.zeros((self.block,) + full.shape[1:], dtype=full.dtype)
-        out[:self.hi - self.lo] = full[self.lo:self.hi]
+        out[:self.n_local] = full[self.my_ids]
         return out
 
 
@@ -140,7 +178,7 @@ class ShardedGCNAlignUnit:
         ill = np.asarray(ill)
         self.t = len(ill)
         self.p_lo, self.p_hi = par.block_range(self.t, sh.rank, sh.world)                     # my seed pairs
-        mine = ill[self.p_lo:self.p_hi]
+        mine = sh.pos_of_id[ill[self.p_lo:self.p_hi]]              # the loss kernel indexes the gathered (position-order) rows
         self.left = torch.as_tensor(mine[:, 0], dtype=torch.int32, device=dev).contiguous()
         self.right = torch.as_tensor(mine[:, 1], dtype=torch.int32, device=dev).contiguous()
         self.gamma, self.k, self.lr = float(gamma), int(k), float(lr)
@@ -155,12 +193,13 @@ class ShardedGCNAlignUnit:
         pre = all_gather_rows(pre_local, sh)
         self._h1 = all_gather_rows(self.ops.spmm(self.A, pre, relu=True), sh)
         self._out_full = all_gather_rows(self.ops.spmm(self.A, self._h1), sh)
-        self.outputs = self._out_full[:self.n]
+        self.outputs = sh.to_global(self._out_full)
         return self.outputs
 
     def _my_negs(self, negs):
         lo, hi = self.p_lo * self.k, self.p_hi * self.k
-        return [n[lo:hi].contiguous() for n in negs]
+        pos = self.shard.pos_tensor(negs[0].device)
+        return [pos[n[lo:hi].long()].to(torch.int32).contiguous() for n in negs]
 
     def train_step(self, neg_left, neg_right, neg2_left, neg2_right):
         """One session.run([loss, opt_op]) of the unit; returns the global loss (device fp64 scalar tensor)."""
@@ -236,17 +275,17 @@ def make_sharded_alinet(base_cls):
             # every rank drew the same full table from the same generator: keep the owned rows only
             full = self.params["init_embedding"].detach()
             local = torch.zeros(sh.block, full.shape[1], dtype=full.dtype, device=full.device)
-            local[:sh.hi - sh.lo] = full[sh.lo:sh.hi]
+            local[:sh.n_local] = full[torch.as_tensor(sh.my_ids, device=full.device)]
             self.params["init_embedding"] = local.requires_grad_(True)
 
         def _layer_input(self, x):
             return AllGatherRows.apply(x, self.shard, False)
 
         def _layer_outputs(self, outs):
-            return [AllGatherRows.apply(o, self.shard, True)[:self.n_ent] for o in outs]
+            return [self.shard.to_global(AllGatherRows.apply(o, self.shard, True)) for o in outs]
 
         def input_embedding(self):
-            return AllGatherRows.apply(self.params["init_embedding"], self.shard, True)[:self.n_ent]
+            return self.shard.to_global(AllGatherRows.apply(self.params["init_embedding"], self.shard, True))
 
         def set_adj1(self, mat, device):
             self.adj1 = self.ops.csr(self.shard.square_rows_of(mat), device)
@@ -281,16 +320,6 @@ class AllReduceSum(torch.autograd.Function):
         return g
 
 
-def row_block_keep_duplicates(mat, shard):
-    """Rows [lo, hi) of a CSR matrix as [block, n_pad] WITHOUT merging duplicate entries (RDGCN's r_mat holds one entry
-    per triple, several of them at the same (h, t))."""
-    m = sp.csr_matrix(mat) if not sp.isspmatrix_csr(mat) else mat
-    a, b = m.indptr[shard.lo], m.indptr[shard.hi]
-    indptr = np.full(shard.block + 1, b - a, dtype=m.indptr.dtype)
-    indptr[:shard.hi - shard.lo + 1] = m.indptr[shard.lo:shard.hi + 1] - a
-    return sp.csr_matrix((m.data[a:b], m.indices[a:b], indptr), shape=(shard.block, shard.n_pad))
-
-
 def make_sharded_rdgcn(base_cls):
     """ShardedRDGCNLayer over the (late-imported) RDGCNLayer: the entity rows of X0, of every intermediate and of the
     entity-side matrices (M, r_mat) are sharded; the relation-side tensors (dual input / attention, [R, ·] with R ≈ 500)
@@ -309,20 +338,16 @@ def make_sharded_rdgcn(base_cls):
         def _entity_rows(self, mat, device, keep_duplicates=False):
             sh = self.shard
             if keep_duplicates:
-                return self.ops.csr(row_block_keep_duplicates(mat, sh), device, keep_duplicates=True)
+                return self.ops.csr(sh.square_rows_of(mat, keep_duplicates=True), device, keep_duplicates=True)
             return self.ops.csr(sh.square_rows_of(mat), device)
 
         def _entity_cols(self, mat, device):
-            sh = self.shard
-            m = sp.csc_matrix(mat)[:, sh.lo:sh.hi]
-            if m.shape[1] < sh.block:
-                m = sp.hstack([m, sp.csc_matrix((m.shape[0], sh.block - m.shape[1]), dtype=m.dtype)])
-            return self.ops.csr(sp.csr_matrix(m), device)
+            return self.ops.csr(self.shard.cols_of(mat), device)
 
         def _own_rows(self, x):
             sh = self.shard
             local = torch.zeros(sh.block, x.shape[1], dtype=x.dtype)
-            local[:sh.hi - sh.lo] = x[sh.lo:sh.hi]
+            local[:sh.n_local] = x[torch.as_tensor(sh.my_ids)]
             return local
 
         def _all_rows(self, x):
@@ -332,7 +357,7 @@ def make_sharded_rdgcn(base_cls):
             return AllReduceSum.apply(x) if self.shard.world > 1 else x
 
         def _full_output(self, x):
-            return AllGatherRows.apply(x, self.shard, True)[:self.n_ent]
+            return self.shard.to_global(AllGatherRows.apply(x, self.shard, True))
 
         def sync_grads(self):
             """Sum the partial gradients of the replicated parameters (everything but the sharded X0)."""

@@ -82,7 +82,7 @@ def _gcn_worker(rank, world, port, out):
             got = float(unit.train_step(*tn))
             assert abs(got - want) <= 1e-4 * max(1.0, abs(want)), (got, want)
             torch.testing.assert_close(unit.outputs, single.outputs, rtol=1e-4, atol=1e-6)
-        W = pg.all_gather_rows(unit.table.weight, shard)[:n]
+        W = shard.to_global(pg.all_gather_rows(unit.table.weight, shard))
         torch.testing.assert_close(W, single.table.weight, rtol=1e-4, atol=1e-6)
         out.put((rank, "ok"))
     except Exception as e:

@@ -113,8 +113,8 @@ def _worker(rank, world, port, with_features, out):
         if with_features:
             W = table.weight.numpy()                                     # replicated: identical on every rank
         else:
-            W = pg.all_gather_rows(table.weight, shard).numpy()[:shard.n]   # assemble the owners' rows
-            assert not table.weight[shard.hi - shard.lo:].any(), "padding rows of the shard must stay zero"
+            W = shard.to_global(pg.all_gather_rows(table.weight, shard)).numpy()   # assemble the owners' rows in id order
+            assert not table.weight[shard.n_local:].any(), "padding rows of the shard must stay zero"
         np.testing.assert_allclose(W, want_W, rtol=1e-4, atol=1e-6)
         out.put((rank, "ok"))
     except Exception as e:  # surface the failure in the parent
@@ -140,17 +140,33 @@ def test_sharded_gcn_unit_equals_single_process_oracle(world, with_features):
 
 
 def test_row_shard_partition_is_exact():
+    """Cyclic ownership: the row blocks (columns renumbered to positions) reassemble the matrix, padding is empty,
+    duplicates are merged or kept on request, and ownership balances a frequency-ordered degree profile."""
     from openea_b200 import parallel_gnn as pg
     m = sp.random(10, 10, density=0.5, random_state=1, format="csr")
-    rows = []
+    back = sp.lil_matrix((10, 10))
     for r in range(4):
         sh = pg.RowShard(10, rank=r, world_size=4)
-        assert (sh.block, sh.n_pad) == (3, 12)
+        assert (sh.block, sh.n_pad) == (3, 12) and sh.my_ids.tolist() == list(range(r, 10, 4))
         blk = sh.square_rows_of(m)
-        assert blk.shape == (3, 12)
-        rows.append(blk[:sh.hi - sh.lo, :10])
-        assert blk[sh.hi - sh.lo:].nnz == 0
-    assert (sp.vstack(rows) != m).nnz == 0
+        assert blk.shape == (3, 12) and blk[sh.n_local:].nnz == 0
+        id_of_pos = np.full(12, -1)
+        id_of_pos[sh.pos_of_id] = np.arange(10)
+        coo = blk.tocoo()
+        for i, j, v in zip(coo.row, coo.col, coo.data):
+            back[sh.my_ids[i], id_of_pos[j]] = v
+        assert (sh.cols_of(m)[:, :sh.n_local] != m[:, sh.my_ids]).nnz == 0
+        x = np.arange(20.0).reshape(10, 2)
+        assert np.array_equal(sh.local_rows(x)[:sh.n_local], x[sh.my_ids])
+    assert abs(back.tocsr() - m).max() < 1e-12
+    sh = pg.RowShard(4, rank=0, world_size=2)
+    dup = sp.csr_matrix((np.array([1.0, 2.0, 5.0]), np.array([1, 1, 3]), np.array([0, 2, 2, 3, 3])), shape=(4, 4))
+    assert sh.square_rows_of(dup, keep_duplicates=True).nnz == 3 and sh.square_rows_of(dup).nnz == 2
+    gathered = torch.arange(4.0)[:, None]                       # position order of ids 0, 2, 1, 3
+    assert sh.to_global(gathered[[0, 1, 2, 3]]).flatten().tolist() == [0.0, 2.0, 1.0, 3.0]
+    deg = 1000.0 / (1 + np.arange(1000))                        # Zipf degrees in id (= frequency) order
+    load = [deg[pg.RowShard(1000, r, 4).my_ids].sum() for r in range(4)]
+    assert max(load) / min(load) < 1.7                          # contiguous blocks would give rank 0 over 5x rank 3
 
 
 # ---- AliNet: row-sharded model vs the single-process model (same forward code, torch stand-ins for the kernels) ----------
@@ -283,7 +299,7 @@ def _rdgcn_worker(rank, world, port, out):
 
         shard = pg.RowShard(kgs.entities_num)
         layer = build(shard)
-        assert layer.params["X0"].shape[0] == shard.block and layer.r_mat.shape == (shard.block, shard.n_pad)
+        assert layer.params["X0"].shape[0] == shard.block and tuple(layer.r_mat.shape) == (shard.block, shard.n_pad)
         n_edges = torch.tensor([layer.r_mat.nnz])
         dist.all_reduce(n_edges)
         assert int(n_edges) == ref.r_mat.nnz                  # every triple's r_mat entry lives on exactly one rank
