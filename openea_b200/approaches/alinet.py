@@ -321,8 +321,18 @@ class AliNet(BasicModel):
 
     def set_kgs(self, kgs):
         self.kgs = kgs
-        self.kg1 = AKG(self.kgs.kg1.relation_triples_set)
-        self.kg2 = AKG(self.kgs.kg2.relation_triples_set)
+        self._tri1 = getattr(kgs.kg1, "relation_triples_array", None)      # array-backed loader: build graphs on arrays
+        self._tri2 = getattr(kgs.kg2, "relation_triples_array", None)
+        if self._tri1 is None or self._tri2 is None:
+            self.kg1 = AKG(self.kgs.kg1.relation_triples_set)
+            self.kg2 = AKG(self.kgs.kg2.relation_triples_set)
+
+    def _akgs(self):
+        """The set / dict containers of alinet.py:456-536, built only when the neighbourhood augmentation needs them."""
+        if getattr(self, "kg1", None) is None:
+            self.kg1 = AKG(self.kgs.kg1.relation_triples_set)
+            self.kg2 = AKG(self.kgs.kg2.relation_triples_set)
+        return self.kg1, self.kg2
 
     def set_args(self, args):
         self.args = args
@@ -338,24 +348,36 @@ class AliNet(BasicModel):
         self.sup_ent1, self.sup_ent2 = self.kgs.train_entities1, self.kgs.train_entities2
         self.linked_ents = set(self.kgs.train_entities1 + self.kgs.train_entities2 + self.kgs.valid_entities1 +
                                self.kgs.test_entities1 + self.kgs.test_entities2 + self.kgs.valid_entities2)
-        enh1, enh2 = enhance_triples(self.kg1, self.kg2, self.sup_ent1, self.sup_ent2)
-        triples = remove_unlinked_triples(self.kg1.triple_list + self.kg2.triple_list + list(enh1) + list(enh2),
-                                          self.linked_ents)
-        self.rel_ht_dict = generate_rel_ht(triples)
         saved = self.args.training_data + self.args.dataset_division + 'alinet_saved_data.pkl'
-        if os.path.exists(saved):
-            print('load saved adj data from', saved)
-            adj = pickle.load(open(saved, 'rb'))
-        else:
-            one_adj, _ = no_weighted_adj(self.kgs.entities_num, triples)
-            two = generate_2hop_triples(self.kg1, self.linked_ents) | generate_2hop_triples(self.kg2, self.linked_ents)
-            two_adj, _ = no_weighted_adj(self.kgs.entities_num, list(two))
+        if self._tri1 is not None:
+            # sorted-key joins on the loader's arrays (approaches/alinet_graph.py) instead of the row-by-row walk
+            from openea_b200.approaches import alinet_graph as ag
+            t0 = time.time()
+            one_adj, two_adj, triples = ag.build(self._tri1, self._tri2, self.sup_ent1, self.sup_ent2, self.linked_ents,
+                                                 self.kgs.entities_num)
+            self.rel_index = ag.relation_index(triples)             # (relations, row pointer, (h, t) pairs by relation)
+            self.rel_ht_dict = dict.fromkeys(self.rel_index[0].tolist())   # the keys are what the window size needs
             adj = [one_adj, two_adj]
-            try:
-                pickle.dump(adj, open(saved, 'wb'))
-                print('save adj data to', saved)
-            except OSError:
-                pass
+            print('generating the one- and two-hop adjacencies on arrays costs time: {:.4f}s'.format(time.time() - t0))
+        else:
+            self.rel_index = None
+            enh1, enh2 = enhance_triples(self.kg1, self.kg2, self.sup_ent1, self.sup_ent2)
+            triples = remove_unlinked_triples(self.kg1.triple_list + self.kg2.triple_list + list(enh1) + list(enh2),
+                                              self.linked_ents)
+            self.rel_ht_dict = generate_rel_ht(triples)
+            if os.path.exists(saved):
+                print('load saved adj data from', saved)
+                adj = pickle.load(open(saved, 'rb'))
+            else:
+                one_adj, _ = no_weighted_adj(self.kgs.entities_num, triples)
+                two = generate_2hop_triples(self.kg1, self.linked_ents) | generate_2hop_triples(self.kg2, self.linked_ents)
+                two_adj, _ = no_weighted_adj(self.kgs.entities_num, list(two))
+                adj = [one_adj, two_adj]
+                try:
+                    pickle.dump(adj, open(saved, 'wb'))
+                    print('save adj data to', saved)
+                except OSError:
+                    pass
         self.adj = adj
         self.rel_win_size = self.args.batch_size // max(1, len(self.rel_ht_dict))
         if self.rel_win_size <= 1:
@@ -399,6 +421,12 @@ class AliNet(BasicModel):
         return pos_links, np.array(sorted(neg), dtype=np.int64).reshape(-1, 2)
 
     def generate_rel_batch(self):
+        if self.rel_index is not None:     # rel_win_size random (h, t) pairs per relation, with replacement, in one shot
+            rels, ptr, pairs = self.rel_index
+            size = np.diff(ptr)
+            pick = ptr[:-1, None] + (np.random.random((len(rels), self.rel_win_size)) * size[:, None]).astype(np.int64)
+            chosen = pairs[pick.reshape(-1)]
+            return chosen[:, 0], np.repeat(rels, self.rel_win_size), chosen[:, 1]
         hs, rs, ts = [], [], []
         for r, hts in self.rel_ht_dict.items():
             for h, t in (random.choice(hts) for _ in range(self.rel_win_size)):
@@ -470,8 +498,9 @@ class AliNet(BasicModel):
         self.new_sup_links_set = set(zip(new1, new2))
         if not new1:
             return
-        self.new_edges1, self.new_edges2 = enhance_triples(self.kg1, self.kg2, self.sup_ent1 + new1, self.sup_ent2 + new2)
-        triples = remove_unlinked_triples(self.kg1.triple_list + self.kg2.triple_list + list(self.new_edges1) +
+        kg1, kg2 = self._akgs()
+        self.new_edges1, self.new_edges2 = enhance_triples(kg1, kg2, self.sup_ent1 + new1, self.sup_ent2 + new2)
+        triples = remove_unlinked_triples(kg1.triple_list + kg2.triple_list + list(self.new_edges1) +
                                           list(self.new_edges2), self.linked_ents)
         one_adj, _ = no_weighted_adj(self.kgs.entities_num, triples)
         print("gcn update adj...")

@@ -187,3 +187,62 @@ def test_graph_builders_give_the_same_graphs_from_either_dataset_loader(tmp_path
             x, y = sp.coo_matrix((x[1], (x[0][:, 0], x[0][:, 1])), shape=x[2]), sp.coo_matrix((y[1], (y[0][:, 0], y[0][:, 1])), shape=y[2])
         x, y = sp.csr_matrix(x), sp.csr_matrix(y)
         assert x.shape == y.shape and abs(x - y).max() < 1e-6, name
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_alinet_array_builders_equal_the_set_based_builders(seed):
+    """approaches/alinet_graph.py (sorted-key joins on arrays) against the set / dict builders of approaches/alinet.py,
+    which are themselves pinned to the reference's source above: enhanced triples, two-hop pairs (the 5 most frequent
+    relation patterns dropped), both adjacencies, the relation index."""
+    import contextlib
+    import io
+    from openea_b200.approaches import alinet, alinet_graph as ag
+    rng = np.random.default_rng(seed)
+    n, n_rel = 90, 7
+
+    def kg(lo, hi, m):
+        hub = rng.integers(lo, lo + 6, m)                                   # a few hubs: many two-hop paths
+        t = np.stack([np.where(rng.random(m) < 0.3, hub, rng.integers(lo, hi, m)), rng.integers(0, n_rel, m),
+                      rng.integers(lo, hi, m)], 1)
+        return np.unique(t, axis=0)
+    t1, t2 = kg(0, 45, 160), kg(45, 90, 150)
+    sup1, sup2 = rng.permutation(45)[:12], 45 + rng.permutation(45)[:12]
+    linked = set(rng.permutation(n)[:70].tolist()) | set(sup1.tolist()) | set(sup2.tolist())
+    with contextlib.redirect_stdout(io.StringIO()):
+        k1, k2 = alinet.AKG([tuple(x) for x in t1.tolist()]), alinet.AKG([tuple(x) for x in t2.tolist()])
+        want_new1, want_new2 = alinet.enhance_triples(k1, k2, sup1.tolist(), sup2.tolist())
+        got_new1, got_new2 = ag.enhance(t1, t2, sup1, sup2, n)
+        assert {tuple(x) for x in got_new1.tolist()} == want_new1 and {tuple(x) for x in got_new2.tolist()} == want_new2
+        for kg_obj, tri in ((k1, t1), (k2, t2)):
+            # the reference orders equally frequent patterns by set iteration order: only compare when rank 5 / 6 differ
+            pats = {}
+            by_head = {}
+            lt = alinet.remove_unlinked_triples(kg_obj.triples, linked)
+            for h, r, t in lt:
+                by_head.setdefault(h, []).append((r, t))
+            for h, rx, m in lt:
+                for ry, t in by_head.get(m, ()):
+                    if (h, t) not in kg_obj.ht:
+                        pats[(rx, ry)] = pats.get((rx, ry), 0) + 1
+            counts = sorted(pats.values(), reverse=True)
+            got = {tuple(x) for x in ag.two_hop_pairs(tri, linked, n, chunk=97).tolist()}     # tiny chunks: many of them
+            # the same selection with the array version's documented tie order (count desc, then (r_x, r_y))
+            dropped = {p for p, _ in sorted(pats.items(), key=lambda kv: (-kv[1], kv[0]))[:5]}
+            want = set()
+            for h, rx, m in lt:
+                for ry, t in by_head.get(m, ()):
+                    if (h, t) not in kg_obj.ht and (rx, ry) not in dropped:
+                        want.update([(h, t), (h, h)])
+            assert got == want and len(got) > 0
+            if len(counts) <= 5 or counts[4] != counts[5]:                   # no tie at the cut: the pinned builder agrees too
+                assert got == {(h, t) for h, _, t in alinet.generate_2hop_triples(kg_obj, linked)}
+        tri_all = alinet.remove_unlinked_triples(k1.triple_list + k2.triple_list + list(want_new1) + list(want_new2), linked)
+        want_one = alinet.no_weighted_adj(n, tri_all)[0]
+        one, two, tri = ag.build(t1, t2, sup1, sup2, linked, n)
+        assert {tuple(x) for x in tri.tolist()} == set(tri_all)
+        assert abs(sp.csr_matrix(one) - sp.csr_matrix(want_one)).max() < 1e-12
+        rels, ptr, pairs = ag.relation_index(tri)
+        want_ht = alinet.generate_rel_ht(tri_all)
+        assert sorted(rels.tolist()) == sorted(want_ht)
+        for i, r in enumerate(rels.tolist()):
+            assert sorted(map(tuple, pairs[ptr[i]:ptr[i + 1]].tolist())) == sorted(want_ht[r])
