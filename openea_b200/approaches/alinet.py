@@ -303,6 +303,50 @@ class DenseAdam:
             p.grad = None          # the kernel zeroed the buffer; drop it so autograd allocates a fresh one
 
 
+class NeighborTable:
+    """ε-truncated candidate lists as one device matrix: row_of[entity] → row of `ids` [n_keys, num] (−1: no list).
+    `table[entity]` still gives the Python list the reference's dict gave (alinet.py:1019-1039)."""
+
+    def __init__(self, keys, ids, n_ent):
+        self.ids = ids                                               # [n_keys, num] entity ids, on the device
+        self.row_of = torch.full((n_ent,), -1, dtype=torch.long, device=ids.device)
+        self.row_of[torch.as_tensor(keys, dtype=torch.long, device=ids.device)] = torch.arange(len(keys), device=ids.device)
+
+    def __getitem__(self, entity):
+        return self.ids[self.row_of[entity]].tolist()
+
+    def rows(self, entities):
+        return self.ids[self.row_of[entities]]
+
+
+def sample_negative_links(pos_links, neighbors1, neighbors2, pools, k, excluded_keys, n_ent, gen):
+    """generate_input_batch's negative links (alinet.py:983-1006) as tensor ops on the links' device.
+    truncated (neighbour tables given): for every positive (e1, e2), k DISTINCT candidates c of e1 give (e1, c) and k
+    of e2 give (c, e2) (random.sample without replacement = the k largest of `num` random keys per row);
+    uniform: k rounds of batch_size distinct entities from each pool, zipped.
+    The result is a set: distinct pairs minus the known links (`excluded_keys`, sorted packed keys i·n_ent + j),
+    returned sorted like np.array(sorted(neg))."""
+    dev = pos_links.device
+    b = pos_links.shape[0]
+    if neighbors1 is not None:
+        def side(table, anchors):
+            cand = table.rows(anchors)                                                   # [b, num]
+            pick = torch.rand(cand.shape, device=dev, generator=gen).topk(k, dim=1).indices
+            return cand.gather(1, pick)                                                  # [b, k] distinct per row
+        c1, c2 = side(neighbors1, pos_links[:, 0]), side(neighbors2, pos_links[:, 1])
+        left = torch.cat([pos_links[:, :1].expand(b, k).reshape(-1), c2.reshape(-1)])
+        right = torch.cat([c1.reshape(-1), pos_links[:, 1:].expand(b, k).reshape(-1)])
+    else:
+        pool1, pool2 = pools
+        draw = lambda pool: torch.cat([pool[torch.randperm(pool.numel(), device=dev, generator=gen)[:b]] for _ in range(k)])
+        left, right = draw(pool1), draw(pool2)
+    keys = torch.unique(left.long() * n_ent + right.long())                              # sorted, distinct
+    if excluded_keys.numel():
+        pos = torch.searchsorted(excluded_keys, keys).clamp(max=excluded_keys.numel() - 1)
+        keys = keys[excluded_keys[pos] != keys]
+    return torch.stack([keys // n_ent, keys % n_ent], 1)
+
+
 class AliNet(BasicModel):
 
     def __init__(self):
@@ -400,11 +444,36 @@ class AliNet(BasicModel):
         self.optimizer = DenseAdam(list(self.model.params.values()), self.args.learning_rate)
 
     # ---- batches (alinet.py:983-1017) ----
+    def _batch_state(self):
+        """Device-side constants of the batch generator: the seed links, the two uniform pools, the RNG stream, and the
+        sorted keys of the links a negative must not hit (seed links + links found by the augmentation)."""
+        dev = self.session.device
+        if getattr(self, "_bs", None) is None:
+            n = self.kgs.entities_num
+            gen = torch.Generator(device=dev)
+            gen.manual_seed(getattr(self.args, "seed", 0) or 0)
+            self._bs = dict(links=torch.as_tensor(self.sup_links, dtype=torch.long, device=dev), n=n, gen=gen,
+                            pools=(torch.as_tensor(self.sup_ent1 + self.ref_ent1, dtype=torch.long, device=dev),
+                                   torch.as_tensor(self.sup_ent2 + self.ref_ent2, dtype=torch.long, device=dev)),
+                            known=None, known_src=None)
+        bs = self._bs
+        if bs["known_src"] is not self.new_sup_links_set:          # augment_neighborhood replaces the set object
+            known = np.array(sorted(self.sup_links_set | self.new_sup_links_set), dtype=np.int64).reshape(-1, 2)
+            bs["known"] = torch.as_tensor(np.sort(known[:, 0] * bs["n"] + known[:, 1]), device=dev)
+            bs["known_src"] = self.new_sup_links_set
+        return bs
+
     def generate_input_batch(self, batch_size, neighbors1=None, neighbors2=None):
         batch_size = min(batch_size, len(self.sup_ent1))
         index = np.random.choice(len(self.sup_ent1), batch_size)
-        pos_links = self.sup_links[index, ]
         k = self.args.neg_triple_num
+        if neighbors1 is None or isinstance(neighbors1, NeighborTable):
+            # the whole batch on the device: no Python loop over the positives (alinet.py:983-1006 as tensor ops)
+            bs = self._batch_state()
+            pos = bs["links"][torch.as_tensor(index, device=bs["links"].device)]
+            neg = sample_negative_links(pos, neighbors1, neighbors2, bs["pools"], k, bs["known"], bs["n"], bs["gen"])
+            return pos, neg
+        pos_links = self.sup_links[index, ]
         if neighbors1 is None:
             pool1, pool2 = self.sup_ent1 + self.ref_ent1, self.sup_ent2 + self.ref_ent2
             neg1, neg2 = [], []
@@ -452,8 +521,8 @@ class AliNet(BasicModel):
                 s = F.sim_matrix(a, b, last.shape[1], "inner")
                 from openea_b200.modules.bootstrapping.alignment_finder import _topk_of_matrix
                 res = _topk_of_matrix(s, num)
-            ids = np.asarray(ids_b)[res.cpu().numpy()]
-            return {k: ids[i].tolist() for i, k in enumerate(keys)}
+            ids = torch.as_tensor(ids_b, dtype=torch.long, device=res.device)[res.long()]
+            return NeighborTable(keys, ids, self.kgs.entities_num)
         n1, n2 = cross(e1, e2, ents2, ents1), cross(e2, e1, ents1, ents2)
         print('finding neighbors for sampling costs time: {:.4f}s'.format(time.time() - start))
         return n1, n2
@@ -508,7 +577,8 @@ class AliNet(BasicModel):
 
     def train_step(self, pos_links, neg_links, hs=None, ts=None):
         dev = self.session.device
-        tl = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.long, device=dev)
+        tl = lambda a: a.to(device=dev, dtype=torch.long) if isinstance(a, torch.Tensor) else \
+            torch.as_tensor(np.asarray(a), dtype=torch.long, device=dev)
         outs = self.model.forward()
         loss = self.model.loss(outs, tl(pos_links), tl(neg_links), self.args.neg_margin, self.args.neg_margin_balance,
                                None if hs is None else tl(hs), None if ts is None else tl(ts), self.rel_win_size,
