@@ -48,7 +48,6 @@ def _hits1(out, tag):
     return float(m[-1])
 
 
-@pytest.mark.first_hw_run      # BootEA.run now bootstraps on the device (modules/bootstrapping/device.py)
 def test_bootea_lifecycle(cuda_device, tiny_kgs, tmp_path):
     from openea_b200 import presets
     from openea_b200.approaches import BootEA

@@ -213,7 +213,6 @@ def test_alinet_step_matches_oracle(cuda_device):
         np.testing.assert_allclose(model.params[k].detach().cpu().numpy(), want, rtol=1e-3, atol=2e-6)
 
 
-@pytest.mark.first_hw_run      # model code re-plumbed for row sharding / array graph builders since its last GPU run
 def test_alinet_lifecycle(cuda_device, tmp_path):
     import os
     import re
@@ -296,7 +295,6 @@ def test_rdgcn_step_matches_oracle(cuda_device):
         np.testing.assert_allclose(g, w, rtol=5e-3, atol=5e-5 * max(1e-9, np.abs(w).max()), err_msg=name)
 
 
-@pytest.mark.first_hw_run      # model code re-plumbed for row sharding / array graph builders since its last GPU run
 def test_rdgcn_lifecycle(cuda_device, tmp_path):
     import os
     import re

@@ -133,7 +133,6 @@ def test_model_training_steps_equal_dense_tf_steps(cuda_device, model, loss, k, 
             assert not tab.grad.any().item() and not tab.touched.any().item()
 
 
-@pytest.mark.first_hw_run
 def test_adadelta_steps_equal_dense_tf_steps(cuda_device):
     """tf.train.AdadeltaOptimizer through oea_rowopt_apply (dense rule: rows without gradient decay their accumulators):
     three TransE steps equal the oracle's dense steps on every row."""
