@@ -230,8 +230,12 @@ class BasicModel:
         self._epoch_seed = (self._epoch_seed * 6364136223846793005 + 1442695040888963407) & ((1 << 63) - 1)
         trained_samples_num = 0
         trainer = self.triple_trainer
-        # epoch 1 runs eagerly (warm-up); the multi-table trainers read the step's size back and are not captured
-        use_graph = getattr(self.args, "cuda_graph", True) and epoch > 1 and hasattr(trainer, "capture_epoch")
+        # the first epoch of a process runs eagerly (module loading, occupancy queries and allocator warm-up must not
+        # happen inside a stream capture; a resumed run starts at epoch > 1); the multi-table trainers read the step's
+        # size back and are not captured
+        use_graph = getattr(self.args, "cuda_graph", True) and getattr(self, "_ran_eager_epoch", False) and \
+            hasattr(trainer, "capture_epoch")
+        self._ran_eager_epoch = True
         if use_graph:
             key = (triple_steps, trainer._views(kg1, kg2, tset) and trainer._view_key)
             if getattr(self, "_epoch_graph_key", None) != key:      # (re)capture: first use, or new candidate lists
