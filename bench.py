@@ -407,11 +407,15 @@ def main():
     alg_bytes = score_bytes + 24.0 * d * n_touched
     kern_med_ms = float(np.median(kern_ms))
     achieved = alg_bytes / (kern_med_ms * 1e-3) / 1e9
-    traffic = None
+    # DRAM bytes per launch from committed `ncu --set full` captures (profiles/traffic_<workload>.json): the one-launch
+    # step kernel has no capture yet (null); the scorer it contains has one and is reported with its own roofline below
+    traffic = score_traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic_%s.json" % args.workload)
     if os.path.exists(tp):
         with open(tp) as f:
-            traffic = json.load(f).get("k_step_sampled_oct_dram_bytes_per_launch")
+            tj = json.load(f)
+        traffic = tj.get("k_step_sampled_oct_dram_bytes_per_launch")
+        score_traffic = tj.get("k_score_sampled_dram_bytes_per_launch")
     # the same steps as two launches (score kernel, optimiser kernel) with an event between them: what the score
     # kernel alone achieves against SURVEY §8d's scoring bytes (continuity with the r01 two-launch numbers)
     evs2 = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
@@ -429,7 +433,7 @@ def main():
                 "score_kernel_alone": {"kernel": "k_score_sampled_oct", "ms_median": score_med_ms,
                                        "achieved": score_bytes / (score_med_ms * 1e-3) / 1e9,
                                        "frac": score_bytes / (score_med_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
-                                       "two_launch_ms_per_step": split_step_ms}}
+                                       "two_launch_ms_per_step": split_step_ms, "traffic": score_traffic}}
 
     _phase("device-timed region done")
     # ---- e2e: the session.run(feed_dict) boundary with HOST index buffers -------------------------------------
