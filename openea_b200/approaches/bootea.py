@@ -237,6 +237,18 @@ class BootEA(AlignE):
             alignment_loss = self.alignment_trainer.read_loss() / total
             print("alignment_loss = {:.3f}, time = {:.3f} s".format(alignment_loss, time.time() - t1))
 
+    # ---- checkpoint / resume at iteration granularity (BasicModel.save_checkpoint + the bootstrapped labels) ---------
+    def _extra_state(self):
+        label = getattr(self, "_label", None)
+        return {"label": None if label is None else label.cpu()}
+
+    def _load_extra_state(self, extra):
+        if extra.get("label") is not None:
+            dev = self.ent_embeds.device
+            self._label = extra["label"].to(dev)
+            self._ref1 = torch.as_tensor(self.ref_ent1, dtype=torch.int64, device=dev)
+            self._ref2 = torch.as_tensor(self.ref_ent2, dtype=torch.int64, device=dev)
+
     def run(self):
         t = time.time()
         triples_num = self.kgs.kg1.relation_triples_num + self.kgs.kg2.relation_triples_num
@@ -245,7 +257,11 @@ class BootEA(AlignE):
         neighbors1, neighbors2 = None, None
         sub_num = self.args.sub_epoch
         iter_nums = self.args.max_epoch // sub_num
-        for i in range(1, iter_nums + 1):
+        first_iter = (getattr(self, "_start_epoch", 1) - 1) // sub_num + 1       # checkpoints are written after whole iterations
+        if first_iter > 1:
+            neighbors1, neighbors2 = self._refresh_neighbours()                  # derived state: rebuilt, not stored
+        every = getattr(self.args, "checkpoint_every", 0)
+        for i in range(first_iter, iter_nums + 1):
             print("\niteration", i)
             self.launch_training_k_epo(i, sub_num, triple_steps, steps_tasks, None, neighbors1, neighbors2)
             if i * sub_num >= self.args.start_valid:
@@ -264,4 +280,6 @@ class BootEA(AlignE):
             ent_num = len(self.kgs.kg1.entities_list) + len(self.kgs.kg2.entities_list)
             torch.cuda.synchronize()
             print("generating neighbors of {} entities costs {:.3f} s.".format(ent_num, time.time() - t1))
+            if every and (i * sub_num) % every == 0:
+                self.save_checkpoint(self.out_folder + "checkpoint.pt", i * sub_num)
         print("Training ends. Total time = {:.3f} s.".format(time.time() - t))

@@ -290,7 +290,8 @@ class BasicModel:
         early-stopping state and the host RNG streams (mapping batches, GNN negatives)."""
         state = {"epoch": int(epoch), "epoch_seed": int(self._epoch_seed), "flag1": self.flag1, "flag2": self.flag2,
                  "class": self.__class__.__name__, "python_random": random.getstate(), "numpy_random": np.random.get_state(),
-                 "tables": {name: tab.state_dict() for name, tab in self._checkpoint_tables().items()}}
+                 "tables": {name: tab.state_dict() for name, tab in self._checkpoint_tables().items()},
+                 "extra": self._extra_state()}
         os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
         tmp = path + ".tmp"
         torch.save(state, tmp)
@@ -311,8 +312,16 @@ class BasicModel:
         self._epoch_seed, self.flag1, self.flag2 = state["epoch_seed"], state["flag1"], state["flag2"]
         random.setstate(state["python_random"])
         np.random.set_state(state["numpy_random"])
+        self._load_extra_state(state.get("extra") or {})
         self._start_epoch = state["epoch"] + 1
         return self._start_epoch
+
+    def _extra_state(self):
+        """Approach-specific state beyond tables and seeds (host tensors / plain Python), e.g. BootEA's labels."""
+        return {}
+
+    def _load_extra_state(self, extra):
+        pass
 
     def run(self):
         t = time.time()

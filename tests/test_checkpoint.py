@@ -81,3 +81,20 @@ def test_checkpoint_of_another_model_is_refused(tmp_path):
     c.__dict__.update(_model(3).__dict__)
     with pytest.raises(ValueError):
         c.load_checkpoint(path)
+
+
+def test_bootea_checkpoint_carries_the_bootstrapped_labels(tmp_path):
+    from openea_b200.approaches.bootea import BootEA
+    def model(seed):
+        m = BootEA()
+        m.__dict__.update(_model(seed).__dict__)
+        m.ref_ent1, m.ref_ent2 = list(range(10)), list(range(10, 20))
+        return m
+    a, b = model(1), model(2)
+    a._label = torch.tensor([3, -1, 0, -1, 9, -1, -1, 2, -1, -1])
+    path = a.save_checkpoint(str(tmp_path) + "/checkpoint.pt", epoch=20)
+    assert b.load_checkpoint(path) == 21
+    assert torch.equal(b._label, a._label) and b._ref1.tolist() == a.ref_ent1 and b._ref2.tolist() == a.ref_ent2
+    c = model(3)                                         # a checkpoint from before the first bootstrapping pass
+    c.load_checkpoint(model(4).save_checkpoint(str(tmp_path) + "/early.pt", epoch=10))
+    assert getattr(c, "_label", None) is None
