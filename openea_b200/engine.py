@@ -424,8 +424,10 @@ class MappingTrainer:
         ws = self.lib.oea_mapping_workspace_bytes(ent.dim)
         self.ws = torch.empty(max(1, ws), dtype=torch.uint8, device=ent.device)
 
-    def step(self, ents1, ents2):
-        """One session.run([mapping_loss, mapping_optimizer]) (basic_model.py:244-246); returns the batch loss."""
+    def step(self, ents1, ents2, read_loss=True):
+        """One session.run([mapping_loss, mapping_optimizer]) (basic_model.py:244-246); returns the batch loss, or —
+        with read_loss=False — leaves it accumulated on the device for `read_loss()` (no host sync per step).
+        ents1 / ents2: entity id lists or int32 device tensors."""
         dev = self.ent.device
         i1 = torch.as_tensor(ents1, dtype=torch.int32, device=dev).contiguous()
         i2 = torch.as_tensor(ents2, dtype=torch.int32, device=dev).contiguous()
@@ -437,7 +439,8 @@ class MappingTrainer:
         L.check(self.lib.oea_table_lookup(C.byref(es), _ptr(i1), n, _ptr(e1), p, st), "oea_table_lookup")
         L.check(self.lib.oea_table_lookup(C.byref(es), _ptr(i2), n, _ptr(e2), p, st), "oea_table_lookup")
         g1, g2 = torch.empty_like(e1), torch.empty_like(e2)
-        self.loss_dev.zero_()
+        if read_loss:
+            self.loss_dev.zero_()
         L.check(self.lib.oea_mapping_fwd_bwd(_ptr(e1), _ptr(e2), n, d, p, _ptr(self.M.weight), self.M.pitch, self.alpha,
                                              _ptr(self.loss_dev), _ptr(g1), _ptr(g2), _ptr(self.M.grad), _ptr(self.ws),
                                              self.ws.numel(), st), "oea_mapping_fwd_bwd")
@@ -449,7 +452,13 @@ class MappingTrainer:
                 tab.adam_t += 1
             cfg = opt_cfg(tab, self.lr)
             L.check(self.lib.oea_rowopt_apply(C.byref(tab.c_struct()), C.byref(cfg), st), "oea_rowopt_apply")
-        return float(self.loss_dev.item())
+        return float(self.loss_dev.item()) if read_loss else None
+
+    def read_loss(self, reset=True):
+        v = float(self.loss_dev.item())
+        if reset:
+            self.loss_dev.zero_()
+        return v
 
 
 class EpochGraph:

@@ -253,13 +253,20 @@ class BasicModel:
 
     def launch_mapping_training_1epo(self, epoch, triple_steps):
         start = time.time()
-        epoch_loss = 0
-        trained_samples_num = 0
-        for _ in range(triple_steps):
-            links_batch = random.sample(self.kgs.train_links, len(self.kgs.train_links) // triple_steps)
-            epoch_loss += self.mapping_trainer.step([x[0] for x in links_batch], [x[1] for x in links_batch])
-            trained_samples_num += len(links_batch)
-        epoch_loss /= max(1, trained_samples_num)
+        # every step draws len(train_links) // triple_steps distinct seed pairs, independently of the other steps
+        # (random.sample per step, basic_model.py:241-243): all steps' index sets in one device draw — the per-row
+        # m largest of n random keys — and one loss read per epoch instead of one host sync per step
+        dev = self.ent_embeds.device
+        if getattr(self, "_links_dev", None) is None:
+            self._links_dev = torch.as_tensor(np.asarray(self.kgs.train_links, dtype=np.int32).reshape(-1, 2), device=dev)
+        n, m = self._links_dev.shape[0], len(self.kgs.train_links) // triple_steps
+        picks = torch.rand(triple_steps, n, device=dev).topk(m, dim=1).indices if m > 0 else None
+        self.mapping_trainer.loss_dev.zero_()
+        for step in range(triple_steps if m > 0 else 0):
+            batch = self._links_dev[picks[step]]
+            self.mapping_trainer.step(batch[:, 0], batch[:, 1], read_loss=False)
+        trained_samples_num = triple_steps * m
+        epoch_loss = self.mapping_trainer.read_loss() / max(1, trained_samples_num)
         print('epoch {}, avg. mapping loss: {:.4f}, cost time: {:.4f}s'.format(epoch, epoch_loss, time.time() - start))
         return epoch_loss
 

@@ -98,3 +98,35 @@ def test_bootea_checkpoint_carries_the_bootstrapped_labels(tmp_path):
     c = model(3)                                         # a checkpoint from before the first bootstrapping pass
     c.load_checkpoint(model(4).save_checkpoint(str(tmp_path) + "/early.pt", epoch=10))
     assert getattr(c, "_label", None) is None
+
+
+def test_mapping_epoch_draws_distinct_seed_pairs_per_step_on_the_device(capsys):
+    """BasicModel.launch_mapping_training_1epo (basic_model.py:238-250): every step trains on len(train_links) // steps
+    DISTINCT seed pairs drawn independently of the other steps; the loss is read once per epoch."""
+    from types import SimpleNamespace
+    rng = np.random.default_rng(0)
+    links = [(int(a), int(b)) for a, b in zip(rng.permutation(500)[:97], 500 + rng.permutation(500)[:97])]
+    seen = []
+
+    class Recorder:
+        loss_dev = torch.zeros(1, dtype=torch.float64)
+
+        def step(self, e1, e2, read_loss=True):
+            assert read_loss is False and e1.dtype == torch.int32
+            seen.append(list(zip(e1.tolist(), e2.tolist())))
+            self.loss_dev += len(e1)
+
+        def read_loss(self):
+            v = float(self.loss_dev.item())
+            self.loss_dev.zero_()
+            return v
+    m = BasicModel()
+    m.kgs = SimpleNamespace(train_links=links)
+    m.ent_embeds = SimpleNamespace(device=torch.device("cpu"))
+    m.mapping_trainer = Recorder()
+    loss = m.launch_mapping_training_1epo(3, 8)
+    assert len(seen) == 8 and all(len(b) == 97 // 8 and len(set(b)) == len(b) and set(b) <= set(links) for b in seen)
+    assert len({frozenset(b) for b in seen}) == 8                      # independent draws: the steps differ
+    assert loss == 1.0 and "avg. mapping loss: 1.0000" in capsys.readouterr().out
+    seen.clear()
+    assert m.launch_mapping_training_1epo(4, 200) == 0.0 and not seen    # more steps than links: empty batches, as [] would be
