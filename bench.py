@@ -274,6 +274,66 @@ def _phase(msg):
     sys.stderr.flush()
 
 
+def probe_pipelined_e2e(args):
+    """The same host-index steps through the depth-2 pipeline (oea_triple_step_fed_host_submit / _collect): first the
+    losses of 6 steps are checked against the synchronous API from identical tables, then K steps are timed back to back
+    (H2D of every step's index vectors and D2H of every step's loss inside the timed region; no L2 flush is possible
+    between overlapping steps, the tables are 12–80 MB).  Runs in its own process under the parent's time limit, so a
+    fault here cannot take the bench line with it.  Informational: not the headline e2e."""
+    import torch
+    from openea_b200 import engine as eng
+    torch.cuda.set_device(0)
+    device = torch.device("cuda", 0)
+    cfg = WORKLOADS[args.workload]
+    B, k = cfg["batch"], cfg["k"]
+
+    W = build_workload(args.workload, 0, device, 1)
+    tr = W["trainer"]
+    snap = [(t, t.weight.clone(), t.state1.clone()) for t in (tr.ent, tr.rel)]
+
+    def restore():       # both APIs start from the same variables and Adagrad accumulators
+        for t, w, a in snap:
+            t.weight.copy_(w); t.state1.copy_(a); t.grad.zero_(); t.touched.zero_()
+        tr.read_loss()
+        torch.cuda.synchronize()
+    t1, t2 = W["arr"]["triples1"], W["arr"]["triples2"]
+    dbg = torch.empty(B, 2 + k, dtype=torch.int32, device=device)
+    npos_dev = torch.zeros(1, dtype=torch.int32, device=device)
+    batches = []
+    for i in range(8):
+        tr.score_sampled(W["kg1"], W["kg2"], W["tset"], B, k, i % max(1, W["steps_per_epoch"] - 1), 0xE2E + i, dbg=dbg,
+                         n_pos_out=npos_dev)
+        torch.cuda.synchronize()
+        pos, neg = decode_dbg(dbg.cpu().numpy(), int(npos_dev.item()), t1, t2, k)
+        batches.append((torch.from_numpy(pos).pin_memory(), torch.from_numpy(neg).pin_memory()))
+    restore()
+    want = [tr.step_fed_host(*batches[i]) for i in range(6)]
+    restore()
+    pipe = eng.FedHostPipeline(tr, 3 * (batches[0][0].shape[1] + batches[0][1].shape[1]) + 64)
+    got = []
+    for i in range(6):
+        pipe.submit(i % 2, *batches[i])
+        if i >= 1:
+            got.append(pipe.collect((i - 1) % 2))
+    got.append(pipe.collect(5 % 2))
+    rel = max(abs(a - b) / max(1e-12, abs(b)) for a, b in zip(got, want))
+    K = max(8, args.steps)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(K):
+        pipe.submit(i % 2, *batches[i % 8])
+        if i >= 1:
+            pipe.collect((i - 1) % 2)
+    pipe.collect((K - 1) % 2)
+    dt = time.perf_counter() - t0
+    n_pos_h, n_neg_h = batches[0][0].shape[1], batches[0][1].shape[1]
+    print(json.dumps({"value": n_pos_h * K / dt, "unit": "positive triples/s", "ms_per_step": 1e3 * dt / K, "steps": K,
+                      "h2d_bytes_per_step": 12 * (n_pos_h + n_neg_h), "d2h_bytes_per_step": 8,
+                      "loss_max_rel_diff_vs_sync_api": rel, "losses_agree": bool(rel <= 1e-4),
+                      "api": "oea_triple_step_fed_host_submit / _collect (depth-2 pipeline, steps back to back, L2 not flushed)"}))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -283,7 +343,11 @@ def main():
     ap.add_argument("--workload", default="bootea_15k", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="diagnostic only: keep L2 warm between timed steps (the number is NOT a valid bench value)")
+    ap.add_argument("--probe-pipelined-e2e", action="store_true",
+                    help="internal: measure the depth-2 pipelined host-index step in this process and print its JSON")
     args = ap.parse_args()
+    if args.probe_pipelined_e2e:
+        return probe_pipelined_e2e(args)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -472,6 +536,15 @@ def main():
                "d2h_bytes_per_step": 8, "ms_per_step": 1e3 * e2e_s / K,
                "api": "oea_triple_step_fed_host (host index buffers, tables resident, synchronous)"}
         _phase("e2e done")
+        if rank == 0 and world == 1:
+            # informational: the same steps through the depth-2 pipelined API, in a process of its own with a time limit
+            try:
+                res = subprocess.run([sys.executable, os.path.abspath(__file__), "--probe-pipelined-e2e", "--workload",
+                                      args.workload, "--steps", str(max(K, 40))], capture_output=True, text=True, timeout=120)
+                e2e["pipelined"] = json.loads(res.stdout.strip().splitlines()[-1])
+            except Exception as exc:
+                e2e["pipelined"] = {"value": None, "note": "probe failed or timed out: %r" % (exc,)}
+            _phase("pipelined e2e probe done")
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             # the CPU port is timed in a fresh process (the same command as `--impl reference`): inside this process
             # the OpenMP runtime shares cores with torch's thread pools and runs up to 2× slower

@@ -221,6 +221,26 @@ int oea_triple_sample_batch(const oea_kg_view* kg1, const oea_kg_view* kg2, cons
                             const oea_sample_cfg* smp, int32_t sampler, const oea_table* warm,
                             int32_t* pos_hrt, int32_t* neg_hrt, int32_t* n_pos_host, void* stream);
 
+/* The same step as a depth-2 pipeline (oea_pipeline.cu): the H2D copy of step i+1 overlaps the kernels of step i and the
+ * host reads step i's loss while step i+1 runs; table updates stay strictly sequential on `compute_stream`.
+ * The caller owns everything: two streams, per slot two events (created with cudaEventDisableTiming or not), a device
+ * index buffer of >= 3·(n_pos+n_neg) int32, a device fp64 loss scalar and a PINNED host fp64 loss scalar.
+ * submit(slot) is asynchronous; collect(slot) blocks until that slot's step has finished and returns its loss.
+ * A submitted step's host index buffers must stay untouched until collect() of that step (or of a later one). */
+typedef struct oea_fed_pipeline {
+    void*    copy_stream;      /* cudaStream_t */
+    void*    compute_stream;   /* cudaStream_t */
+    void*    ev_copied[2];     /* cudaEvent_t */
+    void*    ev_computed[2];   /* cudaEvent_t */
+    int32_t* dev_idx[2];
+    double*  dev_loss[2];
+    double*  host_loss[2];
+} oea_fed_pipeline;
+int oea_triple_step_fed_host_submit(const oea_table* ent, const oea_table* rel, const oea_fed_pipeline* pipe, int32_t slot,
+                                    const int32_t* pos_hrt_host, int32_t n_pos, const int32_t* neg_hrt_host, int32_t n_neg,
+                                    const oea_loss_cfg* loss, const oea_opt_cfg* opt);
+int oea_triple_step_fed_host_collect(const oea_fed_pipeline* pipe, int32_t slot, float* loss_host);
+
 /* Normalised view of a table (what TF returns for `ent_embeds` when is_l2_norm):
  * out[i, :dim] = normalise(weight[ids[i]]) (ids == NULL → all rows).  Replaces
  * tf.nn.embedding_lookup(self.ent_embeds, ids).eval() of basic_model.py:106-121,185,198-204. */

@@ -404,6 +404,54 @@ class ModelTrainer:
         return v
 
 
+class FedHostPipeline:
+    """Depth-2 pipeline over TripleTrainer's host-index step (oea_triple_step_fed_host_submit / _collect): the copy of
+    step i+1 overlaps the kernels of step i; losses come back one step late.  Owns two streams, four events and the
+    per-slot buffers.  Usage: `for i, (pos, neg) in enumerate(batches): p.submit(i % 2, pos, neg); …; p.collect(i % 2)`
+    with the host buffers of a submitted step left untouched until it is collected."""
+
+    def __init__(self, trainer, max_indices):
+        self.trainer = trainer
+        dev = trainer.ent.device
+        torch.cuda.synchronize(dev)                          # tables were initialised on the default stream
+        self.copy_stream, self.compute_stream = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        self.events = [torch.cuda.Event() for _ in range(4)]
+        for ev in self.events:                               # a torch event gets its CUDA handle at the first record
+            ev.record(self.compute_stream)
+        self.compute_stream.synchronize()
+        self.idx = [torch.empty(max(1, max_indices), dtype=torch.int32, device=dev) for _ in range(2)]
+        self.loss_dev = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(2)]
+        self.loss_host = [torch.zeros(1, dtype=torch.float64).pin_memory() for _ in range(2)]
+        vp2 = lambda a, b: (C.c_void_p * 2)(a, b)
+        self.struct = L.FedPipeline(self.copy_stream.cuda_stream, self.compute_stream.cuda_stream,
+                                    vp2(self.events[0].cuda_event, self.events[1].cuda_event),
+                                    vp2(self.events[2].cuda_event, self.events[3].cuda_event),
+                                    vp2(self.idx[0].data_ptr(), self.idx[1].data_ptr()),
+                                    vp2(self.loss_dev[0].data_ptr(), self.loss_dev[1].data_ptr()),
+                                    vp2(self.loss_host[0].data_ptr(), self.loss_host[1].data_ptr()))
+
+    def submit(self, slot, pos_hrt, neg_hrt=None):
+        t = self.trainer
+        pos_t = _as_host_i32(pos_hrt)
+        neg_t = _as_host_i32(neg_hrt) if neg_hrt is not None else None
+        n_pos, n_neg = pos_t.shape[1], 0 if neg_t is None else neg_t.shape[1]
+        assert 3 * (n_pos + n_neg) <= self.idx[slot].numel() and pos_t.is_pinned()
+        for tab in (t.ent, t.rel):
+            if tab.optimizer == "Adam":
+                tab.adam_t += 1
+        cfg = opt_cfg(t.ent, t.lr)
+        L.check(t.lib.oea_triple_step_fed_host_submit(
+            C.byref(t.ent.c_struct()), C.byref(t.rel.c_struct()), C.byref(self.struct), int(slot),
+            C.c_void_p(pos_t.data_ptr()), n_pos, C.c_void_p(0 if neg_t is None else neg_t.data_ptr()), n_neg,
+            C.byref(t.loss), C.byref(cfg)), "oea_triple_step_fed_host_submit")
+
+    def collect(self, slot):
+        loss = C.c_float(0.0)
+        L.check(self.trainer.lib.oea_triple_step_fed_host_collect(C.byref(self.struct), int(slot), C.byref(loss)),
+                "oea_triple_step_fed_host_collect")
+        return float(loss.value)
+
+
 def _as_host_i32(a):
     if isinstance(a, torch.Tensor):
         assert a.dtype == torch.int32 and not a.is_cuda and a.is_contiguous()

@@ -71,6 +71,12 @@ _P, _I, _L = C.c_void_p, C.c_int32, C.c_int64
 _TP = C.POINTER(Table)
 
 
+class FedPipeline(C.Structure):
+    _fields_ = [("copy_stream", C.c_void_p), ("compute_stream", C.c_void_p), ("ev_copied", C.c_void_p * 2),
+                ("ev_computed", C.c_void_p * 2), ("dev_idx", C.c_void_p * 2), ("dev_loss", C.c_void_p * 2),
+                ("host_loss", C.c_void_p * 2)]
+
+
 class Model(C.Structure):
     _fields_ = [("kind", C.c_int32), ("ent", _TP), ("rel", _TP), ("ent_aux", _TP), ("rel_aux", _TP)]
 
@@ -89,6 +95,9 @@ SIGNATURES = {
                                            C.POINTER(SampleCfg), C.POINTER(LossCfg), _P, _P, _P, _P]),
     "oea_triple_step_fed_host": (C.c_int, [_TP, _TP, _P, _I, _P, _I, C.POINTER(LossCfg), C.POINTER(OptCfg),
                                            _P, _P, _P, C.POINTER(C.c_float), _P]),
+    "oea_triple_step_fed_host_submit": (C.c_int, [_TP, _TP, C.POINTER(FedPipeline), _I, _P, _I, _P, _I,
+                                                  C.POINTER(LossCfg), C.POINTER(OptCfg)]),
+    "oea_triple_step_fed_host_collect": (C.c_int, [C.POINTER(FedPipeline), _I, C.POINTER(C.c_float)]),
     "oea_table_lookup": (C.c_int, [_TP, _P, _I, _P, _I, _P]),
     "oea_sim_transpose_ld": (C.c_int64, [_I]),
     "oea_sim_transpose_bytes": (C.c_size_t, [_I, _I]),

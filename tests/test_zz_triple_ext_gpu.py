@@ -363,3 +363,34 @@ def test_resume_from_checkpoint_continues_the_same_run(cuda_device, tiny_kgs, tm
         np.testing.assert_allclose(b.raw().cpu().numpy(), a.raw().cpu().numpy(), rtol=2e-3, atol=2e-5, err_msg=name)
         np.testing.assert_allclose(b.state1.cpu().numpy(), a.state1.cpu().numpy(), rtol=2e-3, atol=2e-5, err_msg=name)
     assert resumed._epoch_seed == straight._epoch_seed
+
+
+@pytest.mark.first_hw_run
+def test_pipelined_host_step_equals_the_synchronous_one(cuda_device):
+    """oea_triple_step_fed_host_submit / _collect (depth-2 pipeline: copies and the host wait off the critical path)
+    against oea_triple_step_fed_host on the same batches from the same tables: per-step losses and the final tables."""
+    eng = _engine()
+    rng = np.random.default_rng(8)
+    d, n_ent, n_rel = 100, 4000, 37
+    from tests.helpers import make_tables
+    ent, rel = make_tables(rng, n_ent, n_rel, d)
+    cfg = eng.loss_cfg("limited", "L2", margin=0.01, neg_margin=2.0, balance=0.2)
+    batches = []
+    for _ in range(7):
+        pos, neg = make_batch(rng, n_ent, n_rel, 600, 10)
+        batches.append((torch.from_numpy(pos).pin_memory(), torch.from_numpy(neg).pin_memory()))
+    a = eng.TripleTrainer(eng.EmbeddingTable(ent, True), eng.EmbeddingTable(rel, True), cfg, 0.01)
+    want = [a.step_fed_host(p, n) for p, n in batches]
+    b = eng.TripleTrainer(eng.EmbeddingTable(ent, True), eng.EmbeddingTable(rel, True), cfg, 0.01)
+    pipe = eng.FedHostPipeline(b, 3 * 600 * 11)
+    got = []
+    for i, (p, n) in enumerate(batches):
+        pipe.submit(i % 2, p, n)
+        if i:
+            got.append(pipe.collect((i - 1) % 2))
+    got.append(pipe.collect((len(batches) - 1) % 2))
+    np.testing.assert_allclose(got, want, rtol=1e-4)
+    torch.cuda.synchronize()
+    for x, y in ((a.ent, b.ent), (a.rel, b.rel)):
+        np.testing.assert_allclose(y.raw().cpu().numpy(), x.raw().cpu().numpy(), rtol=1e-4, atol=1e-6)
+        assert not y.grad.any().item() and not y.touched.any().item()
