@@ -227,17 +227,14 @@ class ArrayKG:
         self.av_dict = _group_pairs((e for e, _, _ in local), ((a, v) for _, a, v in local))
         self.entity_attributes_dict = _group_pairs((e for e, _, _ in local), (a for _, a, _ in local))
 
-    _BUILDERS = {}
-    for _names, _fn in (
-            (("relation_triples_set", "relation_triples_list", "local_relation_triples_set",
-              "local_relation_triples_list"), "_build_relation_sets"),
-            (("attribute_triples_set", "attribute_triples_list", "local_attribute_triples_set",
-              "local_attribute_triples_list"), "_build_attribute_sets"),
-            (("rt_dict", "hr_dict", "entity_relations_dict"), "_build_relation_dicts"),
-            (("av_dict", "entity_attributes_dict"), "_build_attribute_dicts")):
-        for _n in _names:
-            _BUILDERS[_n] = _fn
-    del _names, _fn, _n
+    # reference attribute name → the method that materialises it (together with its siblings) on first access
+    _BUILDERS = dict(
+        [(n, "_build_relation_sets") for n in ("relation_triples_set", "relation_triples_list",
+                                               "local_relation_triples_set", "local_relation_triples_list")] +
+        [(n, "_build_attribute_sets") for n in ("attribute_triples_set", "attribute_triples_list",
+                                                "local_attribute_triples_set", "local_attribute_triples_list")] +
+        [(n, "_build_relation_dicts") for n in ("rt_dict", "hr_dict", "entity_relations_dict")] +
+        [(n, "_build_attribute_dicts") for n in ("av_dict", "entity_attributes_dict")])
 
     def __getattr__(self, name):                 # only reached when the attribute is not on the instance yet
         for kind in ("relation", "attribute"):
