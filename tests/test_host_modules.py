@@ -268,3 +268,66 @@ def test_array_loader_refuses_what_only_the_container_loader_covers(tmp_path):
         fast.load(folder, "721_5fold/1/", "mapping", True, remove_unlinked=True)
     rows = np.array([[3, 1, 2], [3, 1, 2], [0, 0, 0], [3, 1, 1]], dtype=np.int32)
     assert fast.unique_int_rows(rows).tolist() == [[3, 1, 2], [0, 0, 0], [3, 1, 1]]
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_array_loader_equals_container_loader_on_random_folders(tmp_path, monkeypatch, seed):
+    """Random small datasets with everything that stresses the id assignment: equal occurrence counts (ties broken by
+    name), non-ASCII and prefix-related names, KGs of very different sizes, entities that occur only in attribute
+    triples, repeated lines.  Both loaders must agree on every id and every triple in all three id modes (the container
+    loader is the line-by-line mirror of the reference, pinned above)."""
+    from openea_b200.modules.load import fast
+    from openea_b200.modules.load.kgs import read_kgs_from_folder
+    rng = np.random.default_rng(seed)
+    names = ["e%d" % i for i in range(12)] + ["é%d" % i for i in range(6)] + ["e1%d" % i for i in range(6)] + ["实体%d" % i for i in range(4)]
+    folder = str(tmp_path) + "/"
+    os.makedirs(folder + "721_5fold/1")
+    sizes = [(int(rng.integers(8, 28)), int(rng.integers(20, 90))), (int(rng.integers(4, 12)), int(rng.integers(6, 40)))]
+    ents = []
+    for side, (n_e, n_t) in zip(("1", "2"), sizes):
+        e = ["kg%s:%s" % (side, x) for x in rng.permutation(names)[:n_e]]
+        ents.append(e)
+        rels = ["kg%s:p%d" % (side, i) for i in range(int(rng.integers(1, 5)))]
+        with open(folder + "rel_triples_" + side, "w", encoding="utf8") as f:
+            for _ in range(n_t):
+                f.write("%s\t%s\t%s\n" % (e[rng.integers(n_e)], rels[rng.integers(len(rels))], e[rng.integers(n_e)]))
+        with open(folder + "attr_triples_" + side, "w", encoding="utf8") as f:
+            for _ in range(int(rng.integers(3, 30))):
+                who = e[rng.integers(n_e)] if rng.random() < 0.8 else "kg%s:attr-only%d" % (side, rng.integers(3))
+                f.write("%s\tkg%s:a%d\t\"v %d\" .\n" % (who, side, rng.integers(4), rng.integers(6)))
+    n_links = min(len(ents[0]), len(ents[1]))
+    pairs = list(zip(rng.permutation(ents[0])[:n_links], rng.permutation(ents[1])[:n_links]))
+    # only entities that occur in relation / attribute triples can be linked (the reference raises KeyError otherwise)
+    with contextlib.redirect_stdout(io.StringIO()):
+        monkeypatch.setenv("OEA_LOADER", "containers")
+        known1 = {h for h, _, t in _quiet_read(folder + "rel_triples_1")} | {t for _, _, t in _quiet_read(folder + "rel_triples_1")}
+        known2 = {h for h, _, t in _quiet_read(folder + "rel_triples_2")} | {t for _, _, t in _quiet_read(folder + "rel_triples_2")}
+    pairs = [(a, b) for a, b in pairs if a in known1 and b in known2]
+    if len(pairs) < 3:
+        pytest.skip("degenerate draw")
+    cut = max(1, len(pairs) // 3)
+    for name, part in (("train", pairs[:cut]), ("valid", pairs[cut:2 * cut]), ("test", pairs[2 * cut:])):
+        with open(folder + "721_5fold/1/%s_links" % name, "w", encoding="utf8") as f:
+            f.writelines("%s\t%s\n" % p for p in part)
+    monkeypatch.setenv("OEA_NO_DATASET_CACHE", "1")
+    for mode in ("mapping", "sharing", "swapping"):
+        with contextlib.redirect_stdout(io.StringIO()):
+            monkeypatch.setenv("OEA_LOADER", "containers")
+            want = read_kgs_from_folder(folder, "721_5fold/1/", mode, True)
+            monkeypatch.setenv("OEA_LOADER", "arrays")
+            got = read_kgs_from_folder(folder, "721_5fold/1/", mode, True)
+        assert isinstance(got, fast.ArrayKGs) and not isinstance(want, fast.ArrayKGs)
+        assert (got.entities_num, got.relations_num, got.attributes_num) == (want.entities_num, want.relations_num, want.attributes_num)
+        for side in ("kg1", "kg2"):
+            a, b = getattr(got, side), getattr(want, side)
+            for name in ("entities_id_dict", "relations_id_dict", "attributes_id_dict", "relation_triples_set",
+                         "attribute_triples_set", "sup_relation_triples_set", "sup_attribute_triples_set", "rt_dict",
+                         "hr_dict", "av_dict", "entity_relations_dict", "entity_attributes_dict", "entities_set"):
+                assert getattr(a, name) == getattr(b, name), (mode, side, name)
+        assert got.train_links == want.train_links and got.valid_links == want.valid_links and got.test_links == want.test_links
+
+
+def _quiet_read(path):
+    from openea_b200.modules.load import read as rd
+    with contextlib.redirect_stdout(io.StringIO()):
+        return rd.read_relation_triples(path)[0]
