@@ -32,5 +32,21 @@ def build(force=False):
     return OUT
 
 
+def build_selftest(force=False):
+    """tests/emu/libemu_selftest.so: the emulator's own collectives checked against CUDA's documented behaviour."""
+    inc = cuda_include()
+    if inc is None:
+        return None
+    src, out = os.path.join(HERE, "emu_selftest.cpp"), os.path.join(HERE, "libemu_selftest.so")
+    deps = [src, os.path.join(HERE, "cuda_host_emu.h")]
+    if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
+        return out
+    cmd = ["g++", "-std=c++20", "-O1", "-pthread", "-fPIC", "-shared", "-Wno-attributes", "-I", inc, "-o", out, src]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("emulator self-test build failed:\n" + res.stderr[-4000:])
+    return out
+
+
 if __name__ == "__main__":
     print(build(force=True))

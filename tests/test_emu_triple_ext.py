@@ -145,3 +145,15 @@ def test_emulated_adadelta_update_matches_tf_rule(emu):
         assert not tab.grad.any() and not tab.touched.any() and not tab.weight[:, d:].any()
     bad = L.OptCfg(L.OPT_ADAM, 0.7, 0.95, 0.0, 1e-8, 1)
     assert emu.oea_rowopt_adadelta(C.byref(tab.struct), C.byref(bad), None) == 4      # OEA_ERR_KIND
+
+
+def test_emulator_collectives_behave_like_cuda():
+    """cuda_host_emu.h itself: butterfly reductions, broadcasts, ballots, match_any, collectives on lane SUBSETS while
+    the other lanes run ahead, 64-bit payloads, and the publish / barrier / consume pattern of LossAcc::flush."""
+    so = build_emu.build_selftest()
+    if so is None:
+        pytest.skip("no CUDA headers for the emulator build")
+    lib = C.CDLL(so)
+    lib.emu_selftest.restype = C.c_int
+    for _ in range(3):                       # thread interleavings differ from run to run
+        assert lib.emu_selftest() == 0
