@@ -5,7 +5,9 @@
 //   2. latency of ONE dependent chain per warp: index → row → index taken from that row (what a positive's
 //      triple → candidate list → entity row → hash probe chain looks like), L2-resident and DRAM;
 //   3. red.global.add.v4.f32 throughput into an L2-resident gradient table: distinct rows vs 64 hot rows (hubs);
-//   4. cost of one cooperative grid barrier at one CTA per SM and at full occupancy.
+//   4. cost of one cooperative grid barrier at one CTA per SM and at full occupancy;
+//   5. the same independent gathers as 1-D bulk async copies (cp.async.bulk = TMA's linear mode, one elected lane per
+//      row, completion on an mbarrier) into shared memory — does TMA staging beat 25 lanes × ld.global.v4 for 400-B rows?
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -rdc=false -o scripts/ubench_gather.bin scripts/ubench_gather.cu
 // Run on the GPU box: scripts/ubench_gather.bin > gpurun_out/ubench_gather.txt
 #include <cooperative_groups.h>
@@ -39,6 +41,44 @@ __global__ void __launch_bounds__(256) k_gather(const float* __restrict__ tab, u
         }
 #pragma unroll
         for (int j = 0; j < INFLIGHT; ++j) acc += v[j].x + v[j].y + v[j].z + v[j].w;
+    }
+    if (acc == 1234.5f) out[0] = acc;
+}
+
+// 5. independent gathers through the bulk-copy engine: lane 0 of each warp arms its mbarrier with INFLIGHT × 400 B and
+// issues INFLIGHT bulk copies; the warp waits on the barrier's phase and reads the rows from shared memory.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int INFLIGHT>
+__global__ void __launch_bounds__(256) k_gather_bulk(const float* __restrict__ tab, uint32_t rows, int per_warp, float* out) {
+    __shared__ __align__(128) float stage[8][INFLIGHT][128];      // 512-B slots, one set per warp
+    __shared__ __align__(8) unsigned long long bar[8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t b = smem_u32(&bar[w]);
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(b), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    float acc = 0.f;
+    uint32_t phase = 0;
+    for (int it = 0; it < per_warp; it += INFLIGHT) {
+        if (lane == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(b), "r"(INFLIGHT * PITCH * 4) : "memory");
+#pragma unroll
+            for (int j = 0; j < INFLIGHT; ++j) {
+                const uint32_t r = pcg(warp * 9781u + (it + j) * 31u) % rows;
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             :: "r"(smem_u32(&stage[w][j][0])), "l"(tab + (size_t)r * PITCH), "r"(PITCH * 4), "r"(b) : "memory");
+            }
+        }
+        asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @!p bra WAIT_%=;\n}"
+                     :: "r"(b), "r"(phase) : "memory");
+        phase ^= 1u;
+#pragma unroll
+        for (int j = 0; j < INFLIGHT; ++j)
+            if (lane < PITCH / 4) { const float4 v = reinterpret_cast<const float4*>(&stage[w][j][0])[lane]; acc += v.x + v.y + v.z + v.w; }
+        __syncwarp();                                            // all lanes have read the slots before they are refilled
     }
     if (acc == 1234.5f) out[0] = acc;
 }
@@ -114,6 +154,10 @@ int main() {
         printf("gather, 4 rows in flight per warp: %.3f ms  %.2f Grows/s  %.0f GB/s\n", ms, n_rows / ms * 1e-6, n_rows * 400 / ms * 1e-6);
         ms = time_ms([&] { k_gather<8><<<grid, 256>>>(tab, rows, per_warp, out); });
         printf("gather, 8 rows in flight per warp: %.3f ms  %.2f Grows/s  %.0f GB/s\n", ms, n_rows / ms * 1e-6, n_rows * 400 / ms * 1e-6);
+        ms = time_ms([&] { k_gather_bulk<4><<<grid, 256>>>(tab, rows, per_warp, out); });
+        printf("bulk-copy gather (cp.async.bulk + mbarrier), 4 rows in flight per warp: %.3f ms  %.2f Grows/s  %.0f GB/s\n", ms, n_rows / ms * 1e-6, n_rows * 400 / ms * 1e-6);
+        ms = time_ms([&] { k_gather_bulk<8><<<grid, 256>>>(tab, rows, per_warp, out); });
+        printf("bulk-copy gather (cp.async.bulk + mbarrier), 8 rows in flight per warp: %.3f ms  %.2f Grows/s  %.0f GB/s\n", ms, n_rows / ms * 1e-6, n_rows * 400 / ms * 1e-6);
         for (int g : {1, sms, sms * 8}) {
             const int hops = 2000;
             ms = time_ms([&] { k_chain<<<g, 256>>>(tab, rows, hops, out); });
