@@ -34,8 +34,22 @@ def get_model(model_name):
     return getattr(ModelFamily, model_name)
 
 
+def init_process_group_from_env():
+    """Under `torchrun --nproc-per-node G main_from_args.py …` (one process per GPU): bind this rank to its GPU and join
+    the NCCL group; the GNN approaches then row-shard their graphs (openea_b200/parallel_gnn.py) and the evaluation
+    shards its CSLS rows.  A plain `python main_from_args.py …` run is untouched."""
+    if int(os.environ.get("WORLD_SIZE", "1")) <= 1:
+        return
+    import torch
+    import torch.distributed as dist
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+
 if __name__ == '__main__':
     t = time.time()
+    init_process_group_from_env()
     args = load_args(sys.argv[1])
     args.training_data = args.training_data + sys.argv[2] + '/'
     args.dataset_division = sys.argv[3]
