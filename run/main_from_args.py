@@ -36,8 +36,8 @@ def get_model(model_name):
 
 def init_process_group_from_env():
     """Under `torchrun --nproc-per-node G main_from_args.py …` (one process per GPU): bind this rank to its GPU and join
-    the NCCL group; the GNN approaches then row-shard their graphs (openea_b200/parallel_gnn.py) and the evaluation
-    shards its CSLS rows.  A plain `python main_from_args.py …` run is untouched."""
+    the NCCL group; the GNN approaches then row-shard their graphs (openea_b200/parallel_gnn.py).  A plain
+    `python main_from_args.py …` run is untouched."""
     if int(os.environ.get("WORLD_SIZE", "1")) <= 1:
         return
     import torch
