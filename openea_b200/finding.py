@@ -210,7 +210,15 @@ def greedy_alignment(embed1, embed2, top_k, nums_threads, metric, normalize, csl
     """Drop-in for modules/finding/alignment.py:13.  `nums_threads` is accepted and ignored (one GPU pass).
     Quick mode (accurate=False) computes the same exact ranks; only the printed line differs."""
     t = time.time()
-    top1, _, hits, mr, mrr = eval_alignment(embed1, embed2, top_k, metric, normalize, csls_k)
+    from . import parallel as par
+    if par.world()[1] > 1:
+        # one process per GPU: every rank ranks its block of embed1's rows (one all-gather of partial column top-k
+        # lists for CSLS), the statistics are all-reduced and the arg-max column of every row is gathered
+        n1 = embed1.shape[0]
+        hits, mr, mrr, (_, _, top1, _) = eval_alignment_sharded(embed1, embed2, top_k, metric, normalize, csls_k)
+        top1 = par.allgather_blocks(top1, n1)
+    else:
+        top1, _, hits, mr, mrr = eval_alignment(embed1, embed2, top_k, metric, normalize, csls_k)
     top1_h = top1.cpu().numpy()
     alignment_rest = set(zip(range(len(top1_h)), top1_h.tolist()))
     hits_arr = np.array(hits)

@@ -108,3 +108,21 @@ def allreduce_sum(t):
     if ws > 1:
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return t
+
+
+def allgather_blocks(x_local, n_total):
+    """Every rank holds the rows block_range(n_total, rank, G) of a tensor: returns the whole [n_total, …] tensor on every
+    rank (blocks differ by at most one row: padded to the largest, gathered, re-assembled)."""
+    rank, ws = world()
+    if ws == 1:
+        return x_local
+    biggest = -(-n_total // ws)
+    send = torch.zeros((biggest,) + tuple(x_local.shape[1:]), dtype=x_local.dtype, device=x_local.device)
+    send[:x_local.shape[0]] = x_local
+    recv = torch.empty((ws * biggest,) + tuple(x_local.shape[1:]), dtype=x_local.dtype, device=x_local.device)
+    dist.all_gather_into_tensor(recv, send)
+    parts = []
+    for r in range(ws):
+        lo, hi = block_range(n_total, r, ws)
+        parts.append(recv[r * biggest:r * biggest + (hi - lo)])
+    return torch.cat(parts, 0)

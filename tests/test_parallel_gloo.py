@@ -59,6 +59,10 @@ def _worker(rank, world, port, out):
         part_v, _ = orf.topk_rows(np.ascontiguousarray(s[lo:hi].T), k)       # columns over my rows → [n2, k]
         merged = par.merge_partial_topk(par.allgather_partial(torch.from_numpy(part_v)), k).numpy()
         np.testing.assert_allclose(merged, orf.nearest_k_mean(np.ascontiguousarray(s.T), k), rtol=1e-6)
+        # ---- ragged row blocks re-assembled on every rank (the arg-max columns of the sharded evaluation)
+        full = torch.arange(37 * 3, dtype=torch.int32).reshape(37, 3)
+        assert torch.equal(par.allgather_blocks(full[lo:hi].clone(), 37), full)
+        assert torch.equal(par.allgather_blocks(full[lo:hi, 0].clone(), 37), full[:, 0])
         ranges = [par.block_range(37, r, world) for r in range(world)]
         assert ranges[0][0] == 0 and ranges[-1][1] == 37 and all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
         out.put((rank, "ok"))
