@@ -436,6 +436,7 @@ class AliNet(BasicModel):
             # are sharded (openea_b200/parallel_gnn.py); batches must be identical on every rank
             from openea_b200 import parallel_gnn as pg
             random.seed(seed)
+            par.mark_replicas_in_sync()        # every rank holds the same outputs: the evaluation may be sharded
             np.random.seed(seed)
             self.model = pg.ShardedAliNetModel(self.kgs.entities_num, self.args.layer_dims, adj[0], adj[1], dev, seed=seed)
         else:

@@ -105,6 +105,7 @@ class GCN_Align(BasicModel):
             # slices of the single-GPU initialisation
             from openea_b200 import parallel_gnn as pg
             shard = pg.RowShard(n)
+            par.mark_replicas_in_sync()        # every rank holds the same outputs: the evaluation may be sharded
             norm_adj = gnn.preprocess_adj(self.adj)
             self.model_ae = pg.ShardedGCNAlignUnit(norm_adj, EmbeddingTable(ae_init, True, "SGD", dev), self.attr,
                                                    *unit_args, shard=shard)

@@ -231,6 +231,7 @@ class RDGCN(BasicModel):
         if par.world()[1] > 1:      # one process per GPU (torchrun): entity rows sharded (openea_b200/parallel_gnn.py)
             from openea_b200 import parallel_gnn as pg
             layer_cls = pg.ShardedRDGCNLayer
+            par.mark_replicas_in_sync()        # every rank holds the same outputs: the evaluation may be sharded
         self.gcn_model = layer_cls(self.args, self.kgs, self.local_name_vectors, self.session.device,
                                    seed=getattr(self.args, "seed", 0) or 0)
         self.optimizer = DenseAdam(list(self.gcn_model.params.values()), self.args.learning_rate)

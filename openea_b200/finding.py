@@ -211,8 +211,8 @@ def greedy_alignment(embed1, embed2, top_k, nums_threads, metric, normalize, csl
     Quick mode (accurate=False) computes the same exact ranks; only the printed line differs."""
     t = time.time()
     from . import parallel as par
-    if par.world()[1] > 1:
-        # one process per GPU: every rank ranks its block of embed1's rows (one all-gather of partial column top-k
+    if par.replicas_in_sync():
+        # one process per GPU with identical embeddings on every rank: every rank ranks its block of embed1's rows (one all-gather of partial column top-k
         # lists for CSLS), the statistics are all-reduced and the arg-max column of every row is gathered
         n1 = embed1.shape[0]
         hits, mr, mrr, (_, _, top1, _) = eval_alignment_sharded(embed1, embed2, top_k, metric, normalize, csls_k)

@@ -22,6 +22,21 @@ def world():
     return 0, 1
 
 
+# Set by the approaches whose ranks hold identical embeddings (the row-sharded GNN models gather every layer output on
+# every rank).  Only then may the evaluation be sharded: it combines row blocks and column lists computed on different
+# ranks, which is meaningless for independently trained replicas.
+_replicas_in_sync = False
+
+
+def mark_replicas_in_sync(value=True):
+    global _replicas_in_sync
+    _replicas_in_sync = bool(value)
+
+
+def replicas_in_sync():
+    return _replicas_in_sync and world()[1] > 1
+
+
 def owner_of(ids, world_size):
     """Cyclic row ownership: ids interleave the two KGs by descending frequency (read.py:69-79), so contiguous
     blocks would put every hub on rank 0."""
