@@ -167,6 +167,7 @@ class BootEA(AlignE):
             epoch = (iter - 1) * iter_nums + i
             self.launch_triple_training_1epo(epoch, triple_steps, steps_tasks, training_batch_queue, neighbors1,
                                              neighbors2)
+            self._sync_seed_rows()             # no-op on one GPU
 
     def train_alignment(self, kg1: KG, kg2: KG, entities1, entities2, training_epochs):
         if entities1 is None or len(entities1) == 0:
@@ -251,7 +252,7 @@ class BootEA(AlignE):
 
     def run(self):
         t = time.time()
-        triples_num = self.kgs.kg1.relation_triples_num + self.kgs.kg2.relation_triples_num
+        triples_num = self._local_triples_num()
         triple_steps = int(math.ceil(triples_num / self.args.batch_size))
         steps_tasks = task_divide(list(range(triple_steps)), self.args.batch_threads_num)
         neighbors1, neighbors2 = None, None
@@ -269,6 +270,7 @@ class BootEA(AlignE):
                 self.flag1, self.flag2, self.early_stop = early_stop(self.flag1, self.flag2, flag)
                 if self.early_stop or i == iter_nums:
                     break
+            self._sync_replicas()              # under torchrun every rank must label the same pairs (no-op on one GPU)
             entities1, entities2 = self.bootstrap_on_device()
             self.train_alignment_device(entities1, entities2, 1)
             if i * sub_num >= self.args.start_valid:

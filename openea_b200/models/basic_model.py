@@ -20,6 +20,7 @@ import torch
 import openea_b200.modules.load.read as rd
 import openea_b200.modules.train.batch as bat
 from openea_b200 import engine as eng
+from openea_b200 import parallel as par
 from openea_b200.modules.base.initializers import init_embeddings, set_default_optimizer
 from openea_b200.modules.base.mapping import add_mapping_variables, add_mapping_module
 from openea_b200.modules.finding.alignment import stable_alignment
@@ -108,8 +109,41 @@ class BasicModel:
                                     kg.entities_list if entities is None else entities, self.kgs.entities_num, dev)
             self._dkg1, self._dkg2 = device_kg(self.kgs.kg1), device_kg(self.kgs.kg2)
             self._tset = eng.DeviceTripleSet([self._dkg1.triples, self._dkg2.triples], self.kgs.entities_num,
-                                             self.kgs.relations_num, dev)
+                                             self.kgs.relations_num, dev)       # membership test: ALL triples, every rank
+            rank, world = par.world()
+            if world > 1:      # one process per GPU: this rank trains on the triples whose head row it owns (id mod G)
+                for dkg in (self._dkg1, self._dkg2):
+                    mine = par.shard_triples(dkg.triples.cpu().numpy(), rank, world)
+                    dkg.triples = torch.as_tensor(np.ascontiguousarray(mine, dtype=np.int32), device=dev)
         return self._dkg1, self._dkg2, self._tset
+
+    # ---- one process per GPU (the same scheme bench.py times) -----------------------------------------
+    def _sync_seed_rows(self):
+        """End of a local epoch: the owners' copies of the seed-pair rows go to every replica (the only data-path
+        collective of path (i)); replicas are otherwise stale."""
+        rank, world = par.world()
+        if world == 1:
+            return
+        if getattr(self, "_seed_sync", None) is None:
+            seeds = np.asarray(self.kgs.train_links, dtype=np.int64).reshape(-1)
+            self._seed_sync = par.SeedRowSync(self.ent_embeds.weight, seeds, rank, world)
+        self._seed_sync.sync()
+
+    def _sync_replicas(self):
+        """Before anything that must agree across ranks (validation and its early-stop decision, test, bootstrapping,
+        saving): every entity row from its owner, every other table averaged.  Afterwards the replicas are identical."""
+        rank, world = par.world()
+        if world == 1:
+            return False
+        if not isinstance(self.ent_embeds, eng.EmbeddingTable):
+            return par.replicas_in_sync()     # the row-sharded GNN approaches keep every rank's outputs identical themselves
+        import torch.distributed as dist
+        par.assemble_owned_rows(self.ent_embeds.weight, rank, world)
+        for name, tab in vars(self).items():
+            if isinstance(tab, eng.EmbeddingTable) and tab is not self.ent_embeds:
+                dist.all_reduce(tab.weight)
+                tab.weight /= world
+        return True
 
     # ---- evaluation ------------------------------------------------------------------------------------
     def _mapping_array(self):
@@ -130,6 +164,7 @@ class BasicModel:
         return embeds1, embeds2, self._mapping_array()
 
     def valid(self, stop_metric):
+        par.mark_replicas_in_sync(self._sync_replicas())
         embeds1, embeds2, mapping = self._eval_valid_embeddings()
         hits1_12, mrr_12 = valid(embeds1, embeds2, mapping, self.args.top_k,
                                  self.args.test_threads_num, metric=self.args.eval_metric,
@@ -137,6 +172,7 @@ class BasicModel:
         return hits1_12 if stop_metric == 'hits1' else mrr_12
 
     def test(self, save=True):
+        par.mark_replicas_in_sync(self._sync_replicas())
         embeds1, embeds2, mapping = self._eval_test_embeddings()
         rest_12, _, _ = test(embeds1, embeds2, mapping, self.args.top_k, self.args.test_threads_num,
                              metric=self.args.eval_metric, normalize=self.args.eval_norm, csls_k=0, accurate=True)
@@ -203,6 +239,7 @@ class BasicModel:
         self.launch_triple_training_1epo(epoch, triple_steps, steps_tasks, training_batch_queue, neighbors1, neighbors2)
         if self.args.alignment_module == 'mapping':
             self.launch_mapping_training_1epo(epoch, triple_steps)
+        self._sync_seed_rows()
 
     @staticmethod
     def _slice_count(n_triples, batch_kg, step):
@@ -330,9 +367,16 @@ class BasicModel:
     def _load_extra_state(self, extra):
         pass
 
+    def _local_triples_num(self):
+        """Training triples of this process: all of them, or this rank's head-owned shard under torchrun."""
+        if par.world()[1] == 1:
+            return self.kgs.kg1.relation_triples_num + self.kgs.kg2.relation_triples_num
+        kg1, kg2, _ = self._device_kgs()
+        return int(kg1.triples.shape[0] + kg2.triples.shape[0])
+
     def run(self):
         t = time.time()
-        triples_num = self.kgs.kg1.relation_triples_num + self.kgs.kg2.relation_triples_num
+        triples_num = self._local_triples_num()
         triple_steps = int(math.ceil(triples_num / self.args.batch_size))
         steps_tasks = task_divide(list(range(triple_steps)), self.args.batch_threads_num)
         neighbors1, neighbors2 = None, None

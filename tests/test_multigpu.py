@@ -239,3 +239,61 @@ def test_row_sharded_rdgcn_layer_equals_single_gpu():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
+def _bootea_worker(rank, world, port, folder, out):
+    import contextlib
+    import io
+    import re
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from openea_b200 import presets
+        from openea_b200.approaches import BootEA
+        from openea_b200.modules.load.kgs import read_kgs_from_folder
+        args = presets.bootea("15K")
+        args.training_data, args.output = folder, folder + "out%d/" % rank
+        args.batch_size, args.max_epoch, args.start_valid, args.sub_epoch = 1000, 200, 100, 10
+        args.truncated_epsilon, args.dim, args.sim_th = 0.9, 32, 0.5
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            kgs = read_kgs_from_folder(folder, args.dataset_division, "swapping", True)
+            m = BootEA(); m.set_args(args); m.set_kgs(kgs); m.init(); m.run(); m.test(save=False)
+        text = buf.getvalue()
+        h1 = float(re.findall(r"accurate results: hits@\[1, 5, 10, 50\] = \[\s*([0-9.]+)", text)[-1])
+        local = int(m._dkg1.triples.shape[0] + m._dkg2.triples.shape[0])
+        total = torch.tensor([local], device="cuda"); dist.all_reduce(total)
+        assert int(total) == kgs.kg1.relation_triples_num + kgs.kg2.relation_triples_num     # a partition of the triples
+        agree = torch.tensor([h1, -h1], device="cuda"); dist.all_reduce(agree, op=dist.ReduceOp.MAX)
+        assert float(agree[0]) == h1 and float(-agree[1]) == h1, "every rank must print the same (sharded) evaluation"
+        assert h1 > 5.0, h1                                       # chance 0.24 %; one GPU reaches ≈ 10 % at this budget
+        out.put((rank, "ok"))
+    except Exception as e:
+        import traceback
+        out.put((rank, "FAIL: %r\n%s" % (e, traceback.format_exc())))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.first_hw_run
+def test_bootea_lifecycle_on_two_gpus(tmp_path):
+    """SURVEY §8e-i through the reference lifecycle: head-owner triple shards, per-epoch seed-row all-gather, replicas
+    assembled before validation / bootstrapping / test, sharded evaluation — BootEA learns and every rank reports the same
+    result."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import torch.multiprocessing as mp
+    from openea_b200.synth import write_dataset
+    folder = write_dataset(str(tmp_path) + "/tiny/", "tiny")
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_bootea_worker, args=(r, 2, port, folder, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
