@@ -129,6 +129,16 @@ int oea_triple_score_fed(const oea_table* ent, const oea_table* rel,
                          const int32_t* neg_h, const int32_t* neg_r, const int32_t* neg_t, int32_t n_neg,
                          const oea_loss_cfg* loss, double* loss_out, void* stream);
 
+/* oea_triple_score_fed for batches in the reference's layout (batch.py:36-45): the n_neg / n_pos negatives of positive p
+ * sit at p·k … p·k+k−1.  One warp scores a positive and its negatives: rows a negative shares with its positive are
+ * neither reloaded nor reduced separately (3 + k row loads and reductions per positive instead of 3·(1 + k)); a negative
+ * that shares fewer than two rows takes the general path, so every fed batch gives the same result as
+ * oea_triple_score_fed (up to fp32 summation order).  Requires n_pos > 0 and n_neg % n_pos == 0. */
+int oea_triple_score_fed_grouped(const oea_table* ent, const oea_table* rel,
+                                 const int32_t* pos_h, const int32_t* pos_r, const int32_t* pos_t, int32_t n_pos,
+                                 const int32_t* neg_h, const int32_t* neg_r, const int32_t* neg_t, int32_t n_neg,
+                                 const oea_loss_cfg* loss, double* loss_out, void* stream);
+
 /* Optimiser step on a table whose `grad` was filled by a score call.  Replaces
  * optimizer.apply_gradients of modules/base/optimizers.py:4-7.  Adagrad / SGD touch only flagged
  * rows (identical to TF's dense update because untouched rows have g = 0); Adam is dense.

@@ -235,14 +235,17 @@ class TripleTrainer:
         self._loss_pinned = torch.zeros(1, dtype=torch.float64).pin_memory() if dev.type == "cuda" else None
 
     # -- device-index API -------------------------------------------------------------------------
-    def score_fed(self, pos, neg=None, loss_out=None):
+    def score_fed(self, pos, neg=None, loss_out=None, grouped=False):
         """pos/neg: int32 device tensors [3, n] (h | r | t rows).  Accumulates gradients; adds the batch
-        loss into loss_out (device fp64 scalar tensor, default self.loss_dev)."""
+        loss into loss_out (device fp64 scalar tensor, default self.loss_dev).  grouped: the negatives of positive p are
+        columns p·k … p·k+k−1 (the reference's batch layout) → one warp per positive and its negatives
+        (oea_triple_score_fed_grouped; same result)."""
         out = self.loss_dev if loss_out is None else loss_out
         n_pos = pos.shape[1]
         n_neg = 0 if neg is None else neg.shape[1]
         np_ = lambda t, i: C.c_void_p(0 if t is None or t.shape[1] == 0 else t[i].data_ptr())
-        L.check(self.lib.oea_triple_score_fed(
+        fn = self.lib.oea_triple_score_fed_grouped if grouped else self.lib.oea_triple_score_fed
+        L.check(fn(
             C.byref(self.ent.c_struct()), C.byref(self.rel.c_struct()),
             np_(pos, 0), np_(pos, 1), np_(pos, 2), n_pos, np_(neg, 0), np_(neg, 1), np_(neg, 2), n_neg,
             C.byref(self.loss), _ptr(out), _stream_ptr()), "oea_triple_score_fed")

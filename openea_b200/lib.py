@@ -86,6 +86,7 @@ SIGNATURES = {
     "oea_abi_version": (C.c_int, []),
     "oea_error_string": (C.c_char_p, [C.c_int]),
     "oea_triple_score_fed": (C.c_int, [_TP, _TP, _P, _P, _P, _I, _P, _P, _P, _I, C.POINTER(LossCfg), _P, _P]),
+    "oea_triple_score_fed_grouped": (C.c_int, [_TP, _TP, _P, _P, _P, _I, _P, _P, _P, _I, C.POINTER(LossCfg), _P, _P]),
     "oea_rowopt_apply": (C.c_int, [_TP, C.POINTER(OptCfg), _P]),
     "oea_rowopt_apply_pair": (C.c_int, [_TP, _TP, C.POINTER(OptCfg), _P]),
     "oea_rowopt_adadelta": (C.c_int, [_TP, C.POINTER(OptCfg), _P]),

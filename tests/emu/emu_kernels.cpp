@@ -5,3 +5,4 @@
 #include "../../openea_b200/csrc/oea_triple_ext.cu"
 #include "../../openea_b200/csrc/oea_sampler.cu"
 #include "../../openea_b200/csrc/oea_optim_ext.cu"
+#include "../../openea_b200/csrc/oea_triple_grouped.cu"

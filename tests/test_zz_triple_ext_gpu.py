@@ -394,3 +394,41 @@ def test_pipelined_host_step_equals_the_synchronous_one(cuda_device):
     for x, y in ((a.ent, b.ent), (a.rel, b.rel)):
         np.testing.assert_allclose(y.raw().cpu().numpy(), x.raw().cpu().numpy(), rtol=1e-4, atol=1e-6)
         assert not y.grad.any().item() and not y.touched.any().item()
+
+
+@pytest.mark.first_hw_run
+@pytest.mark.parametrize("loss,k", [("limited", 10), ("logistic", 4), ("margin-based", 1), ("positive", 0)])
+@pytest.mark.parametrize("d", [75, 100, 300])
+def test_grouped_fed_scorer_equals_the_per_triple_scorer(cuda_device, monkeypatch, loss, k, d):
+    """oea_triple_score_fed_grouped (one warp per positive and its negatives) against oea_triple_score_fed on a batch in the
+    reference's layout with some unrelated negatives mixed in; then the host-index step with OEA_FED_GROUPED=1 against
+    the default."""
+    eng = _engine()
+    from tests.helpers import make_tables
+    rng = np.random.default_rng(5 * d + k)
+    n_ent, n_rel, n_pos = 3000, 31, 700
+    ent, rel = make_tables(rng, n_ent, n_rel, d)
+    pos, neg = make_batch(rng, n_ent, n_rel, n_pos, k)
+    if k:
+        swap = rng.random(n_pos * k) < 0.1
+        neg[:, swap] = np.stack([rng.integers(0, n_ent, swap.sum()), rng.integers(0, n_rel, swap.sum()),
+                                 rng.integers(0, n_ent, swap.sum())]).astype(np.int32)
+    kw = dict(margin=1.1 if loss == "margin-based" else 0.3, neg_margin=2.2, balance=0.2)
+    cfg = eng.loss_cfg(loss, "L2", **kw)
+    res = []
+    for grouped in (False, True):
+        te, tr = eng.EmbeddingTable(ent, True), eng.EmbeddingTable(rel, True)
+        t = eng.TripleTrainer(te, tr, cfg, 0.01)
+        t.score_fed(_dev(pos), _dev(neg), grouped=grouped)
+        res.append((t.read_loss(), te.grad.cpu().numpy(), tr.grad.cpu().numpy(), te.touched.cpu().numpy()))
+    assert res[1][0] == pytest.approx(res[0][0], rel=1e-5)
+    for i in (1, 2):
+        _assert_rows_close(res[1][i], res[0][i], "gradient, grouped vs per-triple")
+    assert np.array_equal(res[1][3] != 0, res[0][3] != 0)
+    losses = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("OEA_FED_GROUPED", flag)
+        t = eng.TripleTrainer(eng.EmbeddingTable(ent, True), eng.EmbeddingTable(rel, True), cfg, 0.01)
+        losses.append([t.step_fed_host(pos, neg) for _ in range(2)] + [t.ent.raw().cpu().numpy()])
+    assert losses[1][0] == pytest.approx(losses[0][0], rel=1e-5) and losses[1][1] == pytest.approx(losses[0][1], rel=1e-4)
+    _assert_rows_close(losses[1][2], losses[0][2], "entity table after two host-index steps")
