@@ -157,3 +157,34 @@ def test_emulator_collectives_behave_like_cuda():
     lib.emu_selftest.restype = C.c_int
     for _ in range(3):                       # thread interleavings differ from run to run
         assert lib.emu_selftest() == 0
+
+
+@pytest.mark.parametrize("model", ["TransH", "TransD", "DistMult", "SimplE"])
+def test_emulated_scorer_properties_additivity_permutation_scale(emu, model):
+    """Properties that need no oracle (the ones the GPU tests use at full size): scoring a batch in two halves adds up to
+    scoring it at once; permuting the batch changes nothing; loss_scale scales loss and gradients linearly."""
+    rng, slots, tabs, norms = _case(model, 77, 30, 5, 20, True)
+    pos, neg = make_batch(rng, 30, 5, 16, 2)
+    loss = "logistic" if model in ("DistMult", "SimplE") else "limited"
+    kw = dict(margin=0.3, neg_margin=2.2, balance=0.2)
+
+    def run(p, n, scale=1.0, into=None):
+        tables = into or {s: HostTable(tabs[s], norms[s]) for s in slots if s is not None}
+        rc, val = _run(emu, model, slots, tables, p, n, loss, "L2", scale, **kw)
+        assert rc == 0
+        return val, tables
+    whole, t_whole = run(pos, neg)
+    first, t_split = run(pos[:, :8], neg[:, :16])
+    second, _ = run(pos[:, 8:], neg[:, 16:], into=t_split)                       # gradients accumulate in the tables
+    assert first + second == pytest.approx(whole, rel=1e-5)
+    perm_p, perm_n = rng.permutation(16), rng.permutation(32)
+    shuffled, t_perm = run(pos[:, perm_p], neg[:, perm_n])
+    assert shuffled == pytest.approx(whole, rel=1e-5)
+    doubled, t_double = run(pos, neg, scale=2.0)
+    assert doubled == pytest.approx(2 * whole, rel=1e-5)
+    for s in t_whole:
+        ref = t_whole[s].grad
+        tol = dict(rtol=1e-4, atol=1e-5 * max(1e-6, np.abs(ref).max()))
+        np.testing.assert_allclose(t_split[s].grad, ref, **tol)
+        np.testing.assert_allclose(t_perm[s].grad, ref, **tol)
+        np.testing.assert_allclose(t_double[s].grad, 2 * ref, **tol)

@@ -432,3 +432,55 @@ def test_grouped_fed_scorer_equals_the_per_triple_scorer(cuda_device, monkeypatc
         losses.append([t.step_fed_host(pos, neg) for _ in range(2)] + [t.ent.raw().cpu().numpy()])
     assert losses[1][0] == pytest.approx(losses[0][0], rel=1e-5) and losses[1][1] == pytest.approx(losses[0][1], rel=1e-4)
     _assert_rows_close(losses[1][2], losses[0][2], "entity table after two host-index steps")
+
+
+@pytest.mark.first_hw_run
+@pytest.mark.parametrize("shape,n_ent,n_rel,B,k", [("15K", 30000, 450, 5000, 10), ("100K", 200000, 600, 20000, 10)])
+def test_full_size_properties_of_the_fed_scorers(cuda_device, shape, n_ent, n_rel, B, k):
+    """At BASELINE.json's batch shapes, where the oracle is too slow: size-independent properties of the fed scorers
+    (per-triple, grouped, and the TransH instance of the score family) — two half batches add up to the whole batch,
+    a permutation of the batch changes nothing, and grouped == per-triple."""
+    eng = _engine()
+    rng = np.random.default_rng(12)
+    d = 100
+    ent = (rng.standard_normal((n_ent, d)) / 10).astype(np.float32)
+    rel = (rng.standard_normal((n_rel, d)) / 10).astype(np.float32)
+    nrm = (rng.standard_normal((n_rel, d)) / 10).astype(np.float32)
+    pos = np.stack([rng.integers(0, n_ent, B), rng.integers(0, n_rel, B), rng.integers(0, n_ent, B)]).astype(np.int32)
+    neg = np.repeat(pos, k, axis=1)
+    side = rng.random(B * k) < 0.5
+    neg[0, side] = rng.integers(0, n_ent, side.sum())
+    neg[2, ~side] = rng.integers(0, n_ent, (~side).sum())
+    cfg = eng.loss_cfg("limited", "L2", 0.3, 2.2, 0.2)
+
+    def triple(grouped=False, batches=((slice(None), slice(None)),)):
+        te, tr = eng.EmbeddingTable(ent, True), eng.EmbeddingTable(rel, True)
+        t = eng.TripleTrainer(te, tr, cfg, 0.01)
+        for ps, ns in batches:
+            t.score_fed(_dev(pos[:, ps]), _dev(neg[:, ns]), grouped=grouped)
+        return t.read_loss(), te.grad.clone(), tr.grad.clone()
+
+    def close(a, b):
+        assert a[0] == pytest.approx(b[0], rel=1e-5)
+        for x, y in zip(a[1:], b[1:]):
+            scale = float(y.abs().max())
+            assert float((x - y).abs().max()) <= 2e-4 * scale
+    whole = triple()
+    half = B // 2
+    close(triple(batches=((slice(0, half), slice(0, half * k)), (slice(half, B), slice(half * k, B * k)))), whole)
+    close(triple(grouped=True), whole)
+    perm = rng.permutation(B)
+    pos_p, neg_p = pos[:, perm], neg.reshape(3, B, k)[:, perm].reshape(3, B * k)
+    te, tr = eng.EmbeddingTable(ent, True), eng.EmbeddingTable(rel, True)
+    t = eng.TripleTrainer(te, tr, cfg, 0.01)
+    t.score_fed(_dev(pos_p), _dev(neg_p), grouped=True)
+    close((t.read_loss(), te.grad, tr.grad), whole)
+    # the TransH instance of the score family at the same size: additivity
+    def transh(batches):
+        tabs = (eng.EmbeddingTable(ent, True), eng.EmbeddingTable(rel, True), None, eng.EmbeddingTable(nrm, True))
+        m = eng.ModelTrainer("TransH", tabs, cfg, 0.01)
+        for ps, ns in batches:
+            m.score_fed(_dev(pos[:, ps]), _dev(neg[:, ns]))
+        return m.read_loss(), tabs[0].grad.clone(), tabs[1].grad.clone(), tabs[3].grad.clone()
+    close(transh(((slice(0, half), slice(0, half * k)), (slice(half, B), slice(half * k, B * k)))),
+          transh(((slice(None), slice(None)),)))
