@@ -13,6 +13,15 @@
         if (_e != cudaSuccess) return -(int)_e;              \
     } while (0)
 
+// OEA_LAUNCH(kernel, grid, block, dynamic smem bytes, stream, args…): `kernel<<<grid, block, smem, stream>>>(args…)`,
+// or — under tests/emu — the same kernel function run block by block on the CPU warp emulator (whole grid: not every
+// kernel is grid-stride).  A template-id with commas must be bound to a local `auto kernel = …` first.
+#ifdef OEA_HOST_EMU
+#define OEA_LAUNCH(KERNEL, GRID, BLOCK, SMEM, STREAM, ...) emu::launch((int)(GRID), (int)(BLOCK), [&] { KERNEL(__VA_ARGS__); })
+#else
+#define OEA_LAUNCH(KERNEL, GRID, BLOCK, SMEM, STREAM, ...) KERNEL<<<(GRID), (BLOCK), (SMEM), (STREAM)>>>(__VA_ARGS__)
+#endif
+
 #ifdef OEA_HOST_EMU   // tests/emu: the kernels run on the CPU's warp emulator; there is no launch to check
 #define OEA_LAUNCH_CHECK() do { } while (0)
 #else

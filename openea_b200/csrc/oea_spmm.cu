@@ -119,7 +119,11 @@ __global__ void __launch_bounds__(SPMM_THREADS)
 k_spmm_segments(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ val,
                 const int32_t* __restrict__ long_rows, const int32_t* __restrict__ seg_row, const int32_t* __restrict__ seg_start,
                 int n_seg, const float* __restrict__ X, int ldx, float* __restrict__ partial, int ldp, int d4) {
+#ifdef OEA_HOST_EMU
+    static float red[SPMM_WARPS * 4 * 32 * 4];     // tests/emu: the dynamic buffer as a static one of the largest size
+#else
     extern __shared__ __align__(16) float red[];   // [SPMM_WARPS][VEC*32] float4
+#endif
     float4* red4 = reinterpret_cast<float4*>(red);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int sgi = blockIdx.x; sgi < n_seg; sgi += gridDim.x) {
@@ -259,11 +263,11 @@ extern "C" int oea_spmm_csr(const oea_csr* A, const oea_spmm_hubs* hubs,
     float* partial = (float*)workspace;
 #define OEA_SPMM(V)                                                                                                          \
     do {                                                                                                                     \
-        k_spmm_warp_rows<V><<<grid, SPMM_THREADS, 0, st>>>(A->rowptr, A->col, A->val, A->n_rows, X, ldx, Y, ldy, d4, epi);   \
+        OEA_LAUNCH(k_spmm_warp_rows<V>, grid, SPMM_THREADS, 0, st, A->rowptr, A->col, A->val, A->n_rows, X, ldx, Y, ldy, d4, epi); \
         if (n_long > 0) {                                                                                                    \
-            k_spmm_segments<V><<<n_seg, SPMM_THREADS, SPMM_WARPS * V * 32 * sizeof(float4), st>>>(                           \
+            OEA_LAUNCH(k_spmm_segments<V>, n_seg, SPMM_THREADS, SPMM_WARPS * V * 32 * sizeof(float4), st,                    \
                 A->rowptr, A->col, A->val, hubs->long_rows, hubs->seg_row, hubs->seg_start, n_seg, X, ldx, partial, d, d4);  \
-            k_spmm_finalize<V><<<(n_long + SPMM_WARPS - 1) / SPMM_WARPS, SPMM_THREADS, 0, st>>>(                             \
+            OEA_LAUNCH(k_spmm_finalize<V>, (n_long + SPMM_WARPS - 1) / SPMM_WARPS, SPMM_THREADS, 0, st,                      \
                 hubs->long_rows, hubs->seg_ptr, n_long, partial, d, Y, ldy, d4, epi);                                        \
         }                                                                                                                    \
     } while (0)
@@ -285,8 +289,8 @@ extern "C" int oea_align_loss_l1(const float* x, int32_t ld, int32_t dim, const 
     if (t <= 0 || k <= 0 || dim <= 0 || ld < dim) return OEA_ERR_SHAPE;
     const float scale = 1.0f / (2.0f * (float)k * (float)t);
     const int blocks = (t + 7) / 8;
-    k_align_loss_l1<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, ld, dim, left, right, t, k, neg_left, neg_right, neg2_left,
-                                                              neg2_right, gamma, scale, loss_out, grad);
+    OEA_LAUNCH(k_align_loss_l1, blocks, 256, 0, (cudaStream_t)stream, x, ld, dim, left, right, t, k, neg_left, neg_right,
+               neg2_left, neg2_right, gamma, scale, loss_out, grad);
     OEA_LAUNCH_CHECK();
     return OEA_OK;
 }
@@ -390,7 +394,7 @@ extern "C" int oea_edge_softmax_fwd(const oea_csr* A, const float* s1, const flo
     if ((s1 == nullptr) != (s2 == nullptr)) return OEA_ERR_NULL;     // both (node mode) or neither (edge-logit mode)
     if (A->nnz > 0 && (!A->col || !A->val)) return OEA_ERR_NULL;
     if (A->n_rows <= 0) return OEA_ERR_DIM;
-    k_edge_softmax_fwd<<<(A->n_rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(A->rowptr, A->col, A->val, A->n_rows, s1, s2, slope, alpha);
+    OEA_LAUNCH(k_edge_softmax_fwd, (A->n_rows + 7) / 8, 256, 0, (cudaStream_t)stream, A->rowptr, A->col, A->val, A->n_rows, s1, s2, slope, alpha);
     OEA_LAUNCH_CHECK();
     return OEA_OK;
 }
@@ -399,7 +403,7 @@ extern "C" int oea_sddmm(const oea_csr* A, const float* G, int32_t ldg_, const f
     if (!A || !A->rowptr || !G || !M || !out) return OEA_ERR_NULL;
     if (A->n_rows <= 0 || d <= 0 || (d & 3) || ldg_ < d || ldm < d || (ldg_ & 3) || (ldm & 3)) return OEA_ERR_DIM;
     if (!aligned16(G) || !aligned16(M)) return OEA_ERR_ALIGN;
-    k_sddmm<<<(A->n_rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(A->rowptr, A->col, A->n_rows, G, ldg_, M, ldm, d >> 2, out);
+    OEA_LAUNCH(k_sddmm, (A->n_rows + 7) / 8, 256, 0, (cudaStream_t)stream, A->rowptr, A->col, A->n_rows, G, ldg_, M, ldm, d >> 2, out);
     OEA_LAUNCH_CHECK();
     return OEA_OK;
 }
@@ -409,8 +413,8 @@ extern "C" int oea_edge_softmax_bwd(const oea_csr* A, const float* s1, const flo
     if (!A || !A->rowptr || !alpha || !dalpha || !ds1) return OEA_ERR_NULL;
     if ((s1 == nullptr) != (s2 == nullptr) || (s1 != nullptr && !ds2)) return OEA_ERR_NULL;
     if (A->n_rows <= 0) return OEA_ERR_DIM;
-    k_edge_softmax_bwd<<<(A->n_rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(A->rowptr, A->col, A->val, A->n_rows, s1, s2, slope,
-                                                                             alpha, dalpha, ds1, ds2);
+    OEA_LAUNCH(k_edge_softmax_bwd, (A->n_rows + 7) / 8, 256, 0, (cudaStream_t)stream, A->rowptr, A->col, A->val, A->n_rows, s1, s2,
+               slope, alpha, dalpha, ds1, ds2);
     OEA_LAUNCH_CHECK();
     return OEA_OK;
 }

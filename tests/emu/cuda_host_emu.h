@@ -14,6 +14,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <string.h>
+#include <algorithm>
 #include <atomic>
 #include <map>
 #include <mutex>
@@ -136,6 +137,14 @@ inline void __syncthreads() {}
 template <typename T>
 inline T __ldg(const T* p) { return *p; }
 inline double atomicAdd(double* p, double v) { const double old = *p; *p = old + v; return old; }
+inline float atomicAdd(float* p, float v) {          // lanes of one warp may hit the same word (scatter-adds): really atomic
+    std::atomic_ref<float> a(*p);
+    float old = a.load(std::memory_order_relaxed);
+    while (!a.compare_exchange_weak(old, old + v, std::memory_order_relaxed)) {}
+    return old;
+}
+using std::min;
+using std::max;
 inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((uint64_t)a * (uint64_t)b) >> 32); }
 inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 inline float emu_expf(float x) { return expf(x); }

@@ -74,6 +74,68 @@ class TorchOps:
         loss_out += loss.detach().double()
 
 
+class EmuOps(TorchOps):
+    """The unit's sparse products and its loss through the REAL kernel sources (oea_spmm.cu on the CPU warp emulator):
+    the sharded row blocks, padded rows, position-mapped indices and the relu-mask epilogue reach the same code a GPU
+    runs.  Table lookups / updates stay the torch stand-ins (their kernels live in a file the emulator does not cover)."""
+
+    def __init__(self):
+        import ctypes as C
+        from openea_b200 import lib as L
+        from tests.emu import build_emu
+        from tests.test_emu_spmm import HostCsr
+        self.C, self.L, self.HostCsr = C, L, HostCsr
+        self.lib = C.CDLL(build_emu.build())
+        for name in ("oea_spmm_csr", "oea_spmm_workspace_bytes", "oea_spmm_long_row_threshold", "oea_spmm_segment_nnz",
+                     "oea_align_loss_l1"):
+            fn = getattr(self.lib, name)
+            fn.restype, fn.argtypes = L.SIGNATURES[name]
+
+    def csr(self, mat, device, keep_duplicates=False):
+        ops = self
+
+        class Wrapped(ops.HostCsr):
+            def transpose(self):
+                return Wrapped(ops.lib, self.m.T)
+        return Wrapped(self.lib, mat)
+
+    @staticmethod
+    def _padded(x):
+        """[n, d] → contiguous float32 [n, ceil4(d)] NumPy buffer (the kernels want 16-byte rows)."""
+        a = x.detach().numpy().astype(np.float32)
+        p = (a.shape[1] + 3) // 4 * 4
+        out = np.zeros((a.shape[0], p), dtype=np.float32)
+        out[:, :a.shape[1]] = a
+        return out
+
+    def spmm(self, A, X, relu=False, mask_src=None):
+        C = self.C
+        x = self._padded(X)
+        d = x.shape[1]
+        y = np.zeros((A.m.shape[0], d), dtype=np.float32)
+        m = None if mask_src is None else self._padded(mask_src)
+        nbytes = self.lib.oea_spmm_workspace_bytes(A.n_seg, d)
+        ws = np.zeros(max(4, nbytes // 4), dtype=np.float32)
+        cs, hb = A.csr(), A.hubs()
+        rc = self.lib.oea_spmm_csr(C.byref(cs), C.byref(hb), x.ctypes.data, d, y.ctypes.data, d, d, int(relu),
+                                   None if m is None else m.ctypes.data, 0.0, ws.ctypes.data, nbytes, None)
+        assert rc == 0, rc
+        return torch.from_numpy(y[:, :X.shape[1]].copy())
+
+    def align_loss(self, x, dim, left, right, k, negs, gamma, grad, loss_out):
+        xp = self._padded(x)
+        g = np.zeros_like(xp)
+        loss = np.zeros(1, dtype=np.float64)
+        i32 = lambda t: np.ascontiguousarray(t.numpy(), dtype=np.int32)
+        arrs = [i32(left), i32(right)] + [i32(n) for n in negs]
+        rc = self.lib.oea_align_loss_l1(xp.ctypes.data, xp.shape[1], dim, arrs[0].ctypes.data, arrs[1].ctypes.data, len(arrs[0]),
+                                        k, arrs[2].ctypes.data, arrs[3].ctypes.data, arrs[4].ctypes.data, arrs[5].ctypes.data,
+                                        gamma, loss.ctypes.data, g.ctypes.data, None)
+        assert rc == 0, rc
+        grad += torch.from_numpy(g[:, :x.shape[1]])
+        loss_out += float(loss[0])
+
+
 def _problem(with_features):
     rng = np.random.default_rng(4)
     n, d, t, k = 53, 8, 11, 3                      # 53 rows: ragged last block for world 2 and 3
@@ -90,7 +152,7 @@ def _problem(with_features):
     return support, feats, W0, ill, negs, k
 
 
-def _worker(rank, world, port, with_features, out):
+def _worker(rank, world, port, with_features, out, ops_kind="torch"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -102,7 +164,8 @@ def _worker(rank, world, port, with_features, out):
         shard = pg.RowShard(support.shape[0])
         assert (shard.rank, shard.world) == (rank, world) and shard.n_pad == shard.block * world >= shard.n
         table = _Table(W0 if with_features else shard.local_rows(W0))
-        unit = pg.ShardedGCNAlignUnit(support, table, feats, ill, gamma, k, lr, shard=shard, ops=TorchOps())
+        ops = EmuOps() if ops_kind == "kernels" else TorchOps()
+        unit = pg.ShardedGCNAlignUnit(support, table, feats, ill, gamma, k, lr, shard=shard, ops=ops)
         tn = [torch.as_tensor(x, dtype=torch.int32) for x in negs]
         want_W = W0
         for _ in range(2):
@@ -124,16 +187,21 @@ def _worker(rank, world, port, with_features, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("world,ops_kind", [(2, "torch"), (3, "torch"), (2, "kernels")])
 @pytest.mark.parametrize("with_features", [False, True])
-def test_sharded_gcn_unit_equals_single_process_oracle(world, with_features):
+def test_sharded_gcn_unit_equals_single_process_oracle(world, with_features, ops_kind):
+    """ops_kind 'kernels': the SpMMs and the alignment loss run the product's kernel sources on the CPU warp emulator."""
+    if ops_kind == "kernels":
+        from tests.emu import build_emu
+        if build_emu.build() is None:
+            pytest.skip("no CUDA headers for the emulator build")
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, with_features, out)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, with_features, out, ops_kind)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [out.get(timeout=180) for _ in procs]
+    res = [out.get(timeout=400) for _ in procs]
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(r, "ok") for r in range(world)], res
