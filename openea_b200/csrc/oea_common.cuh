@@ -22,6 +22,15 @@
 #define OEA_LAUNCH(KERNEL, GRID, BLOCK, SMEM, STREAM, ...) KERNEL<<<(GRID), (BLOCK), (SMEM), (STREAM)>>>(__VA_ARGS__)
 #endif
 
+// The dynamically sized shared-memory array of a kernel (under tests/emu: a static one of the largest size used).
+#ifdef OEA_HOST_EMU
+#define OEA_DYNAMIC_SMEM(NAME) static float NAME[16384]
+#define OEA_DYNAMIC_SMEM_ALIGNED16(NAME) alignas(16) static float NAME[16384]
+#else
+#define OEA_DYNAMIC_SMEM(NAME) extern __shared__ float NAME[]
+#define OEA_DYNAMIC_SMEM_ALIGNED16(NAME) extern __shared__ __align__(16) float NAME[]
+#endif
+
 #ifdef OEA_HOST_EMU   // tests/emu: the kernels run on the CPU's warp emulator; there is no launch to check
 #define OEA_LAUNCH_CHECK() do { } while (0)
 #else

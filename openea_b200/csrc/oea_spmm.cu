@@ -119,11 +119,7 @@ __global__ void __launch_bounds__(SPMM_THREADS)
 k_spmm_segments(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ val,
                 const int32_t* __restrict__ long_rows, const int32_t* __restrict__ seg_row, const int32_t* __restrict__ seg_start,
                 int n_seg, const float* __restrict__ X, int ldx, float* __restrict__ partial, int ldp, int d4) {
-#ifdef OEA_HOST_EMU
-    static float red[SPMM_WARPS * 4 * 32 * 4];     // tests/emu: the dynamic buffer as a static one of the largest size
-#else
-    extern __shared__ __align__(16) float red[];   // [SPMM_WARPS][VEC*32] float4
-#endif
+    OEA_DYNAMIC_SMEM_ALIGNED16(red);               // [SPMM_WARPS][VEC*32] float4
     float4* red4 = reinterpret_cast<float4*>(red);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int sgi = blockIdx.x; sgi < n_seg; sgi += gridDim.x) {

@@ -748,16 +748,16 @@ extern "C" int oea_triple_score_fed(const oea_table* ent, const oea_table* rel,
     if (loss->loss_kind == OEA_LOSS_MARGIN) {
         const int grid = grid_for(n_pos);
 #define CALL(V)                                                                                                         \
-        if (l1) k_score_margin<OEA_SCORE_L1, V><<<grid, kThreads, 0, st>>>(e, r, pos_h, pos_r, pos_t, neg_h, neg_r, neg_t, n_pos, *loss, loss_out); \
-        else k_score_margin<OEA_SCORE_L2SQ, V><<<grid, kThreads, 0, st>>>(e, r, pos_h, pos_r, pos_t, neg_h, neg_r, neg_t, n_pos, *loss, loss_out)
+        if (l1) OEA_LAUNCH((k_score_margin<OEA_SCORE_L1, V>), grid, kThreads, 0, st, e, r, pos_h, pos_r, pos_t, neg_h, neg_r, neg_t, n_pos, *loss, loss_out); \
+        else OEA_LAUNCH((k_score_margin<OEA_SCORE_L2SQ, V>), grid, kThreads, 0, st, e, r, pos_h, pos_r, pos_t, neg_h, neg_r, neg_t, n_pos, *loss, loss_out)
         OEA_DISPATCH_VEC(ent->pitch, CALL);
 #undef CALL
     } else {
 #define CALL(V)                                                                                                         \
         if (l1) { const int grid = grid_one_wave(k_score_fed<OEA_SCORE_L1, V>, n_pos + n_neg);                              \
-                  k_score_fed<OEA_SCORE_L1, V><<<grid, kThreads, 0, st>>>(e, r, pos_h, pos_r, pos_t, n_pos, neg_h, neg_r, neg_t, n_neg, *loss, loss_out); } \
+                  OEA_LAUNCH((k_score_fed<OEA_SCORE_L1, V>), grid, kThreads, 0, st, e, r, pos_h, pos_r, pos_t, n_pos, neg_h, neg_r, neg_t, n_neg, *loss, loss_out); } \
         else { const int grid = grid_one_wave(k_score_fed<OEA_SCORE_L2SQ, V>, n_pos + n_neg);                               \
-               k_score_fed<OEA_SCORE_L2SQ, V><<<grid, kThreads, 0, st>>>(e, r, pos_h, pos_r, pos_t, n_pos, neg_h, neg_r, neg_t, n_neg, *loss, loss_out); }
+               OEA_LAUNCH((k_score_fed<OEA_SCORE_L2SQ, V>), grid, kThreads, 0, st, e, r, pos_h, pos_r, pos_t, n_pos, neg_h, neg_r, neg_t, n_neg, *loss, loss_out); }
         OEA_DISPATCH_VEC(ent->pitch, CALL);
 #undef CALL
     }
@@ -773,10 +773,10 @@ extern "C" int oea_rowopt_apply(const oea_table* t, const oea_opt_cfg* opt, void
     switch (opt->kind) {
         case OEA_OPT_ADAGRAD:
             if (!t->state1) return OEA_ERR_NULL;
-            k_rowopt<OEA_OPT_ADAGRAD><<<grid, kThreads, 0, st>>>(t->weight, t->grad, t->state1, nullptr, t->touched, t->rows, t->pitch, opt->lr, 0.f, 0.f, 0.f, 0.f);
+            OEA_LAUNCH(k_rowopt<OEA_OPT_ADAGRAD>, grid, kThreads, 0, st, t->weight, t->grad, t->state1, nullptr, t->touched, t->rows, t->pitch, opt->lr, 0.f, 0.f, 0.f, 0.f);
             break;
         case OEA_OPT_SGD:
-            k_rowopt<OEA_OPT_SGD><<<grid, kThreads, 0, st>>>(t->weight, t->grad, nullptr, nullptr, t->touched, t->rows, t->pitch, opt->lr, 0.f, 0.f, 0.f, 0.f);
+            OEA_LAUNCH(k_rowopt<OEA_OPT_SGD>, grid, kThreads, 0, st, t->weight, t->grad, nullptr, nullptr, t->touched, t->rows, t->pitch, opt->lr, 0.f, 0.f, 0.f, 0.f);
             break;
         case OEA_OPT_ADADELTA:
             return oea_rowopt_adadelta(t, opt, stream);   // oea_optim_ext.cu
@@ -786,7 +786,7 @@ extern "C" int oea_rowopt_apply(const oea_table* t, const oea_opt_cfg* opt, void
             const double b1t = 1.0 - pow((double)opt->beta1, (double)opt->t);
             const double b2t = 1.0 - pow((double)opt->beta2, (double)opt->t);
             const float lr_t = (float)((double)opt->lr * sqrt(b2t) / b1t);
-            k_rowopt<OEA_OPT_ADAM><<<grid, kThreads, 0, st>>>(t->weight, t->grad, t->state1, t->state2, t->touched, t->rows, t->pitch, opt->lr, opt->beta1, opt->beta2, opt->eps, lr_t);
+            OEA_LAUNCH(k_rowopt<OEA_OPT_ADAM>, grid, kThreads, 0, st, t->weight, t->grad, t->state1, t->state2, t->touched, t->rows, t->pitch, opt->lr, opt->beta1, opt->beta2, opt->eps, lr_t);
             break;
         }
         default:
@@ -840,13 +840,13 @@ extern "C" int oea_triple_score_sampled(const oea_table* ent, const oea_table* r
     const bool l1 = loss->score_kind == OEA_SCORE_L1;
     if (!l1 && ent->pitch <= 128 && !oea_force_v1()) {
         const int grid = grid_one_wave(k_score_sampled_oct, n_pos, kOctWarps);
-        k_score_sampled_oct<<<grid, kOctThreads, 0, st>>>(e, r, P, *loss, loss_out, dbg_neg);
+        OEA_LAUNCH(k_score_sampled_oct, grid, kOctThreads, 0, st, e, r, P, *loss, loss_out, dbg_neg);
     } else {
 #define CALL(V)                                                                                              \
     if (l1) { const int grid = grid_one_wave(k_score_sampled<OEA_SCORE_L1, V>, n_pos);                       \
-              k_score_sampled<OEA_SCORE_L1, V><<<grid, kThreads, 0, st>>>(e, r, P, *loss, loss_out, dbg_neg); } \
+              OEA_LAUNCH((k_score_sampled<OEA_SCORE_L1, V>), grid, kThreads, 0, st, e, r, P, *loss, loss_out, dbg_neg); } \
     else { const int grid = grid_one_wave(k_score_sampled<OEA_SCORE_L2SQ, V>, n_pos);                        \
-           k_score_sampled<OEA_SCORE_L2SQ, V><<<grid, kThreads, 0, st>>>(e, r, P, *loss, loss_out, dbg_neg); }
+           OEA_LAUNCH((k_score_sampled<OEA_SCORE_L2SQ, V>), grid, kThreads, 0, st, e, r, P, *loss, loss_out, dbg_neg); }
         OEA_DISPATCH_VEC(ent->pitch, CALL);
 #undef CALL
     }
@@ -894,7 +894,7 @@ extern "C" int oea_table_lookup(const oea_table* t, const int32_t* ids, int32_t 
     if (out == nullptr) return OEA_ERR_NULL;
     if (n < 0 || out_pitch < t->dim) return OEA_ERR_SHAPE;
     if (n == 0) return OEA_OK;
-    k_lookup<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(t->weight, t->pitch, t->dim, t->l2_norm != 0, ids, n, out, out_pitch);
+    OEA_LAUNCH(k_lookup, grid_for(n), kThreads, 0, (cudaStream_t)stream, t->weight, t->pitch, t->dim, t->l2_norm != 0, ids, n, out, out_pitch);
     OEA_LAUNCH_CHECK();
     return OEA_OK;
 }
@@ -923,7 +923,7 @@ extern "C" int oea_tripleset_build(const int32_t* triples, int32_t n, uint64_t* 
     cudaStream_t st = (cudaStream_t)stream;
     OEA_CUDA_TRY(cudaMemsetAsync(slots, 0xFF, (size_t)capacity * sizeof(uint64_t), st));
     if (n == 0) return OEA_OK;
-    k_tripleset_build<<<(n + 255) / 256, 256, 0, st>>>(triples, n, (unsigned long long*)slots, capacity, ent_bits, rel_bits);
+    OEA_LAUNCH(k_tripleset_build, (n + 255) / 256, 256, 0, st, triples, n, (unsigned long long*)slots, capacity, ent_bits, rel_bits);
     OEA_LAUNCH_CHECK();
     return OEA_OK;
 }
@@ -1011,7 +1011,7 @@ __global__ void __launch_bounds__(256)
 k_mapping_pairs(const float* __restrict__ e1, const float* __restrict__ e2, int n, int dim, int pitch,
                 const float* __restrict__ M, int mpitch, float alpha, double* __restrict__ loss_out,
                 float* __restrict__ g1, float* __restrict__ g2, float* __restrict__ gM) {
-    extern __shared__ float sm[];
+    OEA_DYNAMIC_SMEM(sm);
     float* a = sm;                       // [MAP_PAIRS][dim]  e1 rows
     float* r = sm + MAP_PAIRS * dim;     // [MAP_PAIRS][dim]  residuals
     __shared__ double s_part[8];
@@ -1091,7 +1091,7 @@ extern "C" int oea_table_scatter_grad(const oea_table* t, const int32_t* ids, in
     if (n < 0 || grad_pitch < t->dim) return OEA_ERR_SHAPE;
     if (n == 0) return OEA_OK;
     if (!ids || !grad_rows) return OEA_ERR_NULL;
-    k_table_scatter<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(t->weight, t->grad, t->touched, t->pitch, t->dim,
+    OEA_LAUNCH(k_table_scatter, grid_for(n), kThreads, 0, (cudaStream_t)stream, t->weight, t->grad, t->touched, t->pitch, t->dim,
                                                                         t->l2_norm != 0, ids, n, grad_rows, grad_pitch);
     OEA_LAUNCH_CHECK();
     return OEA_OK;
@@ -1112,9 +1112,9 @@ extern "C" int oea_loss_rows(const float* ph, const float* pr, const float* pt, 
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = grid_for(n_pos + n_neg);
     if (loss->score_kind == OEA_SCORE_L1)
-        k_loss_rows<OEA_SCORE_L1><<<grid, kThreads, 0, st>>>(ph, pr, pt, n_pos, nh, nr, nt, n_neg, dim, pitch, *loss, loss_out, g_ph, g_pr, g_pt, g_nh, g_nr, g_nt);
+        OEA_LAUNCH(k_loss_rows<OEA_SCORE_L1>, grid, kThreads, 0, st, ph, pr, pt, n_pos, nh, nr, nt, n_neg, dim, pitch, *loss, loss_out, g_ph, g_pr, g_pt, g_nh, g_nr, g_nt);
     else if (loss->score_kind == OEA_SCORE_L2SQ)
-        k_loss_rows<OEA_SCORE_L2SQ><<<grid, kThreads, 0, st>>>(ph, pr, pt, n_pos, nh, nr, nt, n_neg, dim, pitch, *loss, loss_out, g_ph, g_pr, g_pt, g_nh, g_nr, g_nt);
+        OEA_LAUNCH(k_loss_rows<OEA_SCORE_L2SQ>, grid, kThreads, 0, st, ph, pr, pt, n_pos, nh, nr, nt, n_neg, dim, pitch, *loss, loss_out, g_ph, g_pr, g_pt, g_nh, g_nr, g_nt);
     else return OEA_ERR_KIND;
     OEA_LAUNCH_CHECK();
     return OEA_OK;
@@ -1133,12 +1133,12 @@ extern "C" int oea_mapping_fwd_bwd(const float* e1, const float* e2, int32_t n, 
     cudaStream_t st = (cudaStream_t)stream;
     if (n > 0) {
         const size_t smem = 2 * (size_t)MAP_PAIRS * dim * sizeof(float);
-        k_mapping_pairs<<<(n + MAP_PAIRS - 1) / MAP_PAIRS, 256, smem, st>>>(e1, e2, n, dim, pitch, M, mpitch, alpha, loss_out, g_e1, g_e2, g_M);
+        OEA_LAUNCH(k_mapping_pairs, (n + MAP_PAIRS - 1) / MAP_PAIRS, 256, smem, st, e1, e2, n, dim, pitch, M, mpitch, alpha, loss_out, g_e1, g_e2, g_M);
         OEA_LAUNCH_CHECK();
     }
-    k_mapping_orth<<<dim, 256, 0, st>>>(M, dim, mpitch, alpha, loss_out, g_M, (float*)workspace);
+    OEA_LAUNCH(k_mapping_orth, dim, 256, 0, st, M, dim, mpitch, alpha, loss_out, g_M, (float*)workspace);
     OEA_LAUNCH_CHECK();
-    k_mapping_orth_grad<<<dim, 256, 0, st>>>(M, dim, mpitch, alpha, (const float*)workspace, g_M);
+    OEA_LAUNCH(k_mapping_orth_grad, dim, 256, 0, st, M, dim, mpitch, alpha, (const float*)workspace, g_M);
     OEA_LAUNCH_CHECK();
     return OEA_OK;
 }
@@ -1198,8 +1198,8 @@ extern "C" int oea_rowopt_apply_pair(const oea_table* a, const oea_table* b, con
     OptTab A{a->weight, a->grad, a->state1, a->touched, a->rows}, B{b->weight, b->grad, b->state1, b->touched, b->rows};
     const int grid = grid_for(a->rows + b->rows);
     cudaStream_t st = (cudaStream_t)stream;
-    if (opt->kind == OEA_OPT_ADAGRAD) k_rowopt_pair<OEA_OPT_ADAGRAD><<<grid, kThreads, 0, st>>>(A, B, a->pitch, opt->lr);
-    else if (opt->kind == OEA_OPT_SGD) k_rowopt_pair<OEA_OPT_SGD><<<grid, kThreads, 0, st>>>(A, B, a->pitch, opt->lr);
+    if (opt->kind == OEA_OPT_ADAGRAD) OEA_LAUNCH(k_rowopt_pair<OEA_OPT_ADAGRAD>, grid, kThreads, 0, st, A, B, a->pitch, opt->lr);
+    else if (opt->kind == OEA_OPT_SGD) OEA_LAUNCH(k_rowopt_pair<OEA_OPT_SGD>, grid, kThreads, 0, st, A, B, a->pitch, opt->lr);
     else return OEA_ERR_KIND;
     OEA_LAUNCH_CHECK();
     return OEA_OK;

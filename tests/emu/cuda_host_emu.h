@@ -21,6 +21,13 @@
 #include <thread>
 #include <vector>
 
+// stream-ordered runtime calls the entry points make between launches: "device" memory is host memory and launches are
+// synchronous, so they are plain memset / memcpy
+#define cudaMemsetAsync(P, V, N, ST) (memset((P), (V), (N)), cudaSuccess)
+#define cudaMemcpyAsync(D, S, N, KIND, ST) (memcpy((D), (S), (N)), cudaSuccess)
+#define cudaStreamSynchronize(ST) (cudaSuccess)
+#define cudaLaunchCooperativeKernel(...) (cudaErrorNotSupported)        /* grid barriers are not emulated */
+
 #undef __shared__
 #define __shared__ static
 #undef __launch_bounds__
@@ -29,6 +36,12 @@
 struct EmuDim3 { unsigned x = 0, y = 0, z = 0; };
 inline thread_local EmuDim3 threadIdx, blockIdx;
 inline EmuDim3 gridDim, blockDim;
+
+#define _COOPERATIVE_GROUPS_H_          /* keep <cooperative_groups.h> out: it needs nvcc */
+namespace cooperative_groups {
+struct grid_group { void sync() const {} };    // serial blocks cannot honour a grid barrier: kernels using it are not run
+inline grid_group this_grid() { return {}; }
+}  // namespace cooperative_groups
 
 namespace emu {
 
@@ -71,12 +84,30 @@ inline T peek(int lane) {
     return v;
 }
 
+// Lane scheduling of the next launches.  Concurrent (default): the 32 lanes of a warp are free-running threads that meet
+// only at collectives — right for kernels that synchronise explicitly, but a kernel that relies on the hardware keeping a
+// converged warp in step between two plain memory accesses (all lanes read a row's `touched` flag, lane 0 clears it after
+// its columns: the row optimisers) sees a race real lanes never see.  Serial: the lanes of a warp run one after another,
+// lane 31 first and lane 0 last — valid ONLY for kernels without warp collectives, and it gives exactly that order.
+inline std::atomic<bool> g_serial_lanes{false};
+
 // run `body` as a grid of blocks of `threads` threads (a multiple of 32)
 template <typename Body>
 inline void launch(int grid, int threads, Body body) {
     gridDim.x = (unsigned)grid;
     blockDim.x = (unsigned)threads;
     const int warps = threads / 32;
+    if (g_serial_lanes.load()) {
+        for (int b = 0; b < grid; ++b)
+            for (int w = warps - 1; w >= 0; --w)
+                for (int l = 31; l >= 0; --l) {
+                    t_lane = l;
+                    threadIdx.x = (unsigned)(w * 32 + l);
+                    blockIdx.x = (unsigned)b;
+                    body();
+                }
+        return;
+    }
     for (int b = 0; b < grid; ++b) {
         for (int w = warps - 1; w >= 0; --w) {
             std::vector<std::thread> lanes;
@@ -132,6 +163,7 @@ inline unsigned __match_any_sync(unsigned mask, T v) {
     return out;
 }
 inline void __syncthreads() {}
+inline void __syncwarp(unsigned mask = 0xffffffffu) { emu::sync(mask); }     // lanes are threads: a real rendezvous
 
 // ---- loads, atomics, intrinsics ----------------------------------------------------------------------------------------
 template <typename T>
@@ -142,6 +174,11 @@ inline float atomicAdd(float* p, float v) {          // lanes of one warp may hi
     float old = a.load(std::memory_order_relaxed);
     while (!a.compare_exchange_weak(old, old + v, std::memory_order_relaxed)) {}
     return old;
+}
+inline unsigned long long atomicCAS(unsigned long long* p, unsigned long long expected, unsigned long long desired) {
+    std::atomic_ref<unsigned long long> a(*p);
+    a.compare_exchange_strong(expected, desired);
+    return expected;                                  // the value found at *p, as CUDA's atomicCAS returns
 }
 using std::min;
 using std::max;

@@ -1,0 +1,147 @@
+"""CPU: the core of path (i) — oea_triple.cu's fed scorers, the row optimisers, the normalised lookup and its backward,
+the tensor-level losses, the on-device triple set and the warp-per-positive sampled scorer — executed from the product's
+kernel SOURCE on the warp emulator (tests/emu) through the product's own Python engine over CPU tensors, against the C
+oracle.  These kernels are verified on the B200 by tests/test_triple_gpu.py; here the same checks guard refactors where
+no GPU exists.  (The octet / one-launch step kernels and the mapping kernels need a grid barrier resp. real block
+barriers, which the emulator's serial warps cannot give: they are compiled but not run.)"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from openea_b200 import engine as eng
+from openea_b200 import lib as L
+from oracle import triple as orc
+from tests.emu import build_emu
+from tests.helpers import make_batch, make_tables
+
+
+@pytest.fixture()
+def cpu_engine(monkeypatch):
+    so = build_emu.build()
+    if so is None:
+        pytest.skip("no CUDA headers for the emulator build")
+    lib = C.CDLL(so)
+    for name, (res, args) in L.SIGNATURES.items():
+        if hasattr(lib, name):
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+    # the row optimisers have no warp collectives and rely on a converged warp staying in step between reading a row's
+    # `touched` flag and lane 0 clearing it: their lanes run serially (lane 0 last) on the emulator
+    lib.emu_set_serial_lanes.argtypes = [C.c_int]
+    for name in ("oea_rowopt_apply", "oea_rowopt_apply_pair"):
+        real = getattr(lib, name)
+
+        def serial(*a, _real=real):
+            lib.emu_set_serial_lanes(1)
+            try:
+                return _real(*a)
+            finally:
+                lib.emu_set_serial_lanes(0)
+        setattr(lib, name, serial)
+    monkeypatch.setattr(L, "load", lambda: lib)
+    monkeypatch.setattr(eng, "_stream_ptr", lambda: C.c_void_p(0))
+    monkeypatch.setenv("OEA_NO_FUSE", "1")            # the one-launch step needs a grid barrier
+    monkeypatch.setenv("OEA_SCORE_V1", "1")           # the warp-per-positive sampled kernel
+    return eng
+
+
+def _t(x):
+    return torch.from_numpy(np.ascontiguousarray(x))
+
+
+@pytest.mark.parametrize("loss,k", [("limited", 3), ("logistic", 2), ("positive", 0), ("logsigmoid", 0), ("margin-based", 1)])
+@pytest.mark.parametrize("loss_norm,norm,d", [("L2", True, 12), ("L1", False, 75), ("L2", True, 200)])
+def test_emulated_fed_scorers_match_the_c_oracle(cpu_engine, loss, k, loss_norm, norm, d):
+    rng = np.random.default_rng(d + k)
+    n_ent, n_rel, n_pos = 40, 5, 19
+    ent, rel = make_tables(rng, n_ent, n_rel, d)
+    pos, neg = make_batch(rng, n_ent, n_rel, n_pos, k)
+    kw = dict(margin=1.1 if loss == "margin-based" else 0.3, neg_margin=2.2, balance=0.2)
+    want_loss, want_ge, want_gr, _ = orc.fwd_bwd(ent, rel, pos, neg, loss, loss_norm, norm, norm, **kw)
+    te, tr = cpu_engine.EmbeddingTable(ent, norm, device="cpu"), cpu_engine.EmbeddingTable(rel, norm, device="cpu")
+    t = cpu_engine.TripleTrainer(te, tr, cpu_engine.loss_cfg(loss, loss_norm, **kw), 0.01)
+    t.score_fed(_t(pos), None if neg is None else _t(neg))
+    assert t.read_loss() == pytest.approx(want_loss, rel=1e-4)
+    for tab, want in ((te, want_ge), (tr, want_gr)):
+        got = tab.grad[:, :d].numpy()
+        if loss_norm == "L1":
+            assert (np.abs(got - want) > 1e-4 * max(1.0, np.abs(want).max())).mean() < 5e-3
+        else:
+            np.testing.assert_allclose(got, want, rtol=1e-4, atol=2e-5 * max(1e-6, np.abs(want).max()))
+
+
+@pytest.mark.parametrize("opt", ["Adagrad", "SGD", "Adam"])
+def test_emulated_training_steps_equal_dense_tf_steps(cpu_engine, opt):
+    rng = np.random.default_rng(5)
+    d, n_ent, n_rel = 20, 60, 7
+    ent, rel = make_tables(rng, n_ent, n_rel, d)
+    kw = dict(margin=0.01, neg_margin=2.0, balance=0.2)
+    st = orc.DenseState(ent, rel, opt)
+    te, tr = cpu_engine.EmbeddingTable(ent, True, opt, device="cpu"), cpu_engine.EmbeddingTable(rel, True, opt, device="cpu")
+    t = cpu_engine.TripleTrainer(te, tr, cpu_engine.loss_cfg("limited", "L2", **kw), 0.01)
+    for _ in range(3):
+        pos, neg = make_batch(rng, n_ent, n_rel, 16, 3)
+        want = orc.step(st, pos, neg, "limited", "L2", True, True, 0.01, **kw)
+        t.score_fed(_t(pos), _t(neg))
+        t.apply()                                                    # oea_rowopt_apply_pair (Adam: two dense launches)
+        assert t.read_loss() == pytest.approx(want, rel=1e-4)
+    np.testing.assert_allclose(te.raw().numpy(), st.ent, rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(tr.raw().numpy(), st.rel, rtol=1e-4, atol=1e-6)
+    assert not te.grad.any() and not te.touched.any()
+
+
+def test_emulated_lookup_scatter_and_tensor_level_losses(cpu_engine):
+    rng = np.random.default_rng(2)
+    ent, _ = make_tables(rng, 30, 3, 10)
+    te = cpu_engine.EmbeddingTable(ent, True, device="cpu")
+    ids = rng.integers(0, 30, 11).astype(np.int32)
+    got = te.lookup(ids)
+    np.testing.assert_allclose(got.numpy(), orc.l2_normalize(ent)[ids], rtol=1e-5, atol=1e-7)
+    # backward of the lookup: gradient of Σ w·normalise(x) w.r.t. x, accumulated over repeated ids
+    w = rng.standard_normal((11, 10)).astype(np.float32)
+    x = torch.tensor(ent, dtype=torch.float64, requires_grad=True)
+    xn = x * torch.rsqrt(torch.clamp((x * x).sum(1, keepdim=True), min=1e-12))
+    (xn[torch.as_tensor(ids, dtype=torch.long)] * torch.as_tensor(w, dtype=torch.float64)).sum().backward()
+    te.scatter_grad(_t(w), ids)
+    np.testing.assert_allclose(te.grad[:, :10].numpy(), x.grad.numpy(), rtol=1e-4, atol=1e-6)
+    assert set(np.flatnonzero(te.touched.numpy())) == set(ids.tolist())
+
+
+def test_emulated_triple_set_and_sampled_scorer_replay(cpu_engine):
+    """oea_tripleset_build + the warp-per-positive sampled kernel: its debug dump, replayed through the fed scorer, gives
+    the same loss and gradients (the check tests/test_triple_gpu.py makes on the GPU)."""
+    rng = np.random.default_rng(8)
+    n, n_rel, d = 50, 4, 12
+    def kg(lo):
+        t = np.stack([rng.integers(lo, lo + n, 120), rng.integers(0, n_rel, 120), rng.integers(lo, lo + n, 120)], 1)
+        return np.unique(t.astype(np.int32), axis=0)
+    t1, t2 = kg(0), kg(n)
+    ent, rel = make_tables(rng, 2 * n, n_rel, d)
+    kg1 = cpu_engine.DeviceKG(t1, np.arange(0, n), 2 * n, device="cpu")
+    kg2 = cpu_engine.DeviceKG(t2, np.arange(n, 2 * n), 2 * n, device="cpu")
+    tset = cpu_engine.DeviceTripleSet([kg1.triples, kg2.triples], 2 * n, n_rel, device="cpu")
+    from tests.test_emu_sampler import build_tripleset
+    want_slots, _ = build_tripleset(np.concatenate([t1, t2]), tset.ent_bits, tset.rel_bits, capacity=tset.capacity)
+    assert set(tset.slots.numpy().view(np.uint64).tolist()) == set(want_slots.tolist())       # same keys (probe order may differ)
+    cfg = cpu_engine.loss_cfg("limited", "L2", 0.1, 2.0, 0.2)
+    B, k = 32, 3
+    a = cpu_engine.TripleTrainer(cpu_engine.EmbeddingTable(ent, True, device="cpu"),
+                                 cpu_engine.EmbeddingTable(rel, True, device="cpu"), cfg, 0.01)
+    dbg = torch.zeros(B, 2 + k, dtype=torch.int32)
+    n_pos = torch.zeros(1, dtype=torch.int32)
+    a.score_sampled(kg1, kg2, tset, B, k, 1, 4242, dbg=dbg, n_pos_out=n_pos)
+    m = int(n_pos)
+    rows = dbg.numpy()[:m]
+    pos = np.stack([(t2[r[0] - (1 << 30)] if r[0] >= (1 << 30) else t1[r[0]]) for r in rows], 1).astype(np.int32)
+    neg = np.repeat(pos, k, axis=1)
+    for i, r in enumerate(rows):
+        for j in range(k):
+            neg[0 if (r[1] >> j) & 1 else 2, i * k + j] = r[2 + j]
+    b = cpu_engine.TripleTrainer(cpu_engine.EmbeddingTable(ent, True, device="cpu"),
+                                 cpu_engine.EmbeddingTable(rel, True, device="cpu"), cfg, 0.01)
+    b.score_fed(_t(pos), _t(neg))
+    assert a.read_loss() == pytest.approx(b.read_loss(), rel=1e-5)
+    np.testing.assert_allclose(a.ent.grad.numpy(), b.ent.grad.numpy(), rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(a.rel.grad.numpy(), b.rel.grad.numpy(), rtol=1e-4, atol=1e-6)
