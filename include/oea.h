@@ -139,6 +139,24 @@ int oea_triple_score_fed_grouped(const oea_table* ent, const oea_table* rel,
                                  const int32_t* neg_h, const int32_t* neg_r, const int32_t* neg_t, int32_t n_neg,
                                  const oea_loss_cfg* loss, double* loss_out, void* stream);
 
+/* Margin loss with a weight per pair: scale · Σ_i w_i · relu(loss->margin + s(pos_i) − s(neg_i)), s by loss->score_kind.
+ * w_i = weights[i] (OEA_WEIGHT_DIRECT), 1 / weights[i] (OEA_WEIGHT_RECIPROCAL) or 1 (weights NULL).  Replaces
+ * approaches/iptranse.py:170-174 (_generate_transe_alignment_loss; w = similarity of the newly aligned pair) and
+ * iptranse.py:176-180 (_generate_path_loss; reciprocal path weights, scale = args.path_parm).  For the path loss the
+ * three ids of a "triple" are relation ids (r_x + r_y − r): pass the relation table as BOTH `ent` and `rel`.
+ * Accumulates into grad / touched like oea_triple_score_fed; *loss_out (device, fp64) += the weighted batch loss. */
+enum { OEA_WEIGHT_DIRECT = 0, OEA_WEIGHT_RECIPROCAL = 1 };
+int oea_triple_score_margin_weighted(const oea_table* ent, const oea_table* rel,
+                                     const int32_t* pos_h, const int32_t* pos_r, const int32_t* pos_t,
+                                     const int32_t* neg_h, const int32_t* neg_r, const int32_t* neg_t, int32_t n,
+                                     const float* weights, int32_t weight_mode, float scale,
+                                     const oea_loss_cfg* loss, double* loss_out, void* stream);
+
+/* scale · Σ_i w_i · ‖ê[ids_a[i]] − ê[ids_b[i]]‖² over looked-up (normalised when ent->l2_norm) rows, forward + backward
+ * into ent->grad / touched.  weights may be NULL (w = 1).  Replaces IMUSE's align loss (approaches/imuse.py:303-306). */
+int oea_pair_distance_loss(const oea_table* ent, const int32_t* ids_a, const int32_t* ids_b, int32_t n,
+                           const float* weights, float scale, double* loss_out, void* stream);
+
 /* Optimiser step on a table whose `grad` was filled by a score call.  Replaces
  * optimizer.apply_gradients of modules/base/optimizers.py:4-7.  Adagrad / SGD touch only flagged
  * rows (identical to TF's dense update because untouched rows have g = 0); Adam is dense.

@@ -1,6 +1,7 @@
 from openea_b200.approaches.aligne import AlignE
 from openea_b200.approaches.bootea import BootEA
 from openea_b200.approaches.bootea_transh import BootEA_TransH
+from openea_b200.approaches.iptranse import IPTransE
 from openea_b200.approaches.mtranse import MTransE
 from openea_b200.models._stubs import out_of_scope
 
@@ -19,7 +20,6 @@ except ImportError:  # pragma: no cover
 
 JAPE = out_of_scope("JAPE", "attribute skip-gram encoder")
 Attr2Vec = out_of_scope("Attr2Vec", "attribute skip-gram encoder")
-IPTransE = out_of_scope("IPTransE", "path-based TransE with soft alignment")
 AttrE = out_of_scope("AttrE", "character-level literal encoder")
 IMUSE = out_of_scope("IMUSE", "string-similarity preprocessing")
 SEA = out_of_scope("SEA", "adversarial degree-aware training")

@@ -250,6 +250,37 @@ class TripleTrainer:
             np_(pos, 0), np_(pos, 1), np_(pos, 2), n_pos, np_(neg, 0), np_(neg, 1), np_(neg, 2), n_neg,
             C.byref(self.loss), _ptr(out), _stream_ptr()), "oea_triple_score_fed")
 
+    def score_margin_weighted(self, pos, neg, weights=None, reciprocal=False, scale=1.0, paths=False, loss_out=None):
+        """scale · Σ wᵢ · relu(margin + s(posᵢ) − s(negᵢ)) forward + backward (oea_triple_score_margin_weighted;
+        iptranse.py:170-180).  pos / neg: int32 device tensors [3, n]; weights: float32 device tensor [n] or None;
+        reciprocal: wᵢ = 1 / weights[i]; paths: the columns are (r_x, r_y, r) relation ids and all three rows come from
+        the relation table (the path loss).  margin and norm are this trainer's loss configuration."""
+        out = self.loss_dev if loss_out is None else loss_out
+        n = pos.shape[1]
+        if neg.shape[1] != n or (weights is not None and weights.numel() != n):
+            raise ValueError("weighted margin loss pairs positive i with negative i and weight i")
+        if weights is not None:
+            weights = weights.to(torch.float32).contiguous()
+        a = self.rel if paths else self.ent
+        np_ = lambda t, i: C.c_void_p(0 if n == 0 else t[i].data_ptr())
+        L.check(self.lib.oea_triple_score_margin_weighted(
+            C.byref(a.c_struct()), C.byref(self.rel.c_struct()), np_(pos, 0), np_(pos, 1), np_(pos, 2),
+            np_(neg, 0), np_(neg, 1), np_(neg, 2), n, _ptr(weights), L.WEIGHT_RECIPROCAL if reciprocal else L.WEIGHT_DIRECT,
+            float(scale), C.byref(self.loss), _ptr(out), _stream_ptr()), "oea_triple_score_margin_weighted")
+
+    def score_pairs(self, ids_a, ids_b, weights=None, scale=1.0, loss_out=None):
+        """scale · Σ wᵢ · ‖ê_a − ê_b‖² over entity pairs, forward + backward (oea_pair_distance_loss; imuse.py:303-306)."""
+        out = self.loss_dev if loss_out is None else loss_out
+        dev = self.ent.device
+        a = torch.as_tensor(ids_a, dtype=torch.int32, device=dev).contiguous()
+        b = torch.as_tensor(ids_b, dtype=torch.int32, device=dev).contiguous()
+        if a.numel() != b.numel() or (weights is not None and weights.numel() != a.numel()):
+            raise ValueError("pair loss needs one id of each side (and one weight) per pair")
+        if weights is not None:
+            weights = weights.to(torch.float32).contiguous()
+        L.check(self.lib.oea_pair_distance_loss(C.byref(self.ent.c_struct()), _ptr(a), _ptr(b), a.numel(), _ptr(weights),
+                                                float(scale), _ptr(out), _stream_ptr()), "oea_pair_distance_loss")
+
     def apply(self):
         for tab in (self.ent, self.rel):
             if tab.optimizer == "Adam":

@@ -13,6 +13,7 @@ LIB_PATH = os.environ.get("OEA_LIB_PATH") or os.path.join(_HERE, "_lib", "liboea
 SCORE_L1, SCORE_L2SQ = 0, 1
 LOSS_MARGIN, LOSS_LIMITED, LOSS_LOGISTIC, LOSS_POSITIVE, LOSS_LOGSIGMOID = 0, 1, 2, 3, 4
 OPT_SGD, OPT_ADAGRAD, OPT_ADAM, OPT_ADADELTA = 0, 1, 2, 3
+WEIGHT_DIRECT, WEIGHT_RECIPROCAL = 0, 1
 METRIC_INNER, METRIC_L1, METRIC_L2 = 0, 1, 2
 MODEL_TRANSE, MODEL_TRANSH, MODEL_TRANSD, MODEL_DISTMULT, MODEL_SIMPLE = 0, 1, 2, 3, 4
 
@@ -86,6 +87,9 @@ SIGNATURES = {
     "oea_abi_version": (C.c_int, []),
     "oea_error_string": (C.c_char_p, [C.c_int]),
     "oea_triple_score_fed": (C.c_int, [_TP, _TP, _P, _P, _P, _I, _P, _P, _P, _I, C.POINTER(LossCfg), _P, _P]),
+    "oea_triple_score_margin_weighted": (C.c_int, [_TP, _TP, _P, _P, _P, _P, _P, _P, _I, _P, _I, C.c_float,
+                                                   C.POINTER(LossCfg), _P, _P]),
+    "oea_pair_distance_loss": (C.c_int, [_TP, _P, _P, _I, _P, C.c_float, _P, _P]),
     "oea_triple_score_fed_grouped": (C.c_int, [_TP, _TP, _P, _P, _P, _I, _P, _P, _P, _I, C.POINTER(LossCfg), _P, _P]),
     "oea_rowopt_apply": (C.c_int, [_TP, C.POINTER(OptCfg), _P]),
     "oea_rowopt_apply_pair": (C.c_int, [_TP, _TP, C.POINTER(OptCfg), _P]),

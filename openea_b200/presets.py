@@ -97,3 +97,11 @@ def bootea_transh(scale="15K"):
     a = bootea(scale)
     a.embedding_module = "BootEA_TransH"
     return a
+
+
+def iptranse(scale="15K"):
+    """run/args/iptranse_args_*.json."""
+    return _args(embedding_module="IPTransE", alignment_module="sharing", dim=100, init="normal", ent_l2_norm=True,
+                 rel_l2_norm=True, loss_norm="L2", learning_rate=0.01, optimizer="Adagrad",
+                 batch_size=5000 if scale == "15K" else 20000, margin=1.5, path_parm=0.1, neg_sampling="uniform",
+                 neg_triple_num=1, eval_metric="inner", eval_norm=False, sim_th=0.7, bp_freq=100)

@@ -145,3 +145,84 @@ def test_emulated_triple_set_and_sampled_scorer_replay(cpu_engine):
     assert a.read_loss() == pytest.approx(b.read_loss(), rel=1e-5)
     np.testing.assert_allclose(a.ent.grad.numpy(), b.ent.grad.numpy(), rtol=1e-4, atol=1e-6)
     np.testing.assert_allclose(a.rel.grad.numpy(), b.rel.grad.numpy(), rtol=1e-4, atol=1e-6)
+
+
+def _normed(x, on):
+    return x * torch.rsqrt(torch.clamp((x * x).sum(1, keepdim=True), min=1e-12)) if on else x
+
+
+@pytest.mark.parametrize("paths,reciprocal", [(False, False), (True, True), (False, True)])
+@pytest.mark.parametrize("loss_norm,norm,d", [("L2", True, 12), ("L1", False, 75), ("L2", True, 200)])
+def test_emulated_weighted_margin_scorer_matches_autograd(cpu_engine, paths, reciprocal, loss_norm, norm, d):
+    """oea_triple_score_margin_weighted (IPTransE's alignment and path losses, iptranse.py:170-180) against float64
+    autograd of the formula as written there; `paths`: all three rows of a triple come from the relation table."""
+    rng = np.random.default_rng(d + 3 * paths + reciprocal)
+    n_ent, n_rel, n = 30, 9, 23
+    ent, rel = make_tables(rng, n_ent, n_rel, d)
+    hi = n_rel if paths else n_ent
+    pos = np.stack([rng.integers(0, hi, n), rng.integers(0, n_rel, n), rng.integers(0, hi, n)]).astype(np.int32)
+    neg = np.stack([rng.integers(0, hi, n), rng.integers(0, n_rel, n), rng.integers(0, hi, n)]).astype(np.int32)
+    w = (rng.random(n) * 3 + 0.5).astype(np.float32)
+    w[3] = 0.0 if not reciprocal else w[3]
+    margin, scale = 0.8, 0.1 if paths else 1.0
+
+    E = torch.tensor(ent, dtype=torch.float64, requires_grad=True)
+    R = torch.tensor(rel, dtype=torch.float64, requires_grad=True)
+    En, Rn = _normed(E, norm), _normed(R, norm)
+    A = Rn if paths else En
+
+    def score(b):
+        u = A[b[0].astype(np.int64)] + Rn[b[1].astype(np.int64)] - A[b[2].astype(np.int64)]
+        return u.abs().sum(1) if loss_norm == "L1" else (u * u).sum(1)
+    wt = torch.tensor(w, dtype=torch.float64)
+    wt = 1.0 / wt if reciprocal else wt
+    want = scale * (wt * torch.relu(margin + score(pos) - score(neg))).sum()
+    want.backward()
+
+    te, tr = cpu_engine.EmbeddingTable(ent, norm, device="cpu"), cpu_engine.EmbeddingTable(rel, norm, device="cpu")
+    t = cpu_engine.TripleTrainer(te, tr, cpu_engine.loss_cfg("margin-based", loss_norm, margin=margin), 0.01)
+    t.score_margin_weighted(_t(pos), _t(neg), _t(w), reciprocal=reciprocal, scale=scale, paths=paths)
+    assert t.read_loss() == pytest.approx(float(want.detach()), rel=1e-4)
+    for tab, ref in ((te, E), (tr, R)):
+        g = np.zeros_like(ent if tab is te else rel) if ref.grad is None else ref.grad.numpy()
+        got = tab.grad[:, :d].numpy()
+        if loss_norm == "L1":
+            assert (np.abs(got - g) > 1e-4 * max(1.0, np.abs(g).max())).mean() < 5e-3
+        else:
+            np.testing.assert_allclose(got, g, rtol=1e-4, atol=2e-5 * max(1e-6, np.abs(g).max()))
+    if paths:
+        assert not te.touched.any()
+    # unweighted call == the plain margin scorer
+    t2 = cpu_engine.TripleTrainer(cpu_engine.EmbeddingTable(ent, norm, device="cpu"),
+                                  cpu_engine.EmbeddingTable(rel, norm, device="cpu"),
+                                  cpu_engine.loss_cfg("margin-based", loss_norm, margin=margin), 0.01)
+    t3 = cpu_engine.TripleTrainer(cpu_engine.EmbeddingTable(ent, norm, device="cpu"),
+                                  cpu_engine.EmbeddingTable(rel, norm, device="cpu"),
+                                  cpu_engine.loss_cfg("margin-based", loss_norm, margin=margin), 0.01)
+    if not paths:
+        t2.score_margin_weighted(_t(pos), _t(neg))
+        t3.score_fed(_t(pos), _t(neg))
+        assert t2.read_loss() == pytest.approx(t3.read_loss(), rel=1e-6)
+        np.testing.assert_allclose(t2.ent.grad.numpy(), t3.ent.grad.numpy(), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("norm,d,weighted", [(True, 12, False), (False, 75, True), (True, 300, True)])
+def test_emulated_pair_distance_loss_matches_autograd(cpu_engine, norm, d, weighted):
+    rng = np.random.default_rng(d)
+    ent, rel = make_tables(rng, 25, 2, d)
+    a = rng.integers(0, 25, 17).astype(np.int32)
+    b = rng.integers(0, 25, 17).astype(np.int32)
+    b[0] = a[0]                                                    # a pair of one entity with itself: no loss, no gradient
+    w = (rng.random(17) + 0.1).astype(np.float32) if weighted else None
+    E = torch.tensor(ent, dtype=torch.float64, requires_grad=True)
+    En = _normed(E, norm)
+    dist = ((En[a.astype(np.int64)] - En[b.astype(np.int64)]) ** 2).sum(1)
+    want = 0.7 * ((torch.tensor(w, dtype=torch.float64) * dist).sum() if weighted else dist.sum())
+    want.backward()
+    te = cpu_engine.EmbeddingTable(ent, norm, device="cpu")
+    t = cpu_engine.TripleTrainer(te, cpu_engine.EmbeddingTable(rel, norm, device="cpu"),
+                                 cpu_engine.loss_cfg("margin-based", "L2", margin=1.0), 0.01)
+    t.score_pairs(a, b, None if w is None else _t(w), scale=0.7)
+    assert t.read_loss() == pytest.approx(float(want.detach()), rel=1e-4)
+    np.testing.assert_allclose(te.grad[:, :d].numpy(), E.grad.numpy(), rtol=1e-4, atol=2e-5 * float(E.grad.abs().max()))
+    assert set(np.flatnonzero(te.touched.numpy())) <= set(a.tolist()) | set(b.tolist())
