@@ -270,8 +270,10 @@ class BasicModel:
         # the first epoch of a process runs eagerly (module loading, occupancy queries and allocator warm-up must not
         # happen inside a stream capture; a resumed run starts at epoch > 1); the multi-table trainers read the step's
         # size back and are not captured
+        # Adam's bias-corrected step size is a host-computed launch argument that changes every step: a replayed graph
+        # would freeze it, so Adam-optimised models run their epochs eagerly
         use_graph = getattr(self.args, "cuda_graph", True) and getattr(self, "_ran_eager_epoch", False) and \
-            hasattr(trainer, "capture_epoch")
+            hasattr(trainer, "capture_epoch") and getattr(self.ent_embeds, "optimizer", None) != "Adam"
         self._ran_eager_epoch = True
         if use_graph:
             key = (triple_steps, trainer._views(kg1, kg2, tset) and trainer._view_key)

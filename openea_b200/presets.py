@@ -105,3 +105,11 @@ def iptranse(scale="15K"):
                  rel_l2_norm=True, loss_norm="L2", learning_rate=0.01, optimizer="Adagrad",
                  batch_size=5000 if scale == "15K" else 20000, margin=1.5, path_parm=0.1, neg_sampling="uniform",
                  neg_triple_num=1, eval_metric="inner", eval_norm=False, sim_th=0.7, bp_freq=100)
+
+
+def sea(scale="15K"):
+    """run/args/sea_args_*.json."""
+    return _args(embedding_module="SEA", alignment_module="mapping", dim=100, init="normal", ent_l2_norm=True,
+                 rel_l2_norm=True, loss_norm="L2", margin=1.5, loss="margin-based", alpha_1=2.5, alpha_2=0.25,
+                 neg_sampling="uniform", neg_triple_num=1, learning_rate=0.01, optimizer="Adam",
+                 batch_size=5000 if scale == "15K" else 20000, start_valid=10, eval_metric="inner", eval_norm=True)
