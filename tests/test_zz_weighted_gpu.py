@@ -97,3 +97,20 @@ def test_iptranse_lifecycle(cuda_device, tiny_kgs, tmp_path):
     assert "num of path:" in out and "Training ends. Total time" in out
     assert re.search(r"epoch 40, alignment loss: [0-9.]+", out) or "newly triples" not in out
     assert _hits1(out, "accurate results:") >= 0.0       # the result line exists; accuracy is calibrated once this has run on a GPU
+
+
+def test_imuse_lifecycle(cuda_device, tiny_kgs, tmp_path):
+    """set_args / set_kgs / init / run / test / save of IMUSE: the string matcher's pairs feed the pair-distance loss."""
+    import re
+    from openea_b200 import presets
+    from openea_b200.approaches import IMUSE
+    from tests.test_e2e_gpu import _hits1, _run
+    args = presets.imuse("15K")
+    args.batch_size, args.max_epoch, args.start_valid, args.dim = 1000, 60, 1000, 32
+    model, out = _run(IMUSE, args, tiny_kgs, "sharing", tmp_path)
+    triple = [float(x) for x in re.findall(r"avg\. triple loss:\s*([0-9.]+)", out)]
+    align = [float(x) for x in re.findall(r"align learning loss:\s*([0-9.]+)", out)]
+    assert len(triple) == 60 and len(align) == 60 and triple[-1] < triple[0]
+    if model.aligned_ent_pair_set:
+        assert align[-1] < align[0], (align[0], align[-1])
+    assert _hits1(out, "accurate results:") >= 0.0       # the result line exists; accuracy is calibrated once this has run on a GPU
