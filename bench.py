@@ -327,10 +327,35 @@ def probe_pipelined_e2e(args):
     pipe.collect((K - 1) % 2)
     dt = time.perf_counter() - t0
     n_pos_h, n_neg_h = batches[0][0].shape[1], batches[0][1].shape[1]
-    print(json.dumps({"value": n_pos_h * K / dt, "unit": "positive triples/s", "ms_per_step": 1e3 * dt / K, "steps": K,
-                      "h2d_bytes_per_step": 12 * (n_pos_h + n_neg_h), "d2h_bytes_per_step": 8,
-                      "loss_max_rel_diff_vs_sync_api": rel, "losses_agree": bool(rel <= 1e-4),
-                      "api": "oea_triple_step_fed_host_submit / _collect (depth-2 pipeline, steps back to back, L2 not flushed)"}))
+    res = {"value": n_pos_h * K / dt, "unit": "positive triples/s", "ms_per_step": 1e3 * dt / K, "steps": K,
+           "h2d_bytes_per_step": 12 * (n_pos_h + n_neg_h), "d2h_bytes_per_step": 8,
+           "loss_max_rel_diff_vs_sync_api": rel, "losses_agree": bool(rel <= 1e-4),
+           "api": "oea_triple_step_fed_host_submit / _collect (depth-2 pipeline, steps back to back, L2 not flushed)"}
+    try:     # the same pipeline with OEA_FED_GROUPED=1: one warp per positive and its negatives (oea_triple_grouped.cu)
+        os.environ["OEA_FED_GROUPED"] = "1"
+        restore()
+        got = []
+        for i in range(6):
+            pipe.submit(i % 2, *batches[i])
+            if i >= 1:
+                got.append(pipe.collect((i - 1) % 2))
+        got.append(pipe.collect(5 % 2))
+        rel_g = max(abs(a - b) / max(1e-12, abs(b)) for a, b in zip(got, want))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(K):
+            pipe.submit(i % 2, *batches[i % 8])
+            if i >= 1:
+                pipe.collect((i - 1) % 2)
+        pipe.collect((K - 1) % 2)
+        dt = time.perf_counter() - t0
+        res["grouped_scorer"] = {"value": n_pos_h * K / dt, "ms_per_step": 1e3 * dt / K,
+                                 "loss_max_rel_diff_vs_sync_api": rel_g, "losses_agree": bool(rel_g <= 1e-4)}
+    except Exception as exc:
+        res["grouped_scorer"] = {"value": None, "note": "failed: %r" % (exc,)}
+    finally:
+        os.environ.pop("OEA_FED_GROUPED", None)
+    print(json.dumps(res))
     return 0
 
 

@@ -12,6 +12,8 @@
 // The caller owns streams, events and buffers (no allocation here) and keeps a submitted step's pinned host index
 // buffers untouched until that step's `copied` event has fired — with two host buffers used alternately that is
 // guaranteed by collect(slot) of the step two submissions earlier.
+#include <stdlib.h>
+
 #include "oea_rowmath.cuh"
 
 using namespace oea;
@@ -37,8 +39,14 @@ extern "C" int oea_triple_step_fed_host_submit(const oea_table* ent, const oea_t
     OEA_CUDA_TRY(cudaEventRecord(copied, copy));
     OEA_CUDA_TRY(cudaStreamWaitEvent(comp, copied, 0));
     OEA_CUDA_TRY(cudaMemsetAsync(pipe->dev_loss[slot], 0, sizeof(double), comp));
-    int rc = oea_triple_score_fed(ent, rel, dpos, dpos + n_pos, dpos + 2 * (size_t)n_pos, n_pos,
-                                  dneg, dneg + n_neg, dneg + 2 * (size_t)n_neg, n_neg, loss, pipe->dev_loss[slot], comp);
+    // OEA_FED_GROUPED=1: same opt-in as oea_triple_step_fed_host (a positive scored together with its negatives)
+    const char* grouped_env = getenv("OEA_FED_GROUPED");
+    const bool grouped = grouped_env && grouped_env[0] == '1' && n_pos > 0 && n_neg % n_pos == 0;
+    int rc = grouped
+        ? oea_triple_score_fed_grouped(ent, rel, dpos, dpos + n_pos, dpos + 2 * (size_t)n_pos, n_pos,
+                                       dneg, dneg + n_neg, dneg + 2 * (size_t)n_neg, n_neg, loss, pipe->dev_loss[slot], comp)
+        : oea_triple_score_fed(ent, rel, dpos, dpos + n_pos, dpos + 2 * (size_t)n_pos, n_pos,
+                               dneg, dneg + n_neg, dneg + 2 * (size_t)n_neg, n_neg, loss, pipe->dev_loss[slot], comp);
     if (rc) return rc;
     rc = oea_rowopt_apply_pair(ent, rel, opt, comp); if (rc) return rc;
     OEA_CUDA_TRY(cudaMemcpyAsync(pipe->host_loss[slot], pipe->dev_loss[slot], sizeof(double), cudaMemcpyDeviceToHost, comp));
