@@ -24,6 +24,7 @@ import numpy as np
 import torch
 
 from openea_b200 import engine as eng
+from openea_b200 import parallel as par
 from openea_b200.models.basic_model import BasicModel
 from openea_b200.modules.finding.evaluation import early_stop
 from openea_b200.modules.utils.util import load_session, task_divide
@@ -186,6 +187,9 @@ class IMUSE(BasicModel):
         self.alignment_trainer = None
 
     def init(self):
+        if par.world()[1] > 1:
+            raise NotImplementedError("%s runs on one GPU: its extra training passes have no cross-rank exchange yet" %
+                                      self.__class__.__name__)
         self.aligned_ent_pair_set = interactive_model(self.kgs, self.args)
         self.session = load_session()
         self._define_variables()

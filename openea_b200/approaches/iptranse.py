@@ -20,6 +20,7 @@ import torch
 
 from openea_b200 import engine as eng
 from openea_b200 import finding
+from openea_b200 import parallel as par
 from openea_b200.models.basic_model import BasicModel
 from openea_b200.modules.finding.evaluation import early_stop
 from openea_b200.modules.utils.util import load_session, task_divide
@@ -124,6 +125,9 @@ class IPTransE(BasicModel):
         self.alignment_trainer = None
 
     def init(self):
+        if par.world()[1] > 1:
+            raise NotImplementedError("%s runs on one GPU: its extra training passes have no cross-rank exchange yet" %
+                                      self.__class__.__name__)
         self.ref_entities1 = self.kgs.valid_entities1 + self.kgs.test_entities1
         self.ref_entities2 = self.kgs.valid_entities2 + self.kgs.test_entities2
         self.session = load_session()

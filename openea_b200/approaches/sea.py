@@ -19,6 +19,7 @@ import time
 import numpy as np
 import torch
 
+from openea_b200 import parallel as par
 from openea_b200.models.basic_model import BasicModel
 from openea_b200.modules.base.initializers import orthogonal_init
 from openea_b200.modules.finding.evaluation import early_stop
@@ -83,6 +84,9 @@ class SEA(BasicModel):
         self.mapping_mat_1 = self.mapping_mat_2 = None
 
     def init(self):
+        if par.world()[1] > 1:
+            raise NotImplementedError("%s runs on one GPU: its extra training passes have no cross-rank exchange yet" %
+                                      self.__class__.__name__)
         self.session = load_session()
         self._define_variables()
         self._define_embed_graph()
