@@ -35,8 +35,10 @@ def _loss_from_args(args, loss=None):
     if kind == 'margin-based':
         return eng.loss_cfg(kind, args.loss_norm, margin=args.margin)
     if kind == 'limited':
-        return eng.loss_cfg(kind, args.loss_norm, margin=args.pos_margin, neg_margin=args.neg_margin,
-                            balance=getattr(args, "neg_margin_balance", 1.0))
+        # the approaches that name the limited loss themselves pass balance=args.neg_margin_balance (aligne.py:63-65,
+        # bootea_transh.py:94-96); get_loss_func does not, so the default balance = 1.0 applies there (losses.py:10,44)
+        balance = getattr(args, "neg_margin_balance", 1.0) if loss is not None else 1.0
+        return eng.loss_cfg(kind, args.loss_norm, margin=args.pos_margin, neg_margin=args.neg_margin, balance=balance)
     return eng.loss_cfg(kind, getattr(args, "loss_norm", "L2"))
 
 

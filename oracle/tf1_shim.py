@@ -1,0 +1,390 @@
+"""TEST INFRASTRUCTURE: a minimal TensorFlow-1 graph interpreter on torch float64, so that the reference's own
+graph-definition code (modules/base/{losses,initializers,optimizers,mapping}.py, models/*, approaches/*: the
+`_define_variables` / `_define_embed_graph` methods and `session.run([loss, optimizer], feed_dict)`) can be EXECUTED,
+unmodified, in a container without TensorFlow.  `scripts/make_golden_path_i.py` installs this module as `tensorflow`,
+imports the reference from /root/reference/src and writes tests/golden/path_i_*.npz; nothing under openea_b200/
+imports it.
+
+What comes from the reference when a golden is generated: which variables exist and how they are initialised /
+normalised, every lookup, the whole loss expression, which optimiser instance minimises which loss.
+What is restated HERE (from the TF 1.x documentation / op definitions, not executable offline — the residual
+"unpinned" part of path (i)'s parity):
+  * op semantics: reduce_sum / reduce_mean, pow, square, abs (gradient sign(x), 0 at 0), relu (gradient 0 at 0),
+    maximum (ties send the gradient to the first argument), log, exp, sigmoid, softplus, matmul(transpose_b),
+    nn.l2_normalize(x, axis, epsilon=1e-12) = x · rsqrt(max(Σ_axis x², epsilon)) — over ALL elements when axis is None;
+  * gradients of a loss w.r.t. a variable are dense (an embedding_lookup of l2_normalize(var) is dense in TF too; for
+    lookups straight into a variable TF's sparse Adagrad / SGD / Adam updates equal the dense rule; only sparse
+    Adadelta differs, which no shipped configuration uses);
+  * optimiser rules: GradientDescent; Adagrad (initial_accumulator_value 0.1); Adam (β₁ .9, β₂ .999, ε 1e-8,
+    lr_t = lr·√(1−β₂ᵗ)/(1−β₁ᵗ), ε outside the root); Adadelta (ρ .95, ε 1e-8).
+Arithmetic is float64 so that a golden is the mathematical value of the reference's graph to ~1e-15.
+"""
+import contextlib
+import math
+import types
+
+import numpy as np
+import torch
+
+DT = torch.float64
+int32, int64, float32, float64 = "int32", "int64", "float32", "float64"
+_VARIABLES = []
+
+
+def reset_default_graph():
+    _VARIABLES.clear()
+
+
+def _wrap(x):
+    if isinstance(x, Tensor):
+        return x
+    return Tensor(lambda: _const(x), (), "const")
+
+
+def _const(x):
+    if isinstance(x, torch.Tensor):
+        return x
+    a = np.asarray(x)
+    return torch.as_tensor(a, dtype=DT if a.dtype.kind == "f" else None)
+
+
+class Tensor:
+    """A node of the lazy graph: fn(*evaluated inputs) → torch tensor."""
+
+    def __init__(self, fn, inputs, name="op"):
+        self.fn, self.inputs, self.name = fn, tuple(inputs), name
+
+    def _eval(self, env):
+        key = id(self)
+        if key not in env:
+            env[key] = self.fn(*[i._eval(env) for i in self.inputs])
+        return env[key]
+
+    def eval(self, session=None, feed_dict=None):
+        return Session().run(self, feed_dict)
+
+    def _bin(self, other, f, name, swap=False):
+        a, b = (_wrap(other), self) if swap else (self, _wrap(other))
+        return Tensor(f, (a, b), name)
+
+    def __add__(self, o): return self._bin(o, torch.add, "add")
+    def __radd__(self, o): return self._bin(o, torch.add, "add", True)
+    def __sub__(self, o): return self._bin(o, torch.sub, "sub")
+    def __rsub__(self, o): return self._bin(o, torch.sub, "sub", True)
+    def __mul__(self, o): return self._bin(o, torch.mul, "mul")
+    def __rmul__(self, o): return self._bin(o, torch.mul, "mul", True)
+    def __truediv__(self, o): return self._bin(o, torch.div, "div")
+    def __rtruediv__(self, o): return self._bin(o, torch.div, "div", True)
+    def __neg__(self): return Tensor(torch.neg, (self,), "neg")
+    def __pow__(self, p): return pow(self, p)
+
+
+class Placeholder(Tensor):
+    def __init__(self, dtype, shape=None, name=None):
+        super().__init__(None, (), name or "placeholder")
+        self.dtype = dtype
+
+    def _eval(self, env):
+        if id(self) not in env:
+            raise KeyError("placeholder %s was not fed" % self.name)
+        return env[id(self)]
+
+
+class Variable(Tensor):
+    def __init__(self, initial_value, name=None, dtype=None, trainable=True):
+        super().__init__(None, (), name or "Variable")
+        self.value = torch.tensor(np.asarray(initial_value, dtype=np.float64), dtype=DT, requires_grad=True)
+        self.slots = {}
+        if trainable:
+            _VARIABLES.append(self)
+
+    def _eval(self, env):
+        return self.value
+
+    def assign_numpy(self, array):
+        self.value = torch.tensor(np.asarray(array, dtype=np.float64), dtype=DT, requires_grad=True)
+        self.slots = {}
+
+
+def placeholder(dtype, shape=None, name=None):
+    return Placeholder(dtype, shape, name)
+
+
+def constant(value, dtype=None, name=None, shape=None):
+    return _wrap(value)
+
+
+def get_variable(name, shape=None, dtype=None, initializer=None):
+    return Variable(initializer(shape), name=name, dtype=dtype)
+
+
+def trainable_variables():
+    return list(_VARIABLES)
+
+
+@contextlib.contextmanager
+def name_scope(name):
+    yield
+
+
+variable_scope = name_scope
+
+
+def _unary(f, name):
+    return lambda x, name_=None, **kw: Tensor(f, (_wrap(x),), name)
+
+
+abs = _unary(torch.abs, "abs")               # noqa: A001  (TF's names)
+square = _unary(torch.square, "square")
+log = _unary(torch.log, "log")
+exp = _unary(torch.exp, "exp")
+sigmoid = _unary(torch.sigmoid, "sigmoid")
+tanh = _unary(torch.tanh, "tanh")
+
+
+def pow(x, y, name=None):                    # noqa: A001
+    return Tensor(lambda a, b: torch.pow(a, b), (_wrap(x), _wrap(y)), "pow")
+
+
+def add(x, y, name=None): return _wrap(x) + y
+def subtract(x, y, name=None): return _wrap(x) - y
+def multiply(x, y, name=None): return _wrap(x) * y
+
+
+def maximum(x, y, name=None):
+    return Tensor(lambda a, b: torch.where(a >= b, a + 0 * b, b + 0 * a), (_wrap(x), _wrap(y)), "maximum")
+
+
+def cast(x, dtype=None, name=None):
+    return Tensor(lambda a: a.to(DT) if dtype in (float32, float64) else a.long(), (_wrap(x),), "cast")
+
+
+def _reduce(f):
+    def op(x, axis=None, keepdims=False, keep_dims=False, name=None):
+        keep = bool(keepdims or keep_dims)
+        return Tensor(lambda a: f(a) if axis is None else f(a, dim=axis, keepdim=keep), (_wrap(x),), f.__name__)
+    return op
+
+
+reduce_sum = _reduce(torch.sum)
+reduce_mean = _reduce(torch.mean)
+
+
+def matmul(a, b, transpose_a=False, transpose_b=False, name=None):
+    def f(x, y):
+        return (x.t() if transpose_a else x) @ (y.t() if transpose_b else y)
+    return Tensor(f, (_wrap(a), _wrap(b)), "matmul")
+
+
+def reshape(x, shape, name=None):
+    return Tensor(lambda a: a.reshape(shape), (_wrap(x),), "reshape")
+
+
+def _l2_normalize(x, axis=None, epsilon=1e-12, name=None, dim=None):
+    axis = dim if axis is None else axis
+
+    def f(a):
+        ss = (a * a).sum() if axis is None else (a * a).sum(dim=axis, keepdim=True)
+        return a * torch.rsqrt(torch.clamp(ss, min=epsilon))
+    return Tensor(f, (_wrap(x),), "l2_normalize")
+
+
+def _embedding_lookup(params, ids, name=None):
+    return Tensor(lambda p, i: p[torch.as_tensor(i).long()], (_wrap(params), _wrap(ids)), "embedding_lookup")
+
+
+nn = types.SimpleNamespace(
+    embedding_lookup=_embedding_lookup, l2_normalize=_l2_normalize,
+    relu=_unary(torch.relu, "relu"), softplus=_unary(torch.nn.functional.softplus, "softplus"),
+    sigmoid=sigmoid, tanh=tanh)
+
+
+# ---- initialisers (the goldens overwrite the values; shapes and dtypes are what matters) ------------------------
+def _gen():
+    g = torch.Generator()
+    g.manual_seed(1234)
+    return g
+
+
+def _truncated_normal(stddev=1.0, mean=0.0, **kw):
+    def init(shape):
+        x = torch.empty(*shape, dtype=DT)
+        torch.nn.init.trunc_normal_(x, mean=mean, std=stddev, a=mean - 2 * stddev, b=mean + 2 * stddev, generator=_gen())
+        return x.numpy()
+    return init
+
+
+def _random_uniform(minval=0, maxval=None, **kw):
+    hi = 1.0 if maxval is None else maxval
+    return lambda shape: (torch.rand(*shape, dtype=DT, generator=_gen()) * (hi - minval) + minval).numpy()
+
+
+def _orthogonal(gain=1.0, **kw):
+    def init(shape):
+        x = torch.empty(*shape, dtype=DT)
+        torch.nn.init.orthogonal_(x, gain=gain, generator=_gen())
+        return x.numpy()
+    return init
+
+
+def _xavier(uniform=True, **kw):
+    def init(shape):
+        fan = (shape[0] + shape[1]) / 2.0
+        if uniform:
+            lim = math.sqrt(3.0 / fan)
+            return ((torch.rand(*shape, dtype=DT, generator=_gen()) * 2 - 1) * lim).numpy()
+        return _truncated_normal(stddev=math.sqrt(1.3 / fan))(shape)
+    return init
+
+
+initializers = types.SimpleNamespace(truncated_normal=_truncated_normal, random_uniform=_random_uniform,
+                                     orthogonal=_orthogonal)
+contrib = types.SimpleNamespace(layers=types.SimpleNamespace(xavier_initializer=_xavier))
+truncated_normal_initializer = _truncated_normal
+random_uniform_initializer = _random_uniform
+
+
+# ---- optimisers ------------------------------------------------------------------------------------------------
+def _variables_of(node, seen=None, out=None):
+    seen = set() if seen is None else seen
+    out = [] if out is None else out
+    if id(node) in seen:
+        return out
+    seen.add(id(node))
+    if isinstance(node, Variable):
+        out.append(node)
+    for i in node.inputs:
+        _variables_of(i, seen, out)
+    return out
+
+
+class _TrainOp(Tensor):
+    def __init__(self, optimizer, loss, variables):
+        super().__init__(None, (), "train_op")
+        self.optimizer, self.loss, self.variables = optimizer, loss, variables
+
+
+class _Optimizer:
+    def __init__(self, learning_rate, **kw):
+        self.lr = float(learning_rate)
+        self.kw = kw
+        self.key = id(self)          # slot variables belong to the optimiser INSTANCE
+        self.t = 0
+
+    def compute_gradients(self, loss, var_list=None):
+        reach = _variables_of(loss)
+        if var_list is not None:
+            allowed = {id(v) for v in var_list}
+            reach = [v for v in reach if id(v) in allowed]
+        return (loss, reach)
+
+    def apply_gradients(self, grads_and_vars, **kw):
+        loss, variables = grads_and_vars
+        return _TrainOp(self, loss, variables)
+
+    def minimize(self, loss, var_list=None, **kw):
+        return self.apply_gradients(self.compute_gradients(loss, var_list))
+
+    def _run(self, env):
+        loss = self.current.loss._eval(env)
+        variables = self.current.variables
+        grads = torch.autograd.grad(loss, [v.value for v in variables], allow_unused=True, retain_graph=True)
+        self.t += 1
+        with torch.no_grad():
+            for v, g in zip(variables, grads):
+                if g is not None:
+                    self.update(v, g, v.slots.setdefault(self.key, {}))
+
+    def slot(self, slots, name, like, fill=0.0):
+        if name not in slots:
+            slots[name] = torch.full_like(like, fill)
+        return slots[name]
+
+
+class GradientDescentOptimizer(_Optimizer):
+    def update(self, v, g, slots):
+        v.value -= self.lr * g
+
+
+class AdagradOptimizer(_Optimizer):
+    def update(self, v, g, slots):
+        acc = self.slot(slots, "accumulator", v.value, self.kw.get("initial_accumulator_value", 0.1))
+        acc += g * g
+        v.value -= self.lr * g / acc.sqrt()
+
+
+class AdamOptimizer(_Optimizer):
+    def update(self, v, g, slots):
+        b1, b2, eps = self.kw.get("beta1", 0.9), self.kw.get("beta2", 0.999), self.kw.get("epsilon", 1e-8)
+        m, s = self.slot(slots, "m", v.value), self.slot(slots, "v", v.value)
+        m.mul_(b1).add_(g, alpha=1 - b1)
+        s.mul_(b2).addcmul_(g, g, value=1 - b2)
+        lr_t = self.lr * math.sqrt(1 - b2 ** self.t) / (1 - b1 ** self.t)
+        v.value -= lr_t * m / (s.sqrt() + eps)
+
+
+class AdadeltaOptimizer(_Optimizer):
+    def __init__(self, learning_rate=0.001, rho=0.95, epsilon=1e-8, **kw):
+        super().__init__(learning_rate, rho=rho, epsilon=epsilon, **kw)
+
+    def update(self, v, g, slots):
+        rho, eps = self.kw["rho"], self.kw["epsilon"]
+        acc, acc_up = self.slot(slots, "accum", v.value), self.slot(slots, "accum_update", v.value)
+        acc.mul_(rho).addcmul_(g, g, value=1 - rho)
+        up = (acc_up + eps).sqrt() / (acc + eps).sqrt() * g
+        acc_up.mul_(rho).addcmul_(up, up, value=1 - rho)
+        v.value -= self.lr * up
+
+
+train = types.SimpleNamespace(GradientDescentOptimizer=GradientDescentOptimizer, AdagradOptimizer=AdagradOptimizer,
+                              AdamOptimizer=AdamOptimizer, AdadeltaOptimizer=AdadeltaOptimizer)
+
+
+# ---- session ---------------------------------------------------------------------------------------------------
+class ConfigProto:
+    def __init__(self, **kw):
+        self.gpu_options = types.SimpleNamespace(allow_growth=False)
+
+
+class _Init:
+    def run(self, session=None, feed_dict=None):
+        return None
+
+
+def global_variables_initializer():
+    return _Init()
+
+
+class Session:
+    def __init__(self, config=None, **kw):
+        pass
+
+    def run(self, fetches, feed_dict=None):
+        env = {}
+        for ph, val in (feed_dict or {}).items():
+            a = np.asarray(val)
+            env[id(ph)] = torch.as_tensor(a, dtype=DT) if a.dtype.kind == "f" else torch.as_tensor(a)
+        flat, rebuild = _flatten(fetches)
+        values = [None] * len(flat)
+        for i, f in enumerate(flat):                     # forward values first: a fetched loss is the pre-update loss
+            if not isinstance(f, _TrainOp):
+                values[i] = f._eval(env).detach().numpy().copy()
+        for f in flat:
+            if isinstance(f, _TrainOp):
+                f.optimizer.current = f
+                f.optimizer._run(env)
+        for v in _VARIABLES:                              # fresh leaves for the next run's autograd graph
+            v.value = v.value.detach().requires_grad_(True)
+        return rebuild(values)
+
+    def close(self):
+        pass
+
+
+def _flatten(fetches):
+    if isinstance(fetches, dict):
+        keys = list(fetches)
+        return [fetches[k] for k in keys], lambda vals: dict(zip(keys, vals))
+    if isinstance(fetches, (list, tuple)):
+        return list(fetches), lambda vals: list(vals)
+    return [fetches], lambda vals: vals[0]

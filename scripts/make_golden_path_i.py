@@ -1,0 +1,209 @@
+"""Generates tests/golden/path_i_reference_graphs.npz by EXECUTING the reference's own graph-definition code for path
+(i) — `_define_variables`, `_define_embed_graph`, `_define_alignment_graph`, the mapping module, and
+`session.run([loss, optimizer], feed_dict)` — on oracle/tf1_shim.py (a TensorFlow-1 graph interpreter on torch float64;
+TensorFlow itself is not installable here).  Runs only where /root/reference exists; the fixture it writes is what
+travels.  Per case: the variables' start values, every run's feeds, the fetched loss of every run and all variables
+after the last run.
+
+    python scripts/make_golden_path_i.py
+"""
+import importlib
+import json
+import os
+import sys
+import types
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.dont_write_bytecode = True          # never write into /root/reference
+from oracle import tf1_shim  # noqa: E402
+
+REF_SRC = "/root/reference/src"
+OUT = os.path.join(ROOT, "tests", "golden", "path_i_reference_graphs.npz")
+N_ENT, N_REL = 40, 6
+
+
+class _Stub(types.ModuleType):
+    def __getattr__(self, key):
+        if key.startswith("__"):
+            raise AttributeError(key)
+        return lambda *a, **kw: None
+
+
+def _accept_np_matrix():
+    """The reference passes np.matrix to sklearn.preprocessing.normalize (initializers.py:49), which current scikit-learn
+    rejects: convert on the way in (environment compatibility only — the values are overwritten by the goldens)."""
+    from sklearn import preprocessing
+    if not getattr(preprocessing.normalize, "_oea_wrapped", False):
+        orig = preprocessing.normalize
+        wrapped = lambda X, *a, **kw: orig(np.asarray(X), *a, **kw)
+        wrapped._oea_wrapped = True
+        preprocessing.normalize = wrapped
+
+
+def import_reference(name):
+    """Import a reference module with `tensorflow` = the shim and absent third-party packages stubbed."""
+    sys.modules["tensorflow"] = tf1_shim
+    _accept_np_matrix()
+    if REF_SRC not in sys.path:
+        sys.path.insert(0, REF_SRC)
+    for _ in range(40):
+        try:
+            return importlib.import_module(name)
+        except ModuleNotFoundError as exc:
+            sys.modules[exc.name] = _Stub(exc.name)
+    raise RuntimeError("could not import " + name)
+
+
+BASE = dict(dim=12, init="normal", ent_l2_norm=True, rel_l2_norm=True, loss_norm="L2", learning_rate=0.01,
+            optimizer="Adagrad", batch_size=16, neg_triple_num=3, margin=1.5, pos_margin=0.01, neg_margin=2.0,
+            neg_margin_balance=0.2, alpha=5, loss="limited", path_parm=0.1, alpha_1=2.5, alpha_2=0.25, sub_epoch=1)
+
+# case → (module, class, args overrides, graph-definition calls, runs); a run is (kind, number of negatives per positive)
+CASES = {
+    "aligne_limited": ("openea.approaches.aligne", "AlignE", {}, ["_define_variables", "_define_embed_graph"],
+                       [("triple", 3), ("triple", 3)]),
+    "bootea": ("openea.approaches.bootea", "BootEA", {},
+               ["_define_variables", "_define_embed_graph", "_define_alignment_graph"],
+               [("triple", 3), ("align", 0), ("triple", 3), ("align", 0)]),
+    "mtranse": ("openea.approaches.mtranse", "MTransE", dict(init="unit"),
+                ["_define_variables", "_define_mapping_variables", "_define_embed_graph", "_define_mapping_graph"],
+                [("triple", 0), ("mapping", 0), ("triple", 0), ("mapping", 0)]),
+    "transe_margin_l1_sgd": ("openea.models.trans.transe", "TransE", dict(loss="margin-based", loss_norm="L1", optimizer="SGD"),
+                             ["_define_variables", "_define_embed_graph"], [("triple", 1), ("triple", 1)]),
+    "transe_margin_adam": ("openea.models.trans.transe", "TransE", dict(loss="margin-based", optimizer="Adam"),
+                           ["_define_variables", "_define_embed_graph"], [("triple", 1), ("triple", 1), ("triple", 1)]),
+    "transe_logistic_adadelta_nonorm": ("openea.models.trans.transe", "TransE",
+                                        dict(loss="logistic", optimizer="Adadelta", ent_l2_norm=False, rel_l2_norm=False,
+                                             learning_rate=1.0),
+                                        ["_define_variables", "_define_embed_graph"], [("triple", 2), ("triple", 2)]),
+    "transe_limited_d75": ("openea.models.trans.transe", "TransE", dict(dim=75), ["_define_variables", "_define_embed_graph"],
+                           [("triple", 3), ("triple", 3)]),
+    "transh": ("openea.models.trans.transh", "TransH", dict(loss="margin-based"), ["_define_variables", "_define_embed_graph"],
+               [("triple", 1), ("triple", 1)]),
+    "transd": ("openea.models.trans.transd", "TransD", dict(loss="margin-based"), ["_define_variables", "_define_embed_graph"],
+               [("triple", 1), ("triple", 1)]),
+    "distmult": ("openea.models.semantic.distmult", "DistMult", {}, ["_define_variables", "_define_embed_graph"],
+                 [("label", 2), ("label", 2)]),
+    "simple": ("openea.models.semantic.simple", "SimplE", {}, ["_define_variables", "_define_embed_graph"],
+               [("triple", 2), ("triple", 2)]),
+    "bootea_transh": ("openea.approaches.bootea_transh", "BootEA_TransH", {},
+                      ["_define_variables", "_define_embed_graph", "_define_alignment_graph"],
+                      [("triple", 3), ("align", 0), ("triple", 3)]),
+    "iptranse": ("openea.approaches.iptranse", "IPTransE", dict(neg_triple_num=1),
+                 ["_define_variables", "_define_embed_graph", "_define_alignment_graph"],
+                 [("ptranse", 1), ("ipt_align", 1), ("ptranse", 1)]),
+    "sea": ("openea.approaches.sea", "SEA", dict(loss="margin-based", optimizer="Adam", neg_triple_num=1),
+            ["_define_variables", "_define_embed_graph"], [("triple", 1), ("sea_map", 0), ("triple", 1), ("sea_map", 0)]),
+    "imuse": ("openea.approaches.imuse", "IMUSE", dict(loss="margin-based", optimizer="SGD", neg_triple_num=1),
+              ["_define_variables", "_define_embed_graph"], [("triple", 1), ("imuse_align", 0), ("triple", 1)]),
+}
+
+
+def triple_batch(rng, n, k):
+    pos = np.stack([rng.integers(0, N_ENT, n), rng.integers(0, N_REL, n), rng.integers(0, N_ENT, n)]).astype(np.int32)
+    if k == 0:
+        return pos, None
+    neg = np.repeat(pos, k, axis=1)
+    side = rng.random(n * k) < 0.5
+    neg[0, side] = rng.integers(0, N_ENT, int(side.sum()))
+    neg[2, ~side] = rng.integers(0, N_ENT, int((~side).sum()))
+    return pos, neg
+
+
+def make_run(kind, k, rng, model):
+    """→ (fetch attribute names, {placeholder attribute: array})."""
+    n = 16
+    if kind == "triple":
+        pos, neg = triple_batch(rng, n, k)
+        feed = {"pos_hs": pos[0], "pos_rs": pos[1], "pos_ts": pos[2]}
+        if neg is not None:
+            feed.update({"neg_hs": neg[0], "neg_rs": neg[1], "neg_ts": neg[2]})
+        return ("triple_loss", "triple_optimizer"), feed
+    if kind == "label":
+        pos, neg = triple_batch(rng, n, k)
+        both = np.concatenate([pos, neg], 1)
+        label = np.concatenate([np.ones(n), -np.ones(n * k)]).astype(np.float32)
+        return ("triple_loss", "triple_optimizer"), {"hs": both[0], "rs": both[1], "ts": both[2], "label": label}
+    if kind == "align":
+        pos, _ = triple_batch(rng, n, 0)
+        return ("alignment_loss", "alignment_optimizer"), {"new_h": pos[0], "new_r": pos[1], "new_t": pos[2]}
+    if kind == "mapping":
+        return ("mapping_loss", "mapping_optimizer"), {"seed_entities1": rng.integers(0, N_ENT, 9).astype(np.int32),
+                                                       "seed_entities2": rng.integers(0, N_ENT, 9).astype(np.int32)}
+    if kind == "ptranse":
+        pos, neg = triple_batch(rng, n, 1)
+        m = 11
+        path = rng.integers(0, N_REL, (3, m)).astype(np.int32)
+        npath = path.copy()
+        npath[2] = rng.integers(0, N_REL, m)
+        feed = {"pos_hs": pos[0], "pos_rs": pos[1], "pos_ts": pos[2], "neg_hs": neg[0], "neg_rs": neg[1], "neg_ts": neg[2],
+                "pos_rx": path[0], "pos_ry": path[1], "pos_r": path[2], "neg_rx": npath[0], "neg_ry": npath[1],
+                "neg_r": npath[2], "path_weight": rng.integers(1, 100, m).astype(np.float32)}
+        return ("train_loss", "optimizer"), feed
+    if kind == "ipt_align":
+        pos, neg = triple_batch(rng, n, 1)
+        return ("alignment_loss", "alignment_optimizer"), {
+            "new_ph": pos[0], "new_pr": pos[1], "new_pt": pos[2], "new_nh": neg[0], "new_nr": neg[1], "new_nt": neg[2],
+            "tr_weight": (rng.random(n) * 0.3 + 0.7).astype(np.float32)}
+    if kind == "sea_map":
+        ids = lambda m: rng.integers(0, N_ENT, m).astype(np.int32)
+        return ("mapping_loss", "mapping_optimizer"), {"labeled_entities1": ids(7), "labeled_entities2": ids(7),
+                                                       "unlabeled_entities1": ids(10), "unlabeled_entities2": ids(10)}
+    if kind == "imuse_align":
+        return ("align_loss", "align_optimizer"), {"aligned_ents1": rng.integers(0, N_ENT, 8).astype(np.int32),
+                                                   "aligned_ents2": rng.integers(0, N_ENT, 8).astype(np.int32)}
+    raise ValueError(kind)
+
+
+def generate():
+    out, meta = {}, {}
+    for case, (module, cls, overrides, defines, runs) in CASES.items():
+        tf1_shim.reset_default_graph()
+        mod = import_reference(module)
+        args = dict(BASE)
+        args.update(overrides)
+        model = getattr(mod, cls)()
+        model.args = types.SimpleNamespace(**args)
+        model.kgs = types.SimpleNamespace(entities_num=N_ENT, relations_num=N_REL)
+        for name in defines:
+            getattr(model, name)()
+        session = tf1_shim.Session()
+        rng = np.random.default_rng(sum(map(ord, case)))
+        variables = tf1_shim.trainable_variables()
+        names = [v.name for v in variables]
+        assert len(set(names)) == len(names), names
+        for v in variables:
+            shape = tuple(v.value.shape)
+            if v.name.startswith("mapping_matrix"):
+                start = np.linalg.qr(rng.standard_normal(shape))[0]
+            else:
+                start = rng.standard_normal(shape) * 2.0 / np.sqrt(shape[1])
+            start = start.astype(np.float32).astype(np.float64)          # exactly representable in the engine's fp32
+            v.assign_numpy(start)
+            out["%s/var0/%s" % (case, v.name)] = start
+        run_meta = []
+        for i, (kind, k) in enumerate(runs):
+            fetch, feed = make_run(kind, k, rng, model)
+            loss, _ = session.run([getattr(model, fetch[0]), getattr(model, fetch[1])],
+                                  feed_dict={getattr(model, key): val for key, val in feed.items()})
+            out["%s/run%d/loss" % (case, i)] = np.float64(loss)
+            for key, val in feed.items():
+                out["%s/run%d/feed/%s" % (case, i, key)] = val
+            run_meta.append({"kind": kind, "k": k, "fetch": list(fetch)})
+        for v in variables:
+            out["%s/var_final/%s" % (case, v.name)] = v.value.detach().numpy().copy()
+        meta[case] = {"class": module + "." + cls, "args": args, "defines": defines, "runs": run_meta, "variables": names}
+        print("%-34s %s  losses %s" % (case, names, ["%.6g" % float(out["%s/run%d/loss" % (case, i)]) for i in range(len(runs))]))
+    out["meta"] = np.frombuffer(json.dumps(meta, sort_keys=True).encode(), dtype=np.uint8)
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    np.savez_compressed(OUT, **out)
+    print("wrote", OUT, os.path.getsize(OUT), "bytes")
+
+
+if __name__ == "__main__":
+    if not os.path.isdir(REF_SRC):
+        sys.exit("the reference is not present: goldens can only be generated where /root/reference exists")
+    generate()

@@ -1,0 +1,174 @@
+"""Path (i) against the reference's OWN graph code.  tests/golden/path_i_reference_graphs.npz was produced by executing
+the reference's `_define_variables` / `_define_embed_graph` / `_define_alignment_graph` / mapping module and
+`session.run([loss, optimizer], feed_dict)` for 15 model classes on a TensorFlow-1 graph interpreter
+(oracle/tf1_shim.py, float64; scripts/make_golden_path_i.py).  Here the SAME classes of this package are built with the
+same hyper-parameters, started from the same variables, fed the same batches through the engine's entry points, and
+must reproduce every fetched loss and all variables after the last run:
+
+  * CPU: the kernels' sources on the warp emulator (the whole suite runs where no GPU exists);
+  * GPU (`-m gpu`): liboea.so.
+
+What this pins: which variables exist and which are normalised, every loss expression and its constants (e.g. that
+get_loss_func's limited loss ignores neg_margin_balance while AlignE's passes it), sums vs means, which optimiser
+instance owns which slots.  What it cannot pin offline: TensorFlow's op and optimiser semantics, restated in the shim.
+"""
+import json
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from tests.test_emu_triple_core import cpu_engine      # noqa: F401  (fixture: the engine over the emulated library)
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "path_i_reference_graphs.npz")
+G = np.load(GOLDEN)
+META = json.loads(bytes(G["meta"]).decode())
+
+ATTR = {"mapping_matrix": "mapping_mat", "mapping_matrix_1": "mapping_mat_1", "mapping_matrix_2": "mapping_mat_2"}
+
+
+def _class(path):
+    import importlib
+    module, name = path.rsplit(".", 1)
+    return getattr(importlib.import_module(module.replace("openea.", "openea_b200.", 1)), name)
+
+
+def _feed(case, i):
+    prefix = "%s/run%d/feed/" % (case, i)
+    return {k[len(prefix):]: G[k] for k in G.files if k.startswith(prefix)}
+
+
+def _hrt(feed, keys, device):
+    return torch.from_numpy(np.stack([feed[k] for k in keys]).astype(np.int32)).to(device)
+
+
+def replay(case, engine, device, monkeypatch):
+    from openea_b200.modules.base import initializers
+    meta = META[case]
+    monkeypatch.setattr(initializers, "_make", lambda values, norm, optimizer=None: engine.EmbeddingTable(
+        values, bool(norm), optimizer or initializers._DEFAULT_OPT, device))
+    model = _class(meta["class"])()
+    model.args = types.SimpleNamespace(**meta["args"])
+    model.kgs = types.SimpleNamespace(entities_num=40, relations_num=6)
+    for name in meta["defines"]:
+        if hasattr(model, name):
+            getattr(model, name)()
+    tables = {}
+    for name in meta["variables"]:
+        tab = getattr(model, ATTR.get(name, name))
+        start = G["%s/var0/%s" % (case, name)]
+        assert tab.weight[:, :tab.dim].shape == start.shape, name
+        tab.weight[:, :tab.dim] = torch.as_tensor(start, dtype=torch.float32, device=tab.weight.device)
+        tables[name] = tab
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
+    losses = []
+    for i, run in enumerate(meta["runs"]):
+        f = _feed(case, i)
+        kind = run["kind"]
+        if kind in ("triple", "label"):
+            tr = model.triple_trainer
+            if kind == "label":
+                n_pos = int((f["label"] > 0).sum())
+                both = np.stack([f["hs"], f["rs"], f["ts"]]).astype(np.int32)
+                pos, neg = dev(both[:, :n_pos]), dev(both[:, n_pos:])
+            else:
+                pos = _hrt(f, ("pos_hs", "pos_rs", "pos_ts"), device)
+                neg = _hrt(f, ("neg_hs", "neg_rs", "neg_ts"), device) if "neg_hs" in f else None
+            tr.score_fed(pos, neg)
+            tr.apply()
+            losses.append(tr.read_loss())
+        elif kind == "align":
+            tr = model.alignment_trainer
+            tr.score_fed(_hrt(f, ("new_h", "new_r", "new_t"), device))
+            tr.apply()
+            losses.append(tr.read_loss())
+        elif kind == "mapping":
+            losses.append(model.mapping_trainer.step(f["seed_entities1"], f["seed_entities2"]))
+        elif kind == "ptranse":
+            tr = model.triple_trainer
+            tr.score_fed(_hrt(f, ("pos_hs", "pos_rs", "pos_ts"), device), _hrt(f, ("neg_hs", "neg_rs", "neg_ts"), device))
+            tr.score_margin_weighted(_hrt(f, ("pos_rx", "pos_ry", "pos_r"), device), _hrt(f, ("neg_rx", "neg_ry", "neg_r"), device),
+                                     dev(f["path_weight"]), reciprocal=True, scale=model.args.path_parm, paths=True)
+            tr.apply()
+            losses.append(tr.read_loss())
+        elif kind == "ipt_align":
+            tr = model.alignment_trainer
+            tr.score_margin_weighted(_hrt(f, ("new_ph", "new_pr", "new_pt"), device), _hrt(f, ("new_nh", "new_nr", "new_nt"), device),
+                                     dev(f["tr_weight"]))
+            tr.apply()
+            losses.append(tr.read_loss())
+        elif kind == "sea_map":
+            model.mapping_trainer.step(f["labeled_entities1"], f["labeled_entities2"], f["unlabeled_entities1"],
+                                       f["unlabeled_entities2"])
+            losses.append(model.mapping_trainer.read_loss())
+        elif kind == "imuse_align":
+            tr = model.alignment_trainer
+            tr.score_pairs(f["aligned_ents1"], f["aligned_ents2"])
+            tr.apply()
+            losses.append(tr.read_loss())
+        else:
+            raise AssertionError(kind)
+    for i, got in enumerate(losses):
+        assert got == pytest.approx(float(G["%s/run%d/loss" % (case, i)]), rel=2e-4), (case, i, meta["runs"][i])
+    for name, tab in tables.items():
+        want = G["%s/var_final/%s" % (case, name)]
+        start = G["%s/var0/%s" % (case, name)]
+        got = tab.raw().cpu().numpy()
+        assert np.abs(want - start).max() > 0, name                 # every variable of the case was trained
+        # compare the MOVEMENT too: a wrong update direction hides behind the start values at rtol alone
+        np.testing.assert_allclose(got - start, want - start, rtol=5e-3, atol=3e-6 + 2e-3 * np.abs(want - start).max(),
+                                   err_msg="%s: %s" % (case, name))
+        np.testing.assert_allclose(got, want, rtol=2e-4, atol=5e-6, err_msg="%s: %s" % (case, name))
+
+
+@pytest.mark.parametrize("case", sorted(META))
+def test_engine_on_the_emulator_reproduces_the_reference_graph(cpu_engine, monkeypatch, case):
+    from openea_b200.approaches import imuse, iptranse, sea
+    for mod in (imuse, iptranse, sea):
+        monkeypatch.setattr(mod, "load_session", lambda: None, raising=False)
+    if case == "mtranse":
+        pytest.skip("the MTransE mapping kernel needs real block barriers (GPU only)")
+    replay(case, cpu_engine, "cpu", monkeypatch)
+
+
+@pytest.mark.gpu
+@pytest.mark.first_hw_run
+@pytest.mark.parametrize("case", sorted(META))
+def test_engine_on_the_gpu_reproduces_the_reference_graph(cuda_device, monkeypatch, case):
+    from openea_b200 import engine
+    replay(case, engine, "cuda", monkeypatch)
+
+
+def test_golden_file_covers_the_expected_cases():
+    assert set(META) >= {"aligne_limited", "bootea", "mtranse", "transe_margin_adam", "transh", "transd", "distmult",
+                         "simple", "bootea_transh", "iptranse", "sea", "imuse"}
+    for case, meta in META.items():
+        assert meta["class"].startswith("openea.") and len(meta["runs"]) >= 2
+
+
+ORACLE_CASES = {     # case → (loss, loss_norm, normalised?, optimiser, kwargs of the C oracle's step)
+    "aligne_limited": ("limited", "L2", True, "Adagrad", dict(margin=0.01, neg_margin=2.0, balance=0.2)),
+    "transe_limited_d75": ("limited", "L2", True, "Adagrad", dict(margin=0.01, neg_margin=2.0, balance=1.0)),
+    "transe_margin_l1_sgd": ("margin-based", "L1", True, "SGD", dict(margin=1.5)),
+    "transe_margin_adam": ("margin-based", "L2", True, "Adam", dict(margin=1.5)),
+}
+
+
+@pytest.mark.parametrize("case", sorted(ORACLE_CASES))
+def test_c_oracle_reproduces_the_reference_graph(case):
+    """The CPU oracle (oracle/oea_oracle.c, what the GPU parity tests and bench.py's CPU leg use) is itself pinned to the
+    goldens: losses of every run and the variables after the last one."""
+    from oracle import triple as orc
+    loss, loss_norm, norm, opt, kw = ORACLE_CASES[case]
+    meta = META[case]
+    st = orc.DenseState(G[case + "/var0/ent_embeds"].astype(np.float32), G[case + "/var0/rel_embeds"].astype(np.float32), opt)
+    for i, run in enumerate(meta["runs"]):
+        f = _feed(case, i)
+        pos = np.stack([f["pos_hs"], f["pos_rs"], f["pos_ts"]]).astype(np.int32)
+        neg = np.stack([f["neg_hs"], f["neg_rs"], f["neg_ts"]]).astype(np.int32)
+        got = orc.step(st, pos, neg, loss, loss_norm, norm, norm, meta["args"]["learning_rate"], **kw)
+        assert got == pytest.approx(float(G["%s/run%d/loss" % (case, i)]), rel=2e-4), (case, i)
+    np.testing.assert_allclose(st.ent, G[case + "/var_final/ent_embeds"], rtol=2e-4, atol=5e-6)
+    np.testing.assert_allclose(st.rel, G[case + "/var_final/rel_embeds"], rtol=2e-4, atol=5e-6)
