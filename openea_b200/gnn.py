@@ -80,7 +80,7 @@ def spmm(A, X, out=None, relu=False, mask_src=None, beta=0.0, vals=None):
     """Y = A·X (fp32, X row-major with X.shape[1] % 4 == 0), optional fused relu / relu-backward mask.
     `vals` [nnz] replaces A's values (same pattern), e.g. attention coefficients."""
     lib = L.load()
-    assert X.is_cuda and X.dtype == torch.float32 and X.stride(1) == 1
+    assert X.device == A.rowptr.device and X.dtype == torch.float32 and X.stride(1) == 1
     d = X.shape[1]
     if out is None:
         out = torch.empty(A.shape[0], d, dtype=torch.float32, device=X.device)

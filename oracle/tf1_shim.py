@@ -33,6 +33,7 @@ _VARIABLES = []
 
 def reset_default_graph():
     _VARIABLES.clear()
+    _NAMED.clear()
 
 
 def _wrap(x):
@@ -42,7 +43,7 @@ def _wrap(x):
 
 
 def _const(x):
-    if isinstance(x, torch.Tensor):
+    if isinstance(x, torch.Tensor) or type(x).__name__ == "SparseValue":
         return x
     a = np.asarray(x)
     return torch.as_tensor(a, dtype=DT if a.dtype.kind == "f" else None)
@@ -93,8 +94,15 @@ class Placeholder(Tensor):
 class Variable(Tensor):
     def __init__(self, initial_value, name=None, dtype=None, trainable=True):
         super().__init__(None, (), name or "Variable")
+        if isinstance(initial_value, Tensor):              # tf.Variable(tf.truncated_normal(...)): evaluate the initialiser
+            initial_value = initial_value._eval({}).detach().numpy()
         self.value = torch.tensor(np.asarray(initial_value, dtype=np.float64), dtype=DT, requires_grad=True)
         self.slots = {}
+        taken = {v.name for v in _VARIABLES}
+        base, n = self.name, 0
+        while self.name in taken:                          # TF uniquifies: Variable, Variable_1, …
+            n += 1
+            self.name = "%s_%d" % (base, n)
         if trainable:
             _VARIABLES.append(self)
 
@@ -106,8 +114,95 @@ class Variable(Tensor):
         self.slots = {}
 
 
+_NAMED = {}           # "name:0" → placeholder (tf.get_default_graph().get_tensor_by_name, string keys of a feed_dict)
+
+
 def placeholder(dtype, shape=None, name=None):
-    return Placeholder(dtype, shape, name)
+    ph = Placeholder(dtype, shape, name)
+    if name is not None:
+        _NAMED[name + ":0"] = ph
+    return ph
+
+
+class _DefaultPlaceholder(Placeholder):
+    def __init__(self, default, shape=None, name=None):
+        super().__init__(None, shape, name)
+        self.default = default
+
+    def _eval(self, env):
+        return env[id(self)] if id(self) in env else _const(self.default)
+
+
+def placeholder_with_default(input, shape=None, name=None):       # noqa: A002
+    return _DefaultPlaceholder(input, shape, name)
+
+
+class SparseValue:
+    """What a sparse placeholder is fed with / a tf.SparseTensor holds: COO indices [nnz, 2], values, dense shape."""
+
+    def __init__(self, indices, values, dense_shape):
+        self.indices = torch.as_tensor(np.asarray(indices)).long().reshape(-1, 2)
+        self.values = values if isinstance(values, torch.Tensor) else torch.as_tensor(np.asarray(values), dtype=DT)
+        self.shape = tuple(int(x) for x in dense_shape)
+
+
+def sparse_placeholder(dtype, shape=None, name=None):
+    return Placeholder(dtype, shape, name or "sparse_placeholder")
+
+
+def sparse_tensor_dense_matmul(sp_a, b, name=None):
+    def f(a, dense):
+        out = torch.zeros(a.shape[0], dense.shape[1], dtype=DT)
+        return out.index_add(0, a.indices[:, 0], a.values[:, None] * dense[a.indices[:, 1]])
+    return Tensor(f, (_wrap(sp_a), _wrap(b)), "sparse_tensor_dense_matmul")
+
+
+def add_n(inputs, name=None):
+    out = _wrap(inputs[0])
+    for x in inputs[1:]:
+        out = out + x
+    return out
+
+
+def _random(kind):
+    def op(shape, mean=0.0, stddev=1.0, minval=0.0, maxval=1.0, dtype=None, seed=None, name=None):
+        if kind == "normal":
+            return _wrap(_truncated_normal(stddev=stddev, mean=mean)(list(shape)))
+        return _wrap(_random_uniform(minval=minval, maxval=maxval)(list(shape)))
+    return op
+
+
+def truncated_normal(shape, mean=0.0, stddev=1.0, dtype=None, seed=None, name=None):
+    return _wrap(_truncated_normal(stddev=stddev, mean=mean)(list(shape)))
+
+
+def random_uniform(shape, minval=0.0, maxval=None, dtype=None, seed=None, name=None):
+    return _wrap(_random_uniform(minval=minval, maxval=maxval)(list(shape)))
+
+
+def zeros(shape, dtype=None, name=None): return _wrap(np.zeros(shape, dtype=np.float64))
+def ones(shape, dtype=None, name=None): return _wrap(np.ones(shape, dtype=np.float64))
+
+
+class GraphKeys:
+    GLOBAL_VARIABLES = "variables"
+    TRAINABLE_VARIABLES = "trainable_variables"
+
+
+def get_collection(key, scope=None):
+    return list(_VARIABLES)
+
+
+class _Graph:
+    def get_tensor_by_name(self, name):
+        return _NAMED[name]                  # KeyError when absent, like TF
+
+
+def get_default_graph():
+    return _Graph()
+
+
+summary = types.SimpleNamespace(histogram=lambda *a, **kw: None, scalar=lambda *a, **kw: None)
 
 
 def constant(value, dtype=None, name=None, shape=None):
@@ -193,7 +288,21 @@ def _embedding_lookup(params, ids, name=None):
     return Tensor(lambda p, i: p[torch.as_tensor(i).long()], (_wrap(params), _wrap(ids)), "embedding_lookup")
 
 
+def _dropout(x, keep_prob=None, rate=None, noise_shape=None, seed=None, name=None):
+    """Every shipped configuration trains with dropout 0: only the identity is supported (anything else is random)."""
+    def f(a, kp):
+        assert float(kp) == 1.0, "dropout with keep_prob != 1 is random and cannot be put in a golden"
+        return a
+    return Tensor(f, (_wrap(x), _wrap(1.0 - rate if keep_prob is None else keep_prob)), "dropout")
+
+
+def _leaky_relu(x, alpha=0.2, name=None):
+    return Tensor(lambda a: torch.where(a > 0, a, alpha * a), (_wrap(x),), "leaky_relu")
+
+
 nn = types.SimpleNamespace(
+    dropout=_dropout, leaky_relu=_leaky_relu,
+    softmax=lambda x, axis=-1, name=None: Tensor(lambda a: torch.softmax(a, dim=axis), (_wrap(x),), "softmax"),
     embedding_lookup=_embedding_lookup, l2_normalize=_l2_normalize,
     relu=_unary(torch.relu, "relu"), softplus=_unary(torch.nn.functional.softplus, "softplus"),
     sigmoid=sigmoid, tanh=tanh)
@@ -362,6 +471,11 @@ class Session:
     def run(self, fetches, feed_dict=None):
         env = {}
         for ph, val in (feed_dict or {}).items():
+            if isinstance(ph, str):
+                ph = _NAMED[ph]
+            if isinstance(val, tuple) and len(val) == 3 and np.ndim(val[0]) == 2:     # (coords, values, shape)
+                env[id(ph)] = SparseValue(*val)
+                continue
             a = np.asarray(val)
             env[id(ph)] = torch.as_tensor(a, dtype=DT) if a.dtype.kind == "f" else torch.as_tensor(a)
         flat, rebuild = _flatten(fetches)

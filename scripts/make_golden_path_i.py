@@ -203,7 +203,60 @@ def generate():
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
 
 
+def generate_gcn_align():
+    """Path (ii), GCN-Align: the reference's GCN_Align_Unit (gcn_align.py:498-539) for the structure branch (featureless,
+    l2-normalised entity table) and the attribute branch (sparse features · weights), its align_loss and its
+    GradientDescentOptimizer, fed through GCN_Utils.construct_feed_dict exactly as train_embeddings does (:737-757).
+    → tests/golden/path_ii_gcn_align.npz"""
+    import scipy.sparse as sp
+    mod = import_reference("openea.approaches.gcn_align")
+    tf = tf1_shim
+    rng = np.random.default_rng(11)
+    n, n_feat, dim, t, k = 30, 9, 8, 7, 3
+    a = sp.random(n, n, density=0.12, random_state=3, format="coo")
+    a = a + a.T + sp.eye(n)
+    deg = np.asarray(a.sum(1)).ravel()
+    a = sp.coo_matrix(sp.diags(deg ** -0.5) @ a @ sp.diags(deg ** -0.5))
+    support = [(np.vstack((a.row, a.col)).transpose(), a.data.astype(np.float32).astype(np.float64), a.shape)]
+    feat = sp.coo_matrix((rng.random((n, n_feat)) < 0.3).astype(np.float64))
+    features = (np.vstack((feat.row, feat.col)).transpose(), feat.data, feat.shape)
+    ill = np.stack([rng.permutation(n)[:t], rng.permutation(n)[:t]], 1)
+    args = types.SimpleNamespace(learning_rate=8.0, gamma=3.0, neg_triple_num=k, dropout=0.0, support_number=1)
+    out = {"support/coords": support[0][0], "support/values": support[0][1], "features/coords": features[0],
+           "features/values": features[1], "ill": ill,
+           "dims": np.array([n, n_feat, dim, t, k]), "gamma": np.float64(args.gamma), "lr": np.float64(args.learning_rate)}
+    for branch, featureless in (("se", True), ("ae", False)):
+        tf.reset_default_graph()
+        ph = {"support": [tf.sparse_placeholder(tf.float32)],
+              "features": tf.placeholder(tf.float32) if featureless else tf.sparse_placeholder(tf.float32),
+              "dropout": tf.placeholder_with_default(0., shape=()),
+              "num_features_nonzero": tf.placeholder_with_default(0, shape=())}
+        model = mod.GCN_Align_Unit(args, ph, input_dim=n if featureless else n_feat, output_dim=dim, ILL=ill,
+                                   sparse_inputs=not featureless, featureless=featureless, logging=False)
+        (var,) = tf.trainable_variables()
+        start = (rng.standard_normal(tuple(var.value.shape)) * 0.5).astype(np.float32).astype(np.float64)
+        var.assign_numpy(start)
+        out[branch + "/var0"] = start
+        session = tf.Session()
+        for step in range(3):
+            neg = {key: rng.integers(0, n, t * k) for key in ("neg_left", "neg_right", "neg2_left", "neg2_right")}
+            feed = mod.GCN_Utils.construct_feed_dict(1. if featureless else features, support, ph)
+            feed.update({ph["dropout"]: args.dropout})
+            feed.update({key + ":0": val for key, val in neg.items()})
+            loss, _ = session.run([model.loss, model.opt_op], feed_dict=feed)
+            out["%s/run%d/loss" % (branch, step)] = np.float64(loss)
+            for key, val in neg.items():
+                out["%s/run%d/%s" % (branch, step, key)] = val.astype(np.int32)
+        out[branch + "/var_final"] = var.value.detach().numpy().copy()
+        out[branch + "/outputs_final"] = session.run(model.outputs, feed_dict=feed)
+        print("gcn_align %s: losses %s" % (branch, ["%.6g" % float(out["%s/run%d/loss" % (branch, i)]) for i in range(3)]))
+    path = os.path.join(ROOT, "tests", "golden", "path_ii_gcn_align.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF_SRC):
         sys.exit("the reference is not present: goldens can only be generated where /root/reference exists")
     generate()
+    generate_gcn_align()

@@ -172,3 +172,45 @@ def test_c_oracle_reproduces_the_reference_graph(case):
         assert got == pytest.approx(float(G["%s/run%d/loss" % (case, i)]), rel=2e-4), (case, i)
     np.testing.assert_allclose(st.ent, G[case + "/var_final/ent_embeds"], rtol=2e-4, atol=5e-6)
     np.testing.assert_allclose(st.rel, G[case + "/var_final/rel_embeds"], rtol=2e-4, atol=5e-6)
+
+
+# ---- path (ii): GCN-Align's unit, from the reference's GCN_Align_Unit / align_loss / construct_feed_dict ------------
+GCN = np.load(os.path.join(os.path.dirname(GOLDEN), "path_ii_gcn_align.npz"))
+
+
+def replay_gcn_align(engine, device, branch):
+    import scipy.sparse as sp
+    from openea_b200 import gnn
+    from openea_b200.approaches.gcn_align import GCNAlignUnit
+    n, n_feat, dim, t, k = (int(x) for x in GCN["dims"])
+    coo = lambda name, shape: sp.coo_matrix((GCN[name + "/values"], (GCN[name + "/coords"][:, 0], GCN[name + "/coords"][:, 1])),
+                                            shape=shape)
+    support = gnn.DeviceCsr(coo("support", (n, n)), device)
+    features = None if branch == "se" else gnn.DeviceCsr(coo("features", (n, n_feat)), device)
+    table = engine.EmbeddingTable(GCN[branch + "/var0"].astype(np.float32), True, "SGD", device)
+    unit = GCNAlignUnit(support, table, features, GCN["ill"], float(GCN["gamma"]), k, float(GCN["lr"]))
+    for step in range(3):
+        neg = [torch.as_tensor(GCN["%s/run%d/%s" % (branch, step, key)], dtype=torch.int32, device=device)
+               for key in ("neg_left", "neg_right", "neg2_left", "neg2_right")]
+        loss = float(unit.train_step(*neg).item())
+        assert loss == pytest.approx(float(GCN["%s/run%d/loss" % (branch, step)]), rel=2e-4), (branch, step)
+    want, start = GCN[branch + "/var_final"], GCN[branch + "/var0"]
+    got = table.raw().cpu().numpy()
+    np.testing.assert_allclose(got - start, want - start, rtol=5e-3, atol=2e-3 * np.abs(want - start).max())
+    np.testing.assert_allclose(unit.forward()[:, :dim].cpu().numpy(), GCN[branch + "/outputs_final"], rtol=5e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("branch", ["se", "ae"])
+def test_gcn_align_unit_on_the_emulator_reproduces_the_reference_unit(cpu_engine, monkeypatch, branch):
+    import ctypes as C
+    from openea_b200 import gnn
+    monkeypatch.setattr(gnn, "_stream_ptr", lambda: C.c_void_p(0))
+    replay_gcn_align(cpu_engine, "cpu", branch)
+
+
+@pytest.mark.gpu
+@pytest.mark.first_hw_run
+@pytest.mark.parametrize("branch", ["se", "ae"])
+def test_gcn_align_unit_on_the_gpu_reproduces_the_reference_unit(cuda_device, branch):
+    from openea_b200 import engine
+    replay_gcn_align(engine, "cuda", branch)
