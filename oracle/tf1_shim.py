@@ -34,6 +34,7 @@ _VARIABLES = []
 def reset_default_graph():
     _VARIABLES.clear()
     _NAMED.clear()
+    _LAYER_COUNT.clear()
 
 
 def _wrap(x):
@@ -201,6 +202,65 @@ class _Graph:
 def get_default_graph():
     return _Graph()
 
+
+class SparseTensor(Tensor):
+    """tf.SparseTensor(indices, values, dense_shape): `values` may be a graph node; .indices / .values / .dense_shape
+    give back what was passed (the reference uses r_mat.values as lookup ids, rdgcn.py:205)."""
+
+    def __init__(self, indices, values, dense_shape):
+        self.indices, self.values, self.dense_shape = indices, values, dense_shape
+        super().__init__(lambda v: SparseValue(np.asarray(indices), v if v.dtype.is_floating_point else v.to(DT), dense_shape),
+                         (_wrap(values),), "SparseTensor")
+
+
+def sparse_softmax(sp_input, name=None):
+    """Softmax over the stored entries of every row (entries, not coordinates: duplicates of one (i, j) are separate
+    entries).  ASSUMPTION: rows are taken whole — TF documents the op for canonically ordered input; the reference
+    passes triples in list order (rdgcn.py:20-42)."""
+    def f(a):
+        row = a.indices[:, 0]
+        mx = torch.full((a.shape[0],), -float("inf"), dtype=DT).scatter_reduce(0, row, a.values, "amax")
+        ex = torch.exp(a.values - mx[row])
+        den = torch.zeros(a.shape[0], dtype=DT).index_add(0, row, ex)
+        return SparseValue(a.indices, ex / den[row], a.shape)
+    return Tensor(f, (_wrap(sp_input),), "sparse_softmax")
+
+
+def expand_dims(x, axis, name=None):
+    return Tensor(lambda a: a.unsqueeze(axis), (_wrap(x),), "expand_dims")
+
+
+def transpose(x, perm=None, name=None):
+    return Tensor(lambda a: a.t() if perm is None else a.permute(*perm), (_wrap(x),), "transpose")
+
+
+def concat(values, axis, name=None):
+    return Tensor(lambda *v: torch.cat(v, dim=axis), tuple(_wrap(v) for v in values), "concat")
+
+
+_LAYER_COUNT = {}
+
+
+def _conv1d(inputs, filters, kernel_size, use_bias=True, **kw):
+    """tf.layers.conv1d with kernel_size 1 on [1, n, c]: a dense map with its own glorot-uniform kernel [1, c, filters]
+    and zero bias, variables named conv1d[_i]/kernel, conv1d[_i]/bias in creation order.  The channel count is read by
+    evaluating the input once at graph-construction time (it must not depend on a placeholder)."""
+    assert kernel_size == 1
+    x = _wrap(inputs)
+    c = int(x._eval({}).shape[-1])
+    idx = _LAYER_COUNT.get("conv1d", 0)
+    _LAYER_COUNT["conv1d"] = idx + 1
+    scope = "conv1d" if idx == 0 else "conv1d_%d" % idx
+    kernel = Variable(_xavier(uniform=True)([c, filters]).reshape(1, c, filters), name=scope + "/kernel")
+    if not use_bias:
+        return Tensor(lambda a, k: a @ k[0], (x, kernel), scope)
+    bias = Variable(np.zeros(filters), name=scope + "/bias")
+    return Tensor(lambda a, k, b: a @ k[0] + b, (x, kernel, bias), scope)
+
+
+layers = types.SimpleNamespace(conv1d=_conv1d)
+keras = types.SimpleNamespace(activations=types.SimpleNamespace(
+    get=lambda name: {"relu": nn.relu, "tanh": tanh, None: None}[name], relu=lambda x: nn.relu(x), tanh=lambda x: tanh(x)))
 
 summary = types.SimpleNamespace(histogram=lambda *a, **kw: None, scalar=lambda *a, **kw: None)
 

@@ -255,8 +255,69 @@ def generate_gcn_align():
     print("wrote", path, os.path.getsize(path), "bytes")
 
 
+RDGCN_NAMES = ["X0", "self.W", "self.f1.w", "self.f1.b", "self.f2.w", "self.f2.b", "sp1.w", "sp1.b", "dual.W", "dual.b",
+               "dual.f1.w", "dual.f1.b", "dual.f2.w", "dual.f2.b", "sp2.w", "sp2.b", "diag1.w", "hw1.W", "hw1.b",
+               "diag2.w", "hw2.W", "hw2.b"]       # the reference's variables in creation order (rdgcn.py:317-338)
+
+
+def generate_rdgcn():
+    """Path (ii), RDGCN: the reference's Layer.build() (rdgcn.py:160-338: dual relation graph, self / dual attention,
+    per-edge relation attention, diagonal GCN layers, highway gates, L1 alignment loss) and its AdamOptimizer.
+    → tests/golden/path_ii_rdgcn.npz"""
+    mod = import_reference("openea.approaches.rdgcn")
+    tf = tf1_shim
+    rng = np.random.default_rng(21)
+    n_ent, n_rel, dim, t, k = 24, 4, 8, 5, 3
+    tri1 = np.unique(np.stack([rng.integers(0, 12, 30), rng.integers(0, n_rel, 30), rng.integers(0, 12, 30)], 1), axis=0)
+    tri2 = np.unique(np.stack([rng.integers(12, 24, 30), rng.integers(0, n_rel, 30), rng.integers(12, 24, 30)], 1), axis=0)
+    as_list = lambda a: [tuple(int(v) for v in row) for row in a]
+    links = [(int(a), int(b)) for a, b in zip(rng.permutation(12)[:t], 12 + rng.permutation(12)[:t])]
+    kgs = types.SimpleNamespace(train_links=links, relations_num=n_rel, entities_num=n_ent,
+                                kg1=types.SimpleNamespace(relation_triples_list=as_list(tri1)),
+                                kg2=types.SimpleNamespace(relation_triples_list=as_list(tri2)))
+    args = types.SimpleNamespace(dim=dim, dropout=0.0, gamma=1.0, neg_triple_num=k, alpha=0.1, beta=0.3, learning_rate=0.01)
+    embedding = (rng.standard_normal((n_ent, dim)) * 0.5).astype(np.float32)
+    layer = mod.Layer(args, kgs, embedding)
+    output, loss = layer.build()
+    train_op = tf.train.AdamOptimizer(args.learning_rate).minimize(loss)
+    variables = tf.trainable_variables()
+    assert len(variables) == len(RDGCN_NAMES), [v.name for v in variables]
+    out = {"triples1": tri1.astype(np.int32), "triples2": tri2.astype(np.int32), "links": np.asarray(links, dtype=np.int32),
+           "dims": np.array([n_ent, n_rel, dim, t, k]), "alpha": np.float64(args.alpha), "beta": np.float64(args.beta),
+           "gamma": np.float64(args.gamma), "lr": np.float64(args.learning_rate)}
+    for v, name in zip(variables, RDGCN_NAMES):
+        shape = tuple(v.value.shape)
+        if name.startswith("diag"):
+            start = 1.0 + 0.1 * rng.standard_normal(shape)
+        elif name.endswith(".b"):
+            start = 0.05 * rng.standard_normal(shape)
+        elif name == "X0":
+            start = embedding
+        else:
+            start = rng.standard_normal(shape) * 0.4
+        start = np.asarray(start, dtype=np.float32).astype(np.float64)
+        v.assign_numpy(start)
+        out["var0/" + name] = start
+    session = tf.Session()
+    for step in range(3):
+        feed = {key + ":0": rng.integers(0, n_ent, t * k) for key in ("neg_left", "neg_right", "neg2_left", "neg2_right")}
+        val, _ = session.run([loss, train_op], feed_dict=feed)
+        out["run%d/loss" % step] = np.float64(val)
+        for key, ids in feed.items():
+            out["run%d/%s" % (step, key[:-2])] = ids.astype(np.int32)
+    for v, name in zip(variables, RDGCN_NAMES):
+        out["var_final/" + name] = v.value.detach().numpy().copy()
+    out["outputs_final"] = session.run(output, feed_dict=feed)
+    print("rdgcn: losses %s" % ["%.6g" % float(out["run%d/loss" % i]) for i in range(3)],
+          [tuple(v.value.shape) for v in variables])
+    path = os.path.join(ROOT, "tests", "golden", "path_ii_rdgcn.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF_SRC):
         sys.exit("the reference is not present: goldens can only be generated where /root/reference exists")
     generate()
     generate_gcn_align()
+    generate_rdgcn()

@@ -214,3 +214,77 @@ def test_gcn_align_unit_on_the_emulator_reproduces_the_reference_unit(cpu_engine
 def test_gcn_align_unit_on_the_gpu_reproduces_the_reference_unit(cuda_device, branch):
     from openea_b200 import engine
     replay_gcn_align(engine, "cuda", branch)
+
+
+# ---- path (ii): RDGCN's whole layer, from the reference's Layer.build() + AdamOptimizer ---------------------------------
+RD = np.load(os.path.join(os.path.dirname(GOLDEN), "path_ii_rdgcn.npz"))
+RD_NAMES = sorted(k[len("var0/"):] for k in RD.files if k.startswith("var0/"))
+
+
+def _rdgcn_to_param(name, ref):
+    """Reference variable → this package's parameter layout (approaches/rdgcn.py: conv kernels without the leading 1,
+    1-filter kernels and their biases replicated to 4 columns for the 16-byte row optimiser, vectors as [1, d])."""
+    a = np.asarray(ref, dtype=np.float32)
+    if a.ndim == 3:
+        a = a[0]
+    if a.ndim == 1:
+        a = a[None, :]
+    if name.endswith((".f1.w", ".f2.w")) or name in ("sp1.w", "sp2.w"):
+        a = np.repeat(a, 4, axis=1)
+    if name.endswith((".f1.b", ".f2.b")) or name in ("sp1.b", "sp2.b"):
+        a = np.repeat(a, 4, axis=1)
+    return a
+
+
+def replay_rdgcn(device):
+    from openea_b200.approaches.alinet import DenseAdam
+    from openea_b200.approaches.rdgcn import RDGCNLayer
+    n_ent, n_rel, dim, t, k = (int(x) for x in RD["dims"])
+    as_list = lambda a: [tuple(int(v) for v in row) for row in a]
+    kgs = types.SimpleNamespace(train_links=as_list(RD["links"]), relations_num=n_rel, entities_num=n_ent,
+                                kg1=types.SimpleNamespace(relation_triples_list=as_list(RD["triples1"])),
+                                kg2=types.SimpleNamespace(relation_triples_list=as_list(RD["triples2"])))
+    args = types.SimpleNamespace(dim=dim, dropout=0.0, gamma=float(RD["gamma"]), neg_triple_num=k, alpha=float(RD["alpha"]),
+                                 beta=float(RD["beta"]), learning_rate=float(RD["lr"]))
+    layer = RDGCNLayer(args, kgs, RD["var0/X0"].astype(np.float32), torch.device(device))
+    assert sorted(layer.params) == RD_NAMES
+    with torch.no_grad():
+        for name in RD_NAMES:
+            want = _rdgcn_to_param(name, RD["var0/" + name])
+            assert tuple(layer.params[name].shape) == want.shape, (name, tuple(layer.params[name].shape), want.shape)
+            layer.params[name].copy_(torch.as_tensor(want, device=device))
+    opt = DenseAdam(list(layer.params.values()), args.learning_rate)
+    for step in range(3):
+        negs = tuple(torch.as_tensor(RD["run%d/%s" % (step, key)], dtype=torch.int32, device=device)
+                     for key in ("neg_left", "neg_right", "neg2_left", "neg2_right"))
+        loss = layer.loss(layer.forward(), negs)
+        loss.backward()
+        opt.step()
+        assert float(loss.detach()) == pytest.approx(float(RD["run%d/loss" % step]), rel=2e-4), step
+    for name in RD_NAMES:
+        start, want = _rdgcn_to_param(name, RD["var0/" + name]), _rdgcn_to_param(name, RD["var_final/" + name])
+        got = layer.params[name].detach().cpu().numpy()
+        col = slice(0, 1) if want.shape[1] == 4 and name != "X0" and "." in name and name.split(".")[-1] in ("w", "b") \
+            and (name.startswith(("sp", "self.f", "dual.f"))) else slice(None)
+        move = np.abs(want - start).max()
+        if move == 0.0:
+            # a bias added to every logit of a softmax row has a mathematically zero gradient (sp1.b / sp2.b): float64
+            # keeps it at exactly 0, in fp32 Adam turns the rounding noise of that gradient into a tiny drift
+            assert np.abs(got - start).max() < 1e-4, name
+            continue
+        np.testing.assert_allclose((got - start)[:, col], (want - start)[:, col], rtol=2e-2, atol=3e-2 * move + 1e-7, err_msg=name)
+    with torch.no_grad():
+        np.testing.assert_allclose(layer.forward()[:, :dim].cpu().numpy(), RD["outputs_final"], rtol=2e-3, atol=2e-5)
+
+
+def test_rdgcn_layer_on_the_emulator_reproduces_the_reference_layer(cpu_engine, monkeypatch):
+    import ctypes as C
+    from openea_b200 import gnn
+    monkeypatch.setattr(gnn, "_stream_ptr", lambda: C.c_void_p(0))
+    replay_rdgcn("cpu")
+
+
+@pytest.mark.gpu
+@pytest.mark.first_hw_run
+def test_rdgcn_layer_on_the_gpu_reproduces_the_reference_layer(cuda_device):
+    replay_rdgcn("cuda")
