@@ -69,16 +69,39 @@ class Tensor:
         a, b = (_wrap(other), self) if swap else (self, _wrap(other))
         return Tensor(f, (a, b), name)
 
+    def __getitem__(self, idx):
+        return Tensor(lambda a: a[idx], (self,), "getitem")
+
+    @property
+    def shape(self):
+        """Static shape, by evaluating the node once without feeds (only for nodes that do not depend on a placeholder)."""
+        return tuple(self._eval({}).shape)
+
     def __add__(self, o): return self._bin(o, torch.add, "add")
     def __radd__(self, o): return self._bin(o, torch.add, "add", True)
     def __sub__(self, o): return self._bin(o, torch.sub, "sub")
     def __rsub__(self, o): return self._bin(o, torch.sub, "sub", True)
-    def __mul__(self, o): return self._bin(o, torch.mul, "mul")
-    def __rmul__(self, o): return self._bin(o, torch.mul, "mul", True)
+    def __mul__(self, o): return self._bin(o, _mul, "mul")
+    def __rmul__(self, o): return self._bin(o, _mul, "mul", True)
     def __truediv__(self, o): return self._bin(o, torch.div, "div")
     def __rtruediv__(self, o): return self._bin(o, torch.div, "div", True)
     def __neg__(self): return Tensor(torch.neg, (self,), "neg")
     def __pow__(self, p): return pow(self, p)
+
+
+def _mul(a, b):
+    """Dense product, or SparseTensor * dense with TF's broadcasting of a [n, 1] / [1, n] dense operand over the
+    stored entries (alinet.py:668-669)."""
+    if type(a).__name__ != "SparseValue":
+        return torch.mul(a, b)
+    row, col = a.indices[:, 0], a.indices[:, 1]
+    if b.dim() == 2 and b.shape[1] == 1:
+        scale = b[row, 0]
+    elif b.dim() == 2 and b.shape[0] == 1:
+        scale = b[0, col]
+    else:
+        scale = b if b.dim() == 0 else b[row, col]
+    return SparseValue(a.indices, a.values * scale, a.shape)
 
 
 class Placeholder(Tensor):
@@ -204,13 +227,37 @@ def get_default_graph():
 
 
 class SparseTensor(Tensor):
-    """tf.SparseTensor(indices, values, dense_shape): `values` may be a graph node; .indices / .values / .dense_shape
-    give back what was passed (the reference uses r_mat.values as lookup ids, rdgcn.py:205)."""
+    """tf.SparseTensor(indices, values, dense_shape): every component may be a graph node; .indices / .values /
+    .dense_shape give back what was passed (the reference uses r_mat.values as lookup ids, rdgcn.py:205)."""
 
     def __init__(self, indices, values, dense_shape):
         self.indices, self.values, self.dense_shape = indices, values, dense_shape
-        super().__init__(lambda v: SparseValue(np.asarray(indices), v if v.dtype.is_floating_point else v.to(DT), dense_shape),
-                         (_wrap(values),), "SparseTensor")
+
+        def f(i, v, shape):
+            return SparseValue(i, v if v.dtype.is_floating_point else v.to(DT), [int(x) for x in shape])
+        super().__init__(f, (_wrap(indices), _wrap(values), _wrap(dense_shape)), "SparseTensor")
+
+
+class _SparseResult(Tensor):
+    """A sparse-valued node whose components can be taken apart again (weights.indices, weights.values, …)."""
+    indices = property(lambda self: Tensor(lambda a: a.indices, (self,), "indices"))
+    values = property(lambda self: Tensor(lambda a: a.values, (self,), "values"))
+    dense_shape = property(lambda self: Tensor(lambda a: torch.as_tensor(a.shape), (self,), "dense_shape"))
+
+
+def sparse_add(a, b, name=None):
+    def f(x, y):
+        assert torch.equal(x.indices, y.indices), "sparse_add is only needed for operands with one pattern"
+        return SparseValue(x.indices, x.values + y.values, x.shape)
+    return _SparseResult(f, (_wrap(a), _wrap(b)), "sparse_add")
+
+
+def sparse_reshape(sp_input, shape, name=None):
+    return _wrap(sp_input)
+
+
+def tile(x, multiples, name=None):
+    return Tensor(lambda a: a.repeat(*multiples), (_wrap(x),), "tile")
 
 
 def sparse_softmax(sp_input, name=None):
@@ -259,7 +306,29 @@ def _conv1d(inputs, filters, kernel_size, use_bias=True, **kw):
 
 
 layers = types.SimpleNamespace(conv1d=_conv1d)
-keras = types.SimpleNamespace(activations=types.SimpleNamespace(
+class _BatchNormalization:
+    """tf.keras.layers.BatchNormalization() called in a TF-1 graph without `training`: inference mode — the moving
+    statistics (mean 0, variance 1 at initialisation, never updated by the reference's train op) normalise, so
+    y = γ·x / √(1 + ε) + β with ε = 1e-3; γ, β are created at the first call and shared by later calls."""
+
+    def __init__(self, epsilon=1e-3, **kw):
+        self.epsilon, self.gamma, self.beta = epsilon, None, None
+        idx = _LAYER_COUNT.get("bn", 0)
+        _LAYER_COUNT["bn"] = idx + 1
+        self.scope = "batch_normalization" if idx == 0 else "batch_normalization_%d" % idx
+
+    def __call__(self, inputs, training=None):
+        x = _wrap(inputs)
+        if self.gamma is None:
+            c = x.shape[-1]
+            self.gamma = Variable(np.ones(c), name=self.scope + "/gamma")
+            self.beta = Variable(np.zeros(c), name=self.scope + "/beta")
+        eps = self.epsilon
+        return Tensor(lambda a, g, b: a * (g / math.sqrt(1.0 + eps)) + b, (x, self.gamma, self.beta), self.scope)
+
+
+keras = types.SimpleNamespace(layers=types.SimpleNamespace(BatchNormalization=_BatchNormalization),
+                              activations=types.SimpleNamespace(
     get=lambda name: {"relu": nn.relu, "tanh": tanh, None: None}[name], relu=lambda x: nn.relu(x), tanh=lambda x: tanh(x)))
 
 summary = types.SimpleNamespace(histogram=lambda *a, **kw: None, scalar=lambda *a, **kw: None)
@@ -269,8 +338,9 @@ def constant(value, dtype=None, name=None, shape=None):
     return _wrap(value)
 
 
-def get_variable(name, shape=None, dtype=None, initializer=None):
-    return Variable(initializer(shape), name=name, dtype=dtype)
+def get_variable(name, shape=None, dtype=None, initializer=None, regularizer=None, trainable=True, **kw):
+    # a regularizer only registers a loss in a collection; none of the reference's losses reads that collection
+    return Variable(initializer(list(shape)), name=name, dtype=dtype, trainable=trainable)
 
 
 def trainable_variables():
@@ -311,7 +381,11 @@ def maximum(x, y, name=None):
 
 
 def cast(x, dtype=None, name=None):
-    return Tensor(lambda a: a.to(DT) if dtype in (float32, float64) else a.long(), (_wrap(x),), "cast")
+    def f(a):
+        if type(a).__name__ == "SparseValue":
+            return a
+        return a.to(DT) if dtype in (float32, float64) else a.long()
+    return Tensor(f, (_wrap(x),), "cast")
 
 
 def _reduce(f):
@@ -325,7 +399,7 @@ reduce_sum = _reduce(torch.sum)
 reduce_mean = _reduce(torch.mean)
 
 
-def matmul(a, b, transpose_a=False, transpose_b=False, name=None):
+def matmul(a, b, transpose_a=False, transpose_b=False, name=None, **kw):
     def f(x, y):
         return (x.t() if transpose_a else x) @ (y.t() if transpose_b else y)
     return Tensor(f, (_wrap(a), _wrap(b)), "matmul")
@@ -361,7 +435,7 @@ def _leaky_relu(x, alpha=0.2, name=None):
 
 
 nn = types.SimpleNamespace(
-    dropout=_dropout, leaky_relu=_leaky_relu,
+    dropout=_dropout, leaky_relu=_leaky_relu, bias_add=lambda x, b, name=None: _wrap(x) + b,
     softmax=lambda x, axis=-1, name=None: Tensor(lambda a: torch.softmax(a, dim=axis), (_wrap(x),), "softmax"),
     embedding_lookup=_embedding_lookup, l2_normalize=_l2_normalize,
     relu=_unary(torch.relu, "relu"), softplus=_unary(torch.nn.functional.softplus, "softplus"),
@@ -406,9 +480,13 @@ def _xavier(uniform=True, **kw):
     return init
 
 
+glorot_uniform_initializer = lambda **kw: _xavier(uniform=True)
+zeros_initializer = lambda **kw: (lambda shape: np.zeros(shape))
+ones_initializer = lambda **kw: (lambda shape: np.ones(shape))
 initializers = types.SimpleNamespace(truncated_normal=_truncated_normal, random_uniform=_random_uniform,
                                      orthogonal=_orthogonal)
-contrib = types.SimpleNamespace(layers=types.SimpleNamespace(xavier_initializer=_xavier))
+contrib = types.SimpleNamespace(layers=types.SimpleNamespace(xavier_initializer=_xavier,
+                                                             l2_regularizer=lambda scale=0.0, **kw: None))
 truncated_normal_initializer = _truncated_normal
 random_uniform_initializer = _random_uniform
 

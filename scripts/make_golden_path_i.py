@@ -315,9 +315,73 @@ def generate_rdgcn():
     print("wrote", path, os.path.getsize(path), "bytes")
 
 
+def generate_alinet():
+    """Path (ii), AliNet: the reference's _get_variable / _generate_rel_graph (alinet.py:779-883: batch-normalised GCN
+    layers over the one-hop adjacency, edge-softmax attention over the two-hop adjacency, highway gates, the
+    normalised concatenation of all layers, contrastive alignment loss + relation loss) and its AdamOptimizer.
+    → tests/golden/path_ii_alinet.npz"""
+    import scipy.sparse as sp
+    mod = import_reference("openea.approaches.alinet")
+    tf = tf1_shim
+    tf.reset_default_graph()
+    rng = np.random.default_rng(31)
+    n, dims, win = 26, [12, 8, 8], 3
+
+    def adjacency(density, seed):
+        a = sp.random(n, n, density=density, random_state=seed, format="coo")
+        a = sp.coo_matrix(((a + a.T) > 0).astype(np.float64)) + sp.eye(n)
+        deg = np.asarray(a.sum(1)).ravel()
+        a = sp.coo_matrix(sp.diags(deg ** -0.5) @ a @ sp.diags(deg ** -0.5))
+        return (np.vstack((a.row, a.col)).transpose(), a.data.astype(np.float32).astype(np.float64), a.shape)
+    one, two = adjacency(0.10, 5), adjacency(0.18, 6)
+    model = mod.AliNet()
+    model.kgs = types.SimpleNamespace(entities_num=n)
+    model.args = types.SimpleNamespace(layer_dims=dims, num_features_nonzero=0, dropout=0.0, neg_margin=1.5,
+                                       neg_margin_balance=0.1, rel_param=0.01, learning_rate=0.001)
+    model.adj = [one, two]
+    model.rel_win_size = win
+    model._get_variable()
+    model._generate_rel_graph()
+    variables = tf.trainable_variables()
+    names = [v.name for v in variables]
+    out = {"one/coords": one[0], "one/values": one[1], "two/coords": two[0], "two/values": two[1],
+           "dims": np.array([n] + dims + [win]), "neg_margin": np.float64(1.5), "balance": np.float64(0.1),
+           "rel_param": np.float64(0.01), "lr": np.float64(0.001)}
+    for v in variables:
+        shape = tuple(v.value.shape)
+        if v.name.endswith("/gamma"):
+            start = 1.0 + 0.1 * rng.standard_normal(shape)
+        elif v.name.endswith(("/beta", "_bias")):
+            start = 0.05 * rng.standard_normal(shape)
+        else:
+            start = rng.standard_normal(shape) * (0.6 / np.sqrt(shape[0]) if v.name != "init_embedding" else 0.5)
+        start = np.asarray(start, dtype=np.float32).astype(np.float64)
+        v.assign_numpy(start)
+        out["var0/" + v.name] = start
+    session = tf.Session()
+    for step in range(3):
+        pos = np.stack([rng.integers(0, n, 6), rng.integers(0, n, 6), np.zeros(6, dtype=np.int64)], 1)
+        neg = rng.integers(0, n, (14, 2))
+        hs, ts = rng.integers(0, n, 4 * win), rng.integers(0, n, 4 * win)
+        feed = {model.rel_pos_links: pos, model.rel_neg_links: neg, model.hs: hs, model.ts: ts}
+        res = session.run({"loss": model.loss, "optimizer": model.optimizer}, feed_dict=feed)
+        out["run%d/loss" % step] = np.float64(res["loss"])
+        for key, val in (("pos", pos), ("neg", neg), ("hs", hs), ("ts", ts)):
+            out["run%d/%s" % (step, key)] = val.astype(np.int32)
+    for v in variables:
+        out["var_final/" + v.name] = v.value.detach().numpy().copy()
+    for i, node in enumerate(model.output_embeds_list):
+        out["outputs_final/%d" % i] = session.run(node)
+    print("alinet: losses %s" % ["%.6g" % float(out["run%d/loss" % i]) for i in range(3)], names)
+    path = os.path.join(ROOT, "tests", "golden", "path_ii_alinet.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF_SRC):
         sys.exit("the reference is not present: goldens can only be generated where /root/reference exists")
     generate()
     generate_gcn_align()
     generate_rdgcn()
+    generate_alinet()

@@ -288,3 +288,63 @@ def test_rdgcn_layer_on_the_emulator_reproduces_the_reference_layer(cpu_engine, 
 @pytest.mark.first_hw_run
 def test_rdgcn_layer_on_the_gpu_reproduces_the_reference_layer(cuda_device):
     replay_rdgcn("cuda")
+
+
+# ---- path (ii): AliNet's whole graph, from the reference's _get_variable / _generate_rel_graph + AdamOptimizer ---------
+AL = np.load(os.path.join(os.path.dirname(GOLDEN), "path_ii_alinet.npz"))
+AL_NAMES = {"init_embedding": "init_embedding", "gcn_0_kernel_0": "gcn0.kernel", "gcn_0_bias": "gcn0.bias",
+            "batch_normalization/gamma": "gcn0.bn_gamma", "batch_normalization/beta": "gcn0.bn_beta",
+            "alinet_0_kernel": "gat0.kernel", "alinet_0_kernel_1": "gat0.kernel1", "alinet_0_kernel_2": "gat0.kernel2",
+            "batch_normalization_1/gamma": "gat0.bn_gamma", "batch_normalization_1/beta": "gat0.bn_beta",
+            "highwaykernel": "hw0.kernel", "batch_normalization_2/gamma": "hw0.bn_gamma",
+            "batch_normalization_2/beta": "hw0.bn_beta", "gcn_1_kernel_0": "gcn1.kernel", "gcn_1_bias": "gcn1.bias",
+            "batch_normalization_3/gamma": "gcn1.bn_gamma", "batch_normalization_3/beta": "gcn1.bn_beta"}
+
+
+def replay_alinet(device):
+    import scipy.sparse as sp
+    from openea_b200 import gnn
+    from openea_b200.approaches.alinet import AliNetModel, DenseAdam
+    n, win = int(AL["dims"][0]), int(AL["dims"][-1])
+    dims = [int(x) for x in AL["dims"][1:-1]]
+    coo = lambda name: sp.coo_matrix((AL[name + "/values"], (AL[name + "/coords"][:, 0], AL[name + "/coords"][:, 1])), shape=(n, n))
+    model = AliNetModel(n, dims, gnn.DeviceCsr(coo("one"), device), gnn.DeviceCsr(coo("two"), device), torch.device(device))
+    assert sorted(model.params) == sorted(AL_NAMES.values())
+    as2d = lambda a: np.asarray(a, dtype=np.float32).reshape(1, -1) if np.ndim(a) == 1 else np.asarray(a, dtype=np.float32)
+    with torch.no_grad():
+        for ref, mine in AL_NAMES.items():
+            want = as2d(AL["var0/" + ref])
+            assert tuple(model.params[mine].shape) == want.shape, (ref, mine)
+            model.params[mine].copy_(torch.as_tensor(want, device=device))
+    opt = DenseAdam(list(model.params.values()), float(AL["lr"]))
+    idx = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.long, device=device)
+    for step in range(3):
+        outs = model.forward()
+        loss = model.loss(outs, idx(AL["run%d/pos" % step]), idx(AL["run%d/neg" % step]), float(AL["neg_margin"]),
+                          float(AL["balance"]), hs=idx(AL["run%d/hs" % step]), ts=idx(AL["run%d/ts" % step]), rel_win=win,
+                          rel_param=float(AL["rel_param"]))
+        loss.backward()
+        opt.step()
+        assert float(loss.detach()) == pytest.approx(float(AL["run%d/loss" % step]), rel=2e-4), step
+    for ref, mine in AL_NAMES.items():
+        start, want = as2d(AL["var0/" + ref]), as2d(AL["var_final/" + ref])
+        got = model.params[mine].detach().cpu().numpy()
+        move = np.abs(want - start).max()
+        assert move > 0, ref
+        np.testing.assert_allclose(got - start, want - start, rtol=2e-2, atol=3e-2 * move, err_msg=ref)
+    with torch.no_grad():
+        for i, out in enumerate(model.forward()):
+            np.testing.assert_allclose(out[:, :dims[i + 1]].cpu().numpy(), AL["outputs_final/%d" % i], rtol=2e-3, atol=2e-5)
+
+
+def test_alinet_model_on_the_emulator_reproduces_the_reference_graph(cpu_engine, monkeypatch):
+    import ctypes as C
+    from openea_b200 import gnn
+    monkeypatch.setattr(gnn, "_stream_ptr", lambda: C.c_void_p(0))
+    replay_alinet("cpu")
+
+
+@pytest.mark.gpu
+@pytest.mark.first_hw_run
+def test_alinet_model_on_the_gpu_reproduces_the_reference_graph(cuda_device):
+    replay_alinet("cuda")
