@@ -31,3 +31,16 @@ def iptranse_helpers():
                    ["generate_2steps_path", "generate_newly_triples", "generate_triples_of_latent_ents",
                     "generate_neg_triples_w", "generate_neg_paths"],
                    {"np": np, "pd": pd, "random": random, "print": quiet, "KGs": object})
+
+
+def bootea_helpers():
+    """update_labeled_alignment_x / _y, generate_supervised_triples, generate_newly_triples, generate_pos_batch,
+    calculate_likelihood_mat of approaches/bootea.py:35-137 (pure Python; the diagnostics print is silenced)."""
+    import gc
+    import time
+    import numpy as np
+    return extract("approaches/bootea.py",
+                   ["update_labeled_alignment_x", "update_labeled_alignment_y", "generate_supervised_triples",
+                    "generate_newly_triples", "generate_pos_batch", "calculate_likelihood_mat"],
+                   {"np": np, "gc": gc, "time": time, "print": lambda *a, **k: None,
+                    "check_new_alignment": lambda *a, **k: None})

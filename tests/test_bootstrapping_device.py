@@ -164,3 +164,58 @@ def test_bootea_device_iteration_methods_on_cpu_tensors(monkeypatch):
     assert sorted(map(tuple, fed)) == sorted(map(tuple, want)) and all(p.dtype == torch.int32 and p.shape[0] == 3 for p in seen)
     ents1b, _ = _quiet(model.bootstrap_on_device)             # second pass edits the existing labels
     assert ents1b.numel() >= ents1.numel()
+
+
+@pytest.mark.skipif(__import__("oracle.reference_source", fromlist=["x"]).bootea_helpers() is None,
+                    reason="/root/reference not present on this box")
+def test_host_and_device_functions_equal_the_reference_source():
+    """The label-editing, swap-triple and batch-slicing functions of BootEA, executed from the reference's own source
+    (approaches/bootea.py:35-137), against this package's host functions and the tensor versions."""
+    import collections
+    import contextlib
+    import io
+    from openea_b200.approaches import bootea as host
+    from openea_b200.modules.bootstrapping import device as dev
+    from oracle import reference_source
+    ref = reference_source.bootea_helpers()
+    rng = np.random.default_rng(3)
+    n = 40
+    for trial in range(5):
+        e1 = torch.nn.functional.normalize(torch.as_tensor(rng.standard_normal((n, 8)), dtype=torch.float32), dim=1)
+        e2 = torch.nn.functional.normalize(torch.as_tensor(rng.standard_normal((n, 8)), dtype=torch.float32), dim=1)
+        sim, pair_sim = (e1 @ e2.t()).numpy(), host.PairSim(e1, e2)      # the reference indexes a matrix, this package pairs
+        pre = {(int(i), int(j)) for i, j in zip(rng.permutation(n)[:15], rng.integers(0, n, 15))}
+        cur = {(int(i), int(j)) for i, j in zip(rng.permutation(n)[:20], rng.permutation(n)[:20])}     # a matching
+        with contextlib.redirect_stdout(io.StringIO()):
+            want_x = ref["update_labeled_alignment_x"](set(pre), set(cur), sim)
+            want_y = ref["update_labeled_alignment_y"](set(want_x), sim)
+            assert host.update_labeled_alignment_x(set(pre), set(cur), pair_sim) == want_x
+            assert host.update_labeled_alignment_y(set(want_x), pair_sim) == want_y
+    # swap triples: dict walk of the reference vs host mirror vs masked gathers on tensors
+    tri = np.unique(np.stack([rng.integers(0, 30, 200), rng.integers(0, 5, 200), rng.integers(0, 30, 200)], 1), axis=0)
+    tri2 = np.unique(np.stack([rng.integers(30, 60, 200), rng.integers(0, 5, 200), rng.integers(30, 60, 200)], 1), axis=0)
+
+    def dicts(t):
+        rt, hr = collections.defaultdict(set), collections.defaultdict(set)
+        for h, r, tt in t:
+            rt[int(h)].add((int(r), int(tt)))
+            hr[int(tt)].add((int(h), int(r)))
+        return rt, hr
+    rt1, hr1 = dicts(tri)
+    rt2, hr2 = dicts(tri2)
+    e1 = [int(x) for x in rng.permutation(30)[:12]]
+    e2 = [int(x) for x in 30 + rng.permutation(30)[:12]]
+    with contextlib.redirect_stdout(io.StringIO()):
+        w1, w2 = ref["generate_supervised_triples"](rt1, hr1, rt2, hr2, e1, e2)
+        g1, g2 = host.generate_supervised_triples(rt1, hr1, rt2, hr2, e1, e2)
+    assert sorted(g1) == sorted(w1) and sorted(g2) == sorted(w2)
+    t1 = dev.swap_triples(torch.as_tensor(tri.astype(np.int32)), torch.as_tensor(e1), torch.as_tensor(e2), 60)
+    t2 = dev.swap_triples(torch.as_tensor(tri2.astype(np.int32)), torch.as_tensor(e2), torch.as_tensor(e1), 60)
+    assert sorted(map(tuple, t1.tolist())) == sorted(w1) and sorted(map(tuple, t2.tolist())) == sorted(w2)
+    # batch slices
+    a, b = [tuple(x) for x in tri.tolist()], [tuple(x) for x in tri2.tolist()]
+    for step in range(0, 9):
+        want = ref["generate_pos_batch"](a, b, step, 64)
+        assert host.generate_pos_batch(a, b, step, 64) == want
+        got = dev.pos_batch(torch.as_tensor(tri.astype(np.int32)), torch.as_tensor(tri2.astype(np.int32)), step, 64)
+        assert [tuple(x) for x in got.t().tolist()] == list(want[0]) + list(want[1])
