@@ -9,8 +9,8 @@ if [ "$1" = "multi" ]; then
   exit 0
 fi
 # 1. the tests marked first_hw_run (collected last) + the whole suite in front of them
-python -m pytest tests -q -m gpu -p no:cacheprovider > gpurun_out/r02a/tests.txt 2>&1
-tail -25 gpurun_out/r02a/tests.txt
+python -m pytest tests -q -m gpu -rxX -p no:cacheprovider > gpurun_out/r02a/tests.txt 2>&1
+tail -60 gpurun_out/r02a/tests.txt
 # 2. the bench lines, 15K and 100K
 python bench.py > gpurun_out/r02a/bench_15k.json 2> gpurun_out/r02a/bench.err
 python bench.py --workload bootea_100k --steps 40 --warmup 8 > gpurun_out/r02a/bench_100k.json 2>> gpurun_out/r02a/bench.err
