@@ -109,7 +109,7 @@ __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpre
 // 128-bit vector reduction to global memory (sm_90+: red.global.add.v4.f32), no return value.
 __device__ __forceinline__ void red_add4(float* p, float4 v) {
 #ifdef OEA_HOST_EMU
-    p[0] += v.x; p[1] += v.y; p[2] += v.z; p[3] += v.w;
+    atomicAdd(p, v.x); atomicAdd(p + 1, v.y); atomicAdd(p + 2, v.z); atomicAdd(p + 3, v.w);   // warps may run concurrently
 #else
     asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
                  :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");

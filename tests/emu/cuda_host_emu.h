@@ -3,12 +3,16 @@
 // where no GPU exists.  Not a fallback: nothing under openea_b200/ ever loads a library built with it.
 //
 // Model: one OS thread per lane; the 32 lanes of a warp run concurrently and meet at every warp collective
-// (__shfl*_sync, __ballot_sync, __match_any_sync) on a per-mask rendezvous, exactly where real lanes exchange
-// registers.  The warps of a block, and the blocks of a grid, run one after another (warp 0 of a block last, so a
-// block-level reduction that thread 0 finishes after __syncthreads() sees every warp's partial result);
-// __syncthreads() itself is a no-op, which is valid only for kernels whose barriers separate "every warp publishes"
-// from "thread 0 consumes" — the only pattern the emulated kernels use (LossAcc::flush).
-// "Device" pointers are host pointers; red/atomic adds are plain adds (lanes own disjoint addresses, warps are serial).
+// (__shfl*_sync, __ballot_sync, __match_any_sync, __syncwarp) on a per-mask rendezvous of their warp, exactly where real
+// lanes exchange registers.  Three schedules (selected per entry-point call by the tests):
+//   default       the warps of a block, and the blocks of a grid, run one after another (warp 0 of a block last, so a
+//                 block-level reduction that thread 0 finishes after __syncthreads() sees every warp's partial
+//                 result); __syncthreads() is a no-op — valid only for kernels whose barriers separate "every warp
+//                 publishes" from "thread 0 consumes" (LossAcc::flush); cheapest, used for the warp-per-item kernels;
+//   block mode    all warps of a block run concurrently and __syncthreads() is a real barrier (blocks still serial, so
+//                 static __shared__ storage is per block): for kernels whose warps cooperate through shared memory;
+//   serial lanes  the lanes of a warp run one after another (collective-free kernels that rely on warp convergence).
+// "Device" pointers are host pointers; atomics and red adds are real atomics (std::atomic_ref).
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
@@ -49,14 +53,35 @@ struct Rendezvous {
     std::atomic<int> arrived{0};
     std::atomic<unsigned> generation{0};
 };
-inline std::mutex g_map_mutex;
-inline std::map<unsigned, Rendezvous> g_rendezvous;   // one per participation mask
-inline uint64_t g_slot[32];
+// collective state of ONE warp: a rendezvous per participation mask and the 32 exchange slots
+struct WarpState {
+    std::mutex map_mutex;
+    std::map<unsigned, Rendezvous> rendezvous;
+    uint64_t slot[32];
+};
+// __syncthreads() of a block whose warps run concurrently (block mode, below)
+struct BlockBarrier {
+    int expected = 0;
+    std::atomic<int> arrived{0};
+    std::atomic<unsigned> generation{0};
+    void wait() {
+        const unsigned gen = generation.load();
+        if (arrived.fetch_add(1) + 1 == expected) {
+            arrived.store(0);
+            generation.fetch_add(1);
+        } else {
+            while (generation.load() == gen) std::this_thread::yield();
+        }
+    }
+};
+inline WarpState g_the_warp;                               // serial-warp modes: one warp exists at a time
+inline thread_local WarpState* t_warp = &g_the_warp;
+inline thread_local BlockBarrier* t_block = nullptr;       // non-null only in block mode
 inline thread_local int t_lane = 0;
 
 inline Rendezvous& rendezvous_of(unsigned mask) {
-    std::lock_guard<std::mutex> lk(g_map_mutex);
-    return g_rendezvous[mask];
+    std::lock_guard<std::mutex> lk(t_warp->map_mutex);
+    return t_warp->rendezvous[mask];
 }
 // all lanes named in `mask` meet here
 inline void sync(unsigned mask) {
@@ -75,12 +100,12 @@ inline void publish(T v) {
     static_assert(sizeof(T) <= 8, "exchange slot is 64 bits");
     uint64_t bits = 0;
     memcpy(&bits, &v, sizeof(T));
-    g_slot[t_lane] = bits;
+    t_warp->slot[t_lane] = bits;
 }
 template <typename T>
 inline T peek(int lane) {
     T v;
-    memcpy(&v, &g_slot[lane], sizeof(T));
+    memcpy(&v, &t_warp->slot[lane], sizeof(T));
     return v;
 }
 
@@ -90,6 +115,11 @@ inline T peek(int lane) {
 // its columns: the row optimisers) sees a race real lanes never see.  Serial: the lanes of a warp run one after another,
 // lane 31 first and lane 0 last — valid ONLY for kernels without warp collectives, and it gives exactly that order.
 inline std::atomic<bool> g_serial_lanes{false};
+// Block mode: ALL warps of a block run concurrently (one OS thread per CUDA thread) and __syncthreads() is a real
+// barrier; blocks still run one after another, so static __shared__ storage is per block as on the device.  Needed by
+// kernels whose warps cooperate through shared memory between barriers (tiled products, block-wide selections, the
+// mapping kernels); costs a thread per CUDA thread, so the tests use it with small grids only.
+inline std::atomic<bool> g_block_mode{false};
 
 // run `body` as a grid of blocks of `threads` threads (a multiple of 32)
 template <typename Body>
@@ -106,6 +136,27 @@ inline void launch(int grid, int threads, Body body) {
                     blockIdx.x = (unsigned)b;
                     body();
                 }
+        return;
+    }
+    if (g_block_mode.load()) {
+        for (int b = 0; b < grid; ++b) {
+            std::vector<WarpState> ws(warps);
+            BlockBarrier bar;
+            bar.expected = threads;
+            std::vector<std::thread> pool;
+            pool.reserve(threads);
+            for (int t = 0; t < threads; ++t) {
+                pool.emplace_back([&, t] {
+                    t_lane = t & 31;
+                    t_warp = &ws[t >> 5];
+                    t_block = &bar;
+                    threadIdx.x = (unsigned)t;
+                    blockIdx.x = (unsigned)b;
+                    body();
+                });
+            }
+            for (auto& th : pool) th.join();
+        }
         return;
     }
     for (int b = 0; b < grid; ++b) {
@@ -162,13 +213,28 @@ inline unsigned __match_any_sync(unsigned mask, T v) {
     emu::sync(mask);
     return out;
 }
-inline void __syncthreads() {}
+inline void __syncthreads() { if (emu::t_block) emu::t_block->wait(); }     // serial-warp modes: see the header comment
 inline void __syncwarp(unsigned mask = 0xffffffffu) { emu::sync(mask); }     // lanes are threads: a real rendezvous
 
 // ---- loads, atomics, intrinsics ----------------------------------------------------------------------------------------
 template <typename T>
 inline T __ldg(const T* p) { return *p; }
-inline double atomicAdd(double* p, double v) { const double old = *p; *p = old + v; return old; }
+template <typename T>
+inline T emu_atomic_rmw(T* p, T (*op)(T, T), T v) {
+    std::atomic_ref<T> a(*p);
+    T old = a.load(std::memory_order_relaxed);
+    while (!a.compare_exchange_weak(old, op(old, v), std::memory_order_relaxed)) {}
+    return old;
+}
+inline double atomicAdd(double* p, double v) { return emu_atomic_rmw<double>(p, [](double a, double b) { return a + b; }, v); }
+inline unsigned atomicAdd(unsigned* p, unsigned v) { return std::atomic_ref<unsigned>(*p).fetch_add(v); }
+inline int atomicAdd(int* p, int v) { return std::atomic_ref<int>(*p).fetch_add(v); }
+inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return std::atomic_ref<unsigned long long>(*p).fetch_add(v); }
+inline unsigned long long atomicMax(unsigned long long* p, unsigned long long v) {
+    return emu_atomic_rmw<unsigned long long>(p, [](unsigned long long a, unsigned long long b) { return a > b ? a : b; }, v);
+}
+inline unsigned atomicMax(unsigned* p, unsigned v) { return emu_atomic_rmw<unsigned>(p, [](unsigned a, unsigned b) { return a > b ? a : b; }, v); }
+inline int atomicMax(int* p, int v) { return emu_atomic_rmw<int>(p, [](int a, int b) { return a > b ? a : b; }, v); }
 inline float atomicAdd(float* p, float v) {          // lanes of one warp may hit the same word (scatter-adds): really atomic
     std::atomic_ref<float> a(*p);
     float old = a.load(std::memory_order_relaxed);

@@ -40,6 +40,18 @@ def cpu_engine(monkeypatch):
             finally:
                 lib.emu_set_serial_lanes(0)
         setattr(lib, name, serial)
+    # the mapping kernels' warps cooperate through shared memory between __syncthreads(): all warps of a block concurrent
+    lib.emu_set_block_mode.argtypes = [C.c_int]
+    for name in ("oea_mapping_fwd_bwd",):
+        real = getattr(lib, name)
+
+        def block(*a, _real=real):
+            lib.emu_set_block_mode(1)
+            try:
+                return _real(*a)
+            finally:
+                lib.emu_set_block_mode(0)
+        setattr(lib, name, block)
     monkeypatch.setattr(L, "load", lambda: lib)
     monkeypatch.setattr(eng, "_stream_ptr", lambda: C.c_void_p(0))
     monkeypatch.setenv("OEA_NO_FUSE", "1")            # the one-launch step needs a grid barrier

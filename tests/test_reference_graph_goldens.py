@@ -128,8 +128,6 @@ def test_engine_on_the_emulator_reproduces_the_reference_graph(cpu_engine, monke
     from openea_b200.approaches import imuse, iptranse, sea
     for mod in (imuse, iptranse, sea):
         monkeypatch.setattr(mod, "load_session", lambda: None, raising=False)
-    if case == "mtranse":
-        pytest.skip("the MTransE mapping kernel needs real block barriers (GPU only)")
     replay(case, cpu_engine, "cpu", monkeypatch)
 
 
