@@ -17,15 +17,15 @@
 // or — under tests/emu — the same kernel function run block by block on the CPU warp emulator (whole grid: not every
 // kernel is grid-stride).  A template-id with commas must be bound to a local `auto kernel = …` first.
 #ifdef OEA_HOST_EMU
-#define OEA_LAUNCH(KERNEL, GRID, BLOCK, SMEM, STREAM, ...) emu::launch((int)(GRID), (int)(BLOCK), [&] { KERNEL(__VA_ARGS__); })
+#define OEA_LAUNCH(KERNEL, GRID, BLOCK, SMEM, STREAM, ...) emu::launch(dim3(GRID), dim3(BLOCK), [&] { KERNEL(__VA_ARGS__); })
 #else
 #define OEA_LAUNCH(KERNEL, GRID, BLOCK, SMEM, STREAM, ...) KERNEL<<<(GRID), (BLOCK), (SMEM), (STREAM)>>>(__VA_ARGS__)
 #endif
 
 // The dynamically sized shared-memory array of a kernel (under tests/emu: a static one of the largest size used).
 #ifdef OEA_HOST_EMU
-#define OEA_DYNAMIC_SMEM(NAME) static float NAME[16384]
-#define OEA_DYNAMIC_SMEM_ALIGNED16(NAME) alignas(16) static float NAME[16384]
+#define OEA_DYNAMIC_SMEM(NAME) static float NAME[57344]
+#define OEA_DYNAMIC_SMEM_ALIGNED16(NAME) alignas(16) static float NAME[57344]
 #else
 #define OEA_DYNAMIC_SMEM(NAME) extern __shared__ float NAME[]
 #define OEA_DYNAMIC_SMEM_ALIGNED16(NAME) extern __shared__ __align__(16) float NAME[]

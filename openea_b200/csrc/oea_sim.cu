@@ -22,6 +22,12 @@ constexpr int TM = 128, TN = 128, BK = 16;
 constexpr int SIM_THREADS = 256;
 constexpr int STAGES = 3;          // cp.async pipeline depth of the operand tiles
 
+#ifdef OEA_HOST_EMU   // tests/emu: the copy is synchronous, groups are empty
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) { memcpy(smem_dst, gmem_src, 16); }
+__device__ __forceinline__ void cp_async_commit() {}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {}
+#else
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(s), "l"(gmem_src));
@@ -29,6 +35,7 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N)); }
+#endif
 constexpr int KMAX = 32;  // per-row top-k list lives in one warp's lanes
 constexpr int TS_LD = TN + 4;  // tile staging row stride: 16-B aligned rows, conflict-free 128-bit stores
 
@@ -67,7 +74,7 @@ struct SimParams {
 template <int METRIC, int EPI>
 __global__ void __launch_bounds__(SIM_THREADS, 2)
 k_sim_tile(SimParams P) {
-    extern __shared__ __align__(16) float smem[];
+    OEA_DYNAMIC_SMEM_ALIGNED16(smem);
     float (*As)[BK][TM] = reinterpret_cast<float (*)[BK][TM]>(smem);                      // [STAGES][BK][TM]
     float (*Bs)[BK][TN] = reinterpret_cast<float (*)[BK][TN]>(smem + STAGES * BK * TM);   // [STAGES][BK][TN]
     float* Ts = smem + STAGES * BK * TM + STAGES * BK * TN;                                    // [TM][TS_LD] (TOPK only)
@@ -306,7 +313,7 @@ constexpr int SHORTK_MAX = 104;
 template <int METRIC>
 __global__ void __launch_bounds__(SIM_THREADS, 2)
 k_sim_store_shortk(SimParams P, int KH) {
-    extern __shared__ __align__(16) float smem[];
+    OEA_DYNAMIC_SMEM_ALIGNED16(smem);
     float* Ares = smem;                       // [2·KH][TM]
     float* Bbuf0 = Ares + 2 * KH * TM;        // [KH][TN]  k in [0, KH)
     float* Bbuf1 = Bbuf0 + KH * TN;           // [KH][TN]  k in [KH, 2·KH)
@@ -548,7 +555,7 @@ static int launch_sim(const oea_sim_cfg* c, SimParams& P, int splits, cudaStream
 #define OEA_SIM_LAUNCH(M)                                                                                     \
     do {                                                                                                      \
         OEA_CUDA_TRY(cudaFuncSetAttribute(k_sim_tile<M, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        k_sim_tile<M, EPI><<<grid, SIM_THREADS, smem, st>>>(P);                                               \
+        OEA_LAUNCH((k_sim_tile<M, EPI>), grid, SIM_THREADS, smem, st, P);                                               \
     } while (0)
     switch (c->metric) {
         case OEA_METRIC_INNER: OEA_SIM_LAUNCH(OEA_METRIC_INNER); break;
@@ -604,7 +611,7 @@ extern "C" int oea_sim_transpose(const float* in, int32_t pitch, int32_t n, floa
     const long long ld = oea_sim_transpose_ld(n);
     const int kpad = (pitch + BK - 1) / BK * BK;
     const dim3 grid((unsigned)((ld + 31) / 32), (unsigned)((kpad + 31) / 32));
-    k_sim_transpose<<<grid, 256, 0, (cudaStream_t)stream>>>(in, pitch, n, out, ld, kpad);
+    OEA_LAUNCH(k_sim_transpose, grid, 256, 0, (cudaStream_t)stream, in, pitch, n, out, ld, kpad);
     OEA_LAUNCH_CHECK();
     return OEA_OK;
 }
@@ -638,7 +645,7 @@ extern "C" int oea_sim_topk(const oea_sim_cfg* c, const float* e1, const float* 
     P.part_val = (float*)workspace;
     P.part_idx = (int*)((char*)workspace + (size_t)c->n1 * splits * k * sizeof(float));
     rc = launch_sim<EPI_TOPK>(c, P, eff_splits, st); if (rc) return rc;
-    k_topk_merge<<<(c->n1 + 7) / 8, 256, 0, st>>>(P.part_val, P.part_idx, c->n1, eff_splits, k, out_val, out_idx, out_mean);
+    OEA_LAUNCH(k_topk_merge, (c->n1 + 7) / 8, 256, 0, st, P.part_val, P.part_idx, c->n1, eff_splits, k, out_val, out_idx, out_mean);
     OEA_LAUNCH_CHECK();
     return OEA_OK;
 }
@@ -670,14 +677,14 @@ extern "C" int oea_sim_rank(const oea_sim_cfg* c, const float* e1, const float* 
     P.splits = eff_splits;
     const int gb = (c->n1 + 127) / 128;
     switch (c->metric) {
-        case OEA_METRIC_INNER: k_sim_gold<OEA_METRIC_INNER><<<gb, 128, 0, st>>>(e1, e2, c->n1, c->pitch1, c->pitch2, P.kdim, gold, row_off, col_off, gold_val); break;
-        case OEA_METRIC_L1: k_sim_gold<OEA_METRIC_L1><<<gb, 128, 0, st>>>(e1, e2, c->n1, c->pitch1, c->pitch2, P.kdim, gold, row_off, col_off, gold_val); break;
-        default: k_sim_gold<OEA_METRIC_L2><<<gb, 128, 0, st>>>(e1, e2, c->n1, c->pitch1, c->pitch2, P.kdim, gold, row_off, col_off, gold_val); break;
+        case OEA_METRIC_INNER: OEA_LAUNCH(k_sim_gold<OEA_METRIC_INNER>, gb, 128, 0, st, e1, e2, c->n1, c->pitch1, c->pitch2, P.kdim, gold, row_off, col_off, gold_val); break;
+        case OEA_METRIC_L1: OEA_LAUNCH(k_sim_gold<OEA_METRIC_L1>, gb, 128, 0, st, e1, e2, c->n1, c->pitch1, c->pitch2, P.kdim, gold, row_off, col_off, gold_val); break;
+        default: OEA_LAUNCH(k_sim_gold<OEA_METRIC_L2>, gb, 128, 0, st, e1, e2, c->n1, c->pitch1, c->pitch2, P.kdim, gold, row_off, col_off, gold_val); break;
     }
     OEA_LAUNCH_CHECK();
     P.gold = gold; P.gold_val = gold_val; P.best = best; P.rank = out_rank;
     rc = launch_sim<EPI_RANK>(c, P, eff_splits, st); if (rc) return rc;
-    k_rank_finish<<<gb, 128, 0, st>>>(best, c->n1, out_top1);
+    OEA_LAUNCH(k_rank_finish, gb, 128, 0, st, best, c->n1, out_top1);
     OEA_LAUNCH_CHECK();
     return OEA_OK;
 }
@@ -702,7 +709,7 @@ extern "C" int oea_sim_matrix(const oea_sim_cfg* c, const float* e1, const float
 #define OEA_SHORTK_LAUNCH(M)                                                                                              \
     do {                                                                                                                  \
         OEA_CUDA_TRY(cudaFuncSetAttribute(k_sim_store_shortk<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        k_sim_store_shortk<M><<<grid, SIM_THREADS, smem, st>>>(P, KH);                                                    \
+        OEA_LAUNCH(k_sim_store_shortk<M>, grid, SIM_THREADS, smem, st, P, KH);                                                    \
     } while (0)
         switch (c->metric) {
             case OEA_METRIC_INNER: OEA_SHORTK_LAUNCH(OEA_METRIC_INNER); break;
@@ -721,7 +728,7 @@ extern "C" int oea_rows_normalize(const float* in, int32_t in_pitch, int32_t n, 
     if (!in || !out) return OEA_ERR_NULL;
     if (n < 0 || dim <= 0 || in_pitch < dim || out_pitch < dim) return OEA_ERR_DIM;
     if (n == 0) return OEA_OK;
-    k_rows_normalize<<<(n + 7) / 8, 256, 0, (cudaStream_t)stream>>>(in, in_pitch, n, dim, out, out_pitch);
+    OEA_LAUNCH(k_rows_normalize, (n + 7) / 8, 256, 0, (cudaStream_t)stream, in, in_pitch, n, dim, out, out_pitch);
     OEA_LAUNCH_CHECK();
     return OEA_OK;
 }
@@ -767,13 +774,15 @@ k_rows_select(const float* __restrict__ mat, long long ld, int n_rows, int n_col
             // suffix search from the top bin: find digit D with count(> D) < remaining <= count(>= D)
             if (warp == 0) {
                 const int per = nb / 32;
+                // read before the __syncwarp below: the lane that owns the digit rewrites s_remaining, and no lane may
+                // still be about to read it then (independent thread scheduling gives no convergence guarantee)
+                const unsigned remaining = s_remaining;
                 unsigned csum = 0;
                 for (int b = 0; b < per; ++b) csum += hist[lane * per + b];
                 s_chunk[lane] = csum;
                 __syncwarp();
                 unsigned above = 0;  // elements in chunks above this lane's chunk
                 for (int l = lane + 1; l < 32; ++l) above += s_chunk[l];
-                const unsigned remaining = s_remaining;
                 const bool mine = above < remaining && above + csum >= remaining;
                 if (mine) {
                     unsigned acc = above;
@@ -817,7 +826,7 @@ extern "C" int oea_rows_select_topk(const float* mat, int64_t ld, int32_t n_rows
     if (k < 1 || k > n_cols) return OEA_ERR_RANGE;
     if (n_rows == 0) return OEA_OK;
     const int grid = n_rows < 4 * sm_count() ? n_rows : 4 * sm_count();
-    k_rows_select<<<grid, SEL_THREADS, 0, (cudaStream_t)stream>>>(mat, ld, n_rows, n_cols, k, col_ids, out_idx);
+    OEA_LAUNCH(k_rows_select, grid, SEL_THREADS, 0, (cudaStream_t)stream, mat, ld, n_rows, n_cols, k, col_ids, out_idx);
     OEA_LAUNCH_CHECK();
     return OEA_OK;
 }
@@ -1108,7 +1117,7 @@ extern "C" int oea_matrix_topk_mean(const float* mat, int64_t ld, int32_t n_rows
     if (k < 1 || k > KMAX || k > (by_column ? n_rows : n_cols)) return OEA_ERR_RANGE;
     cudaStream_t st = (cudaStream_t)stream;
     if (!by_column) {
-        k_mat_row_topk_mean<<<(n_rows + 7) / 8, 256, 0, st>>>(mat, ld, n_rows, n_cols, k, out_mean);
+        OEA_LAUNCH(k_mat_row_topk_mean, (n_rows + 7) / 8, 256, 0, st, mat, ld, n_rows, n_cols, k, out_mean);
         OEA_LAUNCH_CHECK();
         return OEA_OK;
     }
@@ -1123,8 +1132,8 @@ extern "C" int oea_matrix_topk_mean(const float* mat, int64_t ld, int32_t n_rows
     const dim3 grid((n_cols + 32 * cpt - 1) / (32 * cpt), gy);
 #define OEA_COL_LAUNCH(KC, CP)                                                                                         \
     do {                                                                                                               \
-        k_mat_col_topk_partial<KC, CP><<<grid, CP_WARPS * 32, 0, st>>>(mat, ld, n_rows, n_cols, rows_per_split, part, ldp); \
-        k_col_partial_merge<KC><<<(n_cols + 31) / 32, 256, 0, st>>>(part, ldp, n_cols, n_splits, k, out_mean);        \
+        OEA_LAUNCH((k_mat_col_topk_partial<KC, CP>), grid, CP_WARPS * 32, 0, st, mat, ld, n_rows, n_cols, rows_per_split, part, ldp); \
+        OEA_LAUNCH(k_col_partial_merge<KC>, (n_cols + 31) / 32, 256, 0, st, part, ldp, n_cols, n_splits, k, out_mean);        \
     } while (0)
     switch (kcap) {
         case 4: OEA_COL_LAUNCH(4, 4); break;
@@ -1148,7 +1157,7 @@ extern "C" int oea_rank_stats(const int32_t* rank, int32_t n, const int32_t* top
     OEA_CUDA_TRY(cudaMemsetAsync(out, 0, (size_t)(n_top + 2) * sizeof(double), st));
     int blocks = (n + 255) / 256;
     if (blocks > 2 * sm_count()) blocks = 2 * sm_count();
-    k_rank_stats<<<blocks, 256, 0, st>>>(rank, n, tk, n_top, out);
+    OEA_LAUNCH(k_rank_stats, blocks, 256, 0, st, rank, n, tk, n_top, out);
     OEA_LAUNCH_CHECK();
     return OEA_OK;
 }
@@ -1158,7 +1167,7 @@ extern "C" int oea_matrix_rank(const float* mat, int64_t ld, int32_t n_rows, int
     if (!mat || !gold || !out_top1 || !out_rank) return OEA_ERR_NULL;
     if ((row_off == nullptr) != (col_off == nullptr)) return OEA_ERR_NULL;
     if (n_rows <= 0 || n_cols <= 0 || ld < n_cols) return OEA_ERR_SHAPE;
-    k_mat_rank<<<(n_rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(mat, ld, n_rows, n_cols, row_off, col_off, gold, out_top1, out_rank);
+    OEA_LAUNCH(k_mat_rank, (n_rows + 7) / 8, 256, 0, (cudaStream_t)stream, mat, ld, n_rows, n_cols, row_off, col_off, gold, out_top1, out_rank);
     OEA_LAUNCH_CHECK();
     return OEA_OK;
 }

@@ -31,6 +31,7 @@
 #define cudaMemcpyAsync(D, S, N, KIND, ST) (memcpy((D), (S), (N)), cudaSuccess)
 #define cudaStreamSynchronize(ST) (cudaSuccess)
 #define cudaLaunchCooperativeKernel(...) (cudaErrorNotSupported)        /* grid barriers are not emulated */
+#define cudaFuncSetAttribute(...) (cudaSuccess)
 
 #undef __shared__
 #define __shared__ static
@@ -123,7 +124,20 @@ inline std::atomic<bool> g_block_mode{false};
 
 // run `body` as a grid of blocks of `threads` threads (a multiple of 32)
 template <typename Body>
-inline void launch(int grid, int threads, Body body) {
+inline void launch_row(int grid, int threads, Body body);
+
+// run `body` as a (1- or 2-dimensional) grid of blocks of block.x threads (a multiple of 32)
+template <typename Body>
+inline void launch(dim3 grid, dim3 block, Body body) {
+    gridDim.y = grid.y;
+    for (unsigned y = 0; y < grid.y; ++y) {
+        blockIdx.y = y;
+        launch_row((int)grid.x, (int)block.x, [&, y] { blockIdx.y = y; body(); });
+    }
+}
+
+template <typename Body>
+inline void launch_row(int grid, int threads, Body body) {
     gridDim.x = (unsigned)grid;
     blockDim.x = (unsigned)threads;
     const int warps = threads / 32;
@@ -194,6 +208,24 @@ inline T __shfl_sync(unsigned mask, T v, int src) {
     emu::sync(mask);
     return r;
 }
+template <typename T>
+inline T __shfl_up_sync(unsigned mask, T v, unsigned delta) {
+    emu::publish(v);
+    emu::sync(mask);
+    const int src = emu::t_lane - (int)delta;
+    const T r = src >= 0 ? emu::peek<T>(src) : v;         // lanes below delta keep their own value
+    emu::sync(mask);
+    return r;
+}
+template <typename T>
+inline T __shfl_down_sync(unsigned mask, T v, unsigned delta) {
+    emu::publish(v);
+    emu::sync(mask);
+    const int src = emu::t_lane + (int)delta;
+    const T r = src < 32 ? emu::peek<T>(src) : v;
+    emu::sync(mask);
+    return r;
+}
 inline unsigned __ballot_sync(unsigned mask, bool pred) {
     emu::publish<unsigned>(pred ? 1u : 0u);
     emu::sync(mask);
@@ -248,6 +280,13 @@ inline unsigned long long atomicCAS(unsigned long long* p, unsigned long long ex
 }
 using std::min;
 using std::max;
+inline int __ffs(int x) { return __builtin_ffs(x); }
+inline int __popc(unsigned x) { return __builtin_popcount(x); }
+inline int __clz(int x) { return x == 0 ? 32 : __builtin_clz((unsigned)x); }
+inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
+inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
+inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
 inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((uint64_t)a * (uint64_t)b) >> 32); }
 inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 inline float emu_expf(float x) { return expf(x); }

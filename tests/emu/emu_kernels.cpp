@@ -10,6 +10,7 @@
 #include "../../openea_b200/csrc/oea_triple_weighted.cu"
 #include "../../openea_b200/csrc/oea_spmm.cu"
 #include "../../openea_b200/csrc/oea_triple.cu"
+#include "../../openea_b200/csrc/oea_sim.cu"
 
 // lane scheduling switch for collective-free kernels that rely on warp convergence (see cuda_host_emu.h)
 extern "C" void emu_set_serial_lanes(int on) { emu::g_serial_lanes.store(on != 0); }
