@@ -680,6 +680,7 @@ k_rowopt(float* __restrict__ w, float* __restrict__ grad, float* __restrict__ s1
             *reinterpret_cast<float4*>(w + o) = x;
             *reinterpret_cast<float4*>(grad + o) = f4(0.f);
         }
+        __syncwarp();      // every lane has read the flag (above) before lane 0 clears it: no reliance on convergence
         if (lane == 0) touched[row] = 0;
     }
 }
@@ -1180,6 +1181,7 @@ k_rowopt_pair(OptTab A, OptTab B, int pitch, float lr) {
             *reinterpret_cast<float4*>(T.w + o) = x;
             *reinterpret_cast<float4*>(T.g + o) = f4(0.f);
         }
+        __syncwarp();      // as in k_rowopt: all lanes have read the flag before it is cleared
         if (lane == 0) T.touched[row] = 0;
     }
 }

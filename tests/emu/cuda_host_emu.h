@@ -4,14 +4,13 @@
 //
 // Model: one OS thread per lane; the 32 lanes of a warp run concurrently and meet at every warp collective
 // (__shfl*_sync, __ballot_sync, __match_any_sync, __syncwarp) on a per-mask rendezvous of their warp, exactly where real
-// lanes exchange registers.  Three schedules (selected per entry-point call by the tests):
+// lanes exchange registers.  Two schedules (selected per entry-point call by the tests):
 //   default       the warps of a block, and the blocks of a grid, run one after another (warp 0 of a block last, so a
 //                 block-level reduction that thread 0 finishes after __syncthreads() sees every warp's partial
 //                 result); __syncthreads() is a no-op — valid only for kernels whose barriers separate "every warp
 //                 publishes" from "thread 0 consumes" (LossAcc::flush); cheapest, used for the warp-per-item kernels;
 //   block mode    all warps of a block run concurrently and __syncthreads() is a real barrier (blocks still serial, so
 //                 static __shared__ storage is per block): for kernels whose warps cooperate through shared memory;
-//   serial lanes  the lanes of a warp run one after another (collective-free kernels that rely on warp convergence).
 // "Device" pointers are host pointers; atomics and red adds are real atomics (std::atomic_ref).
 #pragma once
 #include <cuda_runtime.h>
@@ -110,12 +109,6 @@ inline T peek(int lane) {
     return v;
 }
 
-// Lane scheduling of the next launches.  Concurrent (default): the 32 lanes of a warp are free-running threads that meet
-// only at collectives — right for kernels that synchronise explicitly, but a kernel that relies on the hardware keeping a
-// converged warp in step between two plain memory accesses (all lanes read a row's `touched` flag, lane 0 clears it after
-// its columns: the row optimisers) sees a race real lanes never see.  Serial: the lanes of a warp run one after another,
-// lane 31 first and lane 0 last — valid ONLY for kernels without warp collectives, and it gives exactly that order.
-inline std::atomic<bool> g_serial_lanes{false};
 // Block mode: ALL warps of a block run concurrently (one OS thread per CUDA thread) and __syncthreads() is a real
 // barrier; blocks still run one after another, so static __shared__ storage is per block as on the device.  Needed by
 // kernels whose warps cooperate through shared memory between barriers (tiled products, block-wide selections, the
@@ -141,17 +134,6 @@ inline void launch_row(int grid, int threads, Body body) {
     gridDim.x = (unsigned)grid;
     blockDim.x = (unsigned)threads;
     const int warps = threads / 32;
-    if (g_serial_lanes.load()) {
-        for (int b = 0; b < grid; ++b)
-            for (int w = warps - 1; w >= 0; --w)
-                for (int l = 31; l >= 0; --l) {
-                    t_lane = l;
-                    threadIdx.x = (unsigned)(w * 32 + l);
-                    blockIdx.x = (unsigned)b;
-                    body();
-                }
-        return;
-    }
     if (g_block_mode.load()) {
         for (int b = 0; b < grid; ++b) {
             std::vector<WarpState> ws(warps);

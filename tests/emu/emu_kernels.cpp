@@ -12,7 +12,5 @@
 #include "../../openea_b200/csrc/oea_triple.cu"
 #include "../../openea_b200/csrc/oea_sim.cu"
 
-// lane scheduling switch for collective-free kernels that rely on warp convergence (see cuda_host_emu.h)
-extern "C" void emu_set_serial_lanes(int on) { emu::g_serial_lanes.store(on != 0); }
 // block mode: all warps of a block concurrent, real __syncthreads (see cuda_host_emu.h)
 extern "C" void emu_set_block_mode(int on) { emu::g_block_mode.store(on != 0); }

@@ -27,19 +27,6 @@ def cpu_engine(monkeypatch):
         if hasattr(lib, name):
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
-    # the row optimisers have no warp collectives and rely on a converged warp staying in step between reading a row's
-    # `touched` flag and lane 0 clearing it: their lanes run serially (lane 0 last) on the emulator
-    lib.emu_set_serial_lanes.argtypes = [C.c_int]
-    for name in ("oea_rowopt_apply", "oea_rowopt_apply_pair"):
-        real = getattr(lib, name)
-
-        def serial(*a, _real=real):
-            lib.emu_set_serial_lanes(1)
-            try:
-                return _real(*a)
-            finally:
-                lib.emu_set_serial_lanes(0)
-        setattr(lib, name, serial)
     # the mapping kernels' warps cooperate through shared memory between __syncthreads(): all warps of a block concurrent
     lib.emu_set_block_mode.argtypes = [C.c_int]
     for name in ("oea_mapping_fwd_bwd",):
