@@ -2,15 +2,12 @@
 // sources (openea_b200/csrc/*.cu, compiled unchanged with -DOEA_HOST_EMU by g++) can be checked against the oracle
 // where no GPU exists.  Not a fallback: nothing under openea_b200/ ever loads a library built with it.
 //
-// Model: one OS thread per lane; the 32 lanes of a warp run concurrently and meet at every warp collective
-// (__shfl*_sync, __ballot_sync, __match_any_sync, __syncwarp) on a per-mask rendezvous of their warp, exactly where real
-// lanes exchange registers.  Two schedules (selected per entry-point call by the tests):
-//   default       the warps of a block, and the blocks of a grid, run one after another (warp 0 of a block last, so a
-//                 block-level reduction that thread 0 finishes after __syncthreads() sees every warp's partial
-//                 result); __syncthreads() is a no-op — valid only for kernels whose barriers separate "every warp
-//                 publishes" from "thread 0 consumes" (LossAcc::flush); cheapest, used for the warp-per-item kernels;
-//   block mode    all warps of a block run concurrently and __syncthreads() is a real barrier (blocks still serial, so
-//                 static __shared__ storage is per block): for kernels whose warps cooperate through shared memory;
+// Model: one OS thread per CUDA thread.  All warps of a block run concurrently; the 32 lanes of a warp meet at every
+// warp collective (__shfl*_sync, __ballot_sync, __match_any_sync, __syncwarp) on a per-mask rendezvous of their warp —
+// exactly where real lanes exchange registers — and nowhere else (lanes are free-running, so code that silently relies
+// on a converged warp staying in step is caught); __syncthreads() is a real barrier; the blocks of a grid run one after
+// another, so static __shared__ storage is per block as on the device and a grid barrier cannot be honoured (kernels
+// using cooperative_groups::this_grid().sync() are compiled but not run).
 // "Device" pointers are host pointers; atomics and red adds are real atomics (std::atomic_ref).
 #pragma once
 #include <cuda_runtime.h>
@@ -59,7 +56,7 @@ struct WarpState {
     std::map<unsigned, Rendezvous> rendezvous;
     uint64_t slot[32];
 };
-// __syncthreads() of a block whose warps run concurrently (block mode, below)
+// __syncthreads() of a block
 struct BlockBarrier {
     int expected = 0;
     std::atomic<int> arrived{0};
@@ -74,9 +71,8 @@ struct BlockBarrier {
         }
     }
 };
-inline WarpState g_the_warp;                               // serial-warp modes: one warp exists at a time
-inline thread_local WarpState* t_warp = &g_the_warp;
-inline thread_local BlockBarrier* t_block = nullptr;       // non-null only in block mode
+inline thread_local WarpState* t_warp = nullptr;           // set by launch() for every thread of the grid
+inline thread_local BlockBarrier* t_block = nullptr;
 inline thread_local int t_lane = 0;
 
 inline Rendezvous& rendezvous_of(unsigned mask) {
@@ -109,13 +105,6 @@ inline T peek(int lane) {
     return v;
 }
 
-// Block mode: ALL warps of a block run concurrently (one OS thread per CUDA thread) and __syncthreads() is a real
-// barrier; blocks still run one after another, so static __shared__ storage is per block as on the device.  Needed by
-// kernels whose warps cooperate through shared memory between barriers (tiled products, block-wide selections, the
-// mapping kernels); costs a thread per CUDA thread, so the tests use it with small grids only.
-inline std::atomic<bool> g_block_mode{false};
-
-// run `body` as a grid of blocks of `threads` threads (a multiple of 32)
 template <typename Body>
 inline void launch_row(int grid, int threads, Body body);
 
@@ -134,40 +123,23 @@ inline void launch_row(int grid, int threads, Body body) {
     gridDim.x = (unsigned)grid;
     blockDim.x = (unsigned)threads;
     const int warps = threads / 32;
-    if (g_block_mode.load()) {
-        for (int b = 0; b < grid; ++b) {
-            std::vector<WarpState> ws(warps);
-            BlockBarrier bar;
-            bar.expected = threads;
-            std::vector<std::thread> pool;
-            pool.reserve(threads);
-            for (int t = 0; t < threads; ++t) {
-                pool.emplace_back([&, t] {
-                    t_lane = t & 31;
-                    t_warp = &ws[t >> 5];
-                    t_block = &bar;
-                    threadIdx.x = (unsigned)t;
-                    blockIdx.x = (unsigned)b;
-                    body();
-                });
-            }
-            for (auto& th : pool) th.join();
-        }
-        return;
-    }
     for (int b = 0; b < grid; ++b) {
-        for (int w = warps - 1; w >= 0; --w) {
-            std::vector<std::thread> lanes;
-            for (int l = 0; l < 32; ++l) {
-                lanes.emplace_back([=] {
-                    t_lane = l;
-                    threadIdx.x = (unsigned)(w * 32 + l);
-                    blockIdx.x = (unsigned)b;
-                    body();
-                });
-            }
-            for (auto& t : lanes) t.join();
+        std::vector<WarpState> ws(warps);
+        BlockBarrier bar;
+        bar.expected = threads;
+        std::vector<std::thread> pool;
+        pool.reserve(threads);
+        for (int t = 0; t < threads; ++t) {
+            pool.emplace_back([&, t] {
+                t_lane = t & 31;
+                t_warp = &ws[t >> 5];
+                t_block = &bar;
+                threadIdx.x = (unsigned)t;
+                blockIdx.x = (unsigned)b;
+                body();
+            });
         }
+        for (auto& th : pool) th.join();
     }
 }
 
@@ -227,7 +199,7 @@ inline unsigned __match_any_sync(unsigned mask, T v) {
     emu::sync(mask);
     return out;
 }
-inline void __syncthreads() { if (emu::t_block) emu::t_block->wait(); }     // serial-warp modes: see the header comment
+inline void __syncthreads() { emu::t_block->wait(); }
 inline void __syncwarp(unsigned mask = 0xffffffffu) { emu::sync(mask); }     // lanes are threads: a real rendezvous
 
 // ---- loads, atomics, intrinsics ----------------------------------------------------------------------------------------

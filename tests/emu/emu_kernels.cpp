@@ -12,5 +12,3 @@
 #include "../../openea_b200/csrc/oea_triple.cu"
 #include "../../openea_b200/csrc/oea_sim.cu"
 
-// block mode: all warps of a block concurrent, real __syncthreads (see cuda_host_emu.h)
-extern "C" void emu_set_block_mode(int on) { emu::g_block_mode.store(on != 0); }

@@ -1,6 +1,6 @@
 """CPU: the kernels of path (iii) (openea_b200/csrc/oea_sim.cu: tiled similarity with top-k / rank / store epilogues,
 CSLS on the stored matrix, row / column top-k means, radix selection of the k nearest, rank statistics) executed from
-their SOURCE on the warp emulator in block mode (all warps of a block concurrent, real __syncthreads) through the
+their SOURCE on the warp emulator (all warps of a block concurrent, real __syncthreads) through the
 product's own host layer (openea_b200/finding.py over CPU tensors), against the golden vectors the reference itself
 produced (tests/golden/finding_golden.npz).  The same checks run on the B200 in tests/test_finding_gpu.py."""
 import ctypes as C
@@ -22,20 +22,10 @@ def finding_cpu(monkeypatch):
     if so is None:
         pytest.skip("no CUDA headers for the emulator build")
     lib = C.CDLL(so)
-    lib.emu_set_block_mode.argtypes = [C.c_int]
     for name, (res, args) in L.SIGNATURES.items():
-        if not hasattr(lib, name):
-            continue
-        fn = getattr(lib, name)
-        fn.restype, fn.argtypes = res, args
-        if name.startswith(("oea_sim_", "oea_rows_", "oea_matrix_", "oea_mat_", "oea_rank_")) and args and args[-1] is L._P:
-            def block(*a, _real=fn):
-                lib.emu_set_block_mode(1)
-                try:
-                    return _real(*a)
-                finally:
-                    lib.emu_set_block_mode(0)
-            setattr(lib, name, block)
+        if hasattr(lib, name):
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
     from openea_b200 import engine as eng
     from openea_b200 import finding
     monkeypatch.setattr(L, "load", lambda: lib)

@@ -2,8 +2,8 @@
 the tensor-level losses, the on-device triple set and the warp-per-positive sampled scorer — executed from the product's
 kernel SOURCE on the warp emulator (tests/emu) through the product's own Python engine over CPU tensors, against the C
 oracle.  These kernels are verified on the B200 by tests/test_triple_gpu.py; here the same checks guard refactors where
-no GPU exists.  (The octet / one-launch step kernels and the mapping kernels need a grid barrier resp. real block
-barriers, which the emulator's serial warps cannot give: they are compiled but not run.)"""
+no GPU exists.  (The octet / one-launch step kernels need a grid barrier, which the emulator's serial blocks
+cannot give: they are compiled but not run.)"""
 import ctypes as C
 
 import numpy as np
@@ -27,18 +27,6 @@ def cpu_engine(monkeypatch):
         if hasattr(lib, name):
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
-    # the mapping kernels' warps cooperate through shared memory between __syncthreads(): all warps of a block concurrent
-    lib.emu_set_block_mode.argtypes = [C.c_int]
-    for name in ("oea_mapping_fwd_bwd",):
-        real = getattr(lib, name)
-
-        def block(*a, _real=real):
-            lib.emu_set_block_mode(1)
-            try:
-                return _real(*a)
-            finally:
-                lib.emu_set_block_mode(0)
-        setattr(lib, name, block)
     monkeypatch.setattr(L, "load", lambda: lib)
     monkeypatch.setattr(eng, "_stream_ptr", lambda: C.c_void_p(0))
     monkeypatch.setenv("OEA_NO_FUSE", "1")            # the one-launch step needs a grid barrier
