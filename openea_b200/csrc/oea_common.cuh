@@ -22,6 +22,21 @@
 #define OEA_LAUNCH(KERNEL, GRID, BLOCK, SMEM, STREAM, ...) KERNEL<<<(GRID), (BLOCK), (SMEM), (STREAM)>>>(__VA_ARGS__)
 #endif
 
+// Cooperative launch (the kernel uses cooperative_groups::this_grid().sync()); the arguments must be lvalues of exactly
+// the kernel's parameter types.  Under tests/emu the grid is ONE block (every kernel launched this way walks its work
+// with grid-stride loops) and the grid barrier is that block's barrier.
+#ifdef OEA_HOST_EMU
+#define OEA_LAUNCH_COOPERATIVE(KERNEL, GRID, BLOCK, STREAM, ...) \
+    (emu::launch(dim3(1), dim3(BLOCK), [&] { KERNEL(__VA_ARGS__); }), cudaSuccess)
+#else
+template <typename Kernel, typename... Args>
+static inline cudaError_t oea_launch_cooperative(Kernel kernel, int grid, int block, cudaStream_t stream, Args&... args) {
+    void* argv[] = {(void*)&args...};
+    return cudaLaunchCooperativeKernel((void*)kernel, dim3(grid), dim3(block), argv, 0, stream);
+}
+#define OEA_LAUNCH_COOPERATIVE(KERNEL, GRID, BLOCK, STREAM, ...) oea_launch_cooperative(KERNEL, GRID, BLOCK, STREAM, __VA_ARGS__)
+#endif
+
 // The dynamically sized shared-memory array of a kernel (under tests/emu: a static one of the largest size used).
 #ifdef OEA_HOST_EMU
 #define OEA_DYNAMIC_SMEM(NAME) static float NAME[57344]

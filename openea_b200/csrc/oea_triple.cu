@@ -1231,13 +1231,12 @@ extern "C" int oea_triple_step_sampled(const oea_table* ent, const oea_table* re
     OptTab A{ent->weight, ent->grad, ent->state1, ent->touched, ent->rows}, B{rel->weight, rel->grad, rel->state1, rel->touched, rel->rows};
     oea_loss_cfg cfg = *loss;
     float lr = opt->lr;
-    void* args[] = {&e, &r, &P, &cfg, &loss_out, &A, &B, &lr};
     if (opt->kind == OEA_OPT_ADAGRAD) {
         const int grid = grid_one_wave(k_step_sampled_oct<OEA_OPT_ADAGRAD>, n_pos, kOctWarps);
-        OEA_CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_step_sampled_oct<OEA_OPT_ADAGRAD>, dim3(grid), dim3(kOctThreads), args, 0, st));
+        OEA_CUDA_TRY(OEA_LAUNCH_COOPERATIVE(k_step_sampled_oct<OEA_OPT_ADAGRAD>, grid, kOctThreads, st, e, r, P, cfg, loss_out, A, B, lr));
     } else {
         const int grid = grid_one_wave(k_step_sampled_oct<OEA_OPT_SGD>, n_pos, kOctWarps);
-        OEA_CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_step_sampled_oct<OEA_OPT_SGD>, dim3(grid), dim3(kOctThreads), args, 0, st));
+        OEA_CUDA_TRY(OEA_LAUNCH_COOPERATIVE(k_step_sampled_oct<OEA_OPT_SGD>, grid, kOctThreads, st, e, r, P, cfg, loss_out, A, B, lr));
     }
     return OEA_OK;
 }

@@ -6,8 +6,8 @@
 // warp collective (__shfl*_sync, __ballot_sync, __match_any_sync, __syncwarp) on a per-mask rendezvous of their warp —
 // exactly where real lanes exchange registers — and nowhere else (lanes are free-running, so code that silently relies
 // on a converged warp staying in step is caught); __syncthreads() is a real barrier; the blocks of a grid run one after
-// another, so static __shared__ storage is per block as on the device and a grid barrier cannot be honoured (kernels
-// using cooperative_groups::this_grid().sync() are compiled but not run).
+// another, so static __shared__ storage is per block as on the device; a kernel with a grid barrier
+// (cooperative_groups::this_grid().sync()) is launched as ONE block, whose barrier then is the grid's.
 // "Device" pointers are host pointers; atomics and red adds are real atomics (std::atomic_ref).
 #pragma once
 #include <cuda_runtime.h>
@@ -26,7 +26,6 @@
 #define cudaMemsetAsync(P, V, N, ST) (memset((P), (V), (N)), cudaSuccess)
 #define cudaMemcpyAsync(D, S, N, KIND, ST) (memcpy((D), (S), (N)), cudaSuccess)
 #define cudaStreamSynchronize(ST) (cudaSuccess)
-#define cudaLaunchCooperativeKernel(...) (cudaErrorNotSupported)        /* grid barriers are not emulated */
 #define cudaFuncSetAttribute(...) (cudaSuccess)
 
 #undef __shared__
@@ -40,7 +39,7 @@ inline EmuDim3 gridDim, blockDim;
 
 #define _COOPERATIVE_GROUPS_H_          /* keep <cooperative_groups.h> out: it needs nvcc */
 namespace cooperative_groups {
-struct grid_group { void sync() const {} };    // serial blocks cannot honour a grid barrier: kernels using it are not run
+struct grid_group { void sync() const; };      // OEA_LAUNCH_COOPERATIVE runs such kernels as ONE block: its barrier is the grid's
 inline grid_group this_grid() { return {}; }
 }  // namespace cooperative_groups
 
@@ -200,6 +199,7 @@ inline unsigned __match_any_sync(unsigned mask, T v) {
     return out;
 }
 inline void __syncthreads() { emu::t_block->wait(); }
+inline void cooperative_groups::grid_group::sync() const { __syncthreads(); }
 inline void __syncwarp(unsigned mask = 0xffffffffu) { emu::sync(mask); }     // lanes are threads: a real rendezvous
 
 // ---- loads, atomics, intrinsics ----------------------------------------------------------------------------------------

@@ -2,8 +2,7 @@
 the tensor-level losses, the on-device triple set and the warp-per-positive sampled scorer — executed from the product's
 kernel SOURCE on the warp emulator (tests/emu) through the product's own Python engine over CPU tensors, against the C
 oracle.  These kernels are verified on the B200 by tests/test_triple_gpu.py; here the same checks guard refactors where
-no GPU exists.  (The octet / one-launch step kernels need a grid barrier, which the emulator's serial blocks
-cannot give: they are compiled but not run.)"""
+no GPU exists.  The octet scorer and the one-launch step (a cooperative kernel, run as one block here) are at the end."""
 import ctypes as C
 
 import numpy as np
@@ -213,3 +212,73 @@ def test_emulated_pair_distance_loss_matches_autograd(cpu_engine, norm, d, weigh
     assert t.read_loss() == pytest.approx(float(want.detach()), rel=1e-4)
     np.testing.assert_allclose(te.grad[:, :d].numpy(), E.grad.numpy(), rtol=1e-4, atol=2e-5 * float(E.grad.abs().max()))
     assert set(np.flatnonzero(te.touched.numpy())) <= set(a.tolist()) | set(b.tolist())
+
+
+@pytest.fixture()
+def cpu_engine_oct(cpu_engine, monkeypatch):
+    """The same engine with the octet kernels enabled: the octet sampled scorer and the one-launch step (score, grid
+    barrier, octet row optimiser — launched as one block on the emulator, so its grid barrier is the block's)."""
+    monkeypatch.delenv("OEA_NO_FUSE")
+    monkeypatch.delenv("OEA_SCORE_V1")
+    return cpu_engine
+
+
+def _sampled_setup(engine, rng, opt="Adagrad"):
+    n, n_rel, d = 50, 4, 12
+    def kg(lo):
+        t = np.stack([rng.integers(lo, lo + n, 120), rng.integers(0, n_rel, 120), rng.integers(lo, lo + n, 120)], 1)
+        return np.unique(t.astype(np.int32), axis=0)
+    t1, t2 = kg(0), kg(n)
+    ent, rel = make_tables(rng, 2 * n, n_rel, d)
+    kg1 = engine.DeviceKG(t1, np.arange(0, n), 2 * n, device="cpu")
+    kg2 = engine.DeviceKG(t2, np.arange(n, 2 * n), 2 * n, device="cpu")
+    tset = engine.DeviceTripleSet([kg1.triples, kg2.triples], 2 * n, n_rel, device="cpu")
+    make = lambda: engine.TripleTrainer(engine.EmbeddingTable(ent, True, opt, device="cpu"),
+                                        engine.EmbeddingTable(rel, True, opt, device="cpu"),
+                                        engine.loss_cfg("limited", "L2", 0.1, 2.0, 0.2), 0.01)
+    return t1, t2, kg1, kg2, tset, make
+
+
+def test_emulated_octet_scorer_replays_through_the_fed_scorer(cpu_engine_oct):
+    """k_score_sampled_oct (four negatives per warp pass, shared rows staged in shared memory): its debug dump replayed
+    through the per-triple fed scorer gives the same loss and gradients."""
+    rng = np.random.default_rng(18)
+    t1, t2, kg1, kg2, tset, make = _sampled_setup(cpu_engine_oct, rng)
+    B, k = 32, 6
+    a = make()
+    dbg = torch.zeros(B, 2 + k, dtype=torch.int32)
+    n_pos = torch.zeros(1, dtype=torch.int32)
+    a.score_sampled(kg1, kg2, tset, B, k, 1, 4242, dbg=dbg, n_pos_out=n_pos)
+    rows = dbg.numpy()[:int(n_pos)]
+    pos = np.stack([(t2[r[0] - (1 << 30)] if r[0] >= (1 << 30) else t1[r[0]]) for r in rows], 1).astype(np.int32)
+    neg = np.repeat(pos, k, axis=1)
+    for i, r in enumerate(rows):
+        for j in range(k):
+            neg[0 if (r[1] >> j) & 1 else 2, i * k + j] = r[2 + j]
+    b = make()
+    b.score_fed(_t(pos), _t(neg))
+    assert a.read_loss() == pytest.approx(b.read_loss(), rel=1e-5)
+    np.testing.assert_allclose(a.ent.grad.numpy(), b.ent.grad.numpy(), rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(a.rel.grad.numpy(), b.rel.grad.numpy(), rtol=1e-4, atol=1e-6)
+    assert np.array_equal(a.ent.touched.numpy() != 0, b.ent.touched.numpy() != 0)
+
+
+@pytest.mark.parametrize("opt", ["Adagrad", "SGD"])
+def test_emulated_one_launch_step_equals_score_then_optimiser(cpu_engine_oct, monkeypatch, opt):
+    """k_step_sampled_oct (the bench's headline kernel: score + grid barrier + octet row optimiser in one cooperative
+    launch) against the two-launch path (octet scorer, then k_rowopt_pair) with the same sampling seed."""
+    rng = np.random.default_rng(19)
+    t1, t2, kg1, kg2, tset, make = _sampled_setup(cpu_engine_oct, rng, opt)
+    fused, split = make(), make()
+    for step in range(3):
+        fused.step_sampled(kg1, kg2, tset, 32, 6, step, 777)
+    monkeypatch.setenv("OEA_NO_FUSE", "1")
+    for step in range(3):
+        split.step_sampled(kg1, kg2, tset, 32, 6, step, 777)
+    assert fused.read_loss() == pytest.approx(split.read_loss(), rel=1e-5)
+    for x, y in ((fused.ent, split.ent), (fused.rel, split.rel)):
+        np.testing.assert_allclose(x.raw().numpy(), y.raw().numpy(), rtol=1e-4, atol=1e-6)
+        if opt == "Adagrad":
+            np.testing.assert_allclose(x.state1.numpy(), y.state1.numpy(), rtol=1e-4, atol=1e-6)
+        assert not x.grad.any() and not x.touched.any()
+    assert not torch.equal(fused.ent.raw(), make().ent.raw())           # the steps did move the tables
