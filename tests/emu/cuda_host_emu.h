@@ -27,6 +27,10 @@
 #define cudaMemcpyAsync(D, S, N, KIND, ST) (memcpy((D), (S), (N)), cudaSuccess)
 #define cudaStreamSynchronize(ST) (cudaSuccess)
 #define cudaFuncSetAttribute(...) (cudaSuccess)
+/* launches and copies are synchronous and in program order: stream / event ordering is already satisfied */
+#define cudaStreamWaitEvent(...) (cudaSuccess)
+#define cudaEventRecord(...) (cudaSuccess)
+#define cudaEventSynchronize(...) (cudaSuccess)
 
 #undef __shared__
 #define __shared__ static

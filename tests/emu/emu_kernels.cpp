@@ -11,4 +11,5 @@
 #include "../../openea_b200/csrc/oea_spmm.cu"
 #include "../../openea_b200/csrc/oea_triple.cu"
 #include "../../openea_b200/csrc/oea_sim.cu"
+#include "../../openea_b200/csrc/oea_pipeline.cu"
 

@@ -282,3 +282,50 @@ def test_emulated_one_launch_step_equals_score_then_optimiser(cpu_engine_oct, mo
             np.testing.assert_allclose(x.state1.numpy(), y.state1.numpy(), rtol=1e-4, atol=1e-6)
         assert not x.grad.any() and not x.touched.any()
     assert not torch.equal(fused.ent.raw(), make().ent.raw())           # the steps did move the tables
+
+
+@pytest.mark.parametrize("grouped", ["0", "1"])
+def test_emulated_pipelined_host_step_equals_the_synchronous_one(cpu_engine, monkeypatch, grouped):
+    """oea_triple_step_fed_host_submit / _collect (two slots with their own index buffers and loss scalars; the stream /
+    event ordering is trivially satisfied on the emulator) against oea_triple_step_fed_host on the same batches: slot
+    bookkeeping, buffer offsets, the per-step losses and the final tables — also with the grouped scorer selected."""
+    monkeypatch.setenv("OEA_FED_GROUPED", grouped)
+    rng = np.random.default_rng(23)
+    d, n_ent, n_rel = 20, 60, 7
+    ent, rel = make_tables(rng, n_ent, n_rel, d)
+    cfg = cpu_engine.loss_cfg("limited", "L2", 0.01, 2.0, 0.2)
+    batches = [tuple(_t(x) for x in make_batch(rng, n_ent, n_rel, 16, 3)) for _ in range(5)]
+    make = lambda: cpu_engine.TripleTrainer(cpu_engine.EmbeddingTable(ent, True, device="cpu"),
+                                            cpu_engine.EmbeddingTable(rel, True, device="cpu"), cfg, 0.01)
+    a = make()
+    a._loss_pinned = torch.zeros(1, dtype=torch.float64)
+    want = [a.step_fed_host(p, n) for p, n in batches]
+    b = make()
+    idx = [torch.empty(3 * 16 * 4, dtype=torch.int32) for _ in range(2)]
+    loss_dev = [torch.zeros(1, dtype=torch.float64) for _ in range(2)]
+    loss_host = [torch.zeros(1, dtype=torch.float64) for _ in range(2)]
+    vp2 = lambda x, y: (C.c_void_p * 2)(x, y)
+    pipe = L.FedPipeline(0x10, 0x20, vp2(0x30, 0x31), vp2(0x40, 0x41), vp2(idx[0].data_ptr(), idx[1].data_ptr()),
+                         vp2(loss_dev[0].data_ptr(), loss_dev[1].data_ptr()), vp2(loss_host[0].data_ptr(), loss_host[1].data_ptr()))
+    lib = L.load()
+    got = []
+
+    def submit(slot, pos, neg):
+        opt = cpu_engine.opt_cfg(b.ent, b.lr)
+        L.check(lib.oea_triple_step_fed_host_submit(C.byref(b.ent.c_struct()), C.byref(b.rel.c_struct()), C.byref(pipe), slot,
+                                                    C.c_void_p(pos.data_ptr()), pos.shape[1], C.c_void_p(neg.data_ptr()),
+                                                    neg.shape[1], C.byref(b.loss), C.byref(opt)), "submit")
+
+    def collect(slot):
+        out = C.c_float(0.0)
+        L.check(lib.oea_triple_step_fed_host_collect(C.byref(pipe), slot, C.byref(out)), "collect")
+        return float(out.value)
+    for i, (p, n) in enumerate(batches):
+        submit(i % 2, p, n)
+        if i:
+            got.append(collect((i - 1) % 2))
+    got.append(collect((len(batches) - 1) % 2))
+    np.testing.assert_allclose(got, want, rtol=1e-5)
+    for x, y in ((a.ent, b.ent), (a.rel, b.rel)):
+        np.testing.assert_allclose(y.raw().numpy(), x.raw().numpy(), rtol=1e-5, atol=1e-7)
+        assert not y.grad.any() and not y.touched.any()
