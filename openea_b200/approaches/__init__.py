@@ -1,4 +1,5 @@
 from openea_b200.approaches.aligne import AlignE
+from openea_b200.approaches.attre import AttrE
 from openea_b200.approaches.bootea import BootEA
 from openea_b200.approaches.bootea_transh import BootEA_TransH
 from openea_b200.approaches.imuse import IMUSE
@@ -22,7 +23,6 @@ except ImportError:  # pragma: no cover
 
 JAPE = out_of_scope("JAPE", "attribute skip-gram encoder")
 Attr2Vec = out_of_scope("Attr2Vec", "attribute skip-gram encoder")
-AttrE = out_of_scope("AttrE", "character-level literal encoder")
 RSN4EA = out_of_scope("RSN4EA", "recurrent skipping network over paths")
 MultiKE = out_of_scope("MultiKE", "multi-view literal/attribute encoders")
 GMNN = out_of_scope("GMNN", "graph matching network")

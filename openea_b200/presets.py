@@ -122,3 +122,11 @@ def imuse(scale="15K"):
                  neg_triple_num=1, learning_rate=0.01, optimizer="SGD", batch_size=5000 if scale == "15K" else 20000,
                  start_valid=10, eval_metric="inner", eval_norm=True, sim_thresholds_ent=0.6, sim_thresholds_attr=0.6,
                  interactive_model_iter_num=1)
+
+
+def attre(scale="15K"):
+    """run/args/attre_args_*.json."""
+    return _args(embedding_module="AttrE", alignment_module="sharing", dim=100, init="normal", ent_l2_norm=True,
+                 rel_l2_norm=True, attr_l2_norm=True, char_l2_norm=True, loss_norm="L2", margin=1.5, loss="margin-based",
+                 neg_sampling="uniform", neg_triple_num=1, learning_rate=0.01, optimizer="SGD",
+                 batch_size=5000 if scale == "15K" else 20000, eval_metric="inner", eval_norm=True, literal_len=5)

@@ -19,6 +19,7 @@ What is restated HERE (from the TF 1.x documentation / op definitions, not execu
     lr_t = lr·√(1−β₂ᵗ)/(1−β₁ᵗ), ε outside the root); Adadelta (ρ .95, ε 1e-8).
 Arithmetic is float64 so that a golden is the mathematical value of the reference's graph to ~1e-15.
 """
+import builtins
 import contextlib
 import math
 import types
@@ -27,6 +28,7 @@ import numpy as np
 import torch
 
 DT = torch.float64
+builtins_slice = builtins.slice
 int32, int64, float32, float64 = "int32", "int64", "float32", "float64"
 _VARIABLES = []
 
@@ -254,6 +256,47 @@ def sparse_add(a, b, name=None):
 
 def sparse_reshape(sp_input, shape, name=None):
     return _wrap(sp_input)
+
+
+def unstack(value, num=None, axis=0, name=None):
+    x = _wrap(value)
+    n = num if num is not None else x.shape[axis]
+    return [Tensor(lambda a, i=i: a.select(axis, i), (x,), "unstack") for i in range(n)]
+
+
+def stack(values, axis=0, name=None):
+    return Tensor(lambda *v: torch.stack(v, dim=axis), tuple(_wrap(v) for v in values), "stack")
+
+
+def reverse(tensor, axis, name=None):
+    return Tensor(lambda a: torch.flip(a, dims=list(axis)), (_wrap(tensor),), "reverse")
+
+
+def _static(x):
+    """A Python int from a constant node (loop counters, slice offsets): evaluated without feeds."""
+    return int(x._eval({})) if isinstance(x, Tensor) else int(x)
+
+
+def slice(input_, begin, size, name=None):                       # noqa: A001
+    b, n = [_static(v) for v in begin], [_static(v) for v in size]
+
+    def f(a):
+        idx = tuple(builtins_slice(lo, None if cnt == -1 else lo + cnt) for lo, cnt in zip(b, n))
+        return a[idx]
+    return Tensor(f, (_wrap(input_),), "slice")
+
+
+def greater(x, y, name=None):
+    return Tensor(lambda a, b: a > b, (_wrap(x), _wrap(y)), "greater")
+
+
+def while_loop(cond, body, loop_vars, **kw):
+    """Unrolled at graph-construction time: the reference's only loop (attre.py:89-107) counts a constant down, so its
+    condition can be evaluated without feeds while the body keeps building lazy nodes."""
+    variables = list(loop_vars)
+    while bool(cond(*variables)._eval({})):
+        variables = list(body(*variables))
+    return variables
 
 
 def tile(x, multiples, name=None):

@@ -203,6 +203,57 @@ def generate():
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
 
 
+def generate_attre():
+    """AttrE (approaches/attre.py:109-188): the structure loss, the character-level loss over composed literal vectors
+    (n-gram compositional function with its tf.while_loop) and the joint loss, each with its own SGD optimiser.
+    → tests/golden/path_i_attre.npz"""
+    mod = import_reference("openea.approaches.attre")
+    tf = tf1_shim
+    tf.reset_default_graph()
+    rng = np.random.default_rng(41)
+    n_attr, n_val, n_char, lit, batch, dim = 5, 30, 9, 4, 8, 12
+    chars = rng.integers(0, n_char, (n_val, lit))
+    chars[rng.random((n_val, lit)) < 0.15] = 0                    # padding / rare characters
+    model = mod.AttrE()
+    model.args = types.SimpleNamespace(**dict(BASE, loss="margin-based", optimizer="SGD", neg_triple_num=1, batch_size=batch,
+                                              literal_len=lit, attr_l2_norm=True, char_l2_norm=True, dim=dim))
+    model.kgs = types.SimpleNamespace(entities_num=N_ENT, relations_num=N_REL, attributes_num=n_attr)
+    model.value_id_char_ids, model.char_list_size = chars.tolist(), n_char
+    model._define_variables()
+    model._define_embed_graph()
+    variables = tf.trainable_variables()
+    out = {"chars": chars.astype(np.int32), "dims": np.array([n_attr, n_val, n_char, lit, batch, dim])}
+    for v in variables:
+        start = (rng.standard_normal(tuple(v.value.shape)) * 2.0 / np.sqrt(dim)).astype(np.float32).astype(np.float64)
+        v.assign_numpy(start)
+        out["var0/" + v.name] = start
+    session = tf.Session()
+    kinds = ["triple", "ce", "joint", "ce", "triple", "joint"]
+    for i, kind in enumerate(kinds):
+        if kind == "triple":
+            fetch, feed = make_run("triple", 1, rng, model)
+        elif kind == "ce":
+            pos = np.stack([rng.integers(0, N_ENT, batch), rng.integers(0, n_attr, batch), rng.integers(0, n_val, batch)])
+            neg = pos.copy()
+            neg[0] = rng.integers(0, N_ENT, batch)
+            fetch = ("triple_loss_ce", "triple_optimizer_ce")
+            feed = {"pos_es": pos[0], "pos_as": pos[1], "pos_vs": pos[2], "neg_es": neg[0], "neg_as": neg[1], "neg_vs": neg[2]}
+        else:
+            fetch, feed = ("joint_loss", "optimizer_joint"), {"joint_ents": rng.permutation(N_ENT)[:25]}
+        loss, _ = session.run([getattr(model, fetch[0]), getattr(model, fetch[1])],
+                              feed_dict={getattr(model, key): np.asarray(val) for key, val in feed.items()})
+        out["run%d/loss" % i] = np.float64(loss)
+        out["run%d/kind" % i] = np.frombuffer(kind.encode(), dtype=np.uint8)
+        for key, val in feed.items():
+            out["run%d/feed/%s" % (i, key)] = np.asarray(val).astype(np.int32)
+    for v in variables:
+        out["var_final/" + v.name] = v.value.detach().numpy().copy()
+    print("attre: losses %s" % ["%.6g" % float(out["run%d/loss" % i]) for i in range(len(kinds))], [v.name for v in variables])
+    path = os.path.join(ROOT, "tests", "golden", "path_i_attre.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
 def generate_gcn_align():
     """Path (ii), GCN-Align: the reference's GCN_Align_Unit (gcn_align.py:498-539) for the structure branch (featureless,
     l2-normalised entity table) and the attribute branch (sparse features · weights), its align_loss and its
@@ -382,6 +433,7 @@ if __name__ == "__main__":
     if not os.path.isdir(REF_SRC):
         sys.exit("the reference is not present: goldens can only be generated where /root/reference exists")
     generate()
+    generate_attre()
     generate_gcn_align()
     generate_rdgcn()
     generate_alinet()

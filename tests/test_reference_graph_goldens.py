@@ -346,3 +346,65 @@ def test_alinet_model_on_the_emulator_reproduces_the_reference_graph(cpu_engine,
 @pytest.mark.first_hw_run
 def test_alinet_model_on_the_gpu_reproduces_the_reference_graph(cuda_device):
     replay_alinet("cuda")
+
+
+# ---- AttrE: structure + character-level + joint losses, from the reference's _define_embed_graph ----------------------
+AT = np.load(os.path.join(os.path.dirname(GOLDEN), "path_i_attre.npz"))
+
+
+def replay_attre(engine, device, monkeypatch):
+    from openea_b200.approaches.attre import AttrE, ngram_weights
+    from openea_b200.modules.base import initializers
+    n_attr, n_val, n_char, lit, batch, dim = (int(x) for x in AT["dims"])
+    monkeypatch.setattr(initializers, "_make", lambda values, norm, optimizer=None: engine.EmbeddingTable(
+        values, bool(norm), optimizer or initializers._DEFAULT_OPT, device))
+    model = AttrE()
+    model.args = types.SimpleNamespace(dim=dim, init="normal", ent_l2_norm=True, rel_l2_norm=True, attr_l2_norm=True,
+                                       char_l2_norm=True, loss="margin-based", loss_norm="L2", margin=1.5, learning_rate=0.01,
+                                       optimizer="SGD", batch_size=batch, neg_triple_num=1, literal_len=lit)
+    model.kgs = types.SimpleNamespace(entities_num=40, relations_num=6, attributes_num=n_attr)
+    model.value_id_char_ids, model.char_list_size = AT["chars"], n_char
+    model._define_variables()
+    model._define_embed_graph()
+    names = sorted(k[len("var0/"):] for k in AT.files if k.startswith("var0/"))
+    for name in names:
+        tab = getattr(model, name)
+        tab.weight[:, :dim] = torch.as_tensor(AT["var0/" + name], dtype=torch.float32, device=tab.weight.device)
+    # the composition weights are the suffix-mean sum of attre.py:89-107 written out
+    np.testing.assert_allclose(ngram_weights(4), [1 / 4 + 1 / 3 + 1 / 2 + 1, 1 / 4 + 1 / 3 + 1 / 2, 1 / 4 + 1 / 3, 1 / 4], rtol=1e-6)
+    i = 0
+    while "run%d/loss" % i in AT.files:
+        kind = bytes(AT["run%d/kind" % i]).decode()
+        f = {k[len("run%d/feed/" % i):]: AT[k] for k in AT.files if k.startswith("run%d/feed/" % i)}
+        dev = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.int32, device=device)
+        if kind == "triple":
+            tr = model.triple_trainer
+            tr.score_fed(_hrt(f, ("pos_hs", "pos_rs", "pos_ts"), device), _hrt(f, ("neg_hs", "neg_rs", "neg_ts"), device))
+            tr.apply()
+            got = tr.read_loss()
+        elif kind == "ce":
+            got = float(model.ce_step(_hrt(f, ("pos_es", "pos_as", "pos_vs"), device), _hrt(f, ("neg_es", "neg_as", "neg_vs"), device)))
+        else:
+            got = float(model.joint_step(dev(f["joint_ents"])))
+        assert got == pytest.approx(float(AT["run%d/loss" % i]), rel=2e-4), (i, kind)
+        i += 1
+    for name in names:
+        start, want = AT["var0/" + name], AT["var_final/" + name]
+        got = getattr(model, name).raw().cpu().numpy()
+        move = np.abs(want - start).max()
+        assert move > 0, name
+        np.testing.assert_allclose(got - start, want - start, rtol=5e-3, atol=3e-6 + 2e-3 * move, err_msg=name)
+
+
+def test_attre_on_the_emulator_reproduces_the_reference_graph(cpu_engine, monkeypatch):
+    import ctypes as C
+    from openea_b200.modules.base import losses
+    monkeypatch.setattr(losses, "_stream_ptr", lambda: C.c_void_p(0))
+    replay_attre(cpu_engine, "cpu", monkeypatch)
+
+
+@pytest.mark.gpu
+@pytest.mark.first_hw_run
+def test_attre_on_the_gpu_reproduces_the_reference_graph(cuda_device, monkeypatch):
+    from openea_b200 import engine
+    replay_attre(engine, "cuda", monkeypatch)

@@ -114,3 +114,20 @@ def test_imuse_lifecycle(cuda_device, tiny_kgs, tmp_path):
     if model.aligned_ent_pair_set:
         assert align[-1] < align[0], (align[0], align[-1])
     assert _hits1(out, "accurate results:") >= 0.0       # the result line exists; accuracy is calibrated once this has run on a GPU
+
+
+def test_attre_lifecycle(cuda_device, tiny_kgs, tmp_path):
+    """set_args / set_kgs / init / run / test / save of AttrE: structure, character-level and joint passes per epoch."""
+    import re
+    from openea_b200 import presets
+    from openea_b200.approaches import AttrE
+    from tests.test_e2e_gpu import _hits1, _run
+    args = presets.attre("15K")
+    args.batch_size, args.max_epoch, args.start_valid, args.dim = 1000, 40, 1000, 32
+    model, out = _run(AttrE, args, tiny_kgs, "sharing", tmp_path)
+    for tag in (r"avg\. triple loss:\s*([0-9.]+)", r"CE, avg\. triple loss:\s*([0-9.]+)", r"joint learning loss:\s*([0-9.]+)"):
+        vals = [float(x) for x in re.findall(tag, out)]
+        assert len(vals) >= 40 and all(np.isfinite(vals)), tag
+    ce = [float(x) for x in re.findall(r"CE, avg\. triple loss:\s*([0-9.]+)", out)]
+    assert ce[-1] < ce[0], (ce[0], ce[-1])
+    assert _hits1(out, "accurate results:") >= 0.0       # the result line exists; accuracy is calibrated once this has run on a GPU
