@@ -18,6 +18,7 @@ python bench.py --workload bootea_100k --steps 40 --warmup 8 > gpurun_out/r02a/b
 python scripts/bench_approaches.py > gpurun_out/r02a/approaches.json 2>> gpurun_out/r02a/bench.err
 python scripts/bench_ext.py > gpurun_out/r02a/score_family.jsonl 2>> gpurun_out/r02a/bench.err
 python scripts/bench_fed_grouped.py > gpurun_out/r02a/fed_grouped.jsonl 2>> gpurun_out/r02a/bench.err
+python scripts/bench_weighted.py > gpurun_out/r02a/weighted.jsonl 2>> gpurun_out/r02a/bench.err
 # 4. ncu of the score family's scorer (TransD limited loss is the heaviest instantiation)
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_model_fed -s 20 -c 1 -o gpurun_out/r02a/model_fed python scripts/bench_ext.py > gpurun_out/r02a/ncu.log 2>&1
 # 5. what bounds K1: gather throughput vs rows in flight, dependent-chain latency, red.v4 throughput, grid-barrier cost
