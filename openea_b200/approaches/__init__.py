@@ -4,6 +4,7 @@ from openea_b200.approaches.bootea import BootEA
 from openea_b200.approaches.bootea_transh import BootEA_TransH
 from openea_b200.approaches.imuse import IMUSE
 from openea_b200.approaches.iptranse import IPTransE
+from openea_b200.approaches.jape import JAPE
 from openea_b200.approaches.mtranse import MTransE
 from openea_b200.approaches.sea import SEA
 from openea_b200.models._stubs import out_of_scope
@@ -21,8 +22,7 @@ try:
 except ImportError:  # pragma: no cover
     RDGCN = out_of_scope("RDGCN", "not built yet")
 
-JAPE = out_of_scope("JAPE", "attribute skip-gram encoder")
-Attr2Vec = out_of_scope("Attr2Vec", "attribute skip-gram encoder")
+Attr2Vec = out_of_scope("Attr2Vec", "stand-alone attribute skip-gram model (JAPE carries its own auxiliary, approaches/jape.py)")
 RSN4EA = out_of_scope("RSN4EA", "recurrent skipping network over paths")
 MultiKE = out_of_scope("MultiKE", "multi-view literal/attribute encoders")
 GMNN = out_of_scope("GMNN", "graph matching network")

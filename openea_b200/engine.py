@@ -389,13 +389,15 @@ class ModelTrainer:
         ptr = lambda t: C.pointer(t.c_struct()) if t is not None else None
         return L.Model(self.kind, *[ptr(t) for t in self.tables])
 
-    def score_fed(self, pos, neg=None, loss_out=None):
+    def score_fed(self, pos, neg=None, loss_out=None, scale=None):
         """pos / neg: int32 device tensors [3, n] (h | r | t rows); accumulates gradients into every table and adds
-        the batch loss into loss_out (default self.loss_dev)."""
+        the batch loss into loss_out (default self.loss_dev).  `scale` multiplies loss and gradient (default 1, or
+        1 / batch for `mean_loss`); it may be negative (JAPE's −α·Σ s⁻ term)."""
         out = self.loss_dev if loss_out is None else loss_out
         n_pos = pos.shape[1]
         n_neg = 0 if neg is None else neg.shape[1]
-        scale = 1.0 / max(1, n_pos + n_neg) if self.mean_loss else 1.0
+        if scale is None:
+            scale = 1.0 / max(1, n_pos + n_neg) if self.mean_loss else 1.0
         np_ = lambda t, i: C.c_void_p(0 if t is None or t.shape[1] == 0 else t[i].data_ptr())
         model = self._c_model()
         L.check(self.lib.oea_model_score_fed(

@@ -130,3 +130,12 @@ def attre(scale="15K"):
                  rel_l2_norm=True, attr_l2_norm=True, char_l2_norm=True, loss_norm="L2", margin=1.5, loss="margin-based",
                  neg_sampling="uniform", neg_triple_num=1, learning_rate=0.01, optimizer="SGD",
                  batch_size=5000 if scale == "15K" else 20000, eval_metric="inner", eval_norm=True, literal_len=5)
+
+
+def jape(scale="15K"):
+    """run/args/jape_args_*.json."""
+    return _args(embedding_module="JAPE", alignment_module="sharing", dim=100, init="normal", ent_l2_norm=True,
+                 rel_l2_norm=True, loss_norm="L2", learning_rate=0.01, optimizer="Adagrad",
+                 batch_size=5000 if scale == "15K" else 20000, attr_max_epoch=200, top_attr_threshold=0.9,
+                 attr_sim_mat_threshold=0.95, attr_sim_mat_beta=0.001, neg_alpha=0.1, neg_sampling="uniform",
+                 neg_triple_num=1, sub_mat_size=1000, eval_metric="inner", eval_norm=False)

@@ -92,6 +92,8 @@ CASES = {
     "bootea_transh": ("openea.approaches.bootea_transh", "BootEA_TransH", {},
                       ["_define_variables", "_define_embed_graph", "_define_alignment_graph"],
                       [("triple", 3), ("align", 0), ("triple", 3)]),
+    "jape": ("openea.approaches.jape", "JAPE", dict(neg_alpha=0.1), ["_define_variables", "_define_embed_graph"],
+             [("triple", 2), ("triple", 2)]),
     "iptranse": ("openea.approaches.iptranse", "IPTransE", dict(neg_triple_num=1),
                  ["_define_variables", "_define_embed_graph", "_define_alignment_graph"],
                  [("ptranse", 1), ("ipt_align", 1), ("ptranse", 1)]),

@@ -131,3 +131,20 @@ def test_attre_lifecycle(cuda_device, tiny_kgs, tmp_path):
     ce = [float(x) for x in re.findall(r"CE, avg\. triple loss:\s*([0-9.]+)", out)]
     assert ce[-1] < ce[0], (ce[0], ce[-1])
     assert _hits1(out, "accurate results:") >= 0.0       # the result line exists; accuracy is calibrated once this has run on a GPU
+
+
+def test_jape_lifecycle(cuda_device, tiny_kgs, tmp_path):
+    """set_args / set_kgs / init / run / test / save of JAPE: the attribute auxiliary, then epochs of the signed-scale
+    structure loss with the evaluated (never optimised) attribute-similarity loss printed next to it."""
+    import re
+    from openea_b200 import presets
+    from openea_b200.approaches import JAPE
+    from tests.test_e2e_gpu import _hits1, _run
+    args = presets.jape("15K")
+    args.batch_size, args.max_epoch, args.start_valid, args.dim = 1000, 60, 1000, 32
+    args.attr_max_epoch, args.sub_mat_size = 3, 50
+    model, out = _run(JAPE, args, tiny_kgs, "sharing", tmp_path)
+    triple = [float(x) for x in re.findall(r"avg\\. triple loss:\\s*(-?[0-9.]+)", out)]
+    assert len(triple) == 60 and triple[-1] < triple[0], (triple[0], triple[-1])
+    assert len(re.findall(r"sim loss:", out)) == 60
+    assert _hits1(out, "accurate results:") >= 0.0       # the result line exists; accuracy is calibrated once this has run on a GPU
