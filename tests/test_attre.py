@@ -5,7 +5,6 @@ import re
 import types
 
 import numpy as np
-import pytest
 import torch
 
 from openea_b200.approaches import attre as at
