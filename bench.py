@@ -373,6 +373,30 @@ def probe_pipelined_e2e(args):
         res["grouped_scorer"] = {"value": None, "note": "failed: %r" % (exc,)}
     finally:
         os.environ.pop("OEA_FED_GROUPED", None)
+    try:     # and with OEA_FED_FUSED=1: grouped scoring + row optimiser as one cooperative launch per step
+        os.environ["OEA_FED_FUSED"] = "1"
+        restore()
+        got = []
+        for i in range(6):
+            pipe.submit(i % 2, *batches[i])
+            if i >= 1:
+                got.append(pipe.collect((i - 1) % 2))
+        got.append(pipe.collect(5 % 2))
+        rel_f = max(abs(a - b) / max(1e-12, abs(b)) for a, b in zip(got, want))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(K):
+            pipe.submit(i % 2, *batches[i % 8])
+            if i >= 1:
+                pipe.collect((i - 1) % 2)
+        pipe.collect((K - 1) % 2)
+        dt = time.perf_counter() - t0
+        res["one_launch_step"] = {"value": n_pos_h * K / dt, "ms_per_step": 1e3 * dt / K,
+                                  "loss_max_rel_diff_vs_sync_api": rel_f, "losses_agree": bool(rel_f <= 1e-4)}
+    except Exception as exc:
+        res["one_launch_step"] = {"value": None, "note": "failed: %r" % (exc,)}
+    finally:
+        os.environ.pop("OEA_FED_FUSED", None)
     print(json.dumps(res))
     return 0
 

@@ -157,6 +157,15 @@ int oea_triple_score_margin_weighted(const oea_table* ent, const oea_table* rel,
 int oea_pair_distance_loss(const oea_table* ent, const int32_t* ids_a, const int32_t* ids_b, int32_t n,
                            const float* weights, float scale, double* loss_out, void* stream);
 
+/* The whole fed step — oea_triple_score_fed_grouped followed by oea_rowopt_apply_pair — as ONE cooperative launch
+ * (grouped scoring, grid barrier, row optimiser): session.run([triple_loss, triple_optimizer], feed_dict) of
+ * models/basic_model.py:222-232 on device index vectors.  Squared-L2 score, pitch <= 256, Adagrad / SGD; returns
+ * OEA_ERR_KIND for anything else (take the two-call path then).  Opt-in on the host-index steps: OEA_FED_FUSED=1. */
+int oea_triple_step_fed_grouped(const oea_table* ent, const oea_table* rel,
+                                const int32_t* pos_h, const int32_t* pos_r, const int32_t* pos_t, int32_t n_pos,
+                                const int32_t* neg_h, const int32_t* neg_r, const int32_t* neg_t, int32_t n_neg,
+                                const oea_loss_cfg* loss, const oea_opt_cfg* opt, double* loss_out, void* stream);
+
 /* Optimiser step on a table whose `grad` was filled by a score call.  Replaces
  * optimizer.apply_gradients of modules/base/optimizers.py:4-7.  Adagrad / SGD touch only flagged
  * rows (identical to TF's dense update because untouched rows have g = 0); Adam is dense.

@@ -42,13 +42,21 @@ extern "C" int oea_triple_step_fed_host_submit(const oea_table* ent, const oea_t
     // OEA_FED_GROUPED=1: same opt-in as oea_triple_step_fed_host (a positive scored together with its negatives)
     const char* grouped_env = getenv("OEA_FED_GROUPED");
     const bool grouped = grouped_env && grouped_env[0] == '1' && n_pos > 0 && n_neg % n_pos == 0;
-    int rc = grouped
-        ? oea_triple_score_fed_grouped(ent, rel, dpos, dpos + n_pos, dpos + 2 * (size_t)n_pos, n_pos,
-                                       dneg, dneg + n_neg, dneg + 2 * (size_t)n_neg, n_neg, loss, pipe->dev_loss[slot], comp)
-        : oea_triple_score_fed(ent, rel, dpos, dpos + n_pos, dpos + 2 * (size_t)n_pos, n_pos,
-                               dneg, dneg + n_neg, dneg + 2 * (size_t)n_neg, n_neg, loss, pipe->dev_loss[slot], comp);
+    const char* fused_env = getenv("OEA_FED_FUSED");     // one cooperative launch (oea_triple_step_fed_grouped) where it applies
+    int rc = OEA_ERR_KIND;
+    if (fused_env && fused_env[0] == '1' && n_pos > 0 && n_neg % n_pos == 0)
+        rc = oea_triple_step_fed_grouped(ent, rel, dpos, dpos + n_pos, dpos + 2 * (size_t)n_pos, n_pos,
+                                         dneg, dneg + n_neg, dneg + 2 * (size_t)n_neg, n_neg, loss, opt, pipe->dev_loss[slot], comp);
+    if (rc == OEA_ERR_KIND) {
+        rc = grouped
+            ? oea_triple_score_fed_grouped(ent, rel, dpos, dpos + n_pos, dpos + 2 * (size_t)n_pos, n_pos,
+                                           dneg, dneg + n_neg, dneg + 2 * (size_t)n_neg, n_neg, loss, pipe->dev_loss[slot], comp)
+            : oea_triple_score_fed(ent, rel, dpos, dpos + n_pos, dpos + 2 * (size_t)n_pos, n_pos,
+                                   dneg, dneg + n_neg, dneg + 2 * (size_t)n_neg, n_neg, loss, pipe->dev_loss[slot], comp);
+        if (rc) return rc;
+        rc = oea_rowopt_apply_pair(ent, rel, opt, comp);
+    }
     if (rc) return rc;
-    rc = oea_rowopt_apply_pair(ent, rel, opt, comp); if (rc) return rc;
     OEA_CUDA_TRY(cudaMemcpyAsync(pipe->host_loss[slot], pipe->dev_loss[slot], sizeof(double), cudaMemcpyDeviceToHost, comp));
     OEA_CUDA_TRY(cudaEventRecord(computed, comp));
     return OEA_OK;

@@ -14,6 +14,7 @@
 // vector reductions (red.global.add.v4.f32) into the L2-resident gradient table.
 #include <stdlib.h>
 #include "oea_rowmath.cuh"
+#include "oea_rowopt.cuh"
 #include "oea_sampler.cuh"
 #include <cooperative_groups.h>
 
@@ -548,78 +549,6 @@ k_score_sampled_oct(TableDev ent, TableDev rel, const __grid_constant__ SampledP
     oct_score_body(ent, rel, P, cfg, loss_out, dbg, s_loss, s_stage);
 }
 
-// Row optimiser over the concatenated row space [ent rows | rel rows] in the octet layout: a warp reads 32 row
-// flags at once, then finishes the flagged rows four at a time (octet o takes the o-th flagged row; 12 independent
-// 16-byte loads per lane are in flight).  TF1 Adagrad / SGD as in k_rowopt.
-struct OptTab {
-    float* w;
-    float* g;
-    float* s1;
-    int32_t* touched;
-    int rows;
-};
-
-template <int KIND>
-__device__ __forceinline__ void oct_rowopt_body(const OptTab& A, const OptTab& B, int pitch, float lr, int warp_global,
-                                                int n_warps) {
-    const int lane = threadIdx.x & 31, oct = lane >> 3, l = lane & 7;
-    const int p4 = pitch >> 2;
-    const int total = A.rows + B.rows;
-    const int n_quads = (total + 3) >> 2;          // work unit: 4 consecutive rows, one per octet
-    auto flag_of = [&](int quad) -> int32_t* {
-        const int r = 4 * quad + oct;
-        if (quad >= n_quads || r >= total) return nullptr;
-        return r < A.rows ? A.touched + r : B.touched + (r - A.rows);
-    };
-    int quad = warp_global;
-    int32_t* flag = flag_of(quad);
-    int on = (flag != nullptr && l == 0) ? *flag : 0;
-    while (quad < n_quads) {
-        // the next quad's flag is in flight while this quad's rows are processed
-        const int next = quad + n_warps;
-        int32_t* nflag = flag_of(next);
-        const int non = (nflag != nullptr && l == 0) ? *nflag : 0;
-        const bool mine = __shfl_sync(OEA_FULL, on, oct << 3) != 0;
-        if (mine) {
-            const int rr = 4 * quad + oct;
-            const bool first = rr < A.rows;
-            const OptTab& T = first ? A : B;
-            const size_t off = (size_t)(first ? rr : rr - A.rows) * pitch;
-            if (l == 0) *flag = 0;
-            for (int q0 = 0; q0 < p4; q0 += 32) {
-                float4 g[4], x[4], a[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int q = q0 + l + 8 * i;
-                    if (q < p4) {
-                        g[i] = *reinterpret_cast<const float4*>(T.g + off + 4 * q);
-                        x[i] = *reinterpret_cast<const float4*>(T.w + off + 4 * q);
-                        if (KIND == OEA_OPT_ADAGRAD) a[i] = *reinterpret_cast<const float4*>(T.s1 + off + 4 * q);
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int q = q0 + l + 8 * i;
-                    if (q < p4) {
-                        if (KIND == OEA_OPT_ADAGRAD) {
-                            a[i].x = fmaf(g[i].x, g[i].x, a[i].x); a[i].y = fmaf(g[i].y, g[i].y, a[i].y);
-                            a[i].z = fmaf(g[i].z, g[i].z, a[i].z); a[i].w = fmaf(g[i].w, g[i].w, a[i].w);
-                            x[i].x -= lr * g[i].x * rsqrtf(a[i].x); x[i].y -= lr * g[i].y * rsqrtf(a[i].y);
-                            x[i].z -= lr * g[i].z * rsqrtf(a[i].z); x[i].w -= lr * g[i].w * rsqrtf(a[i].w);
-                            *reinterpret_cast<float4*>(T.s1 + off + 4 * q) = a[i];
-                        } else {
-                            x[i].x -= lr * g[i].x; x[i].y -= lr * g[i].y; x[i].z -= lr * g[i].z; x[i].w -= lr * g[i].w;
-                        }
-                        *reinterpret_cast<float4*>(T.w + off + 4 * q) = x[i];
-                        *reinterpret_cast<float4*>(T.g + off + 4 * q) = f4(0.f);
-                    }
-                }
-            }
-        }
-        quad = next; flag = nflag; on = non;
-    }
-}
-
 // The whole sampled training step as ONE cooperative launch: score + gradients, grid barrier, row optimiser.
 // Saves the second launch and its ramp (≈ 6 µs of a 43 µs step at the 15K shape); the grid is one resident wave by
 // construction (grid_one_wave), which is what a cooperative launch requires.
@@ -876,13 +805,22 @@ extern "C" int oea_triple_step_fed_host(const oea_table* ent, const oea_table* r
     // (oea_triple_grouped.cu; opt-in until it has been timed on hardware)
     const char* grouped_env = getenv("OEA_FED_GROUPED");
     const bool grouped = grouped_env && grouped_env[0] == '1' && n_pos > 0 && n_neg % n_pos == 0;
-    int rc = grouped
-        ? oea_triple_score_fed_grouped(ent, rel, dpos, dpos + n_pos, dpos + 2 * (size_t)n_pos, n_pos,
-                                       dneg, dneg + n_neg, dneg + 2 * (size_t)n_neg, n_neg, loss, dev_loss_ws, stream)
-        : oea_triple_score_fed(ent, rel, dpos, dpos + n_pos, dpos + 2 * (size_t)n_pos, n_pos,
-                               dneg, dneg + n_neg, dneg + 2 * (size_t)n_neg, n_neg, loss, dev_loss_ws, stream);
+    // OEA_FED_FUSED=1: grouped scoring and the row optimiser as one cooperative launch where that kernel applies
+    const char* fused_env = getenv("OEA_FED_FUSED");
+    int rc = OEA_ERR_KIND;
+    if (fused_env && fused_env[0] == '1' && n_pos > 0 && n_neg % n_pos == 0)
+        rc = oea_triple_step_fed_grouped(ent, rel, dpos, dpos + n_pos, dpos + 2 * (size_t)n_pos, n_pos,
+                                         dneg, dneg + n_neg, dneg + 2 * (size_t)n_neg, n_neg, loss, opt, dev_loss_ws, stream);
+    if (rc == OEA_ERR_KIND) {
+        rc = grouped
+            ? oea_triple_score_fed_grouped(ent, rel, dpos, dpos + n_pos, dpos + 2 * (size_t)n_pos, n_pos,
+                                           dneg, dneg + n_neg, dneg + 2 * (size_t)n_neg, n_neg, loss, dev_loss_ws, stream)
+            : oea_triple_score_fed(ent, rel, dpos, dpos + n_pos, dpos + 2 * (size_t)n_pos, n_pos,
+                                   dneg, dneg + n_neg, dneg + 2 * (size_t)n_neg, n_neg, loss, dev_loss_ws, stream);
+        if (rc) return rc;
+        rc = oea_rowopt_apply_pair(ent, rel, opt, stream);
+    }
     if (rc) return rc;
-    rc = oea_rowopt_apply_pair(ent, rel, opt, stream); if (rc) return rc;
     OEA_CUDA_TRY(cudaMemcpyAsync(loss_pinned_host, dev_loss_ws, sizeof(double), cudaMemcpyDeviceToHost, st));
     OEA_CUDA_TRY(cudaStreamSynchronize(st));
     *loss_host = (float)(*loss_pinned_host);

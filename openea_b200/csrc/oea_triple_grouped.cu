@@ -9,17 +9,20 @@
 //
 // Opt-in: oea_triple_step_fed_host uses it when OEA_FED_GROUPED=1 (until it has been timed on hardware);
 // tests/test_emu_triple_grouped.py checks it on the CPU warp emulator against the C oracle.
+#include <stdlib.h>
+#include <cooperative_groups.h>
+
 #include "oea_rowmath.cuh"
+#include "oea_rowopt.cuh"
 
 namespace oea {
 
 template <int SCORE, int VEC>
-__global__ void __launch_bounds__(kThreads)
-k_score_fed_grouped(TableDev ent, TableDev rel,
-                    const int32_t* __restrict__ ph, const int32_t* __restrict__ pr, const int32_t* __restrict__ pt, int n_pos,
-                    const int32_t* __restrict__ nh, const int32_t* __restrict__ nr, const int32_t* __restrict__ nt, int k,
-                    oea_loss_cfg cfg, double* __restrict__ loss_out) {
-    __shared__ double s_loss[kWarpsPerBlock];
+__device__ __forceinline__ void
+grouped_score_body(const TableDev& ent, const TableDev& rel,
+                   const int32_t* __restrict__ ph, const int32_t* __restrict__ pr, const int32_t* __restrict__ pt, int n_pos,
+                   const int32_t* __restrict__ nh, const int32_t* __restrict__ nr, const int32_t* __restrict__ nt, int k,
+                   const oea_loss_cfg& cfg, double* __restrict__ loss_out, double* s_loss) {
     const int lane = threadIdx.x & 31;
     const int warp_global = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     const int n_warps = gridDim.x * kWarpsPerBlock;
@@ -160,6 +163,30 @@ k_score_fed_grouped(TableDev ent, TableDev rel,
     acc.flush(warp_loss, loss_out);
 }
 
+template <int SCORE, int VEC>
+__global__ void __launch_bounds__(kThreads)
+k_score_fed_grouped(TableDev ent, TableDev rel,
+                    const int32_t* __restrict__ ph, const int32_t* __restrict__ pr, const int32_t* __restrict__ pt, int n_pos,
+                    const int32_t* __restrict__ nh, const int32_t* __restrict__ nr, const int32_t* __restrict__ nt, int k,
+                    oea_loss_cfg cfg, double* __restrict__ loss_out) {
+    __shared__ double s_loss[kWarpsPerBlock];
+    grouped_score_body<SCORE, VEC>(ent, rel, ph, pr, pt, n_pos, nh, nr, nt, k, cfg, loss_out, s_loss);
+}
+
+// The whole fed training step as ONE cooperative launch: grouped scoring + gradients, grid barrier, octet row optimiser
+// (the host-index step's two kernels and the launch ramp between them in one; same structure as k_step_sampled_oct).
+template <int SCORE, int VEC, int KIND>
+__global__ void __launch_bounds__(kThreads)
+k_step_fed_grouped(TableDev ent, TableDev rel,
+                   const int32_t* __restrict__ ph, const int32_t* __restrict__ pr, const int32_t* __restrict__ pt, int n_pos,
+                   const int32_t* __restrict__ nh, const int32_t* __restrict__ nr, const int32_t* __restrict__ nt, int k,
+                   oea_loss_cfg cfg, double* __restrict__ loss_out, OptTab A, OptTab B, float lr) {
+    __shared__ double s_loss[kWarpsPerBlock];
+    grouped_score_body<SCORE, VEC>(ent, rel, ph, pr, pt, n_pos, nh, nr, nt, k, cfg, loss_out, s_loss);
+    cooperative_groups::this_grid().sync();
+    oct_rowopt_body<KIND>(A, B, ent.pitch, lr, blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5), gridDim.x * kWarpsPerBlock);
+}
+
 }  // namespace oea
 
 using namespace oea;
@@ -182,18 +209,48 @@ extern "C" int oea_triple_score_fed_grouped(const oea_table* ent, const oea_tabl
     TableDev e = table_dev(ent), r = table_dev(rel);
     const bool l1 = loss->score_kind == OEA_SCORE_L1;
     const int grid = grid_for(n_pos);
-#ifdef OEA_HOST_EMU   // tests/emu: the same kernel on the CPU warp emulator
-#define OEA_RUN_GROUPED(S, V)                                                                                          \
-    do { auto kernel = k_score_fed_grouped<S, V>;                                                                      \
-         emu::launch(grid < 2 ? grid : 2, kThreads, [&] { kernel(e, r, pos_h, pos_r, pos_t, n_pos, neg_h, neg_r, neg_t, k, *loss, loss_out); }); } while (0)
-#else
-#define OEA_RUN_GROUPED(S, V)                                                                                          \
-    k_score_fed_grouped<S, V><<<grid, kThreads, 0, (cudaStream_t)stream>>>(e, r, pos_h, pos_r, pos_t, n_pos, neg_h, neg_r, neg_t, k, *loss, loss_out)
-#endif
+#define OEA_RUN_GROUPED(S, V) \
+    OEA_LAUNCH((k_score_fed_grouped<S, V>), grid, kThreads, 0, (cudaStream_t)stream, e, r, pos_h, pos_r, pos_t, n_pos, neg_h, neg_r, neg_t, k, *loss, loss_out)
 #define CALL(V) do { if (l1) OEA_RUN_GROUPED(OEA_SCORE_L1, V); else OEA_RUN_GROUPED(OEA_SCORE_L2SQ, V); } while (0)
     OEA_DISPATCH_VEC(ent->pitch, CALL);
 #undef CALL
 #undef OEA_RUN_GROUPED
     OEA_LAUNCH_CHECK();
+    return OEA_OK;
+}
+
+// One cooperative launch for the whole fed step (grouped scorer + row optimiser).  Same contract as
+// oea_triple_score_fed_grouped followed by oea_rowopt_apply_pair; squared-L2 score, pitch <= 256, Adagrad / SGD —
+// OEA_ERR_KIND otherwise (the caller then takes the two-launch path).
+extern "C" int oea_triple_step_fed_grouped(const oea_table* ent, const oea_table* rel,
+                                           const int32_t* pos_h, const int32_t* pos_r, const int32_t* pos_t, int32_t n_pos,
+                                           const int32_t* neg_h, const int32_t* neg_r, const int32_t* neg_t, int32_t n_neg,
+                                           const oea_loss_cfg* loss, const oea_opt_cfg* opt, double* loss_out, void* stream) {
+    int rc = check_table(ent, true); if (rc) return rc;
+    rc = check_table(rel, true); if (rc) return rc;
+    if (!loss || !loss_out || !opt) return OEA_ERR_NULL;
+    if (ent->pitch != rel->pitch || ent->dim != rel->dim) return OEA_ERR_DIM;
+    if (n_pos <= 0 || n_neg < 0 || n_neg % n_pos != 0) return OEA_ERR_SHAPE;
+    if (!pos_h || !pos_r || !pos_t || (n_neg > 0 && (!neg_h || !neg_r || !neg_t))) return OEA_ERR_NULL;
+    if (loss->loss_kind < OEA_LOSS_MARGIN || loss->loss_kind > OEA_LOSS_LOGSIGMOID) return OEA_ERR_KIND;
+    if (loss->score_kind != OEA_SCORE_L2SQ || ent->pitch > 256) return OEA_ERR_KIND;
+    if (opt->kind != OEA_OPT_ADAGRAD && opt->kind != OEA_OPT_SGD) return OEA_ERR_KIND;
+    if (opt->kind == OEA_OPT_ADAGRAD && (!ent->state1 || !rel->state1)) return OEA_ERR_NULL;
+    int k = n_neg / n_pos;
+    if (loss->loss_kind == OEA_LOSS_MARGIN && k != 1) return OEA_ERR_SHAPE;
+    if ((loss->loss_kind == OEA_LOSS_POSITIVE || loss->loss_kind == OEA_LOSS_LOGSIGMOID) && k != 0) return OEA_ERR_SHAPE;
+    cudaStream_t st = (cudaStream_t)stream;
+    TableDev e = table_dev(ent), r = table_dev(rel);
+    OptTab A{ent->weight, ent->grad, ent->state1, ent->touched, ent->rows}, B{rel->weight, rel->grad, rel->state1, rel->touched, rel->rows};
+    oea_loss_cfg cfg = *loss;
+    float lr = opt->lr;
+    int np = n_pos;
+#define OEA_RUN_STEP(V, KIND)                                                                                            \
+    do { const int grid = grid_one_wave(k_step_fed_grouped<OEA_SCORE_L2SQ, V, KIND>, n_pos);                             \
+         OEA_CUDA_TRY(OEA_LAUNCH_COOPERATIVE((k_step_fed_grouped<OEA_SCORE_L2SQ, V, KIND>), grid, kThreads, st, e, r, pos_h, pos_r, \
+                                             pos_t, np, neg_h, neg_r, neg_t, k, cfg, loss_out, A, B, lr)); } while (0)
+    if (ent->pitch <= 128) { if (opt->kind == OEA_OPT_ADAGRAD) OEA_RUN_STEP(1, OEA_OPT_ADAGRAD); else OEA_RUN_STEP(1, OEA_OPT_SGD); }
+    else { if (opt->kind == OEA_OPT_ADAGRAD) OEA_RUN_STEP(2, OEA_OPT_ADAGRAD); else OEA_RUN_STEP(2, OEA_OPT_SGD); }
+#undef OEA_RUN_STEP
     return OEA_OK;
 }

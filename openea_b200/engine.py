@@ -250,6 +250,19 @@ class TripleTrainer:
             np_(pos, 0), np_(pos, 1), np_(pos, 2), n_pos, np_(neg, 0), np_(neg, 1), np_(neg, 2), n_neg,
             C.byref(self.loss), _ptr(out), _stream_ptr()), "oea_triple_score_fed")
 
+    def step_fed_grouped(self, pos, neg=None, loss_out=None):
+        """score_fed(grouped=True) + apply() as one cooperative launch (oea_triple_step_fed_grouped); raises OeaError
+        where the one-launch kernel does not apply (L1 score, pitch > 256, Adam / Adadelta)."""
+        out = self.loss_dev if loss_out is None else loss_out
+        n_pos = pos.shape[1]
+        n_neg = 0 if neg is None else neg.shape[1]
+        np_ = lambda t, i: C.c_void_p(0 if t is None or t.shape[1] == 0 else t[i].data_ptr())
+        cfg = opt_cfg(self.ent, self.lr)
+        L.check(self.lib.oea_triple_step_fed_grouped(
+            C.byref(self.ent.c_struct()), C.byref(self.rel.c_struct()),
+            np_(pos, 0), np_(pos, 1), np_(pos, 2), n_pos, np_(neg, 0), np_(neg, 1), np_(neg, 2), n_neg,
+            C.byref(self.loss), C.byref(cfg), _ptr(out), _stream_ptr()), "oea_triple_step_fed_grouped")
+
     def score_margin_weighted(self, pos, neg, weights=None, reciprocal=False, scale=1.0, paths=False, loss_out=None):
         """scale · Σ wᵢ · relu(margin + s(posᵢ) − s(negᵢ)) forward + backward (oea_triple_score_margin_weighted;
         iptranse.py:170-180).  pos / neg: int32 device tensors [3, n]; weights: float32 device tensor [n] or None;

@@ -91,6 +91,8 @@ SIGNATURES = {
                                                    C.POINTER(LossCfg), _P, _P]),
     "oea_pair_distance_loss": (C.c_int, [_TP, _P, _P, _I, _P, C.c_float, _P, _P]),
     "oea_triple_score_fed_grouped": (C.c_int, [_TP, _TP, _P, _P, _P, _I, _P, _P, _P, _I, C.POINTER(LossCfg), _P, _P]),
+    "oea_triple_step_fed_grouped": (C.c_int, [_TP, _TP, _P, _P, _P, _I, _P, _P, _P, _I, C.POINTER(LossCfg),
+                                              C.POINTER(OptCfg), _P, _P]),
     "oea_rowopt_apply": (C.c_int, [_TP, C.POINTER(OptCfg), _P]),
     "oea_rowopt_apply_pair": (C.c_int, [_TP, _TP, C.POINTER(OptCfg), _P]),
     "oea_rowopt_adadelta": (C.c_int, [_TP, C.POINTER(OptCfg), _P]),

@@ -37,6 +37,24 @@ for shape, n_ent, n_rel, B, k in (("15K", 30000, 450, 5000, 10), ("100K", 200000
                     times.append(e0.elapsed_time(e1))
                 tr.apply()
             row["grouped_us" if grouped else "per_triple_us"] = 1e3 * float(np.median(times))
+        tr = eng.TripleTrainer(eng.EmbeddingTable(ent, True), eng.EmbeddingTable(rel, True), cfg, 0.01)
+        times = []
+        for it in range(13):                 # grouped scoring + row optimiser as one cooperative launch (whole step)
+            flush.fill_(it & 1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); tr.step_fed_grouped(dp, dn); e1.record(); torch.cuda.synchronize()
+            if it >= 3:
+                times.append(e0.elapsed_time(e1))
+        row["one_launch_step_us"] = 1e3 * float(np.median(times))
+        tr = eng.TripleTrainer(eng.EmbeddingTable(ent, True), eng.EmbeddingTable(rel, True), cfg, 0.01)
+        times = []
+        for it in range(13):                 # the same step as two launches (per-triple scorer, then k_rowopt_pair)
+            flush.fill_(it & 1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); tr.score_fed(dp, dn); tr.apply(); e1.record(); torch.cuda.synchronize()
+            if it >= 3:
+                times.append(e0.elapsed_time(e1))
+        row["two_launch_step_us"] = 1e3 * float(np.median(times))
         hp, hn = torch.from_numpy(pos).pin_memory(), torch.from_numpy(neg).pin_memory()
         for flag in ("0", "1"):
             os.environ["OEA_FED_GROUPED"] = flag
@@ -47,4 +65,14 @@ for shape, n_ent, n_rel, B, k in (("15K", 30000, 450, 5000, 10), ("100K", 200000
             for _ in range(20):
                 tr.step_fed_host(hp, hn)
             row["host_step_grouped_us" if flag == "1" else "host_step_us"] = 1e6 * (time.perf_counter() - t0) / 20
+        os.environ["OEA_FED_GROUPED"] = "0"
+        os.environ["OEA_FED_FUSED"] = "1"
+        tr = eng.TripleTrainer(eng.EmbeddingTable(ent, True), eng.EmbeddingTable(rel, True), cfg, 0.01)
+        for _ in range(3):
+            tr.step_fed_host(hp, hn)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        for _ in range(20):
+            tr.step_fed_host(hp, hn)
+        row["host_step_one_launch_us"] = 1e6 * (time.perf_counter() - t0) / 20
+        os.environ["OEA_FED_FUSED"] = "0"
         print(json.dumps(row), flush=True)

@@ -284,12 +284,13 @@ def test_emulated_one_launch_step_equals_score_then_optimiser(cpu_engine_oct, mo
     assert not torch.equal(fused.ent.raw(), make().ent.raw())           # the steps did move the tables
 
 
-@pytest.mark.parametrize("grouped", ["0", "1"])
+@pytest.mark.parametrize("grouped", ["0", "1", "fused"])
 def test_emulated_pipelined_host_step_equals_the_synchronous_one(cpu_engine, monkeypatch, grouped):
     """oea_triple_step_fed_host_submit / _collect (two slots with their own index buffers and loss scalars; the stream /
     event ordering is trivially satisfied on the emulator) against oea_triple_step_fed_host on the same batches: slot
     bookkeeping, buffer offsets, the per-step losses and the final tables — also with the grouped scorer selected."""
-    monkeypatch.setenv("OEA_FED_GROUPED", grouped)
+    monkeypatch.setenv("OEA_FED_GROUPED", "1" if grouped == "1" else "0")
+    monkeypatch.setenv("OEA_FED_FUSED", "1" if grouped == "fused" else "0")
     rng = np.random.default_rng(23)
     d, n_ent, n_rel = 20, 60, 7
     ent, rel = make_tables(rng, n_ent, n_rel, d)
@@ -329,3 +330,68 @@ def test_emulated_pipelined_host_step_equals_the_synchronous_one(cpu_engine, mon
     for x, y in ((a.ent, b.ent), (a.rel, b.rel)):
         np.testing.assert_allclose(y.raw().numpy(), x.raw().numpy(), rtol=1e-5, atol=1e-7)
         assert not y.grad.any() and not y.touched.any()
+
+
+@pytest.mark.parametrize("opt", ["Adagrad", "SGD"])
+@pytest.mark.parametrize("loss,k,d", [("limited", 3, 20), ("margin-based", 1, 75), ("logistic", 2, 200), ("positive", 0, 20)])
+def test_emulated_one_launch_fed_step_equals_dense_tf_steps(cpu_engine, opt, loss, k, d):
+    """oea_triple_step_fed_grouped (grouped scoring + grid barrier + octet row optimiser in one cooperative launch, run as
+    one block on the emulator) against the C oracle's dense TF steps, and against the two-launch path it replaces."""
+    rng = np.random.default_rng(7 * d + k)
+    n_ent, n_rel = 60, 7
+    ent, rel = make_tables(rng, n_ent, n_rel, d)
+    kw = dict(margin=1.1 if loss == "margin-based" else 0.3, neg_margin=2.2, balance=0.2)
+    cfg = cpu_engine.loss_cfg(loss, "L2", **kw)
+    st = orc.DenseState(ent, rel, opt)
+    make = lambda: cpu_engine.TripleTrainer(cpu_engine.EmbeddingTable(ent, True, opt, device="cpu"),
+                                            cpu_engine.EmbeddingTable(rel, True, opt, device="cpu"), cfg, 0.01)
+    fused, split = make(), make()
+    for _ in range(3):
+        pos, neg = make_batch(rng, n_ent, n_rel, 16, k)
+        want = orc.step(st, pos, neg, loss, "L2", True, True, 0.01, **kw)
+        fused.step_fed_grouped(_t(pos), None if neg is None else _t(neg))
+        split.score_fed(_t(pos), None if neg is None else _t(neg), grouped=True)
+        split.apply()
+        assert fused.read_loss() == pytest.approx(want, rel=1e-4)
+        assert split.read_loss() == pytest.approx(want, rel=1e-4)
+    for tab, ref, other in ((fused.ent, st.ent, split.ent), (fused.rel, st.rel, split.rel)):
+        np.testing.assert_allclose(tab.raw().numpy(), ref, rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(tab.raw().numpy(), other.raw().numpy(), rtol=1e-5, atol=1e-7)
+        assert not tab.grad.any() and not tab.touched.any()
+
+
+def test_one_launch_fed_step_refuses_what_it_does_not_cover(cpu_engine):
+    rng = np.random.default_rng(3)
+    ent, rel = make_tables(rng, 30, 3, 12)
+    pos, neg = make_batch(rng, 30, 3, 8, 2)
+    t = cpu_engine.TripleTrainer(cpu_engine.EmbeddingTable(ent, True, "Adam", device="cpu"),
+                                 cpu_engine.EmbeddingTable(rel, True, "Adam", device="cpu"),
+                                 cpu_engine.loss_cfg("limited", "L2", 0.1, 2.0, 0.2), 0.01)
+    with pytest.raises(L.OeaError):
+        t.step_fed_grouped(_t(pos), _t(neg))                       # Adam: dense update, not the flagged-row optimiser
+    t = cpu_engine.TripleTrainer(cpu_engine.EmbeddingTable(ent, True, device="cpu"), cpu_engine.EmbeddingTable(rel, True, device="cpu"),
+                                 cpu_engine.loss_cfg("limited", "L1", 0.1, 2.0, 0.2), 0.01)
+    with pytest.raises(L.OeaError):
+        t.step_fed_grouped(_t(pos), _t(neg))                       # L1 score
+    assert not t.ent.grad.any()                                    # nothing was launched
+
+
+def test_emulated_host_steps_with_the_one_launch_kernel(cpu_engine, monkeypatch):
+    """OEA_FED_FUSED=1 on the synchronous host-index step and on the pipelined one: same losses and tables as the default;
+    with Adam (not covered by the kernel) the flag falls back to the two-launch path."""
+    rng = np.random.default_rng(29)
+    d, n_ent, n_rel = 20, 60, 7
+    ent, rel = make_tables(rng, n_ent, n_rel, d)
+    cfg = cpu_engine.loss_cfg("limited", "L2", 0.01, 2.0, 0.2)
+    batches = [tuple(_t(x) for x in make_batch(rng, n_ent, n_rel, 16, 3)) for _ in range(4)]
+    for opt in ("Adagrad", "Adam"):
+        res = []
+        for flag in ("0", "1"):
+            monkeypatch.setenv("OEA_FED_FUSED", flag)
+            t = cpu_engine.TripleTrainer(cpu_engine.EmbeddingTable(ent, True, opt, device="cpu"),
+                                         cpu_engine.EmbeddingTable(rel, True, opt, device="cpu"), cfg, 0.01)
+            t._loss_pinned = torch.zeros(1, dtype=torch.float64)
+            res.append(([t.step_fed_host(p, n) for p, n in batches], t.ent.raw().numpy().copy(), t.rel.raw().numpy().copy()))
+        np.testing.assert_allclose(res[1][0], res[0][0], rtol=1e-5)
+        np.testing.assert_allclose(res[1][1], res[0][1], rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(res[1][2], res[0][2], rtol=1e-5, atol=1e-7)

@@ -484,3 +484,38 @@ def test_full_size_properties_of_the_fed_scorers(cuda_device, shape, n_ent, n_re
         return m.read_loss(), tabs[0].grad.clone(), tabs[1].grad.clone(), tabs[3].grad.clone()
     close(transh(((slice(0, half), slice(0, half * k)), (slice(half, B), slice(half * k, B * k)))),
           transh(((slice(None), slice(None)),)))
+
+
+@pytest.mark.first_hw_run
+@pytest.mark.parametrize("opt", ["Adagrad", "SGD"])
+@pytest.mark.parametrize("loss,k,d", [("limited", 10, 100), ("margin-based", 1, 75), ("logistic", 4, 200)])
+def test_one_launch_fed_step_equals_the_two_launch_path(cuda_device, monkeypatch, opt, loss, k, d):
+    """oea_triple_step_fed_grouped (grouped scoring + grid barrier + row optimiser, one cooperative launch) against
+    score_fed + apply from the same tables, three steps; then the host-index step with OEA_FED_FUSED=1 against the
+    default."""
+    eng = _engine()
+    from tests.helpers import make_tables
+    rng = np.random.default_rng(11 * d + k)
+    n_ent, n_rel, n_pos = 3000, 31, 700
+    ent, rel = make_tables(rng, n_ent, n_rel, d)
+    kw = dict(margin=1.1 if loss == "margin-based" else 0.3, neg_margin=2.2, balance=0.2)
+    cfg = eng.loss_cfg(loss, "L2", **kw)
+    make = lambda: eng.TripleTrainer(eng.EmbeddingTable(ent, True, opt), eng.EmbeddingTable(rel, True, opt), cfg, 0.01)
+    fused, split = make(), make()
+    batches = [make_batch(rng, n_ent, n_rel, n_pos, k) for _ in range(3)]
+    for pos, neg in batches:
+        fused.step_fed_grouped(_dev(pos), _dev(neg))
+        split.score_fed(_dev(pos), _dev(neg))
+        split.apply()
+        assert fused.read_loss() == pytest.approx(split.read_loss(), rel=1e-5)
+    torch.cuda.synchronize()
+    for x, y in ((fused.ent, split.ent), (fused.rel, split.rel)):
+        _assert_rows_close(x.raw().cpu().numpy(), y.raw().cpu().numpy(), "table after three one-launch steps")
+        assert not x.grad.any().item() and not x.touched.any().item()
+    res = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("OEA_FED_FUSED", flag)
+        t = make()
+        res.append(([t.step_fed_host(p, n) for p, n in batches], t.ent.raw().cpu().numpy()))
+    np.testing.assert_allclose(res[1][0], res[0][0], rtol=1e-4)
+    _assert_rows_close(res[1][1], res[0][1], "entity table after host-index steps with OEA_FED_FUSED")
