@@ -663,7 +663,8 @@ class Session:
         values = [None] * len(flat)
         for i, f in enumerate(flat):                     # forward values first: a fetched loss is the pre-update loss
             if not isinstance(f, _TrainOp):
-                values[i] = f._eval(env).detach().numpy().copy()
+                out = f._eval(env)
+                values[i] = out if isinstance(out, SparseValue) else out.detach().numpy().copy()
         for f in flat:
             if isinstance(f, _TrainOp):
                 f.optimizer.current = f
