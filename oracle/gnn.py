@@ -1,6 +1,8 @@
 """CPU ORACLE for path (ii) (GCN-Align aggregation + L1 alignment loss) — TEST INFRASTRUCTURE ONLY.
 
-PARITY UNPINNED for the TF part: the graph of approaches/gcn_align.py runs in TensorFlow 1.x (absent here).
+PARITY: the GCN-Align unit below reproduces the reference's own GCN_Align_Unit executed on oracle/tf1_shim.py
+(tests/test_reference_graph_goldens.py, 1e-9); the engine's AliNet model and RDGCN layer are held to such goldens
+directly.  TF's op / optimiser semantics (restated in that interpreter) stay unpinned: TensorFlow 1.x is absent here.
 This restates it with torch-CPU autograd at the reference's call sites:
   GraphConvolution._call  gcn_align.py:239-267   (featureless first layer, weight-less second layer)
   trunc_normal + l2_normalize(·, 1)  gcn_align.py:52-56
@@ -74,7 +76,7 @@ def unit_train_step(support, W0, features, ill, gamma, k, negs, lr, dtype=torch.
     return float(loss.detach()), W_new.numpy(), out.detach().numpy()
 
 
-# ---- AliNet (approaches/alinet.py) — torch-CPU restatement with dense-free sparse ops; PARITY UNPINNED vs TF ----
+# ---- AliNet (approaches/alinet.py) — torch-CPU restatement with dense-free sparse ops (TF semantics unpinned) ----
 ALINET_REF_FILE = "/root/reference/src/openea/approaches/alinet.py"
 
 
@@ -149,7 +151,7 @@ def alinet_loss(params, outs, pos, neg, neg_margin, balance, hs, ts, rel_win, re
     return total
 
 
-# ---- RDGCN (approaches/rdgcn.py) — torch-CPU restatement; PARITY UNPINNED vs TF -------------------------------
+# ---- RDGCN (approaches/rdgcn.py) — torch-CPU restatement (TF semantics unpinned) -------------------------------
 RDGCN_REF_FILE = "/root/reference/src/openea/approaches/rdgcn.py"
 
 

@@ -5,7 +5,10 @@
  * nju-websoft/OpenEA builds for negative-sampled triple scoring.  Only tests/, __graft_entry__.smoke()
  * and bench.py's cpu_baseline / --impl reference legs may load this.
  *
- * PARITY UNPINNED for path (i): the arithmetic lives in TensorFlow 1.x (tested 1.8/1.12 per the
+ * PARITY: pinned to the reference's own graph code — its _define_* methods and session.run executed on a TF-1 graph
+ * interpreter (oracle/tf1_shim.py) give tests/golden/path_i_reference_graphs.npz, which this oracle reproduces
+ * (tests/test_reference_graph_goldens.py::test_c_oracle_reproduces_the_reference_graph).  UNPINNED remains what that
+ * interpreter itself restates, TF's op and optimiser semantics: the arithmetic lives in TensorFlow 1.x (tested 1.8/1.12 per the
  * reference README.md:110; un-pinned in setup.py:13), which is absent from /root/reference and cannot be
  * installed here (no cp312 wheel, no network).  The reference ships no tests or golden vectors for this
  * path.  This file restates TF's documented semantics at the reference's own call sites:

@@ -11,8 +11,10 @@ and `init_embeddings(..., is_l2_norm)` returning the normalised variable (module
 so gradients flow through the normalisation into the raw variable.  The losses are those of
 modules/base/losses.py:15-73.
 
-PARITY UNPINNED: the arithmetic of these graphs lives in TensorFlow 1.x, which is not in /root/reference and
-cannot be installed here; the reference ships no golden vectors for them.  tests/test_oracle_triple_ext.py
+PARITY: pinned to the reference's own graph code executed on oracle/tf1_shim.py (tests/test_reference_graph_goldens.py::
+test_score_family_oracle_reproduces_the_reference_graph, 1e-9); TF's op / optimiser semantics, restated in that
+interpreter, stay unpinned — TensorFlow 1.x is not in /root/reference and cannot be installed here, and the reference
+ships no golden vectors for these graphs.  tests/test_oracle_triple_ext.py
 checks this restatement against hand-computed known answers and against an independent closed-form statement
 of the gradients (the formulas the CUDA kernels implement).
 """

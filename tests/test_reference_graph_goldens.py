@@ -408,3 +408,57 @@ def test_attre_on_the_emulator_reproduces_the_reference_graph(cpu_engine, monkey
 def test_attre_on_the_gpu_reproduces_the_reference_graph(cuda_device, monkeypatch):
     from openea_b200 import engine
     replay_attre(engine, "cuda", monkeypatch)
+
+
+# ---- the other oracles, held to the same goldens -------------------------------------------------------------------
+EXT_CASES = {   # case → (model of oracle.triple_ext, {oracle slot: reference variable}, loss, kwargs, mean loss?)
+    "transh": ("TransH", {"ent": "ent_embeds", "rel": "rel_embeds", "normal": "normal_vector"}, "margin-based", dict(margin=1.5), False),
+    "transd": ("TransD", {"ent": "ent_embeds", "rel": "rel_embeds", "ent_transfer": "ent_transfer", "rel_transfer": "rel_transfer"},
+               "margin-based", dict(margin=1.5), False),
+    "simple": ("SimplE", {"head_ent": "head_ent_embeds", "rel1": "rel_embeds1", "tail_ent": "tail_ent_embeds", "rel2": "rel_embeds2"},
+               "logistic", {}, False),
+    "distmult": ("DistMult", {"ent": "ent_embeds", "rel": "rel_embeds"}, "logistic", {}, True),
+}
+
+
+@pytest.mark.parametrize("case", sorted(EXT_CASES))
+def test_score_family_oracle_reproduces_the_reference_graph(case):
+    """oracle/triple_ext.py (the float64 restatement the score-family kernels are tested against on the GPU)."""
+    from oracle import triple_ext as ox
+    model, slots, loss, kw, mean = EXT_CASES[case]
+    meta = META[case]
+    st = ox.DenseState({slot: G["%s/var0/%s" % (case, name)] for slot, name in slots.items()}, "Adagrad")
+    norms = {slot: True for slot in slots}
+    for i, run in enumerate(meta["runs"]):
+        f = _feed(case, i)
+        if run["kind"] == "label":
+            n_pos = int((f["label"] > 0).sum())
+            both = np.stack([f["hs"], f["rs"], f["ts"]]).astype(np.int32)
+            pos, neg = both[:, :n_pos], both[:, n_pos:]
+        else:
+            pos = np.stack([f["pos_hs"], f["pos_rs"], f["pos_ts"]]).astype(np.int32)
+            neg = np.stack([f["neg_hs"], f["neg_rs"], f["neg_ts"]]).astype(np.int32)
+        scale = 1.0 / (pos.shape[1] + neg.shape[1]) if mean else 1.0
+        got = ox.step(st, model, norms, pos, neg, loss, meta["args"]["learning_rate"], scale=scale, **kw)
+        assert got == pytest.approx(float(G["%s/run%d/loss" % (case, i)]), rel=1e-9), (case, i)
+    for slot, name in slots.items():
+        np.testing.assert_allclose(st.w[slot], G["%s/var_final/%s" % (case, name)], rtol=1e-9, atol=1e-12, err_msg=name)
+
+
+@pytest.mark.parametrize("branch", ["se", "ae"])
+def test_gcn_align_oracle_reproduces_the_reference_unit(branch):
+    """oracle/gnn.py's GCN-Align unit (what tests/test_gnn_gpu.py checks the kernels against)."""
+    import scipy.sparse as sp
+    from oracle import gnn as og
+    n, n_feat, dim, t, k = (int(x) for x in GCN["dims"])
+    coo = lambda name, shape: sp.coo_matrix((GCN[name + "/values"], (GCN[name + "/coords"][:, 0], GCN[name + "/coords"][:, 1])),
+                                            shape=shape).tocsr()
+    support = coo("support", (n, n))
+    features = None if branch == "se" else coo("features", (n, n_feat))
+    W = GCN[branch + "/var0"]
+    for step in range(3):
+        negs = [GCN["%s/run%d/%s" % (branch, step, key)] for key in ("neg_left", "neg_right", "neg2_left", "neg2_right")]
+        loss, W, out = og.unit_train_step(support, W, features, GCN["ill"], float(GCN["gamma"]), k, negs, float(GCN["lr"]),
+                                          dtype=torch.float64)
+        assert loss == pytest.approx(float(GCN["%s/run%d/loss" % (branch, step)]), rel=1e-9)
+    np.testing.assert_allclose(W, GCN[branch + "/var_final"], rtol=1e-9, atol=1e-12)
