@@ -8,19 +8,9 @@ from openea_b200.approaches.jape import JAPE
 from openea_b200.approaches.mtranse import MTransE
 from openea_b200.approaches.sea import SEA
 from openea_b200.models._stubs import out_of_scope
-
-try:
-    from openea_b200.approaches.gcn_align import GCN_Align
-except ImportError:  # pragma: no cover - file lands later in the build plan
-    GCN_Align = out_of_scope("GCN_Align", "not built yet")
-try:
-    from openea_b200.approaches.alinet import AliNet
-except ImportError:  # pragma: no cover
-    AliNet = out_of_scope("AliNet", "not built yet")
-try:
-    from openea_b200.approaches.rdgcn import RDGCN
-except ImportError:  # pragma: no cover
-    RDGCN = out_of_scope("RDGCN", "not built yet")
+from openea_b200.approaches.alinet import AliNet
+from openea_b200.approaches.gcn_align import GCN_Align
+from openea_b200.approaches.rdgcn import RDGCN
 
 Attr2Vec = out_of_scope("Attr2Vec", "stand-alone attribute skip-gram model (JAPE carries its own auxiliary, approaches/jape.py)")
 RSN4EA = out_of_scope("RSN4EA", "recurrent skipping network over paths")
