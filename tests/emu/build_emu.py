@@ -18,6 +18,9 @@ def cuda_include():
 
 
 def build(force=False):
+    prebuilt = os.environ.get("OEA_EMU_LIB")          # e.g. a build with -fsanitize=address,undefined
+    if prebuilt:
+        return prebuilt
     inc = cuda_include()
     if inc is None:
         return None

@@ -52,6 +52,42 @@ void kernel_checks(int* block_sums) {
         for (int w = 0; w < (int)(blockDim.x / 32); ++w) t += partial[w];
         block_sums[blockIdx.x] = t;
     }
+    // 8. shift shuffles: lanes without a source keep their own value
+    const int up = __shfl_up_sync(0xffffffffu, lane, 3), down = __shfl_down_sync(0xffffffffu, lane, 5);
+    expect(up == (lane >= 3 ? lane - 3 : lane), 10);
+    expect(down == (lane + 5 < 32 ? lane + 5 : lane), 11);
+    // 9. all warps of the block are concurrent and __syncthreads() is a real barrier: a two-phase exchange through
+    //    shared memory between DIFFERENT warps, several rounds, plus shared and global atomics from every thread
+    __shared__ int ring[256];
+    __shared__ unsigned hits;
+    __shared__ float fsum;
+    if (threadIdx.x == 0) { hits = 0u; fsum = 0.f; }
+    __syncthreads();
+    int token = (int)threadIdx.x;
+    for (int round = 0; round < 4; ++round) {
+        ring[threadIdx.x] = token;
+        __syncthreads();
+        token = ring[(threadIdx.x + 37) % blockDim.x] + 1;            // a thread of another warp wrote this slot
+        __syncthreads();
+    }
+    expect(token == (int)((threadIdx.x + 4 * 37) % blockDim.x) + 4, 12);
+    atomicAdd(&hits, 1u);
+    atomicAdd(&fsum, 0.5f);
+    atomicMax(reinterpret_cast<unsigned*>(&ring[0]), threadIdx.x);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        expect(hits == blockDim.x, 13);
+        expect(fsum == 0.5f * blockDim.x, 14);
+        expect((unsigned)ring[0] >= blockDim.x - 1, 15);
+    }
+    // 10. __syncwarp orders a lane-0 write after every lane's read of the same word (the row optimisers' flag)
+    __shared__ int flag[8];
+    if (lane == 0) flag[warp] = 1;
+    __syncwarp();
+    const int seen = flag[warp];
+    __syncwarp();
+    if (lane == 0) flag[warp] = 0;
+    expect(seen == 1, 16);
 }
 
 }  // namespace
@@ -59,8 +95,12 @@ void kernel_checks(int* block_sums) {
 extern "C" int emu_selftest() {
     g_fail = 0;
     int sums[3] = {0, 0, 0};
-    emu::launch(3, 256, [&] { kernel_checks(sums); });
+    emu::launch(dim3(3), dim3(256), [&] { kernel_checks(sums); });
     for (int b = 0; b < 3; ++b) expect(sums[b] == 36, 8);
     expect(gridDim.x == 3 && blockDim.x == 256, 9);
+    // 2-dimensional grids: blockIdx.y / gridDim.y
+    std::atomic<int> cells{0};
+    emu::launch(dim3(2, 3), dim3(32), [&] { if (threadIdx.x == 0) cells.fetch_add(1 + 10 * (int)blockIdx.y + 100 * (int)(gridDim.y == 3)); });
+    expect(cells.load() == 6 + 2 * 10 * (0 + 1 + 2) + 600, 17);
     return g_fail.load();
 }

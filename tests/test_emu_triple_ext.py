@@ -149,7 +149,8 @@ def test_emulated_adadelta_update_matches_tf_rule(emu):
 
 def test_emulator_collectives_behave_like_cuda():
     """cuda_host_emu.h itself: butterfly reductions, broadcasts, ballots, match_any, collectives on lane SUBSETS while
-    the other lanes run ahead, 64-bit payloads, and the publish / barrier / consume pattern of LossAcc::flush."""
+    the other lanes run ahead, 64-bit payloads, shift shuffles, cross-warp exchanges between real barriers, shared and
+    global atomics, __syncwarp ordering, 2-D grids."""
     so = build_emu.build_selftest()
     if so is None:
         pytest.skip("no CUDA headers for the emulator build")
