@@ -267,8 +267,9 @@ def replay_rdgcn(device):
         move = np.abs(want - start).max()
         if move == 0.0:
             # a bias added to every logit of a softmax row has a mathematically zero gradient (sp1.b / sp2.b): float64
-            # keeps it at exactly 0, in fp32 Adam turns the rounding noise of that gradient into a tiny drift
-            assert np.abs(got - start).max() < 1e-4, name
+            # keeps it at exactly 0, in fp32 Adam normalises the rounding noise of that gradient (whose size depends on
+            # the order of the atomic adds) into a drift of at most its step bound, lr per step
+            assert np.abs(got - start).max() <= 3 * args.learning_rate * 1.01, name
             continue
         np.testing.assert_allclose((got - start)[:, col], (want - start)[:, col], rtol=2e-2, atol=3e-2 * move + 1e-7, err_msg=name)
     with torch.no_grad():
