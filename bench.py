@@ -247,7 +247,19 @@ def bench_csls(shape, device, reps=3):
                "api": "finding.greedy_alignment(embeds1, embeds2, top_k, threads, 'inner', False, csls_k=10, accurate=True)"}
     except Exception as exc:       # informational: never lose the bench line over it
         e2e = {"value": None, "note": "failed: %r" % (exc,)}
+    # the reference's CPU path for the same evaluation (NumPy port of similarity.py / alignment.py, one thread) on a
+    # bounded 4000 x 4000 sub-problem (~1.5 s); pairs/s is size-normalised
+    try:
+        from oracle import finding as orf
+        m = min(n, 4000)
+        t0 = time.perf_counter()
+        orf.greedy_alignment(e1[:m].numpy(), e2[:m].numpy(), [1, 5, 10, 50], "inner", False, 10)
+        cpu = {"value": float(m) * m / (time.perf_counter() - t0), "unit": "pairs/s", "cores": 1, "kind": "port",
+               "sample": "%d x %d sub-problem, inner + CSLS(k=10), accurate ranks" % (m, m)}
+    except Exception as exc:
+        cpu = {"value": None, "note": "failed: %r" % (exc,)}
     return {"metric": "CSLS pairs/sec", "value": pairs / (ms * 1e-3), "unit": "pairs/s", "n1": n, "n2": n, "dim": d, "e2e": e2e,
+            "cpu_baseline": cpu,
             "ms": ms, "contraction_passes": 1, "streaming_passes": 3, "matrix_bytes": 4.0 * pairs,
             "fp32_tflops_whole_eval": flops / (ms * 1e-3) / 1e12, "hits1": hits[0],
             "note": "inner + CSLS(k=10), exact ranks (greedy_alignment accurate=True equivalent); includes the host-side "
