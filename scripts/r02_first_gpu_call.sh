@@ -21,6 +21,7 @@ python scripts/bench_fed_grouped.py > gpurun_out/r02a/fed_grouped.jsonl 2>> gpur
 python scripts/bench_weighted.py > gpurun_out/r02a/weighted.jsonl 2>> gpurun_out/r02a/bench.err
 # 4. ncu of the score family's scorer (TransD limited loss is the heaviest instantiation)
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_model_fed -s 20 -c 1 -o gpurun_out/r02a/model_fed python scripts/bench_ext.py > gpurun_out/r02a/ncu.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_step_fed_grouped -s 4 -c 1 -o gpurun_out/r02a/step_fed_grouped python scripts/bench_fed_grouped.py > gpurun_out/r02a/ncu_fed.log 2>&1
 # 5. what bounds K1: gather throughput vs rows in flight, dependent-chain latency, red.v4 throughput, grid-barrier cost
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o scripts/ubench_gather.bin scripts/ubench_gather.cu && timeout 180 scripts/ubench_gather.bin > gpurun_out/r02a/ubench_gather.txt 2>&1
 ls -la gpurun_out/r02a
