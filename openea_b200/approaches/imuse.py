@@ -12,6 +12,8 @@ attributes.  It is restated here on plain dicts with two differences that do not
     with Hyyrö's bit-parallel LCS on Python integers;
   * an entity pair can only score above the (positive) threshold if the two entities share at least one paired
     attribute, so only those pairs are scored instead of all |E₁|·|E₂|.
+The cost stays what the reference's is — every entity with a paired attribute against every such entity of the other
+KG, one string comparison each — so, like there, the matcher is only practical on small KGs or selective attributes.
 Where the reference's result depends on the iteration order of a Python set of tuples holding strings (which changes
 from process to process), ids are visited in ascending order here; and its 8 worker processes each keep their own
 "already taken" set (imuse.py:83-92), so a right-hand entity can be handed out once per worker — here once overall.
