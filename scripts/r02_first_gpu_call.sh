@@ -14,6 +14,8 @@ tail -60 gpurun_out/r02a/tests.txt
 # 2. the bench lines, 15K and 100K
 python bench.py > gpurun_out/r02a/bench_15k.json 2> gpurun_out/r02a/bench.err
 python bench.py --workload bootea_100k --steps 40 --warmup 8 > gpurun_out/r02a/bench_100k.json 2>> gpurun_out/r02a/bench.err
+#    + the launch list of the same command (kernel share of the step; the one-launch step has no list from round 1)
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02a/launches_bootea15k.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/r02a/bench_under_ncu.log 2>&1
 # 3. the approaches through the lifecycle (AliNet's epoch was 92 ms with host-side sampling; BootEA's iteration with host bootstrapping)
 python scripts/bench_approaches.py > gpurun_out/r02a/approaches.json 2>> gpurun_out/r02a/bench.err
 python scripts/bench_ext.py > gpurun_out/r02a/score_family.jsonl 2>> gpurun_out/r02a/bench.err
