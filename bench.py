@@ -620,7 +620,10 @@ def main():
             try:
                 res = subprocess.run([sys.executable, os.path.abspath(__file__), "--probe-pipelined-e2e", "--workload",
                                       args.workload, "--steps", str(max(K, 40))], capture_output=True, text=True, timeout=120)
-                e2e["pipelined"] = json.loads(res.stdout.strip().splitlines()[-1])
+                lines = res.stdout.strip().splitlines()
+                if not lines:
+                    raise RuntimeError("no output, exit %d: %s" % (res.returncode, res.stderr.strip()[-300:]))
+                e2e["pipelined"] = json.loads(lines[-1])
             except Exception as exc:
                 e2e["pipelined"] = {"value": None, "note": "probe failed or timed out: %r" % (exc,)}
             _phase("pipelined e2e probe done")
