@@ -1,0 +1,106 @@
+"""TEST INFRASTRUCTURE: runs GPU-only Python entry points of this repository (bench.py, __graft_entry__.smoke) in a
+process where torch's CUDA surface is faked and liboea's entry points are served by the CPU warp emulator, so that their
+Python logic — argument plumbing, JSON contract, probe choreography — is exercised where no GPU exists.  Numbers printed
+this way are meaningless as measurements.  Only tests/test_bench_on_emulator.py starts this, in a subprocess.
+
+    python tests/emu/fake_cuda.py bench [bench.py arguments…]      (a `micro` workload is registered)
+    python tests/emu/fake_cuda.py probe
+    python tests/emu/fake_cuda.py smoke
+"""
+import ctypes as C
+import os
+import sys
+import time
+import types
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+from openea_b200 import engine as eng  # noqa: E402
+from openea_b200 import finding  # noqa: E402
+from openea_b200 import lib as L  # noqa: E402
+from tests.emu import build_emu  # noqa: E402
+
+
+def install():
+    lib = C.CDLL(build_emu.build())
+    for name, (res, args) in L.SIGNATURES.items():
+        if hasattr(lib, name):
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+    L.load = lambda: lib
+    null = lambda: C.c_void_p(0)
+    eng._stream_ptr = finding._stream_ptr = null
+    cpu = torch.device("cpu")
+
+    class Stream:
+        def __init__(self, *a, **k):
+            self.cuda_stream = 0x10
+
+        def synchronize(self):
+            pass
+
+    class Event:
+        count = 0
+
+        def __init__(self, *a, **k):
+            Event.count += 1
+            self.cuda_event, self.t = 0x100 + Event.count, None
+
+        def record(self, *a, **k):
+            self.t = time.perf_counter()
+
+        def elapsed_time(self, other):
+            return 1e3 * (other.t - self.t)
+
+        def synchronize(self):
+            pass
+    torch.cuda.Stream, torch.cuda.Event = Stream, Event
+    torch.cuda.synchronize = torch.cuda.set_device = lambda *a, **k: None
+    torch.cuda.is_available = lambda: True
+    torch.cuda.current_device = lambda: 0
+    torch.Tensor.cuda = torch.Tensor.pin_memory = lambda self, *a, **k: self
+    torch.Tensor.is_pinned = lambda self, *a, **k: True
+    real_device = torch.device
+    torch.device = lambda *a, **k: real_device("cpu")
+    finding._device = lambda: cpu
+    table_init = eng.EmbeddingTable.__init__
+    eng.EmbeddingTable.__init__ = lambda self, init, l2_norm, optimizer="Adagrad", device="cpu": table_init(
+        self, init, l2_norm, optimizer, "cpu")
+    trainer_init = eng.TripleTrainer.__init__
+
+    def trainer(self, *a, **k):
+        trainer_init(self, *a, **k)
+        self._loss_pinned = torch.zeros(1, dtype=torch.float64)
+    eng.TripleTrainer.__init__ = trainer
+
+    class EagerEpoch:                      # CUDA graphs need a device: replay = the same steps, eagerly
+        def __init__(self, tr, kg1, kg2, tset, batch, k, steps, max_try=10):
+            self.args = (tr, kg1, kg2, tset, batch, k, steps)
+
+        def replay(self, seed):
+            tr, kg1, kg2, tset, batch, k, steps = self.args
+            for step in range(steps):
+                tr.step_sampled(kg1, kg2, tset, batch, k, step, seed)
+    eng.EpochGraph = EagerEpoch
+
+
+def main():
+    install()
+    what, rest = sys.argv[1], sys.argv[2:]
+    if what == "smoke":
+        import __graft_entry__
+        return __graft_entry__.smoke()
+    import bench
+    bench.WORKLOADS["micro"] = dict(shape="micro", dim=16, batch=48, k=3, eps=0.5, lr=0.01, margin=0.01, neg_margin=2.0,
+                                    balance=0.2, name="micro (emulator)")
+    bench.L2_FLUSH_BYTES = 1 << 20
+    if what == "probe":
+        return bench.probe_pipelined_e2e(types.SimpleNamespace(workload="micro", steps=8))
+    sys.argv = ["bench.py"] + rest
+    return bench.main()
+
+
+if __name__ == "__main__":
+    sys.exit(main() or 0)

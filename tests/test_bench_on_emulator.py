@@ -1,0 +1,47 @@
+"""CPU: bench.py's and smoke()'s Python logic (argument plumbing, the JSON contract of the bench line, the pipelined
+probe's choreography and its three variants) executed in a subprocess whose CUDA surface is faked and whose liboea entry
+points are the kernels' sources on the warp emulator (tests/emu/fake_cuda.py).  The numbers are not measurements."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from tests.emu import build_emu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+RUNNER = os.path.join(ROOT, "tests", "emu", "fake_cuda.py")
+
+
+def run(*args, timeout=600):
+    if build_emu.build() is None:
+        pytest.skip("no CUDA headers for the emulator build")
+    res = subprocess.run([sys.executable, RUNNER] + list(args), capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+    assert res.returncode == 0, res.stderr[-2000:]
+    return res.stdout.strip().splitlines()
+
+
+def test_bench_line_contract_on_the_emulator():
+    line = json.loads(run("bench", "--workload", "micro", "--steps", "3", "--warmup", "3", "--no-cpu-baseline")[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "roofline", "e2e", "cpu_baseline", "clocks", "gpu_launches"):
+        assert key in line, key
+    assert line["n_gpus"] == 1 and line["steps"] == 3 and line["higher_is_better"] is True and line["dtype"] == "f32"
+    assert line["value"] > 0 and line["gpu_launches"] == 3 and "workload" in line["config"]
+    roof = line["roofline"]
+    assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(roof) and roof["bound"] == "hbm"
+    e2e = line["e2e"]
+    assert e2e["value"] > 0 and e2e["h2d_bytes_per_step"] == 12 * 48 * 4 and e2e["d2h_bytes_per_step"] == 8
+    csls = line["csls"]
+    assert csls["value"] > 0 and csls["e2e"]["value"] > 0 and csls["cpu_baseline"]["value"] > 0 and csls["hits1"] > 0
+
+
+def test_pipelined_probe_variants_agree_with_the_synchronous_step():
+    out = json.loads(run("probe")[-1])
+    assert out["losses_agree"] and out["value"] > 0
+    assert out["grouped_scorer"]["losses_agree"] and out["one_launch_step"]["losses_agree"]
+
+
+def test_smoke_passes_on_the_emulator():
+    assert any(line.startswith("smoke ok") for line in run("smoke", timeout=900))
