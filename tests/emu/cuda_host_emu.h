@@ -2,7 +2,7 @@
 // sources (openea_b200/csrc/*.cu, compiled unchanged with -DOEA_HOST_EMU by g++) can be checked against the oracle
 // where no GPU exists.  Not a fallback: nothing under openea_b200/ ever loads a library built with it.
 //
-// Model: one OS thread per CUDA thread.  All warps of a block run concurrently; the 32 lanes of a warp meet at every
+// Model: one OS thread per CUDA thread (a worker pool reused from block to block).  All warps of a block run concurrently; the 32 lanes of a warp meet at every
 // warp collective (__shfl*_sync, __ballot_sync, __match_any_sync, __syncwarp) on a per-mask rendezvous of their warp —
 // exactly where real lanes exchange registers — and nowhere else (lanes are free-running, so code that silently relies
 // on a converged warp staying in step is caught); __syncthreads() is a real barrier; the blocks of a grid run one after
@@ -16,6 +16,8 @@
 #include <string.h>
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <thread>
@@ -121,28 +123,76 @@ inline void launch(dim3 grid, dim3 block, Body body) {
     }
 }
 
+// The CUDA threads of a block run on a pool of worker threads that lives for the process: one block at a time, all of its
+// threads concurrently (they meet at barriers), workers reused by the next block and the next launch.
+class BlockPool {
+public:
+    template <typename Job>
+    void run(int n, Job&& job) {
+        std::lock_guard<std::mutex> serial(run_mutex_);
+        {
+            std::unique_lock<std::mutex> lk(m_);
+            while ((int)workers_ < n) {
+                const int id = workers_++;
+                std::thread([this, id] { work(id); }).detach();
+            }
+            job_ = job;
+            active_ = n;
+            done_ = 0;
+            ++generation_;
+        }
+        start_.notify_all();
+        std::unique_lock<std::mutex> lk(m_);
+        finished_.wait(lk, [&] { return done_ == active_; });
+    }
+
+private:
+    void work(int id) {
+        uint64_t seen = 0;
+        for (;;) {
+            std::function<void(int)> job;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                start_.wait(lk, [&] { return generation_ != seen; });
+                seen = generation_;
+                if (id >= active_) continue;
+                job = job_;
+            }
+            job(id);
+            std::lock_guard<std::mutex> lk(m_);
+            if (++done_ == active_) finished_.notify_all();
+        }
+    }
+    std::mutex m_, run_mutex_;
+    std::condition_variable start_, finished_;
+    std::function<void(int)> job_;
+    uint64_t generation_ = 0;
+    int workers_ = 0, active_ = 0, done_ = 0;
+};
+inline BlockPool& block_pool() {
+    static BlockPool* pool = new BlockPool();       // never destroyed: its detached workers outlive static destruction
+    return *pool;
+}
+
 template <typename Body>
 inline void launch_row(int grid, int threads, Body body) {
     gridDim.x = (unsigned)grid;
     blockDim.x = (unsigned)threads;
     const int warps = threads / 32;
+    const unsigned by = blockIdx.y;                        // the launching thread's value: workers have their own copy
     for (int b = 0; b < grid; ++b) {
         std::vector<WarpState> ws(warps);
         BlockBarrier bar;
         bar.expected = threads;
-        std::vector<std::thread> pool;
-        pool.reserve(threads);
-        for (int t = 0; t < threads; ++t) {
-            pool.emplace_back([&, t] {
-                t_lane = t & 31;
-                t_warp = &ws[t >> 5];
-                t_block = &bar;
-                threadIdx.x = (unsigned)t;
-                blockIdx.x = (unsigned)b;
-                body();
-            });
-        }
-        for (auto& th : pool) th.join();
+        block_pool().run(threads, [&](int t) {
+            t_lane = t & 31;
+            t_warp = &ws[t >> 5];
+            t_block = &bar;
+            threadIdx.x = (unsigned)t;
+            blockIdx.x = (unsigned)b;
+            blockIdx.y = by;
+            body();
+        });
     }
 }
 

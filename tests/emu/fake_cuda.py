@@ -6,6 +6,7 @@ this way are meaningless as measurements.  Only tests/test_bench_on_emulator.py 
     python tests/emu/fake_cuda.py bench [bench.py arguments…]      (a `micro` workload is registered)
     python tests/emu/fake_cuda.py probe
     python tests/emu/fake_cuda.py smoke
+    python tests/emu/fake_cuda.py lifecycle <Approach> <tmp folder>
 """
 import ctypes as C
 import os
@@ -63,7 +64,23 @@ def install():
     torch.Tensor.cuda = torch.Tensor.pin_memory = lambda self, *a, **k: self
     torch.Tensor.is_pinned = lambda self, *a, **k: True
     real_device = torch.device
-    torch.device = lambda *a, **k: real_device("cpu")
+
+    class _DeviceMeta(type):                # torch.device stays usable as a type (isinstance, `torch.device | None`)
+        def __call__(cls, *a, **k):
+            return real_device("cpu")
+
+        def __instancecheck__(cls, obj):
+            return isinstance(obj, real_device)
+
+        def __or__(cls, other):
+            return real_device | other
+
+        def __ror__(cls, other):
+            return other | real_device
+
+    class CpuDevice(metaclass=_DeviceMeta):
+        pass
+    torch.device = CpuDevice
     finding._device = lambda: cpu
     table_init = eng.EmbeddingTable.__init__
     eng.EmbeddingTable.__init__ = lambda self, init, l2_norm, optimizer="Adagrad", device="cpu": table_init(
@@ -86,9 +103,41 @@ def install():
     eng.EpochGraph = EagerEpoch
 
 
+def lifecycle(name, folder):
+    """set_args / set_kgs / init / run / test / save of one approach on the micro synthetic dataset, two epochs."""
+    from openea_b200 import approaches, presets
+    presets.gcn_align, presets.bootea_transh = presets.gcn_align, presets.bootea_transh      # preset names are lower-cased class names
+    from openea_b200.modules.load.kgs import read_kgs_from_folder
+    from openea_b200.synth import write_dataset
+    data = write_dataset(os.path.join(folder, "micro") + "/", "micro")
+    args = getattr(presets, name.lower())("15K")
+    args.training_data, args.output = data, os.path.join(folder, "out") + "/"
+    args.batch_size, args.max_epoch, args.start_valid, args.eval_freq, args.dim, args.cuda_graph = 64, 2, 1, 1, 16, False
+    # sizes that only make sense on real datasets (125 hard negatives, a 2 % candidate list) scaled to 40 entities
+    for key, val in dict(bp_freq=1, sim_th=0.05, attr_max_epoch=2, sub_mat_size=4, attr_sim_mat_threshold=0.5,
+                         truncated_epsilon=0.5).items():
+        if hasattr(args, key):
+            setattr(args, key, val)
+    if hasattr(args, "neg_triple_num"):
+        args.neg_triple_num = min(args.neg_triple_num, 3)
+    from openea_b200.models import semantic, trans
+    cls = next(getattr(m, name) for m in (approaches, trans, semantic) if hasattr(m, name))
+    model = cls()
+    model.set_args(args)
+    model.set_kgs(read_kgs_from_folder(data, args.dataset_division, args.alignment_module, args.ordered))
+    model.init()
+    model.run()
+    model.test()
+    model.save()
+    assert os.path.exists(model.out_folder + "ent_embeds.npy")
+    print("lifecycle ok:", name)
+
+
 def main():
     install()
     what, rest = sys.argv[1], sys.argv[2:]
+    if what == "lifecycle":
+        return lifecycle(rest[0], rest[1])
     if what == "smoke":
         import __graft_entry__
         return __graft_entry__.smoke()

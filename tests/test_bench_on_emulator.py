@@ -45,3 +45,27 @@ def test_pipelined_probe_variants_agree_with_the_synchronous_step():
 
 def test_smoke_passes_on_the_emulator():
     assert any(line.startswith("smoke ok") for line in run("smoke", timeout=900))
+
+
+LIFECYCLES = ["TransE", "TransH", "TransD", "DistMult", "SimplE", "MTransE", "AlignE", "BootEA", "BootEA_TransH", "GCN_Align",
+              "AliNet", "RDGCN", "IPTransE", "SEA", "IMUSE", "AttrE", "JAPE"]
+
+
+def test_every_model_class_runs_its_lifecycle_on_the_emulator(tmp_path):
+    """set_args / set_kgs / init / run (two epochs, one validation) / test / save of all 17 model classes on the micro
+    synthetic dataset, kernels on the emulator: every Python line of the lifecycles — evaluation, result lines, files on
+    disk, bootstrapping, graph builders — executes without a GPU (several processes side by side)."""
+    import concurrent.futures
+    if build_emu.build() is None:
+        pytest.skip("no CUDA headers for the emulator build")
+
+    def one(name):
+        folder = str(tmp_path / name)
+        os.makedirs(folder)
+        res = subprocess.run([sys.executable, RUNNER, "lifecycle", name, folder], capture_output=True, text=True, timeout=900,
+                             cwd=ROOT)
+        return name, res.returncode, res.stdout[-300:] + res.stderr[-1500:]
+    with concurrent.futures.ThreadPoolExecutor(max_workers=min(17, max(2, (os.cpu_count() or 4) // 4))) as pool:
+        results = list(pool.map(one, LIFECYCLES))
+    failed = [(name, tail) for name, rc, tail in results if rc != 0 or "lifecycle ok: " + name not in tail]
+    assert not failed, failed
