@@ -7,6 +7,7 @@ this way are meaningless as measurements.  Only tests/test_bench_on_emulator.py 
     python tests/emu/fake_cuda.py probe
     python tests/emu/fake_cuda.py smoke
     python tests/emu/fake_cuda.py lifecycle <Approach> <tmp folder>
+    python tests/emu/fake_cuda.py pytest <pytest arguments…>      (ad-hoc: GPU-marked tests against the emulator)
 """
 import ctypes as C
 import os
@@ -63,6 +64,7 @@ def install():
     torch.cuda.current_device = lambda: 0
     torch.Tensor.cuda = torch.Tensor.pin_memory = lambda self, *a, **k: self
     torch.Tensor.is_pinned = lambda self, *a, **k: True
+    torch.Tensor.cpu = lambda self, *a, **k: self.clone()      # a device → host read is a copy, never an alias
     real_device = torch.device
 
     class _DeviceMeta(type):                # torch.device stays usable as a type (isinstance, `torch.device | None`)
@@ -91,6 +93,18 @@ def install():
         trainer_init(self, *a, **k)
         self._loss_pinned = torch.zeros(1, dtype=torch.float64)
     eng.TripleTrainer.__init__ = trainer
+
+    def is_cuda_name(x):
+        return (isinstance(x, str) and x.startswith("cuda")) or (isinstance(x, real_device) and x.type == "cuda")
+
+    class CudaToCpu(torch.overrides.TorchFunctionMode):     # device="cuda" / .to("cuda") anywhere in torch's API → CPU
+        def __torch_function__(self, func, types, args=(), kwargs=None):
+            kwargs = dict(kwargs or {})
+            if is_cuda_name(kwargs.get("device")):
+                kwargs["device"] = "cpu"
+            args = tuple("cpu" if is_cuda_name(a) else a for a in args)
+            return func(*args, **kwargs)
+    CudaToCpu().__enter__()
 
     class EagerEpoch:                      # CUDA graphs need a device: replay = the same steps, eagerly
         def __init__(self, tr, kg1, kg2, tset, batch, k, steps, max_try=10):
@@ -138,6 +152,9 @@ def main():
     what, rest = sys.argv[1], sys.argv[2:]
     if what == "lifecycle":
         return lifecycle(rest[0], rest[1])
+    if what == "pytest":                     # ad-hoc audits: GPU-marked tests executed against the emulator
+        import pytest
+        return pytest.main(rest)
     if what == "smoke":
         import __graft_entry__
         return __graft_entry__.smoke()
