@@ -3,10 +3,12 @@
 
 A "step" is one pass of hot path (i) over one batch: the fused on-device negative sampler + triple scoring
 forward/backward kernel + the row optimiser on both tables (what one session.run([loss, optimizer]) of
-models/basic_model.py:224-230 does in the reference).  Default workload = BASELINE.json configs[1]
-(BootEA on the D_W_15K_V1 shape, dim 100, batch 5000, 10 ε-truncated negatives), synthetic KG of that shape.
+models/basic_model.py:224-230 does in the reference).  Default workload = the shape BASELINE.json's north-star target
+is quoted on (BootEA, D_W_100K_V1 shape, dim 100, batch 20000, 10 ε-truncated negatives; it fits one GPU); the
+BASELINE.json configs[1] shape (D_W_15K_V1, batch 5000) is measured in the same run and reported as the
+`bootea_15k` block of the same JSON line (N = 1 only).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload bootea_15k|bootea_100k]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload bootea_100k|bootea_15k]
 
 Prints ONE JSON line on rank 0.
 """
@@ -32,6 +34,7 @@ WORKLOADS = {
                         balance=0.2, name="BootEA D_W_100K_V1 shape (synthetic), dim=100, batch=20000, 10 eps-truncated negatives"),
 }
 L2_FLUSH_BYTES = 512 << 20
+SHAPE_ENTITIES = {"15K": 15000, "100K": 100000}      # entities per KG (openea_b200/synth.py SHAPES)
 
 
 def peaks():
@@ -101,6 +104,7 @@ def build_workload(wl, rank, device, world=1):
     from openea_b200.synth import synth_id_arrays
     cfg = WORKLOADS[wl]
     arr = synth_id_arrays(cfg["shape"], seed=20200901)
+    n_triples_global = len(arr["triples1"]) + len(arr["triples2"])
     if world > 1:   # every rank trains on the triples whose head row it owns (openea_b200/parallel.py)
         from openea_b200 import parallel as par
         arr = dict(arr)
@@ -129,7 +133,7 @@ def build_workload(wl, rank, device, world=1):
     T = kg1.triples.shape[0] + kg2.triples.shape[0]
     steps_per_epoch = int(np.ceil(T / cfg["batch"]))
     return dict(cfg=cfg, arr=arr, ent=ent, rel=rel, kg1=kg1, kg2=kg2, tset=tset, trainer=trainer,
-                steps_per_epoch=steps_per_epoch, n_triples=T)
+                steps_per_epoch=steps_per_epoch, n_triples=T, n_triples_global=n_triples_global)
 
 
 def decode_dbg(dbg, n, t1, t2, k):
@@ -175,17 +179,21 @@ def cpu_reference_run(wl, steps, warmup, batches=None, budget_s=25.0):
             neg[0, side] = repl[side]; neg[2, ~side] = repl[~side]
             batches.append((pos, np.ascontiguousarray(neg)))
     kw = dict(margin=cfg["margin"], neg_margin=cfg["neg_margin"], balance=cfg["balance"])
-    # give the CPU arm its best thread count (OpenMP over all cores is not always the fastest on many-core hosts)
-    best_t, best_dt = None, None
+    # give the CPU arm its best thread count (OpenMP over all cores is not always the fastest on many-core hosts):
+    # per candidate 2 untimed + 5 timed steps, MEDIAN; the whole sweep is reported.  One noisy sample used to pick a
+    # slow setting and swing the baseline several-fold between boxes.
     ncpu = os.cpu_count() or 1
+    sweep = {}
     for nt in sorted({ncpu, max(1, ncpu // 2), max(1, ncpu // 4), min(ncpu, 16), min(ncpu, 8)}):
         orc.set_num_threads(nt)
-        orc.step(st, *batches[0], "limited", "L2", True, True, cfg["lr"], **kw)
-        t0 = time.perf_counter()
-        orc.step(st, *batches[0], "limited", "L2", True, True, cfg["lr"], **kw)
-        dt = time.perf_counter() - t0
-        if best_dt is None or dt < best_dt:
-            best_t, best_dt = nt, dt
+        ts = []
+        for rep in range(7):
+            t0 = time.perf_counter()
+            orc.step(st, *batches[rep % len(batches)], "limited", "L2", True, True, cfg["lr"], **kw)
+            if rep >= 2:
+                ts.append(time.perf_counter() - t0)
+        sweep[nt] = float(np.median(ts))
+    best_t = min(sweep, key=sweep.get)
     orc.set_num_threads(best_t)
     for i in range(max(1, warmup)):
         orc.step(st, *batches[i % len(batches)], "limited", "L2", True, True, cfg["lr"], **kw)
@@ -199,7 +207,8 @@ def cpu_reference_run(wl, steps, warmup, batches=None, budget_s=25.0):
         if time.perf_counter() - t0 > budget_s:
             break
     dt = time.perf_counter() - t0
-    info = dict(cores=best_t, steps=done, seconds=dt,
+    info = dict(cores=best_t, steps=done, seconds=dt, thread_sweep_ms={str(k): 1e3 * v for k, v in sorted(sweep.items())},
+                omp_env={k: os.environ.get(k) for k in ("OMP_PROC_BIND", "OMP_PLACES")},
                 sample="%d steps of %d positives + %d negatives (dense TF-style step, C/OpenMP port)" % (done, batches[0][0].shape[1], batches[0][1].shape[1]))
     return n_pos / dt, info
 
@@ -413,82 +422,52 @@ def probe_pipelined_e2e(args):
     return 0
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="bootea_15k", choices=sorted(WORKLOADS))
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-flush", action="store_true", help="diagnostic only: keep L2 warm between timed steps (the number is NOT a valid bench value)")
-    ap.add_argument("--probe-pipelined-e2e", action="store_true",
-                    help="internal: measure the depth-2 pipelined host-index step in this process and print its JSON")
-    args = ap.parse_args()
-    if args.probe_pipelined_e2e:
-        return probe_pipelined_e2e(args)
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    cfg = WORKLOADS[args.workload]
-    unit = "positive triples/s"
-    config = {"workload": cfg["name"], "batch_size": cfg["batch"], "neg_per_pos": cfg["k"], "dim": cfg["dim"],
-              "sharding": ("triples sharded by head-row owner (id mod G), replicated tables, per-epoch NCCL all-gather of "
-                           "seed-pair rows") if world > 1 else "single", "l2": "flushed between timed steps (512 MiB write)"}
-
-    if args.no_flush:
-        config["l2"] = "NOT flushed (diagnostic run, invalid as a bench value)"
-    if args.impl == "reference":
-        if rank != 0:
-            return 0
-        val, info = cpu_reference_run(args.workload, args.steps, args.warmup)
-        line = {"impl": "reference", "metric": "training triples/sec", "value": val, "unit": unit, "n_gpus": args.gpus,
-                "steps": info["steps"], "warmup": args.warmup, "ms_per_step": 1e3 * info["seconds"] / max(1, info["steps"]),
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": config,
-                "cpu_baseline": {"value": val, "unit": unit, "cores": info["cores"], "kind": "port", "sample": info["sample"]},
-                "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
-        return 0
-
-    os.environ.setdefault("NCCL_DEBUG", "WARN")     # no version banner on stdout: the JSON line must stand alone
+def bench_triples(args, wl, rank, local_rank, world, device, full):
+    """Device-timed K steps of workload `wl` (+ roofline); with `full` also the e2e leg, the epoch graph and the clocks.
+    Returns the fields of the JSON line that describe this workload."""
     import torch
     import torch.distributed as dist
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    device = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=device)
-    _phase("cuda ready; building workload")
-    W = build_workload(args.workload, rank, device, world)
-    _phase("workload resident")
+    cfg = WORKLOADS[wl]
+    unit = "positive triples/s"
+    W = build_workload(wl, rank, device, world)
+    _phase("%s: workload resident" % wl)
     tr, kg1, kg2, tset = W["trainer"], W["kg1"], W["kg2"], W["tset"]
     B, k, d = cfg["batch"], cfg["k"], cfg["dim"]
     spe = W["steps_per_epoch"]
     flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device=device)
     npos_dev = torch.zeros(1, dtype=torch.int32, device=device)
+    full_steps = max(1, spe - 1) if spe > 1 else 1   # full batches per pass over the local shard (the ragged last step is skipped)
 
-    sync = None
+    # ---- multi-GPU: seed-row exchange on a GLOBAL cadence (identical on every rank by construction) -------------------
+    xchg = None
+    epoch_steps = None
     if world > 1:
         from openea_b200 import parallel as par
         seeds = np.concatenate([W["arr"]["train_links"][:, 0], W["arr"]["train_links"][:, 1]])
-        sync = par.SeedRowSync(W["ent"].weight, seeds, rank, world)
-    full_steps = max(1, spe - 1) if spe > 1 else 1   # full batches per local epoch (the ragged last step is skipped)
-    n_syncs = [0]
+        xchg = par.SeedRowSync(W["ent"].weight, seeds, rank, world, mode=os.environ.get("OEA_XCHG_MODE", "auto"))
+        # one global epoch = every triple of the UNSHARDED lists once = ceil(T / (G·B)) steps on every rank
+        epoch_steps = max(1, int(np.ceil(W["n_triples_global"] / float(world * B))))
+    gstep = [0]          # steps issued with the exchange enabled: drives the cadence, the same sequence on every rank
+    pulled = [0]
 
-    def one_step(i, ev=None, split=False):
-        # weak scaling: every rank steps through ITS shard with the full per-GPU batch; at each local epoch
-        # boundary the owners' seed-pair rows are all-gathered into every replica (the only collective)
+    def one_step(i, ev=None, split=False, exchange=True):
+        # weak scaling: every rank steps through ITS shard with the full per-GPU batch.  After the last step of a global
+        # epoch the owners publish their seed-pair rows (push); one step later every replica applies them (pull), so the
+        # NVLink transfer overlaps a training step.
         step = i % full_steps
         seed = 0xB007EA + 1000003 * (i // full_steps) + rank
         if ev:
             ev[0].record()
-        if sync is not None and step == 0 and i > 0:
-            sync.sync()
-            n_syncs[0] += 1
+        if xchg is not None and exchange:
+            g = gstep[0]
+            gstep[0] += 1
+            if g > 0 and g % epoch_steps == 1 % epoch_steps and xchg.epoch > pulled[0]:
+                xchg.pull()
+                pulled[0] = xchg.epoch
+            if g > 0 and g % epoch_steps == 0:
+                xchg.push()
         if ev and split:
-            ev[3].record()          # kernel-only interval starts after the (rare) collective
+            ev[3].record()          # kernel-only interval starts after the (rare) exchange
             tr.score_sampled(kg1, kg2, tset, B, k, step, seed)
             ev[1].record()
             tr.apply()
@@ -501,11 +480,13 @@ def main():
             # n_pos_out costs a small H2D copy in front of the kernel: asked for once, outside the timed region
             tr.step_sampled(kg1, kg2, tset, B, k, step, seed, n_pos_out=npos_dev if i == 0 else None)
 
-    for i in range(max(3, args.warmup)):
+    n_warm = max(3, args.warmup)
+    for i in range(n_warm):
         one_step(i)
-    if sync is not None:      # the first collective of a shape pays NCCL's lazy channel set-up: keep that out of the timing
-        for _ in range(3):
-            sync.sync()
+    if xchg is not None:      # first use of a transport pays lazy set-up (NCCL channels / first peer mapping touch): untimed
+        for _ in range(2):
+            xchg.sync()
+        pulled[0] = xchg.epoch
     torch.cuda.synchronize()
     n_pos_step = int(npos_dev.item())
     tr.read_loss()
@@ -516,14 +497,16 @@ def main():
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    n_push0 = 0 if xchg is None else xchg.epoch
     with ClockSampler(local_rank) as clocks:
         t_wall0 = time.perf_counter()
         for i in range(K):
             if not args.no_flush:
                 flush.fill_(float(i))   # L2 flush (not timed: outside the event pairs)
-            one_step(args.warmup + i, evs[i])
+            one_step(n_warm + i, evs[i])
         torch.cuda.synchronize()
         t_wall = time.perf_counter() - t_wall0
+    n_push = 0 if xchg is None else xchg.epoch - n_push0
     if world > 1:
         dist.barrier()
     kern_ms = np.array([e[3].elapsed_time(e[2]) for e in evs])
@@ -537,108 +520,127 @@ def main():
     value = world * n_pos_step * K / (total_ms * 1e-3)
 
     # ---- roofline of the dominant kernel: k_step_sampled_oct = the whole step in one launch --------------------
-    # algorithmic bytes: scoring 24·d per scored triple + row optimiser 24·d per
-    # touched row (read g, x, acc; write x, acc, g := 0).  Touched rows are counted on the device, outside the timing.
+    # 24·d bytes per scored triple (3 row reads + 3 row-gradient writes); frac is computed on THOSE bytes.
+    # The row optimiser the same launch runs moves another 24·d per touched row (read g, x, acc; write x, acc, g := 0):
+    # reported separately (`optimiser_bytes`), not part of `achieved`.
     pk, pk_kind = peaks()
     touched = []
     for i in range(4):
-        tr.score_sampled(kg1, kg2, tset, B, k, (args.warmup + i) % full_steps, 0xB007EA + rank)
+        tr.score_sampled(kg1, kg2, tset, B, k, (n_warm + i) % full_steps, 0xB007EA + rank)
         touched.append(int((tr.ent.touched != 0).sum().item()) + int((tr.rel.touched != 0).sum().item()))
         tr.apply()
     n_touched = float(np.mean(touched))
     score_bytes = 24.0 * d * (1 + k) * n_pos_step
-    alg_bytes = score_bytes + 24.0 * d * n_touched
+    opt_bytes = 24.0 * d * n_touched
     kern_med_ms = float(np.median(kern_ms))
-    achieved = alg_bytes / (kern_med_ms * 1e-3) / 1e9
-    # DRAM bytes per launch from committed `ncu --set full` captures (profiles/traffic_<workload>.json): the one-launch
-    # step kernel has no capture yet (null); the scorer it contains has one and is reported with its own roofline below
+    achieved = score_bytes / (kern_med_ms * 1e-3) / 1e9
     traffic = score_traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic_%s.json" % args.workload)
+    tp = os.path.join(ROOT, "profiles", "traffic_%s.json" % wl)
     if os.path.exists(tp):
         with open(tp) as f:
             tj = json.load(f)
         traffic = tj.get("k_step_sampled_oct_dram_bytes_per_launch")
         score_traffic = tj.get("k_score_sampled_dram_bytes_per_launch")
     # the same steps as two launches (score kernel, optimiser kernel) with an event between them: what the score
-    # kernel alone achieves against SURVEY §8d's scoring bytes (continuity with the r01 two-launch numbers)
+    # kernel alone achieves against the same bytes
     evs2 = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
     for i in range(K):
         if not args.no_flush:
             flush.fill_(float(i))
-        one_step(args.warmup + K + i, evs2[i], split=True)
+        one_step(n_warm + K + i, evs2[i], split=True)
+    if xchg is not None and xchg.epoch > pulled[0]:      # the last publication is applied on every rank (matched)
+        xchg.pull()
+        pulled[0] = xchg.epoch
     torch.cuda.synchronize()
     score_med_ms = float(np.median([e[3].elapsed_time(e[1]) for e in evs2]))
     split_step_ms = float(np.mean([e[0].elapsed_time(e[2]) for e in evs2]))
     roofline = {"bound": "hbm", "kernel": "k_step_sampled_oct", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "peak_kind": pk_kind + " (burst copy)",
-                "algorithmic_bytes_per_launch": alg_bytes, "scoring_bytes": score_bytes, "touched_rows_per_step": n_touched,
+                "algorithmic_bytes_per_launch": score_bytes, "bytes_model": "SURVEY 8(d): 24*d per scored triple",
+                "optimiser_bytes": opt_bytes, "achieved_incl_optimiser": (score_bytes + opt_bytes) / (kern_med_ms * 1e-3) / 1e9,
+                "touched_rows_per_step": n_touched,
                 "kernel_ms_median": kern_med_ms, "kernel_share_of_step": float(kern_ms.sum() / step_ms.sum()),
                 "score_kernel_alone": {"kernel": "k_score_sampled_oct", "ms_median": score_med_ms,
                                        "achieved": score_bytes / (score_med_ms * 1e-3) / 1e9,
                                        "frac": score_bytes / (score_med_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
                                        "two_launch_ms_per_step": split_step_ms, "traffic": score_traffic}}
+    _phase("%s: device-timed region done" % wl)
+    out = {"value": value, "unit": unit, "ms_per_step": total_ms / K, "positives_per_step": n_pos_step,
+           "scored_triples_per_s": value * (1 + k), "roofline": roofline, "wall_s_timed_region": t_wall, "last_loss_sum": loss_val,
+           "workload": cfg["name"]}
+    if xchg is not None:
+        out["collective"] = {"kind": {"p2p": "own kernels: peer-memory stores over NVLink + release/acquire flags (oea_seed_push / oea_seed_pull)",
+                                      "nccl": "oea_seed_pack + ncclAllGather (async) + oea_seed_unpack",
+                                      "torch": "torch ops + all_gather"}[xchg.mode],
+                             "mode": xchg.mode, "bytes_per_exchange": xchg.bytes_per_sync, "exchanges_in_timed_region": n_push,
+                             "epoch_steps": epoch_steps, "time_to_global_epoch_ms": epoch_steps * total_ms / K,
+                             "status": xchg.status()}
+    if not full:
+        if xchg is not None:
+            xchg.close()
+        return out, None
 
-    _phase("device-timed region done")
     # ---- e2e: the session.run(feed_dict) boundary with HOST index buffers -------------------------------------
-    e2e = None
-    cpu_base = None
-    if True:
-        n_b = min(K, 8)
-        t1, t2 = W["arr"]["triples1"], W["arr"]["triples2"]
-        host_batches = []
-        dbg = torch.empty(B, 2 + k, dtype=torch.int32, device=device)
-        for i in range(n_b):
-            tr.score_sampled(kg1, kg2, tset, B, k, i % full_steps, 0xE2E + i + rank, dbg=dbg, n_pos_out=npos_dev)
-            torch.cuda.synchronize()
-            pos, neg = decode_dbg(dbg.cpu().numpy(), int(npos_dev.item()), t1, t2, k)
-            host_batches.append((torch.from_numpy(pos).pin_memory(), torch.from_numpy(neg).pin_memory()))
-            tr.ent.grad.zero_(); tr.rel.grad.zero_(); tr.ent.touched.zero_(); tr.rel.touched.zero_()
-        tr.read_loss()
-        for i in range(3):
-            tr.step_fed_host(*host_batches[i % n_b])
+    n_b = min(K, 8)
+    t1, t2 = W["arr"]["triples1"], W["arr"]["triples2"]
+    host_batches = []
+    dbg = torch.empty(B, 2 + k, dtype=torch.int32, device=device)
+    for i in range(n_b):
+        tr.score_sampled(kg1, kg2, tset, B, k, i % full_steps, 0xE2E + i + rank, dbg=dbg, n_pos_out=npos_dev)
+        torch.cuda.synchronize()
+        pos, neg = decode_dbg(dbg.cpu().numpy(), int(npos_dev.item()), t1, t2, k)
+        host_batches.append((torch.from_numpy(pos).pin_memory(), torch.from_numpy(neg).pin_memory()))
+        tr.ent.grad.zero_(); tr.rel.grad.zero_(); tr.ent.touched.zero_(); tr.rel.touched.zero_()
+    tr.read_loss()
+    n_pos_h, n_neg_h = host_batches[0][0].shape[1], host_batches[0][1].shape[1]
+    # (a) synchronous call, L2 flushed between steps: one session.run at a time
+    for i in range(3):
+        tr.step_fed_host(*host_batches[i % n_b])
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e2e_s = 0.0
+    for i in range(K):
+        flush.fill_(float(i)); torch.cuda.synchronize()
+        pos, neg = host_batches[i % n_b]
+        t0 = time.perf_counter()
+        tr.step_fed_host(pos, neg)          # H2D of 6 index vectors, score, optimiser, D2H loss, sync
+        e2e_s += time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    sync_e2e = {"value": world * n_pos_h * K / e2e_s, "ms_per_step": 1e3 * e2e_s / K,
+                "api": "oea_triple_step_fed_host (host index buffers, tables resident, synchronous, L2 flushed between steps)"}
+    # (b) the same steps through the depth-2 pipelined entry points (the copy of step i+1 overlaps the kernels of step i,
+    # every step's indices still cross PCIe and every step's loss still comes back inside the timed region).  Steps run
+    # back to back, so L2 cannot be flushed between them: see config["l2_e2e"].
+    from openea_b200 import engine as eng
+    os.environ["OEA_FED_FUSED"] = "1"       # grouped scorer + row optimiser as one cooperative launch per step
+    pipe = eng.FedHostPipeline(tr, 3 * (n_pos_h + n_neg_h) + 64)
+    Kp = max(K, 40)
+    for rep in range(2):                    # rep 0 = warm-up
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        e2e_s = 0.0
-        for i in range(K):
-            flush.fill_(float(i)); torch.cuda.synchronize()
-            pos, neg = host_batches[i % n_b]
-            t0 = time.perf_counter()
-            tr.step_fed_host(pos, neg)          # H2D of 6 index vectors, score, optimiser, D2H loss, sync
-            e2e_s += time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([e2e_s], dtype=torch.float64, device=device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_s = float(t.item())
-        n_pos_h, n_neg_h = host_batches[0][0].shape[1], host_batches[0][1].shape[1]
-        e2e = {"value": world * n_pos_h * K / e2e_s, "unit": unit, "h2d_bytes_per_step": 12 * (n_pos_h + n_neg_h),
-               "d2h_bytes_per_step": 8, "ms_per_step": 1e3 * e2e_s / K,
-               "api": "oea_triple_step_fed_host (host index buffers, tables resident, synchronous)"}
-        _phase("e2e done")
-        if rank == 0 and world == 1:
-            # informational: the same steps through the depth-2 pipelined API, in a process of its own with a time limit
-            try:
-                res = subprocess.run([sys.executable, os.path.abspath(__file__), "--probe-pipelined-e2e", "--workload",
-                                      args.workload, "--steps", str(max(K, 40))], capture_output=True, text=True, timeout=120)
-                lines = res.stdout.strip().splitlines()
-                if not lines:
-                    raise RuntimeError("no output, exit %d: %s" % (res.returncode, res.stderr.strip()[-300:]))
-                e2e["pipelined"] = json.loads(lines[-1])
-            except Exception as exc:
-                e2e["pipelined"] = {"value": None, "note": "probe failed or timed out: %r" % (exc,)}
-            _phase("pipelined e2e probe done")
-        if rank == 0 and world == 1 and not args.no_cpu_baseline:
-            # the CPU port is timed in a fresh process (the same command as `--impl reference`): inside this process
-            # the OpenMP runtime shares cores with torch's thread pools and runs up to 2× slower
-            try:
-                res = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload",
-                                      args.workload, "--steps", "60", "--warmup", "2"], capture_output=True, text=True,
-                                     timeout=300)
-                cpu_base = json.loads(res.stdout.strip().splitlines()[-1])["cpu_baseline"]
-            except Exception as exc:   # never lose the GPU line because the CPU leg failed
-                cpu_base = {"value": None, "unit": unit, "cores": None, "kind": "port", "sample": "failed: %r" % (exc,)}
+        t0 = time.perf_counter()
+        for i in range(Kp):
+            pipe.submit(i % 2, *host_batches[i % n_b])
+            if i >= 1:
+                pipe.collect((i - 1) % 2)
+        pipe.collect((Kp - 1) % 2)
+        pipe_s = time.perf_counter() - t0
+    os.environ.pop("OEA_FED_FUSED", None)
+    if world > 1:
+        t = torch.tensor([pipe_s], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        pipe_s = float(t.item())
+    e2e = {"value": world * n_pos_h * Kp / pipe_s, "unit": unit, "h2d_bytes_per_step": 12 * (n_pos_h + n_neg_h),
+           "d2h_bytes_per_step": 8, "ms_per_step": 1e3 * pipe_s / Kp, "steps": Kp,
+           "api": "oea_triple_step_fed_host_submit / _collect (pinned host index buffers, depth-2 pipeline, one cooperative launch per step)",
+           "synchronous": sync_e2e}
+    _phase("%s: e2e done" % wl)
 
-    _phase("cpu baseline done")
     # ---- informational: the same steps as ONE CUDA graph per epoch, L2 warm (how the training loop really runs) ----
     graph_info = None
     if world == 1:
@@ -657,42 +659,143 @@ def main():
         graph_info = {"ms_per_step": g_ms, "positives_per_s": n_pos_step / (g_ms * 1e-3), "steps_per_graph": full_steps,
                       "note": "one CUDA graph per epoch, L2 NOT flushed between steps: informational, not the bench value"}
         tr.read_loss()
-    csls = None
-    if world == 1:
-        csls = bench_csls(cfg["shape"], device)
-    else:
-        csls = bench_csls_sharded(cfg["shape"], device)
-    _phase("csls done")
-    # clocks: the timed region is a few ms, shorter than nvidia-smi's sampling period; continue the SAME loop
-    # untimed under the sampler until it has >= 5 samples so the clocks line reflects this load
+    # clocks: the timed region is a few ms, shorter than nvidia-smi's sampling period; continue the SAME step loop
+    # untimed under the sampler until it has >= 5 samples so the clocks line reflects this load.  The continuation runs a
+    # wall-clock-bounded, rank-dependent number of steps, so it issues NO exchange and no collective (exchange=False).
     clk = clocks.summary()
     if clk["samples"] < 5:
         with ClockSampler(local_rank) as clocks2:
             t_end = time.perf_counter() + 1.0
             i = 0
             while time.perf_counter() < t_end:
-                flush.fill_(0.0); one_step(i); i += 1
+                flush.fill_(0.0); one_step(i, exchange=False); i += 1
                 if i % 64 == 0:
                     torch.cuda.synchronize()
             torch.cuda.synchronize()
         clk = clocks2.summary()
-        clk["note"] = "timed region shorter than the sampling period: sampled over an untimed 1 s continuation of the same step loop"
+        clk["note"] = "timed region shorter than the sampling period: sampled over an untimed 1 s continuation of the same step loop (no exchange inside)"
         tr.read_loss()
+    out.update({"e2e": e2e, "clocks": clk, "epoch_graph": graph_info})
+    if xchg is not None:
+        out["collective"]["status"] = xchg.status()
+        xchg.close()
+    return out, W
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="bootea_100k", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the bootea_15k block and the CSLS block (profiling runs)")
+    ap.add_argument("--no-flush", action="store_true", help="diagnostic only: keep L2 warm between timed steps (the number is NOT a valid bench value)")
+    ap.add_argument("--probe-pipelined-e2e", action="store_true",
+                    help="internal: measure the depth-2 pipelined host-index step in this process and print its JSON")
+    args = ap.parse_args()
+    if args.probe_pipelined_e2e:
+        return probe_pipelined_e2e(args)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cfg = WORKLOADS[args.workload]
+    unit = "positive triples/s"
+    config = {"workload": cfg["name"], "batch_size": cfg["batch"], "neg_per_pos": cfg["k"], "dim": cfg["dim"],
+              "sharding": ("triples sharded by head-row owner (id mod G), replicated tables, seed-pair rows exchanged once per "
+                           "global epoch over NVLink peer memory") if world > 1 else "single",
+              "l2": "flushed between timed steps (512 MiB write)",
+              "l2_e2e": "pipelined e2e steps run back to back (no flush possible); per-step working set = tables + gradients + "
+                        "Adagrad slots (%d MB) + candidate lists, vs 126 MB of L2" % (3 * 4 * cfg["dim"] * 2 * SHAPE_ENTITIES.get(cfg["shape"], 0) // 1000000)}
+
+    if args.no_flush:
+        config["l2"] = "NOT flushed (diagnostic run, invalid as a bench value)"
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        val, info = cpu_reference_run(args.workload, args.steps, args.warmup)
+        line = {"impl": "reference", "metric": "training triples/sec", "value": val, "unit": unit, "n_gpus": args.gpus,
+                "steps": info["steps"], "warmup": args.warmup, "ms_per_step": 1e3 * info["seconds"] / max(1, info["steps"]),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config,
+                "cpu_baseline": {"value": val, "unit": unit, "cores": info["cores"], "kind": "port", "sample": info["sample"],
+                                 "thread_sweep_ms_per_step": info["thread_sweep_ms"], "omp_env": info["omp_env"]},
+                "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    os.environ.setdefault("NCCL_DEBUG", "WARN")     # no version banner on stdout: the JSON line must stand alone
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    _phase("cuda ready; building workload")
+    main_blk, W = bench_triples(args, args.workload, rank, local_rank, world, device, full=True)
+    K = args.steps
+    k = cfg["k"]
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        # the CPU port is timed in a fresh process (the same command as `--impl reference`): inside this process
+        # the OpenMP runtime shares cores with torch's thread pools and runs up to 2× slower
+        try:
+            res = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload",
+                                  args.workload, "--steps", "40", "--warmup", "2"], capture_output=True, text=True,
+                                 timeout=300, env=reference_env())
+            cpu_base = json.loads(res.stdout.strip().splitlines()[-1])["cpu_baseline"]
+        except Exception as exc:   # never lose the GPU line because the CPU leg failed
+            cpu_base = {"value": None, "unit": unit, "cores": None, "kind": "port", "sample": "failed: %r" % (exc,)}
+    _phase("cpu baseline done")
+    del W
+    torch.cuda.empty_cache()
+    secondary = None
+    if world == 1 and not args.no_secondary and args.workload == "bootea_100k":
+        try:
+            secondary, _ = bench_triples(args, "bootea_15k", rank, local_rank, world, device, full=False)
+            secondary["note"] = "BASELINE.json configs[1] shape, same run, device-timed (same rules: L2 flushed, CUDA events)"
+        except Exception as exc:
+            secondary = {"value": None, "note": "failed: %r" % (exc,)}
+        torch.cuda.empty_cache()
+    csls = None
+    if not args.no_secondary:
+        if world == 1:
+            csls = bench_csls(cfg["shape"], device)
+        else:
+            csls = bench_csls_sharded(cfg["shape"], device)
+    _phase("csls done")
     if rank == 0:
-        line = {"metric": "training triples/sec", "value": value, "unit": unit, "n_gpus": world, "steps": K,
-                "warmup": max(3, args.warmup), "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
+        line = {"metric": "training triples/sec", "value": main_blk["value"], "unit": unit, "n_gpus": world, "steps": K,
+                "warmup": max(3, args.warmup), "ms_per_step": main_blk["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-                "scored_triples_per_s": value * (1 + k), "positives_per_step": n_pos_step,
+                "scored_triples_per_s": main_blk["scored_triples_per_s"], "positives_per_step": main_blk["positives_per_step"],
                 "gpu_launches": K, "kernels": ["k_step_sampled_oct (score + grid barrier + row optimiser, one cooperative launch)"],
-                "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_base, "clocks": clk, "csls": csls, "epoch_graph": graph_info,
-                "wall_s_timed_region": t_wall, "last_loss_sum": loss_val,
-                "collective": None if sync is None else {"kind": "ncclAllGather of seed-pair rows per local epoch",
-                                                         "bytes_per_sync": sync.bytes_per_sync, "syncs_in_run": n_syncs[0]}}
+                "roofline": main_blk["roofline"], "e2e": main_blk["e2e"], "cpu_baseline": cpu_base, "clocks": main_blk["clocks"],
+                "bootea_15k": secondary, "csls": csls, "epoch_graph": main_blk["epoch_graph"],
+                "wall_s_timed_region": main_blk["wall_s_timed_region"], "last_loss_sum": main_blk["last_loss_sum"],
+                "collective": main_blk.get("collective")}
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 
 
+def reference_env():
+    """Environment of the CPU reference arm: threads pinned to cores in order (a migrating OpenMP team was one source
+    of the 5.6x box-to-box swing of the r01 baseline)."""
+    env = dict(os.environ)
+    env.setdefault("OMP_PROC_BIND", "close")
+    env.setdefault("OMP_PLACES", "cores")
+    return env
+
+
 if __name__ == "__main__":
+    if "--impl" in sys.argv and "reference" in sys.argv and "OMP_PROC_BIND" not in os.environ:
+        # libgomp reads its binding policy at load time: re-exec once with the pinned environment
+        os.execve(sys.executable, [sys.executable] + sys.argv, reference_env())
     sys.exit(main())

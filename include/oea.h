@@ -112,6 +112,21 @@ typedef struct oea_sample_cfg {
                                * whole epoch (one node pair per step) be replayed with a new seed every epoch */
 } oea_sample_cfg;
 
+/* ---- path (i) across GPUs: peer-memory exchange of seed-pair rows (oea_p2p.cu) ------------------ */
+#define OEA_P2P_MAX_WORLD 16
+/* One rank's view of the exchange.  window[g] is rank g's window (oea_p2p_window_create on rank g) as mapped in THIS
+ * process (window[rank] is the local allocation, the others come from oea_p2p_window_open). */
+typedef struct oea_seed_xchg {
+    int32_t        rank, world;      /* world <= OEA_P2P_MAX_WORLD */
+    int32_t        pitch;            /* floats per row, == the table's pitch */
+    int32_t        max_rows;         /* rows per (parity, source rank) slot: max over ranks of the owned-row count */
+    void*          window[OEA_P2P_MAX_WORLD];
+    const int32_t* own_ids;          /* [n_own] device: the rows this rank owns and publishes, in slot order */
+    int32_t        n_own;
+    const int32_t* slot_ids;         /* [world, max_rows] device: table row of every received slot, -1 = padding */
+    int32_t*       ticket;           /* device int32, zero-initialised (last-CTA election of the push kernel) */
+} oea_seed_xchg;
+
 /* ---- misc ---------------------------------------------------------------------------------- */
 int         oea_abi_version(void);
 const char* oea_error_string(int code);
@@ -452,6 +467,29 @@ int oea_align_loss_l1(const float* x, int32_t ld, int32_t dim, const int32_t* le
                       int32_t k, const int32_t* neg_left, const int32_t* neg_right,
                       const int32_t* neg2_left, const int32_t* neg2_right, float gamma,
                       double* loss_out, float* grad, void* stream);
+
+/* ---- path (i) across GPUs (the reference is single-device: models/basic_model.py:211-236 keeps the
+ * seed entities coherent simply by training both KGs' triples in one session) ---------------------------------------
+ * Exception to "never allocate": an exchange window must be a whole cudaMalloc allocation to be IPC-exportable, so
+ * the library creates and frees it.  create/open/close/destroy and oea_seed_xchg_status are synchronous host calls;
+ * pack/unpack/push/pull are asynchronous on `stream`. */
+size_t oea_seed_xchg_window_bytes(int32_t world, int32_t max_rows, int32_t pitch);
+int oea_p2p_window_create(size_t bytes, void** dev_ptr, void* handle_out64);   /* zero-filled; 64-byte IPC handle out */
+int oea_p2p_window_open(const void* handle64, void** peer_ptr);                /* maps a peer's window (lazy peer access) */
+int oea_p2p_window_close(void* peer_ptr);
+int oea_p2p_window_destroy(void* dev_ptr);
+/* Publish this rank's owned rows of `weight` as epoch `epoch` (>= 1, increasing by 1 per call) into every peer's window:
+ * one kernel, 128-bit stores over NVLink + a release flag per peer.  No library collective is involved. */
+int oea_seed_push(const oea_seed_xchg* x, const float* weight, uint64_t epoch, void* stream);
+/* Wait (on the device, at most timeout_ns) until every peer has published `epoch`, then copy the received rows into
+ * `weight` (rows owned by this rank are left alone).  A timeout sets the status word instead of hanging. */
+int oea_seed_pull(const oea_seed_xchg* x, float* weight, uint64_t epoch, uint64_t timeout_ns, void* stream);
+int oea_seed_xchg_status(const oea_seed_xchg* x, int32_t* status_host);        /* 0 = ok, 1 = a pull timed out */
+/* The same exchange around a library all-gather (fallback where peer mapping is unavailable): own rows -> contiguous
+ * send buffer, and [world, max_rows, pitch] receive buffer -> table rows (skipping `rank`'s own slot). */
+int oea_seed_pack(const float* weight, int32_t pitch, const int32_t* ids, int32_t n, float* out, void* stream);
+int oea_seed_unpack(float* weight, int32_t pitch, const float* recv, const int32_t* slot_ids, int32_t world,
+                    int32_t max_rows, int32_t rank, void* stream);
 
 #ifdef __cplusplus
 }

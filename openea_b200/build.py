@@ -43,27 +43,56 @@ def _digest(paths):
     return h.hexdigest()
 
 
-def build_cuda(force=False, verbose=False):
-    os.makedirs(LIB_DIR, exist_ok=True)
-    srcs = _sources()
-    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
-    deps.append(os.path.join(ROOT, "include", "oea.h"))
-    stamp = os.path.join(LIB_DIR, "liboea.sha256")
-    digest = _digest(deps)
-    if not force and os.path.exists(LIB_PATH) and os.path.exists(stamp):
-        with open(stamp) as f:
-            if f.read().strip() == digest:
-                return LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + srcs
+def _compile_one(job):
+    src, obj, flags = job
+    cmd = [_nvcc()] + flags + ["-c", "-o", obj, src]
     res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError("nvcc failed building liboea.so")
-    if verbose:
-        sys.stderr.write(res.stderr)
-    with open(stamp, "w") as f:
-        f.write(digest)
-    return LIB_PATH
+    return src, res.returncode, res.stdout + res.stderr
+
+
+def build_cuda(force=False, verbose=False, defines=(), out=None):
+    """Compile every csrc/*.cu to an object (in parallel, cached per file on the digest of the file + all headers +
+    flags) and link liboea.so.  `defines`/`out`: kernel A/B variants (scripts/ab_*.sh) built next to the default."""
+    from concurrent.futures import ThreadPoolExecutor
+    os.makedirs(LIB_DIR, exist_ok=True)
+    out = out or LIB_PATH
+    srcs = _sources()
+    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    hdrs.append(os.path.join(ROOT, "include", "oea.h"))
+    flags = [f for f in NVCC_FLAGS if f != "-shared"] + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else [])
+    tag = hashlib.sha256(" ".join(flags).encode()).hexdigest()[:8]
+    obj_dir = os.path.join(LIB_DIR, "obj_" + tag)
+    os.makedirs(obj_dir, exist_ok=True)
+    hdr_digest = _digest(hdrs)
+    jobs, objs = [], []
+    for src in srcs:
+        obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".o")
+        stamp = obj + ".sha256"
+        digest = hashlib.sha256((hdr_digest + _digest([src])).encode()).hexdigest()
+        objs.append(obj)
+        fresh = os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read().strip() == digest
+        if force or verbose or not fresh:
+            jobs.append((src, obj, flags, stamp, digest))
+    relink = bool(jobs) or not os.path.exists(out)
+    if jobs:
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as pool:
+            results = list(pool.map(_compile_one, [j[:3] for j in jobs]))
+        failed = [r for r in results if r[1] != 0]
+        for src, rc, text in results:
+            if rc != 0 or verbose:
+                sys.stderr.write(text)
+        if failed:
+            raise RuntimeError("nvcc failed building " + ", ".join(os.path.basename(r[0]) for r in failed))
+        for _, obj, _, stamp, digest in jobs:
+            with open(stamp, "w") as f:
+                f.write(digest)
+    if relink:
+        cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out] + objs
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+            raise RuntimeError("nvcc failed linking liboea.so")
+    return out
 
 
 def build_oracle(force=False):

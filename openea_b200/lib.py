@@ -15,6 +15,7 @@ LOSS_MARGIN, LOSS_LIMITED, LOSS_LOGISTIC, LOSS_POSITIVE, LOSS_LOGSIGMOID = 0, 1,
 OPT_SGD, OPT_ADAGRAD, OPT_ADAM, OPT_ADADELTA = 0, 1, 2, 3
 WEIGHT_DIRECT, WEIGHT_RECIPROCAL = 0, 1
 METRIC_INNER, METRIC_L1, METRIC_L2 = 0, 1, 2
+P2P_MAX_WORLD = 16
 MODEL_TRANSE, MODEL_TRANSH, MODEL_TRANSD, MODEL_DISTMULT, MODEL_SIMPLE = 0, 1, 2, 3, 4
 
 
@@ -78,6 +79,12 @@ class FedPipeline(C.Structure):
                 ("host_loss", C.c_void_p * 2)]
 
 
+class SeedXchg(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("pitch", C.c_int32), ("max_rows", C.c_int32),
+                ("window", C.c_void_p * 16), ("own_ids", C.c_void_p), ("n_own", C.c_int32), ("slot_ids", C.c_void_p),
+                ("ticket", C.c_void_p)]
+
+
 class Model(C.Structure):
     _fields_ = [("kind", C.c_int32), ("ent", _TP), ("rel", _TP), ("ent_aux", _TP), ("rel_aux", _TP)]
 
@@ -135,6 +142,16 @@ SIGNATURES = {
     "oea_tripleset_build": (C.c_int, [_P, _I, _P, C.c_uint32, C.c_uint32, C.c_uint32, _P]),
     "oea_model_score_fed": (C.c_int, [C.POINTER(Model), _P, _P, _P, _I, _P, _P, _P, _I, C.POINTER(LossCfg), C.c_float,
                                       _P, _P]),
+    "oea_seed_xchg_window_bytes": (C.c_size_t, [_I, _I, _I]),
+    "oea_p2p_window_create": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p), _P]),
+    "oea_p2p_window_open": (C.c_int, [_P, C.POINTER(C.c_void_p)]),
+    "oea_p2p_window_close": (C.c_int, [_P]),
+    "oea_p2p_window_destroy": (C.c_int, [_P]),
+    "oea_seed_push": (C.c_int, [C.POINTER(SeedXchg), _P, C.c_uint64, _P]),
+    "oea_seed_pull": (C.c_int, [C.POINTER(SeedXchg), _P, C.c_uint64, C.c_uint64, _P]),
+    "oea_seed_xchg_status": (C.c_int, [C.POINTER(SeedXchg), C.POINTER(C.c_int32)]),
+    "oea_seed_pack": (C.c_int, [_P, _I, _P, _I, _P, _P]),
+    "oea_seed_unpack": (C.c_int, [_P, _I, _P, _P, _I, _I, _I, _P]),
     "oea_triple_sample_batch": (C.c_int, [C.POINTER(KgView), C.POINTER(KgView), C.POINTER(TripleSet),
                                           C.POINTER(SampleCfg), _I, _TP, _P, _P, C.POINTER(C.c_int32), _P]),
 }

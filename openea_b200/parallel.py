@@ -57,9 +57,19 @@ def block_range(n, rank, world_size):
 
 
 class SeedRowSync:
-    """Per-epoch exchange of the seed-pair rows: every rank sends the rows it owns, all ranks receive all."""
+    """Per-epoch exchange of the seed-pair rows: every rank publishes the rows it owns, every rank receives the others'.
 
-    def __init__(self, weight, seed_ids, rank, world_size):
+    Three transports, same result:
+      'p2p'   (GPUs of one box) — oea_seed_push / oea_seed_pull (csrc/oea_p2p.cu): one kernel stores the owned rows straight
+              into every peer's exchange window over NVLink and raises a release flag; the consumer kernel acquires the
+              flags and copies the rows into its table.  No library collective, no host synchronisation.
+      'nccl'  — oea_seed_pack → ncclAllGather (asynchronous, overlaps the next training step) → oea_seed_unpack; the
+              fallback where peer mapping (CUDA IPC) is not available.
+      'torch' — index_select / all_gather / index_copy_ (CPU tensors with gloo: the host-logic tests).
+    `push()` publishes, `pull()` applies the last publication; a training loop calls push() after the last step of an
+    epoch and pull() one step later so the transfer overlaps a step; `sync()` = push + pull."""
+
+    def __init__(self, weight, seed_ids, rank, world_size, mode="auto", timeout_s=20.0):
         self.weight = weight                    # [rows, pitch] tensor (CUDA with NCCL, CPU with gloo)
         self.rank, self.world = rank, world_size
         ids = np.unique(np.asarray(seed_ids, dtype=np.int64))
@@ -68,34 +78,163 @@ class SeedRowSync:
         self.counts = [len(p) for p in per_owner]
         self.max_cnt = max(1, max(self.counts))
         dev = weight.device
-        self.mine = torch.as_tensor(per_owner[rank], dtype=torch.long, device=dev)
-        # destination row of every received slot (padding slots point at a scratch row index −1 → masked out)
-        dst = np.full((world_size, self.max_cnt), -1, dtype=np.int64)
-        for g, p in enumerate(per_owner):
-            dst[g, :len(p)] = p
-        flat = dst.reshape(-1)
-        self.valid = torch.as_tensor(np.flatnonzero(flat >= 0), dtype=torch.long, device=dev)
-        self.dst_rows = torch.as_tensor(flat[flat >= 0], dtype=torch.long, device=dev)
         pitch = weight.shape[1]
-        self.send = torch.zeros(self.max_cnt, pitch, dtype=weight.dtype, device=dev)
-        self.recv = torch.zeros(world_size * self.max_cnt, pitch, dtype=weight.dtype, device=dev)
-        self.bytes_per_sync = self.recv.numel() * self.recv.element_size()
+        slot = np.full((world_size, self.max_cnt), -1, dtype=np.int64)
+        for g, p in enumerate(per_owner):
+            slot[g, :len(p)] = p
+        self.n_own = self.counts[rank]
+        self.bytes_per_sync = world_size * self.max_cnt * pitch * weight.element_size()
+        self.epoch = 0
+        self._pending = None
+        self._x = None
+        self.timeout_ns = int(timeout_s * 1e9)
+        if mode == "auto":
+            mode = "p2p" if weight.is_cuda else "torch"
+        if world_size == 1:
+            mode = "torch"
+        self.mode = mode
+        if mode == "torch":
+            self.mine = torch.as_tensor(per_owner[rank], dtype=torch.long, device=dev)
+            flat = slot.copy()
+            flat[rank, :] = -1                  # own rows are authoritative: never overwritten
+            flat = flat.reshape(-1)
+            self.valid = torch.as_tensor(np.flatnonzero(flat >= 0), dtype=torch.long, device=dev)
+            self.dst_rows = torch.as_tensor(flat[flat >= 0], dtype=torch.long, device=dev)
+            self.send = torch.zeros(self.max_cnt, pitch, dtype=weight.dtype, device=dev)
+            self.recv = torch.zeros(world_size * self.max_cnt, pitch, dtype=weight.dtype, device=dev)
+            return
+        from . import lib as L
+        self._L, self._lib = L, L.load()
+        self.own_ids = torch.as_tensor(per_owner[rank], dtype=torch.int32, device=dev)
+        self.slot_ids = torch.as_tensor(slot.reshape(-1), dtype=torch.int32, device=dev)
+        if mode == "p2p" and not self._open_windows(pitch):
+            self.mode = mode = "nccl"           # every rank takes the same decision (all-reduced inside)
+        if mode == "nccl":
+            self.send = torch.zeros(self.max_cnt, pitch, dtype=weight.dtype, device=dev)
+            self.recv = torch.zeros(world_size * self.max_cnt, pitch, dtype=weight.dtype, device=dev)
 
-    def sync(self):
+    # ---- p2p plumbing: windows are created by the library (IPC-exportable), handles travel through torch.distributed ----
+    def _open_windows(self, pitch):
+        import ctypes as C
+        L, lib = self._L, self._lib
+        dev = self.weight.device
+        nbytes = lib.oea_seed_xchg_window_bytes(self.world, self.max_cnt, pitch)
+        ok = 1
+        local = C.c_void_p(0)
+        handle = (C.c_ubyte * 64)()
+        if self.world > L.P2P_MAX_WORLD or lib.oea_p2p_window_create(nbytes, C.byref(local), handle) != 0:
+            ok = 0
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle) if ok else None)
+        opened = {}
+        if ok and all(h is not None for h in handles):
+            for g, h in enumerate(handles):
+                if g == self.rank:
+                    continue
+                ptr = C.c_void_p(0)
+                if lib.oea_p2p_window_open((C.c_ubyte * 64).from_buffer_copy(h), C.byref(ptr)) != 0:
+                    ok = 0
+                    break
+                opened[g] = ptr.value
+        else:
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            for ptr in opened.values():
+                lib.oea_p2p_window_close(C.c_void_p(ptr))
+            if local.value:
+                lib.oea_p2p_window_destroy(local)
+            return False
+        self._local_window, self._opened = local.value, opened
+        self._ticket = torch.zeros(1, dtype=torch.int32, device=dev)
+        win = (C.c_void_p * 16)()
+        for g in range(self.world):
+            win[g] = local.value if g == self.rank else opened[g]
+        self._x = L.SeedXchg(self.rank, self.world, pitch, self.max_cnt, win, self.own_ids.data_ptr(), self.n_own,
+                             self.slot_ids.data_ptr(), self._ticket.data_ptr())
+        dist.barrier()                          # every window is mapped everywhere before the first push
+        return True
+
+    def _stream(self):
+        import ctypes as C
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def push(self):
+        """Publish this rank's owned rows (epoch += 1)."""
         if self.world == 1:
             return
-        n = self.mine.numel()
-        if n:
-            self.send[:n] = self.weight.index_select(0, self.mine)
-        dist.all_gather_into_tensor(self.recv, self.send)
-        self.weight.index_copy_(0, self.dst_rows, self.recv.index_select(0, self.valid))
+        self.epoch += 1
+        if self.mode == "p2p":
+            import ctypes as C
+            self._L.check(self._lib.oea_seed_push(C.byref(self._x), C.c_void_p(self.weight.data_ptr()), self.epoch,
+                                                  self._stream()), "oea_seed_push")
+        elif self.mode == "nccl":
+            import ctypes as C
+            self._L.check(self._lib.oea_seed_pack(C.c_void_p(self.weight.data_ptr()), self.weight.shape[1],
+                                                  C.c_void_p(self.own_ids.data_ptr()), self.n_own,
+                                                  C.c_void_p(self.send.data_ptr()), self._stream()), "oea_seed_pack")
+            self._pending = dist.all_gather_into_tensor(self.recv, self.send, async_op=True)
+        else:
+            n = self.mine.numel()
+            if n:
+                self.send[:n] = self.weight.index_select(0, self.mine)
+            dist.all_gather_into_tensor(self.recv, self.send)
+
+    def pull(self):
+        """Apply the last publication of every peer to this replica."""
+        if self.world == 1 or self.epoch == 0:
+            return
+        if self.mode == "p2p":
+            import ctypes as C
+            self._L.check(self._lib.oea_seed_pull(C.byref(self._x), C.c_void_p(self.weight.data_ptr()), self.epoch,
+                                                  self.timeout_ns, self._stream()), "oea_seed_pull")
+        elif self.mode == "nccl":
+            import ctypes as C
+            if self._pending is not None:
+                self._pending.wait()            # stream-level dependency, no host block
+                self._pending = None
+            self._L.check(self._lib.oea_seed_unpack(C.c_void_p(self.weight.data_ptr()), self.weight.shape[1],
+                                                    C.c_void_p(self.recv.data_ptr()), C.c_void_p(self.slot_ids.data_ptr()),
+                                                    self.world, self.max_cnt, self.rank, self._stream()), "oea_seed_unpack")
+        else:
+            if self.dst_rows.numel():
+                self.weight.index_copy_(0, self.dst_rows, self.recv.index_select(0, self.valid))
+
+    def sync(self):
+        self.push()
+        self.pull()
+
+    def status(self):
+        """0 = ok; 1 = a device-side wait for a peer's publication timed out (p2p mode)."""
+        if self.mode != "p2p" or self._x is None:
+            return 0
+        import ctypes as C
+        st = C.c_int32(0)
+        self._L.check(self._lib.oea_seed_xchg_status(C.byref(self._x), C.byref(st)), "oea_seed_xchg_status")
+        return int(st.value)
+
+    def close(self):
+        """Unmap the peers' windows and free the local one (collective: every rank calls it)."""
+        if self.mode != "p2p" or self._x is None:
+            return
+        import ctypes as C
+        torch.cuda.synchronize()
+        dist.barrier()                          # nobody is still storing into a window that is about to go away
+        for ptr in self._opened.values():
+            self._lib.oea_p2p_window_close(C.c_void_p(ptr))
+        dist.barrier()
+        self._lib.oea_p2p_window_destroy(C.c_void_p(self._local_window))
+        self._x = None
 
 
 def assemble_owned_rows(weight, rank, world_size):
     """Final table: every row taken from its owner (all rows, same mechanism as the seed sync)."""
     if world_size == 1:
         return weight
-    SeedRowSync(weight, np.arange(weight.shape[0]), rank, world_size).sync()
+    # one-off, whole table: the library all-gather is the right tool (no window of table size is mapped for it)
+    x = SeedRowSync(weight, np.arange(weight.shape[0]), rank, world_size, mode="nccl" if weight.is_cuda else "torch")
+    x.sync()
     return weight
 
 

@@ -14,25 +14,24 @@ os.environ.setdefault("OEA_CACHE_DIR", os.path.join(tempfile.gettempdir(), "oea_
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
-    config.addinivalue_line("markers", "first_hw_run: exercises code that has not yet executed on a GPU; collected last and "
-                                       "quarantined (a failure is reported as xfailed + listed in the summary)")
+    config.addinivalue_line("markers", "first_hw_run: exercises code that has not yet executed on a GPU; collected last, strict "
+                                       "(OEA_QUARANTINE=1 opts into xfail reporting)")
 
 
 def pytest_collection_modifyitems(config, items):
-    """Tests of code that has never executed on a GPU (`first_hw_run`) are collected last and QUARANTINED: they run, but
-    a failure is reported as xfailed (and listed with its first line in the terminal summary) instead of turning the
-    suite of hardware-verified tests red or — under `-x` — cutting it short; a stuck kernel ends the process after 10
-    minutes instead of holding the GPU box.  OEA_STRICT_FIRST_HW=1 makes them ordinary tests.  A test leaves the
-    quarantine (the marker is removed) after its first green run on hardware."""
+    """Tests of code that has never executed on a GPU (`first_hw_run`) are collected LAST, so that under `-x` a fault in
+    brand-new code cannot cut the hardware-verified tests short, and get a 10-minute timeout (a stuck kernel ends the
+    process instead of holding the GPU box).  They are ORDINARY, strict tests: a failure is a failure.
+    OEA_QUARANTINE=1 (opt-in, builder's own exploratory runs only) additionally reports their failures as xfailed and
+    lists them in the terminal summary.  The marker is removed after the first green run on hardware."""
     late = [it for it in items if it.get_closest_marker("first_hw_run")]
     if late:
         items[:] = [it for it in items if not it.get_closest_marker("first_hw_run")] + late
-    if os.environ.get("OEA_STRICT_FIRST_HW") == "1":
-        return
     for it in late:
-        it.add_marker(pytest.mark.xfail(strict=False, reason="first run on hardware (quarantined, see tests/conftest.py)"))
         if config.pluginmanager.hasplugin("timeout"):
             it.add_marker(pytest.mark.timeout(600, method="thread"))
+        if os.environ.get("OEA_QUARANTINE") == "1":
+            it.add_marker(pytest.mark.xfail(strict=False, reason="first run on hardware (quarantined, see tests/conftest.py)"))
 
 
 def pytest_terminal_summary(terminalreporter, exitstatus, config):

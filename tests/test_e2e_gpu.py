@@ -70,7 +70,6 @@ def test_bootea_lifecycle(cuda_device, tiny_kgs, tmp_path):
     assert len(pairs) == len(model.kgs.test_links)
 
 
-@pytest.mark.first_hw_run      # the mapping epoch now draws its seed-pair batches on the device
 def test_mtranse_lifecycle(cuda_device, tiny_kgs, tmp_path):
     from openea_b200 import presets
     from openea_b200.approaches import MTransE

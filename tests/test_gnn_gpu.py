@@ -119,7 +119,6 @@ def test_gcn_unit_step_matches_oracle(cuda_device, with_features):
     np.testing.assert_allclose(table.raw().cpu().numpy(), want_W, rtol=1e-4, atol=2e-6 * np.abs(want_W).max() + 1e-7)
 
 
-@pytest.mark.first_hw_run      # model code re-plumbed for row sharding / array graph builders since its last GPU run
 def test_gcn_align_lifecycle(cuda_device, tmp_path):
     import os
     import re
@@ -176,7 +175,6 @@ def test_gat_aggregate_fwd_bwd_matches_autograd(cuda_device):
     np.testing.assert_allclose(s2.grad.cpu().numpy(), o2.grad.numpy(), rtol=2e-4, atol=2e-5)
 
 
-@pytest.mark.first_hw_run      # model code re-plumbed for row sharding / array graph builders since its last GPU run
 def test_alinet_step_matches_oracle(cuda_device):
     """One session.run([loss, optimizer]) of the AliNet graph: loss, gradients and the TF-Adam update."""
     from openea_b200 import gnn
@@ -253,7 +251,6 @@ class _FakeKgs:
         self.train_links = [tuple(x) for x in arr["train_links"].tolist()]
 
 
-@pytest.mark.first_hw_run      # model code re-plumbed for row sharding / array graph builders since its last GPU run
 def test_rdgcn_step_matches_oracle(cuda_device):
     """One session.run([optimizer, loss]) of the RDGCN graph (rdgcn.py:317-338): outputs, loss, gradients."""
     from openea_b200.approaches import rdgcn as R

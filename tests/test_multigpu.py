@@ -55,6 +55,63 @@ def test_sharded_eval_equals_single_gpu():
     assert sorted(res) == [(0, "ok"), (1, "ok")], res
 
 
+def _xchg_worker(rank, world, port, out):
+    """Seed-row exchange transports: own kernels over peer memory ('p2p'), pack + ncclAllGather + unpack ('nccl')."""
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from openea_b200 import parallel as par
+        rng = np.random.default_rng(5)
+        rows, pitch = 4001, 100
+        seeds = rng.permutation(rows)[:1500]
+        owner = seeds % world
+        modes = {}
+        for mode in ("p2p", "nccl"):
+            w = torch.zeros(rows, pitch, device="cuda")
+            x = par.SeedRowSync(w, seeds, rank, world, mode=mode)
+            modes[mode] = x.mode
+            for epoch in range(1, 6):        # five epochs: both parities of the double buffer are reused
+                # every rank's replica: row r holds (epoch, rank, r) patterns; after the exchange a seed row must hold its
+                # OWNER's pattern, every other row this rank's own
+                base = torch.arange(rows, device="cuda", dtype=torch.float32)[:, None] + torch.arange(pitch, device="cuda")[None, :] / 128.0
+                w.copy_(base + 10000.0 * epoch + 1000000.0 * rank)
+                x.push()
+                w[0, 0] += 0.0               # an unrelated kernel between push and pull (the training step's place)
+                x.pull()
+                torch.cuda.synchronize()
+                want = (base + 10000.0 * epoch + 1000000.0 * rank).clone()
+                so = torch.as_tensor(seeds, device="cuda"), torch.as_tensor(owner, device="cuda", dtype=torch.float32)
+                want[so[0]] = base[so[0]] + 10000.0 * epoch + 1000000.0 * so[1][:, None]
+                assert torch.equal(w, want), (mode, epoch, int((w != want).sum()))
+            assert x.status() == 0
+            x.close()
+        out.put((rank, "ok " + modes["p2p"]))
+    except Exception as e:
+        import traceback
+        out.put((rank, "FAIL: %r\n%s" % (e, traceback.format_exc())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_seed_row_exchange_transports():
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_xchg_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    # the peer-memory transport must actually have been used on a P2P-capable box (no silent fallback)
+    assert sorted(res) == [(0, "ok p2p"), (1, "ok p2p")], res
+
+
 def _gcn_worker(rank, world, port, out):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)

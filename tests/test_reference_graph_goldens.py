@@ -132,7 +132,6 @@ def test_engine_on_the_emulator_reproduces_the_reference_graph(cpu_engine, monke
 
 
 @pytest.mark.gpu
-@pytest.mark.first_hw_run
 @pytest.mark.parametrize("case", sorted(META))
 def test_engine_on_the_gpu_reproduces_the_reference_graph(cuda_device, monkeypatch, case):
     from openea_b200 import engine
@@ -207,7 +206,6 @@ def test_gcn_align_unit_on_the_emulator_reproduces_the_reference_unit(cpu_engine
 
 
 @pytest.mark.gpu
-@pytest.mark.first_hw_run
 @pytest.mark.parametrize("branch", ["se", "ae"])
 def test_gcn_align_unit_on_the_gpu_reproduces_the_reference_unit(cuda_device, branch):
     from openea_b200 import engine
@@ -284,7 +282,6 @@ def test_rdgcn_layer_on_the_emulator_reproduces_the_reference_layer(cpu_engine, 
 
 
 @pytest.mark.gpu
-@pytest.mark.first_hw_run
 def test_rdgcn_layer_on_the_gpu_reproduces_the_reference_layer(cuda_device):
     replay_rdgcn("cuda")
 
@@ -344,7 +341,6 @@ def test_alinet_model_on_the_emulator_reproduces_the_reference_graph(cpu_engine,
 
 
 @pytest.mark.gpu
-@pytest.mark.first_hw_run
 def test_alinet_model_on_the_gpu_reproduces_the_reference_graph(cuda_device):
     replay_alinet("cuda")
 
@@ -405,7 +401,6 @@ def test_attre_on_the_emulator_reproduces_the_reference_graph(cpu_engine, monkey
 
 
 @pytest.mark.gpu
-@pytest.mark.first_hw_run
 def test_attre_on_the_gpu_reproduces_the_reference_graph(cuda_device, monkeypatch):
     from openea_b200 import engine
     replay_attre(engine, "cuda", monkeypatch)

@@ -62,14 +62,12 @@ def test_mapping_trainer_steps_equal_float64_dense_adam(cpu_engine):
 
 
 @pytest.mark.gpu
-@pytest.mark.first_hw_run
 def test_mapping_trainer_steps_equal_float64_dense_adam_gpu(cuda_device):
     from openea_b200 import engine
     _check_mapping_trainer(engine, "cuda")
 
 
 @pytest.mark.gpu
-@pytest.mark.first_hw_run
 def test_sea_lifecycle_gpu(cuda_device, tiny_kgs, tmp_path):
     """set_args / set_kgs / init / run / test / save of SEA on the tiny synthetic KG pair (mapping mode: separate id
     spaces): both losses fall, the mapped alignment beats chance, both mapping matrices are saved."""

@@ -311,7 +311,6 @@ def test_score_family_lifecycle(cuda_device, tiny_kgs, tmp_path, name):
     assert ent.shape == (model.kgs.entities_num, 32) and np.isfinite(ent).all()
 
 
-@pytest.mark.first_hw_run      # passed on a B200 with the host bootstrapping; BootEA.run now bootstraps on the device
 def test_bootea_transh_lifecycle(cuda_device, tiny_kgs, tmp_path):
     from openea_b200 import presets
     from openea_b200.approaches import BootEA_TransH
@@ -326,7 +325,6 @@ def test_bootea_transh_lifecycle(cuda_device, tiny_kgs, tmp_path):
     assert _hits1(out, "accurate results:") > 4.0        # chance = 0.24 %; BootEA (TransE) reaches > 8 % at 300 epochs
 
 
-@pytest.mark.first_hw_run
 def test_resume_from_checkpoint_continues_the_same_run(cuda_device, tiny_kgs, tmp_path):
     """6 epochs in one go == 3 epochs, checkpoint, a NEW model restored from the file, 3 more epochs (variables and
     Adagrad accumulators; gradient sums are atomics, so agreement is to fp32 accumulation noise, not bit-wise)."""
@@ -365,7 +363,6 @@ def test_resume_from_checkpoint_continues_the_same_run(cuda_device, tiny_kgs, tm
     assert resumed._epoch_seed == straight._epoch_seed
 
 
-@pytest.mark.first_hw_run
 def test_pipelined_host_step_equals_the_synchronous_one(cuda_device):
     """oea_triple_step_fed_host_submit / _collect (depth-2 pipeline: copies and the host wait off the critical path)
     against oea_triple_step_fed_host on the same batches from the same tables: per-step losses and the final tables."""
@@ -396,7 +393,6 @@ def test_pipelined_host_step_equals_the_synchronous_one(cuda_device):
         assert not y.grad.any().item() and not y.touched.any().item()
 
 
-@pytest.mark.first_hw_run
 @pytest.mark.parametrize("loss,k", [("limited", 10), ("logistic", 4), ("margin-based", 1), ("positive", 0)])
 @pytest.mark.parametrize("d", [75, 100, 300])
 def test_grouped_fed_scorer_equals_the_per_triple_scorer(cuda_device, monkeypatch, loss, k, d):
@@ -434,7 +430,6 @@ def test_grouped_fed_scorer_equals_the_per_triple_scorer(cuda_device, monkeypatc
     _assert_rows_close(losses[1][2], losses[0][2], "entity table after two host-index steps")
 
 
-@pytest.mark.first_hw_run
 @pytest.mark.parametrize("shape,n_ent,n_rel,B,k", [("15K", 30000, 450, 5000, 10), ("100K", 200000, 600, 20000, 10)])
 def test_full_size_properties_of_the_fed_scorers(cuda_device, shape, n_ent, n_rel, B, k):
     """At BASELINE.json's batch shapes, where the oracle is too slow: size-independent properties of the fed scorers
@@ -486,7 +481,6 @@ def test_full_size_properties_of_the_fed_scorers(cuda_device, shape, n_ent, n_re
           transh(((slice(None), slice(None)),)))
 
 
-@pytest.mark.first_hw_run
 @pytest.mark.parametrize("opt", ["Adagrad", "SGD"])
 @pytest.mark.parametrize("loss,k,d", [("limited", 10, 100), ("margin-based", 1, 75), ("logistic", 4, 200)])
 def test_one_launch_fed_step_equals_the_two_launch_path(cuda_device, monkeypatch, opt, loss, k, d):

@@ -8,7 +8,7 @@ import torch
 from tests.helpers import make_tables
 from tests.test_e2e_gpu import tiny_kgs        # noqa: F401  (fixture: the tiny synthetic dataset folder)
 
-pytestmark = [pytest.mark.gpu, pytest.mark.first_hw_run]
+pytestmark = [pytest.mark.gpu]
 
 
 def _normed(x, on):
@@ -144,7 +144,8 @@ def test_jape_lifecycle(cuda_device, tiny_kgs, tmp_path):
     args.batch_size, args.max_epoch, args.start_valid, args.dim = 1000, 60, 1000, 32
     args.attr_max_epoch, args.sub_mat_size = 3, 50
     model, out = _run(JAPE, args, tiny_kgs, "sharing", tmp_path)
-    triple = [float(x) for x in re.findall(r"avg\\. triple loss:\\s*(-?[0-9.]+)", out)]
-    assert len(triple) == 60 and triple[-1] < triple[0], (triple[0], triple[-1])
+    triple = [float(x) for x in re.findall(r"avg\. triple loss:\s*(-?[0-9.]+)", out)]
+    assert len(triple) == 60, (len(triple), out[-600:])
+    assert triple[-1] < triple[0], (triple[0], triple[-1])
     assert len(re.findall(r"sim loss:", out)) == 60
     assert _hits1(out, "accurate results:") >= 0.0       # the result line exists; accuracy is calibrated once this has run on a GPU
