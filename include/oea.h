@@ -110,6 +110,10 @@ typedef struct oea_sample_cfg {
     uint64_t epoch_seed;      /* permutation + sampling seed of this epoch */
     const uint64_t* dev_seed; /* optional DEVICE scalar xor-ed into epoch_seed at kernel start: lets a CUDA graph of a
                                * whole epoch (one node pair per step) be replayed with a new seed every epoch */
+    int32_t  shard_rank;      /* exact-parity multi-GPU mode: this call scores only the positives p of the   */
+    int32_t  shard_world;     /* step's batch with p % shard_world == shard_rank (draws depend on p, not on the shard, so
+                               * the union over ranks IS the single-GPU batch); 0 or 1 = the whole batch.  Honoured by
+                               * oea_triple_score_sampled; the other sampling entry points require the whole batch. */
 } oea_sample_cfg;
 
 /* ---- path (i) across GPUs: peer-memory exchange of seed-pair rows (oea_p2p.cu) ------------------ */

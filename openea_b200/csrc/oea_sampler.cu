@@ -87,6 +87,7 @@ extern "C" int oea_triple_sample_batch(const oea_kg_view* kg1, const oea_kg_view
     SampledParams P;
     int n_pos = 0;
     int rc = sampler_prepare(kg1, kg2, tset, smp, &P, &n_pos); if (rc) return rc;
+    if (P.shard_world != 1) return OEA_ERR_RANGE;
     if (sampler != 0 && sampler != 1) return OEA_ERR_KIND;
     if (!pos_hrt || !n_pos_host || (smp->neg_per_pos > 0 && !neg_hrt)) return OEA_ERR_NULL;
     if (warm != nullptr) { rc = check_table(warm, false); if (rc) return rc; }

@@ -17,6 +17,7 @@ struct SampledParams {
     int max_try;
     uint64_t seed;
     const uint64_t* dev_seed;   // optional device scalar xor-ed into seed (CUDA-graph replays)
+    int shard_rank, shard_world;   // this launch scores the positives p ≡ shard_rank (mod shard_world); 0 / 1 = all
     int diag;            // OEA_DIAG bit mask (measurement only): 1 synthetic negatives (no cand/hash chain),
                          // 2 no gradient output, 4 no negatives, 8 identity permutation
 };
@@ -123,6 +124,9 @@ inline int sampler_prepare(const oea_kg_view* kg1, const oea_kg_view* kg2, const
     slice_of(kg2->n_triples, b2, smp->step, &P.start[1], &P.n_slice[1]);
     P.k = smp->neg_per_pos; P.step = smp->step; P.max_try = smp->max_try; P.seed = smp->epoch_seed;
     P.dev_seed = smp->dev_seed;
+    if (smp->shard_world < 0 || (smp->shard_world > 1 && (smp->shard_rank < 0 || smp->shard_rank >= smp->shard_world))) return OEA_ERR_RANGE;
+    P.shard_world = smp->shard_world > 1 ? smp->shard_world : 1;
+    P.shard_rank = smp->shard_world > 1 ? smp->shard_rank : 0;
     {   // measurement-only ablation switches ("where the time goes"); read once per process
         static int diag_cached = -1;
         if (diag_cached < 0) { const char* dg = getenv("OEA_DIAG"); diag_cached = dg ? atoi(dg) : 0; }

@@ -16,6 +16,7 @@
 #include "oea_rowmath.cuh"
 #include "oea_rowopt.cuh"
 #include "oea_sampler.cuh"
+#include "oea_duo.cuh"
 #include <cooperative_groups.h>
 
 namespace oea {
@@ -161,7 +162,7 @@ k_score_sampled(TableDev ent, TableDev rel, SampledParams P, oea_loss_cfg cfg,
     const int k = P.k;
     float warp_loss = 0.f;
 
-    for (int p = warp_global; p < n_pos; p += n_warps) {
+    for (int p = warp_global * P.shard_world + P.shard_rank; p < n_pos; p += n_warps * P.shard_world) {
         const int q = p < P.n_slice[0] ? 0 : 1;
         const oea_kg_view& kg = P.kg[q];
         const int local = q == 0 ? p : p - P.n_slice[0];
@@ -282,39 +283,6 @@ k_score_sampled(TableDev ent, TableDev rel, SampledParams P, oea_loss_cfg cfg,
 // negatives: only Σ g_j·ê_j (per corrupted side) and Σ g_j are accumulated per octet, merged across the
 // 4 octets once, and octets 0/1/2 finish rows h / r / t.
 // ------------------------------------------------------------------------------------------------
-struct R4 {
-    float4 v[4];
-};
-__device__ __forceinline__ R4 load_oct(const float* __restrict__ base, int row, int pitch, int l, int p4) {
-    R4 r;
-    const float* p = base + (size_t)row * pitch;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int q = l + 8 * i;
-        r.v[i] = q < p4 ? ldg4(p + 4 * q) : f4(0.f);
-    }
-    return r;
-}
-__device__ __forceinline__ void red_oct(float* __restrict__ base, int row, int pitch, int l, int p4, const R4& g) {
-    float* p = base + (size_t)row * pitch;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int q = l + 8 * i;
-        if (q < p4) red_add4(p + 4 * q, g.v[i]);
-    }
-}
-__device__ __forceinline__ float oct_sum(float v) {
-    v += __shfl_xor_sync(OEA_FULL, v, 1);
-    v += __shfl_xor_sync(OEA_FULL, v, 2);
-    v += __shfl_xor_sync(OEA_FULL, v, 4);
-    return v;
-}
-__device__ __forceinline__ float cross_oct_sum(float v) {
-    v += __shfl_xor_sync(OEA_FULL, v, 8);
-    v += __shfl_xor_sync(OEA_FULL, v, 16);
-    return v;
-}
-
 #ifndef OEA_OCT_WARPS
 #define OEA_OCT_WARPS 4
 #endif
@@ -356,7 +324,7 @@ __device__ __forceinline__ void oct_score_body(const TableDev& ent, const TableD
     const bool margin_mode = cfg.loss_kind == OEA_LOSS_MARGIN;
     float lane_loss = 0.f;
 
-    for (int p = warp_global; p < n_pos; p += n_warps) {
+    for (int p = warp_global * P.shard_world + P.shard_rank; p < n_pos; p += n_warps * P.shard_world) {
         const int q = p < P.n_slice[0] ? 0 : 1;
         const oea_kg_view& kg = P.kg[q];
         const int local = q == 0 ? p : p - P.n_slice[0];
@@ -561,6 +529,29 @@ k_step_sampled_oct(TableDev ent, TableDev rel, const __grid_constant__ SampledPa
     oct_score_body(ent, rel, P, cfg, loss_out, nullptr, s_loss, s_stage);
     cooperative_groups::this_grid().sync();
     oct_rowopt_body<KIND>(A, B, ent.pitch, lr, blockIdx.x * kOctWarps + (threadIdx.x >> 5), gridDim.x * kOctWarps);
+}
+
+// The duo scorer (oea_duo.cuh): two positives per warp, sampled source.
+__global__ void __launch_bounds__(kDuoThreads, OEA_DUO_MINB)
+k_score_sampled_duo(TableDev ent, TableDev rel, const __grid_constant__ SampledParams P, oea_loss_cfg cfg,
+                    double* __restrict__ loss_out, int32_t* __restrict__ dbg) {
+    __shared__ double s_loss[kDuoWarps];
+    __shared__ DuoStage s_stage[kDuoWarps];
+    FedBatch none{};
+    duo_score_body<false>(ent, rel, P, none, cfg, loss_out, dbg, s_loss, s_stage);
+}
+
+// The whole sampled training step as ONE cooperative launch, duo scorer: score + gradients, grid barrier, row optimiser.
+template <int KIND>
+__global__ void __launch_bounds__(kDuoThreads, OEA_DUO_MINB)
+k_step_sampled_duo(TableDev ent, TableDev rel, const __grid_constant__ SampledParams P, oea_loss_cfg cfg,
+                   double* __restrict__ loss_out, OptTab A, OptTab B, float lr) {
+    __shared__ double s_loss[kDuoWarps];
+    __shared__ DuoStage s_stage[kDuoWarps];
+    FedBatch none{};
+    duo_score_body<false>(ent, rel, P, none, cfg, loss_out, nullptr, s_loss, s_stage);
+    cooperative_groups::this_grid().sync();
+    oct_rowopt_body<KIND>(A, B, ent.pitch, lr, blockIdx.x * kDuoWarps + (threadIdx.x >> 5), gridDim.x * kDuoWarps);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -768,14 +759,18 @@ extern "C" int oea_triple_score_sampled(const oea_table* ent, const oea_table* r
     if (n_pos == 0) return OEA_OK;
     TableDev e = table_dev(ent), r = table_dev(rel);
     const bool l1 = loss->score_kind == OEA_SCORE_L1;
-    if (!l1 && ent->pitch <= 128 && !oea_force_v1()) {
-        const int grid = grid_one_wave(k_score_sampled_oct, n_pos, kOctWarps);
+    if (!l1 && ent->pitch <= 128 && !oea_force_v1() && oea_use_duo(P.k)) {
+        const int pairs = ((n_pos + P.shard_world - 1) / P.shard_world + 1) / 2;
+        const int grid = grid_one_wave(k_score_sampled_duo, pairs, kDuoWarps);
+        OEA_LAUNCH(k_score_sampled_duo, grid, kDuoThreads, 0, st, e, r, P, *loss, loss_out, dbg_neg);
+    } else if (!l1 && ent->pitch <= 128 && !oea_force_v1()) {
+        const int grid = grid_one_wave(k_score_sampled_oct, (n_pos + P.shard_world - 1) / P.shard_world, kOctWarps);
         OEA_LAUNCH(k_score_sampled_oct, grid, kOctThreads, 0, st, e, r, P, *loss, loss_out, dbg_neg);
     } else {
 #define CALL(V)                                                                                              \
-    if (l1) { const int grid = grid_one_wave(k_score_sampled<OEA_SCORE_L1, V>, n_pos);                       \
+    if (l1) { const int grid = grid_one_wave(k_score_sampled<OEA_SCORE_L1, V>, (n_pos + P.shard_world - 1) / P.shard_world);                     \
               OEA_LAUNCH((k_score_sampled<OEA_SCORE_L1, V>), grid, kThreads, 0, st, e, r, P, *loss, loss_out, dbg_neg); } \
-    else { const int grid = grid_one_wave(k_score_sampled<OEA_SCORE_L2SQ, V>, n_pos);                        \
+    else { const int grid = grid_one_wave(k_score_sampled<OEA_SCORE_L2SQ, V>, (n_pos + P.shard_world - 1) / P.shard_world);                      \
            OEA_LAUNCH((k_score_sampled<OEA_SCORE_L2SQ, V>), grid, kThreads, 0, st, e, r, P, *loss, loss_out, dbg_neg); }
         OEA_DISPATCH_VEC(ent->pitch, CALL);
 #undef CALL
@@ -1150,6 +1145,7 @@ extern "C" int oea_triple_step_sampled(const oea_table* ent, const oea_table* re
                                        const oea_sample_cfg* smp, const oea_loss_cfg* loss, const oea_opt_cfg* opt,
                                        double* loss_out, int32_t* n_pos_out, void* stream) {
     if (!opt) return OEA_ERR_NULL;
+    if (smp && smp->shard_world > 1) return OEA_ERR_RANGE;   // sharded batches: score_sampled → gradient exchange → rowopt
     // One cooperative launch when the octet kernel applies and the optimiser is row-sparse (Adagrad / SGD)
     const bool fuse = loss && ent && rel && loss->score_kind == OEA_SCORE_L2SQ && ent->pitch <= 128 && !oea_force_v1() &&
                       (opt->kind == OEA_OPT_ADAGRAD || opt->kind == OEA_OPT_SGD) && !oea_no_fuse();
@@ -1161,6 +1157,7 @@ extern "C" int oea_triple_step_sampled(const oea_table* ent, const oea_table* re
     SampledParams P;
     int n_pos = 0;
     int rc = sampled_prepare(ent, rel, kg1, kg2, tset, smp, loss, loss_out, &P, &n_pos); if (rc) return rc;
+    if (P.shard_world != 1) return OEA_ERR_RANGE;      // a sharded batch needs the gradient exchange between score and optimiser
     if (opt->kind == OEA_OPT_ADAGRAD && (!ent->state1 || !rel->state1)) return OEA_ERR_NULL;
     cudaStream_t st = (cudaStream_t)stream;
     if (n_pos_out) OEA_CUDA_TRY(cudaMemcpyAsync(n_pos_out, &n_pos, sizeof(int), cudaMemcpyHostToDevice, st));
@@ -1169,6 +1166,17 @@ extern "C" int oea_triple_step_sampled(const oea_table* ent, const oea_table* re
     OptTab A{ent->weight, ent->grad, ent->state1, ent->touched, ent->rows}, B{rel->weight, rel->grad, rel->state1, rel->touched, rel->rows};
     oea_loss_cfg cfg = *loss;
     float lr = opt->lr;
+    if (oea_use_duo(P.k)) {
+        const int pairs = (n_pos + 1) / 2;
+        if (opt->kind == OEA_OPT_ADAGRAD) {
+            const int grid = grid_one_wave(k_step_sampled_duo<OEA_OPT_ADAGRAD>, pairs, kDuoWarps);
+            OEA_CUDA_TRY(OEA_LAUNCH_COOPERATIVE(k_step_sampled_duo<OEA_OPT_ADAGRAD>, grid, kDuoThreads, st, e, r, P, cfg, loss_out, A, B, lr));
+        } else {
+            const int grid = grid_one_wave(k_step_sampled_duo<OEA_OPT_SGD>, pairs, kDuoWarps);
+            OEA_CUDA_TRY(OEA_LAUNCH_COOPERATIVE(k_step_sampled_duo<OEA_OPT_SGD>, grid, kDuoThreads, st, e, r, P, cfg, loss_out, A, B, lr));
+        }
+        return OEA_OK;
+    }
     if (opt->kind == OEA_OPT_ADAGRAD) {
         const int grid = grid_one_wave(k_step_sampled_oct<OEA_OPT_ADAGRAD>, n_pos, kOctWarps);
         OEA_CUDA_TRY(OEA_LAUNCH_COOPERATIVE(k_step_sampled_oct<OEA_OPT_ADAGRAD>, grid, kOctThreads, st, e, r, P, cfg, loss_out, A, B, lr));

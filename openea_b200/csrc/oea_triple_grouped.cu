@@ -14,6 +14,7 @@
 
 #include "oea_rowmath.cuh"
 #include "oea_rowopt.cuh"
+#include "oea_duo.cuh"
 
 namespace oea {
 
@@ -187,6 +188,27 @@ k_step_fed_grouped(TableDev ent, TableDev rel,
     oct_rowopt_body<KIND>(A, B, ent.pitch, lr, blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5), gridDim.x * kWarpsPerBlock);
 }
 
+// The duo scorer (oea_duo.cuh) on a fed batch: two positives per warp, octet row layout, squared-L2 score, pitch <= 128,
+// k <= 16.  Negatives that share fewer than two rows with their positive take the general-triple path inside the body.
+__global__ void __launch_bounds__(kDuoThreads, OEA_DUO_MINB)
+k_score_fed_duo(TableDev ent, TableDev rel, FedBatch F, oea_loss_cfg cfg, double* __restrict__ loss_out) {
+    __shared__ double s_loss[kDuoWarps];
+    __shared__ DuoStage s_stage[kDuoWarps];
+    SampledParams none;
+    duo_score_body<true>(ent, rel, none, F, cfg, loss_out, nullptr, s_loss, s_stage);
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(kDuoThreads, OEA_DUO_MINB)
+k_step_fed_duo(TableDev ent, TableDev rel, FedBatch F, oea_loss_cfg cfg, double* __restrict__ loss_out, OptTab A, OptTab B, float lr) {
+    __shared__ double s_loss[kDuoWarps];
+    __shared__ DuoStage s_stage[kDuoWarps];
+    SampledParams none;
+    duo_score_body<true>(ent, rel, none, F, cfg, loss_out, nullptr, s_loss, s_stage);
+    cooperative_groups::this_grid().sync();
+    oct_rowopt_body<KIND>(A, B, ent.pitch, lr, blockIdx.x * kDuoWarps + (threadIdx.x >> 5), gridDim.x * kDuoWarps);
+}
+
 }  // namespace oea
 
 using namespace oea;
@@ -208,6 +230,13 @@ extern "C" int oea_triple_score_fed_grouped(const oea_table* ent, const oea_tabl
     if ((loss->loss_kind == OEA_LOSS_POSITIVE || loss->loss_kind == OEA_LOSS_LOGSIGMOID) && k != 0) return OEA_ERR_SHAPE;
     TableDev e = table_dev(ent), r = table_dev(rel);
     const bool l1 = loss->score_kind == OEA_SCORE_L1;
+    if (!l1 && ent->pitch <= 128 && oea_use_duo(k)) {
+        FedBatch F{pos_h, pos_r, pos_t, neg_h, neg_r, neg_t, n_pos, k};
+        const int grid = grid_one_wave(k_score_fed_duo, (n_pos + 1) / 2, kDuoWarps);
+        OEA_LAUNCH(k_score_fed_duo, grid, kDuoThreads, 0, (cudaStream_t)stream, e, r, F, *loss, loss_out);
+        OEA_LAUNCH_CHECK();
+        return OEA_OK;
+    }
     const int grid = grid_for(n_pos);
 #define OEA_RUN_GROUPED(S, V) \
     OEA_LAUNCH((k_score_fed_grouped<S, V>), grid, kThreads, 0, (cudaStream_t)stream, e, r, pos_h, pos_r, pos_t, n_pos, neg_h, neg_r, neg_t, k, *loss, loss_out)
@@ -245,6 +274,17 @@ extern "C" int oea_triple_step_fed_grouped(const oea_table* ent, const oea_table
     oea_loss_cfg cfg = *loss;
     float lr = opt->lr;
     int np = n_pos;
+    if (ent->pitch <= 128 && oea_use_duo(k)) {
+        FedBatch F{pos_h, pos_r, pos_t, neg_h, neg_r, neg_t, n_pos, k};
+        if (opt->kind == OEA_OPT_ADAGRAD) {
+            const int grid = grid_one_wave(k_step_fed_duo<OEA_OPT_ADAGRAD>, (n_pos + 1) / 2, kDuoWarps);
+            OEA_CUDA_TRY(OEA_LAUNCH_COOPERATIVE(k_step_fed_duo<OEA_OPT_ADAGRAD>, grid, kDuoThreads, st, e, r, F, cfg, loss_out, A, B, lr));
+        } else {
+            const int grid = grid_one_wave(k_step_fed_duo<OEA_OPT_SGD>, (n_pos + 1) / 2, kDuoWarps);
+            OEA_CUDA_TRY(OEA_LAUNCH_COOPERATIVE(k_step_fed_duo<OEA_OPT_SGD>, grid, kDuoThreads, st, e, r, F, cfg, loss_out, A, B, lr));
+        }
+        return OEA_OK;
+    }
 #define OEA_RUN_STEP(V, KIND)                                                                                            \
     do { const int grid = grid_one_wave(k_step_fed_grouped<OEA_SCORE_L2SQ, V, KIND>, n_pos);                             \
          OEA_CUDA_TRY(OEA_LAUNCH_COOPERATIVE((k_step_fed_grouped<OEA_SCORE_L2SQ, V, KIND>), grid, kThreads, st, e, r, pos_h, pos_r, \

@@ -333,9 +333,12 @@ class TripleTrainer:
         return self._view_val
 
     def score_sampled(self, kg1, kg2, tset, batch_size, neg_per_pos, step, epoch_seed, max_try=10,
-                      loss_out=None, dbg=None, n_pos_out=None):
+                      loss_out=None, dbg=None, n_pos_out=None, shard=None):
+        """Fused sampler + scorer, gradients accumulated (no optimiser).  shard = (rank, world): score only the positives
+        p ≡ rank (mod world) of the step's batch — the exact-parity multi-GPU mode (parallel.ExactReplicaStep)."""
         out = self.loss_dev if loss_out is None else loss_out
-        smp = L.SampleCfg(int(batch_size), int(neg_per_pos), int(step), int(max_try), int(epoch_seed) & (2**64 - 1), 0)
+        sr, sw = (0, 0) if shard is None else (int(shard[0]), int(shard[1]))
+        smp = L.SampleCfg(int(batch_size), int(neg_per_pos), int(step), int(max_try), int(epoch_seed) & (2**64 - 1), 0, sr, sw)
         k1, k2, ts = kg1.view(), kg2.view(), tset.view()
         L.check(self.lib.oea_triple_score_sampled(
             C.byref(self.ent.c_struct()), C.byref(self.rel.c_struct()), C.byref(k1), C.byref(k2), C.byref(ts),

@@ -50,7 +50,7 @@ class TripleSet(C.Structure):
 
 class SampleCfg(C.Structure):
     _fields_ = [("batch_size", C.c_int32), ("neg_per_pos", C.c_int32), ("step", C.c_int32), ("max_try", C.c_int32),
-                ("epoch_seed", C.c_uint64), ("dev_seed", C.c_void_p)]
+                ("epoch_seed", C.c_uint64), ("dev_seed", C.c_void_p), ("shard_rank", C.c_int32), ("shard_world", C.c_int32)]
 
 
 class SimCfg(C.Structure):

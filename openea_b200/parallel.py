@@ -228,6 +228,35 @@ class SeedRowSync:
         self._x = None
 
 
+class ExactReplicaStep:
+    """Exact-parity multi-GPU mode of path (i) ("exact-parity alternative"): tables REPLICATED, the BATCH
+    sharded.  Rank g scores the positives p ≡ g (mod G) of the very batch one GPU would draw (the sampler's draws depend
+    on p, not on the shard), then gradients, row flags and the loss are all-reduced and the identical optimiser step is
+    applied on every replica.  Replicas stay bit-identical to each other; against one GPU the only difference is the
+    fp32 summation order of the gradient (1e-4 relative, the same tolerance as the oracle tests)."""
+
+    def __init__(self, trainer):
+        self.trainer = trainer
+        self.loss_step = torch.zeros(1, dtype=torch.float64, device=trainer.ent.device)
+
+    def step(self, kg1, kg2, tset, batch_size, neg_per_pos, step, epoch_seed, max_try=10):
+        tr = self.trainer
+        rank, ws = world()
+        if ws == 1:
+            tr.score_sampled(kg1, kg2, tset, batch_size, neg_per_pos, step, epoch_seed, max_try=max_try)
+            tr.apply()
+            return
+        self.loss_step.zero_()
+        tr.score_sampled(kg1, kg2, tset, batch_size, neg_per_pos, step, epoch_seed, max_try=max_try,
+                         loss_out=self.loss_step, shard=(rank, ws))
+        for tab in (tr.ent, tr.rel):
+            dist.all_reduce(tab.grad)
+            dist.all_reduce(tab.touched, op=dist.ReduceOp.MAX)
+        dist.all_reduce(self.loss_step)
+        tr.loss_dev += self.loss_step
+        tr.apply()
+
+
 def assemble_owned_rows(weight, rank, world_size):
     """Final table: every row taken from its owner (all rows, same mechanism as the seed sync)."""
     if world_size == 1:

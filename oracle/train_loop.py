@@ -24,7 +24,7 @@ def _batch_module():
 
 
 def train_triples(arr, dim, batch_size, neg_per_pos, epochs, loss="limited", lr=0.01, margin=0.01, neg_margin=2.0,
-                  balance=0.2, truncated_eps=None, truncated_freq=10, seed=0, init="normal", log=None):
+                  balance=0.2, truncated_eps=None, truncated_freq=10, seed=0, init="normal", log=None, on_epoch=None):
     """arr: dict from openea_b200.synth.synth_id_arrays.  Returns the final DenseState."""
     bat = _batch_module()
     random.seed(seed)
@@ -72,6 +72,8 @@ def train_triples(arr, dim, batch_size, neg_per_pos, epochs, loss="limited", lr=
         random.shuffle(t2)
         if log:
             log("epoch %d, avg. triple loss: %.4f" % (epoch, tot / max(1, cnt)))
+        if on_epoch is not None:
+            on_epoch(epoch, st)
         if truncated_eps is not None and epoch % truncated_freq == 0:
             en = orc.l2_normalize(st.ent)
             k1, k2 = int((1 - truncated_eps) * len(e1)), int((1 - truncated_eps) * len(e2))

@@ -214,13 +214,46 @@ def test_emulated_pair_distance_loss_matches_autograd(cpu_engine, norm, d, weigh
     assert set(np.flatnonzero(te.touched.numpy())) <= set(a.tolist()) | set(b.tolist())
 
 
-@pytest.fixture()
-def cpu_engine_oct(cpu_engine, monkeypatch):
-    """The same engine with the octet kernels enabled: the octet sampled scorer and the one-launch step (score, grid
-    barrier, octet row optimiser — launched as one block on the emulator, so its grid barrier is the block's)."""
+@pytest.fixture(params=["duo", "oct"])
+def cpu_engine_oct(cpu_engine, monkeypatch, request):
+    """The same engine with the octet-layout kernels enabled: the sampled scorer (duo: two positives per warp, the default;
+    oct: one positive per warp, OEA_SCORE_DUO=0) and the one-launch step (score, grid barrier, octet row optimiser —
+    launched as one block on the emulator, so its grid barrier is the block's)."""
     monkeypatch.delenv("OEA_NO_FUSE")
     monkeypatch.delenv("OEA_SCORE_V1")
+    monkeypatch.setenv("OEA_SCORE_DUO", "1" if request.param == "duo" else "0")
     return cpu_engine
+
+
+def test_emulated_duo_and_octet_scorers_sample_the_same_batch(cpu_engine, monkeypatch):
+    """The duo scorer (two positives per warp) draws, negative for negative, the batch the one-positive octet scorer draws
+    from the same seed, and accumulates the same gradients: odd and even numbers of positives, k = 0 / 1 (margin) / 6 / 16,
+    sharded launches included."""
+    monkeypatch.delenv("OEA_NO_FUSE")
+    monkeypatch.delenv("OEA_SCORE_V1")
+    rng = np.random.default_rng(77)
+    t1, t2, kg1, kg2, tset, _ = _sampled_setup(cpu_engine, rng)
+    n, n_rel, d = 50, 4, 12
+    ent, rel = make_tables(rng, 2 * n, n_rel, d)
+    for loss, k, B, shard in (("limited", 6, 33, None), ("limited", 16, 32, None), ("margin-based", 1, 31, None),
+                              ("positive", 0, 20, None), ("limited", 5, 37, (1, 3)), ("logistic", 3, 34, (0, 2))):
+        got = {}
+        for variant in ("1", "0"):
+            monkeypatch.setenv("OEA_SCORE_DUO", variant)
+            tr = cpu_engine.TripleTrainer(cpu_engine.EmbeddingTable(ent, True, "Adagrad", device="cpu"),
+                                          cpu_engine.EmbeddingTable(rel, True, "Adagrad", device="cpu"),
+                                          cpu_engine.loss_cfg(loss, "L2", 0.8 if loss == "margin-based" else 0.1, 2.0, 0.2), 0.01)
+            dbg = torch.full((B, 2 + k), -7, dtype=torch.int32)
+            tr.score_sampled(kg1, kg2, tset, B, k, 1, 991, dbg=dbg, shard=shard)
+            got[variant] = (dbg.numpy().copy(), tr.ent.grad.numpy().copy(), tr.rel.grad.numpy().copy(),
+                            tr.ent.touched.numpy().copy(), tr.read_loss())
+        a, b = got["1"], got["0"]
+        assert np.array_equal(a[0], b[0]), (loss, k, B, shard)
+        assert (a[0][:, 0] != -7).sum() > 0
+        np.testing.assert_allclose(a[1], b[1], rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(a[2], b[2], rtol=1e-4, atol=1e-6)
+        assert np.array_equal(a[3] != 0, b[3] != 0)
+        assert a[4] == pytest.approx(b[4], rel=1e-5)
 
 
 def _sampled_setup(engine, rng, opt="Adagrad"):

@@ -112,6 +112,96 @@ def test_seed_row_exchange_transports():
     assert sorted(res) == [(0, "ok p2p"), (1, "ok p2p")], res
 
 
+def _exact_setup(seed=11):
+    from openea_b200 import engine as eng
+    from tests.helpers import make_tables
+    rng = np.random.default_rng(seed)
+    n_ent, n_rel, d = 3000, 24, 100
+    ent, rel = make_tables(rng, n_ent, n_rel, d)
+    ents1, ents2 = np.arange(0, n_ent, 2, dtype=np.int32), np.arange(1, n_ent, 2, dtype=np.int32)
+
+    def mk(ents, n, lo, hi):
+        tri = np.stack([rng.choice(ents, n), rng.integers(lo, hi, n), rng.choice(ents, n)], 1).astype(np.int32)
+        return np.unique(tri, axis=0)
+    t1, t2 = mk(ents1, 2600, 0, 12), mk(ents2, 2200, 12, 24)
+    kg1, kg2 = eng.DeviceKG(t1, ents1, n_ent), eng.DeviceKG(t2, ents2, n_ent)
+    tset = eng.DeviceTripleSet([kg1.triples, kg2.triples], n_ent, n_rel)
+    te, tr = eng.EmbeddingTable(ent, True, "Adagrad", "cuda"), eng.EmbeddingTable(rel, True, "Adagrad", "cuda")
+    trn = eng.TripleTrainer(te, tr, eng.loss_cfg("limited", "L2", 0.01, 2.0, 0.2), lr=0.01)
+    return trn, kg1, kg2, tset
+
+
+def test_batch_shards_union_is_the_whole_batch(cuda_device):
+    """One GPU: the gradients of the G shards of a step's batch (shard = (g, G)) add up to the whole batch's gradients,
+    same touched rows, same loss — the property the exact-parity multi-GPU mode rests on."""
+    B, k = 512, 10
+    for G in (2, 3, 8):
+        whole, kg1, kg2, tset = _exact_setup()
+        parts, *_ = _exact_setup()
+        for step in range(2):
+            whole.score_sampled(kg1, kg2, tset, B, k, step, 4242)
+            for g in range(G):
+                parts.score_sampled(kg1, kg2, tset, B, k, step, 4242, shard=(g, G))
+            torch.cuda.synchronize()
+            for a, b in ((whole.ent, parts.ent), (whole.rel, parts.rel)):
+                torch.testing.assert_close(b.grad, a.grad, rtol=1e-4, atol=1e-6)
+                assert torch.equal(a.touched != 0, b.touched != 0)
+            lw, lp = whole.read_loss(), parts.read_loss()
+            assert abs(lw - lp) <= 1e-6 * abs(lw), (lw, lp)
+            whole.apply(); parts.apply()
+
+
+def _exact_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from openea_b200 import parallel as par
+        B, k, steps = 512, 10, 12
+        single, kg1, kg2, tset = _exact_setup()
+        sharded, kg1b, kg2b, tsetb = _exact_setup()
+        ex = par.ExactReplicaStep(sharded)
+        for step in range(steps):
+            single.step_sampled(kg1, kg2, tset, B, k, step % 9, 99 + step // 9)
+            ex.step(kg1b, kg2b, tsetb, B, k, step % 9, 99 + step // 9)
+        torch.cuda.synchronize()
+        lw, lp = single.read_loss(), sharded.read_loss()
+        assert abs(lw - lp) <= 1e-4 * abs(lw), (lw, lp)
+        for a, b in ((single.ent, sharded.ent), (single.rel, sharded.rel)):
+            torch.testing.assert_close(b.weight, a.weight, rtol=1e-4, atol=1e-6)
+            torch.testing.assert_close(b.state1, a.state1, rtol=1e-4, atol=1e-6)
+            # replicas are bit-identical to each other
+            mine = b.weight.clone()
+            other = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(other, mine)
+            assert all(torch.equal(o, mine) for o in other)
+        out.put((rank, "ok"))
+    except Exception as e:
+        import traceback
+        out.put((rank, "FAIL: %r\n%s" % (e, traceback.format_exc())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_exact_parity_mode_equals_single_gpu():
+    """SURVEY §8e exact-parity mode over NCCL: 12 sharded-batch steps on 2 GPUs leave the tables and Adagrad slots within
+    1e-4 of the single-GPU run on the same seeds, and the replicas bit-identical to each other."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_exact_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
 def _gcn_worker(rank, world, port, out):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
