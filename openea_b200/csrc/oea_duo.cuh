@@ -59,7 +59,7 @@ __device__ __forceinline__ float cross_oct_sum(float v) {
 #define OEA_DUO_WARPS 4
 #endif
 #ifndef OEA_DUO_MINB
-#define OEA_DUO_MINB 6
+#define OEA_DUO_MINB 5      // measured on B200 (profiles/r02_ab_duo.txt): 5 CTAs x 4 warps (<= 96 registers, no spills) beats 6 and 8 at both shapes
 #endif
 constexpr int kDuoWarps = OEA_DUO_WARPS;
 constexpr int kDuoThreads = kDuoWarps * OEA_WARP;

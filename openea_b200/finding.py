@@ -7,6 +7,8 @@ API) or CUDA tensors (internal fast path: no host round trip).  No fallback to N
 import ctypes as C
 import time
 
+import collections.abc
+
 import numpy as np
 import torch
 
@@ -206,6 +208,37 @@ def rank_stats(rk, top_k):
     return hits, float(sums[0] / n), float(sums[1] / n)
 
 
+class PairSet(collections.abc.Set):
+    """The alignment result {(i, top1[i])} as an immutable set view over the device result's host copy: a drop-in for the
+    Python set modules/finding/alignment.py:13 returns (membership, iteration, len, ==, set algebra), built without the
+    70 000-tuple Python loop in the evaluation's critical path — tuples are produced only when something iterates."""
+
+    __slots__ = ("_top1",)
+
+    def __init__(self, top1):
+        self._top1 = np.asarray(top1)
+
+    def __len__(self):
+        return int(self._top1.shape[0])          # row indices are distinct, so the pairs are
+
+    def __iter__(self):
+        return iter(zip(range(len(self)), self._top1.tolist()))
+
+    def __contains__(self, pair):
+        try:
+            i, j = pair
+            return 0 <= i < len(self) and int(self._top1[i]) == j
+        except (TypeError, ValueError):
+            return False
+
+    @classmethod
+    def _from_iterable(cls, it):                 # set algebra (|, &, -, ^) yields ordinary sets
+        return set(it)
+
+    def __repr__(self):
+        return "PairSet(%d pairs)" % len(self)
+
+
 def greedy_alignment(embed1, embed2, top_k, nums_threads, metric, normalize, csls_k, accurate):
     """Drop-in for modules/finding/alignment.py:13.  `nums_threads` is accepted and ignored (one GPU pass).
     Quick mode (accurate=False) computes the same exact ranks; only the printed line differs."""
@@ -219,8 +252,7 @@ def greedy_alignment(embed1, embed2, top_k, nums_threads, metric, normalize, csl
         top1 = par.allgather_blocks(top1, n1)
     else:
         top1, _, hits, mr, mrr = eval_alignment(embed1, embed2, top_k, metric, normalize, csls_k)
-    top1_h = top1.cpu().numpy()
-    alignment_rest = set(zip(range(len(top1_h)), top1_h.tolist()))
+    alignment_rest = PairSet(top1.cpu().numpy())
     hits_arr = np.array(hits)
     cost = time.time() - t
     if accurate:

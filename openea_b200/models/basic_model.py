@@ -219,6 +219,9 @@ class BasicModel:
                          nums_threads=self.args.test_threads_num)
 
     def save(self):
+        self._sync_replicas()          # under torchrun: the owners' rows everywhere; only rank 0 writes the files
+        if par.world()[0] != 0:
+            return
         ent_embeds = self.ent_embeds.lookup().cpu().numpy()      # what `self.ent_embeds.eval()` returns in TF
         rel_embeds = self.rel_embeds.lookup().cpu().numpy()
         mapping_mat = self.mapping_mat.raw().cpu().numpy() if self.mapping_mat is not None else None
@@ -336,10 +339,20 @@ class BasicModel:
     def save_checkpoint(self, path, epoch):
         """Everything a run needs to continue after `epoch`: variables, optimiser slots, the sampler's epoch seed,
         early-stopping state and the host RNG streams (mapping batches, GNN negatives)."""
+        # RNG streams as plain ints / tensors so that the file loads with torch.load(weights_only=True): a checkpoint
+        # from an untrusted source cannot run code at load time
+        pr = random.getstate()
+        nr = np.random.get_state()
         state = {"epoch": int(epoch), "epoch_seed": int(self._epoch_seed), "flag1": self.flag1, "flag2": self.flag2,
-                 "class": self.__class__.__name__, "python_random": random.getstate(), "numpy_random": np.random.get_state(),
+                 "class": self.__class__.__name__,
+                 "python_random": {"version": int(pr[0]), "state": [int(x) for x in pr[1]], "gauss": pr[2]},
+                 "numpy_random": {"kind": str(nr[0]), "keys": torch.from_numpy(np.asarray(nr[1], dtype=np.int64).copy()),
+                                  "pos": int(nr[2]), "has_gauss": int(nr[3]), "cached": float(nr[4])},
                  "tables": {name: tab.state_dict() for name, tab in self._checkpoint_tables().items()},
                  "extra": self._extra_state()}
+        # under torchrun every rank reaches this point with identical replicas (the callers sync first): rank 0 writes
+        if par.world()[0] != 0:
+            return path
         os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
         tmp = path + ".tmp"
         torch.save(state, tmp)
@@ -349,7 +362,7 @@ class BasicModel:
     def load_checkpoint(self, path):
         """Restore a save_checkpoint() file into an initialised model (call after init()); returns the epoch to
         continue from and makes run() start there."""
-        state = torch.load(path, map_location="cpu", weights_only=False)
+        state = torch.load(path, map_location="cpu", weights_only=True)
         if state["class"] != self.__class__.__name__:
             raise ValueError("checkpoint of %s loaded into %s" % (state["class"], self.__class__.__name__))
         tables = self._checkpoint_tables()
@@ -358,8 +371,9 @@ class BasicModel:
         for name, tab in tables.items():
             tab.load_state_dict(state["tables"][name])
         self._epoch_seed, self.flag1, self.flag2 = state["epoch_seed"], state["flag1"], state["flag2"]
-        random.setstate(state["python_random"])
-        np.random.set_state(state["numpy_random"])
+        pr, nr = state["python_random"], state["numpy_random"]
+        random.setstate((pr["version"], tuple(pr["state"]), pr["gauss"]))
+        np.random.set_state((nr["kind"], nr["keys"].numpy().astype(np.uint32), nr["pos"], nr["has_gauss"], nr["cached"]))
         self._load_extra_state(state.get("extra") or {})
         self._start_epoch = state["epoch"] + 1
         return self._start_epoch
@@ -391,6 +405,7 @@ class BasicModel:
         for i in range(start_epoch, self.args.max_epoch + 1):
             self.launch_training_1epo(i, triple_steps, steps_tasks, None, neighbors1, neighbors2)
             if every and i % every == 0:
+                self._sync_replicas()          # under torchrun: identical tables on every rank, rank 0 writes the file
                 self.save_checkpoint(self.out_folder + "checkpoint.pt", i)
             if i >= self.args.start_valid and i % self.args.eval_freq == 0:
                 flag = self.valid(self.args.stop_metric)

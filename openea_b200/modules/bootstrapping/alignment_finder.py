@@ -111,12 +111,13 @@ def _weight_lookup(sim_mat):
     return lambda x, y: float(sim_mat[x, y])
 
 
-def mwgm_scipy(pairs, sim_mat):
-    """Maximum-weight matching on the bipartite candidate graph.  The reference calls graph-tool's
-    max_cardinality_matching(heuristic=True, weight=…) (itself a heuristic) or igraph's
-    maximum_bipartite_matching; neither library exists here, so this uses a greedy-by-weight matching
-    improved by SciPy's optimal assignment on each connected component when it is small enough.
-    Exact agreement with the reference's matcher is unpinned."""
+def mwgm_greedy(pairs, sim_mat):
+    """Greedy-by-weight matching on the bipartite candidate graph: edges in descending weight, an edge is kept when both
+    endpoints are still free (a 1/2-approximation of the maximum weight).  This is the counterpart of what the reference's
+    BootEA actually runs: graph-tool's max_cardinality_matching(heuristic=True, weight=…, minimize=False)
+    (alignment_finder.py:83-113) is itself a greedy heuristic, not an exact matcher, and graph-tool does not exist here —
+    agreement with it is unpinned.  The device version (bootstrapping/device.py greedy_matching)
+    computes exactly this matching."""
     pairs = list(pairs)
     w = _weight_lookup(sim_mat)
     weights = np.array([w(x, y) for x, y in pairs], dtype=np.float64)
@@ -131,8 +132,49 @@ def mwgm_scipy(pairs, sim_mat):
     return matched
 
 
-mwgm_graph_tool = mwgm_scipy
-mwgm_igraph = mwgm_scipy
+def mwgm_exact(pairs, sim_mat):
+    """EXACT maximum-weight bipartite matching of the candidate graph — what the reference's igraph path computes
+    (alignment_finder.py:116-140, Graph.maximum_bipartite_matching(weights=…)).  igraph is absent here; the matching is
+    obtained from SciPy's sparse assignment solver on the doubled graph: left' = L ∪ R°, right' = R ∪ L° (° = a copy),
+    real edges (i, j) and their mirrors (j°, i°) cost C − w_ij, "stay unmatched" edges (i, i°), (j°, j) cost C with
+    C > max w.  A perfect matching of the doubled graph always exists and costs C·(|L|+|R|) − w(M) − w(M°) with M, M°
+    matchings over the same vertex set, so the minimum puts a maximum-weight matching on the original side.
+    Weights must be positive (they are similarities above sim_th > 0); ties between equal-weight optima are broken by
+    the solver, as they are by igraph."""
+    import scipy.sparse as sp
+    from scipy.sparse.csgraph import min_weight_full_bipartite_matching
+    pairs = list(pairs)
+    if not pairs:
+        return set()
+    w = _weight_lookup(sim_mat)
+    weights = np.array([w(x, y) for x, y in pairs], dtype=np.float64)
+    if (weights <= 0).any():
+        raise ValueError("mwgm_exact needs positive edge weights")
+    xs = {x: i for i, x in enumerate(dict.fromkeys(p[0] for p in pairs))}
+    ys = {y: j for j, y in enumerate(dict.fromkeys(p[1] for p in pairs))}
+    n1, n2 = len(xs), len(ys)
+    ei = np.array([xs[x] for x, _ in pairs]); ej = np.array([ys[y] for _, y in pairs])
+    big = float(weights.max()) * 2.0 + 1.0
+    # rows: L (0..n1) then R° (n1..n1+n2); columns: R (0..n2) then L° (n2..n2+n1)
+    rows = np.concatenate([ei, n1 + ej, np.arange(n1), n1 + np.arange(n2)])
+    cols = np.concatenate([ej, n2 + ei, n2 + np.arange(n1), np.arange(n2)])
+    cost = np.concatenate([big - weights, big - weights, np.full(n1 + n2, big)])
+    # duplicate candidate edges (the same (x, y) listed twice) would be summed by the sparse constructor: keep the best
+    key = rows.astype(np.int64) * (n1 + n2) + cols
+    order = np.lexsort((cost, key))
+    first = np.ones(len(order), dtype=bool)
+    first[1:] = key[order][1:] != key[order][:-1]
+    sel = order[first]
+    m = sp.csr_matrix((cost[sel], (rows[sel], cols[sel])), shape=(n1 + n2, n1 + n2))
+    r, c = min_weight_full_bipartite_matching(m)
+    inv_x = list(xs); inv_y = list(ys)
+    cand = set(pairs)
+    return {(inv_x[i], inv_y[j]) for i, j in zip(r.tolist(), c.tolist()) if i < n1 and j < n2 and (inv_x[i], inv_y[j]) in cand}
+
+
+mwgm_scipy = mwgm_greedy          # historical name (tests, device parity): the greedy matching
+mwgm_graph_tool = mwgm_greedy     # graph-tool's heuristic=True matcher is a greedy heuristic
+mwgm_igraph = mwgm_exact          # igraph's maximum_bipartite_matching is exact
 
 
 def check_new_alignment(aligned_pairs, context="check alignment"):

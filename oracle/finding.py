@@ -87,6 +87,23 @@ def greedy_alignment(e1, e2, top_k, metric, normalize, csls_k):
     return {(i, int(j)) for i, j in enumerate(top1)}, hits, mr, mrr
 
 
+def greedy_alignment_mt(e1, e2, top_k, metric, normalize, csls_k, nums_threads):
+    """greedy_alignment with the reference's task split (alignment.py:43-60: rows divided into `nums_threads` tasks, one
+    worker each, partial results merged); workers are threads here (the NumPy kernels release the GIL) instead of a
+    multiprocessing pool that pickles its slice of the matrix.  Same results as greedy_alignment."""
+    from concurrent.futures import ThreadPoolExecutor
+    s = sim(e1, e2, metric, normalize, csls_k)
+    n = s.shape[0]
+    bounds = np.linspace(0, n, max(1, int(nums_threads)) + 1).astype(int)
+    tasks = [(int(a), int(b)) for a, b in zip(bounds[:-1], bounds[1:]) if b > a]
+    with ThreadPoolExecutor(max_workers=len(tasks)) as pool:
+        parts = list(pool.map(lambda ab: rank_rows(s[ab[0]:ab[1]], np.arange(ab[0], ab[1])), tasks))
+    top1 = np.concatenate([p[0] for p in parts])
+    rank = np.concatenate([p[1] for p in parts])
+    hits, mr, mrr = metrics_from_ranks(rank, top_k)
+    return {(i, int(j)) for i, j in enumerate(top1)}, hits, mr, mrr
+
+
 def topk_rows(s, k):
     """Per-row k largest (values, indices), sorted descending, ties → lower index."""
     order = np.lexsort((np.broadcast_to(np.arange(s.shape[1]), s.shape), -s), axis=1)[:, :k]

@@ -27,7 +27,15 @@ def one_seed(job):
     from oracle import train_loop as tl, triple as orc
     from openea_b200.synth import synth_id_arrays
     orc.set_num_threads(threads)
-    arr = synth_id_arrays("15K")
+    arr = dict(synth_id_arrays("15K"))
+    # The reference trains its FIRST epoch on the triple lists in load order (they are shuffled only after every epoch,
+    # models/basic_model.py:234-235) — on the real datasets that is Python-set order, i.e. effectively random, but
+    # synth_id_arrays emits np.unique-SORTED triples: an epoch of batches with contiguous head ids inflates Adagrad's
+    # accumulators early and leaves the run ~6 epochs behind for good (measured: Hits@1 34.8 vs 36.4 at epoch 100,
+    # profiles/r02_hits_parity_15k.md).  The oracle therefore starts from a seeded random order, as real data would.
+    prng = np.random.default_rng(1000 + seed)
+    arr["triples1"] = arr["triples1"][prng.permutation(len(arr["triples1"]))]
+    arr["triples2"] = arr["triples2"][prng.permutation(len(arr["triples2"]))]
     curve, losses = {}, []
 
     def on_epoch(epoch, st):
@@ -51,7 +59,7 @@ def main():
     from oracle import ref_adapter
     with ProcessPoolExecutor(max_workers=len(args.seeds)) as pool:
         runs = list(pool.map(one_seed, [(s, args.epochs, args.threads) for s in args.seeds]))
-    out = {"what": "CPU oracle (reference sampler + dense TF-style step), AlignE/BootEA triple training on synth_id_arrays('15K')",
+    out = {"what": "CPU oracle (reference sampler + dense TF-style step), AlignE/BootEA triple training on synth_id_arrays('15K'), triple lists in a seeded random initial order",
            "sampler": "reference modules/train/batch.py" if ref_adapter.available() else "behavioural port",
            "config": {"dim": 100, "batch": 5000, "neg": 10, "loss": "limited(0.01, 2.0, 0.2)", "lr": 0.01, "eps": 0.9,
                       "truncated_freq": 10, "epochs": args.epochs, "top_k": [1, 5, 10, 50]},

@@ -331,3 +331,38 @@ def _quiet_read(path):
     from openea_b200.modules.load import read as rd
     with contextlib.redirect_stdout(io.StringIO()):
         return rd.read_relation_triples(path)[0]
+
+
+def test_mwgm_exact_is_optimal_where_greedy_is_not():
+    """alignment_finder.mwgm_igraph's counterpart (exact maximum-weight bipartite matching via the doubled-graph
+    assignment) against brute force on random small candidate graphs; greedy (graph-tool heuristic's counterpart) is a
+    1/2-approximation and differs on the textbook case."""
+    import itertools
+    from openea_b200.modules.bootstrapping import alignment_finder as af
+    sim = {(0, 0): 0.9, (0, 1): 0.85, (1, 0): 0.85}
+    assert af.mwgm_greedy(list(sim), sim) == {(0, 0)}
+    assert af.mwgm_exact(list(sim), sim) == {(0, 1), (1, 0)} == af.mwgm(list(sim), sim, af.mwgm_igraph)
+    rng = np.random.default_rng(0)
+    for _ in range(150):
+        n1, n2 = rng.integers(2, 7, 2)
+        edges = [(i, j) for i in range(n1) for j in range(n2) if rng.random() < 0.5]
+        if not edges:
+            continue
+        w = {e: float(rng.random() * 0.5 + 0.5) for e in edges}
+        got = af.mwgm_exact(edges, w)
+        assert len({a for a, _ in got}) == len(got) == len({b for _, b in got}) and got <= set(edges)
+        best = max(sum(w[e] for e in sub) for r in range(min(n1, n2) + 1) for sub in itertools.combinations(edges, r)
+                   if len({a for a, _ in sub}) == r and len({b for _, b in sub}) == r)
+        assert abs(sum(w[e] for e in got) - best) < 1e-9
+        assert sum(w[e] for e in af.mwgm_greedy(edges, w)) >= 0.5 * best - 1e-9
+
+
+def test_pair_set_behaves_like_the_reference_set():
+    """finding.PairSet (what greedy_alignment returns instead of a 70 000-tuple Python set) against a real set."""
+    from openea_b200.finding import PairSet
+    top1 = np.array([3, 0, 0, 2], dtype=np.int32)
+    ps, real = PairSet(top1), {(0, 3), (1, 0), (2, 0), (3, 2)}
+    assert len(ps) == 4 and set(ps) == real and ps == real and real == ps
+    assert (1, 0) in ps and (1, 1) not in ps and (9, 0) not in ps and "x" not in ps
+    assert ps - {(0, 3)} == real - {(0, 3)} and ps | {(7, 7)} == real | {(7, 7)} and ps & {(2, 0), (5, 5)} == {(2, 0)}
+    assert sorted(ps) == sorted(real) and [(i, j) for i, j in ps][0] == (0, 3)
