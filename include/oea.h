@@ -495,6 +495,16 @@ int oea_seed_pack(const float* weight, int32_t pitch, const int32_t* ids, int32_
 int oea_seed_unpack(float* weight, int32_t pitch, const float* recv, const int32_t* slot_ids, int32_t world,
                     int32_t max_rows, int32_t rank, void* stream);
 
+/* ---- f-4: stable alignment (modules/finding/alignment.py:87-133 stable_alignment, :171-224 galeshapley) ----------
+ * Suitor-proposing deferred acceptance over K3's top-`cut` lists: pref_idx / pref_val [n1, cut] are oea_sim_topk's
+ * outputs (descending similarity; the reviewer side ranks suitors by the same similarities, ties → lower suitor index).
+ * match[s] = reviewer held by suitor s, or -1.  At most max_rounds proposal rounds (the reference passes cut).
+ * SYNCHRONOUS: the round loop polls a device counter; *rounds_host (optional) receives the rounds run. */
+size_t oea_gale_shapley_workspace_bytes(int32_t n1, int32_t n2);
+int oea_gale_shapley(const int32_t* pref_idx, const float* pref_val, int32_t n1, int32_t n2, int32_t cut,
+                     int32_t max_rounds, int32_t* match, void* workspace, size_t workspace_bytes,
+                     int32_t* rounds_host, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

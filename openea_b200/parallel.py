@@ -257,6 +257,33 @@ class ExactReplicaStep:
         tr.apply()
 
 
+class ReplicaDeltaSum:
+    """Periodic combination of independently trained replicas (local-update data parallelism): every replica adds up what
+    ALL replicas changed since the last combination,  x ← x_ref + Σ_g (x_g − x_ref),  for the variables and for their
+    optimiser slots (Adagrad's accumulator is a sum of g², so the same rule gives the accumulator one process would
+    hold).  Unlike the owner-wins seed-row exchange no gradient contribution is discarded — a row trained as a tail on
+    one rank and as a head on another receives both — at the price of an all-reduce of the tables per combination.
+    Replicas are identical after every sync()."""
+
+    def __init__(self, tables):
+        self.items = []
+        for t in tables:
+            for name in ("weight", "state1", "state2"):
+                x = getattr(t, name, None)
+                if x is not None:
+                    self.items.append((x, x.clone()))
+        self.bytes_per_sync = sum(x.numel() * x.element_size() for x, _ in self.items)
+
+    def sync(self):
+        if world()[1] == 1:
+            return
+        for x, ref in self.items:
+            x -= ref                      # this replica's change since the last combination
+            dist.all_reduce(x)            # everybody's changes
+            x += ref
+            ref.copy_(x)
+
+
 def assemble_owned_rows(weight, rank, world_size):
     """Final table: every row taken from its owner (all rows, same mechanism as the seed sync)."""
     if world_size == 1:

@@ -25,7 +25,8 @@ sys.path.insert(0, ROOT)
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--mode", default="stale", choices=["stale", "exact"])
+    ap.add_argument("--mode", default="stale", choices=["stale", "exact", "delta"])
+    ap.add_argument("--sync-steps", type=int, default=0, help="delta mode: steps between delta sums (0 = once per global epoch)")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--epochs", type=int, default=100)
     ap.add_argument("--seeds", type=int, nargs="+", default=[11, 12, 13])
@@ -44,10 +45,10 @@ def main():
     dim, B, k, eps, freq = 100, 5000, 10, 0.9, 10
     T_global = len(arr["triples1"]) + len(arr["triples2"])
     t1, t2 = arr["triples1"], arr["triples2"]
-    if args.mode == "stale" and world > 1:
+    if args.mode in ("stale", "delta") and world > 1:
         t1, t2 = par.shard_triples(t1, rank, world), par.shard_triples(t2, rank, world)
     b_rank = B if (args.scaling == "weak" or args.mode == "exact") else max(1, B // world)
-    b_global = b_rank * (world if args.mode == "stale" else 1)
+    b_global = b_rank * (world if args.mode in ("stale", "delta") else 1)
     steps = -(-T_global // b_global)
     links = arr["test_links"]
     results = []
@@ -75,6 +76,8 @@ def main():
             xchg = par.SeedRowSync(ent.weight, seeds_rows, rank, world)
         if args.mode == "exact":
             exact = par.ExactReplicaStep(trn)
+        delta = par.ReplicaDeltaSum([ent, rel]) if (args.mode == "delta" and world > 1) else None
+        gstep = 0
         curve = {}
         for epoch in range(1, args.epochs + 1):
             for step in range(steps):
@@ -83,9 +86,14 @@ def main():
                 else:
                     # stale mode: every rank draws from ITS shard (different permutation seed per rank)
                     trn.step_sampled(kg1, kg2, tset, b_rank, k, step, 7919 * seed + epoch + 104729 * rank)
+                    gstep += 1
+                    if delta is not None and args.sync_steps > 0 and gstep % args.sync_steps == 0:
+                        delta.sync()
             trn.read_loss()
             if xchg is not None:
                 xchg.sync()
+            if delta is not None and (args.sync_steps == 0 or epoch in args.eval_at or epoch % freq == 0):
+                delta.sync()
             need_full = epoch in args.eval_at or epoch % freq == 0
             if need_full and world > 1 and args.mode == "stale":
                 par.assemble_owned_rows(ent.weight, rank, world)      # every row from its owner: replicas agree here
@@ -106,7 +114,7 @@ def main():
         torch.cuda.empty_cache()
     if rank == 0:
         out = {"n_gpus": world, "mode": args.mode if world > 1 else "single", "scaling": args.scaling, "epochs": args.epochs,
-               "seeds": args.seeds, "batch_per_rank": b_rank, "steps_per_epoch": steps, "at": {}}
+               "seeds": args.seeds, "sync_steps": args.sync_steps, "batch_per_rank": b_rank, "steps_per_epoch": steps, "at": {}}
         for ep in args.eval_at:
             h1 = np.array([c[ep]["hits"][0] for c in results]); h10 = np.array([c[ep]["hits"][2] for c in results])
             c1 = np.array([c[ep]["csls_hits"][0] for c in results]); mrr = np.array([c[ep]["mrr"] for c in results])

@@ -239,7 +239,6 @@ def _gcn_worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.first_hw_run
 def test_row_sharded_gcn_unit_equals_single_gpu():
     """SURVEY §8e-ii over NCCL: the row-sharded GCN-Align unit (liboea kernels + 3 all-gathers / 3 reduce-scatters per
     step) reproduces the single-GPU unit's loss, outputs and updated entity table."""
@@ -301,7 +300,6 @@ def _alinet_worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.first_hw_run
 def test_row_sharded_alinet_model_equals_single_gpu():
     """The row-sharded AliNet model (liboea aggregation kernels on rectangular row blocks + autograd all-gathers) gives
     the single-GPU model's layer outputs, loss and gradients."""
@@ -369,7 +367,6 @@ def _rdgcn_worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.first_hw_run
 def test_row_sharded_rdgcn_layer_equals_single_gpu():
     """The row-sharded RDGCN layer (entity rows sharded, relation-side tensors replicated, 2 all-reduces + 5 all-gathers
     per forward) gives the single-GPU layer's output, loss and gradients with the real kernels."""
@@ -413,7 +410,7 @@ def _bootea_worker(rank, world, port, folder, out):
         local = int(m._dkg1.triples.shape[0] + m._dkg2.triples.shape[0])
         total = torch.tensor([local], device="cuda"); dist.all_reduce(total)
         assert int(total) == kgs.kg1.relation_triples_num + kgs.kg2.relation_triples_num     # a partition of the triples
-        agree = torch.tensor([h1, -h1], device="cuda"); dist.all_reduce(agree, op=dist.ReduceOp.MAX)
+        agree = torch.tensor([h1, -h1], device="cuda", dtype=torch.float64); dist.all_reduce(agree, op=dist.ReduceOp.MAX)
         assert float(agree[0]) == h1 and float(-agree[1]) == h1, "every rank must print the same (sharded) evaluation"
         assert h1 > 5.0, h1                                       # chance 0.24 %; one GPU reaches ≈ 10 % at this budget
         out.put((rank, "ok"))
