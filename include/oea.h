@@ -500,6 +500,9 @@ int oea_seed_unpack(float* weight, int32_t pitch, const float* recv, const int32
  * outputs (descending similarity; the reviewer side ranks suitors by the same similarities, ties → lower suitor index).
  * match[s] = reviewer held by suitor s, or -1.  At most max_rounds proposal rounds (the reference passes cut).
  * SYNCHRONOUS: the round loop polls a device counter; *rounds_host (optional) receives the rounds run. */
+/* Turns oea_rows_select_topk's unordered per-row sets (k <= 128) into preference lists: val[r, :] = mat[r, idx[r, :]]
+ * sorted descending (equal values: lower column first), idx permuted alongside (in place). */
+int oea_rows_gather_sort(const float* mat, int64_t ld, int32_t n_rows, int32_t k, int32_t* idx, float* val, void* stream);
 size_t oea_gale_shapley_workspace_bytes(int32_t n1, int32_t n2);
 int oea_gale_shapley(const int32_t* pref_idx, const float* pref_val, int32_t n1, int32_t n2, int32_t cut,
                      int32_t max_rounds, int32_t* match, void* workspace, size_t workspace_bytes,

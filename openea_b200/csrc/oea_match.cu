@@ -60,9 +60,57 @@ __global__ void k_gs_resolve(int n1, const int32_t* __restrict__ prop, const uns
     }
 }
 
+// Orders an UNORDERED top-k set per row (oea_rows_select_topk's output, k <= 128) into a preference list: gathers the
+// similarities from the materialised matrix and sorts (value descending, equal values → lower column first) with a
+// 128-slot bitonic network in shared memory, one CTA of 128 threads per row.
+__global__ void __launch_bounds__(128)
+k_rows_gather_sort(const float* __restrict__ mat, long long ld, int n_rows, int k, int32_t* __restrict__ idx, float* __restrict__ val) {
+    __shared__ unsigned long long key[128];
+    const int row = blockIdx.x, t = threadIdx.x;
+    if (row >= n_rows) return;
+    unsigned long long mine = 0ull;                       // padding sorts last (every real key has bit 63 or payload set)
+    if (t < k) {
+        const int c = idx[(size_t)row * k + t];
+        mine = gs_key(__ldg(mat + (size_t)row * ld + c), c);
+    }
+    key[t] = mine;
+    __syncthreads();
+    for (int size = 2; size <= 128; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            const int partner = t ^ stride;
+            if (partner > t) {
+                const bool desc = (t & size) == 0;        // descending blocks first → whole array descending at the end
+                const unsigned long long a = key[t], b = key[partner];
+                if ((a < b) == desc) { key[t] = b; key[partner] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    if (t < k) {
+        const unsigned long long v = key[t];
+        const unsigned int c = 0xFFFFFFFFu - (unsigned int)(v & 0xFFFFFFFFull);
+        unsigned int u = (unsigned int)(v >> 32);
+        u = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
+        idx[(size_t)row * k + t] = (int32_t)c;
+        val[(size_t)row * k + t] = __uint_as_float(u);
+    }
+}
+
 }  // namespace oea
 
 using namespace oea;
+
+extern "C" int oea_rows_gather_sort(const float* mat, int64_t ld, int32_t n_rows, int32_t k, int32_t* idx, float* val, void* stream) {
+    if (!mat || !idx || !val) return OEA_ERR_NULL;
+    if (n_rows < 1 || k < 1 || k > 128 || ld < k) return OEA_ERR_RANGE;
+#ifndef OEA_HOST_EMU
+    k_rows_gather_sort<<<n_rows, 128, 0, (cudaStream_t)stream>>>(mat, (long long)ld, n_rows, k, idx, val);
+    OEA_LAUNCH_CHECK();
+    return OEA_OK;
+#else
+    return OEA_ERR_KIND;
+#endif
+}
 
 extern "C" size_t oea_gale_shapley_workspace_bytes(int32_t n1, int32_t n2) {
     if (n1 < 1 || n2 < 1) return 0;

@@ -270,6 +270,40 @@ def greedy_alignment(embed1, embed2, top_k, nums_threads, metric, normalize, csl
     return alignment_rest, hits_arr[0], mr, mrr
 
 
+def stable_matching(embed1, embed2, metric, normalize, csls_k, cut=100):
+    """Gale–Shapley (suitor-proposing, at most `cut` rounds) on the device: K3's top-`cut` list of every row is the
+    suitor's preference list, reviewers rank by the same similarities (oea_gale_shapley; alignment.py:87-133,171-224).
+    Returns (match [n1] int32 device tensor: the column held by row i or −1, rounds run)."""
+    lib = L.load()
+    e1, e2, d = _prep_pair(embed1, embed2, metric, normalize)
+    n1, n2 = e1.shape[0], e2.shape[0]
+    r = c = None
+    if csls_k > 0:
+        r, c = csls_offsets(e1, e2, d, metric, csls_k)
+    kk = max(1, min(int(cut), n2))
+    if kk <= 32:                      # K3's fused sorted top-k (one warp holds a row's list)
+        res = topk(e1, e2, d, metric, kk, r, c, want=("val", "idx"))
+        idx, val = res["idx"].contiguous(), res["val"].contiguous()
+    else:                             # longer lists: materialise S (or CSLS S'), radix-select the set, order it
+        if kk > 128:
+            raise ValueError("stable_matching: cut > 128 is not supported on the device path")
+        ld = (n2 + 3) // 4 * 4
+        s = torch.empty(n1, ld, dtype=torch.float32, device=e1.device)
+        sim_matrix(e1, e2, d, metric, r, c, out=s)
+        idx = torch.empty(n1, kk, dtype=torch.int32, device=e1.device)
+        val = torch.empty(n1, kk, dtype=torch.float32, device=e1.device)
+        L.check(lib.oea_rows_select_topk(_ptr(s), ld, n1, n2, kk, None, _ptr(idx), _stream_ptr()), "oea_rows_select_topk")
+        L.check(lib.oea_rows_gather_sort(_ptr(s), ld, n1, kk, _ptr(idx), _ptr(val), _stream_ptr()), "oea_rows_gather_sort")
+        del s
+    match = torch.empty(n1, dtype=torch.int32, device=e1.device)
+    ws_bytes = lib.oea_gale_shapley_workspace_bytes(n1, n2)
+    ws = torch.empty(ws_bytes // 8 + 1, dtype=torch.int64, device=e1.device)
+    rounds = C.c_int32(0)
+    L.check(lib.oea_gale_shapley(_ptr(idx), _ptr(val), n1, n2, kk, int(cut), _ptr(match), _ptr(ws), ws.numel() * 8,
+                                 C.byref(rounds), _stream_ptr()), "oea_gale_shapley")
+    return match, int(rounds.value)
+
+
 def find_neighbours_device(embeds, entity_list, k, row_block=8192):
     """ε-truncated neighbour search (batch.py:145-165) on device: for every row of `embeds` the k entities of
     `entity_list` with the largest inner product → int32 CUDA tensor [n, k] of ENTITY IDS (set semantics)."""

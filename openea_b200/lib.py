@@ -142,6 +142,7 @@ SIGNATURES = {
     "oea_tripleset_build": (C.c_int, [_P, _I, _P, C.c_uint32, C.c_uint32, C.c_uint32, _P]),
     "oea_model_score_fed": (C.c_int, [C.POINTER(Model), _P, _P, _P, _I, _P, _P, _P, _I, C.POINTER(LossCfg), C.c_float,
                                       _P, _P]),
+    "oea_rows_gather_sort": (C.c_int, [_P, _L, _I, _I, _P, _P, _P]),
     "oea_gale_shapley_workspace_bytes": (C.c_size_t, [_I, _I]),
     "oea_gale_shapley": (C.c_int, [_P, _P, _I, _I, _I, _I, _P, _P, C.c_size_t, C.POINTER(C.c_int32), _P]),
     "oea_seed_xchg_window_bytes": (C.c_size_t, [_I, _I, _I]),

@@ -39,9 +39,21 @@ def arg_sort(idx, sim_mat, prefix1, prefix2):
 
 
 def stable_alignment(embed1, embed2, metric, normalize, csls_k, nums_threads, cut=100, sim_mat=None):
+    """Stable (Gale–Shapley) alignment, reference signature (alignment.py:87).  Without a precomputed `sim_mat` the whole
+    search runs on the device: K3's top-`cut` lists are the preference lists (only the first `cut` entries of a list can be
+    reached in `cut` proposal rounds) and oea_gale_shapley plays the rounds; `nums_threads` is accepted and ignored.  With a
+    host `sim_mat` the reference's own route (full argsort lists + the Python loop below) is kept."""
     t = time.time()
     if sim_mat is None:
-        sim_mat = sim(embed1, embed2, metric=metric, normalize=normalize, csls_k=csls_k)
+        match, rounds = _f.stable_matching(embed1, embed2, metric, normalize, csls_k, cut)
+        print("generating candidate lists costs time {:.3f} s ".format(time.time() - t))
+        t = time.time()
+        m = match.cpu().numpy()
+        held = m >= 0
+        n = int((m[held] == np.arange(len(m))[held]).sum())
+        cost = time.time() - t
+        print("stable alignment precision = {:.3f}%, time = {:.3f} s ".format(n / max(1, int(held.sum())) * 100, cost))
+        return
     n1, n2 = sim_mat.shape
     kg1_candidates = arg_sort(list(range(n1)), sim_mat, 'x_', 'y_')
     kg2_candidates = arg_sort(list(range(n2)), sim_mat.T, 'y_', 'x_')

@@ -366,3 +366,23 @@ def test_pair_set_behaves_like_the_reference_set():
     assert (1, 0) in ps and (1, 1) not in ps and (9, 0) not in ps and "x" not in ps
     assert ps - {(0, 3)} == real - {(0, 3)} and ps | {(7, 7)} == real | {(7, 7)} and ps & {(2, 0), (5, 5)} == {(2, 0)}
     assert sorted(ps) == sorted(real) and [(i, j) for i, j in ps][0] == (0, 3)
+
+
+def test_galeshapley_port_equals_the_reference_function():
+    """The host restatement of galeshapley against the reference's own function (imported live with TF stubbed) on
+    random preference structures, including max_iteration cut-offs that stop before everybody is matched."""
+    from oracle import ref_adapter
+    if not ref_adapter.available():
+        pytest.skip("reference sources not present")
+    import copy
+    from openea_b200.modules.finding.alignment import arg_sort, galeshapley
+    ref = ref_adapter.load().alignment
+    rng = np.random.default_rng(5)
+    for n1, n2, cut in ((12, 12, 100), (20, 15, 100), (15, 20, 3), (30, 30, 2)):
+        s = rng.standard_normal((n1, n2)).astype(np.float32)
+        a = arg_sort(list(range(n1)), s, "x_", "y_"); b = arg_sort(list(range(n2)), s.T, "y_", "x_")
+        if n1 > n2 and cut >= n2:
+            continue      # more suitors than reviewers and unlimited rounds: the reference runs lists empty (IndexError)
+        want = ref.galeshapley(copy.deepcopy(a), copy.deepcopy(b), cut)
+        got = galeshapley(copy.deepcopy(a), copy.deepcopy(b), cut)
+        assert got == want, (n1, n2, cut)
