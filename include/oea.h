@@ -381,6 +381,12 @@ int oea_sim_rank(const oea_sim_cfg* cfg, const float* e1, const float* e2,
  * approaches/bootea.py:214-219).  Also the first stage of the large-k neighbour search. */
 int oea_sim_matrix(const oea_sim_cfg* cfg, const float* e1, const float* e2,
                    const float* row_off, const float* col_off, float* out, int64_t ld_out, void* stream);
+/* oea_sim_matrix for the inner-product metric on the tensor cores (oea_sim_tc.cu): 3xTF32 tcgen05.mma with fp32 TMEM
+ * accumulators; values agree with oea_sim_matrix to fp32 round-off (not bit for bit: the summation order differs), which
+ * is why it is opt-in (OEA_SIM_TC=1 in openea_b200.finding).  Takes the ROW-major operands (e1_t / e2_t are not read);
+ * ld_out % 4 == 0.  OEA_ERR_KIND for other metrics. */
+int oea_sim_matrix_tc(const oea_sim_cfg* cfg, const float* e1, const float* e2, const float* row_off, const float* col_off,
+                      float* out, int64_t ld_out, void* stream);
 
 /* CSLS on a MATERIALISED similarity matrix (from oea_sim_matrix): used when n1·n2·4 B fits in memory, so the
  * contraction runs once instead of three times (similarity.py:57-83, alignment.py:146-168).

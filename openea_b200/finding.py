@@ -144,6 +144,26 @@ def sim(embed1, embed2, metric="inner", normalize=False, csls_k=0):
 MATERIALIZE_MAX_BYTES = 48 << 30   # CSLS runs on a stored n1×n2 matrix (1 contraction pass) below this size
 
 
+def use_tensor_cores(metric):
+    """OEA_SIM_TC=1 routes the stored similarity matrix of the materialised evaluation through the 3xTF32 tcgen05 kernel
+    (oea_sim_matrix_tc; inner / normalised-cosine only).  Off by default: its values equal the FP32 kernel's only to fp32
+    round-off, so arg-max / rank may differ on exact near-ties (measured: profiles/r02_sim_tc_agreement.json)."""
+    import os
+    return os.environ.get("OEA_SIM_TC") == "1" and _METRICS[metric] == L.METRIC_INNER
+
+
+def sim_matrix_tc(e1, e2, d, metric, row_off=None, col_off=None, out=None):
+    """oea_sim_matrix_tc on prepared device rows → [n1, ld] tensor (ld = n2 rounded up to a multiple of 4)."""
+    lib = L.load()
+    cfg = _cfg(metric, e1, e2, d)
+    n1, n2 = e1.shape[0], e2.shape[0]
+    if out is None:
+        out = torch.empty(n1, (n2 + 3) // 4 * 4, dtype=torch.float32, device=e1.device)
+    L.check(lib.oea_sim_matrix_tc(C.byref(cfg), _ptr(e1), _ptr(e2), _ptr(row_off), _ptr(col_off), _ptr(out), out.stride(0),
+                                  _stream_ptr()), "oea_sim_matrix_tc")
+    return out
+
+
 def _eval_materialized(e1, e2, d, metric, csls_k, gold):
     """CSLS evaluation with ONE contraction pass: S stored once (tile kernel, store epilogue), then three
     HBM-bound streaming kernels (row k-means, column k-means, rank)."""
@@ -153,7 +173,10 @@ def _eval_materialized(e1, e2, d, metric, csls_k, gold):
     s = torch.empty(n1, ld, dtype=torch.float32, device=e1.device)
     cfg = _cfg(metric, e1, e2, d)
     st = _stream_ptr()
-    L.check(lib.oea_sim_matrix(C.byref(cfg), _ptr(e1), _ptr(e2), None, None, _ptr(s), ld, st), "oea_sim_matrix")
+    if use_tensor_cores(metric):
+        L.check(lib.oea_sim_matrix_tc(C.byref(cfg), _ptr(e1), _ptr(e2), None, None, _ptr(s), ld, st), "oea_sim_matrix_tc")
+    else:
+        L.check(lib.oea_sim_matrix(C.byref(cfg), _ptr(e1), _ptr(e2), None, None, _ptr(s), ld, st), "oea_sim_matrix")
     r = torch.empty(n1, dtype=torch.float32, device=e1.device)
     c = torch.empty(n2, dtype=torch.float32, device=e1.device)
     L.check(lib.oea_matrix_topk_mean(_ptr(s), ld, n1, n2, csls_k, 0, _ptr(r), None, 0, st), "oea_matrix_topk_mean")

@@ -121,6 +121,7 @@ SIGNATURES = {
     "oea_sim_rank_workspace_bytes": (C.c_size_t, [C.POINTER(SimCfg)]),
     "oea_sim_rank": (C.c_int, [C.POINTER(SimCfg), _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "oea_sim_matrix": (C.c_int, [C.POINTER(SimCfg), _P, _P, _P, _P, _P, _L, _P]),
+    "oea_sim_matrix_tc": (C.c_int, [C.POINTER(SimCfg), _P, _P, _P, _P, _P, _L, _P]),
     "oea_matrix_topk_mean_workspace_bytes": (C.c_size_t, [_I, _I, _I, _I]),
     "oea_matrix_topk_mean": (C.c_int, [_P, _L, _I, _I, _I, _I, _P, _P, C.c_size_t, _P]),
     "oea_rank_stats": (C.c_int, [_P, _I, _P, _I, _P, _P]),
