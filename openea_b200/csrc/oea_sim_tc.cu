@@ -7,14 +7,14 @@
 // lo = tf32(x − hi); a·b ≈ lo_a·hi_b + hi_a·lo_b + hi_a·hi_b accumulated in fp32 — the dropped lo·lo term is 2⁻²² relative,
 // below fp32 rounding, so values agree with the FFMA kernel to fp32 round-off (summation order differs).
 //
-// One CTA (128 threads) per 128 × 256 output tile, persistent over tiles, two CTAs per SM so that one CTA's loads and
+// One CTA (256 threads) per 128 × 256 output tile, persistent over tiles, two CTAs per SM so that one CTA's loads and
 // epilogue overlap the other's MMAs (each owns 256 of the SM's 512 TMEM columns and 96 KB of shared memory):
 //   load      all threads read a 32-wide K chunk of the tile's 128 E1 rows and 256 E2 rows (128-bit global loads, every
 //             32-B sector fully used), split hi / lo in registers and store both into the canonical K-major no-swizzle UMMA
 //             layout (8-row × 16-B core matrices: byte = (r/8)·1024 + (k/4)·128 + (r%8)·16 + (k%4)·4);
 //   mma       one elected thread issues 4 k-steps × 3 tcgen05.mma (M = 128, N = 256, K = 8) from shared-memory descriptors
 //             and commits them to an mbarrier; the chunk's buffers are reused once that barrier has flipped;
-//   epilogue  warp w reads TMEM lanes 32w … 32w+31 (tcgen05.ld 32x32b.x32: one row, 32 columns per thread), applies the
+//   epilogue  warp w reads TMEM lanes 32(w%4) … +31, column half w/4 (tcgen05.ld 32x32b.x32: one row, 32 columns per thread), applies the
 //             CSLS offsets and writes 128 contiguous bytes per thread and step.
 // Every mbarrier wait is bounded (the kernel traps instead of hanging the device).
 #include "oea_rowmath.cuh"
@@ -22,7 +22,7 @@
 namespace oea {
 
 constexpr int TCM = 128, TCN = 256, TCK = 32;             // tile rows of E1, rows of E2, K chunk (fp32 elements)
-constexpr int TC_THREADS = 128;
+constexpr int TC_THREADS = 256;
 constexpr int TC_A_BYTES = TCM * TCK * 4, TC_B_BYTES = TCN * TCK * 4;
 constexpr int TC_SMEM_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES + 64;   // A hi/lo, B hi/lo, barrier + TMEM pointer
 
@@ -68,20 +68,29 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     __trap();      // the MMAs never completed: fail the launch instead of hanging the device
 }
 
-// hi / lo split of 4 consecutive K values of one row into the UMMA layout of a [rows × 32] chunk
+// hi / lo split of a [ROWS × 32] fp32 chunk into the UMMA layout.  256 threads cover 32 rows × 8 sixteen-byte columns per
+// pass; ALL of a thread's loads are issued before the first conversion (ROWS/32 independent 128-bit loads in flight per
+// thread — the first version issued them one at a time and was bound by L2 latency: 16.9 ms for the 70 000² store).
+template <int ROWS>
 __device__ __forceinline__ void stage_chunk(const float* __restrict__ src_base, int pitch, int n_rows, int row0, int k0, int kdim,
-                                            char* hi, char* lo, int tile_rows, int tid) {
-    // 128 threads cover 16 rows × 8 sixteen-byte chunks per pass: a quarter-warp writes one 128-B core-matrix row group
-    const int r_in = (tid & 7) + 8 * (tid >> 6);
+                                            char* hi, char* lo, int tid) {
+    constexpr int PASSES = ROWS / 32;
+    const int r_in = (tid & 7) + 8 * (tid >> 6);          // quarter-warps write whole 128-B core-matrix row groups
     const int kc = (tid >> 3) & 7;
-    for (int rb = 0; rb < tile_rows; rb += 16) {
-        const int r = rb + r_in;
-        const int k = k0 + 4 * kc;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row0 + r < n_rows && k < kdim) v = __ldg(reinterpret_cast<const float4*>(src_base + (size_t)(row0 + r) * pitch + k));
+    const int k = k0 + 4 * kc;
+    float4 v[PASSES];
+#pragma unroll
+    for (int p = 0; p < PASSES; ++p) {
+        const int r = 32 * p + r_in;
+        v[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row0 + r < n_rows && k < kdim) v[p] = __ldg(reinterpret_cast<const float4*>(src_base + (size_t)(row0 + r) * pitch + k));
+    }
+#pragma unroll
+    for (int p = 0; p < PASSES; ++p) {
+        const int r = 32 * p + r_in;
         float4 h, l;
-        h.x = tf32_round(v.x); h.y = tf32_round(v.y); h.z = tf32_round(v.z); h.w = tf32_round(v.w);
-        l.x = tf32_round(v.x - h.x); l.y = tf32_round(v.y - h.y); l.z = tf32_round(v.z - h.z); l.w = tf32_round(v.w - h.w);
+        h.x = tf32_round(v[p].x); h.y = tf32_round(v[p].y); h.z = tf32_round(v[p].z); h.w = tf32_round(v[p].w);
+        l.x = tf32_round(v[p].x - h.x); l.y = tf32_round(v[p].y - h.y); l.z = tf32_round(v[p].z - h.z); l.w = tf32_round(v[p].w - h.w);
         const int off = (r >> 3) * 1024 + kc * 128 + (r & 7) * 16;
         *reinterpret_cast<float4*>(hi + off) = h;
         *reinterpret_cast<float4*>(lo + off) = l;
@@ -125,8 +134,8 @@ k_sim_store_tc(TcParams P) {
         const int row0 = tm * TCM, col0 = tn * TCN;
         for (int ch = 0; ch < n_chunks; ++ch) {
             if (ch > 0) { mbar_wait(bar_addr, parity); parity ^= 1u; }       // the previous chunk's MMAs have read the buffers
-            stage_chunk(P.e1, P.pitch1, P.n1, row0, ch * TCK, P.kdim, a_hi, a_lo, TCM, tid);
-            stage_chunk(P.e2, P.pitch2, P.n2, col0, ch * TCK, P.kdim, b_hi, b_lo, TCN, tid);
+            stage_chunk<TCM>(P.e1, P.pitch1, P.n1, row0, ch * TCK, P.kdim, a_hi, a_lo, tid);
+            stage_chunk<TCN>(P.e2, P.pitch2, P.n2, col0, ch * TCK, P.kdim, b_hi, b_lo, tid);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores → visible to the MMA's async reads
             __syncthreads();
             if (tid == 0) {
@@ -149,14 +158,15 @@ k_sim_store_tc(TcParams P) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
         // ---- epilogue: TMEM lane = tile row; thread (warp, lane) owns row 32·warp + lane ----
-        const int r = row0 + warp * 32 + lane;
+        const int lane_grp = warp & 3, col_half = warp >> 2;      // a warp may read TMEM lanes 32·(warp % 4) … +31 only
+        const int r = row0 + lane_grp * 32 + lane;
         const bool use_csls = P.row_off != nullptr;
         const float roff = (use_csls && r < P.n1) ? __ldg(P.row_off + r) : 0.f;
         float* orow = P.out + (size_t)r * P.ld_out;
 #pragma unroll 1
-        for (int c0 = 0; c0 < TCN; c0 += 32) {
+        for (int c0 = col_half * (TCN / 2); c0 < (col_half + 1) * (TCN / 2); c0 += 32) {
             uint32_t v[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+            const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)c0;
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
