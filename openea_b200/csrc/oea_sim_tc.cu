@@ -17,6 +17,7 @@
 //   epilogue  warp w reads TMEM lanes 32(w%4) … +31, column half w/4 (tcgen05.ld 32x32b.x32: one row, 32 columns per thread), applies the
 //             CSLS offsets and writes 128 contiguous bytes per thread and step.
 // Every mbarrier wait is bounded (the kernel traps instead of hanging the device).
+#include <stdlib.h>
 #include "oea_rowmath.cuh"
 
 namespace oea {
@@ -207,6 +208,186 @@ k_sim_store_tc(TcParams P) {
 
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" :: "r"(tmem_base) : "memory");
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// v3: the same maths as a warp-specialised, double-buffered pipeline (one CTA of 288 threads per SM):
+//   warps 4-7  producers: global → hi/lo split → shared memory, two 96-KB stages (full / empty mbarriers);
+//   warp 8     MMA issuer: 12 tcgen05.mma per stage, tcgen05.commit releases the stage; two 256-column TMEM accumulators;
+//   warps 0-3  epilogue: TMEM → registers → global, releases the accumulator (tmem_full / tmem_empty mbarriers).
+// Loads of chunk c+1, the MMAs of chunk c and the store of the previous tile overlap inside one SM (v2 — one phase at a time per
+// CTA, two CTAs per SM — kept the tensor pipe 25 % busy, profiles/r02_ncu_sim_store_tc_v2.txt).  The split is done with integer
+// ops (round-to-nearest on the magnitude: hi = (bits + 0x1000) & ~0x1FFF, lo = x − hi exactly; the MMA reads lo's top 11 bits):
+// cvt.rna.tf32 ran on the quarter-rate conversion pipe and was 11 % of v2's stall samples.
+constexpr int V3_THREADS = 288;
+constexpr int V3_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;            // 96 KB
+constexpr int V3_SMEM_BYTES = 2 * V3_STAGE_BYTES + 128;
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void split_store(float4 v, char* hi, char* lo, int off) {
+    float4 h, l;
+    h.x = __uint_as_float((__float_as_uint(v.x) + 0x1000u) & 0xFFFFE000u); h.y = __uint_as_float((__float_as_uint(v.y) + 0x1000u) & 0xFFFFE000u);
+    h.z = __uint_as_float((__float_as_uint(v.z) + 0x1000u) & 0xFFFFE000u); h.w = __uint_as_float((__float_as_uint(v.w) + 0x1000u) & 0xFFFFE000u);
+    l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+    *reinterpret_cast<float4*>(hi + off) = h;
+    *reinterpret_cast<float4*>(lo + off) = l;
+}
+// 128 producer threads cover 16 rows × 8 sixteen-byte columns per pass; 8 loads in flight per thread
+template <int ROWS>
+__device__ __forceinline__ void stage_chunk_v3(const float* __restrict__ src_base, int pitch, int n_rows, int row0, int k0, int kdim,
+                                               char* hi, char* lo, int ptid) {
+    const int r_in = (ptid & 7) + 8 * (ptid >> 6);
+    const int kc = (ptid >> 3) & 7;
+    const int k = k0 + 4 * kc;
+#pragma unroll
+    for (int base = 0; base < ROWS; base += 128) {
+        float4 v[8];
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+            const int r = base + 16 * p + r_in;
+            v[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row0 + r < n_rows && k < kdim) v[p] = __ldg(reinterpret_cast<const float4*>(src_base + (size_t)(row0 + r) * pitch + k));
+        }
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+            const int r = base + 16 * p + r_in;
+            split_store(v[p], hi, lo, (r >> 3) * 1024 + kc * 128 + (r & 7) * 16);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(V3_THREADS, 1)
+k_sim_store_tc3(TcParams P) {
+    extern __shared__ __align__(1024) char smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * V3_STAGE_BYTES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + 2), tfull0 = smem_u32(bars + 4), tempty0 = smem_u32(bars + 6);
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(full0 + 8 * i, 128); mbar_init(empty0 + 8 * i, 1);
+            mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    const int n_chunks = (P.kdim + TCK - 1) / TCK;
+    const long long n_tiles = (long long)P.tiles_m * P.tiles_n;
+
+    if (warp >= 4 && warp < 8) {
+        // ===== producers =====
+        const int ptid = tid - 128;
+        uint32_t stage = 0, phase = 0;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int row0 = (int)(tile / P.tiles_n) * TCM, col0 = (int)(tile % P.tiles_n) * TCN;
+            for (int ch = 0; ch < n_chunks; ++ch) {
+                mbar_wait(empty0 + 8 * stage, phase ^ 1u);                 // the MMAs that read this stage have completed
+                char* st = smem + stage * V3_STAGE_BYTES;
+                stage_chunk_v3<TCM>(P.e1, P.pitch1, P.n1, row0, ch * TCK, P.kdim, st, st + TC_A_BYTES, ptid);
+                stage_chunk_v3<TCN>(P.e2, P.pitch2, P.n2, col0, ch * TCK, P.kdim, st + 2 * TC_A_BYTES, st + 2 * TC_A_BYTES + TC_B_BYTES, ptid);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(full0 + 8 * stage);
+                stage ^= 1u; if (stage == 0u) phase ^= 1u;
+            }
+        }
+    } else if (warp == 8) {
+        // ===== MMA issuer (lane 0 issues; the whole warp walks the barriers) =====
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TCN >> 3) << 17) | ((uint32_t)(TCM >> 4) << 24);
+        uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1u);                  // the epilogue has drained this accumulator
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int ch = 0; ch < n_chunks; ++ch) {
+                mbar_wait(full0 + 8 * stage, phase);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (lane == 0) {
+                    const uint32_t sb = smem_u32(smem + stage * V3_STAGE_BYTES);
+                    const uint32_t ah = sb, al = sb + TC_A_BYTES, bh = sb + 2 * TC_A_BYTES, bl = sb + 2 * TC_A_BYTES + TC_B_BYTES;
+                    const uint32_t d = tmem_base + acc * 256u;
+#pragma unroll
+                    for (int s = 0; s < TCK / 8; ++s) {
+                        const uint32_t o = (uint32_t)s * 256u;
+                        mma_tf32(d, umma_desc(al + o, 128, 1024), umma_desc(bh + o, 128, 1024), idesc, (ch | s) != 0 ? 1u : 0u);
+                        mma_tf32(d, umma_desc(ah + o, 128, 1024), umma_desc(bl + o, 128, 1024), idesc, 1u);
+                        mma_tf32(d, umma_desc(ah + o, 128, 1024), umma_desc(bh + o, 128, 1024), idesc, 1u);
+                    }
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(empty0 + 8 * stage) : "memory");
+                    if (ch == n_chunks - 1)
+                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(tfull0 + 8 * acc) : "memory");
+                }
+                __syncwarp();
+                stage ^= 1u; if (stage == 0u) phase ^= 1u;
+            }
+            acc ^= 1u; if (acc == 0u) acc_phase ^= 1u;
+        }
+    } else {
+        // ===== epilogue (warps 0-3: TMEM lanes 32·warp … +31) =====
+        uint32_t acc = 0, acc_phase = 0;
+        const bool use_csls = P.row_off != nullptr;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int row0 = (int)(tile / P.tiles_n) * TCM, col0 = (int)(tile % P.tiles_n) * TCN;
+            mbar_wait(tfull0 + 8 * acc, acc_phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int r = row0 + warp * 32 + lane;
+            const float roff = (use_csls && r < P.n1) ? __ldg(P.row_off + r) : 0.f;
+            float* orow = P.out + (size_t)r * P.ld_out;
+#pragma unroll 1
+            for (int c0 = 0; c0 < TCN; c0 += 32) {
+                uint32_t v[32];
+                const uint32_t taddr = tmem_base + acc * 256u + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr) : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (r < P.n1) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int c = col0 + c0 + 4 * q;
+                        float4 o4 = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                                                __uint_as_float(v[4 * q + 3]));
+                        if (use_csls) {
+                            const float c0f = c < P.n2 ? __ldg(P.col_off + c) : 0.f, c1f = c + 1 < P.n2 ? __ldg(P.col_off + c + 1) : 0.f;
+                            const float c2f = c + 2 < P.n2 ? __ldg(P.col_off + c + 2) : 0.f, c3f = c + 3 < P.n2 ? __ldg(P.col_off + c + 3) : 0.f;
+                            o4.x = (2.f * o4.x - roff) - c0f; o4.y = (2.f * o4.y - roff) - c1f;
+                            o4.z = (2.f * o4.z - roff) - c2f; o4.w = (2.f * o4.w - roff) - c3f;
+                        }
+                        if (c + 3 < P.ld_out && c < P.n2) {
+                            *reinterpret_cast<float4*>(orow + c) = o4;
+                        } else {
+                            if (c < P.n2) orow[c] = o4.x;
+                            if (c + 1 < P.n2) orow[c + 1] = o4.y;
+                            if (c + 2 < P.n2) orow[c + 2] = o4.z;
+                            if (c + 3 < P.n2) orow[c + 3] = o4.w;
+                        }
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(tempty0 + 8 * acc);
+            acc ^= 1u; if (acc == 0u) acc_phase ^= 1u;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem_base) : "memory");
+}
 #endif  // OEA_HOST_EMU
 
 }  // namespace oea
@@ -230,12 +411,20 @@ extern "C" int oea_sim_matrix_tc(const oea_sim_cfg* c, const float* e1, const fl
     static bool attr_set = false;
     if (!attr_set) {
         OEA_CUDA_TRY(cudaFuncSetAttribute(k_sim_store_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+        OEA_CUDA_TRY(cudaFuncSetAttribute(k_sim_store_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM_BYTES));
         attr_set = true;
     }
     const long long tiles = (long long)P.tiles_m * P.tiles_n;
-    const long long cap = 2ll * sm_count_cached();
-    const int grid = (int)(tiles < cap ? tiles : cap);
-    k_sim_store_tc<<<grid, TC_THREADS, TC_SMEM_BYTES, (cudaStream_t)stream>>>(P);
+    const char* v2 = getenv("OEA_SIM_TC_V2");            // A/B: the one-phase-at-a-time kernel (two CTAs per SM)
+    if (v2 != nullptr && v2[0] == '1') {
+        const long long cap = 2ll * sm_count_cached();
+        const int grid = (int)(tiles < cap ? tiles : cap);
+        k_sim_store_tc<<<grid, TC_THREADS, TC_SMEM_BYTES, (cudaStream_t)stream>>>(P);
+    } else {
+        const long long cap = sm_count_cached();
+        const int grid = (int)(tiles < cap ? tiles : cap);
+        k_sim_store_tc3<<<grid, V3_THREADS, V3_SMEM_BYTES, (cudaStream_t)stream>>>(P);
+    }
     OEA_LAUNCH_CHECK();
     return OEA_OK;
 #else

@@ -8,10 +8,13 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("n1,n2,d", [(128, 256, 32), (1000, 777, 100), (300, 1300, 75), (513, 511, 300), (257, 300, 8), (64, 40, 36)])
+@pytest.mark.parametrize("n1,n2,d", [(128, 256, 32), (1000, 777, 100), (300, 1300, 75), (513, 511, 300), (257, 300, 8), (64, 40, 36), (2000, 3000, 100)])
 @pytest.mark.parametrize("csls", [False, True])
-def test_tc_matrix_equals_fp32_matrix(cuda_device, n1, n2, d, csls):
+@pytest.mark.parametrize("variant", ["v3", "v2"])
+def test_tc_matrix_equals_fp32_matrix(cuda_device, monkeypatch, n1, n2, d, csls, variant):
+    """v3 = warp-specialised double-buffered pipeline (default); v2 = one phase at a time per CTA (OEA_SIM_TC_V2=1)."""
     from openea_b200 import finding as F
+    monkeypatch.setenv("OEA_SIM_TC_V2", "1" if variant == "v2" else "0")
     rng = np.random.default_rng(n1 + d)
     e1, _ = F.to_device_rows(rng.standard_normal((n1, d)).astype(np.float32), False)
     e2, _ = F.to_device_rows(rng.standard_normal((n2, d)).astype(np.float32), False)
