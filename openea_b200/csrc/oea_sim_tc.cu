@@ -211,14 +211,15 @@ k_sim_store_tc(TcParams P) {
 
 // ------------------------------------------------------------------------------------------------------------------
 // v3: the same maths as a warp-specialised, double-buffered pipeline (one CTA of 288 threads per SM):
-//   warps 4-7  producers: global → hi/lo split → shared memory, two 96-KB stages (full / empty mbarriers);
-//   warp 8     MMA issuer: 12 tcgen05.mma per stage, tcgen05.commit releases the stage; two 256-column TMEM accumulators;
+//   warps 4-11 producers: global → hi/lo split → shared memory, two 96-KB stages (full / empty mbarriers);
+//   warp 12    MMA issuer: 12 tcgen05.mma per stage, tcgen05.commit releases the stage; two 256-column TMEM accumulators;
 //   warps 0-3  epilogue: TMEM → registers → global, releases the accumulator (tmem_full / tmem_empty mbarriers).
 // Loads of chunk c+1, the MMAs of chunk c and the store of the previous tile overlap inside one SM (v2 — one phase at a time per
 // CTA, two CTAs per SM — kept the tensor pipe 25 % busy, profiles/r02_ncu_sim_store_tc_v2.txt).  The split is done with integer
 // ops (round-to-nearest on the magnitude: hi = (bits + 0x1000) & ~0x1FFF, lo = x − hi exactly; the MMA reads lo's top 11 bits):
 // cvt.rna.tf32 ran on the quarter-rate conversion pipe and was 11 % of v2's stall samples.
-constexpr int V3_THREADS = 288;
+constexpr int V3_PRODUCER_WARPS = 8;
+constexpr int V3_THREADS = 32 * (4 + V3_PRODUCER_WARPS + 1);     // 4 epilogue warps, 8 producer warps, the MMA warp
 constexpr int V3_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;            // 96 KB
 constexpr int V3_SMEM_BYTES = 2 * V3_STAGE_BYTES + 128;
 
@@ -236,27 +237,27 @@ __device__ __forceinline__ void split_store(float4 v, char* hi, char* lo, int of
     *reinterpret_cast<float4*>(hi + off) = h;
     *reinterpret_cast<float4*>(lo + off) = l;
 }
-// 128 producer threads cover 16 rows × 8 sixteen-byte columns per pass; 8 loads in flight per thread
+// 256 producer threads cover 32 rows × 8 sixteen-byte columns per pass; all of a thread's loads of an operand are in flight
+// together (with 4 producer warps the stage fill took ~6 000 cycles against 1 600 cycles of MMAs per stage: 28 % tensor-pipe
+// activity, profiles/r02_ncu_sim_store_tc3_4producers.txt — the producers' shared-memory stores were the limiter)
 template <int ROWS>
 __device__ __forceinline__ void stage_chunk_v3(const float* __restrict__ src_base, int pitch, int n_rows, int row0, int k0, int kdim,
                                                char* hi, char* lo, int ptid) {
+    constexpr int PASSES = ROWS / 32;
     const int r_in = (ptid & 7) + 8 * (ptid >> 6);
     const int kc = (ptid >> 3) & 7;
     const int k = k0 + 4 * kc;
+    float4 v[PASSES];
 #pragma unroll
-    for (int base = 0; base < ROWS; base += 128) {
-        float4 v[8];
+    for (int p = 0; p < PASSES; ++p) {
+        const int r = 32 * p + r_in;
+        v[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row0 + r < n_rows && k < kdim) v[p] = __ldg(reinterpret_cast<const float4*>(src_base + (size_t)(row0 + r) * pitch + k));
+    }
 #pragma unroll
-        for (int p = 0; p < 8; ++p) {
-            const int r = base + 16 * p + r_in;
-            v[p] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row0 + r < n_rows && k < kdim) v[p] = __ldg(reinterpret_cast<const float4*>(src_base + (size_t)(row0 + r) * pitch + k));
-        }
-#pragma unroll
-        for (int p = 0; p < 8; ++p) {
-            const int r = base + 16 * p + r_in;
-            split_store(v[p], hi, lo, (r >> 3) * 1024 + kc * 128 + (r & 7) * 16);
-        }
+    for (int p = 0; p < PASSES; ++p) {
+        const int r = 32 * p + r_in;
+        split_store(v[p], hi, lo, (r >> 3) * 1024 + kc * 128 + (r & 7) * 16);
     }
 }
 
@@ -269,7 +270,7 @@ k_sim_store_tc3(TcParams P) {
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + 2), tfull0 = smem_u32(bars + 4), tempty0 = smem_u32(bars + 6);
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
-            mbar_init(full0 + 8 * i, 128); mbar_init(empty0 + 8 * i, 1);
+            mbar_init(full0 + 8 * i, 32 * V3_PRODUCER_WARPS); mbar_init(empty0 + 8 * i, 1);
             mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 128);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -285,7 +286,7 @@ k_sim_store_tc3(TcParams P) {
     const int n_chunks = (P.kdim + TCK - 1) / TCK;
     const long long n_tiles = (long long)P.tiles_m * P.tiles_n;
 
-    if (warp >= 4 && warp < 8) {
+    if (warp >= 4 && warp < 4 + V3_PRODUCER_WARPS) {
         // ===== producers =====
         const int ptid = tid - 128;
         uint32_t stage = 0, phase = 0;
@@ -301,7 +302,7 @@ k_sim_store_tc3(TcParams P) {
                 stage ^= 1u; if (stage == 0u) phase ^= 1u;
             }
         }
-    } else if (warp == 8) {
+    } else if (warp == 4 + V3_PRODUCER_WARPS) {
         // ===== MMA issuer (lane 0 issues; the whole warp walks the barriers) =====
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TCN >> 3) << 17) | ((uint32_t)(TCM >> 4) << 24);
         uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
