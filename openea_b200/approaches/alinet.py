@@ -239,17 +239,17 @@ class AliNetModel:
         outs = []
         for i in range(self.n_layers):
             xb = _bn(x, P["gcn%d.bn_gamma" % i], P["gcn%d.bn_beta" % i])
-            one = torch.tanh(self.spmm_fn(self._layer_input(xb @ P["gcn%d.kernel" % i]), self.adj1) + P["gcn%d.bias" % i])
+            one = torch.tanh(self.spmm_fn(self._layer_input(gnn.dense_matmul(xb, P["gcn%d.kernel" % i])), self.adj1) + P["gcn%d.bias" % i])
             if i < self.n_layers - 1:
                 xg = _bn(x, P["gat%d.bn_gamma" % i], P["gat%d.bn_beta" % i])
-                mapped = xg @ P["gat%d.kernel" % i]
-                s1 = torch.tanh(((xg @ P["gat%d.kernel1" % i]) * xg).sum(1))
-                s2 = torch.tanh(((xg @ P["gat%d.kernel2" % i]) * xg).sum(1))
+                mapped = gnn.dense_matmul(xg, P["gat%d.kernel" % i])
+                s1 = torch.tanh((gnn.dense_matmul(xg, P["gat%d.kernel1" % i]) * xg).sum(1))
+                s2 = torch.tanh((gnn.dense_matmul(xg, P["gat%d.kernel2" % i]) * xg).sum(1))
                 two = torch.tanh(self.gat_fn(s1, self._layer_input(s2[:, None])[:, 0], self._layer_input(mapped),
                                              self.adj2, LEAKY_SLOPE))
                 g_in1 = _bn(two, P["hw%d.bn_gamma" % i], P["hw%d.bn_beta" % i])   # one BN object serves both inputs
                 g_in2 = _bn(one, P["hw%d.bn_gamma" % i], P["hw%d.bn_beta" % i])
-                gate = torch.relu(torch.tanh(g_in1 @ P["hw%d.kernel" % i]))
+                gate = torch.relu(torch.tanh(gnn.dense_matmul(g_in1, P["hw%d.kernel" % i])))
                 x = torch.tanh(g_in2 * (1 - gate) + g_in1 * gate)
             else:
                 x = one

@@ -176,7 +176,7 @@ class RDGCNLayer:
         return torch.relu(self.edge_fn(edge_logits, self._all_rows(x), self.r_mat, LEAKY_SLOPE))
 
     def _highway(self, l1, l2, name):
-        gate = torch.sigmoid(l1 @ self.params[name + ".W"] + self.params[name + ".b"])
+        gate = torch.sigmoid(gnn.dense_matmul(l1, self.params[name + ".W"]) + self.params[name + ".b"])
         return gate * l2 + (1.0 - gate) * l1
 
     def forward(self):

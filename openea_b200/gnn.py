@@ -104,6 +104,48 @@ class SpmmFn(torch.autograd.Function):
         return spmm(ctx.A.transpose(), gY.contiguous()), None
 
 
+def tc_gemm_nt(A, B):
+    """C = A·Bᵀ for row-major fp32 A [m, k], B [n, k] (k % 4 == 0) on the tensor cores: the 3xTF32 tcgen05 kernel of path
+    (iii) (oea_sim_matrix_tc) used as a GEMM-NT; values agree with an FP32 GEMM to fp32 round-off.  Returns [m, n]."""
+    lib = L.load()
+    m, k = A.shape
+    n = B.shape[0]
+    assert B.shape[1] == k and k % 4 == 0 and A.is_contiguous() and B.is_contiguous()
+    ld = (n + 3) // 4 * 4
+    out = torch.empty(m, ld, dtype=torch.float32, device=A.device)
+    cfg = L.SimCfg(L.METRIC_INNER, m, n, k, k, k, 0, 0, 0, 0)
+    L.check(lib.oea_sim_matrix_tc(C.byref(cfg), _ptr(A), _ptr(B), None, None, _ptr(out), ld, _stream_ptr()), "oea_sim_matrix_tc")
+    return out if ld == n else out[:, :n]
+
+
+class TcMatmulFn(torch.autograd.Function):
+    """Y = X·W for the dense products of AliNet / RDGCN (alinet.py:574-590 `tf.matmul(inputs, kernel)`) on our tensor-core
+    kernel: forward and dX are GEMM-NTs of the 3xTF32 kernel; dW = Xᵀ·dY has a contraction length of N entities and a tiny
+    output (it would need split-K on that kernel) and stays a library GEMM."""
+
+    @staticmethod
+    def forward(ctx, X, W):
+        ctx.save_for_backward(X, W)
+        return tc_gemm_nt(X.contiguous(), W.t().contiguous())
+
+    @staticmethod
+    def backward(ctx, gY):
+        X, W = ctx.saved_tensors
+        gX = tc_gemm_nt(gY.contiguous(), W.contiguous()) if ctx.needs_input_grad[0] else None
+        gW = X.t() @ gY if ctx.needs_input_grad[1] else None
+        return gX, gW
+
+
+def dense_matmul(X, W):
+    """X·W: the tensor-core kernel for CUDA fp32 operands whose inner and output widths are multiples of 4 (every layer of
+    the shipped configs), a library GEMM otherwise.  OEA_GNN_TC=0 keeps the library GEMM everywhere (A/B, parity checks)."""
+    import os
+    if (X.is_cuda and X.dtype == torch.float32 and W.dtype == torch.float32 and X.dim() == 2 and W.dim() == 2
+            and X.shape[1] % 4 == 0 and W.shape[1] % 4 == 0 and X.shape[0] >= 128 and os.environ.get("OEA_GNN_TC", "1") != "0"):
+        return TcMatmulFn.apply(X, W)
+    return X @ W
+
+
 class GatAggregateFn(torch.autograd.Function):
     """out_i = Σ_j softmax_j(leaky_relu(a_ij·(s1_i + s2_j)))·M_j over the non-zeros of A (alinet.py:656-677)."""
 
