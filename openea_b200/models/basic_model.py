@@ -113,18 +113,29 @@ class BasicModel:
             self._tset = eng.DeviceTripleSet([self._dkg1.triples, self._dkg2.triples], self.kgs.entities_num,
                                              self.kgs.relations_num, dev)       # membership test: ALL triples, every rank
             rank, world = par.world()
-            if world > 1:      # one process per GPU: this rank trains on the triples whose head row it owns (id mod G)
+            if world > 1 and self._multi_mode() == "seed":   # this rank trains on the triples whose head row it owns (id mod G)
                 for dkg in (self._dkg1, self._dkg2):
                     mine = par.shard_triples(dkg.triples.cpu().numpy(), rank, world)
                     dkg.triples = torch.as_tensor(np.ascontiguousarray(mine, dtype=np.int32), device=dev)
         return self._dkg1, self._dkg2, self._tset
 
-    # ---- one process per GPU (the same scheme bench.py times) -----------------------------------------
+    # ---- one process per GPU ----------------------------------------------------------------------
+    def _multi_mode(self):
+        """How path (i) trains under torchrun.  'exact' (default): replicated tables, every step's batch
+        sharded over the ranks, gradients all-reduced, identical updates — the accuracy of one GPU (Hits@1 36.4 = 36.4 at
+        N = 2 and N = 8), no speed-up at these table sizes.  'seed': the north-star's stale-replica scheme that bench.py
+        times (head-owner triple shards, seed-pair rows exchanged once per epoch over NVLink) — fast, but it loses accuracy
+        (Hits@1 36.4 → 19.7 at N = 2, 9.2 at N = 8 on the 15K shape), so it is opt-in: args.multi_gpu_mode or OEA_MULTI_MODE."""
+        mode = getattr(self.args, "multi_gpu_mode", None) or os.environ.get("OEA_MULTI_MODE") or "exact"
+        if mode not in ("exact", "seed"):
+            raise ValueError("multi_gpu_mode must be 'exact' or 'seed', not %r" % (mode,))
+        return mode
+
     def _sync_seed_rows(self):
-        """End of a local epoch: the owners' copies of the seed-pair rows go to every replica (the only data-path
-        collective of path (i)); replicas are otherwise stale."""
+        """'seed' mode, end of a local epoch: the owners' copies of the seed-pair rows go to every replica (the only
+        data-path collective of that mode); replicas are otherwise stale."""
         rank, world = par.world()
-        if world == 1:
+        if world == 1 or self._multi_mode() != "seed":
             return
         if getattr(self, "_seed_sync", None) is None:
             seeds = np.asarray(self.kgs.train_links, dtype=np.int64).reshape(-1)
@@ -280,6 +291,16 @@ class BasicModel:
         use_graph = getattr(self.args, "cuda_graph", True) and getattr(self, "_ran_eager_epoch", False) and \
             hasattr(trainer, "capture_epoch") and getattr(self.ent_embeds, "optimizer", None) != "Adam"
         self._ran_eager_epoch = True
+        exact = None
+        if par.world()[1] > 1 and self._multi_mode() == "exact" and isinstance(trainer, eng.TripleTrainer):
+            # batch sharded over the ranks, gradients all-reduced between scorer and optimiser (two launches + NCCL per step:
+            # not graph-captured).  Trainers without a shardable scorer (the multi-table score family) run the whole batch
+            # on every rank instead: replicas stay equal up to the order of the float reductions, and _sync_replicas
+            # re-unifies them before anything that must agree.
+            exact = getattr(self, "_exact_step", None)
+            if exact is None or exact.trainer is not trainer:
+                exact = self._exact_step = par.ExactReplicaStep(trainer)
+            use_graph = False
         if use_graph:
             key = (triple_steps, trainer._views(kg1, kg2, tset) and trainer._view_key)
             if getattr(self, "_epoch_graph_key", None) != key:      # (re)capture: first use, or new candidate lists
@@ -288,7 +309,9 @@ class BasicModel:
                 self._epoch_graph_key = key
             self._epoch_graph.replay(self._epoch_seed)
         for step in range(triple_steps):
-            if not use_graph:
+            if exact is not None:
+                exact.step(kg1, kg2, tset, self.args.batch_size, self.neg_per_pos, step, self._epoch_seed)
+            elif not use_graph:
                 trainer.step_sampled(kg1, kg2, tset, self.args.batch_size, self.neg_per_pos, step, self._epoch_seed)
             trained_samples_num += self._slice_count(t1, b1, step) + self._slice_count(t2, b2, step)
         epoch_loss = trainer.read_loss() / max(1, trained_samples_num)     # one device→host read per epoch
