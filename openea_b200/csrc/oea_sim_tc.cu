@@ -221,7 +221,9 @@ k_sim_store_tc(TcParams P) {
 constexpr int V3_PRODUCER_WARPS = 8;
 constexpr int V3_THREADS = 32 * (4 + V3_PRODUCER_WARPS + 1);     // 4 epilogue warps, 8 producer warps, the MMA warp
 constexpr int V3_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;            // 96 KB
-constexpr int V3_SMEM_BYTES = 2 * V3_STAGE_BYTES + 128;
+constexpr int V3_EPI_LD = 36;                                            // floats per staged row (32 + 4 pad: conflict-free 128-bit accesses)
+constexpr int V3_EPI_BYTES = 4 * 32 * V3_EPI_LD * 4;                       // one 32 × 32 transpose tile per epilogue warp
+constexpr int V3_SMEM_BYTES = 2 * V3_STAGE_BYTES + 128 + V3_EPI_BYTES;
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count));
@@ -334,15 +336,23 @@ k_sim_store_tc3(TcParams P) {
         }
     } else {
         // ===== epilogue (warps 0-3: TMEM lanes 32·warp … +31) =====
+        // tcgen05.ld hands a thread one ROW's 32 columns; written out directly, a warp store instruction would touch 32 rows
+        // × 16 B (32 half-filled sectors — the 70 000² store ran at 1.6 TB/s that way).  Each warp transposes its 32 × 32 block
+        // through a padded shared-memory tile so that a store instruction covers 4 rows × 128 contiguous bytes.
+        float* tile = reinterpret_cast<float*>(smem + 2 * V3_STAGE_BYTES + 128) + warp * 32 * V3_EPI_LD;
         uint32_t acc = 0, acc_phase = 0;
         const bool use_csls = P.row_off != nullptr;
-        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int row0 = (int)(tile / P.tiles_n) * TCM, col0 = (int)(tile % P.tiles_n) * TCN;
+        const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;            // store mapping: rows sub_r + 4j, columns sub_c … +3
+        for (long long tile_i = blockIdx.x; tile_i < n_tiles; tile_i += gridDim.x) {
+            const int row0 = (int)(tile_i / P.tiles_n) * TCM + warp * 32, col0 = (int)(tile_i % P.tiles_n) * TCN;
             mbar_wait(tfull0 + 8 * acc, acc_phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int r = row0 + warp * 32 + lane;
-            const float roff = (use_csls && r < P.n1) ? __ldg(P.row_off + r) : 0.f;
-            float* orow = P.out + (size_t)r * P.ld_out;
+            float roff[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int r = row0 + sub_r + 4 * j;
+                roff[j] = (use_csls && r < P.n1) ? __ldg(P.row_off + r) : 0.f;
+            }
 #pragma unroll 1
             for (int c0 = 0; c0 < TCN; c0 += 32) {
                 uint32_t v[32];
@@ -357,18 +367,27 @@ k_sim_store_tc3(TcParams P) {
                       "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                     : "r"(taddr) : "memory");
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (r < P.n1) {
+                __syncwarp();                                   // the previous step's reads of the tile are done
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const int c = col0 + c0 + 4 * q;
-                        float4 o4 = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
-                                                __uint_as_float(v[4 * q + 3]));
-                        if (use_csls) {
-                            const float c0f = c < P.n2 ? __ldg(P.col_off + c) : 0.f, c1f = c + 1 < P.n2 ? __ldg(P.col_off + c + 1) : 0.f;
-                            const float c2f = c + 2 < P.n2 ? __ldg(P.col_off + c + 2) : 0.f, c3f = c + 3 < P.n2 ? __ldg(P.col_off + c + 3) : 0.f;
-                            o4.x = (2.f * o4.x - roff) - c0f; o4.y = (2.f * o4.y - roff) - c1f;
-                            o4.z = (2.f * o4.z - roff) - c2f; o4.w = (2.f * o4.w - roff) - c3f;
-                        }
+                for (int q = 0; q < 8; ++q)
+                    *reinterpret_cast<uint4*>(tile + lane * V3_EPI_LD + 4 * q) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                __syncwarp();
+                const int c = col0 + c0 + sub_c;
+                float4 coff = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (use_csls) {
+                    coff.x = c < P.n2 ? __ldg(P.col_off + c) : 0.f; coff.y = c + 1 < P.n2 ? __ldg(P.col_off + c + 1) : 0.f;
+                    coff.z = c + 2 < P.n2 ? __ldg(P.col_off + c + 2) : 0.f; coff.w = c + 3 < P.n2 ? __ldg(P.col_off + c + 3) : 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int rl = sub_r + 4 * j, r = row0 + rl;
+                    float4 o4 = *reinterpret_cast<const float4*>(tile + rl * V3_EPI_LD + sub_c);
+                    if (use_csls) {
+                        o4.x = (2.f * o4.x - roff[j]) - coff.x; o4.y = (2.f * o4.y - roff[j]) - coff.y;
+                        o4.z = (2.f * o4.z - roff[j]) - coff.z; o4.w = (2.f * o4.w - roff[j]) - coff.w;
+                    }
+                    if (r < P.n1) {
+                        float* orow = P.out + (size_t)r * P.ld_out;
                         if (c + 3 < P.ld_out && c < P.n2) {
                             *reinterpret_cast<float4*>(orow + c) = o4;
                         } else {
