@@ -263,6 +263,7 @@ __device__ __forceinline__ void stage_chunk_v3(const float* __restrict__ src_bas
     }
 }
 
+template <bool COALESCED>
 __global__ void __launch_bounds__(V3_THREADS, 1)
 k_sim_store_tc3(TcParams P) {
     extern __shared__ __align__(1024) char smem[];
@@ -335,7 +336,60 @@ k_sim_store_tc3(TcParams P) {
             acc ^= 1u; if (acc == 0u) acc_phase ^= 1u;
         }
     } else {
-        // ===== epilogue (warps 0-3: TMEM lanes 32·warp … +31) =====
+        if constexpr (!COALESCED) {
+        // ===== epilogue (warps 0-3: TMEM lanes 32·warp … +31), direct: the version every hardware run of round 2 used =====
+        uint32_t acc = 0, acc_phase = 0;
+        const bool use_csls = P.row_off != nullptr;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int row0 = (int)(tile / P.tiles_n) * TCM, col0 = (int)(tile % P.tiles_n) * TCN;
+            mbar_wait(tfull0 + 8 * acc, acc_phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int r = row0 + warp * 32 + lane;
+            const float roff = (use_csls && r < P.n1) ? __ldg(P.row_off + r) : 0.f;
+            float* orow = P.out + (size_t)r * P.ld_out;
+#pragma unroll 1
+            for (int c0 = 0; c0 < TCN; c0 += 32) {
+                uint32_t v[32];
+                const uint32_t taddr = tmem_base + acc * 256u + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr) : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (r < P.n1) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int c = col0 + c0 + 4 * q;
+                        float4 o4 = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                                                __uint_as_float(v[4 * q + 3]));
+                        if (use_csls) {
+                            const float c0f = c < P.n2 ? __ldg(P.col_off + c) : 0.f, c1f = c + 1 < P.n2 ? __ldg(P.col_off + c + 1) : 0.f;
+                            const float c2f = c + 2 < P.n2 ? __ldg(P.col_off + c + 2) : 0.f, c3f = c + 3 < P.n2 ? __ldg(P.col_off + c + 3) : 0.f;
+                            o4.x = (2.f * o4.x - roff) - c0f; o4.y = (2.f * o4.y - roff) - c1f;
+                            o4.z = (2.f * o4.z - roff) - c2f; o4.w = (2.f * o4.w - roff) - c3f;
+                        }
+                        if (c + 3 < P.ld_out && c < P.n2) {
+                            *reinterpret_cast<float4*>(orow + c) = o4;
+                        } else {
+                            if (c < P.n2) orow[c] = o4.x;
+                            if (c + 1 < P.n2) orow[c + 1] = o4.y;
+                            if (c + 2 < P.n2) orow[c + 2] = o4.z;
+                            if (c + 3 < P.n2) orow[c + 3] = o4.w;
+                        }
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(tempty0 + 8 * acc);
+            acc ^= 1u; if (acc == 0u) acc_phase ^= 1u;
+        }
+        } else {
+        // ===== epilogue, shared-memory transposed (OEA_SIM_TC_EPI=smem): written after the round's GPU budget was spent, NOT yet run on hardware =====
         // tcgen05.ld hands a thread one ROW's 32 columns; written out directly, a warp store instruction would touch 32 rows
         // × 16 B (32 half-filled sectors — the 70 000² store ran at 1.6 TB/s that way).  Each warp transposes its 32 × 32 block
         // through a padded shared-memory tile so that a store instruction covers 4 rows × 128 contiguous bytes.
@@ -403,6 +457,7 @@ k_sim_store_tc3(TcParams P) {
             mbar_arrive(tempty0 + 8 * acc);
             acc ^= 1u; if (acc == 0u) acc_phase ^= 1u;
         }
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -431,7 +486,8 @@ extern "C" int oea_sim_matrix_tc(const oea_sim_cfg* c, const float* e1, const fl
     static bool attr_set = false;
     if (!attr_set) {
         OEA_CUDA_TRY(cudaFuncSetAttribute(k_sim_store_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-        OEA_CUDA_TRY(cudaFuncSetAttribute(k_sim_store_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM_BYTES));
+        OEA_CUDA_TRY(cudaFuncSetAttribute(k_sim_store_tc3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM_BYTES));
+        OEA_CUDA_TRY(cudaFuncSetAttribute(k_sim_store_tc3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM_BYTES));
         attr_set = true;
     }
     const long long tiles = (long long)P.tiles_m * P.tiles_n;
@@ -443,7 +499,9 @@ extern "C" int oea_sim_matrix_tc(const oea_sim_cfg* c, const float* e1, const fl
     } else {
         const long long cap = sm_count_cached();
         const int grid = (int)(tiles < cap ? tiles : cap);
-        k_sim_store_tc3<<<grid, V3_THREADS, V3_SMEM_BYTES, (cudaStream_t)stream>>>(P);
+        const char* epi = getenv("OEA_SIM_TC_EPI");      // "smem": the transposed epilogue (not yet run on hardware; default = direct)
+        if (epi != nullptr && epi[0] == 's') k_sim_store_tc3<true><<<grid, V3_THREADS, V3_SMEM_BYTES, (cudaStream_t)stream>>>(P);
+        else k_sim_store_tc3<false><<<grid, V3_THREADS, V3_SMEM_BYTES, (cudaStream_t)stream>>>(P);
     }
     OEA_LAUNCH_CHECK();
     return OEA_OK;
