@@ -577,7 +577,10 @@ def bench_triples(args, wl, rank, local_rank, world, device, full):
                                       "torch": "torch ops + all_gather"}[xchg.mode],
                              "mode": xchg.mode, "bytes_per_exchange": xchg.bytes_per_sync, "exchanges_in_timed_region": n_push,
                              "epoch_steps": epoch_steps, "time_to_global_epoch_ms": epoch_steps * total_ms / K,
-                             "status": xchg.status()}
+                             "status": xchg.status(),
+                             "accuracy_note": "this is the north-star's stale-replica scheme: fast, but measured to lose Hits@1 "
+                                              "(15K shape, 100 epochs: 36.4 on one GPU, 19.7 at N=2, 9.2 at N=8); the exact and "
+                                              "delta-sum modes keep it (DESIGN.md section 6, scripts/bench_multi_modes.py)"}
     if not full:
         if xchg is not None:
             xchg.close()
