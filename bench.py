@@ -522,7 +522,7 @@ def bench_triples(args, wl, rank, local_rank, world, device, full):
     loss_val = tr.read_loss()
     value = world * n_pos_step * K / (total_ms * 1e-3)
 
-    # ---- roofline of the dominant kernel: k_step_sampled_oct = the whole step in one launch --------------------
+    # ---- roofline of the dominant kernel: k_step_sampled_duo = the whole step in one launch --------------------
     # 24·d bytes per scored triple (3 row reads + 3 row-gradient writes); frac is computed on THOSE bytes.
     # The row optimiser the same launch runs moves another 24·d per touched row (read g, x, acc; write x, acc, g := 0):
     # reported separately (`optimiser_bytes`), not part of `achieved`.
@@ -542,7 +542,7 @@ def bench_triples(args, wl, rank, local_rank, world, device, full):
     if os.path.exists(tp):
         with open(tp) as f:
             tj = json.load(f)
-        traffic = tj.get("k_step_sampled_oct_dram_bytes_per_launch")
+        traffic = tj.get("k_step_sampled_dram_bytes_per_launch", tj.get("k_step_sampled_oct_dram_bytes_per_launch"))
         score_traffic = tj.get("k_score_sampled_dram_bytes_per_launch")
     # the same steps as two launches (score kernel, optimiser kernel) with an event between them: what the score
     # kernel alone achieves against the same bytes
@@ -557,13 +557,13 @@ def bench_triples(args, wl, rank, local_rank, world, device, full):
     torch.cuda.synchronize()
     score_med_ms = float(np.median([e[3].elapsed_time(e[1]) for e in evs2]))
     split_step_ms = float(np.mean([e[0].elapsed_time(e[2]) for e in evs2]))
-    roofline = {"bound": "hbm", "kernel": "k_step_sampled_oct", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "k_step_sampled_duo", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "peak_kind": pk_kind + " (burst copy)",
                 "algorithmic_bytes_per_launch": score_bytes, "bytes_model": "SURVEY 8(d): 24*d per scored triple",
                 "optimiser_bytes": opt_bytes, "achieved_incl_optimiser": (score_bytes + opt_bytes) / (kern_med_ms * 1e-3) / 1e9,
                 "touched_rows_per_step": n_touched,
                 "kernel_ms_median": kern_med_ms, "kernel_share_of_step": float(kern_ms.sum() / step_ms.sum()),
-                "score_kernel_alone": {"kernel": "k_score_sampled_oct", "ms_median": score_med_ms,
+                "score_kernel_alone": {"kernel": "k_score_sampled_duo", "ms_median": score_med_ms,
                                        "achieved": score_bytes / (score_med_ms * 1e-3) / 1e9,
                                        "frac": score_bytes / (score_med_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
                                        "two_launch_ms_per_step": split_step_ms, "traffic": score_traffic}}
@@ -779,7 +779,7 @@ def main():
                 "warmup": max(3, args.warmup), "ms_per_step": main_blk["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                 "scored_triples_per_s": main_blk["scored_triples_per_s"], "positives_per_step": main_blk["positives_per_step"],
-                "gpu_launches": K, "kernels": ["k_step_sampled_oct (score + grid barrier + row optimiser, one cooperative launch)"],
+                "gpu_launches": K, "kernels": ["k_step_sampled_duo (fused sampler + duo scorer, grid barrier, row optimiser: one cooperative launch)"],
                 "roofline": main_blk["roofline"], "e2e": main_blk["e2e"], "cpu_baseline": cpu_base, "clocks": main_blk["clocks"],
                 "bootea_15k": secondary, "csls": csls, "epoch_graph": main_blk["epoch_graph"],
                 "wall_s_timed_region": main_blk["wall_s_timed_region"], "last_loss_sum": main_blk["last_loss_sum"],
