@@ -337,7 +337,7 @@ k_sim_store_tc3(TcParams P) {
         }
     } else {
         if constexpr (!COALESCED) {
-        // ===== epilogue (warps 0-3: TMEM lanes 32·warp … +31), direct: the version every hardware run of round 2 used =====
+        // ===== epilogue (warps 0-3: TMEM lanes 32·warp … +31), direct row-per-thread stores (OEA_SIM_TC_EPI=direct; 12.2 ms at 70 000²) =====
         uint32_t acc = 0, acc_phase = 0;
         const bool use_csls = P.row_off != nullptr;
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -389,7 +389,7 @@ k_sim_store_tc3(TcParams P) {
             acc ^= 1u; if (acc == 0u) acc_phase ^= 1u;
         }
         } else {
-        // ===== epilogue, shared-memory transposed (OEA_SIM_TC_EPI=smem): written after the round's GPU budget was spent, NOT yet run on hardware =====
+        // ===== epilogue, shared-memory transposed (default; 11.1 ms at 70 000², profiles/r02_sim_tc_v3c_70000.json) =====
         // tcgen05.ld hands a thread one ROW's 32 columns; written out directly, a warp store instruction would touch 32 rows
         // × 16 B (32 half-filled sectors — the 70 000² store ran at 1.6 TB/s that way).  Each warp transposes its 32 × 32 block
         // through a padded shared-memory tile so that a store instruction covers 4 rows × 128 contiguous bytes.
@@ -499,9 +499,9 @@ extern "C" int oea_sim_matrix_tc(const oea_sim_cfg* c, const float* e1, const fl
     } else {
         const long long cap = sm_count_cached();
         const int grid = (int)(tiles < cap ? tiles : cap);
-        const char* epi = getenv("OEA_SIM_TC_EPI");      // "smem": the transposed epilogue (not yet run on hardware; default = direct)
-        if (epi != nullptr && epi[0] == 's') k_sim_store_tc3<true><<<grid, V3_THREADS, V3_SMEM_BYTES, (cudaStream_t)stream>>>(P);
-        else k_sim_store_tc3<false><<<grid, V3_THREADS, V3_SMEM_BYTES, (cudaStream_t)stream>>>(P);
+        const char* epi = getenv("OEA_SIM_TC_EPI");      // "direct": row-per-thread stores (A/B); default = the transposed epilogue
+        if (epi != nullptr && epi[0] == 'd') k_sim_store_tc3<false><<<grid, V3_THREADS, V3_SMEM_BYTES, (cudaStream_t)stream>>>(P);
+        else k_sim_store_tc3<true><<<grid, V3_THREADS, V3_SMEM_BYTES, (cudaStream_t)stream>>>(P);
     }
     OEA_LAUNCH_CHECK();
     return OEA_OK;
