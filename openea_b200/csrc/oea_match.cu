@@ -103,13 +103,9 @@ using namespace oea;
 extern "C" int oea_rows_gather_sort(const float* mat, int64_t ld, int32_t n_rows, int32_t k, int32_t* idx, float* val, void* stream) {
     if (!mat || !idx || !val) return OEA_ERR_NULL;
     if (n_rows < 1 || k < 1 || k > 128 || ld < k) return OEA_ERR_RANGE;
-#ifndef OEA_HOST_EMU
-    k_rows_gather_sort<<<n_rows, 128, 0, (cudaStream_t)stream>>>(mat, (long long)ld, n_rows, k, idx, val);
+    OEA_LAUNCH(k_rows_gather_sort, n_rows, 128, 0, (cudaStream_t)stream, mat, (long long)ld, n_rows, k, idx, val);
     OEA_LAUNCH_CHECK();
     return OEA_OK;
-#else
-    return OEA_ERR_KIND;
-#endif
 }
 
 extern "C" size_t oea_gale_shapley_workspace_bytes(int32_t n1, int32_t n2) {
@@ -131,16 +127,15 @@ extern "C" int oea_gale_shapley(const int32_t* pref_idx, const float* pref_val, 
     int32_t* prop = ptr + n1;
     int32_t* n_prop = prop + n1;
     const int big = n1 > n2 ? n1 : n2;
-#ifndef OEA_HOST_EMU
-    k_gs_init<<<(big + 255) / 256, 256, 0, st>>>(match, ptr, holder, best, n1, n2);
+    OEA_LAUNCH(k_gs_init, (big + 255) / 256, 256, 0, st, match, ptr, holder, best, n1, n2);
     OEA_LAUNCH_CHECK();
     int rounds = 0;
     int32_t h_prop = 0;
     const int grid = (n1 + 255) / 256;
     while (rounds < max_rounds) {
         OEA_CUDA_TRY(cudaMemsetAsync(n_prop, 0, sizeof(int32_t), st));
-        k_gs_propose<<<grid, 256, 0, st>>>(pref_idx, pref_val, n1, cut, match, ptr, prop, best, n_prop);
-        k_gs_resolve<<<grid, 256, 0, st>>>(n1, prop, best, match, ptr, holder);
+        OEA_LAUNCH(k_gs_propose, grid, 256, 0, st, pref_idx, pref_val, n1, cut, match, ptr, prop, best, n_prop);
+        OEA_LAUNCH(k_gs_resolve, grid, 256, 0, st, n1, prop, best, match, ptr, holder);
         OEA_LAUNCH_CHECK();
         ++rounds;
         // the reference stops as soon as no suitor is free; poll every 4th round (one 4-byte read) and at the end
@@ -152,9 +147,5 @@ extern "C" int oea_gale_shapley(const int32_t* pref_idx, const float* pref_val, 
     }
     OEA_CUDA_TRY(cudaStreamSynchronize(st));
     if (rounds_host) *rounds_host = rounds;
-#else
-    (void)st; (void)big; (void)best; (void)holder; (void)ptr; (void)prop; (void)n_prop;
-    return OEA_ERR_KIND;      // not served by the CPU emulator
-#endif
     return OEA_OK;
 }

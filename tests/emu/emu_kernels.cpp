@@ -12,4 +12,5 @@
 #include "../../openea_b200/csrc/oea_triple.cu"
 #include "../../openea_b200/csrc/oea_sim.cu"
 #include "../../openea_b200/csrc/oea_pipeline.cu"
+#include "../../openea_b200/csrc/oea_match.cu"
 
