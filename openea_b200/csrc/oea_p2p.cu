@@ -16,6 +16,10 @@
 // Two parities are enough: a rank publishes epoch e+2 only after it has pulled e+1, which every peer publishes only
 // after having pulled e (stream order on each rank: … pull(e), push(e+1) …), so the slot it overwrites has been read.
 #include <string.h>
+#ifdef OEA_HOST_EMU
+#include <atomic>
+#include <chrono>
+#endif
 #include "oea_rowmath.cuh"
 
 namespace oea {
@@ -40,7 +44,21 @@ struct XchgDev {
     int rank, world, pitch, max_rows, n_own;
 };
 
-#ifndef OEA_HOST_EMU
+#ifdef OEA_HOST_EMU   // tests/emu: "peers" are buffers of the same process; plain atomics stand in for the system-scope PTX
+inline void st_release_sys(unsigned long long* p, unsigned long long v) { std::atomic_ref<unsigned long long>(*p).store(v, std::memory_order_release); }
+inline unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    return std::atomic_ref<unsigned long long>(*const_cast<unsigned long long*>(p)).load(std::memory_order_acquire);
+}
+inline unsigned long long global_ns() {
+    return (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+inline float4 ld_cg4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+inline void __threadfence_system() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+inline void __nanosleep(unsigned) {}
+inline int emu_exchange(int32_t* p, int v) { return std::atomic_ref<int32_t>(*p).exchange(v); }
+#define OEA_ATOMIC_EXCH(P, V) emu_exchange((P), (V))
+#else
+#define OEA_ATOMIC_EXCH(P, V) atomicExch((P), (V))
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -55,6 +73,7 @@ __device__ __forceinline__ unsigned long long global_ns() {
     return t;
 }
 __device__ __forceinline__ float4 ld_cg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+#endif
 
 // own rows → contiguous [n_own, pitch] (the NCCL variant's send buffer)
 __global__ void __launch_bounds__(kThreads)
@@ -133,7 +152,7 @@ k_seed_pull(XchgDev X, float* __restrict__ w, unsigned long long epoch, unsigned
         const unsigned long long t0 = global_ns();
         while (ld_acquire_sys(flag) < epoch) {
             if (global_ns() - t0 > timeout_ns) {     // a peer never published: report, do not hang the device
-                atomicExch(reinterpret_cast<int32_t*>(win + L.status_off), 1);
+                OEA_ATOMIC_EXCH(reinterpret_cast<int32_t*>(win + L.status_off), 1);
                 break;
             }
             __nanosleep(200);
@@ -143,7 +162,6 @@ k_seed_pull(XchgDev X, float* __restrict__ w, unsigned long long epoch, unsigned
     const float* recv = reinterpret_cast<const float*>(win) + (size_t)parity * X.world * X.max_rows * X.pitch;
     unpack_body(w, X.pitch, recv, X.slot_ids, X.world, X.max_rows, X.rank);
 }
-#endif  // OEA_HOST_EMU
 
 static int xchg_dev(const oea_seed_xchg* x, XchgDev* out) {
     if (!x) return OEA_ERR_NULL;
@@ -209,10 +227,8 @@ extern "C" int oea_seed_pack(const float* weight, int32_t pitch, const int32_t* 
     if (n < 0 || pitch <= 0 || (pitch & 3) != 0) return OEA_ERR_DIM;
     if (n == 0) return OEA_OK;
     if (!weight || !ids || !out) return OEA_ERR_NULL;
-#ifndef OEA_HOST_EMU
-    k_seed_pack<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(weight, pitch, ids, n, out);
+    OEA_LAUNCH(k_seed_pack, grid_for(n), kThreads, 0, (cudaStream_t)stream, weight, pitch, ids, n, out);
     OEA_LAUNCH_CHECK();
-#endif
     return OEA_OK;
 }
 
@@ -220,10 +236,8 @@ extern "C" int oea_seed_unpack(float* weight, int32_t pitch, const float* recv, 
                                int32_t max_rows, int32_t rank, void* stream) {
     if (world < 1 || max_rows < 1 || pitch <= 0 || (pitch & 3) != 0) return OEA_ERR_DIM;
     if (!weight || !recv || !slot_ids) return OEA_ERR_NULL;
-#ifndef OEA_HOST_EMU
-    k_seed_unpack<<<grid_for(world * max_rows), kThreads, 0, (cudaStream_t)stream>>>(weight, pitch, recv, slot_ids, world, max_rows, rank);
+    OEA_LAUNCH(k_seed_unpack, grid_for(world * max_rows), kThreads, 0, (cudaStream_t)stream, weight, pitch, recv, slot_ids, world, max_rows, rank);
     OEA_LAUNCH_CHECK();
-#endif
     return OEA_OK;
 }
 
@@ -233,11 +247,9 @@ extern "C" int oea_seed_push(const oea_seed_xchg* x, const float* weight, uint64
     if (!weight) return OEA_ERR_NULL;
     if (epoch == 0) return OEA_ERR_RANGE;
     if (X.world == 1) return OEA_OK;
-#ifndef OEA_HOST_EMU
     const int grid = grid_for(X.n_own > 0 ? X.n_own : 1);
-    k_seed_push<<<grid, kThreads, 0, (cudaStream_t)stream>>>(X, weight, (unsigned long long)epoch);
+    OEA_LAUNCH(k_seed_push, grid, kThreads, 0, (cudaStream_t)stream, X, weight, (unsigned long long)epoch);
     OEA_LAUNCH_CHECK();
-#endif
     return OEA_OK;
 }
 
@@ -247,17 +259,19 @@ extern "C" int oea_seed_pull(const oea_seed_xchg* x, float* weight, uint64_t epo
     if (!weight) return OEA_ERR_NULL;
     if (epoch == 0) return OEA_ERR_RANGE;
     if (X.world == 1) return OEA_OK;
-#ifndef OEA_HOST_EMU
-    k_seed_pull<<<grid_for(X.world * X.max_rows), kThreads, 0, (cudaStream_t)stream>>>(X, weight, (unsigned long long)epoch,
-                                                                                      (unsigned long long)timeout_ns);
+    OEA_LAUNCH(k_seed_pull, grid_for(X.world * X.max_rows), kThreads, 0, (cudaStream_t)stream, X, weight, (unsigned long long)epoch,
+               (unsigned long long)timeout_ns);
     OEA_LAUNCH_CHECK();
-#endif
     return OEA_OK;
 }
 
 extern "C" int oea_seed_xchg_status(const oea_seed_xchg* x, int32_t* status_host) {
     if (!x || !status_host || x->rank < 0 || x->rank >= OEA_P2P_MAX_WORLD || !x->window[x->rank]) return OEA_ERR_NULL;
     const XchgLayout L = xchg_layout(x->world, x->max_rows, x->pitch);
+#ifdef OEA_HOST_EMU
+    memcpy(status_host, (const char*)x->window[x->rank] + L.status_off, sizeof(int32_t));
+#else
     OEA_CUDA_TRY(cudaMemcpy(status_host, (const char*)x->window[x->rank] + L.status_off, sizeof(int32_t), cudaMemcpyDeviceToHost));
+#endif
     return OEA_OK;
 }

@@ -7,7 +7,7 @@ OUT = os.path.join(HERE, "libemu_oea.so")
 SRC = os.path.join(HERE, "emu_kernels.cpp")
 CSRC = os.path.join(os.path.dirname(os.path.dirname(HERE)), "openea_b200", "csrc")
 DEPS = [SRC, os.path.join(HERE, "cuda_host_emu.h")] + [os.path.join(CSRC, f) for f in
-                                                        ("oea_triple_ext.cu", "oea_sampler.cu", "oea_optim_ext.cu", "oea_triple_grouped.cu", "oea_triple_weighted.cu", "oea_spmm.cu", "oea_triple.cu", "oea_sim.cu", "oea_pipeline.cu", "oea_match.cu", "oea_sampler.cuh", "oea_rowmath.cuh", "oea_common.cuh")]
+                                                        ("oea_triple_ext.cu", "oea_sampler.cu", "oea_optim_ext.cu", "oea_triple_grouped.cu", "oea_triple_weighted.cu", "oea_spmm.cu", "oea_triple.cu", "oea_sim.cu", "oea_pipeline.cu", "oea_match.cu", "oea_p2p.cu", "oea_sampler.cuh", "oea_rowmath.cuh", "oea_common.cuh")]
 
 
 def cuda_include():

@@ -13,4 +13,5 @@
 #include "../../openea_b200/csrc/oea_sim.cu"
 #include "../../openea_b200/csrc/oea_pipeline.cu"
 #include "../../openea_b200/csrc/oea_match.cu"
+#include "../../openea_b200/csrc/oea_p2p.cu"
 
