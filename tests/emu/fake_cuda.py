@@ -116,6 +116,16 @@ def install():
                 tr.step_sampled(kg1, kg2, tset, batch, k, step, seed)
     eng.EpochGraph = EagerEpoch
 
+    # one process per "GPU" on the CPU: torch.distributed joins a gloo group whatever backend the caller names, so that the
+    # N > 1 control flow of bench.py (exchange cadence, matched collectives, sharded CSLS) can run under the emulator
+    import torch.distributed as dist
+    real_init = dist.init_process_group
+
+    def init_gloo(backend=None, *a, **k):
+        k.pop("device_id", None)
+        return real_init("gloo", *a, **k)
+    dist.init_process_group = init_gloo
+
 
 def lifecycle(name, folder):
     """set_args / set_kgs / init / run / test / save of one approach on the micro synthetic dataset, two epochs."""
