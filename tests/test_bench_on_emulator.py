@@ -71,7 +71,8 @@ def test_every_model_class_runs_its_lifecycle_on_the_emulator(tmp_path):
     assert not failed, failed
 
 
-def test_bench_two_ranks_issue_matched_collectives_on_the_emulator():
+@pytest.mark.parametrize("world", [2, 8])        # 8 ranks on the micro KG: a global epoch is ONE step (pull and push every step)
+def test_bench_two_ranks_issue_matched_collectives_on_the_emulator(world):
     """bench.py's N > 1 path as two processes on the CPU (gloo instead of NCCL, kernels on the emulator, the exchange in its
     torch transport): the exchange cadence is a global step count, the wall-clock-bounded clock continuation issues no
     collective, so both ranks finish — round 1's N = 8 run deadlocked in exactly this code — and rank 0 prints one line."""
@@ -80,17 +81,20 @@ def test_bench_two_ranks_issue_matched_collectives_on_the_emulator():
         pytest.skip("no CUDA headers for the emulator build")
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     procs = []
-    for rank in range(2):
-        env = dict(os.environ, RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
-        procs.append(subprocess.Popen([sys.executable, RUNNER, "bench", "--workload", "micro", "--gpus", "2", "--steps", "9", "--warmup", "3",
+    for rank in range(world):
+        env = dict(os.environ, RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+                   OMP_NUM_THREADS="1")
+        procs.append(subprocess.Popen([sys.executable, RUNNER, "bench", "--workload", "micro", "--gpus", str(world), "--steps", "9", "--warmup", "3",
                                        "--no-cpu-baseline"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=ROOT, env=env))
     outs = [p.communicate(timeout=600) for p in procs]
     assert all(p.returncode == 0 for p in procs), [o[1][-1500:] for o in outs]
     lines = outs[0][0].strip().splitlines()
     line = json.loads(lines[-1])
-    assert outs[1][0].strip() == "", "only rank 0 prints"
-    assert line["n_gpus"] == 2 and line["steps"] == 9 and line["value"] > 0 and line["scaling"] == "weak"
+    assert all(o[0].strip() == "" for o in outs[1:]), "only rank 0 prints"
+    assert line["n_gpus"] == world and line["steps"] == 9 and line["value"] > 0 and line["scaling"] == "weak"
     coll = line["collective"]
     assert coll["mode"] == "torch" and coll["exchanges_in_timed_region"] >= 1 and coll["epoch_steps"] >= 1 and coll["status"] == 0
+    if world == 8:
+        assert coll["epoch_steps"] == 1 and coll["exchanges_in_timed_region"] == 9
     assert line["csls"]["value"] > 0 and "sharding" in line["csls"]
     assert line["e2e"]["value"] > 0
