@@ -134,7 +134,13 @@ def lifecycle(name, folder):
     from openea_b200.modules.load.kgs import read_kgs_from_folder
     from openea_b200.synth import write_dataset
     data = write_dataset(os.path.join(folder, "micro") + "/", "micro")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:      # one process per "GPU": what run/main_from_args.py does under torchrun (gloo here, see install())
+        import torch.distributed as dist
+        dist.init_process_group("nccl", rank=int(os.environ["RANK"]), world_size=world)
     args = getattr(presets, name.lower())("15K")
+    if os.environ.get("OEA_MULTI_MODE"):
+        args.multi_gpu_mode = os.environ["OEA_MULTI_MODE"]
     args.training_data, args.output = data, os.path.join(folder, "out") + "/"
     args.batch_size, args.max_epoch, args.start_valid, args.eval_freq, args.dim, args.cuda_graph = 64, 2, 1, 1, 16, False
     # sizes that only make sense on real datasets (125 hard negatives, a 2 % candidate list) scaled to 40 entities
@@ -153,7 +159,12 @@ def lifecycle(name, folder):
     model.run()
     model.test()
     model.save()
-    assert os.path.exists(model.out_folder + "ent_embeds.npy")
+    if world == 1 or int(os.environ["RANK"]) == 0:
+        assert os.path.exists(model.out_folder + "ent_embeds.npy")
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
     print("lifecycle ok:", name)
 
 

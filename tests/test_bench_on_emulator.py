@@ -98,3 +98,29 @@ def test_bench_two_ranks_issue_matched_collectives_on_the_emulator(world):
         assert coll["epoch_steps"] == 1 and coll["exchanges_in_timed_region"] == 9
     assert line["csls"]["value"] > 0 and "sharding" in line["csls"]
     assert line["e2e"]["value"] > 0
+
+
+@pytest.mark.parametrize("mode", ["exact", "seed"])
+def test_bootea_lifecycle_as_two_ranks_on_the_emulator(tmp_path, mode):
+    """The reference lifecycle of BootEA as two gloo ranks on the CPU (kernels on the emulator) in both multi-GPU modes of
+    DESIGN.md §6: 'exact' (batch sharded, gradients all-reduced) and 'seed' (head-owner shards + seed-row exchange) — replica
+    sync before validation / bootstrapping / test, sharded evaluation, rank 0 writes the results; every rank prints the same
+    accurate-results line."""
+    import re
+    import socket
+    if build_emu.build() is None:
+        pytest.skip("no CUDA headers for the emulator build")
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    procs = []
+    for rank in range(2):
+        folder = str(tmp_path / ("r%d" % rank))
+        os.makedirs(folder)
+        env = dict(os.environ, RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+                   OEA_MULTI_MODE=mode, OMP_NUM_THREADS="1")
+        procs.append(subprocess.Popen([sys.executable, RUNNER, "lifecycle", "BootEA", folder], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                                      text=True, cwd=ROOT, env=env))
+    outs = [p.communicate(timeout=900) for p in procs]
+    assert all(p.returncode == 0 for p in procs), [o[1][-1500:] for o in outs]
+    lines = [re.findall(r"accurate results: hits@.*?mrr = [0-9.]+", o[0]) for o in outs]
+    assert lines[0] and lines[0][-1] == lines[1][-1], (lines[0][-1:], lines[1][-1:])
+    assert all("lifecycle ok: BootEA" in o[0] for o in outs)
